@@ -1,0 +1,70 @@
+"""Build recipe of libagofrt.so (nvcc, sm_100a only).  In-tree output: analisi_b200/libagofrt.so.
+
+    python -m analisi_b200.build [--force]
+
+nvcc cross-compiles without a GPU.  The flags matter for parity: no fast-math, no FMA contraction
+on the host side (the threshold table is computed with the reference's own expression), -lineinfo
+so ncu's source page maps to the .cu files.
+"""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "libagofrt.so")
+SOURCES = ["agofrt_kernels.cu", "agofrt_cabi.cu"]
+HEADERS = [os.path.join(CSRC, "agofrt_kernels.cuh"), os.path.join(ROOT, "include", "agofrt.h")]
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-O3", "-std=c++17", "-lineinfo",
+    "-Xcompiler", "-fPIC,-fvisibility=hidden,-ffp-contract=off,-fno-fast-math",
+    "-Xptxas", "-v",
+]
+
+
+def nvcc():
+    for cand in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", "nvcc"):
+        if cand and (os.path.isabs(cand) and os.path.exists(cand) or not os.path.isabs(cand)):
+            return cand
+    raise RuntimeError("nvcc not found")
+
+
+def stale():
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    deps = [os.path.join(CSRC, s) for s in SOURCES] + HEADERS + [os.path.abspath(__file__)]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force=False, verbose=False):
+    """Compile libagofrt.so if it is missing or older than its sources; return its path."""
+    if not force and not stale():
+        return LIB
+    objs = []
+    log = []
+    for s in SOURCES:
+        o = os.path.join(CSRC, s.replace(".cu", ".o"))
+        cmd = [nvcc()] + NVCC_FLAGS + ["-I", os.path.join(ROOT, "include"), "-I", CSRC, "-c",
+                                       os.path.join(CSRC, s), "-o", o]
+        r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        log.append(r.stdout)
+        if r.returncode != 0:
+            raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + r.stdout)
+        objs.append(o)
+    cmd = [nvcc(), "-shared", "-o", LIB] + objs + ["-ldl"]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("link failed:\n" + r.stdout)
+    with open(os.path.join(CSRC, "ptxas.log"), "w") as f:
+        f.write("\n".join(log))
+    if verbose:
+        print("\n".join(log))
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

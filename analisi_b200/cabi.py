@@ -1,0 +1,297 @@
+"""ctypes binding of the C ABI in ``include/agofrt.h`` (tests and ``bench.py`` go through this).
+
+Nothing here computes: every call lands in ``libagofrt.so``.  Loading fails loudly when the library
+is missing, and every compute call fails with ``AgofrtError`` when no B200 is usable -- there is no
+CPU path.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libagofrt.so")
+
+OK = 0
+ERR_ARG, ERR_CUDA, ERR_WINDOW, ERR_NCCL, ERR_NONFINITE, ERR_TOO_LARGE, ERR_INTERNAL = -1, -2, -3, -4, -5, -6, -7
+OPT_EDGES, OPT_FORCE_GENERAL, OPT_NO_AGGREGATE, OPT_AGGREGATE = 1, 2, 4, 8
+COMM_ID_BYTES = 128
+
+# every symbol include/agofrt.h declares (tests check the library exports all of them)
+SYMBOLS = [
+    "agofrt_version", "agofrt_last_error", "agofrt_device_count", "agofrt_host_alloc", "agofrt_host_free",
+    "agofrt_ctx_create", "agofrt_ctx_destroy", "agofrt_ctx_ndev", "agofrt_comm_unique_id", "agofrt_comm_join",
+    "agofrt_ctx_set_shard", "agofrt_shard_range", "agofrt_traj_create", "agofrt_traj_destroy", "agofrt_traj_upload",
+    "agofrt_traj_download_frame", "agofrt_pbc_wrap", "agofrt_traj_d2_all", "agofrt_plan_create",
+    "agofrt_plan_destroy", "agofrt_plan_thresholds", "agofrt_block", "agofrt_fp64_peak",
+]
+
+
+class AgofrtError(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__("agofrt error %d: %s" % (code, message))
+        self.code = code
+
+
+class Stats(C.Structure):
+    _fields_ = [
+        ("kernel_ms", C.c_double),
+        ("total_ms", C.c_double),
+        ("pair_evals", C.c_uint64),
+        ("pair_evals_total", C.c_uint64),
+        ("jobs", C.c_uint64),
+        ("jobs_fast", C.c_uint64),
+        ("launches", C.c_uint32),
+        ("ndev_local", C.c_uint32),
+        ("world", C.c_uint32),
+        ("reserved", C.c_uint32),
+    ]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
+
+
+_lib = None
+
+
+def lib():
+    """Load libagofrt.so (built in-tree by ``analisi_b200.build``).  No fallback."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            "%s is missing: build it with `python -m analisi_b200.build` (nvcc, sm_100a). "
+            "analisi_b200 has no CPU or PyTorch fallback." % LIB_PATH)
+    L = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+    vp, dp, ip = C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int)
+    u64p = C.POINTER(C.c_uint64)
+    L.agofrt_version.restype = C.c_char_p
+    L.agofrt_last_error.restype = C.c_char_p
+    L.agofrt_device_count.argtypes = [ip]
+    L.agofrt_host_alloc.argtypes = [C.POINTER(vp), C.c_size_t]
+    L.agofrt_host_free.argtypes = [vp]
+    L.agofrt_ctx_create.argtypes = [C.POINTER(vp), ip, C.c_int]
+    L.agofrt_ctx_destroy.argtypes = [vp]
+    L.agofrt_ctx_ndev.argtypes = [vp]
+    L.agofrt_comm_unique_id.argtypes = [C.c_char_p]
+    L.agofrt_comm_join.argtypes = [vp, C.c_char_p, C.c_int, C.c_int]
+    L.agofrt_ctx_set_shard.argtypes = [vp, C.c_int, C.c_int]
+    L.agofrt_shard_range.argtypes = [C.c_uint64, C.c_int, C.c_int, u64p, u64p]
+    L.agofrt_traj_create.argtypes = [C.POINTER(vp), vp, C.c_size_t, C.c_int, ip, C.c_int, C.c_size_t]
+    L.agofrt_traj_destroy.argtypes = [vp]
+    L.agofrt_traj_upload.argtypes = [vp, C.c_size_t, C.c_size_t, vp, vp]
+    L.agofrt_traj_download_frame.argtypes = [vp, C.c_size_t, dp]
+    L.agofrt_pbc_wrap.argtypes = [vp, vp, C.c_size_t, C.c_size_t, dp, C.c_int]
+    L.agofrt_traj_d2_all.argtypes = [vp, C.c_size_t, C.c_size_t, dp]
+    L.agofrt_plan_create.argtypes = [C.POINTER(vp), vp, C.c_double, C.c_double, C.c_uint]
+    L.agofrt_plan_destroy.argtypes = [vp]
+    L.agofrt_plan_thresholds.argtypes = [vp, dp]
+    L.agofrt_block.argtypes = [vp, C.c_size_t, C.c_uint, C.c_uint, C.c_uint, C.c_uint, C.c_uint, u64p, u64p,
+                               C.POINTER(Stats)]
+    L.agofrt_fp64_peak.argtypes = [vp, C.c_int, C.c_double, dp]
+    for name in SYMBOLS:
+        fn = getattr(L, name)
+        if name not in ("agofrt_version", "agofrt_last_error"):
+            fn.restype = C.c_int
+    _lib = L
+    return L
+
+
+def _check(rc):
+    if rc != OK:
+        raise AgofrtError(rc, lib().agofrt_last_error().decode("utf-8", "replace"))
+
+
+def device_count():
+    n = C.c_int(0)
+    rc = lib().agofrt_device_count(C.byref(n))
+    return n.value if rc == OK else 0
+
+
+def shard_range(units, rank, world):
+    b, e = C.c_uint64(0), C.c_uint64(0)
+    _check(lib().agofrt_shard_range(int(units), int(rank), int(world), C.byref(b), C.byref(e)))
+    return int(b.value), int(e.value)
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+class PinnedArray:
+    """A float64 numpy array in page-locked host memory (agofrt_host_alloc)."""
+
+    def __init__(self, shape):
+        n = int(np.prod(shape))
+        self._ptr = C.c_void_p()
+        _check(lib().agofrt_host_alloc(C.byref(self._ptr), n * 8))
+        buf = (C.c_double * n).from_address(self._ptr.value)
+        self.array = np.frombuffer(buf, dtype=np.float64, count=n).reshape(shape)
+
+    def free(self):
+        if self._ptr:
+            self.array = None
+            lib().agofrt_host_free(self._ptr)
+            self._ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Context:
+    def __init__(self, devices=None):
+        self._h = C.c_void_p()
+        if devices is None:
+            rc = lib().agofrt_ctx_create(C.byref(self._h), None, 0)
+        elif devices == "all":
+            rc = lib().agofrt_ctx_create(C.byref(self._h), None, -1)
+        else:
+            arr = (C.c_int * len(devices))(*devices)
+            rc = lib().agofrt_ctx_create(C.byref(self._h), arr, len(devices))
+        _check(rc)
+
+    @property
+    def ndev(self):
+        return lib().agofrt_ctx_ndev(self._h)
+
+    @staticmethod
+    def unique_id():
+        buf = C.create_string_buffer(COMM_ID_BYTES)
+        _check(lib().agofrt_comm_unique_id(buf))
+        return buf.raw
+
+    def join(self, comm_id, first_rank, world):
+        assert len(comm_id) == COMM_ID_BYTES
+        _check(lib().agofrt_comm_join(self._h, comm_id, first_rank, world))
+
+    def set_shard(self, first_rank, world):
+        _check(lib().agofrt_ctx_set_shard(self._h, first_rank, world))
+
+    def pbc_wrap(self, pos, box_internal):
+        """In-place BaseTrajectory::pbc_wrap of pos[F,N,3] (float64, C-contiguous)."""
+        assert pos.dtype == np.float64 and pos.flags.c_contiguous and pos.ndim == 3
+        box = np.ascontiguousarray(box_internal, dtype=np.float64)
+        assert box.shape[0] == pos.shape[0] and box.shape[1] in (6, 9)
+        _check(lib().agofrt_pbc_wrap(self._h, pos.ctypes.data, pos.shape[0], pos.shape[1], _dp(box), box.shape[1]))
+        return pos
+
+    def fp64_peak(self, seconds=0.5, local_device=0):
+        out = C.c_double(0)
+        _check(lib().agofrt_fp64_peak(self._h, local_device, seconds, C.byref(out)))
+        return out.value
+
+    def close(self):
+        if self._h:
+            lib().agofrt_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class DeviceTrajectory:
+    """Device-resident window: positions [frame][atom][3], internal box rows, dense type ids."""
+
+    def __init__(self, ctx, natoms, box_stride, type_id, ntypes, max_frames):
+        self.ctx = ctx
+        self.natoms, self.box_stride, self.ntypes = int(natoms), int(box_stride), int(ntypes)
+        tid = np.ascontiguousarray(type_id, dtype=np.int32)
+        assert tid.shape == (self.natoms,)
+        self._h = C.c_void_p()
+        _check(lib().agofrt_traj_create(C.byref(self._h), ctx._h, self.natoms, self.box_stride,
+                                        tid.ctypes.data_as(C.POINTER(C.c_int)), self.ntypes, int(max_frames)))
+
+    def upload(self, first_frame, pos, box_internal):
+        assert pos.dtype == np.float64 and pos.flags.c_contiguous
+        assert pos.ndim == 3 and pos.shape[1] == self.natoms and pos.shape[2] == 3
+        box = np.ascontiguousarray(box_internal, dtype=np.float64)
+        assert box.shape == (pos.shape[0], self.box_stride)
+        _check(lib().agofrt_traj_upload(self._h, int(first_frame), pos.shape[0], pos.ctypes.data, box.ctypes.data))
+
+    def download_frame(self, frame):
+        out = np.empty((self.natoms, 3), dtype=np.float64)
+        _check(lib().agofrt_traj_download_frame(self._h, int(frame), _dp(out)))
+        return out
+
+    def d2_all(self, frame_i, frame_j):
+        out = np.zeros((self.natoms, self.natoms, 4), dtype=np.float64)
+        _check(lib().agofrt_traj_d2_all(self._h, int(frame_i), int(frame_j), _dp(out)))
+        return out
+
+    def close(self):
+        if self._h:
+            lib().agofrt_traj_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Plan:
+    def __init__(self, traj, rmin, rmax, nbin):
+        self.traj = traj
+        self.nbin = int(nbin)
+        self._h = C.c_void_p()
+        _check(lib().agofrt_plan_create(C.byref(self._h), traj._h, float(rmin), float(rmax), self.nbin))
+
+    def thresholds(self):
+        out = np.empty(self.nbin + 1, dtype=np.float64)
+        _check(lib().agofrt_plan_thresholds(self._h, _dp(out)))
+        return out
+
+    def block(self, primo, ntimesteps, leff, skip=1, every=1, options=0, edges=False):
+        """Integer counts [leff][ntypes*(ntypes+1)][nbin] of one calculate(primo) after reset(ntimesteps).
+
+        Returns (counts, stats dict[, edge_pairs])."""
+        nt = self.traj.ntypes
+        counts = np.zeros((int(leff), nt * (nt + 1), self.nbin), dtype=np.uint64)
+        st = Stats()
+        e = C.c_uint64(0)
+        rc = lib().agofrt_block(self._h, int(primo), int(ntimesteps), int(leff), int(skip), int(every),
+                                int(options) | (OPT_EDGES if edges else 0),
+                                counts.ctypes.data_as(C.POINTER(C.c_uint64)),
+                                C.byref(e) if edges else None, C.byref(st))
+        _check(rc)
+        if edges:
+            return counts, st.as_dict(), int(e.value)
+        return counts, st.as_dict()
+
+    def close(self):
+        if self._h:
+            lib().agofrt_plan_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+# ---- the host-side arithmetic of Gofrt that is not pair work (mirrors lib/src/gofrt.cpp) -------
+def gofrt_leff(ntimesteps, lmax):
+    """Gofrt::reset, reference lib/src/gofrt.cpp:55."""
+    return ntimesteps if (ntimesteps < lmax or lmax == 0) else lmax
+
+
+def gofrt_incr(ntimesteps, skip):
+    """Gofrt::calc_init, reference lib/src/gofrt.cpp:91-92."""
+    skip = skip or 1
+    q = ntimesteps // skip
+    return 1.0 / int(q) if q > 0 else 1.0
+
+
+def gofrt_nextra(total_frames, n_b, lmax):
+    """Gofrt::nExtraTimesteps, reference lib/src/gofrt.cpp:37-39."""
+    a = total_frames // (n_b + 1) + 1
+    return a if (a < lmax or lmax == 0) else lmax

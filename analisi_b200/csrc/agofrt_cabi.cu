@@ -1,0 +1,1092 @@
+// agofrt_cabi.cu -- host side of libagofrt.so: the C ABI declared in include/agofrt.h.
+//
+// No CPU compute path lives here: the only arithmetic done on the host is O(nbin) / O(frames)
+// planning (the exact bin-threshold table, the per-job single-pass proof from coordinate bounds,
+// the atom permutation).  Every pair evaluation happens in agofrt_kernels.cu.
+#include "agofrt.h"
+#include "agofrt_kernels.cuh"
+
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <memory>
+#include <numeric>
+#include <string>
+#include <vector>
+
+using namespace agofrt;
+
+// ---------------------------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------------------------
+static thread_local std::string g_last_error;
+
+static int fail(int code, const char *fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return code;
+}
+
+#define CU(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e__ = (call);                                                                        \
+        if (e__ != cudaSuccess)                                                                          \
+            return fail(AGOFRT_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, \
+                        __LINE__);                                                                       \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// NCCL, bound at run time (dlopen) so that whichever libnccl.so.2 the process already carries --
+// the system one, or the one a python launcher has loaded -- is the one used.
+// ---------------------------------------------------------------------------------------------
+struct NcclApi {
+    void *handle = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t,
+                              cudaStream_t) = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+    bool ok = false;
+};
+
+static NcclApi &nccl_api() {
+    static NcclApi api;
+    static bool tried = false;
+    if (tried) return api;
+    tried = true;
+    const char *names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char *n : names) {
+        api.handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (api.handle) break;
+    }
+    if (!api.handle) return api;
+#define LOAD(field, sym)                                                             \
+    api.field = reinterpret_cast<decltype(api.field)>(dlsym(api.handle, sym));       \
+    if (!api.field) return api;
+    LOAD(GetUniqueId, "ncclGetUniqueId")
+    LOAD(CommInitRank, "ncclCommInitRank")
+    LOAD(CommDestroy, "ncclCommDestroy")
+    LOAD(GroupStart, "ncclGroupStart")
+    LOAD(GroupEnd, "ncclGroupEnd")
+    LOAD(AllReduce, "ncclAllReduce")
+    LOAD(GetErrorString, "ncclGetErrorString")
+#undef LOAD
+    api.ok = true;
+    return api;
+}
+
+#define NC(call)                                                                                            \
+    do {                                                                                                    \
+        ncclResult_t r__ = (call);                                                                          \
+        if (r__ != ncclSuccess)                                                                             \
+            return fail(AGOFRT_ERR_NCCL, "%s failed: %s (%s:%d)", #call, nccl_api().GetErrorString(r__),     \
+                        __FILE__, __LINE__);                                                                \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// objects
+// ---------------------------------------------------------------------------------------------
+struct Dev {
+    int id = 0;
+    int sm_count = 0;
+    size_t smem_optin = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_begin = nullptr, ev_end = nullptr, ev_k0 = nullptr, ev_k1 = nullptr;
+    ncclComm_t comm = nullptr;
+    double *peak_sink = nullptr;
+};
+
+struct agofrt_ctx {
+    std::vector<Dev> devs;
+    int first_rank = 0;
+    int world = 0;       // 0: not sharded beyond the local devices
+    bool comm_ready = false;
+    bool shard_only = false;
+};
+
+struct TrajDev {
+    double *pos = nullptr;       // [max_frames][3][npad]
+    double *box6 = nullptr;      // [max_frames][6]
+    double *bounds = nullptr;    // [max_frames][6]
+    double *stage = nullptr;     // AoS staging
+    double *box_stage = nullptr; // [max_frames][stride]
+    int *perm = nullptr;         // [npad]
+    int *type_pad = nullptr;     // [npad]
+    int *type_start = nullptr;   // [ntypes+1]
+    unsigned int *flags = nullptr;  // [4]: 0 = inf seen, 1 = wrap cap hit
+};
+
+struct agofrt_traj {
+    agofrt_ctx *ctx = nullptr;
+    size_t natoms = 0, max_frames = 0;
+    int npad = 0, ntypes = 0, stride = 6;
+    std::vector<int> type_id, type_start, type_pad, perm;
+    std::vector<TrajDev> dev;
+    size_t stage_frames = 0;
+    // current window
+    size_t first_frame = 0, nframes = 0;
+    std::vector<double> box6;    // host copy [nframes][6]
+    std::vector<double> bounds;  // host copy [nframes][6]
+    bool has_inf = false;
+    bool bad_box = false;
+};
+
+struct PlanDev {
+    double *thr = nullptr, *thr_full = nullptr;
+    unsigned long long *ghist = nullptr;
+    size_t ghist_len = 0;
+    Job *jobs = nullptr;
+    size_t jobs_cap = 0;
+    unsigned int *counter = nullptr;      // [1]
+    unsigned long long *edges = nullptr;  // [1]
+};
+
+struct agofrt_plan {
+    agofrt_traj *traj = nullptr;
+    double rmin = 0, rmax = 0, dr = 0, rmin2 = 0, rmax2 = 0;
+    unsigned nbin = 0;
+    std::vector<double> thr_full, thr;
+    bool empty_range = false;
+    unsigned hlo = 0, hspan = 0;
+    float inv_dr = 0, c0 = 0;
+    std::vector<PlanDev> dev;
+    unsigned long long *host_counts = nullptr;  // pinned
+    size_t host_counts_len = 0;
+    unsigned long long *host_edges = nullptr;   // pinned [ndev]
+    unsigned int *host_flags = nullptr;         // pinned [ndev]
+};
+
+// ---------------------------------------------------------------------------------------------
+// library
+// ---------------------------------------------------------------------------------------------
+extern "C" const char *agofrt_version(void) { return "agofrt 0.1 (sm_100a)"; }
+extern "C" const char *agofrt_last_error(void) { return g_last_error.c_str(); }
+
+extern "C" int agofrt_device_count(int *count) {
+    if (!count) return fail(AGOFRT_ERR_ARG, "count is NULL");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        *count = 0;
+        return fail(AGOFRT_ERR_CUDA, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+    }
+    *count = n;
+    return AGOFRT_OK;
+}
+
+extern "C" int agofrt_host_alloc(void **ptr, size_t bytes) {
+    if (!ptr) return fail(AGOFRT_ERR_ARG, "ptr is NULL");
+    CU(cudaHostAlloc(ptr, bytes ? bytes : 1, cudaHostAllocPortable));
+    return AGOFRT_OK;
+}
+extern "C" int agofrt_host_free(void *ptr) {
+    if (ptr) CU(cudaFreeHost(ptr));
+    return AGOFRT_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------------------------
+extern "C" int agofrt_ctx_create(agofrt_ctx **out, const int *devices, int ndev) {
+    if (!out) return fail(AGOFRT_ERR_ARG, "ctx is NULL");
+    *out = nullptr;
+    int avail = 0;
+    cudaError_t e = cudaGetDeviceCount(&avail);
+    if (e != cudaSuccess || avail <= 0)
+        return fail(AGOFRT_ERR_CUDA, "no usable CUDA device (%s); libagofrt has no CPU path",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "0 devices");
+    std::vector<int> ids;
+    if (ndev == -1) {
+        for (int i = 0; i < avail; ++i) ids.push_back(i);
+    } else if (ndev == 0 || devices == nullptr) {
+        ids.push_back(0);
+    } else {
+        for (int i = 0; i < ndev; ++i) {
+            if (devices[i] < 0 || devices[i] >= avail)
+                return fail(AGOFRT_ERR_ARG, "device %d not in [0,%d)", devices[i], avail);
+            ids.push_back(devices[i]);
+        }
+    }
+    auto ctx = std::make_unique<agofrt_ctx>();
+    for (int id : ids) {
+        Dev d;
+        d.id = id;
+        CU(cudaSetDevice(id));
+        cudaDeviceProp prop;
+        CU(cudaGetDeviceProperties(&prop, id));
+        if (prop.major < 10)
+            return fail(AGOFRT_ERR_CUDA, "device %d is sm_%d%d; libagofrt is built for sm_100a only", id, prop.major,
+                        prop.minor);
+        d.sm_count = prop.multiProcessorCount;
+        d.smem_optin = prop.sharedMemPerBlockOptin;
+        CU(cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking));
+        CU(cudaEventCreate(&d.ev_begin));
+        CU(cudaEventCreate(&d.ev_end));
+        CU(cudaEventCreate(&d.ev_k0));
+        CU(cudaEventCreate(&d.ev_k1));
+        CU(prepare_pair_kernels(d.smem_optin));
+        ctx->devs.push_back(d);
+    }
+    *out = ctx.release();
+    return AGOFRT_OK;
+}
+
+extern "C" int agofrt_ctx_destroy(agofrt_ctx *ctx) {
+    if (!ctx) return AGOFRT_OK;
+    for (Dev &d : ctx->devs) {
+        cudaSetDevice(d.id);
+        if (d.comm && nccl_api().ok) nccl_api().CommDestroy(d.comm);
+        if (d.peak_sink) cudaFree(d.peak_sink);
+        if (d.stream) cudaStreamDestroy(d.stream);
+        if (d.ev_begin) cudaEventDestroy(d.ev_begin);
+        if (d.ev_end) cudaEventDestroy(d.ev_end);
+        if (d.ev_k0) cudaEventDestroy(d.ev_k0);
+        if (d.ev_k1) cudaEventDestroy(d.ev_k1);
+    }
+    delete ctx;
+    return AGOFRT_OK;
+}
+
+extern "C" int agofrt_ctx_ndev(const agofrt_ctx *ctx) { return ctx ? static_cast<int>(ctx->devs.size()) : 0; }
+
+extern "C" int agofrt_comm_unique_id(char id[AGOFRT_COMM_ID_BYTES]) {
+    static_assert(AGOFRT_COMM_ID_BYTES == NCCL_UNIQUE_ID_BYTES, "id size");
+    if (!id) return fail(AGOFRT_ERR_ARG, "id is NULL");
+    NcclApi &api = nccl_api();
+    if (!api.ok) return fail(AGOFRT_ERR_NCCL, "libnccl.so.2 could not be loaded");
+    ncclUniqueId u;
+    NC(api.GetUniqueId(&u));
+    memcpy(id, u.internal, NCCL_UNIQUE_ID_BYTES);
+    return AGOFRT_OK;
+}
+
+static int comm_init(agofrt_ctx *ctx, const ncclUniqueId &u, int first_rank, int world) {
+    NcclApi &api = nccl_api();
+    if (!api.ok) return fail(AGOFRT_ERR_NCCL, "libnccl.so.2 could not be loaded");
+    const int nloc = static_cast<int>(ctx->devs.size());
+    if (first_rank < 0 || first_rank + nloc > world) return fail(AGOFRT_ERR_ARG, "rank range outside world");
+    NC(api.GroupStart());
+    for (int i = 0; i < nloc; ++i) {
+        CU(cudaSetDevice(ctx->devs[i].id));
+        NC(api.CommInitRank(&ctx->devs[i].comm, world, u, first_rank + i));
+    }
+    NC(api.GroupEnd());
+    ctx->first_rank = first_rank;
+    ctx->world = world;
+    ctx->comm_ready = true;
+    ctx->shard_only = false;
+    return AGOFRT_OK;
+}
+
+extern "C" int agofrt_comm_join(agofrt_ctx *ctx, const char id[AGOFRT_COMM_ID_BYTES], int first_rank, int world) {
+    if (!ctx || !id) return fail(AGOFRT_ERR_ARG, "NULL argument");
+    if (ctx->comm_ready) return fail(AGOFRT_ERR_ARG, "context already has a communicator");
+    ncclUniqueId u;
+    memcpy(u.internal, id, NCCL_UNIQUE_ID_BYTES);
+    return comm_init(ctx, u, first_rank, world);
+}
+
+extern "C" int agofrt_ctx_set_shard(agofrt_ctx *ctx, int first_rank, int world) {
+    if (!ctx) return fail(AGOFRT_ERR_ARG, "NULL argument");
+    const int nloc = static_cast<int>(ctx->devs.size());
+    if (world < nloc || first_rank < 0 || first_rank + nloc > world)
+        return fail(AGOFRT_ERR_ARG, "rank range outside world");
+    if (ctx->comm_ready) return fail(AGOFRT_ERR_ARG, "context already has a communicator");
+    ctx->first_rank = first_rank;
+    ctx->world = world;
+    ctx->shard_only = true;
+    return AGOFRT_OK;
+}
+
+extern "C" int agofrt_shard_range(uint64_t units, int rank, int world, uint64_t *begin, uint64_t *end) {
+    if (!begin || !end || world <= 0 || rank < 0 || rank >= world) return fail(AGOFRT_ERR_ARG, "bad shard arguments");
+    // 128-bit products: units * world never overflows
+    *begin = static_cast<uint64_t>(static_cast<unsigned __int128>(units) * rank / world);
+    *end = static_cast<uint64_t>(static_cast<unsigned __int128>(units) * (rank + 1) / world);
+    return AGOFRT_OK;
+}
+
+// a multi-device context without a joined communicator is its own communicator
+static int ensure_local_comm(agofrt_ctx *ctx) {
+    if (ctx->comm_ready || ctx->shard_only || ctx->devs.size() <= 1) return AGOFRT_OK;
+    NcclApi &api = nccl_api();
+    if (!api.ok) return fail(AGOFRT_ERR_NCCL, "libnccl.so.2 could not be loaded (needed for >1 device)");
+    ncclUniqueId u;
+    NC(api.GetUniqueId(&u));
+    return comm_init(ctx, u, 0, static_cast<int>(ctx->devs.size()));
+}
+
+// ---------------------------------------------------------------------------------------------
+// trajectory window
+// ---------------------------------------------------------------------------------------------
+static void free_traj_dev(agofrt_traj *t) {
+    for (size_t i = 0; i < t->dev.size(); ++i) {
+        cudaSetDevice(t->ctx->devs[i].id);
+        TrajDev &d = t->dev[i];
+        cudaFree(d.pos);
+        cudaFree(d.box6);
+        cudaFree(d.bounds);
+        cudaFree(d.stage);
+        cudaFree(d.box_stage);
+        cudaFree(d.perm);
+        cudaFree(d.type_pad);
+        cudaFree(d.type_start);
+        cudaFree(d.flags);
+    }
+}
+
+extern "C" int agofrt_traj_create(agofrt_traj **out, agofrt_ctx *ctx, size_t natoms, int box_stride,
+                                  const int *type_id, int ntypes, size_t max_frames) {
+    if (!out || !ctx) return fail(AGOFRT_ERR_ARG, "NULL argument");
+    *out = nullptr;
+    if (box_stride != 6 && box_stride != 9) return fail(AGOFRT_ERR_ARG, "box_stride must be 6 or 9");
+    if (ntypes <= 0 || ntypes > 64) return fail(AGOFRT_ERR_ARG, "ntypes must be in [1,64]");
+    if (natoms > 0 && !type_id) return fail(AGOFRT_ERR_ARG, "type_id is NULL");
+    if (natoms > (1u << 30)) return fail(AGOFRT_ERR_ARG, "natoms too large");
+    if (max_frames == 0) return fail(AGOFRT_ERR_ARG, "max_frames must be > 0");
+    auto t = std::make_unique<agofrt_traj>();
+    t->ctx = ctx;
+    t->natoms = natoms;
+    t->ntypes = ntypes;
+    t->stride = box_stride;
+    t->max_frames = max_frames;
+    t->type_id.assign(type_id, type_id + natoms);
+    std::vector<size_t> cnt(ntypes, 0);
+    for (size_t i = 0; i < natoms; ++i) {
+        if (type_id[i] < 0 || type_id[i] >= ntypes)
+            return fail(AGOFRT_ERR_ARG, "type_id[%zu]=%d not in [0,%d)", i, type_id[i], ntypes);
+        cnt[type_id[i]]++;
+    }
+    t->type_start.resize(ntypes + 1);
+    size_t off = 0;
+    for (int k = 0; k < ntypes; ++k) {
+        t->type_start[k] = static_cast<int>(off);
+        off += (cnt[k] + kPadGroup - 1) / kPadGroup * kPadGroup;
+    }
+    t->type_start[ntypes] = static_cast<int>(off);
+    t->npad = static_cast<int>(off);
+    t->type_pad.assign(t->npad, 0);
+    for (int k = 0; k < ntypes; ++k)
+        for (int s = t->type_start[k]; s < t->type_start[k + 1]; ++s) t->type_pad[s] = k;
+    t->perm.assign(t->npad, -1);
+
+    // staging: at most ~256 MiB of AoS frames at a time
+    const size_t frame_bytes = std::max<size_t>(natoms * 3 * sizeof(double), 1);
+    t->stage_frames = std::max<size_t>(1, std::min<size_t>(max_frames, (256u << 20) / frame_bytes));
+
+    const size_t npad1 = std::max(t->npad, 1);
+    t->dev.resize(ctx->devs.size());
+    for (size_t i = 0; i < ctx->devs.size(); ++i) {
+        CU(cudaSetDevice(ctx->devs[i].id));
+        TrajDev &d = t->dev[i];
+        cudaError_t e = cudaMalloc(&d.pos, max_frames * 3 * npad1 * sizeof(double));
+        if (e != cudaSuccess) {
+            free_traj_dev(t.get());
+            return fail(AGOFRT_ERR_CUDA, "cudaMalloc of the %zu-frame window (%zu bytes) failed: %s", max_frames,
+                        max_frames * 3 * npad1 * sizeof(double), cudaGetErrorString(e));
+        }
+        CU(cudaMalloc(&d.box6, max_frames * 6 * sizeof(double)));
+        CU(cudaMalloc(&d.bounds, max_frames * 6 * sizeof(double)));
+        CU(cudaMalloc(&d.stage, t->stage_frames * frame_bytes));
+        CU(cudaMalloc(&d.box_stage, max_frames * box_stride * sizeof(double)));
+        CU(cudaMalloc(&d.perm, npad1 * sizeof(int)));
+        CU(cudaMalloc(&d.type_pad, npad1 * sizeof(int)));
+        CU(cudaMalloc(&d.type_start, (ntypes + 1) * sizeof(int)));
+        CU(cudaMalloc(&d.flags, 4 * sizeof(unsigned int)));
+        CU(cudaMemset(d.flags, 0, 4 * sizeof(unsigned int)));
+        if (t->npad > 0) CU(cudaMemcpy(d.type_pad, t->type_pad.data(), t->npad * sizeof(int), cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(d.type_start, t->type_start.data(), (ntypes + 1) * sizeof(int), cudaMemcpyHostToDevice));
+    }
+    *out = t.release();
+    return AGOFRT_OK;
+}
+
+extern "C" int agofrt_traj_destroy(agofrt_traj *t) {
+    if (!t) return AGOFRT_OK;
+    free_traj_dev(t);
+    delete t;
+    return AGOFRT_OK;
+}
+
+static inline uint32_t spread3(uint32_t v) {  // 10 bits -> every third bit
+    v &= 0x3ffu;
+    v = (v | (v << 16)) & 0x030000ffu;
+    v = (v | (v << 8)) & 0x0300f00fu;
+    v = (v | (v << 4)) & 0x030c30c3u;
+    v = (v | (v << 2)) & 0x09249249u;
+    return v;
+}
+
+// Type-major, Morton-ordered permutation from the first frame of the window.  Only the ORDER of the
+// device slots depends on it -- never a count -- so a poor key costs speed, not correctness.
+static void build_perm(agofrt_traj *t, const double *pos0, const double *box_row) {
+    const size_t n = t->natoms;
+    std::vector<uint64_t> key(n);
+    const double Lx = 2 * box_row[3], Ly = 2 * box_row[4], Lz = 2 * box_row[5];
+    const bool tri = t->stride == 9;
+    const double xy = tri ? box_row[6] : 0.0, xz = tri ? box_row[7] : 0.0, yz = tri ? box_row[8] : 0.0;
+    const bool okbox = Lx > 0 && Ly > 0 && Lz > 0 && std::isfinite(Lx) && std::isfinite(Ly) && std::isfinite(Lz);
+    int bits = 1;
+    while (bits < 10 && (static_cast<size_t>(1) << (3 * bits)) * 4 < n) ++bits;
+    const double scale = static_cast<double>(1u << bits);
+    for (size_t i = 0; i < n; ++i) {
+        uint32_t m = 0;
+        if (okbox) {
+            const double x = pos0[3 * i], y = pos0[3 * i + 1], z = pos0[3 * i + 2];
+            double sz = z / Lz;
+            double sy = (y - yz * sz) / Ly;
+            double sx = (x - xy * sy - xz * sz) / Lx;
+            sx -= std::floor(sx);
+            sy -= std::floor(sy);
+            sz -= std::floor(sz);
+            if (std::isfinite(sx) && std::isfinite(sy) && std::isfinite(sz)) {
+                const uint32_t cx = std::min<uint32_t>(static_cast<uint32_t>(sx * scale), (1u << bits) - 1);
+                const uint32_t cy = std::min<uint32_t>(static_cast<uint32_t>(sy * scale), (1u << bits) - 1);
+                const uint32_t cz = std::min<uint32_t>(static_cast<uint32_t>(sz * scale), (1u << bits) - 1);
+                m = spread3(cx) | (spread3(cy) << 1) | (spread3(cz) << 2);
+            }
+        }
+        key[i] = (static_cast<uint64_t>(t->type_id[i]) << 32) | m;
+    }
+    std::vector<int> order(n);
+    std::iota(order.begin(), order.end(), 0);
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return key[a] < key[b]; });
+    std::fill(t->perm.begin(), t->perm.end(), -1);
+    std::vector<int> fill(t->type_start.begin(), t->type_start.end() - 1);
+    for (size_t k = 0; k < n; ++k) {
+        const int a = order[k];
+        t->perm[fill[t->type_id[a]]++] = a;
+    }
+}
+
+extern "C" int agofrt_traj_upload(agofrt_traj *t, size_t first_frame, size_t nframes, const double *pos_aos,
+                                  const double *box_internal) {
+    if (!t) return fail(AGOFRT_ERR_ARG, "traj is NULL");
+    if (nframes > t->max_frames) return fail(AGOFRT_ERR_ARG, "window of %zu frames > max_frames %zu", nframes, t->max_frames);
+    if (nframes > 0 && (!box_internal || (t->natoms > 0 && !pos_aos))) return fail(AGOFRT_ERR_ARG, "NULL buffer");
+    t->first_frame = first_frame;
+    t->nframes = nframes;
+    t->box6.assign(nframes * 6, 0.0);
+    t->bounds.assign(nframes * 6, 0.0);
+    t->has_inf = false;
+    t->bad_box = false;
+    if (nframes == 0) return AGOFRT_OK;
+
+    for (size_t f = 0; f < nframes; ++f) {
+        const double *r = box_internal + f * t->stride;
+        double *o = &t->box6[f * 6];
+        o[0] = r[3];
+        o[1] = r[4];
+        o[2] = r[5];
+        o[3] = t->stride == 9 ? r[6] : 0.0;
+        o[4] = t->stride == 9 ? r[7] : 0.0;
+        o[5] = t->stride == 9 ? r[8] : 0.0;
+        for (int k = 0; k < 3; ++k)
+            if (!(o[k] > 0.0) || !std::isfinite(o[k])) t->bad_box = true;
+        for (int k = 3; k < 6; ++k)
+            if (!std::isfinite(o[k])) t->bad_box = true;
+    }
+    if (t->natoms > 0) build_perm(t, pos_aos, box_internal);
+
+    const size_t frame_elems = t->natoms * 3;
+    for (size_t i = 0; i < t->dev.size(); ++i) {
+        Dev &dv = t->ctx->devs[i];
+        TrajDev &d = t->dev[i];
+        CU(cudaSetDevice(dv.id));
+        CU(cudaMemsetAsync(d.flags, 0, 4 * sizeof(unsigned int), dv.stream));
+        if (t->npad > 0)
+            CU(cudaMemcpyAsync(d.perm, t->perm.data(), t->npad * sizeof(int), cudaMemcpyHostToDevice, dv.stream));
+        CU(cudaMemcpyAsync(d.box_stage, box_internal, nframes * t->stride * sizeof(double), cudaMemcpyHostToDevice,
+                           dv.stream));
+        CU(launch_pack_box(d.box_stage, t->stride, static_cast<int>(nframes), d.box6, dv.stream));
+    }
+    if (t->npad > 0) {
+        for (size_t f0 = 0; f0 < nframes; f0 += t->stage_frames) {
+            const size_t nf = std::min(t->stage_frames, nframes - f0);
+            for (size_t i = 0; i < t->dev.size(); ++i) {
+                Dev &dv = t->ctx->devs[i];
+                TrajDev &d = t->dev[i];
+                CU(cudaSetDevice(dv.id));
+                CU(cudaMemcpyAsync(d.stage, pos_aos + f0 * frame_elems, nf * frame_elems * sizeof(double),
+                                   cudaMemcpyHostToDevice, dv.stream));
+                CU(launch_gather_soa(d.stage, d.perm, static_cast<int>(t->natoms), t->npad, static_cast<int>(nf),
+                                     d.pos + f0 * 3 * static_cast<size_t>(t->npad), dv.stream));
+            }
+        }
+        // coordinate bounds per frame (device 0 is enough: every device holds the same window)
+        Dev &dv = t->ctx->devs[0];
+        TrajDev &d = t->dev[0];
+        CU(cudaSetDevice(dv.id));
+        CU(launch_frame_bounds(d.pos, t->npad, static_cast<int>(nframes), d.bounds, d.flags, dv.stream));
+        unsigned int flags[4] = {0, 0, 0, 0};
+        CU(cudaMemcpyAsync(t->bounds.data(), d.bounds, nframes * 6 * sizeof(double), cudaMemcpyDeviceToHost, dv.stream));
+        CU(cudaMemcpyAsync(flags, d.flags, sizeof(flags), cudaMemcpyDeviceToHost, dv.stream));
+        CU(cudaStreamSynchronize(dv.stream));
+        t->has_inf = flags[0] != 0;
+    }
+    for (size_t i = 0; i < t->dev.size(); ++i) {
+        CU(cudaSetDevice(t->ctx->devs[i].id));
+        CU(cudaStreamSynchronize(t->ctx->devs[i].stream));
+    }
+    return AGOFRT_OK;
+}
+
+extern "C" int agofrt_traj_download_frame(agofrt_traj *t, size_t frame, double *pos_aos) {
+    if (!t || !pos_aos) return fail(AGOFRT_ERR_ARG, "NULL argument");
+    if (frame < t->first_frame || frame >= t->first_frame + t->nframes)
+        return fail(AGOFRT_ERR_WINDOW, "frame %zu is not in the uploaded window", frame);
+    if (t->natoms == 0) return AGOFRT_OK;
+    Dev &dv = t->ctx->devs[0];
+    TrajDev &d = t->dev[0];
+    CU(cudaSetDevice(dv.id));
+    const size_t rel = frame - t->first_frame;
+    CU(launch_scatter_aos(d.pos + rel * 3 * static_cast<size_t>(t->npad), d.perm, static_cast<int>(t->natoms), t->npad,
+                          d.stage, dv.stream));
+    CU(cudaMemcpyAsync(pos_aos, d.stage, t->natoms * 3 * sizeof(double), cudaMemcpyDeviceToHost, dv.stream));
+    CU(cudaStreamSynchronize(dv.stream));
+    return AGOFRT_OK;
+}
+
+extern "C" int agofrt_pbc_wrap(agofrt_ctx *ctx, double *pos_aos, size_t nframes, size_t natoms,
+                               const double *box_internal, int box_stride) {
+    if (!ctx) return fail(AGOFRT_ERR_ARG, "ctx is NULL");
+    if (box_stride != 6 && box_stride != 9) return fail(AGOFRT_ERR_ARG, "box_stride must be 6 or 9");
+    if (nframes == 0 || natoms == 0) return AGOFRT_OK;
+    if (!pos_aos || !box_internal) return fail(AGOFRT_ERR_ARG, "NULL buffer");
+    for (size_t f = 0; f < nframes; ++f)
+        for (int k = 3; k < box_stride; ++k) {
+            const double v = box_internal[f * box_stride + k];
+            if (!std::isfinite(v) || (k < 6 && !(v > 0.0)))
+                return fail(AGOFRT_ERR_NONFINITE, "frame %zu: box entry %d = %g (the reference would not terminate)", f, k, v);
+        }
+    Dev &dv = ctx->devs[0];
+    CU(cudaSetDevice(dv.id));
+    const size_t frame_bytes = natoms * 3 * sizeof(double);
+    const size_t chunk = std::max<size_t>(1, std::min<size_t>(nframes, (256u << 20) / frame_bytes));
+    double *dpos = nullptr, *dbox = nullptr;
+    unsigned int *dflag = nullptr;
+    CU(cudaMalloc(&dpos, chunk * frame_bytes));
+    CU(cudaMalloc(&dbox, nframes * box_stride * sizeof(double)));
+    CU(cudaMalloc(&dflag, sizeof(unsigned int)));
+    int rc = AGOFRT_OK;
+    auto body = [&]() -> int {
+        CU(cudaMemsetAsync(dflag, 0, sizeof(unsigned int), dv.stream));
+        CU(cudaMemcpyAsync(dbox, box_internal, nframes * box_stride * sizeof(double), cudaMemcpyHostToDevice, dv.stream));
+        for (size_t f0 = 0; f0 < nframes; f0 += chunk) {
+            const size_t nf = std::min(chunk, nframes - f0);
+            CU(cudaMemcpyAsync(dpos, pos_aos + f0 * natoms * 3, nf * frame_bytes, cudaMemcpyHostToDevice, dv.stream));
+            CU(launch_pbc_wrap(dpos, static_cast<int>(natoms), static_cast<int>(nf), dbox + f0 * box_stride, box_stride,
+                               dflag, dv.stream));
+            CU(cudaMemcpyAsync(pos_aos + f0 * natoms * 3, dpos, nf * frame_bytes, cudaMemcpyDeviceToHost, dv.stream));
+        }
+        unsigned int flag = 0;
+        CU(cudaMemcpyAsync(&flag, dflag, sizeof(flag), cudaMemcpyDeviceToHost, dv.stream));
+        CU(cudaStreamSynchronize(dv.stream));
+        if (flag) return fail(AGOFRT_ERR_NONFINITE, "minimum image did not converge (non-finite or absurdly far coordinate)");
+        return AGOFRT_OK;
+    };
+    rc = body();
+    cudaFree(dpos);
+    cudaFree(dbox);
+    cudaFree(dflag);
+    return rc;
+}
+
+extern "C" int agofrt_traj_d2_all(agofrt_traj *t, size_t frame_i, size_t frame_j, double *out) {
+    if (!t || !out) return fail(AGOFRT_ERR_ARG, "NULL argument");
+    for (size_t f : {frame_i, frame_j})
+        if (f < t->first_frame || f >= t->first_frame + t->nframes)
+            return fail(AGOFRT_ERR_WINDOW, "frame %zu is not in the uploaded window", f);
+    if (t->natoms == 0) return AGOFRT_OK;
+    if (t->natoms > 4096) return fail(AGOFRT_ERR_ARG, "d2_all is a small-N probe (natoms <= 4096)");
+    if (t->bad_box || t->has_inf) return fail(AGOFRT_ERR_NONFINITE, "non-finite coordinates or invalid box");
+    Dev &dv = t->ctx->devs[0];
+    TrajDev &d = t->dev[0];
+    CU(cudaSetDevice(dv.id));
+    const size_t ri = frame_i - t->first_frame, rj = frame_j - t->first_frame;
+    double *dout = nullptr;
+    const size_t bytes = t->natoms * t->natoms * 4 * sizeof(double);
+    CU(cudaMalloc(&dout, bytes));
+    auto body = [&]() -> int {
+        CU(cudaMemsetAsync(d.flags + 1, 0, sizeof(unsigned int), dv.stream));
+        CU(launch_d2_all(d.pos + ri * 3 * static_cast<size_t>(t->npad), d.pos + rj * 3 * static_cast<size_t>(t->npad),
+                         d.box6 + ri * 6, t->stride == 9, d.perm, static_cast<int>(t->natoms), t->npad, dout,
+                         d.flags + 1, dv.stream));
+        CU(cudaMemcpyAsync(out, dout, bytes, cudaMemcpyDeviceToHost, dv.stream));
+        unsigned int flag = 0;
+        CU(cudaMemcpyAsync(&flag, d.flags + 1, sizeof(flag), cudaMemcpyDeviceToHost, dv.stream));
+        CU(cudaStreamSynchronize(dv.stream));
+        if (flag) return fail(AGOFRT_ERR_NONFINITE, "minimum image did not converge");
+        return AGOFRT_OK;
+    };
+    const int rc = body();
+    cudaFree(dout);
+    return rc;
+}
+
+// ---------------------------------------------------------------------------------------------
+// plan: the exact threshold table
+// ---------------------------------------------------------------------------------------------
+// The reference's bin index for an accepted pair (lib/src/gofrt.cpp:114-117), clipped to
+// [-1, nbin]: sqrt in double, subtract and divide in double, ROUND TO FLOAT, floorf, (int).
+// This translation unit is compiled without FMA contraction and without fast-math.
+static int ref_bin_clipped(double d2, double rmin, double dr, unsigned nbin) {
+    volatile double d = std::sqrt(d2);
+    volatile double q = (d - rmin) / dr;
+    volatile float qf = static_cast<float>(q);
+    const float f = floorf(qf);
+    if (!(f >= 0.0f)) return -1;
+    if (f >= static_cast<float>(nbin)) return static_cast<int>(nbin);
+    return static_cast<int>(f);
+}
+
+static inline double bits_to_double(uint64_t b) {
+    double d;
+    memcpy(&d, &b, 8);
+    return d;
+}
+static inline uint64_t double_to_bits(double d) {
+    uint64_t b;
+    memcpy(&b, &d, 8);
+    return b;
+}
+
+// thresholds[k] = smallest non-negative double d2 with ref_bin_clipped(d2) >= k, k = 0..nbin.
+// ref_bin_clipped is monotone non-decreasing in d2 (a composition of monotone roundings), so a
+// bisection over the bit patterns of the non-negative doubles finds it exactly.
+static void build_thresholds(double rmin, double dr, unsigned nbin, std::vector<double> &thr) {
+    thr.resize(nbin + 1);
+    const uint64_t inf_bits = 0x7ff0000000000000ull;
+    uint64_t lo_start = 0;
+    for (unsigned k = 0; k <= nbin; ++k) {
+        uint64_t lo = lo_start, hi = inf_bits;  // answer in [lo, hi]
+        if (ref_bin_clipped(bits_to_double(lo), rmin, dr, nbin) >= static_cast<int>(k)) {
+            thr[k] = bits_to_double(lo);
+            continue;
+        }
+        // invariant: f(lo) < k <= f(hi)   (f(+inf) = nbin >= k)
+        while (hi - lo > 1) {
+            const uint64_t mid = lo + (hi - lo) / 2;
+            if (ref_bin_clipped(bits_to_double(mid), rmin, dr, nbin) >= static_cast<int>(k))
+                hi = mid;
+            else
+                lo = mid;
+        }
+        thr[k] = bits_to_double(hi);
+        lo_start = lo;
+    }
+}
+
+extern "C" int agofrt_plan_create(agofrt_plan **out, agofrt_traj *traj, double rmin, double rmax, unsigned nbin) {
+    if (!out || !traj) return fail(AGOFRT_ERR_ARG, "NULL argument");
+    *out = nullptr;
+    if (nbin == 0 || nbin > (1u << 24)) return fail(AGOFRT_ERR_ARG, "nbin must be in [1, 2^24]");
+    auto p = std::make_unique<agofrt_plan>();
+    p->traj = traj;
+    p->rmin = rmin;
+    p->rmax = rmax;
+    p->nbin = nbin;
+    // reference lib/src/gofrt.cpp:27-29
+    p->dr = (rmax - rmin) / nbin;
+    p->rmax2 = rmax * rmax;
+    p->rmin2 = rmin * rmin;
+
+    const int nt = traj->ntypes;
+    const size_t smem = pair_kernel_smem_bytes(nt, static_cast<int>(nbin), true);
+    for (const Dev &d : traj->ctx->devs)
+        if (smem > d.smem_optin)
+            return fail(AGOFRT_ERR_TOO_LARGE,
+                        "histogram of %d type-pair rows x %u bins needs %zu bytes of shared memory (> %zu)",
+                        nt * (nt + 1), nbin, smem, d.smem_optin);
+
+    if (p->dr > 0 && std::isfinite(p->dr) && std::isfinite(rmin)) {
+        build_thresholds(rmin, p->dr, nbin, p->thr_full);
+    } else {
+        // dr <= 0 or NaN: the reference's idx is negative, NaN or huge for every pair -> nothing counted
+        p->thr_full.assign(nbin + 1, std::numeric_limits<double>::infinity());
+    }
+    // fold the inclusive range test rmin2 <= d2 <= rmax2 (lib/src/gofrt.cpp:104) into the table
+    const double lo = std::max(p->rmin2, p->thr_full[0]);
+    const double hi_excl = std::min(std::nextafter(p->rmax2, std::numeric_limits<double>::infinity()), p->thr_full[nbin]);
+    p->thr.resize(nbin + 1);
+    if (!(lo < hi_excl)) {
+        p->empty_range = true;
+        std::fill(p->thr.begin(), p->thr.end(), std::numeric_limits<double>::infinity());
+        p->hlo = 1;
+        p->hspan = 0;
+    } else {
+        for (unsigned k = 0; k <= nbin; ++k) p->thr[k] = std::min(std::max(p->thr_full[k], lo), hi_excl);
+        const uint64_t lob = double_to_bits(lo), hib = double_to_bits(hi_excl) - 1;  // 0 <= lo < hi_excl
+        p->hlo = static_cast<unsigned>(lob >> 32);
+        p->hspan = static_cast<unsigned>(hib >> 32) - p->hlo;
+    }
+    p->inv_dr = static_cast<float>(1.0 / p->dr);
+    p->c0 = static_cast<float>(-rmin / p->dr);
+    if (!std::isfinite(p->inv_dr)) p->inv_dr = 0.0f;
+    if (!std::isfinite(p->c0)) p->c0 = 0.0f;
+
+    p->dev.resize(traj->ctx->devs.size());
+    for (size_t i = 0; i < p->dev.size(); ++i) {
+        CU(cudaSetDevice(traj->ctx->devs[i].id));
+        PlanDev &d = p->dev[i];
+        CU(cudaMalloc(&d.thr, (nbin + 1) * sizeof(double)));
+        CU(cudaMalloc(&d.thr_full, (nbin + 1) * sizeof(double)));
+        CU(cudaMalloc(&d.counter, sizeof(unsigned int)));
+        CU(cudaMalloc(&d.edges, sizeof(unsigned long long)));
+        CU(cudaMemcpy(d.thr, p->thr.data(), (nbin + 1) * sizeof(double), cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(d.thr_full, p->thr_full.data(), (nbin + 1) * sizeof(double), cudaMemcpyHostToDevice));
+    }
+    CU(cudaHostAlloc(reinterpret_cast<void **>(&p->host_edges), sizeof(unsigned long long) * p->dev.size(),
+                     cudaHostAllocPortable));
+    CU(cudaHostAlloc(reinterpret_cast<void **>(&p->host_flags), sizeof(unsigned int) * p->dev.size(),
+                     cudaHostAllocPortable));
+    *out = p.release();
+    return AGOFRT_OK;
+}
+
+extern "C" int agofrt_plan_destroy(agofrt_plan *p) {
+    if (!p) return AGOFRT_OK;
+    for (size_t i = 0; i < p->dev.size(); ++i) {
+        cudaSetDevice(p->traj->ctx->devs[i].id);
+        PlanDev &d = p->dev[i];
+        cudaFree(d.thr);
+        cudaFree(d.thr_full);
+        cudaFree(d.ghist);
+        cudaFree(d.jobs);
+        cudaFree(d.counter);
+        cudaFree(d.edges);
+    }
+    if (p->host_counts) cudaFreeHost(p->host_counts);
+    if (p->host_edges) cudaFreeHost(p->host_edges);
+    if (p->host_flags) cudaFreeHost(p->host_flags);
+    delete p;
+    return AGOFRT_OK;
+}
+
+extern "C" int agofrt_plan_thresholds(const agofrt_plan *p, double *thresholds) {
+    if (!p || !thresholds) return fail(AGOFRT_ERR_ARG, "NULL argument");
+    memcpy(thresholds, p->thr_full.data(), (p->nbin + 1) * sizeof(double));
+    return AGOFRT_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// one block
+// ---------------------------------------------------------------------------------------------
+// Is one image per dimension PROVABLY enough for every pair of this (frame fi, frame fj) job?
+// |xi-xj| is bounded by the coordinate ranges of the two frames (the rounded difference is
+// monotone in its operands), each tilt correction adds at most |tilt|, and a value with
+// |d| <= 3*l_half lands in [-l_half, l_half] after one +-2*l_half.  2.99 leaves room for the
+// roundings of the bound itself.
+static bool job_is_single_pass(const agofrt_traj *t, size_t fi, size_t fj) {
+    const double *b = &t->box6[fi * 6];
+    const double *bi = &t->bounds[fi * 6], *bj = &t->bounds[fj * 6];
+    double D[3];
+    for (int c = 0; c < 3; ++c) {
+        const double a = std::fabs(bi[3 + c] - bj[c]);  // max_i - min_j
+        const double d = std::fabs(bi[c] - bj[3 + c]);  // min_i - max_j
+        D[c] = std::max(a, d);
+        if (!std::isfinite(D[c])) return false;
+    }
+    const double xy = std::fabs(b[3]), xz = std::fabs(b[4]), yz = std::fabs(b[5]);
+    const double m = 2.99;
+    if (!(D[2] <= m * b[2])) return false;
+    if (!(D[1] + yz <= m * b[1])) return false;
+    if (!(D[0] + xz + xy <= m * b[0])) return false;
+    return true;
+}
+
+extern "C" int agofrt_block(agofrt_plan *p, size_t primo, unsigned ntimesteps, unsigned leff, unsigned skip,
+                            unsigned every, unsigned options, uint64_t *counts_out, uint64_t *edge_pairs_out,
+                            agofrt_stats *stats) {
+    if (!p) return fail(AGOFRT_ERR_ARG, "plan is NULL");
+    agofrt_traj *t = p->traj;
+    agofrt_ctx *ctx = t->ctx;
+    if (skip == 0) skip = 1;    // reference lib/include/calculatemultithread.h:44-45
+    if (every == 0) every = 1;
+    const int nt = t->ntypes;
+    const size_t rowlen = static_cast<size_t>(nt) * (nt + 1) * p->nbin;
+    const size_t len = static_cast<size_t>(leff) * rowlen;
+    if (len > 0 && !counts_out) return fail(AGOFRT_ERR_ARG, "counts_out is NULL");
+    if (stats) memset(stats, 0, sizeof(*stats));
+    if (edge_pairs_out) *edge_pairs_out = 0;
+    const bool want_edges = (options & AGOFRT_OPT_EDGES) != 0 || edge_pairs_out != nullptr;
+
+    int rc = ensure_local_comm(ctx);
+    if (rc != AGOFRT_OK) return rc;
+    const int nloc = static_cast<int>(ctx->devs.size());
+    const int world = ctx->world > 0 ? ctx->world : nloc;
+    const int first_rank = ctx->world > 0 ? ctx->first_rank : 0;
+
+    // ---- the (lag, origin) jobs, in the reference's loop order (calculatemultithread.h:114-115) ----
+    std::vector<Job> jobs_fast, jobs_gen;
+    uint64_t njobs = 0;
+    if (ntimesteps > 0 && leff > 0) {
+        // the last frame the loops really touch: last origin + last lag
+        const size_t last = primo + static_cast<size_t>((ntimesteps - 1) / skip) * skip +
+                            static_cast<size_t>((leff - 1) / every) * every;
+        if (primo < t->first_frame || last >= t->first_frame + t->nframes)
+            return fail(AGOFRT_ERR_WINDOW,
+                        "block needs frames [%zu,%zu] but the device window holds [%zu,%zu)", primo, last,
+                        t->first_frame, t->first_frame + t->nframes);
+        if (t->natoms > 0 && (t->bad_box || t->has_inf))
+            return fail(AGOFRT_ERR_NONFINITE,
+                        "the window holds an infinite coordinate or a non-positive / non-finite box edge "
+                        "(the reference's minimum image would not terminate)");
+        for (unsigned tl = 0; tl < leff; tl += every)
+            for (unsigned im = 0; im < ntimesteps; im += skip) {
+                const size_t fi = primo + im - t->first_frame;
+                Job j{static_cast<int>(fi), static_cast<int>(fi + tl), static_cast<int>(tl)};
+                const bool fast = !(options & AGOFRT_OPT_FORCE_GENERAL) && job_is_single_pass(t, fi, fi + tl);
+                (fast ? jobs_fast : jobs_gen).push_back(j);
+                ++njobs;
+            }
+    }
+    const uint64_t n2 = static_cast<uint64_t>(t->natoms) * t->natoms;
+    const bool nothing = njobs == 0 || t->natoms == 0 || p->empty_range || len == 0;
+
+    // ---- work units ----
+    const int n_itiles = std::max(1, (t->npad + kTileI - 1) / kTileI);
+    int total_ctas = 0;
+    for (const Dev &d : ctx->devs) total_ctas += 2 * d.sm_count;
+    total_ctas = total_ctas / nloc * world;
+    int n_jchunks = 1;
+    {
+        const int max_chunks = std::max(1, (t->npad + 4 * kTileJ - 1) / (4 * kTileJ));
+        const uint64_t want = 16ull * total_ctas;
+        const uint64_t base = std::max<uint64_t>(1, njobs * n_itiles);
+        n_jchunks = static_cast<int>(std::min<uint64_t>(max_chunks, (want + base - 1) / base));
+        n_jchunks = std::max(1, n_jchunks);
+    }
+    int jchunk = (t->npad + n_jchunks - 1) / n_jchunks;
+    jchunk = std::max(kTileJ, (jchunk + kTileJ - 1) / kTileJ * kTileJ);
+    n_jchunks = std::max(1, (t->npad + jchunk - 1) / jchunk);
+    const uint64_t per_job = static_cast<uint64_t>(n_itiles) * n_jchunks;
+    if (njobs * per_job >= 0xF0000000ull) return fail(AGOFRT_ERR_ARG, "too many work units in one block (%llu)",
+                                                      static_cast<unsigned long long>(njobs * per_job));
+
+    bool aggregate = p->nbin * static_cast<unsigned>(nt * (nt + 1) / 2) < 64;  // few counters: collisions are the rule
+    if (options & AGOFRT_OPT_AGGREGATE) aggregate = true;
+    if (options & AGOFRT_OPT_NO_AGGREGATE) aggregate = false;
+    const bool tri = t->stride == 9;
+    const size_t smem = pair_kernel_smem_bytes(nt, static_cast<int>(p->nbin), want_edges);
+
+    // ---- pinned read-back buffer ----
+    if (len > p->host_counts_len) {
+        if (p->host_counts) cudaFreeHost(p->host_counts);
+        p->host_counts = nullptr;
+        p->host_counts_len = 0;
+        CU(cudaHostAlloc(reinterpret_cast<void **>(&p->host_counts), len * sizeof(unsigned long long),
+                         cudaHostAllocPortable));
+        p->host_counts_len = len;
+    }
+
+    unsigned launches = 0;
+    uint64_t my_pairs = 0;
+    // ---- enqueue on every local device ----
+    for (int i = 0; i < nloc; ++i) {
+        Dev &dv = ctx->devs[i];
+        TrajDev &td = t->dev[i];
+        PlanDev &pd = p->dev[i];
+        CU(cudaSetDevice(dv.id));
+        if (len > pd.ghist_len) {
+            cudaFree(pd.ghist);
+            pd.ghist = nullptr;
+            pd.ghist_len = 0;
+            CU(cudaMalloc(&pd.ghist, len * sizeof(unsigned long long)));
+            pd.ghist_len = len;
+        }
+        const size_t njall = jobs_fast.size() + jobs_gen.size();
+        if (njall > pd.jobs_cap) {
+            cudaFree(pd.jobs);
+            pd.jobs = nullptr;
+            pd.jobs_cap = 0;
+            CU(cudaMalloc(&pd.jobs, njall * sizeof(Job)));
+            pd.jobs_cap = njall;
+        }
+        CU(cudaEventRecord(dv.ev_begin, dv.stream));
+        if (len > 0) CU(cudaMemsetAsync(pd.ghist, 0, len * sizeof(unsigned long long), dv.stream));
+        CU(cudaMemsetAsync(pd.edges, 0, sizeof(unsigned long long), dv.stream));
+        CU(cudaMemsetAsync(td.flags + 1, 0, sizeof(unsigned int), dv.stream));
+        if (!jobs_fast.empty())
+            CU(cudaMemcpyAsync(pd.jobs, jobs_fast.data(), jobs_fast.size() * sizeof(Job), cudaMemcpyHostToDevice, dv.stream));
+        if (!jobs_gen.empty())
+            CU(cudaMemcpyAsync(pd.jobs + jobs_fast.size(), jobs_gen.data(), jobs_gen.size() * sizeof(Job),
+                               cudaMemcpyHostToDevice, dv.stream));
+        CU(cudaEventRecord(dv.ev_k0, dv.stream));
+        if (!nothing) {
+            const int g = first_rank + i;
+            for (int pass = 0; pass < 2; ++pass) {
+                const std::vector<Job> &list = pass == 0 ? jobs_fast : jobs_gen;
+                if (list.empty()) continue;
+                const uint64_t units = list.size() * per_job;
+                uint64_t ub = 0, ue = 0;
+                agofrt_shard_range(units, g, world, &ub, &ue);
+                if (ue <= ub) continue;
+                PairParams pp;
+                pp.pos = td.pos;
+                pp.box = td.box6;
+                pp.type_pad = td.type_pad;
+                pp.type_start = td.type_start;
+                pp.jobs = pd.jobs + (pass == 0 ? 0 : jobs_fast.size());
+                pp.ghist = pd.ghist;
+                pp.edges = pd.edges;
+                pp.counter = pd.counter;
+                pp.error_flag = td.flags + 1;
+                pp.thr = pd.thr;
+                pp.thr_full = pd.thr_full;
+                pp.rmin2 = p->rmin2;
+                pp.rmax2 = p->rmax2;
+                pp.unit_begin = static_cast<unsigned>(ub);
+                pp.unit_end = static_cast<unsigned>(ue);
+                pp.npad = t->npad;
+                pp.ntypes = nt;
+                pp.nbin = static_cast<int>(p->nbin);
+                pp.n_itiles = n_itiles;
+                pp.n_jchunks = n_jchunks;
+                pp.jchunk = jchunk;
+                pp.inv_dr = p->inv_dr;
+                pp.c0 = p->c0;
+                pp.hlo = p->hlo;
+                pp.hspan = p->hspan;
+                const int variant = (tri ? 1 : 0) | (pass == 0 ? 2 : 0) | ((aggregate && !want_edges) ? 4 : 0) |
+                                    (want_edges ? 8 : 0);
+                const int grid = static_cast<int>(std::min<uint64_t>(ue - ub, 2ull * dv.sm_count));
+                CU(cudaMemsetAsync(pd.counter, 0, sizeof(unsigned int), dv.stream));
+                CU(launch_pair_kernel(variant, grid, smem, dv.stream, pp));
+                ++launches;
+                // pair evaluations of this shard, counted on real atoms: units are equal-sized
+                my_pairs += static_cast<uint64_t>(static_cast<double>(ue - ub) / static_cast<double>(per_job) * n2 + 0.5);
+            }
+        }
+        CU(cudaEventRecord(dv.ev_k1, dv.stream));
+    }
+    // ---- combine: one all-reduce of the integer histograms (replaces mp.h:35-41) ----
+    if (ctx->comm_ready && world > 1 && len > 0) {
+        NcclApi &api = nccl_api();
+        NC(api.GroupStart());
+        for (int i = 0; i < nloc; ++i) {
+            Dev &dv = ctx->devs[i];
+            PlanDev &pd = p->dev[i];
+            NC(api.AllReduce(pd.ghist, pd.ghist, len, ncclUint64, ncclSum, dv.comm, dv.stream));
+            if (want_edges) NC(api.AllReduce(pd.edges, pd.edges, 1, ncclUint64, ncclSum, dv.comm, dv.stream));
+        }
+        NC(api.GroupEnd());
+    }
+    // ---- read back ----
+    {
+        Dev &dv = ctx->devs[0];
+        PlanDev &pd = p->dev[0];
+        CU(cudaSetDevice(dv.id));
+        if (len > 0)
+            CU(cudaMemcpyAsync(p->host_counts, pd.ghist, len * sizeof(unsigned long long), cudaMemcpyDeviceToHost, dv.stream));
+    }
+    for (int i = 0; i < nloc; ++i) {
+        Dev &dv = ctx->devs[i];
+        CU(cudaSetDevice(dv.id));
+        CU(cudaMemcpyAsync(&p->host_edges[i], p->dev[i].edges, sizeof(unsigned long long), cudaMemcpyDeviceToHost, dv.stream));
+        CU(cudaMemcpyAsync(&p->host_flags[i], t->dev[i].flags + 1, sizeof(unsigned int), cudaMemcpyDeviceToHost, dv.stream));
+        CU(cudaEventRecord(dv.ev_end, dv.stream));
+    }
+    double kernel_ms = 0, total_ms = 0;
+    for (int i = 0; i < nloc; ++i) {
+        Dev &dv = ctx->devs[i];
+        CU(cudaSetDevice(dv.id));
+        CU(cudaStreamSynchronize(dv.stream));
+        float a = 0, b = 0;
+        CU(cudaEventElapsedTime(&a, dv.ev_k0, dv.ev_k1));
+        CU(cudaEventElapsedTime(&b, dv.ev_begin, dv.ev_end));
+        kernel_ms = std::max<double>(kernel_ms, a);
+        total_ms = std::max<double>(total_ms, b);
+        if (p->host_flags[i])
+            return fail(AGOFRT_ERR_NONFINITE, "minimum image did not converge within %d images", kWrapCap);
+    }
+    // a sharded context without communicator and several local devices: partial counts are summed
+    // here only because they are all in this process (integer sum, order-free)
+    if (len > 0) {
+        memcpy(counts_out, p->host_counts, len * sizeof(uint64_t));
+        if (!ctx->comm_ready && nloc > 1) {
+            for (int i = 1; i < nloc; ++i) {
+                Dev &dv = ctx->devs[i];
+                CU(cudaSetDevice(dv.id));
+                CU(cudaMemcpy(p->host_counts, p->dev[i].ghist, len * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+                for (size_t k = 0; k < len; ++k) counts_out[k] += p->host_counts[k];
+            }
+        }
+    }
+    if (edge_pairs_out) {
+        if (ctx->comm_ready && world > 1) {
+            *edge_pairs_out = p->host_edges[0];
+        } else {
+            uint64_t s = 0;
+            for (int i = 0; i < nloc; ++i) s += p->host_edges[i];
+            *edge_pairs_out = s;
+        }
+    }
+    if (stats) {
+        stats->kernel_ms = kernel_ms;
+        stats->total_ms = total_ms;
+        stats->pair_evals = nothing ? 0 : my_pairs;
+        stats->pair_evals_total = njobs * n2;
+        stats->jobs = njobs;
+        stats->jobs_fast = jobs_fast.size();
+        stats->launches = launches;
+        stats->ndev_local = static_cast<uint32_t>(nloc);
+        stats->world = static_cast<uint32_t>(world);
+    }
+    return AGOFRT_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// FP64 issue-rate microbenchmark
+// ---------------------------------------------------------------------------------------------
+extern "C" int agofrt_fp64_peak(agofrt_ctx *ctx, int local_device, double seconds, double *dfma_per_second) {
+    if (!ctx || !dfma_per_second) return fail(AGOFRT_ERR_ARG, "NULL argument");
+    if (local_device < 0 || local_device >= static_cast<int>(ctx->devs.size()))
+        return fail(AGOFRT_ERR_ARG, "local_device out of range");
+    Dev &dv = ctx->devs[local_device];
+    CU(cudaSetDevice(dv.id));
+    if (!dv.peak_sink) CU(cudaMalloc(&dv.peak_sink, sizeof(double)));
+    const int blocks = dv.sm_count * 8;
+    unsigned long long count = 0;
+    // calibrate
+    int iters = 2000;
+    float ms = 0;
+    for (int rep = 0; rep < 2; ++rep) {
+        CU(cudaEventRecord(dv.ev_k0, dv.stream));
+        CU(launch_dfma_peak(dv.peak_sink, blocks, iters, dv.stream, &count));
+        CU(cudaEventRecord(dv.ev_k1, dv.stream));
+        CU(cudaStreamSynchronize(dv.stream));
+        CU(cudaEventElapsedTime(&ms, dv.ev_k0, dv.ev_k1));
+    }
+    if (!(seconds > 0)) seconds = 0.5;
+    const double per_launch_ms = std::max(ms, 1e-3f);
+    int nlaunch = static_cast<int>(std::min(200.0, std::max(3.0, seconds * 1e3 / per_launch_ms)));
+    double best = 0, total_ms = 0;
+    unsigned long long total = 0;
+    for (int k = 0; k < nlaunch; ++k) {
+        CU(cudaEventRecord(dv.ev_k0, dv.stream));
+        CU(launch_dfma_peak(dv.peak_sink, blocks, iters, dv.stream, &count));
+        CU(cudaEventRecord(dv.ev_k1, dv.stream));
+        CU(cudaStreamSynchronize(dv.stream));
+        CU(cudaEventElapsedTime(&ms, dv.ev_k0, dv.ev_k1));
+        total_ms += ms;
+        total += count;
+        best = std::max(best, count / (ms * 1e-3));
+    }
+    (void)best;
+    *dfma_per_second = total / (total_ms * 1e-3);  // sustained over the whole run
+    return AGOFRT_OK;
+}

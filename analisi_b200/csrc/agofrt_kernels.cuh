@@ -1,0 +1,85 @@
+// agofrt_kernels.cuh -- device side of libagofrt.so (sm_100a only).
+//
+// The pair kernel restates, on the GPU, the body of Gofrt::calc_single_th
+// (reference lib/src/gofrt.cpp:95-122) on top of BaseTrajectory::d2_minImage_triclinic /
+// minImage_triclinic (reference lib/include/basetrajectory.h:200-268), with the SAME double
+// arithmetic: every subtraction, addition and product is rounded on its own (__dsub_rn / __dadd_rn
+// / __dmul_rn, never contracted to FMA), the minimum image adds +-2*l_half (and the tilt factors)
+// one image at a time in the order z, y, x, and d2 = ((0+dx*dx)+dy*dy)+dz*dz.
+//
+// The bin index (int)floorf((sqrt(d2)-rmin)/dr) is a monotone step function of d2, so it is
+// looked up in a table of exact d2 thresholds computed on the host with the reference expression
+// (agofrt_cabi.cu: build_thresholds).  The kernel only needs a float guess of the bin and two
+// FP64 compares to land on exactly the reference's bin: no FP64 sqrt or divide on the device.
+#pragma once
+
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace agofrt {
+
+constexpr int kThreads = 256;               // threads per CTA
+constexpr int kIPT = 2;                     // i atoms held in registers per thread
+constexpr int kTileI = kThreads * kIPT;     // i atoms per work unit
+constexpr int kTileJ = 512;                 // j atoms per shared-memory stage
+constexpr int kStages = 2;                  // bulk-copy stages
+constexpr int kPadGroup = 8;                // every type group is padded to a multiple of this
+constexpr int kJU = 2;                      // j atoms per inner step (one LDS.128 per coordinate)
+constexpr int kWrapCap = 1 << 20;           // images the general minimum image may add per dimension
+
+struct Job {
+    int fi;    // window-relative frame of the i atoms (its box is used)
+    int fj;    // window-relative frame of the j atoms
+    int tout;  // output lag row
+};
+
+struct PairParams {
+    const double *pos;        // [frames][3][npad]  (x row, y row, z row per frame; ghosts are NaN)
+    const double *box;        // [frames][6]: lx/2, ly/2, lz/2, xy, xz, yz
+    const int *type_pad;      // [npad] dense type of every slot (ghosts: the type of their group)
+    const int *type_start;    // [ntypes+1] first slot of every type group
+    const Job *jobs;
+    unsigned long long *ghist;  // [leff][2P][nbin]
+    unsigned long long *edges;  // [1] (EDGES variant)
+    unsigned int *counter;      // work-unit ticket
+    unsigned int *error_flag;   // set when the general minimum image hits kWrapCap
+    const double *thr;          // [nbin+1] thresholds folded with the rmin2/rmax2 test
+    const double *thr_full;     // [nbin+1] plain thresholds (EDGES variant)
+    double rmin2, rmax2;
+    unsigned unit_begin, unit_end;
+    int npad, ntypes, nbin;
+    int n_itiles, n_jchunks, jchunk;  // jchunk is a multiple of kTileJ
+    float inv_dr, c0;                 // bin guess = floor(sqrtf(d2) * inv_dr + c0)
+    unsigned hlo, hspan;              // candidate test on the high word of d2
+};
+
+size_t pair_kernel_smem_bytes(int ntypes, int nbin, bool edges);
+
+// variant = TRI | FAST<<1 | AGG<<2 | EDGES<<3
+cudaError_t launch_pair_kernel(int variant, int grid, size_t smem, cudaStream_t stream, const PairParams &p);
+cudaError_t prepare_pair_kernels(size_t max_smem_optin);
+
+// pos_aos [nframes][natoms][3] -> pos_soa [nframes][3][npad] through perm[npad] (-1 = ghost -> NaN)
+cudaError_t launch_gather_soa(const double *pos_aos, const int *perm, int natoms, int npad, int nframes,
+                              double *pos_soa, cudaStream_t stream);
+// inverse: one frame back to the caller's order
+cudaError_t launch_scatter_aos(const double *pos_soa_frame, const int *perm, int natoms, int npad,
+                               double *pos_aos, cudaStream_t stream);
+// box rows [nframes][stride] -> [nframes][6] (lx/2, ly/2, lz/2, xy, xz, yz)
+cudaError_t launch_pack_box(const double *box_internal, int stride, int nframes, double *box6,
+                            cudaStream_t stream);
+// per frame: min x,y,z, max x,y,z (NaN ignored), and a flag if any coordinate is +-inf
+cudaError_t launch_frame_bounds(const double *pos_soa, int npad, int nframes, double *bounds6,
+                                unsigned int *inf_flag, cudaStream_t stream);
+// BaseTrajectory::pbc_wrap on AoS positions
+cudaError_t launch_pbc_wrap(double *pos_aos, int natoms, int nframes, const double *box_internal,
+                            int stride, unsigned int *error_flag, cudaStream_t stream);
+// all N^2 (dx,dy,dz,d2), caller's atom order
+cudaError_t launch_d2_all(const double *pos_i, const double *pos_j, const double *box6, int triclinic,
+                          const int *perm, int natoms, int npad, double *out, unsigned int *error_flag,
+                          cudaStream_t stream);
+// DFMA chains; *count_per_launch receives the number of lane-level DFMAs one launch executes
+cudaError_t launch_dfma_peak(double *sink, int blocks, int iters, cudaStream_t stream,
+                             unsigned long long *count_per_launch);
+
+}  // namespace agofrt

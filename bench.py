@@ -1,0 +1,358 @@
+#!/usr/bin/env python
+"""bench.py -- g(r,t) pair-distance evaluations per second on B200 (BASELINE.json's metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload C2] [--impl native|reference]
+
+A "step" is one Gofrt block: ``reset(ntimesteps); calculate(primo)`` of the named workload, i.e.
+ceil(leff/every) * ceil(ntimesteps/skip) (lag, origin) jobs of N^2 pair evaluations each, through
+the C ABI of libagofrt.so (no PyTorch in the data path; torch is only used for the multi-process
+rendezvous, the barrier and the NCCL-id broadcast).
+
+``value``   pair evaluations / s with the trajectory window already resident in HBM, timed with
+            CUDA events on the library's own stream (agofrt_stats.total_ms), max over ranks.
+``e2e``     the same through the host-buffer call sequence a user makes: upload of the window from
+            pinned host memory (H2D), the block, and the read-back of the counts (D2H), wall clock
+            around the calls with a device synchronise inside them.
+``roofline`` FP64-pipe bound: 16 (orthorhombic) / 19 (triclinic) FP64
+            operations per pair evaluation against the DFMA issue rate measured in this same run.
+``cpu_baseline`` the reference's own CPU implementation (oracle/_ref, compiled from the unmodified
+            sources) -- or the oracle port when that is absent -- on a bounded sample of the same
+            workload on this box's host cores.
+
+N > 1: one process per GPU (torchrun); every rank holds the whole window, the work units of the
+block are sharded over the ranks, one NCCL all-reduce of the integer histograms per step
+("strong" scaling: the total work per step is fixed).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from analisi_b200 import synth  # noqa: E402
+
+METRIC = "g(r,t) pair-distance evals/sec"
+UNIT = "pair_evals/s"
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
+# workloads
+# ---------------------------------------------------------------------------------------------
+def block_spec(name, quick=False):
+    """(workload, ntimesteps, primo) of the step: SURVEY.md section 8(d)."""
+    w = synth.WORKLOADS[name]
+    if name == "C2":
+        # throughput run: reset(1899); calculate(0), skip 1, lags 0..100 -> 101*1899 jobs of 4096^2
+        nts = 1899 if not quick else 64
+        return w, nts, 0
+    if name == "C3":
+        return w, 960, 0
+    if name == "C4":
+        return w, 768, 0
+    raise SystemExit("workload %s is not a single-block bench workload" % name)
+
+
+def jobs_of(nts, leff, skip, every):
+    return ((leff + every - 1) // every) * ((nts + skip - 1) // skip)
+
+
+def make_window(w, nframes):
+    t0 = time.time()
+    pos, box_lammps, types = synth.generate(w, nframes=nframes)
+    box_internal = synth.lammps_rows_to_internal(box_lammps)
+    log("[bench] generated %s: %d atoms x %d frames in %.1f s" % (w.name, w.natoms, nframes, time.time() - t0))
+    return pos, box_lammps, box_internal, types
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index):
+        self.dev = device_index
+        self.rows = []
+        self.proc = None
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.dev), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "200"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        rows = [r for (t, r) in self.rows if t0 <= t <= t1 + 0.3 and len(r) >= 9] or [r for (_, r) in self.rows if len(r) >= 9]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm = sorted(float(r[1]) for r in rows)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(r[5 + k].lower().startswith("active") for r in rows)]
+        pw = [float(r[3]) for r in rows if r[3].replace(".", "", 1).isdigit()]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(rows[0][2]), "reasons": reasons,
+                "samples": len(rows), "power_w_max": max(pw) if pw else None}
+
+
+# ---------------------------------------------------------------------------------------------
+# the reference's CPU implementation on a bounded sample
+# ---------------------------------------------------------------------------------------------
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def cpu_sample(w, pos, box_lammps, box_internal, types, target_s=12.0, threads=None):
+    """Time the reference CPU path on the first frames of the same window.  Returns a dict."""
+    import oracle
+    threads = threads or host_threads()
+    ref = oracle.load_ref()
+    n2 = float(w.natoms) ** 2
+    fmt_tri = w.triclinic
+
+    def run(lags, origins):
+        nfr = origins + lags
+        p = np.ascontiguousarray(pos[:nfr])
+        if ref is not None:
+            fmt = ref.BoxFormat.LammpsTriclinic if fmt_tri else ref.BoxFormat.LammpsOrtho
+            tr = ref.Trajectory(p, np.zeros_like(p), types, np.ascontiguousarray(box_lammps[:nfr]), fmt, True, False)
+            g = ref.Gofrt(tr, w.rmin, w.rmax, w.nbin, lags, threads, 1, 1, False)
+            g.reset(origins)
+            t0 = time.perf_counter()
+            g.calculate(0)
+            dt = time.perf_counter() - t0
+        else:
+            pw = oracle.pbc_wrap(p, box_internal[:nfr])
+            t0 = time.perf_counter()
+            oracle.counts(pw, box_internal[:nfr], types, w.rmin, w.rmax, w.nbin, lags, origins, nthreads=threads,
+                          ntypes=w.ntypes)
+            dt = time.perf_counter() - t0
+        return lags * origins * n2 / dt, dt
+
+    # calibrate on one lag x two origins, then size the sample for ~target_s
+    rate, dt = run(1, 2)
+    jobs = int(max(2, min(4096, target_s * rate / n2)))
+    lags = max(1, min(4, jobs // 2, pos.shape[0] // 2))
+    origins = max(1, min(jobs // lags, pos.shape[0] - lags))
+    rate, dt = run(lags, origins)
+    return {
+        "value": rate, "unit": UNIT, "cores": threads,
+        "kind": "reference" if ref is not None else "port",
+        "sample": "%s: first %d frames, lags 0-%d x %d origins = %d (lag,origin) jobs of %d^2 pairs, %.1f s, %d threads"
+                  % (w.name.split()[0], lags + origins, lags - 1, origins, lags * origins, w.natoms, dt, threads),
+    }
+
+
+# ---------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--workload", default=None, help="C2 (default at N=1), C3, C4")
+    ap.add_argument("--quick", action="store_true", help="tiny block (smoke/profiling), not a bench number")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--options", type=int, default=0)
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    name = args.workload or "C2"
+    w, nts, primo = block_spec(name, args.quick)
+    leff = min(nts, w.tmax) if w.tmax else nts
+    nframes = primo + (nts - 1) // w.skip * w.skip + (leff - 1) // w.every * w.every + 1
+    njobs = jobs_of(nts, leff, w.skip, w.every)
+    pairs_per_step = njobs * w.natoms * w.natoms
+    config = {
+        "workload": w.name, "natoms": w.natoms, "frames_in_window": nframes, "ntypes": w.ntypes,
+        "triclinic": w.triclinic, "rmin": w.rmin, "rmax": w.rmax, "nbin": w.nbin, "lags": leff, "skip": w.skip,
+        "every": w.every, "origins": (nts + w.skip - 1) // w.skip, "jobs_per_step": njobs,
+        "pair_evals_per_step": pairs_per_step, "parallelism": "work units sharded over %d GPU(s), 1 NCCL all-reduce/step" % world,
+        "l2": "window (%.0f MB) larger than L2; every step re-reads it from HBM" % (nframes * w.natoms * 24 / 1e6),
+    }
+
+    # ------------------------------------------------------------------ reference arm
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        pos, box_lammps, box_internal, types = make_window(w, min(nframes, 80))
+        vals = []
+        res = None
+        for k in range(args.warmup + args.steps):
+            res = cpu_sample(w, pos, box_lammps, box_internal, types, target_s=8.0)
+            if k >= args.warmup:
+                vals.append(res["value"])
+            if k == 0 and args.warmup > 1:
+                # the CPU path has no warm-up effects worth three full samples; keep the run short
+                vals_warm = res["value"]
+        v = float(np.mean(vals))
+        res["value"] = v
+        line = {
+            "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": None, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": config, "impl": "reference", "cpu_baseline": res,
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        }
+        print(json.dumps(line), flush=True)
+        return 0
+
+    # ------------------------------------------------------------------ native arm
+    from analisi_b200 import cabi
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    ctx = cabi.Context([local_rank])
+    if world > 1:
+        import torch
+        idt = torch.zeros(cabi.COMM_ID_BYTES, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            idt.copy_(torch.frombuffer(bytearray(cabi.Context.unique_id()), dtype=torch.uint8))
+        dist.broadcast(idt, 0)
+        ctx.join(bytes(idt.cpu().numpy().tobytes()), rank, world)
+
+    pos, box_lammps, box_internal, types = make_window(w, nframes)
+    # wrap=True, as the reference callers do (analisi/main.cpp:558): the wrap runs on the GPU
+    pinned = cabi.PinnedArray(pos.shape)
+    pinned.array[...] = pos
+    ctx.pbc_wrap(pinned.array, box_internal)
+    hpos = pinned.array
+
+    tr = cabi.DeviceTrajectory(ctx, w.natoms, box_internal.shape[1], types, w.ntypes, nframes)
+    plan = cabi.Plan(tr, w.rmin, w.rmax, w.nbin)
+
+    def barrier():
+        if dist is not None:
+            import torch
+            torch.cuda.synchronize()
+            dist.barrier()
+
+    def maxrank(x):
+        if dist is None:
+            return x
+        import torch
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # roofline denominator, measured in this run
+    peak = ctx.fp64_peak(1.0)
+    log("[bench] rank %d: FP64 issue rate %.3e DFMA/s" % (rank, peak))
+
+    tr.upload(0, hpos, box_internal)
+    counts0 = None
+    for k in range(args.warmup):
+        counts0, st = plan.block(primo, nts, leff, w.skip, w.every, options=args.options)
+        log("[bench] warmup %d: %.1f ms (kernel %.1f ms), fast jobs %d/%d" % (k, st["total_ms"], st["kernel_ms"], st["jobs_fast"], st["jobs"]))
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.3)
+    # ---- device-resident timing ----
+    barrier()
+    t0 = time.time()
+    dev_ms = 0.0
+    ker_ms = 0.0
+    launches = 0
+    for k in range(args.steps):
+        counts, st = plan.block(primo, nts, leff, w.skip, w.every, options=args.options)
+        dev_ms += st["total_ms"]
+        ker_ms += st["kernel_ms"]
+        launches += st["launches"]
+    barrier()
+    t1 = time.time()
+    wall_ms = (t1 - t0) * 1e3
+    dev_ms = maxrank(dev_ms)
+    ker_ms = maxrank(ker_ms)
+    clocks = sampler.stop(t0, t1)
+    if counts0 is not None and not np.array_equal(counts, counts0):
+        raise SystemExit("non-deterministic counts between steps")
+
+    # ---- end to end: host buffers in, counts out ----
+    barrier()
+    e0 = time.time()
+    for k in range(args.steps):
+        tr.upload(0, hpos, box_internal)
+        counts_e, st = plan.block(primo, nts, leff, w.skip, w.every, options=args.options)
+    barrier()
+    e2e_ms = maxrank((time.time() - e0) * 1e3)
+    if not np.array_equal(counts_e, counts):
+        raise SystemExit("e2e counts differ from resident counts")
+
+    value = args.steps * pairs_per_step / (dev_ms * 1e-3)
+    e2e_value = args.steps * pairs_per_step / (e2e_ms * 1e-3)
+    ops = 19 if w.triclinic else 16
+    kernel_rate = args.steps * pairs_per_step / (ker_ms * 1e-3) / world   # per GPU
+    achieved = kernel_rate * ops
+    in_range = float(counts.sum()) / float(pairs_per_step)
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic", "config": config,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(hpos.nbytes + box_internal.nbytes),
+                "d2h_bytes_per_step": int(counts.nbytes), "ms_per_step": e2e_ms / args.steps},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": {
+            "bound": "fp64", "achieved": achieved / 1e12, "peak": peak / 1e12, "unit": "T FP64-op/s per GPU",
+            "frac": achieved / peak, "traffic": None,
+            "ops_per_pair_eval": ops, "kernel_ms_per_step": ker_ms / args.steps,
+            "pair_evals_per_s_per_gpu": kernel_rate, "in_range_fraction": in_range,
+            "peak_source": "DFMA-chain microbenchmark in this run (agofrt_fp64_peak); MEASURED_PEAKS.json has no FP64 entry",
+        },
+        "wall_ms_per_step": wall_ms / args.steps,
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            line["cpu_baseline"] = cpu_sample(w, pos, box_lammps, box_internal, types)
+        except Exception as e:  # the baseline is a report, never a reason to lose the GPU number
+            line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": host_threads(), "kind": "unavailable",
+                                    "sample": "failed: %r" % (e,)}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    plan.close()
+    tr.close()
+    ctx.close()
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,166 @@
+/* agofrt.h -- C ABI of libagofrt.so: B200-native (sm_100a) g(r,t) for rikigigi/analisi.
+ *
+ * This is the drop-in boundary.  The only callers are the host C++ classes of this repository that
+ * mirror the reference's API (include/analisi/...: Gofrt, BlockAverageG, Trajectory,
+ * Trajectory_numpy) and, for tests and bench.py, a ctypes binding.  Plain pointers and sizes; no
+ * C++ or torch types; nothing throws across it.  There is NO CPU fallback behind it: every entry
+ * point that needs a GPU returns AGOFRT_ERR_CUDA when none is usable.
+ *
+ * What each group replaces in the reference (paths relative to the reference tree):
+ *
+ *   agofrt_traj_*      the window buffers of BaseTrajectory (lib/include/basetrajectory.h:310-323)
+ *                      as filled by Trajectory::set_access_at (lib/src/trajectory.cpp:450-690) or
+ *                      the Trajectory_numpy ctor (lib/src/trajectory_numpy.cpp:7-199): positions
+ *                      [frame][atom][3] float64, one internal box row per frame
+ *                      [xlo,ylo,zlo,lx/2,ly/2,lz/2(,xy,xz,yz)], dense type ids
+ *                      (lib/src/basetrajectory.cpp:51-89).
+ *   agofrt_plan_*      the Gofrt constructor state: rmin, rmax, nbin and the derived dr, rmin2,
+ *                      rmax2 (lib/src/gofrt.cpp:22-31).
+ *   agofrt_block       one CalculateMultiThread::calculate(primo) of a Gofrt after reset(ntimesteps)
+ *                      (lib/include/calculatemultithread.h:106-162 driving
+ *                      Gofrt::calc_init / calc_single_th / calc_end, lib/src/gofrt.cpp:73-155, which
+ *                      call BaseTrajectory::d2_minImage, lib/include/basetrajectory.h:168-268).
+ *                      It returns INTEGER bin counts; the host shim multiplies by `incr`
+ *                      (lib/src/gofrt.cpp:91-92).
+ *   agofrt_comm_*      the block exchange of Mp::send_to_root / recv_root
+ *                      (lib/include/mp.h:35-41, used by lib/include/blockaverage.h:146-186),
+ *                      replaced by one NCCL all-reduce of the integer histograms.
+ *   agofrt_pbc_wrap    BaseTrajectory::pbc_wrap<TRICLINIC> (lib/include/basetrajectory.h:145-161).
+ *
+ * Conventions: every function returns 0 (AGOFRT_OK) or a negative agofrt_status; the message of the
+ * last failure on the calling thread is agofrt_last_error().  Host pointers passed in are only read
+ * (or written, for outputs) during the call; no ownership is transferred.  All calls on one context
+ * must come from one host thread at a time.
+ */
+#ifndef AGOFRT_H
+#define AGOFRT_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define AGOFRT_API __attribute__((visibility("default")))
+#else
+#define AGOFRT_API
+#endif
+
+typedef enum {
+    AGOFRT_OK = 0,
+    AGOFRT_ERR_ARG = -1,       /* invalid argument                                              */
+    AGOFRT_ERR_CUDA = -2,      /* CUDA runtime / driver failure, or no usable device            */
+    AGOFRT_ERR_WINDOW = -3,    /* the block needs frames that are not in the uploaded window    */
+    AGOFRT_ERR_NCCL = -4,      /* NCCL missing or failed                                        */
+    AGOFRT_ERR_NONFINITE = -5, /* an infinite coordinate or box entry (the reference would spin) */
+    AGOFRT_ERR_TOO_LARGE = -6, /* histogram does not fit the shared-memory budget               */
+    AGOFRT_ERR_INTERNAL = -7
+} agofrt_status;
+
+typedef struct agofrt_ctx agofrt_ctx;    /* a set of GPUs of this process (+ optional peers)   */
+typedef struct agofrt_traj agofrt_traj;  /* device-resident trajectory window                  */
+typedef struct agofrt_plan agofrt_plan;  /* Gofrt parameters + threshold table on the devices  */
+
+/* ---- library ------------------------------------------------------------------------------- */
+AGOFRT_API const char *agofrt_version(void);
+AGOFRT_API const char *agofrt_last_error(void);
+AGOFRT_API int agofrt_device_count(int *count);
+
+/* Pinned host memory for window buffers (the reference uses fftw_malloc only as an aligned
+ * allocator, lib/src/trajectory.cpp:362-371). */
+AGOFRT_API int agofrt_host_alloc(void **ptr, size_t bytes);
+AGOFRT_API int agofrt_host_free(void *ptr);
+
+/* ---- context ------------------------------------------------------------------------------- */
+/* devices == NULL, ndev == 0: device 0 only.  ndev == -1: every visible device. */
+AGOFRT_API int agofrt_ctx_create(agofrt_ctx **ctx, const int *devices, int ndev);
+AGOFRT_API int agofrt_ctx_destroy(agofrt_ctx *ctx);
+AGOFRT_API int agofrt_ctx_ndev(const agofrt_ctx *ctx);
+
+#define AGOFRT_COMM_ID_BYTES 128
+/* Multi-process operation (one process per GPU, e.g. under torchrun): rank 0 calls
+ * agofrt_comm_unique_id, the bytes are broadcast by whatever launcher plumbing exists, and every
+ * process calls agofrt_comm_join with the rank of its first device and the total device count.
+ * Afterwards agofrt_block shards its work over all `world` devices and all-reduces the counts.
+ * A context with several local devices and no join is its own single-process communicator. */
+AGOFRT_API int agofrt_comm_unique_id(char id[AGOFRT_COMM_ID_BYTES]);
+AGOFRT_API int agofrt_comm_join(agofrt_ctx *ctx, const char id[AGOFRT_COMM_ID_BYTES], int first_rank, int world);
+/* Shard geometry without any communicator (tests; "weak scaling" replicas): the context then
+ * computes only its share of the work units and returns PARTIAL counts. */
+AGOFRT_API int agofrt_ctx_set_shard(agofrt_ctx *ctx, int first_rank, int world);
+
+/* The contiguous share [begin,end) of `units` equal work units that device `rank` of `world`
+ * computes (pure host arithmetic; agofrt_block uses exactly this). */
+AGOFRT_API int agofrt_shard_range(uint64_t units, int rank, int world, uint64_t *begin, uint64_t *end);
+
+/* ---- trajectory window --------------------------------------------------------------------- */
+/* type_id[natoms] are dense ids in [0,ntypes) (BaseTrajectory::get_type).  box_stride is 6
+ * (orthorhombic) or 9 (triclinic, BaseTrajectory::is_triclinic).  max_frames bounds the windows
+ * that will be uploaded (Trajectory::set_data_access_block_size). */
+AGOFRT_API int agofrt_traj_create(agofrt_traj **traj, agofrt_ctx *ctx, size_t natoms, int box_stride,
+                                  const int *type_id, int ntypes, size_t max_frames);
+AGOFRT_API int agofrt_traj_destroy(agofrt_traj *traj);
+/* Replace the device window by frames [first_frame, first_frame+nframes): pos_aos is
+ * [nframes][natoms][3], box_internal [nframes][box_stride].  The device keeps the atoms in a
+ * type-major, spatially sorted, padded SoA layout (a permutation: counts do not depend on it). */
+AGOFRT_API int agofrt_traj_upload(agofrt_traj *traj, size_t first_frame, size_t nframes,
+                                  const double *pos_aos, const double *box_internal);
+/* Read one frame back in the caller's atom order (tests: the layout round-trips bit-exactly). */
+AGOFRT_API int agofrt_traj_download_frame(agofrt_traj *traj, size_t frame, double *pos_aos);
+/* In-place BaseTrajectory::pbc_wrap on a host buffer through the GPU (frames with their own box
+ * rows).  Same arithmetic as the reference: x-=l_half; minImage; x+=l_half. */
+AGOFRT_API int agofrt_pbc_wrap(agofrt_ctx *ctx, double *pos_aos, size_t nframes, size_t natoms,
+                               const double *box_internal, int box_stride);
+/* All N^2 (dx,dy,dz,d2) of BaseTrajectory::d2_minImage(i,j,frame_i,frame_j,x) for small N
+ * (the probe tests/src/test_trajectory.cpp:21-41 dumps); out is [natoms][natoms][4]. */
+AGOFRT_API int agofrt_traj_d2_all(agofrt_traj *traj, size_t frame_i, size_t frame_j, double *out);
+
+/* ---- plan ---------------------------------------------------------------------------------- */
+AGOFRT_API int agofrt_plan_create(agofrt_plan **plan, agofrt_traj *traj, double rmin, double rmax,
+                                  unsigned nbin);
+AGOFRT_API int agofrt_plan_destroy(agofrt_plan *plan);
+/* thresholds[nbin+1]: thresholds[k] = the smallest d2 (>=0) whose reference bin index
+ * (int)floorf((sqrt(d2)-rmin)/dr) is >= k (+inf if none). */
+AGOFRT_API int agofrt_plan_thresholds(const agofrt_plan *plan, double *thresholds);
+
+enum {
+    AGOFRT_OPT_DEFAULT = 0,
+    AGOFRT_OPT_EDGES = 1,          /* also count the pairs within 1 ulp of a bin edge            */
+    AGOFRT_OPT_FORCE_GENERAL = 2,  /* never take the single-pass minimum-image kernel            */
+    AGOFRT_OPT_NO_AGGREGATE = 4,   /* plain shared atomics instead of __match_any_sync merging   */
+    AGOFRT_OPT_AGGREGATE = 8       /* force warp-aggregated shared atomics                       */
+};
+
+typedef struct {
+    double kernel_ms;          /* device time of the pair kernels, CUDA events on their stream, max over local devices */
+    double total_ms;           /* device time of the whole call (zeroing, kernels, all-reduce, read-back) */
+    uint64_t pair_evals;       /* pair evaluations this context performed (N^2 per (lag, origin))  */
+    uint64_t pair_evals_total; /* ... the whole job over all shards                                */
+    uint64_t jobs;             /* (lag, origin) pairs in the whole job                             */
+    uint64_t jobs_fast;        /* ... of which proven single-pass minimum image                    */
+    uint32_t launches;         /* kernels launched by this call on this context                    */
+    uint32_t ndev_local;
+    uint32_t world;
+    uint32_t reserved;
+} agofrt_stats;
+
+/* counts_out [leff][ntypes*(ntypes+1)][nbin] (host, uint64): the number of ordered pairs (i,j)
+ * per lag, type-pair slot (Gofrt::get_itype; +P for i==j) and bin, summed over the origins
+ * primo, primo+skip, ... < primo+ntimesteps and over the lags 0, every, ... < leff.
+ * edge_pairs_out (optional): pairs whose d2 is a bin threshold or the double just below one.
+ * stats (optional). */
+AGOFRT_API int agofrt_block(agofrt_plan *plan, size_t primo, unsigned ntimesteps, unsigned leff,
+                            unsigned skip, unsigned every, unsigned options, uint64_t *counts_out,
+                            uint64_t *edge_pairs_out, agofrt_stats *stats);
+
+/* ---- measurement --------------------------------------------------------------------------- */
+/* Sustained FP64 FMA issue rate of one device (DFMA chains, CUDA events): the roofline
+ * denominator of SURVEY.md section 8(d).  Runs for about `seconds`. */
+AGOFRT_API int agofrt_fp64_peak(agofrt_ctx *ctx, int local_device, double seconds, double *dfma_per_second);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AGOFRT_H */

@@ -235,9 +235,10 @@ static int setup(worker_t *w, const gofrt_oracle_traj *tr, const gofrt_oracle_pa
     w->rmin2 = p->rmin * p->rmin;
     /* gofrt.cpp:81-83 */
     if ((size_t)w->leff + ntimesteps + primo > tr->total_frames + 1) return GOFRT_ORACLE_TOO_SHORT;
-    /* the loop reads frames up to primo + (ntimesteps-1) + (leff-1) from the loaded window */
-    if (ntimesteps > 0) {
-        const size_t last = primo + (ntimesteps - 1) + (w->leff - 1);
+    /* the loop reads frames up to primo + (last origin) + (last lag) from the loaded window */
+    if (ntimesteps > 0 && w->leff > 0) {
+        const size_t last = primo + (size_t)((ntimesteps - 1) / w->skip) * w->skip +
+                            (size_t)((w->leff - 1) / w->every) * w->every;
         if (primo < tr->first_frame || last >= tr->first_frame + tr->nframes) return GOFRT_ORACLE_BAD_ARG;
     }
     /* gofrt.cpp:91-92 */

@@ -1,0 +1,180 @@
+"""Generate the committed fixtures under tests/golden/ (run HERE, where /root/reference exists).
+
+    python tests/golden/make_golden.py
+
+Sources of truth, in this order:
+  * the reference's own golden files for the g(r,t) path:
+      tests/test_gofrt/test_gofr.csv, tests/test_notebook/test_gofr.csv,
+      tests/cpp_regression_data/{min_image,pbc_1,pbc_2}
+    cut down to the frames they really use so the fixtures stay small;
+  * the UNMODIFIED reference compiled by oracle/Makefile (oracle/_ref/analisi_ref*.so) for what no
+    golden file pins: triclinic minimum image, every>1, ragged skip, NPT boxes.
+The GPU box has no /root/reference: the -m gpu tests read only these .npz files.
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+REF = os.environ.get("ANALISI_REFERENCE", "/root/reference")
+
+import oracle  # noqa: E402
+from analisi_b200 import synth  # noqa: E402
+
+
+def ref_module():
+    oracle.oracle.build_ref(REF)
+    m = oracle.load_ref()
+    if m is None:
+        raise SystemExit("oracle/_ref could not be built/imported")
+    return m
+
+
+def read_csv_column(path):
+    return np.loadtxt(path, delimiter=",", skiprows=1, usecols=1)
+
+
+def gofr_numpy(m):
+    """tests/test_gofrt.py: Gofrt(traj,0,3.8,200,10,4,10,False,1); reset(700); calculate(0)
+    on positions.npy/cells.npy (CellVectors, wrap=False), 3 types 40/8/8."""
+    pos = np.load(REF + "/tests/data/positions.npy")
+    cells = np.load(REF + "/tests/data/cells.npy")
+    types = np.zeros(pos.shape[1], dtype=np.int32)
+    types[-16:-8] = 1
+    types[-8:] = 2
+    csv = read_csv_column(REF + "/tests/test_gofrt/test_gofr.csv").reshape(10, 12, 200)
+    nfr = 700  # origins 0,10,..,690 and lags 0..9 touch frames 0..699
+    vel = np.zeros_like(pos[:nfr])
+    traj = m.Trajectory(np.ascontiguousarray(pos[:nfr]), vel, types, np.ascontiguousarray(cells[:nfr]),
+                        m.BoxFormat.CellVectors, False, False)
+    box_internal = traj.get_box_copy()
+    assert np.array_equal(traj.get_positions_copy(), pos[:nfr])  # diagonal cell: no rotation
+    incr = 1.0 / 70
+    counts = np.rint(csv / incr).astype(np.uint64)
+    assert np.abs(counts * incr - csv).max() < 1e-9
+    np.savez_compressed(os.path.join(HERE, "gofr_numpy.npz"), pos=pos[:nfr], box_internal=box_internal,
+                        types=types, csv=csv, counts=counts,
+                        params=np.array([0.0, 3.8, 200, 10, 10, 700]))  # rmin rmax nbin tmax skip ntimesteps
+
+
+def gofr_notebook(m):
+    """notebooks/calc_inspector.ipynb via tests/test_notebook.py: Traj('lammps.bin'), wrap on,
+    Gofrt_lammps(traj,0.5,3.8,100,1,4,10,False,1); reset(999); calculate(0).  Only lag 0 and the
+    origins 0,10,..,990 are touched, so the fixture keeps those 100 frames (skip becomes 1)."""
+    csv = read_csv_column(REF + "/tests/test_notebook/test_gofr.csv")
+    tr = m.Traj(REF + "/tests/data/lammps.bin")
+    tr.setWrapPbc(False)
+    tr.setAccessWindowSize(1000)
+    tr.setAccessStart(0)
+    raw = tr.get_positions_copy()[0:1000:10].copy()
+    box = tr.get_box_copy()[0:1000:10].copy()
+    types = tr.get_type_ids()
+    tw = m.Traj(REF + "/tests/data/lammps.bin")
+    tw.setWrapPbc(True)
+    tw.setAccessWindowSize(1000)
+    tw.setAccessStart(0)
+    wrapped = tw.get_positions_copy()[0:1000:10].copy()
+    ntypes = int(tw.get_ntypes())
+    csv = csv.reshape(1, ntypes * (ntypes + 1), 100)
+    incr = 1.0 / 99
+    counts = np.rint(csv / incr).astype(np.uint64)
+    assert np.abs(counts * incr - csv).max() < 1e-9
+    np.savez_compressed(os.path.join(HERE, "gofr_notebook.npz"), pos_unwrapped=raw, pos_wrapped=wrapped,
+                        box_internal=box, types=types, csv=csv, counts=counts,
+                        params=np.array([0.5, 3.8, 100, 1, 1, 100]))
+
+
+def min_image_and_pbc(m):
+    """tests/src/test_trajectory.cpp:21-59: all 56^2 d2_minImage of lammps.bin frame 0, and the
+    wrapped first frames of lammps.bin / lammps2020.bin."""
+    out = {}
+    for tag, fname, gold in (("1", "lammps.bin", "pbc_1"), ("2", "lammps2020.bin", "pbc_2")):
+        tr = m.Traj(REF + "/tests/data/" + fname)
+        tr.setWrapPbc(False)
+        tr.setAccessWindowSize(1)
+        tr.setAccessStart(0)
+        pos = tr.get_positions_copy()[0].copy()
+        box = tr.get_box_copy()[0].copy()
+        g = np.fromfile(REF + "/tests/cpp_regression_data/" + gold, dtype=np.float64).reshape(-1, 3)
+        assert g.shape == pos.shape
+        out["pos_" + tag] = pos
+        out["box_" + tag] = box
+        out["pbc_" + tag] = g
+        if tag == "1":
+            tw = m.Traj(REF + "/tests/data/" + fname)
+            tw.setWrapPbc(True)
+            tw.setAccessWindowSize(1)
+            tw.setAccessStart(0)
+            out["pos_wrapped_1"] = tw.get_positions_copy()[0].copy()
+            mi = np.fromfile(REF + "/tests/cpp_regression_data/min_image", dtype=np.float64)
+            n = pos.shape[0]
+            out["min_image_1"] = mi.reshape(n, n, 4)
+    np.savez_compressed(os.path.join(HERE, "min_image_pbc.npz"), **out)
+
+
+def ref_counts(m, pos, box_lammps, types, fmt, wrap, rmin, rmax, nbin, tmax, skip, every, ntimesteps, primo,
+               nthreads=3):
+    vel = np.zeros_like(pos)
+    tr = m.Trajectory(pos, vel, types, box_lammps, fmt, wrap, False)
+    g = m.Gofrt(tr, rmin, rmax, nbin, tmax, nthreads, skip, every, False)
+    g.reset(ntimesteps)
+    g.calculate(primo)
+    v = np.array(g, copy=True)
+    sk = skip or 1
+    incr = 1.0 / (ntimesteps // sk) if ntimesteps // sk > 0 else 1.0
+    counts = np.rint(v / incr).astype(np.uint64)
+    assert np.abs(counts * incr - v).max() < 1e-9 * max(1.0, v.max())
+    return counts, v, tr.get_positions_copy(), tr.get_box_copy(), tr.get_type_ids()
+
+
+def live_reference_cases(m):
+    """What no reference golden pins, taken from the compiled reference itself."""
+    cases = {}
+
+    def add(name, seed, cells, ntypes, triclinic, nframes, npt, wrap, gofrt, tilt=(0.15, -0.10, 0.08),
+            type_rule="parity", a=1.1):
+        pos, box, types = synth.small_case(seed, cells, a, ntypes, triclinic, nframes, type_rule, tilt, npt)
+        raw_types = (types * 3 + 2).astype(np.int32)  # non-dense raw ids exercise the compaction
+        fmt = m.BoxFormat.LammpsTriclinic if triclinic else m.BoxFormat.LammpsOrtho
+        rmin, rmax, nbin, tmax, skip, every, ntimesteps, primo = gofrt
+        counts, v, rpos, rbox, rtypes = ref_counts(m, pos, box, raw_types, fmt, wrap, rmin, rmax, nbin, tmax, skip,
+                                                   every, ntimesteps, primo)
+        cases[name] = dict(pos_in=pos, box_lammps=box, raw_types=raw_types, wrap=wrap, pos_ref=rpos, box_internal=rbox,
+                           type_ids=rtypes, counts=counts, vdata=v,
+                           params=np.array([rmin, rmax, nbin, tmax, skip, every, ntimesteps, primo], dtype=np.float64))
+
+    # triclinic, wrapped, two types, a few lags
+    add("tri_wrap", 11, (6, 5, 4), 2, True, 14, False, True, (0.0, 2.6, 40, 5, 2, 1, 8, 1))
+    # triclinic NPT (box changes per frame, lag pairs use the box of the origin frame)
+    add("tri_npt", 12, (5, 5, 4), 3, True, 12, True, True, (0.3, 2.4, 25, 4, 3, 2, 7, 0))
+    # orthorhombic, UNWRAPPED input drifting out of the box (many images per pair)
+    add("ortho_unwrapped", 13, (5, 4, 4), 2, False, 10, False, False, (0.0, 2.0, 30, 3, 1, 1, 6, 2), a=0.9)
+    # big tilt: |xy|+|xz| > lx/2, the x loop can need two images even for wrapped input
+    add("tri_bigtilt", 14, (4, 4, 4), 1, True, 8, False, True, (0.0, 2.2, 32, 3, 1, 1, 5, 0),
+        tilt=(0.45, -0.40, 0.35))
+    # ragged: skip does not divide ntimesteps, every does not divide leff, nbin small
+    add("ragged", 15, (4, 4, 3), 2, True, 16, False, True, (0.2, 2.0, 7, 6, 4, 4, 9, 1))
+    flat = {}
+    for name, d in cases.items():
+        for k, v in d.items():
+            flat[name + "/" + k] = np.asarray(v)
+    np.savez_compressed(os.path.join(HERE, "live_reference.npz"), **flat)
+
+
+def main():
+    m = ref_module()
+    gofr_numpy(m)
+    gofr_notebook(m)
+    min_image_and_pbc(m)
+    live_reference_cases(m)
+    for f in sorted(os.listdir(HERE)):
+        if f.endswith(".npz"):
+            print("%-24s %8d bytes" % (f, os.path.getsize(os.path.join(HERE, f))))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,62 @@
+"""CPU: the C-ABI library builds, loads, and exports every symbol include/agofrt.h declares.
+No compute calls (there is no GPU here); the no-GPU behaviour must be a loud error, not a fallback."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+from analisi_b200 import cabi
+from conftest import ROOT
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "agofrt.h")).read()
+    return sorted(set(re.findall(r"AGOFRT_API\s+[\w\s\*]+?\b(agofrt_\w+)\s*\(", text)))
+
+
+def test_header_and_binding_agree():
+    assert declared_symbols() == sorted(cabi.SYMBOLS)
+
+
+def test_library_exports_every_declared_symbol():
+    L = cabi.lib()
+    for name in declared_symbols():
+        assert hasattr(L, name), name
+    assert b"sm_100a" in L.agofrt_version()
+
+
+def test_shard_range_partitions():
+    for units in (0, 1, 7, 1000, 12864 * 196 * 3, 2 ** 40 + 12345):
+        for world in (1, 2, 3, 8):
+            prev = 0
+            for r in range(world):
+                b, e = cabi.shard_range(units, r, world)
+                assert b == prev and e >= b
+                prev = e
+            assert prev == units
+            sizes = [cabi.shard_range(units, r, world) for r in range(world)]
+            lens = [e - b for b, e in sizes]
+            assert max(lens) - min(lens) <= 1
+    with pytest.raises(cabi.AgofrtError):
+        cabi.shard_range(10, 2, 2)
+
+
+def test_no_gpu_is_a_loud_error():
+    if cabi.device_count() > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(cabi.AgofrtError) as e:
+        cabi.Context()
+    assert e.value.code == cabi.ERR_CUDA
+    assert "no CPU path" in str(e.value)
+
+
+def test_host_side_gofrt_arithmetic_matches_oracle():
+    import oracle
+    for nts, lmax in ((700, 10), (5, 10), (9, 0), (0, 3)):
+        assert cabi.gofrt_leff(nts, lmax) == oracle.leff(nts, lmax)
+    for total, n_b, lmax in ((200, 20, 10), (200, 20, 1), (7958, 20, 0), (1000, 1, 201)):
+        assert cabi.gofrt_nextra(total, n_b, lmax) == oracle.nextra(total, n_b, lmax)
+    assert cabi.gofrt_incr(700, 10) == 1.0 / 70
+    assert cabi.gofrt_incr(5, 10) == 1.0
+    assert cabi.gofrt_incr(1899, 30) == 1.0 / 63

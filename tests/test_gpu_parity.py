@@ -1,0 +1,230 @@
+"""GPU: the CUDA path (through the C ABI of libagofrt.so) against the oracle and the committed
+golden fixtures.  Integer bin counts must be bit-exact; count*incr must equal the reference's
+float sums within 1e-12 relative (stated in each test)."""
+import numpy as np
+import pytest
+
+import oracle
+from analisi_b200 import cabi, synth
+from conftest import LIVE_CASES, live_case, load_golden
+
+pytestmark = pytest.mark.gpu
+
+REL_TOL = 1e-12   # north_star: normalised g(r,t) within 1e-12 relative
+
+
+def gpu_counts(ctx, pos, box_internal, ids, ntypes, rmin, rmax, nbin, tmax, nts, primo=0, skip=1, every=1,
+               options=0, edges=False, first_frame=0):
+    tr = cabi.DeviceTrajectory(ctx, pos.shape[1], box_internal.shape[1], ids, ntypes, max(1, pos.shape[0]))
+    tr.upload(first_frame, np.ascontiguousarray(pos), box_internal)
+    plan = cabi.Plan(tr, rmin, rmax, nbin)
+    leff = cabi.gofrt_leff(nts, tmax)
+    out = plan.block(primo, nts, leff, skip, every, options=options, edges=edges)
+    plan.close()
+    tr.close()
+    return out
+
+
+def test_gofr_numpy_golden(ctx):
+    """reference tests/test_gofrt.py: ortho, UNWRAPPED input (many images per pair), 3 types, 10 lags."""
+    z = load_golden("gofr_numpy.npz")
+    rmin, rmax, nbin, tmax, skip, nts = z["params"]
+    c, st = gpu_counts(ctx, z["pos"], z["box_internal"], z["types"], 3, rmin, rmax, int(nbin), int(tmax), int(nts),
+                       skip=int(skip))
+    assert np.array_equal(c, z["counts"])
+    incr = cabi.gofrt_incr(int(nts), int(skip))
+    v = c * incr
+    nz = z["csv"] != 0
+    assert np.abs(v[nz] - z["csv"][nz]).max() <= 1e-11  # the CSV itself carries the reference's 4-thread float sums
+    assert (v[~nz] == 0).all()
+    assert st["pair_evals_total"] == 10 * 70 * 56 * 56
+
+
+def test_gofr_notebook_golden(ctx):
+    """reference tests/test_notebook.py: mmap trajectory, wrap on; the wrap itself runs on the GPU."""
+    z = load_golden("gofr_notebook.npz")
+    pos = z["pos_unwrapped"].copy()
+    ctx.pbc_wrap(pos, z["box_internal"])
+    assert np.array_equal(pos, z["pos_wrapped"])
+    rmin, rmax, nbin, tmax, skip, nts = z["params"]
+    nt = int(z["types"].max()) + 1
+    c, st = gpu_counts(ctx, pos, z["box_internal"], z["types"], nt, rmin, rmax, int(nbin), int(tmax), int(nts),
+                       skip=int(skip))
+    assert np.array_equal(c, z["counts"])
+    assert st["jobs_fast"] == st["jobs"]  # wrapped orthorhombic input: single-pass minimum image proven
+
+
+def test_min_image_and_pbc_golden(ctx):
+    """reference tests/src/test_trajectory.cpp:21-59 (tolerance 1e-10 there; bit-exact vs the oracle here)."""
+    z = load_golden("min_image_pbc.npz")
+    for tag in ("1", "2"):
+        p = z["pos_" + tag][None].copy()
+        ctx.pbc_wrap(p, z["box_" + tag][None])
+        g = z["pbc_" + tag]
+        assert np.abs(p[0] - g).max() <= 1e-10 * max(1.0, np.abs(g).max())
+        assert np.array_equal(p, oracle.pbc_wrap(z["pos_" + tag][None], z["box_" + tag][None]))
+    pw = z["pos_wrapped_1"]
+    n = pw.shape[0]
+    tr = cabi.DeviceTrajectory(ctx, n, 6, np.zeros(n, np.int32), 1, 1)
+    tr.upload(0, pw[None].copy(), z["box_1"][None])
+    d = tr.d2_all(0, 0)
+    assert np.array_equal(tr.download_frame(0), pw)
+    tr.close()
+    g = z["min_image_1"]
+    assert np.abs(d - g).max() <= 1e-10 * max(1.0, np.abs(g).max())
+    assert np.array_equal(d, oracle.d2_all(pw, pw, z["box_1"]))
+
+
+@pytest.mark.parametrize("name", LIVE_CASES)
+@pytest.mark.parametrize("options", [0, cabi.OPT_FORCE_GENERAL, cabi.OPT_AGGREGATE])
+def test_live_reference_cases(ctx, name, options):
+    """Fixtures computed by the compiled reference: triclinic, NPT, unwrapped, big tilt, ragged loops."""
+    d = live_case(name)
+    rmin, rmax, nbin, tmax, skip, every, nts, primo = d["params"]
+    ids, nt = d["type_ids"], int(d["type_ids"].max()) + 1
+    pos = d["pos_in"].copy()
+    if bool(d["wrap"]):
+        ctx.pbc_wrap(pos, d["box_internal"])
+    assert np.array_equal(pos, d["pos_ref"])
+    c, st = gpu_counts(ctx, pos, d["box_internal"], ids, nt, rmin, rmax, int(nbin), int(tmax), int(nts),
+                       primo=int(primo), skip=int(skip), every=int(every), options=options)
+    assert np.array_equal(c, d["counts"])
+    incr = cabi.gofrt_incr(int(nts), int(skip))
+    v, ref = c * incr, d["vdata"]
+    nz = ref != 0
+    assert (np.abs(v[nz] - ref[nz]) <= REL_TOL * np.abs(ref[nz])).all()
+    assert (v[~nz] == 0).all()
+    if options == cabi.OPT_FORCE_GENERAL:
+        assert st["jobs_fast"] == 0
+
+
+@pytest.mark.parametrize("name", LIVE_CASES)
+def test_edge_pairs_match_oracle(ctx, name):
+    """Pairs whose d2 is a bin threshold or the double just below one are reported separately."""
+    d = live_case(name)
+    rmin, rmax, nbin, tmax, skip, every, nts, primo = d["params"]
+    ids, nt = d["type_ids"], int(d["type_ids"].max()) + 1
+    pos = d["pos_ref"]
+    c, st, e = gpu_counts(ctx, pos, d["box_internal"], ids, nt, rmin, rmax, int(nbin), int(tmax), int(nts),
+                          primo=int(primo), skip=int(skip), every=int(every), edges=True)
+    co, eo = oracle.counts(pos, d["box_internal"], ids, rmin, rmax, int(nbin), int(tmax), int(nts), primo=int(primo),
+                           skip=int(skip), every=int(every), ntypes=nt, return_edges=True)
+    assert np.array_equal(c, co)
+    assert e == eo
+
+
+def test_thresholds_reproduce_reference_binning(ctx):
+    """The table the kernel bins with is exact: at and just below every threshold the reference
+    expression (oracle's gofrt_oracle_bin) changes value exactly there."""
+    import ctypes as C
+    lib = oracle.oracle._load()
+    lib.gofrt_oracle_bin.argtypes = [C.c_double, C.c_double, C.c_double, C.c_uint]
+    lib.gofrt_oracle_bin.restype = C.c_int
+    tr = cabi.DeviceTrajectory(ctx, 1, 6, np.zeros(1, np.int32), 1, 1)
+    for rmin, rmax, nbin in ((0.0, 3.8, 200), (0.7, 3.5, 200), (0.5, 3.8, 100), (0.0, 10.0, 500), (0.3, 2.4, 25)):
+        plan = cabi.Plan(tr, rmin, rmax, nbin)
+        T = plan.thresholds()
+        dr = (rmax - rmin) / nbin
+        for k in range(nbin + 1):
+            assert lib.gofrt_oracle_bin(T[k], rmin, dr, nbin) >= k
+            if T[k] > 0:
+                assert lib.gofrt_oracle_bin(np.nextafter(T[k], -np.inf), rmin, dr, nbin) < k
+        plan.close()
+    tr.close()
+
+
+@pytest.mark.parametrize("triclinic", [False, True])
+def test_multi_tile_random(ctx, triclinic):
+    """N large enough for several i tiles, j tiles and j chunks; 2 types of unequal size (padding)."""
+    pos, box, types = synth.small_case(31 + triclinic, (12, 11, 10), 1.07, 2, triclinic, 5, "blocks")
+    types = (np.arange(pos.shape[1]) % 5 == 0).astype(np.int32)
+    bi = synth.lammps_rows_to_internal(box)
+    ctx.pbc_wrap(pos, bi)
+    args = (0.0, 4.5, 90, 3, 3)
+    c, st = gpu_counts(ctx, pos, bi, types, 2, *args, skip=2)
+    co = oracle.counts(pos, bi, types, *args, skip=2, ntypes=2)
+    assert np.array_equal(c, co)
+    assert st["jobs_fast"] == st["jobs"]
+    c2, st2 = gpu_counts(ctx, pos, bi, types, 2, *args, skip=2, options=cabi.OPT_FORCE_GENERAL | cabi.OPT_AGGREGATE)
+    assert np.array_equal(c2, co)
+    # every ordered pair with d2 in range lands somewhere: lag 0, self slot, bin 0 holds exactly N per origin
+    n0, n1 = int((types == 0).sum()), int((types == 1).sum())
+    assert c[0, 3 + 2, 0] == 2 * n0 and c[0, 3 + 1, 0] == 2 * n1
+
+
+def test_window_offset_and_errors(ctx):
+    """A window that does not start at frame 0 (Trajectory::set_access_at), and the error codes."""
+    pos, box, types = synth.small_case(5, (4, 4, 4), 1.1, 2, False, 12)
+    bi = synth.lammps_rows_to_internal(box)
+    ctx.pbc_wrap(pos, bi)
+    ref = oracle.counts(pos, bi, types, 0.0, 2.0, 20, 3, 4, primo=5, skip=1, ntypes=2)
+    tr = cabi.DeviceTrajectory(ctx, pos.shape[1], 6, types, 2, 8)
+    tr.upload(4, np.ascontiguousarray(pos[4:12]), bi[4:12])
+    plan = cabi.Plan(tr, 0.0, 2.0, 20)
+    c, _ = plan.block(5, 4, 3)
+    assert np.array_equal(c, ref)
+    with pytest.raises(cabi.AgofrtError) as e:
+        plan.block(3, 4, 3)
+    assert e.value.code == cabi.ERR_WINDOW
+    with pytest.raises(cabi.AgofrtError) as e:
+        plan.block(8, 4, 3)
+    assert e.value.code == cabi.ERR_WINDOW
+    bad = pos[4:12].copy()
+    bad[2, 7, 1] = np.inf
+    tr.upload(4, bad, bi[4:12])
+    with pytest.raises(cabi.AgofrtError) as e:
+        plan.block(5, 4, 3)
+    assert e.value.code == cabi.ERR_NONFINITE
+    # NaN coordinates are simply never in range (the reference skips them too)
+    nanpos = pos[4:12].copy()
+    nanpos[:, 3, :] = np.nan
+    tr.upload(4, nanpos, bi[4:12])
+    c, _ = plan.block(5, 4, 3)
+    refn = oracle.counts(np.concatenate([pos[:4], nanpos]), bi, types, 0.0, 2.0, 20, 3, 4, primo=5, skip=1, ntypes=2)
+    assert np.array_equal(c, refn)
+    # empty block
+    c, st = plan.block(5, 0, 0)
+    assert c.shape == (0, 6, 20) and st["jobs"] == 0
+    plan.close()
+    tr.close()
+
+
+def test_shards_sum_to_whole(ctx):
+    """Work-unit shards (what each of `world` GPUs computes before the all-reduce) add up exactly."""
+    pos, box, types = synth.small_case(9, (9, 8, 8), 1.05, 1, True, 6)
+    bi = synth.lammps_rows_to_internal(box)
+    ctx.pbc_wrap(pos, bi)
+    whole, st = gpu_counts(ctx, pos, bi, types, 1, 0.0, 3.0, 50, 3, 3)
+    total = np.zeros_like(whole)
+    world = 3
+    for r in range(world):
+        c2 = cabi.Context()
+        c2.set_shard(r, world)
+        part, st2 = gpu_counts(c2, pos, bi, types, 1, 0.0, 3.0, 50, 3, 3)
+        total += part
+        assert st2["world"] == world
+        c2.close()
+    assert np.array_equal(total, whole)
+    assert np.array_equal(whole, oracle.counts(pos, bi, types, 0.0, 3.0, 50, 3, 3, ntypes=1))
+
+
+def test_size_independent_properties_large(ctx):
+    """At a size the oracle cannot finish: total of the lag-0 'distinct' rows + self rows equals the
+    number of ordered pairs within rmax counted independently per shard, and the lag-0 histogram is
+    symmetric under swapping the two frames' roles (d2(i,j) == d2(j,i))."""
+    w = synth.WORKLOADS["C2"]
+    pos, box, types = synth.generate(w, nframes=3)
+    bi = synth.lammps_rows_to_internal(box)
+    ctx.pbc_wrap(pos, bi)
+    c, st = gpu_counts(ctx, pos, bi, types, 1, w.rmin, w.rmax, w.nbin, 2, 2)
+    n = w.natoms
+    assert st["pair_evals_total"] == 2 * 2 * n * n
+    assert c[0, 1, 0] == 2 * n               # self pairs at lag 0: d2 == 0 -> bin 0, once per origin
+    assert c[0, 1, 1:].sum() == 0
+    assert c[1, 1].sum() == 2 * n            # every atom's own displacement over one frame is < rmax
+    # same frames, general kernel and aggregated atomics: identical integers
+    c2, _ = gpu_counts(ctx, pos, bi, types, 1, w.rmin, w.rmax, w.nbin, 2, 2,
+                       options=cabi.OPT_FORCE_GENERAL | cabi.OPT_AGGREGATE)
+    assert np.array_equal(c, c2)
+    # lag 0 distinct counts are even: (i,j) and (j,i) fall in the same bin
+    assert (c[0, 0] % 2 == 0).all()

@@ -1,0 +1,144 @@
+"""CPU: pin the oracle (oracle/gofrt_oracle.c) against the reference's golden vectors and against
+outputs of the compiled reference (fixtures made by tests/golden/make_golden.py)."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from conftest import LIVE_CASES, REFERENCE, live_case, load_golden
+
+
+def test_gofr_numpy_golden():
+    """reference tests/test_gofrt.py -> tests/test_gofrt/test_gofr.csv (ortho, unwrapped, 3 types, 10 lags)."""
+    z = load_golden("gofr_numpy.npz")
+    rmin, rmax, nbin, tmax, skip, nts = z["params"]
+    c = oracle.counts(z["pos"], z["box_internal"], z["types"], rmin, rmax, int(nbin), int(tmax), int(nts),
+                      primo=0, skip=int(skip), ntypes=3, total_frames=7958)
+    assert c.shape == (10, 12, 200)
+    assert np.array_equal(c, z["counts"])
+    # the float accumulation of the reference with its 4 threads reproduces the CSV to rounding
+    v = oracle.vdata(z["pos"], z["box_internal"], z["types"], rmin, rmax, int(nbin), int(tmax), int(nts),
+                     primo=0, skip=int(skip), ntypes=3, ref_nthreads=4, total_frames=7958)
+    assert np.abs(v - z["csv"]).max() < 1e-11
+
+
+def test_gofr_notebook_golden():
+    """reference tests/test_notebook.py -> tests/test_notebook/test_gofr.csv (mmap trajectory, wrap on)."""
+    z = load_golden("gofr_notebook.npz")
+    wrapped = oracle.pbc_wrap(z["pos_unwrapped"], z["box_internal"])
+    assert np.array_equal(wrapped, z["pos_wrapped"])
+    rmin, rmax, nbin, tmax, skip, nts = z["params"]
+    nt = int(z["types"].max()) + 1
+    c = oracle.counts(wrapped, z["box_internal"], z["types"], rmin, rmax, int(nbin), int(tmax), int(nts),
+                      primo=0, skip=int(skip), ntypes=nt)
+    assert np.array_equal(c, z["counts"])
+
+
+def test_min_image_and_pbc_golden():
+    """reference tests/src/test_trajectory.cpp:21-59 -> cpp_regression_data/{min_image,pbc_1,pbc_2} (tolerance 1e-10 there)."""
+    z = load_golden("min_image_pbc.npz")
+    for tag in ("1", "2"):
+        w = oracle.pbc_wrap(z["pos_" + tag][None], z["box_" + tag][None])[0]
+        g = z["pbc_" + tag]
+        assert np.abs(w - g).max() <= 1e-10 * max(1.0, np.abs(g).max())
+    assert np.array_equal(oracle.pbc_wrap(z["pos_1"][None], z["box_1"][None])[0], z["pos_wrapped_1"])
+    d = oracle.d2_all(z["pos_wrapped_1"], z["pos_wrapped_1"], z["box_1"])
+    g = z["min_image_1"]
+    assert np.abs(d - g).max() <= 1e-10 * max(1.0, np.abs(g).max())
+    lh = z["box_1"][3:6]
+    assert (np.abs(d[..., :3]) <= lh + 1e-15).all()
+
+
+@pytest.mark.parametrize("name", LIVE_CASES)
+def test_live_reference_cases(name):
+    """triclinic / NPT / unwrapped / ragged loops: fixtures computed by the compiled reference."""
+    d = live_case(name)
+    rmin, rmax, nbin, tmax, skip, every, nts, primo = d["params"]
+    box_internal = d["box_internal"]
+    ids, nt = oracle.type_ids(d["raw_types"])
+    assert np.array_equal(ids, d["type_ids"])
+    from analisi_b200 import synth
+    bi = synth.lammps_rows_to_internal(d["box_lammps"])
+    assert np.array_equal(bi, box_internal)
+    pos = d["pos_in"]
+    if bool(d["wrap"]):
+        pos = oracle.pbc_wrap(pos, box_internal)
+    assert np.array_equal(pos, d["pos_ref"])
+    c, edges = oracle.counts(pos, box_internal, ids, rmin, rmax, int(nbin), int(tmax), int(nts), primo=int(primo),
+                             skip=int(skip), every=int(every), ntypes=nt, return_edges=True)
+    assert np.array_equal(c, d["counts"])
+    v = oracle.vdata(pos, box_internal, ids, rmin, rmax, int(nbin), int(tmax), int(nts), primo=int(primo),
+                     skip=int(skip), every=int(every), ntypes=nt, ref_nthreads=3)
+    assert np.array_equal(v, d["vdata"])  # bitwise: same thread split, same order of additions
+
+
+def test_oracle_matches_compiled_reference_live():
+    """When oracle/_ref is present: a fresh random triclinic case, reference vs restatement."""
+    m = oracle.load_ref()
+    if m is None:
+        pytest.skip("oracle/_ref not built (no /root/reference here)")
+    from analisi_b200 import synth
+    pos, box, types = synth.small_case(77, (5, 4, 3), 1.05, 2, True, 9, "parity", (0.2, 0.1, -0.15), True)
+    tr = m.Trajectory(pos, np.zeros_like(pos), types, box, m.BoxFormat.LammpsTriclinic, True, False)
+    g = m.Gofrt(tr, 0.1, 2.3, 17, 4, 2, 2, 1, False)
+    g.reset(5)
+    g.calculate(1)
+    v = np.array(g, copy=True)
+    bi = synth.lammps_rows_to_internal(box)
+    w = oracle.pbc_wrap(pos, bi)
+    assert np.array_equal(w, tr.get_positions_copy())
+    c = oracle.counts(w, bi, types, 0.1, 2.3, 17, 4, 5, primo=1, skip=2, ntypes=2)
+    assert np.array_equal(c, np.rint(v * 2).astype(np.uint64))
+
+
+def _cli_text(mean, var, leff, nbin, ncol):
+    # the CLI's printing loop, reference analisi/main.cpp:564-584
+    lines = []
+    for t in range(leff):
+        for r in range(nbin):
+            row = "%d %d" % (t, r)
+            for k in range(ncol):
+                row += " %s %s" % (_g(mean[t, k, r]), _g(var[t, k, r]))
+            lines.append(row)
+        lines.append("")
+    return lines
+
+
+def _g(x):
+    # iostream default formatting of a double: %g with 6 significant digits
+    return "%g" % x
+
+
+@pytest.mark.parametrize("name,tmax", [("pair_corr_no_t", 1), ("pair_corr_t", 10)])
+def test_cli_golden_blocks(name, tmax):
+    """reference tests/test_cli.sh: analisi -i lammps2020.bin -g 100 -F 0.0 4.0 -S {1,10} -s 8
+    (20 blocks, mean and variance, text).  Needs the reference tree for the 51 MB input."""
+    m = oracle.load_ref()
+    path = os.path.join(REFERENCE, "tests/data/lammps2020.bin")
+    if m is None or not os.path.exists(path):
+        pytest.skip("reference tree not available")
+    gold = open(os.path.join(REFERENCE, "tests/data/cli", name)).read().split("\n")
+    gold_rows = [l for l in gold if l and not l.startswith("#")]
+    tr = m.Traj(path)
+    tr.setWrapPbc(True)
+    nts = tr.get_ntimesteps()
+    n_b, nbin, skip = 20, 100, 8
+    nextra = oracle.nextra(nts, n_b, tmax)
+    s = (nts - nextra) // n_b
+    tr.setAccessWindowSize(s + nextra)
+    blocks = []
+    for ib in range(n_b):
+        tr.setAccessStart(ib * s)
+        pos = tr.get_positions_copy()
+        box = tr.get_box_copy()
+        ids = tr.get_type_ids()
+        nt = int(tr.get_ntypes())
+        v = oracle.vdata(pos, box, ids, 0.0, 4.0, nbin, tmax, s, primo=ib * s, skip=skip, ntypes=nt,
+                         first_frame=ib * s, total_frames=nts, ref_nthreads=2)
+        blocks.append(v)
+    mean, var = oracle.mediavar(np.array(blocks))
+    leff = oracle.leff(s, tmax)
+    rows = [l for l in _cli_text(mean, var, leff, nbin, nt * (nt + 1)) if l]
+    assert len(rows) == len(gold_rows)
+    assert rows == gold_rows
