@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libagofrt.so")
 
 OK = 0
 ERR_ARG, ERR_CUDA, ERR_WINDOW, ERR_NCCL, ERR_NONFINITE, ERR_TOO_LARGE, ERR_INTERNAL = -1, -2, -3, -4, -5, -6, -7
-OPT_EDGES, OPT_FORCE_GENERAL, OPT_NO_AGGREGATE, OPT_AGGREGATE = 1, 2, 4, 8
+OPT_EDGES, OPT_FORCE_GENERAL, OPT_NO_AGGREGATE, OPT_AGGREGATE, OPT_NO_SAFE = 1, 2, 4, 8, 16
 COMM_ID_BYTES = 128
 
 # every symbol include/agofrt.h declares (tests check the library exports all of them)
@@ -44,11 +44,11 @@ class Stats(C.Structure):
         ("launches", C.c_uint32),
         ("ndev_local", C.c_uint32),
         ("world", C.c_uint32),
-        ("reserved", C.c_uint32),
+        ("kernel_modes", C.c_uint32),
     ]
 
     def as_dict(self):
-        return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
+        return {k: getattr(self, k) for k, _ in self._fields_ }
 
 
 _lib = None

@@ -141,6 +141,7 @@ struct agofrt_traj {
     std::vector<double> box6;    // host copy [nframes][6]
     std::vector<double> bounds;  // host copy [nframes][6]
     bool has_inf = false;
+    bool has_nan = false;   // NaN coordinates in the input (they are never in range, as in the reference)
     bool bad_box = false;
 };
 
@@ -162,6 +163,9 @@ struct agofrt_plan {
     bool empty_range = false;
     unsigned hlo = 0, hspan = 0;
     float inv_dr = 0, c0 = 0;
+    float c0h = 0, lim = 0;      // safe-zone binning: c0 - 0.5, 0.5 - eps
+    bool safe_ok = false;        // validated on the device when the plan was made
+    double q_reach = 0;          // largest bin coordinate the float path may meet before it must give up
     std::vector<PlanDev> dev;
     unsigned long long *host_counts = nullptr;  // pinned
     size_t host_counts_len = 0;
@@ -482,6 +486,7 @@ extern "C" int agofrt_traj_upload(agofrt_traj *t, size_t first_frame, size_t nfr
     t->box6.assign(nframes * 6, 0.0);
     t->bounds.assign(nframes * 6, 0.0);
     t->has_inf = false;
+    t->has_nan = false;
     t->bad_box = false;
     if (nframes == 0) return AGOFRT_OK;
 
@@ -530,12 +535,13 @@ extern "C" int agofrt_traj_upload(agofrt_traj *t, size_t first_frame, size_t nfr
         Dev &dv = t->ctx->devs[0];
         TrajDev &d = t->dev[0];
         CU(cudaSetDevice(dv.id));
-        CU(launch_frame_bounds(d.pos, t->npad, static_cast<int>(nframes), d.bounds, d.flags, dv.stream));
+        CU(launch_frame_bounds(d.pos, d.perm, t->npad, static_cast<int>(nframes), d.bounds, d.flags, dv.stream));
         unsigned int flags[4] = {0, 0, 0, 0};
         CU(cudaMemcpyAsync(t->bounds.data(), d.bounds, nframes * 6 * sizeof(double), cudaMemcpyDeviceToHost, dv.stream));
         CU(cudaMemcpyAsync(flags, d.flags, sizeof(flags), cudaMemcpyDeviceToHost, dv.stream));
         CU(cudaStreamSynchronize(dv.stream));
         t->has_inf = flags[0] != 0;
+        t->has_nan = flags[2] != 0;
     }
     for (size_t i = 0; i < t->dev.size(); ++i) {
         CU(cudaSetDevice(t->ctx->devs[i].id));
@@ -690,6 +696,80 @@ static void build_thresholds(double rmin, double dr, unsigned nbin, std::vector<
     }
 }
 
+// Exact bin of d2 from the folded table (the kernel's own definition): k with thr[k] <= d2 < thr[k+1], else -1.
+static int exact_bin(const std::vector<double> &thr, unsigned nbin, double d2) {
+    if (!(d2 >= thr[0]) || !(d2 < thr[nbin])) return -1;
+    unsigned lo = 0, hi = nbin;  // thr[lo] <= d2 < thr[hi]
+    while (hi - lo > 1) {
+        const unsigned mid = (lo + hi) / 2;
+        if (d2 >= thr[mid]) lo = mid; else hi = mid;
+    }
+    return static_cast<int>(lo);
+}
+
+// Run the device's float guess on probes at, next to and between all bin thresholds; a single
+// unflagged wrong guess disables the safe-zone mode for this plan (the threshold mode is always exact).
+static int validate_safe_zone(agofrt_plan *p) {
+    const unsigned nbin = p->nbin;
+    std::vector<double> probes;
+    auto add_around = [&](double t) {
+        if (!std::isfinite(t)) return;
+        uint64_t b = double_to_bits(t);
+        for (int d = -3; d <= 3; ++d) {
+            const uint64_t bb = b + static_cast<uint64_t>(static_cast<int64_t>(d));
+            if (d < 0 && b < static_cast<uint64_t>(-d)) continue;
+            probes.push_back(bits_to_double(bb));
+        }
+    };
+    probes.push_back(0.0);
+    for (unsigned k = 0; k <= nbin; ++k) {
+        add_around(p->thr[k]);
+        add_around(p->thr_full[k]);
+    }
+    for (unsigned k = 0; k < nbin; ++k) {
+        const double a = p->thr[k], b = p->thr[k + 1];
+        if (!(a < b) || !std::isfinite(b)) continue;
+        for (int i = 1; i < 32; ++i) probes.push_back(a + (b - a) * (i / 32.0));
+        // also points a relative 1e-7 .. 1e-3 inside either edge (where the float guess is weakest)
+        for (double rel : {1e-7, 1e-6, 1e-5, 1e-4, 1e-3}) {
+            probes.push_back(a + (b - a) * rel);
+            probes.push_back(b - (b - a) * rel);
+        }
+    }
+    const double top = p->thr[nbin];
+    if (std::isfinite(top))
+        for (double f : {1.0000001, 1.001, 1.5, 4.0, 100.0, 1e6}) probes.push_back(top * f + 1e-300);
+    std::vector<int> expected(probes.size());
+    for (size_t i = 0; i < probes.size(); ++i) expected[i] = exact_bin(p->thr, nbin, probes[i]);
+
+    Dev &dv = p->traj->ctx->devs[0];
+    CU(cudaSetDevice(dv.id));
+    double *dprobe = nullptr;
+    int *dexp = nullptr;
+    unsigned int *dbad = nullptr;
+    CU(cudaMalloc(&dprobe, probes.size() * sizeof(double)));
+    CU(cudaMalloc(&dexp, probes.size() * sizeof(int)));
+    CU(cudaMalloc(&dbad, sizeof(unsigned int)));
+    unsigned int bad = 0;
+    auto body = [&]() -> int {
+        CU(cudaMemcpyAsync(dprobe, probes.data(), probes.size() * sizeof(double), cudaMemcpyHostToDevice, dv.stream));
+        CU(cudaMemcpyAsync(dexp, expected.data(), probes.size() * sizeof(int), cudaMemcpyHostToDevice, dv.stream));
+        CU(cudaMemsetAsync(dbad, 0, sizeof(unsigned int), dv.stream));
+        CU(launch_validate_safe(dprobe, dexp, static_cast<int>(probes.size()), p->inv_dr, p->c0h, p->lim,
+                                static_cast<int>(nbin), dbad, dv.stream));
+        CU(cudaMemcpyAsync(&bad, dbad, sizeof(bad), cudaMemcpyDeviceToHost, dv.stream));
+        CU(cudaStreamSynchronize(dv.stream));
+        return AGOFRT_OK;
+    };
+    const int rc = body();
+    cudaFree(dprobe);
+    cudaFree(dexp);
+    cudaFree(dbad);
+    if (rc != AGOFRT_OK) return rc;
+    if (bad != 0) p->safe_ok = false;
+    return AGOFRT_OK;
+}
+
 extern "C" int agofrt_plan_create(agofrt_plan **out, agofrt_traj *traj, double rmin, double rmax, unsigned nbin) {
     if (!out || !traj) return fail(AGOFRT_ERR_ARG, "NULL argument");
     *out = nullptr;
@@ -738,6 +818,25 @@ extern "C" int agofrt_plan_create(agofrt_plan **out, agofrt_traj *traj, double r
     if (!std::isfinite(p->inv_dr)) p->inv_dr = 0.0f;
     if (!std::isfinite(p->c0)) p->c0 = 0.0f;
 
+    // Safe-zone binning (MODE_SAFE): the float guess q = sqrtf(d2)*inv_dr + c0 differs from the
+    // reference's float quotient by at most q_top * (2^-22 + 2^-23 + 2^-24): truncation of d2 to
+    // float (2^-24 after the root), sqrt.approx (2^-23), inv_dr and FFMA roundings (2^-24 each) and
+    // the reference's own rounding to float (2^-24).  A guess farther than eps = 2*bound from
+    // both edges of its bin is therefore the reference's bin; everything closer goes through the
+    // exact bracket search.  The claim is then CHECKED on the device against the exact table.
+    p->safe_ok = false;
+    if (!p->empty_range && p->dr > 0 && std::isfinite(p->dr)) {
+        const double q_top = static_cast<double>(nbin) + std::fabs(rmin) / p->dr;
+        const double bound = q_top * (std::ldexp(1.0, -22) + std::ldexp(1.0, -23) + std::ldexp(1.0, -24));
+        const double eps = 2.0 * bound + std::ldexp(1.0, -20);
+        if (eps <= std::ldexp(1.0, -6) && q_top < std::ldexp(1.0, 21)) {
+            p->c0h = static_cast<float>(-rmin / p->dr - 0.5);
+            p->lim = static_cast<float>(0.5 - eps);
+            p->q_reach = std::ldexp(1.0, 21);
+            p->safe_ok = true;
+        }
+    }
+
     p->dev.resize(traj->ctx->devs.size());
     for (size_t i = 0; i < p->dev.size(); ++i) {
         CU(cudaSetDevice(traj->ctx->devs[i].id));
@@ -748,6 +847,10 @@ extern "C" int agofrt_plan_create(agofrt_plan **out, agofrt_traj *traj, double r
         CU(cudaMalloc(&d.edges, sizeof(unsigned long long)));
         CU(cudaMemcpy(d.thr, p->thr.data(), (nbin + 1) * sizeof(double), cudaMemcpyHostToDevice));
         CU(cudaMemcpy(d.thr_full, p->thr_full.data(), (nbin + 1) * sizeof(double), cudaMemcpyHostToDevice));
+    }
+    if (p->safe_ok) {
+        const int rcv = validate_safe_zone(p.get());
+        if (rcv != AGOFRT_OK) return rcv;
     }
     CU(cudaHostAlloc(reinterpret_cast<void **>(&p->host_edges), sizeof(unsigned long long) * p->dev.size(),
                      cudaHostAllocPortable));
@@ -881,6 +984,17 @@ extern "C" int agofrt_block(agofrt_plan *p, size_t primo, unsigned ntimesteps, u
     if (options & AGOFRT_OPT_AGGREGATE) aggregate = true;
     if (options & AGOFRT_OPT_NO_AGGREGATE) aggregate = false;
     const bool tri = t->stride == 9;
+    // safe-zone binning needs the bin coordinate of every reachable distance to stay below 2^21
+    bool use_safe = p->safe_ok && !(options & AGOFRT_OPT_NO_SAFE) && !t->has_nan;
+    if (use_safe) {
+        double reach = 0;
+        for (size_t f = 0; f < t->nframes; ++f) {
+            const double *b = &t->box6[f * 6];
+            const double ex = 3 * b[0] + std::fabs(b[3]) + std::fabs(b[4]), ey = 3 * b[1] + std::fabs(b[5]), ez = 3 * b[2];
+            reach = std::max(reach, std::sqrt(ex * ex + ey * ey + ez * ez));
+        }
+        if (!(reach / p->dr < p->q_reach)) use_safe = false;
+    }
     const size_t smem = pair_kernel_smem_bytes(nt, static_cast<int>(p->nbin), want_edges);
 
     // ---- pinned read-back buffer ----
@@ -893,7 +1007,7 @@ extern "C" int agofrt_block(agofrt_plan *p, size_t primo, unsigned ntimesteps, u
         p->host_counts_len = len;
     }
 
-    unsigned launches = 0;
+    unsigned launches = 0, modes_used = 0;
     uint64_t my_pairs = 0;
     // ---- enqueue on every local device ----
     for (int i = 0; i < nloc; ++i) {
@@ -961,12 +1075,22 @@ extern "C" int agofrt_block(agofrt_plan *p, size_t primo, unsigned ntimesteps, u
                 pp.c0 = p->c0;
                 pp.hlo = p->hlo;
                 pp.hspan = p->hspan;
-                const int variant = (tri ? 1 : 0) | (pass == 0 ? 2 : 0) | ((aggregate && !want_edges) ? 4 : 0) |
-                                    (want_edges ? 8 : 0);
+                pp.c0h = p->c0h;
+                pp.lim = p->lim;
+                pp.hhi = p->hlo + p->hspan;
+                int mode = kModeThr;
+                if (want_edges)
+                    mode = kModeEdges;
+                else if (aggregate)
+                    mode = kModeAgg;
+                else if (pass == 0 && use_safe)
+                    mode = kModeSafe;
+                const int variant = (tri ? 1 : 0) | (pass == 0 ? 2 : 0) | (mode << 2);
                 const int grid = static_cast<int>(std::min<uint64_t>(ue - ub, 2ull * dv.sm_count));
                 CU(cudaMemsetAsync(pd.counter, 0, sizeof(unsigned int), dv.stream));
                 CU(launch_pair_kernel(variant, grid, smem, dv.stream, pp));
                 ++launches;
+                modes_used |= 1u << mode;
                 // pair evaluations of this shard, counted on real atoms: units are equal-sized
                 my_pairs += static_cast<uint64_t>(static_cast<double>(ue - ub) / static_cast<double>(per_job) * n2 + 0.5);
             }
@@ -1045,6 +1169,7 @@ extern "C" int agofrt_block(agofrt_plan *p, size_t primo, unsigned ntimesteps, u
         stats->launches = launches;
         stats->ndev_local = static_cast<uint32_t>(nloc);
         stats->world = static_cast<uint32_t>(world);
+        stats->kernel_modes = modes_used;
     }
     return AGOFRT_OK;
 }

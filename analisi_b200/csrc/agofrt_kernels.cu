@@ -43,8 +43,11 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
                  : "memory");
 }
 
-__device__ __forceinline__ double xor_sign(uint32_t hi, uint32_t lo, uint32_t sign) {
-    return __hiloint2double(static_cast<int>(hi ^ sign), static_cast<int>(lo));
+// explicit shared-window accesses (32-bit addresses: no generic-pointer arithmetic in the hot loop)
+__device__ __forceinline__ double2 lds_f64x2(uint32_t addr) {
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+    return v;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -98,36 +101,50 @@ __device__ __forceinline__ bool min_image_general(double &dx, double &dy, double
 }
 
 // Single-pass form, used only for (lag, origin) jobs whose coordinate bounds PROVE that one image
-// per dimension is enough (agofrt_cabi.cu: job_is_single_pass).  x -= copysign(2*l_half, x) is
-// the same rounding as the reference's += / -= of l_half*2; the sign is injected with one LOP3.
-struct BoxBits {
-    double lhx, lhy, lhz;
-    uint32_t Lx_hi, Lx_lo, Ly_hi, Ly_lo, Lz_hi, Lz_lo;
-    uint32_t xy_hi, xy_lo, xz_hi, xz_lo, yz_hi, yz_lo;
-};
+// per dimension is enough (agofrt_cabi.cu: job_is_single_pass).
+//
+// The reference's loop body is odd-symmetric: every operation it performs (add, subtract, |x|
+// compare, round-to-nearest) commutes with a global sign flip of the vector, and the vector is only
+// ever squared afterwards.  So instead of choosing between "+= 2*l_half" and "-= 2*l_half" by the
+// sign of the component, flip the sign of the WHOLE remaining vector so that the component is
+// positive (one LOP3 on the high word of each lower component, nothing at all for the component
+// itself: |x| is an operand modifier) and always subtract.  fl(-a-b) == -fl(a+b), so every
+// intermediate is, up to that global sign, bit-identical to the reference's.
+// The wrap of one component is  x = fma(m, -2*l_half, |x|)  with m = 1.0 or 0.0 from the compare:
+// m*c is exact, so the fused operation rounds once, exactly like the reference's "x -= 2*l_half"
+// (m = 1) or leaves |x| untouched (m = 0).  Building m costs one 32-bit select (its low word is
+// the constant 0), and the same m serves the tilt corrections of the lower components:
+// 2 FP64 instructions + 1 select per wrapped component, nothing on the other pipes.
+__device__ __forceinline__ double flip_by(double v, double sign_source) {
+    const int hi = __double2hiint(v) ^ (__double2hiint(sign_source) & 0x80000000);
+    return __hiloint2double(hi, __double2loint(v));
+}
+__device__ __forceinline__ double mask01(bool p) { return __hiloint2double(p ? 0x3FF00000 : 0, 0); }
 
 template <bool TRI>
-__device__ __forceinline__ void min_image_single(double &dx, double &dy, double &dz, const BoxBits &b) {
-    {
-        const uint32_t s = static_cast<uint32_t>(__double2hiint(dz)) & 0x80000000u;
-        if (fabs(dz) > b.lhz) {
-            dz = __dsub_rn(dz, xor_sign(b.Lz_hi, b.Lz_lo, s));
-            if (TRI) {
-                dy = __dsub_rn(dy, xor_sign(b.yz_hi, b.yz_lo, s));
-                dx = __dsub_rn(dx, xor_sign(b.xz_hi, b.xz_lo, s));
-            }
-        }
+__device__ __forceinline__ void min_image_single(double &dx, double &dy, double &dz, const BoxRegs &b,
+                                                 double nLx, double nLy, double nLz) {  // nL = -(2*l_half)
+    if (TRI) {
+        dy = flip_by(dy, dz);
+        dx = flip_by(dx, dz);
     }
     {
-        const uint32_t s = static_cast<uint32_t>(__double2hiint(dy)) & 0x80000000u;
-        if (fabs(dy) > b.lhy) {
-            dy = __dsub_rn(dy, xor_sign(b.Ly_hi, b.Ly_lo, s));
-            if (TRI) dx = __dsub_rn(dx, xor_sign(b.xy_hi, b.xy_lo, s));
+        const double m = mask01(fabs(dz) > b.lhz);
+        dz = __fma_rn(m, nLz, fabs(dz));
+        if (TRI) {
+            dy = __fma_rn(m, -b.yz, dy);
+            dx = __fma_rn(m, -b.xz, dx);
         }
     }
+    if (TRI) dx = flip_by(dx, dy);
     {
-        const uint32_t s = static_cast<uint32_t>(__double2hiint(dx)) & 0x80000000u;
-        if (fabs(dx) > b.lhx) dx = __dsub_rn(dx, xor_sign(b.Lx_hi, b.Lx_lo, s));
+        const double m = mask01(fabs(dy) > b.lhy);
+        dy = __fma_rn(m, nLy, fabs(dy));
+        if (TRI) dx = __fma_rn(m, -b.xy, dx);
+    }
+    {
+        const double m = mask01(fabs(dx) > b.lhx);
+        dx = __fma_rn(m, nLx, fabs(dx));
     }
 }
 
@@ -139,21 +156,32 @@ __device__ __forceinline__ double d2_of(double dx, double dy, double dz) {
 // ---------------------------------------------------------------------------------------------
 // binning
 // ---------------------------------------------------------------------------------------------
+// MODE_THR   float guess of the bin + bracket test against the exact thresholds (always exact)
+// MODE_AGG   the same, the shared atomic merged across the warp with __match_any_sync
+// MODE_EDGES plain thresholds + explicit range test + count of pairs within 1 ulp of a bin edge
+// MODE_SAFE  float guess accepted without looking at the thresholds when it is farther than `eps`
+//            bins from a bin edge (eps bounds the float error, validated on the device when the plan
+//            is made); the few pairs closer than eps to an edge go through the exact bracket search
+enum { MODE_THR = 0, MODE_AGG = 1, MODE_EDGES = 2, MODE_SAFE = 3 };
+
 // float guess of the bin from the bits of d2 (no FP64 conversion instruction): rebias the
-// exponent, keep 23 mantissa bits, MUFU sqrt, one FFMA.
-__device__ __forceinline__ int bin_guess(double d2, float inv_dr, float c0, int nbin) {
+// exponent, keep 23 mantissa bits, MUFU sqrt, one FFMA.  Returns guess+1 clamped to [0, nbin+2]:
+// the index into the padded pair table below.
+__device__ __forceinline__ float d2_as_float(double d2) {
     const int hi = __double2hiint(d2);
     const uint32_t lo = static_cast<uint32_t>(__double2loint(d2));
-    int hh = hi - 0x38000000;              // exponent 1023-127 = 896
-    hh = max(hh, 0);
+    int hh = max(hi, 0x38000000) - 0x38000000;   // exponent 1023-127 = 896; tiny and zero -> 0
     hh = min(hh, 0x0FEFFFFF);
-    const uint32_t fb = __funnelshift_l(lo, static_cast<uint32_t>(hh), 3);
+    return __uint_as_float(__funnelshift_l(lo, static_cast<uint32_t>(hh), 3));
+}
+__device__ __forceinline__ float sqrt_approx(float f) {
     float s;
-    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(s) : "f"(__uint_as_float(fb)));
-    int g = __float2int_rd(fmaf(s, inv_dr, c0));
-    g = max(g, 0);
-    g = min(g, nbin - 1);
-    return g;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(s) : "f"(f));
+    return s;
+}
+__device__ __forceinline__ unsigned int bin_guess1(double d2, float inv_dr, float c0, unsigned int nbin2) {
+    const int g = __float2int_rd(fmaf(sqrt_approx(d2_as_float(d2)), inv_dr, c0));
+    return min(static_cast<unsigned int>(g + 1), nbin2);
 }
 
 template <bool AGG>
@@ -167,17 +195,19 @@ __device__ __forceinline__ void hist_add(unsigned int *hist, unsigned int idx) {
     }
 }
 
-// production path: thr[] already encodes rmin2 <= d2 <= rmax2 and 0 <= idx < nbin
+// The shared-memory threshold table is stored as pairs: thr2[g+1] = {T[g], T[g+1]} for
+// g = -1 .. nbin+1, with {+inf,+inf} for the slots outside [0,nbin) -- one LDS.128 brackets a guess,
+// and a guess outside the histogram can never pass the bracket test.
+// Rare path: exact bracket search (the guess missed, or sits within eps of an edge, or d2 is outside).
 template <bool AGG>
-__device__ __forceinline__ void bin_pair(double d2, const double *__restrict__ thr, int nbin, float inv_dr,
-                                         float c0, unsigned int *hist, unsigned int row) {
-    int g = bin_guess(d2, inv_dr, c0, nbin);
-    const double t0 = thr[g], t1 = thr[g + 1];
-    if (!(d2 >= t0) || !(d2 < t1)) {
-        if (!(d2 >= thr[0]) || !(d2 < thr[nbin])) return;  // not counted by the reference
-        while (d2 < thr[g]) --g;
-        while (d2 >= thr[g + 1]) ++g;
-    }
+__device__ __noinline__ void bin_pair_slow(double d2, const double2 *__restrict__ thr2, int nbin, float inv_dr,
+                                           float c0, unsigned int *hist, unsigned int row) {
+    // thr2[1].x = T[0], thr2[nbin].y = T[nbin]
+    if (!(d2 >= thr2[1].x) || !(d2 < thr2[nbin].y)) return;  // not counted by the reference
+    int g = static_cast<int>(bin_guess1(d2, inv_dr, c0, static_cast<unsigned int>(nbin) + 2u)) - 1;
+    g = min(max(g, 0), nbin - 1);
+    while (d2 < thr2[g + 1].x) --g;
+    while (d2 >= thr2[g + 1].y) ++g;
     hist_add<AGG>(hist, row + static_cast<unsigned int>(g));
 }
 
@@ -187,7 +217,8 @@ __device__ __forceinline__ void bin_pair_edges(double d2, const double *__restri
                                                float c0, double rmin2, double rmax2, unsigned int *hist,
                                                unsigned int row, unsigned long long &edges) {
     if (d2 > rmax2 || d2 < rmin2 || d2 != d2) return;  // reference lib/src/gofrt.cpp:104
-    int g = bin_guess(d2, inv_dr, c0, nbin);            // in [0, nbin-1]
+    int g = static_cast<int>(bin_guess1(d2, inv_dr, c0, static_cast<unsigned int>(nbin) + 2u)) - 1;
+    g = min(max(g, 0), nbin - 1);
     // idx = (number of k in 0..nbin with thrf[k] <= d2) - 1, in [-1, nbin]
     while (g >= 0 && d2 < thrf[g]) --g;
     while (g < nbin && d2 >= thrf[g + 1]) ++g;
@@ -201,11 +232,60 @@ __device__ __forceinline__ void bin_pair_edges(double d2, const double *__restri
     if (g >= 0 && g < nbin) atomicAdd(hist + row + static_cast<unsigned int>(g), 1u);
 }
 
+// MODE_THR fast path for one pair: bracket test and predicated shared atomic; returns nonzero if
+// the bracket test failed (the caller decides whether the pair needs the exact search).
+__device__ __forceinline__ unsigned int bin_pair_thr(double v, uint32_t thr2_addr, uint32_t row_addr_m4,
+                                                     float inv_dr, float c0, unsigned int nbin2) {
+    const unsigned int gi = bin_guess1(v, inv_dr, c0, nbin2);
+    const double2 t = lds_f64x2(thr2_addr + gi * 16u);
+    unsigned int miss;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ge.f64 p, %1, %2;\n\t"
+        "setp.lt.and.f64 p, %1, %3, p;\n\t"
+        "@p red.shared.add.u32 [%4], 1;\n\t"
+        "selp.u32 %0, 0, 1, p;\n\t}"
+        : "=r"(miss)
+        : "d"(v), "d"(t.x), "d"(t.y), "r"(row_addr_m4 + gi * 4u)
+        : "memory");
+    return miss;
+}
+
+// MODE_SAFE fast path for one pair.  qh = sqrtf(d2)*inv_dr + (c0 - 0.5) is the bin coordinate minus
+// one half; adding 1.5*2^23 rounds it to the nearest integer n (the guessed bin) in the low mantissa
+// bits, and |qh - n| < 0.5 - eps says the guess is more than eps bins away from both edges of bin n.
+// min.f32 returns the non-NaN operand: NaN (ghost slots) and absurdly large values land on QMAX,
+// which is "safe" and outside every histogram.  `mask |= bit` marks the pairs that need the exact
+// search.
+__device__ __forceinline__ void bin_pair_safe(double v, uint32_t row_addr_adj, float inv_dr, float c0h, float lim,
+                                              unsigned int nbin, unsigned int &mask, unsigned int bit) {
+    const float s = sqrt_approx(d2_as_float(v));
+    asm volatile(
+        "{\n\t.reg .pred ps, pu;\n\t.reg .f32 q, r, n, dl;\n\t.reg .b32 ri, gi, ad;\n\t"
+        "fma.rn.f32 q, %1, %2, %3;\n\t"
+        "min.f32 q, q, 0f4A800000;\n\t"          // 4194304.0
+        "add.rn.f32 r, q, 0f4B400000;\n\t"       // 1.5 * 2^23
+        "add.rn.f32 n, r, 0fCB400000;\n\t"
+        "sub.rn.f32 dl, q, n;\n\t"
+        "abs.f32 dl, dl;\n\t"
+        "setp.lt.f32 ps|pu, dl, %4;\n\t"
+        "mov.b32 ri, r;\n\t"
+        "sub.s32 gi, ri, 0x4B400000;\n\t"
+        "setp.lt.and.u32 ps, gi, %5, ps;\n\t"
+        "shl.b32 ad, ri, 2;\n\t"
+        "add.s32 ad, ad, %6;\n\t"
+        "@ps red.shared.add.u32 [ad], 1;\n\t"
+        "@pu or.b32 %0, %0, %7;\n\t}"
+        : "+r"(mask)
+        : "f"(s), "f"(inv_dr), "f"(c0h), "f"(lim), "r"(nbin), "r"(row_addr_adj), "r"(bit)
+        : "memory");
+}
+
 // ---------------------------------------------------------------------------------------------
 // the pair kernel
 // ---------------------------------------------------------------------------------------------
 struct SmemLayout {
-    size_t thr, thr_full, stage, hist, rowtab, tstart, bars, sched, total;
+    size_t thr2, thr_full, stage, hist, rowtab, tstart, bars, sched, total;
 };
 
 __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -215,12 +295,12 @@ __host__ __device__ inline SmemLayout smem_layout(int ntypes, int nbin, bool edg
     size_t o = 0;
     L.stage = o;
     o += static_cast<size_t>(kStages) * 3 * kTileJ * sizeof(double);
-    L.thr = o;
-    o += static_cast<size_t>(nbin + 1) * sizeof(double);
+    L.thr2 = o;
+    o += static_cast<size_t>(nbin + 3) * 2 * sizeof(double);
     L.thr_full = o;
     if (edges) o += static_cast<size_t>(nbin + 1) * sizeof(double);
-    L.bars = o;
-    o += kStages * sizeof(uint64_t);
+    L.bars = align_up(o, 8);
+    o = L.bars + kStages * sizeof(uint64_t);
     L.hist = o;
     o += static_cast<size_t>(ntypes) * (ntypes + 1) * nbin * sizeof(unsigned int);
     L.rowtab = o;
@@ -235,12 +315,143 @@ __host__ __device__ inline SmemLayout smem_layout(int ntypes, int nbin, bool edg
 
 size_t pair_kernel_smem_bytes(int ntypes, int nbin, bool edges) { return smem_layout(ntypes, nbin, edges).total; }
 
-template <bool TRI, bool FAST, bool AGG, bool EDGES>
+struct PairConst {
+    BoxRegs box;
+    double nLx, nLy, nLz;   // -(2*l_half), exact
+    uint32_t thr2_addr;     // shared-window address of thr2[0]
+    uint32_t hist_addr;     // shared-window address of hist[0]
+};
+
+// One group = kIPT i atoms (registers) x kJU j atoms (shared memory): all d2 first (straight-line,
+// independent FP64 chains), then one cheap test for "some pair of the group may be in range", then
+// the binning of the group's pairs without per-pair branches.
+//   DIAG: the j atoms may include one of this thread's own i atoms (i == j goes to the "self" rows).
+template <bool TRI, bool FAST, int MODE, bool DIAG>
+__device__ __forceinline__ void process_group(const PairParams &p, const PairConst &c, const double (&xi)[kIPT],
+                                              const double (&yi)[kIPT], const double (&zi)[kIPT],
+                                              const int (&ii)[kIPT], const unsigned int (&row)[kIPT],
+                                              uint32_t sx_addr, int jrel, int j, const double2 *s_thr2,
+                                              const double *s_thrf, unsigned int *s_hist, unsigned int self_off,
+                                              unsigned long long &edges, bool &wrap_ok) {
+    double xj[kJU], yj[kJU], zj[kJU];
+#pragma unroll
+    for (int q = 0; q < kJU; q += 2) {
+        const uint32_t a = sx_addr + static_cast<uint32_t>(jrel + q) * 8u;
+        const double2 vx = lds_f64x2(a);
+        const double2 vy = lds_f64x2(a + kTileJ * 8u);
+        const double2 vz = lds_f64x2(a + 2u * kTileJ * 8u);
+        xj[q] = vx.x;
+        xj[q + 1] = vx.y;
+        yj[q] = vy.x;
+        yj[q + 1] = vy.y;
+        zj[q] = vz.x;
+        zj[q + 1] = vz.y;
+    }
+    double d2[kIPT][kJU];
+#pragma unroll
+    for (int k = 0; k < kIPT; ++k) {
+#pragma unroll
+        for (int q = 0; q < kJU; ++q) {
+            // reference lib/include/basetrajectory.h:207-209: x = xi - xj
+            double dx = __dsub_rn(xi[k], xj[q]);
+            double dy = __dsub_rn(yi[k], yj[q]);
+            double dz = __dsub_rn(zi[k], zj[q]);
+            if (FAST) {
+                min_image_single<TRI>(dx, dy, dz, c.box, c.nLx, c.nLy, c.nLz);
+            } else {
+                wrap_ok &= min_image_general<TRI>(dx, dy, dz, c.box);
+            }
+            d2[k][q] = d2_of(dx, dy, dz);
+        }
+    }
+    if (MODE == MODE_EDGES) {
+#pragma unroll
+        for (int k = 0; k < kIPT; ++k) {
+#pragma unroll
+            for (int q = 0; q < kJU; ++q) {
+                const unsigned int r = row[k] + ((DIAG && ii[k] == j + q) ? self_off : 0u);
+                bin_pair_edges(d2[k][q], s_thrf, p.nbin, p.inv_dr, p.c0, p.rmin2, p.rmax2, s_hist, r, edges);
+            }
+        }
+        return;
+    }
+    // group filter on the high words (d2 >= 0 or NaN: the unsigned high word is monotone in d2);
+    // only the upper end is tested here, the exact range test is in the binning
+    unsigned int m = 0xffffffffu;
+#pragma unroll
+    for (int k = 0; k < kIPT; ++k) {
+#pragma unroll
+        for (int q = 0; q < kJU; ++q) m = min(m, static_cast<unsigned int>(__double2hiint(d2[k][q])));
+    }
+    if (m > p.hhi) return;
+
+    unsigned int mask = 0;
+    if (MODE == MODE_SAFE) {
+#pragma unroll
+        for (int k = 0; k < kIPT; ++k) {
+#pragma unroll
+            for (int q = 0; q < kJU; ++q) {
+                const unsigned int r = row[k] + ((DIAG && ii[k] == j + q) ? self_off : 0u);
+                // byte address of hist[r + n] = hist_addr + 4*(r + bits(rounded) - 0x4B400000)
+                const uint32_t adj = c.hist_addr + 4u * r - 4u * 0x4B400000u;
+                bin_pair_safe(d2[k][q], adj, p.inv_dr, p.c0h, p.lim, static_cast<unsigned int>(p.nbin), mask,
+                              1u << (k * kJU + q));
+            }
+        }
+    } else if (MODE == MODE_THR) {
+        const unsigned int nbin2 = static_cast<unsigned int>(p.nbin) + 2u;
+#pragma unroll
+        for (int k = 0; k < kIPT; ++k) {
+#pragma unroll
+            for (int q = 0; q < kJU; ++q) {
+                const unsigned int r = row[k] + ((DIAG && ii[k] == j + q) ? self_off : 0u);
+                const unsigned int miss =
+                    bin_pair_thr(d2[k][q], c.thr2_addr, c.hist_addr + 4u * r - 4u, p.inv_dr, p.c0, nbin2);
+                const unsigned int h = static_cast<unsigned int>(__double2hiint(d2[k][q]));
+                if (miss && (h - p.hlo <= p.hspan)) mask |= 1u << (k * kJU + q);
+            }
+        }
+    } else {  // MODE_AGG: every candidate pair through the generic path with warp aggregation
+        const unsigned int nbin2 = static_cast<unsigned int>(p.nbin) + 2u;
+#pragma unroll
+        for (int k = 0; k < kIPT; ++k) {
+#pragma unroll
+            for (int q = 0; q < kJU; ++q) {
+                const double v = d2[k][q];
+                const unsigned int h = static_cast<unsigned int>(__double2hiint(v));
+                if (h - p.hlo <= p.hspan) {
+                    const unsigned int r = row[k] + ((DIAG && ii[k] == j + q) ? self_off : 0u);
+                    const unsigned int gi = bin_guess1(v, p.inv_dr, p.c0, nbin2);
+                    const double2 t = s_thr2[gi];
+                    if ((v >= t.x) && (v < t.y))
+                        hist_add<true>(s_hist, r + gi - 1u);
+                    else
+                        bin_pair_slow<true>(v, s_thr2, p.nbin, p.inv_dr, p.c0, s_hist, r);
+                }
+            }
+        }
+    }
+    if (mask) {
+#pragma unroll
+        for (int k = 0; k < kIPT; ++k) {
+#pragma unroll
+            for (int q = 0; q < kJU; ++q) {
+                if (mask & (1u << (k * kJU + q))) {
+                    const unsigned int r = row[k] + ((DIAG && ii[k] == j + q) ? self_off : 0u);
+                    bin_pair_slow<false>(d2[k][q], s_thr2, p.nbin, p.inv_dr, p.c0, s_hist, r);
+                }
+            }
+        }
+    }
+}
+
+template <bool TRI, bool FAST, int MODE>
 __global__ void __launch_bounds__(kThreads, 2) pair_kernel(const PairParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
+    constexpr bool EDGES = MODE == MODE_EDGES;
     const SmemLayout L = smem_layout(p.ntypes, p.nbin, EDGES);
     double *s_stage = reinterpret_cast<double *>(smem + L.stage);
-    double *s_thr = reinterpret_cast<double *>(smem + L.thr);
+    double2 *s_thr2 = reinterpret_cast<double2 *>(smem + L.thr2);
     double *s_thrf = reinterpret_cast<double *>(smem + L.thr_full);
     uint64_t *s_bar = reinterpret_cast<uint64_t *>(smem + L.bars);
     unsigned int *s_hist = reinterpret_cast<unsigned int *>(smem + L.hist);
@@ -256,10 +467,20 @@ __global__ void __launch_bounds__(kThreads, 2) pair_kernel(const PairParams p) {
     const unsigned int self_off = static_cast<unsigned int>(P * nbin);
 
     for (int k = tid; k < hlen; k += kThreads) s_hist[k] = 0u;
-    for (int k = tid; k <= nbin; k += kThreads) {
-        s_thr[k] = p.thr[k];
-        if (EDGES) s_thrf[k] = p.thr_full[k];
+    for (int k = tid; k < nbin + 3; k += kThreads) {
+        // slot k <-> bin g = k-1
+        const int g = k - 1;
+        double2 t;
+        if (g >= 0 && g < nbin) {
+            t.x = p.thr[g];
+            t.y = p.thr[g + 1];
+        } else {
+            t.x = t.y = INFINITY;
+        }
+        s_thr2[k] = t;
     }
+    if (EDGES)
+        for (int k = tid; k <= nbin; k += kThreads) s_thrf[k] = p.thr_full[k];
     for (int k = tid; k < nt * nt; k += kThreads) {
         // Gofrt::get_itype, reference lib/include/gofrt.h:86-104
         int a = k / nt, b = k % nt;
@@ -276,6 +497,11 @@ __global__ void __launch_bounds__(kThreads, 2) pair_kernel(const PairParams p) {
         mbar_fence_init();
     }
     __syncthreads();
+
+    PairConst c;
+    c.thr2_addr = smem_u32(s_thr2);
+    c.hist_addr = smem_u32(s_hist);
+    const uint32_t stage_addr = smem_u32(s_stage);
 
     int cur_t = -1;
     unsigned long long acc_pairs = 0;
@@ -316,41 +542,26 @@ __global__ void __launch_bounds__(kThreads, 2) pair_kernel(const PairParams p) {
         }
         acc_pairs += unit_pairs;
 
-        // ---- this thread's i atoms (frame fi) and the box of frame fi ----
+        // ---- the box of frame fi (used for both atoms, reference basetrajectory.h:190-191) ----
         const double *bx = p.box + static_cast<size_t>(job.fi) * 6;
-        BoxRegs breg;
-        breg.lhx = __ldg(bx + 0);
-        breg.lhy = __ldg(bx + 1);
-        breg.lhz = __ldg(bx + 2);
-        breg.xy = __ldg(bx + 3);
-        breg.xz = __ldg(bx + 4);
-        breg.yz = __ldg(bx + 5);
-        BoxBits bb;
-        if (FAST) {
-            bb.lhx = breg.lhx;
-            bb.lhy = breg.lhy;
-            bb.lhz = breg.lhz;
-            const double Lx = __dmul_rn(breg.lhx, 2.0), Ly = __dmul_rn(breg.lhy, 2.0), Lz = __dmul_rn(breg.lhz, 2.0);
-            bb.Lx_hi = __double2hiint(Lx);
-            bb.Lx_lo = __double2loint(Lx);
-            bb.Ly_hi = __double2hiint(Ly);
-            bb.Ly_lo = __double2loint(Ly);
-            bb.Lz_hi = __double2hiint(Lz);
-            bb.Lz_lo = __double2loint(Lz);
-            bb.xy_hi = __double2hiint(breg.xy);
-            bb.xy_lo = __double2loint(breg.xy);
-            bb.xz_hi = __double2hiint(breg.xz);
-            bb.xz_lo = __double2loint(breg.xz);
-            bb.yz_hi = __double2hiint(breg.yz);
-            bb.yz_lo = __double2loint(breg.yz);
-        }
+        c.box.lhx = __ldg(bx + 0);
+        c.box.lhy = __ldg(bx + 1);
+        c.box.lhz = __ldg(bx + 2);
+        c.box.xy = __ldg(bx + 3);
+        c.box.xz = __ldg(bx + 4);
+        c.box.yz = __ldg(bx + 5);
+        c.nLx = __dmul_rn(c.box.lhx, -2.0);
+        c.nLy = __dmul_rn(c.box.lhy, -2.0);
+        c.nLz = __dmul_rn(c.box.lhz, -2.0);
 
+        // ---- this thread's i atoms (frame fi) ----
         double xi[kIPT], yi[kIPT], zi[kIPT];
         int ii[kIPT], ti[kIPT];
         const double *pi = p.pos + static_cast<size_t>(job.fi) * 3 * p.npad;
+        const int wi0 = itile * kTileI + warp * (32 * kIPT);  // this warp's i atoms: [wi0, wi0 + 32*kIPT)
 #pragma unroll
         for (int k = 0; k < kIPT; ++k) {
-            const int idx = itile * kTileI + warp * (32 * kIPT) + k * 32 + lane;
+            const int idx = wi0 + k * 32 + lane;
             ii[k] = idx;
             if (idx < p.npad) {
                 xi[k] = pi[idx];
@@ -384,9 +595,7 @@ __global__ void __launch_bounds__(kThreads, 2) pair_kernel(const PairParams p) {
             if (tid == 0 && tl + 1 < ntile) issue(tl + 1, gt + 1);
             mbar_wait(&s_bar[gt & 1u], (gt >> 1) & 1u);
 
-            const double *sx = s_stage + static_cast<size_t>(gt & 1u) * 3 * kTileJ;
-            const double *sy = sx + kTileJ;
-            const double *sz = sy + kTileJ;
+            const uint32_t sx_addr = stage_addr + (gt & 1u) * (3u * kTileJ * 8u);
             const int j0 = jbeg + tl * kTileJ;
             const int j1 = min(j0 + kTileJ, jend);
 
@@ -397,40 +606,21 @@ __global__ void __launch_bounds__(kThreads, 2) pair_kernel(const PairParams p) {
                 unsigned int row[kIPT];
 #pragma unroll
                 for (int k = 0; k < kIPT; ++k) row[k] = s_rowtab[ti[k] * nt + ty];
-
+                // [lo,hi) = before | overlap with this warp's own atoms | after   (all multiples of kPadGroup)
+                const int da = min(max(wi0, lo), hi);
+                const int db = min(max(wi0 + 32 * kIPT, lo), hi);
 #pragma unroll 1
-                for (int j = lo; j < hi; j += kJU) {
-                    const double2 xj = *reinterpret_cast<const double2 *>(sx + (j - j0));
-                    const double2 yj = *reinterpret_cast<const double2 *>(sy + (j - j0));
-                    const double2 zj = *reinterpret_cast<const double2 *>(sz + (j - j0));
-                    const double xjv[2] = {xj.x, xj.y}, yjv[2] = {yj.x, yj.y}, zjv[2] = {zj.x, zj.y};
-#pragma unroll
-                    for (int k = 0; k < kIPT; ++k) {
-#pragma unroll
-                        for (int q = 0; q < kJU; ++q) {
-                            // reference lib/include/basetrajectory.h:207-209: x = xi - xj
-                            double dx = __dsub_rn(xi[k], xjv[q]);
-                            double dy = __dsub_rn(yi[k], yjv[q]);
-                            double dz = __dsub_rn(zi[k], zjv[q]);
-                            if (FAST) {
-                                min_image_single<TRI>(dx, dy, dz, bb);
-                            } else {
-                                wrap_ok &= min_image_general<TRI>(dx, dy, dz, breg);
-                            }
-                            const double d2 = d2_of(dx, dy, dz);
-                            if (EDGES) {
-                                const unsigned int r = row[k] + ((ii[k] == j + q) ? self_off : 0u);
-                                bin_pair_edges(d2, s_thrf, nbin, p.inv_dr, p.c0, p.rmin2, p.rmax2, s_hist, r, edges);
-                            } else {
-                                const unsigned int h = static_cast<unsigned int>(__double2hiint(d2));
-                                if (h - p.hlo <= p.hspan) {
-                                    const unsigned int r = row[k] + ((ii[k] == j + q) ? self_off : 0u);
-                                    bin_pair<AGG>(d2, s_thr, nbin, p.inv_dr, p.c0, s_hist, r);
-                                }
-                            }
-                        }
-                    }
-                }
+                for (int j = lo; j < da; j += kJU)
+                    process_group<TRI, FAST, MODE, false>(p, c, xi, yi, zi, ii, row, sx_addr, j - j0, j, s_thr2, s_thrf,
+                                                          s_hist, self_off, edges, wrap_ok);
+#pragma unroll 1
+                for (int j = da; j < db; j += kJU)
+                    process_group<TRI, FAST, MODE, true>(p, c, xi, yi, zi, ii, row, sx_addr, j - j0, j, s_thr2, s_thrf,
+                                                         s_hist, self_off, edges, wrap_ok);
+#pragma unroll 1
+                for (int j = db; j < hi; j += kJU)
+                    process_group<TRI, FAST, MODE, false>(p, c, xi, yi, zi, ii, row, sx_addr, j - j0, j, s_thr2, s_thrf,
+                                                          s_hist, self_off, edges, wrap_ok);
             }
         }
     }
@@ -451,48 +641,69 @@ __global__ void __launch_bounds__(kThreads, 2) pair_kernel(const PairParams p) {
     if (!wrap_ok) atomicExch(p.error_flag, 1u);
 }
 
+// variant = TRI | FAST<<1 | MODE<<2
 template <int V>
 static cudaError_t launch_variant(int grid, size_t smem, cudaStream_t stream, const PairParams &p) {
-    constexpr bool TRI = (V & 1) != 0, FAST = (V & 2) != 0, AGG = (V & 4) != 0, EDGES = (V & 8) != 0;
-    pair_kernel<TRI, FAST, AGG, EDGES><<<grid, kThreads, smem, stream>>>(p);
+    pair_kernel<(V & 1) != 0, (V & 2) != 0, (V >> 2)><<<grid, kThreads, smem, stream>>>(p);
     return cudaGetLastError();
 }
 
 template <int V>
 static cudaError_t prepare_variant(size_t max_smem) {
-    constexpr bool TRI = (V & 1) != 0, FAST = (V & 2) != 0, AGG = (V & 4) != 0, EDGES = (V & 8) != 0;
-    return cudaFuncSetAttribute(pair_kernel<TRI, FAST, AGG, EDGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                static_cast<int>(max_smem));
+    return cudaFuncSetAttribute(pair_kernel<(V & 1) != 0, (V & 2) != 0, (V >> 2)>,
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(max_smem));
 }
 
-// EDGES variants never aggregate (tests only): 8..11
 cudaError_t launch_pair_kernel(int variant, int grid, size_t smem, cudaStream_t stream, const PairParams &p) {
     switch (variant) {
-        case 0: return launch_variant<0>(grid, smem, stream, p);
-        case 1: return launch_variant<1>(grid, smem, stream, p);
-        case 2: return launch_variant<2>(grid, smem, stream, p);
-        case 3: return launch_variant<3>(grid, smem, stream, p);
-        case 4: return launch_variant<4>(grid, smem, stream, p);
-        case 5: return launch_variant<5>(grid, smem, stream, p);
-        case 6: return launch_variant<6>(grid, smem, stream, p);
-        case 7: return launch_variant<7>(grid, smem, stream, p);
-        case 8: return launch_variant<8>(grid, smem, stream, p);
-        case 9: return launch_variant<9>(grid, smem, stream, p);
-        case 10: return launch_variant<10>(grid, smem, stream, p);
-        case 11: return launch_variant<11>(grid, smem, stream, p);
+#define AGOFRT_CASE(V) \
+    case V: return launch_variant<V>(grid, smem, stream, p);
+        AGOFRT_CASE(0) AGOFRT_CASE(1) AGOFRT_CASE(2) AGOFRT_CASE(3) AGOFRT_CASE(4) AGOFRT_CASE(5) AGOFRT_CASE(6)
+        AGOFRT_CASE(7) AGOFRT_CASE(8) AGOFRT_CASE(9) AGOFRT_CASE(10) AGOFRT_CASE(11) AGOFRT_CASE(12) AGOFRT_CASE(13)
+        AGOFRT_CASE(14) AGOFRT_CASE(15)
+#undef AGOFRT_CASE
         default: return cudaErrorInvalidValue;
     }
 }
 
 cudaError_t prepare_pair_kernels(size_t max_smem) {
     cudaError_t e;
-#define AGOFRT_PREP(V)                       \
-    e = prepare_variant<V>(max_smem);        \
+#define AGOFRT_PREP(V)                \
+    e = prepare_variant<V>(max_smem); \
     if (e != cudaSuccess) return e;
     AGOFRT_PREP(0) AGOFRT_PREP(1) AGOFRT_PREP(2) AGOFRT_PREP(3) AGOFRT_PREP(4) AGOFRT_PREP(5) AGOFRT_PREP(6)
-    AGOFRT_PREP(7) AGOFRT_PREP(8) AGOFRT_PREP(9) AGOFRT_PREP(10) AGOFRT_PREP(11)
+    AGOFRT_PREP(7) AGOFRT_PREP(8) AGOFRT_PREP(9) AGOFRT_PREP(10) AGOFRT_PREP(11) AGOFRT_PREP(12) AGOFRT_PREP(13)
+    AGOFRT_PREP(14) AGOFRT_PREP(15)
 #undef AGOFRT_PREP
     return cudaSuccess;
+}
+
+// Device-side validation of MODE_SAFE's float guess (run once per plan): for every probe value the
+// guess must either be flagged "within eps of an edge" or equal the exact bin expected[k].
+__global__ void validate_safe_kernel(const double *__restrict__ probes, const int *__restrict__ expected, int n,
+                                     float inv_dr, float c0h, float lim, int nbin, unsigned int *bad) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const float s = sqrt_approx(d2_as_float(probes[k]));
+    float q = fminf(fmaf(s, inv_dr, c0h), 4194304.0f);
+    const float r = __fadd_rn(q, 12582912.0f);
+    const float nn = __fadd_rn(r, -12582912.0f);
+    const float dl = fabsf(__fsub_rn(q, nn));
+    const bool safe = dl < lim;
+    const int g = __float_as_int(r) - 0x4B400000;
+    const int e = expected[k];  // exact bin, or -1 / nbin when outside
+    if (safe) {
+        const bool counted = static_cast<unsigned int>(g) < static_cast<unsigned int>(nbin);
+        const bool should = e >= 0 && e < nbin;
+        if (counted != should || (counted && g != e)) atomicAdd(bad, 1u);
+    }
+}
+
+cudaError_t launch_validate_safe(const double *probes, const int *expected, int n, float inv_dr, float c0h, float lim,
+                                 int nbin, unsigned int *bad, cudaStream_t stream) {
+    if (n <= 0) return cudaSuccess;
+    validate_safe_kernel<<<(n + 255) / 256, 256, 0, stream>>>(probes, expected, n, inv_dr, c0h, lim, nbin, bad);
+    return cudaGetLastError();
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -563,15 +774,16 @@ cudaError_t launch_pack_box(const double *box_internal, int stride, int nframes,
     return cudaGetLastError();
 }
 
-__global__ void frame_bounds_kernel(const double *__restrict__ pos_soa, int npad, double *__restrict__ bounds,
-                                    unsigned int *inf_flag) {
+__global__ void frame_bounds_kernel(const double *__restrict__ pos_soa, const int *__restrict__ perm, int npad,
+                                    double *__restrict__ bounds, unsigned int *inf_flag) {
     const int f = blockIdx.x, c = blockIdx.y;
     const double *row = pos_soa + (static_cast<size_t>(f) * 3 + c) * npad;
     double lo = INFINITY, hi = -INFINITY;
-    bool inf = false;
+    bool inf = false, nan = false;
     for (int k = threadIdx.x; k < npad; k += blockDim.x) {
         const double v = row[k];
         if (isinf(v)) inf = true;
+        if (v != v && perm[k] >= 0) nan = true;  // a NaN that is not a ghost slot
         lo = fmin(lo, v);  // fmin/fmax drop NaN (ghost slots, NaN input)
         hi = fmax(hi, v);
     }
@@ -586,6 +798,7 @@ __global__ void frame_bounds_kernel(const double *__restrict__ pos_soa, int npad
         shi[w] = hi;
     }
     if (inf) atomicExch(inf_flag, 1u);
+    if (nan) atomicExch(inf_flag + 2, 1u);
     __syncthreads();
     if (threadIdx.x == 0) {
         const int nw = blockDim.x >> 5;
@@ -598,11 +811,11 @@ __global__ void frame_bounds_kernel(const double *__restrict__ pos_soa, int npad
     }
 }
 
-cudaError_t launch_frame_bounds(const double *pos_soa, int npad, int nframes, double *bounds6, unsigned int *inf_flag,
-                                cudaStream_t stream) {
+cudaError_t launch_frame_bounds(const double *pos_soa, const int *perm, int npad, int nframes, double *bounds6,
+                                unsigned int *inf_flag, cudaStream_t stream) {
     if (nframes <= 0) return cudaSuccess;
     dim3 grid(nframes, 3);
-    frame_bounds_kernel<<<grid, 256, 0, stream>>>(pos_soa, npad, bounds6, inf_flag);
+    frame_bounds_kernel<<<grid, 256, 0, stream>>>(pos_soa, perm, npad, bounds6, inf_flag);
     return cudaGetLastError();
 }
 

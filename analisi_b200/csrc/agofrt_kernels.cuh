@@ -24,7 +24,7 @@ constexpr int kTileI = kThreads * kIPT;     // i atoms per work unit
 constexpr int kTileJ = 512;                 // j atoms per shared-memory stage
 constexpr int kStages = 2;                  // bulk-copy stages
 constexpr int kPadGroup = 8;                // every type group is padded to a multiple of this
-constexpr int kJU = 2;                      // j atoms per inner step (one LDS.128 per coordinate)
+constexpr int kJU = 4;                      // j atoms per inner step (two LDS.128 per coordinate)
 constexpr int kWrapCap = 1 << 20;           // images the general minimum image may add per dimension
 
 struct Job {
@@ -50,12 +50,14 @@ struct PairParams {
     int npad, ntypes, nbin;
     int n_itiles, n_jchunks, jchunk;  // jchunk is a multiple of kTileJ
     float inv_dr, c0;                 // bin guess = floor(sqrtf(d2) * inv_dr + c0)
-    unsigned hlo, hspan;              // candidate test on the high word of d2
+    float c0h, lim;                   // MODE_SAFE: c0 - 0.5 and 0.5 - eps
+    unsigned hlo, hspan, hhi;         // candidate tests on the high word of d2 (hhi = hlo + hspan)
 };
 
 size_t pair_kernel_smem_bytes(int ntypes, int nbin, bool edges);
 
-// variant = TRI | FAST<<1 | AGG<<2 | EDGES<<3
+// variant = TRI | FAST<<1 | MODE<<2, MODE: 0 thresholds, 1 thresholds + warp aggregation, 2 edges, 3 safe-zone
+enum { kModeThr = 0, kModeAgg = 1, kModeEdges = 2, kModeSafe = 3 };
 cudaError_t launch_pair_kernel(int variant, int grid, size_t smem, cudaStream_t stream, const PairParams &p);
 cudaError_t prepare_pair_kernels(size_t max_smem_optin);
 
@@ -69,8 +71,8 @@ cudaError_t launch_scatter_aos(const double *pos_soa_frame, const int *perm, int
 cudaError_t launch_pack_box(const double *box_internal, int stride, int nframes, double *box6,
                             cudaStream_t stream);
 // per frame: min x,y,z, max x,y,z (NaN ignored), and a flag if any coordinate is +-inf
-cudaError_t launch_frame_bounds(const double *pos_soa, int npad, int nframes, double *bounds6,
-                                unsigned int *inf_flag, cudaStream_t stream);
+cudaError_t launch_frame_bounds(const double *pos_soa, const int *perm, int npad, int nframes, double *bounds6,
+                                unsigned int *flags /* [0] inf seen, [2] NaN in a real atom */, cudaStream_t stream);
 // BaseTrajectory::pbc_wrap on AoS positions
 cudaError_t launch_pbc_wrap(double *pos_aos, int natoms, int nframes, const double *box_internal,
                             int stride, unsigned int *error_flag, cudaStream_t stream);
@@ -78,6 +80,9 @@ cudaError_t launch_pbc_wrap(double *pos_aos, int natoms, int nframes, const doub
 cudaError_t launch_d2_all(const double *pos_i, const double *pos_j, const double *box6, int triclinic,
                           const int *perm, int natoms, int npad, double *out, unsigned int *error_flag,
                           cudaStream_t stream);
+// MODE_SAFE validation: bad += number of probes whose unflagged float guess differs from expected[]
+cudaError_t launch_validate_safe(const double *probes, const int *expected, int n, float inv_dr, float c0h, float lim,
+                                 int nbin, unsigned int *bad, cudaStream_t stream);
 // DFMA chains; *count_per_launch receives the number of lane-level DFMAs one launch executes
 cudaError_t launch_dfma_peak(double *sink, int blocks, int iters, cudaStream_t stream,
                              unsigned long long *count_per_launch);

@@ -130,7 +130,8 @@ enum {
     AGOFRT_OPT_EDGES = 1,          /* also count the pairs within 1 ulp of a bin edge            */
     AGOFRT_OPT_FORCE_GENERAL = 2,  /* never take the single-pass minimum-image kernel            */
     AGOFRT_OPT_NO_AGGREGATE = 4,   /* plain shared atomics instead of __match_any_sync merging   */
-    AGOFRT_OPT_AGGREGATE = 8       /* force warp-aggregated shared atomics                       */
+    AGOFRT_OPT_AGGREGATE = 8,      /* force warp-aggregated shared atomics                       */
+    AGOFRT_OPT_NO_SAFE = 16        /* bracket every guess against the exact thresholds (no safe-zone shortcut) */
 };
 
 typedef struct {
@@ -143,7 +144,7 @@ typedef struct {
     uint32_t launches;         /* kernels launched by this call on this context                    */
     uint32_t ndev_local;
     uint32_t world;
-    uint32_t reserved;
+    uint32_t kernel_modes;     /* bit m set: a pair kernel of binning mode m ran (0 thresholds, 1 aggregated, 2 edges, 3 safe-zone) */
 } agofrt_stats;
 
 /* counts_out [leff][ntypes*(ntypes+1)][nbin] (host, uint64): the number of ordered pairs (i,j)
