@@ -40,16 +40,23 @@ def stale():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
-    """Compile libagofrt.so if it is missing or older than its sources; return its path."""
+def build(force=False, verbose=False, defs=None, out=None):
+    """Compile libagofrt.so if it is missing or older than its sources; return its path.
+
+    ``defs`` (e.g. ["-DAGOFRT_IPT=4"]) and ``out`` build a tuning variant next to the product library."""
+    global LIB
+    if out is not None:
+        LIB = os.path.join(HERE, out)
+        force = True
     if not force and not stale():
         return LIB
     objs = []
     log = []
     for s in SOURCES:
         o = os.path.join(CSRC, s.replace(".cu", ".o"))
-        cmd = [nvcc()] + NVCC_FLAGS + ["-I", os.path.join(ROOT, "include"), "-I", CSRC, "-c",
-                                       os.path.join(CSRC, s), "-o", o]
+        o = o if out is None else o.replace(".o", "." + out + ".o")
+        cmd = [nvcc()] + NVCC_FLAGS + list(defs or []) + ["-I", os.path.join(ROOT, "include"), "-I", CSRC, "-c",
+                                                          os.path.join(CSRC, s), "-o", o]
         r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
         log.append(r.stdout)
         if r.returncode != 0:

@@ -10,11 +10,11 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libagofrt.so")
+LIB_PATH = os.environ.get("AGOFRT_LIB", os.path.join(_HERE, "libagofrt.so"))  # AGOFRT_LIB: tuning builds only
 
 OK = 0
 ERR_ARG, ERR_CUDA, ERR_WINDOW, ERR_NCCL, ERR_NONFINITE, ERR_TOO_LARGE, ERR_INTERNAL = -1, -2, -3, -4, -5, -6, -7
-OPT_EDGES, OPT_FORCE_GENERAL, OPT_NO_AGGREGATE, OPT_AGGREGATE, OPT_NO_SAFE = 1, 2, 4, 8, 16
+OPT_EDGES, OPT_FORCE_GENERAL, OPT_NO_AGGREGATE, OPT_AGGREGATE, OPT_NO_SAFE, OPT_DENSE, OPT_SPARSE = 1, 2, 4, 8, 16, 32, 64
 COMM_ID_BYTES = 128
 
 # every symbol include/agofrt.h declares (tests check the library exports all of them)

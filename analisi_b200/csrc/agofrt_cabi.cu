@@ -963,7 +963,7 @@ extern "C" int agofrt_block(agofrt_plan *p, size_t primo, unsigned ntimesteps, u
     // ---- work units ----
     const int n_itiles = std::max(1, (t->npad + kTileI - 1) / kTileI);
     int total_ctas = 0;
-    for (const Dev &d : ctx->devs) total_ctas += 2 * d.sm_count;
+    for (const Dev &d : ctx->devs) total_ctas += kMinBlocks * d.sm_count;
     total_ctas = total_ctas / nloc * world;
     int n_jchunks = 1;
     {
@@ -994,6 +994,21 @@ extern "C" int agofrt_block(agofrt_plan *p, size_t primo, unsigned ntimesteps, u
             reach = std::max(reach, std::sqrt(ex * ex + ey * ey + ez * ez));
         }
         if (!(reach / p->dr < p->q_reach)) use_safe = false;
+    }
+    // dense or sparse?  The share of pairs within rmax, from the sphere / cell volume ratio of the
+    // smallest cell of the window; above ~15% nearly every group of 8 pairs holds an in-range pair.
+    bool dense = false;
+    {
+        double vmin = std::numeric_limits<double>::infinity();
+        for (size_t f = 0; f < t->nframes; ++f) {
+            const double *b = &t->box6[f * 6];
+            vmin = std::min(vmin, 8.0 * b[0] * b[1] * b[2]);
+        }
+        const double rm = std::max(p->rmax, 0.0), r0 = std::max(p->rmin, 0.0);
+        const double share = 4.18879020478639 * (rm * rm * rm - r0 * r0 * r0) / vmin;
+        dense = share > 0.15;
+        if (options & AGOFRT_OPT_DENSE) dense = true;
+        if (options & AGOFRT_OPT_SPARSE) dense = false;
     }
     const size_t smem = pair_kernel_smem_bytes(nt, static_cast<int>(p->nbin), want_edges);
 
@@ -1084,9 +1099,9 @@ extern "C" int agofrt_block(agofrt_plan *p, size_t primo, unsigned ntimesteps, u
                 else if (aggregate)
                     mode = kModeAgg;
                 else if (pass == 0 && use_safe)
-                    mode = kModeSafe;
+                    mode = dense ? kModeSafeDense : kModeSafe;
                 const int variant = (tri ? 1 : 0) | (pass == 0 ? 2 : 0) | (mode << 2);
-                const int grid = static_cast<int>(std::min<uint64_t>(ue - ub, 2ull * dv.sm_count));
+                const int grid = static_cast<int>(std::min<uint64_t>(ue - ub, static_cast<uint64_t>(kMinBlocks) * dv.sm_count));
                 CU(cudaMemsetAsync(pd.counter, 0, sizeof(unsigned int), dv.stream));
                 CU(launch_pair_kernel(variant, grid, smem, dv.stream, pp));
                 ++launches;

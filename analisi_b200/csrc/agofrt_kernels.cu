@@ -162,7 +162,7 @@ __device__ __forceinline__ double d2_of(double dx, double dy, double dz) {
 // MODE_SAFE  float guess accepted without looking at the thresholds when it is farther than `eps`
 //            bins from a bin edge (eps bounds the float error, validated on the device when the plan
 //            is made); the few pairs closer than eps to an edge go through the exact bracket search
-enum { MODE_THR = 0, MODE_AGG = 1, MODE_EDGES = 2, MODE_SAFE = 3 };
+enum { MODE_THR = 0, MODE_AGG = 1, MODE_EDGES = 2, MODE_SAFE = 3, MODE_SAFE_DENSE = 4 };
 
 // float guess of the bin from the bits of d2 (no FP64 conversion instruction): rebias the
 // exponent, keep 23 mantissa bits, MUFU sqrt, one FFMA.  Returns guess+1 clamped to [0, nbin+2]:
@@ -257,27 +257,32 @@ __device__ __forceinline__ unsigned int bin_pair_thr(double v, uint32_t thr2_add
 // min.f32 returns the non-NaN operand: NaN (ghost slots) and absurdly large values land on QMAX,
 // which is "safe" and outside every histogram.  `mask |= bit` marks the pairs that need the exact
 // search.
-__device__ __forceinline__ void bin_pair_safe(double v, uint32_t row_addr_adj, float inv_dr, float c0h, float lim,
-                                              unsigned int nbin, unsigned int &mask, unsigned int bit) {
-    const float s = sqrt_approx(d2_as_float(v));
+__device__ __forceinline__ void bin_pair_safe(double v, uint32_t row_addr_adj, uint32_t dump_addr, float inv_dr,
+                                              float c0h, float lim, unsigned int nbin_fbits, unsigned int &mask,
+                                              unsigned int bit) {
+    float f;
+    asm("cvt.rz.f32.f64 %0, %1;" : "=f"(f) : "d"(v));   // +inf for huge, NaN stays NaN; sqrt.ftz flushes denormals
+    const float s = sqrt_approx(f);
+    // ptxas turns every predicated shared atomic into a branch around it (4 issue slots); an
+    // UNCONDITIONAL atomic whose address is switched to a per-lane dump word costs 2.
     asm volatile(
-        "{\n\t.reg .pred ps, pu;\n\t.reg .f32 q, r, n, dl;\n\t.reg .b32 ri, gi, ad;\n\t"
+        "{\n\t.reg .pred ps, pu;\n\t.reg .f32 q, r, n, dl;\n\t.reg .b32 ri, ni, ad;\n\t"
         "fma.rn.f32 q, %1, %2, %3;\n\t"
-        "min.f32 q, q, 0f4A800000;\n\t"          // 4194304.0
-        "add.rn.f32 r, q, 0f4B400000;\n\t"       // 1.5 * 2^23
+        "min.f32 q, q, 0f4A800000;\n\t"          // 4194304.0; NaN -> 4194304.0
+        "add.rn.f32 r, q, 0f4B400000;\n\t"       // 1.5 * 2^23: r = 1.5*2^23 + n, n = rint(q)
         "add.rn.f32 n, r, 0fCB400000;\n\t"
         "sub.rn.f32 dl, q, n;\n\t"
         "abs.f32 dl, dl;\n\t"
         "setp.lt.f32 ps|pu, dl, %4;\n\t"
+        "mov.b32 ni, n;\n\t"
+        "setp.lt.and.u32 ps, ni, %5, ps;\n\t"    // 0 <= n < nbin on the bit patterns (negative n: sign bit set)
         "mov.b32 ri, r;\n\t"
-        "sub.s32 gi, ri, 0x4B400000;\n\t"
-        "setp.lt.and.u32 ps, gi, %5, ps;\n\t"
-        "shl.b32 ad, ri, 2;\n\t"
-        "add.s32 ad, ad, %6;\n\t"
-        "@ps red.shared.add.u32 [ad], 1;\n\t"
+        "mad.lo.u32 ad, ri, 4, %6;\n\t"
+        "selp.b32 ad, ad, %8, ps;\n\t"
+        "red.shared.add.u32 [ad], 1;\n\t"
         "@pu or.b32 %0, %0, %7;\n\t}"
         : "+r"(mask)
-        : "f"(s), "f"(inv_dr), "f"(c0h), "f"(lim), "r"(nbin), "r"(row_addr_adj), "r"(bit)
+        : "f"(s), "f"(inv_dr), "f"(c0h), "f"(lim), "r"(nbin_fbits), "r"(row_addr_adj), "r"(bit), "r"(dump_addr)
         : "memory");
 }
 
@@ -285,7 +290,7 @@ __device__ __forceinline__ void bin_pair_safe(double v, uint32_t row_addr_adj, f
 // the pair kernel
 // ---------------------------------------------------------------------------------------------
 struct SmemLayout {
-    size_t thr2, thr_full, stage, hist, rowtab, tstart, bars, sched, total;
+    size_t thr2, thr_full, stage, hist, dump, rowtab, tstart, bars, sched, total;
 };
 
 __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -303,6 +308,8 @@ __host__ __device__ inline SmemLayout smem_layout(int ntypes, int nbin, bool edg
     o = L.bars + kStages * sizeof(uint64_t);
     L.hist = o;
     o += static_cast<size_t>(ntypes) * (ntypes + 1) * nbin * sizeof(unsigned int);
+    L.dump = o;
+    o += 32 * sizeof(unsigned int);
     L.rowtab = o;
     o += static_cast<size_t>(ntypes) * ntypes * sizeof(unsigned int);
     L.tstart = o;
@@ -320,19 +327,18 @@ struct PairConst {
     double nLx, nLy, nLz;   // -(2*l_half), exact
     uint32_t thr2_addr;     // shared-window address of thr2[0]
     uint32_t hist_addr;     // shared-window address of hist[0]
+    uint32_t dump_addr;     // this lane's dump word (unconditional atomics of pairs that are not counted)
 };
 
 // One group = kIPT i atoms (registers) x kJU j atoms (shared memory): all d2 first (straight-line,
 // independent FP64 chains), then one cheap test for "some pair of the group may be in range", then
 // the binning of the group's pairs without per-pair branches.
 //   DIAG: the j atoms may include one of this thread's own i atoms (i == j goes to the "self" rows).
-template <bool TRI, bool FAST, int MODE, bool DIAG>
-__device__ __forceinline__ void process_group(const PairParams &p, const PairConst &c, const double (&xi)[kIPT],
-                                              const double (&yi)[kIPT], const double (&zi)[kIPT],
-                                              const int (&ii)[kIPT], const unsigned int (&row)[kIPT],
-                                              uint32_t sx_addr, int jrel, int j, const double2 *s_thr2,
-                                              const double *s_thrf, unsigned int *s_hist, unsigned int self_off,
-                                              unsigned long long &edges, bool &wrap_ok) {
+// All kIPT x kJU squared distances of one group (straight-line, independent FP64 chains).
+template <bool TRI, bool FAST>
+__device__ __forceinline__ void group_distances(const PairConst &c, const double (&xi)[kIPT], const double (&yi)[kIPT],
+                                                const double (&zi)[kIPT], uint32_t sx_addr, int jrel,
+                                                double (&d2)[kIPT][kJU], bool &wrap_ok) {
     double xj[kJU], yj[kJU], zj[kJU];
 #pragma unroll
     for (int q = 0; q < kJU; q += 2) {
@@ -347,7 +353,6 @@ __device__ __forceinline__ void process_group(const PairParams &p, const PairCon
         zj[q] = vz.x;
         zj[q + 1] = vz.y;
     }
-    double d2[kIPT][kJU];
 #pragma unroll
     for (int k = 0; k < kIPT; ++k) {
 #pragma unroll
@@ -364,6 +369,48 @@ __device__ __forceinline__ void process_group(const PairParams &p, const PairCon
             d2[k][q] = d2_of(dx, dy, dz);
         }
     }
+}
+
+// Safe-zone binning of one group: no branch except the rare exact search.
+template <bool DIAG>
+__device__ __forceinline__ void group_bin_safe(const PairParams &p, const PairConst &c, const double (&d2)[kIPT][kJU],
+                                               const int (&ii)[kIPT], const unsigned int (&row)[kIPT], int j,
+                                               const double2 *s_thr2, unsigned int *s_hist, unsigned int self_off) {
+    unsigned int mask = 0;
+    const unsigned int nbin_fbits = __float_as_uint(static_cast<float>(p.nbin));
+#pragma unroll
+    for (int k = 0; k < kIPT; ++k) {
+#pragma unroll
+        for (int q = 0; q < kJU; ++q) {
+            const unsigned int r = row[k] + ((DIAG && ii[k] == j + q) ? self_off : 0u);
+            // byte address of hist[r + n] = hist_addr + 4*(r + bits(rounded) - 0x4B400000)
+            const uint32_t adj = c.hist_addr + 4u * r - 4u * 0x4B400000u;
+            bin_pair_safe(d2[k][q], adj, c.dump_addr, p.inv_dr, p.c0h, p.lim, nbin_fbits, mask, 1u << (k * kJU + q));
+        }
+    }
+    if (mask) {
+#pragma unroll
+        for (int k = 0; k < kIPT; ++k) {
+#pragma unroll
+            for (int q = 0; q < kJU; ++q) {
+                if (mask & (1u << (k * kJU + q))) {
+                    const unsigned int r = row[k] + ((DIAG && ii[k] == j + q) ? self_off : 0u);
+                    bin_pair_slow<false>(d2[k][q], s_thr2, p.nbin, p.inv_dr, p.c0, s_hist, r);
+                }
+            }
+        }
+    }
+}
+
+template <bool TRI, bool FAST, int MODE, bool DIAG>
+__device__ __forceinline__ void process_group(const PairParams &p, const PairConst &c, const double (&xi)[kIPT],
+                                              const double (&yi)[kIPT], const double (&zi)[kIPT],
+                                              const int (&ii)[kIPT], const unsigned int (&row)[kIPT],
+                                              uint32_t sx_addr, int jrel, int j, const double2 *s_thr2,
+                                              const double *s_thrf, unsigned int *s_hist, unsigned int self_off,
+                                              unsigned long long &edges, bool &wrap_ok) {
+    double d2[kIPT][kJU];
+    group_distances<TRI, FAST>(c, xi, yi, zi, sx_addr, jrel, d2, wrap_ok);
     if (MODE == MODE_EDGES) {
 #pragma unroll
         for (int k = 0; k < kIPT; ++k) {
@@ -383,22 +430,14 @@ __device__ __forceinline__ void process_group(const PairParams &p, const PairCon
 #pragma unroll
         for (int q = 0; q < kJU; ++q) m = min(m, static_cast<unsigned int>(__double2hiint(d2[k][q])));
     }
-    if (m > p.hhi) return;
+    if (MODE != MODE_SAFE_DENSE && m > p.hhi) return;
 
+    if (MODE == MODE_SAFE || MODE == MODE_SAFE_DENSE) {
+        group_bin_safe<DIAG>(p, c, d2, ii, row, j, s_thr2, s_hist, self_off);
+        return;
+    }
     unsigned int mask = 0;
-    if (MODE == MODE_SAFE) {
-#pragma unroll
-        for (int k = 0; k < kIPT; ++k) {
-#pragma unroll
-            for (int q = 0; q < kJU; ++q) {
-                const unsigned int r = row[k] + ((DIAG && ii[k] == j + q) ? self_off : 0u);
-                // byte address of hist[r + n] = hist_addr + 4*(r + bits(rounded) - 0x4B400000)
-                const uint32_t adj = c.hist_addr + 4u * r - 4u * 0x4B400000u;
-                bin_pair_safe(d2[k][q], adj, p.inv_dr, p.c0h, p.lim, static_cast<unsigned int>(p.nbin), mask,
-                              1u << (k * kJU + q));
-            }
-        }
-    } else if (MODE == MODE_THR) {
+    if (MODE == MODE_THR) {
         const unsigned int nbin2 = static_cast<unsigned int>(p.nbin) + 2u;
 #pragma unroll
         for (int k = 0; k < kIPT; ++k) {
@@ -446,7 +485,7 @@ __device__ __forceinline__ void process_group(const PairParams &p, const PairCon
 }
 
 template <bool TRI, bool FAST, int MODE>
-__global__ void __launch_bounds__(kThreads, 2) pair_kernel(const PairParams p) {
+__global__ void __launch_bounds__(kThreads, kMinBlocks) pair_kernel(const PairParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
     constexpr bool EDGES = MODE == MODE_EDGES;
     const SmemLayout L = smem_layout(p.ntypes, p.nbin, EDGES);
@@ -501,6 +540,7 @@ __global__ void __launch_bounds__(kThreads, 2) pair_kernel(const PairParams p) {
     PairConst c;
     c.thr2_addr = smem_u32(s_thr2);
     c.hist_addr = smem_u32(s_hist);
+    c.dump_addr = smem_u32(smem + L.dump) + 4u * static_cast<uint32_t>(lane);
     const uint32_t stage_addr = smem_u32(s_stage);
 
     int cur_t = -1;
@@ -609,6 +649,32 @@ __global__ void __launch_bounds__(kThreads, 2) pair_kernel(const PairParams p) {
                 // [lo,hi) = before | overlap with this warp's own atoms | after   (all multiples of kPadGroup)
                 const int da = min(max(wi0, lo), hi);
                 const int db = min(max(wi0 + 32 * kIPT, lo), hi);
+                if (MODE == MODE_SAFE_DENSE) {
+                    // off-diagonal ranges: software-pipelined; the (at most 32*kIPT wide) diagonal range: plain
+                    auto run = [&](int a, int b) {
+                        if (a >= b) return;
+                        double cur[kIPT][kJU];
+                        group_distances<TRI, FAST>(c, xi, yi, zi, sx_addr, a - j0, cur, wrap_ok);
+#pragma unroll 1
+                        for (int j = a; j < b; j += kJU) {
+                            double nxt[kIPT][kJU];
+                            const int jn = min(j + kJU, b - kJU);  // last turn: recompute the last group, unused
+                            group_distances<TRI, FAST>(c, xi, yi, zi, sx_addr, jn - j0, nxt, wrap_ok);
+                            group_bin_safe<false>(p, c, cur, ii, row, j, s_thr2, s_hist, self_off);
+#pragma unroll
+                            for (int k = 0; k < kIPT; ++k)
+#pragma unroll
+                                for (int q = 0; q < kJU; ++q) cur[k][q] = nxt[k][q];
+                        }
+                    };
+                    run(lo, da);
+#pragma unroll 1
+                    for (int j = da; j < db; j += kJU)
+                        process_group<TRI, FAST, MODE, true>(p, c, xi, yi, zi, ii, row, sx_addr, j - j0, j, s_thr2,
+                                                             s_thrf, s_hist, self_off, edges, wrap_ok);
+                    run(db, hi);
+                    continue;
+                }
 #pragma unroll 1
                 for (int j = lo; j < da; j += kJU)
                     process_group<TRI, FAST, MODE, false>(p, c, xi, yi, zi, ii, row, sx_addr, j - j0, j, s_thr2, s_thrf,
@@ -660,7 +726,7 @@ cudaError_t launch_pair_kernel(int variant, int grid, size_t smem, cudaStream_t 
     case V: return launch_variant<V>(grid, smem, stream, p);
         AGOFRT_CASE(0) AGOFRT_CASE(1) AGOFRT_CASE(2) AGOFRT_CASE(3) AGOFRT_CASE(4) AGOFRT_CASE(5) AGOFRT_CASE(6)
         AGOFRT_CASE(7) AGOFRT_CASE(8) AGOFRT_CASE(9) AGOFRT_CASE(10) AGOFRT_CASE(11) AGOFRT_CASE(12) AGOFRT_CASE(13)
-        AGOFRT_CASE(14) AGOFRT_CASE(15)
+        AGOFRT_CASE(14) AGOFRT_CASE(15) AGOFRT_CASE(18) AGOFRT_CASE(19)
 #undef AGOFRT_CASE
         default: return cudaErrorInvalidValue;
     }
@@ -673,7 +739,7 @@ cudaError_t prepare_pair_kernels(size_t max_smem) {
     if (e != cudaSuccess) return e;
     AGOFRT_PREP(0) AGOFRT_PREP(1) AGOFRT_PREP(2) AGOFRT_PREP(3) AGOFRT_PREP(4) AGOFRT_PREP(5) AGOFRT_PREP(6)
     AGOFRT_PREP(7) AGOFRT_PREP(8) AGOFRT_PREP(9) AGOFRT_PREP(10) AGOFRT_PREP(11) AGOFRT_PREP(12) AGOFRT_PREP(13)
-    AGOFRT_PREP(14) AGOFRT_PREP(15)
+    AGOFRT_PREP(14) AGOFRT_PREP(15) AGOFRT_PREP(18) AGOFRT_PREP(19)
 #undef AGOFRT_PREP
     return cudaSuccess;
 }
@@ -684,7 +750,9 @@ __global__ void validate_safe_kernel(const double *__restrict__ probes, const in
                                      float inv_dr, float c0h, float lim, int nbin, unsigned int *bad) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
-    const float s = sqrt_approx(d2_as_float(probes[k]));
+    float f;
+    asm("cvt.rz.f32.f64 %0, %1;" : "=f"(f) : "d"(probes[k]));
+    const float s = sqrt_approx(f);
     float q = fminf(fmaf(s, inv_dr, c0h), 4194304.0f);
     const float r = __fadd_rn(q, 12582912.0f);
     const float nn = __fadd_rn(r, -12582912.0f);
@@ -693,7 +761,8 @@ __global__ void validate_safe_kernel(const double *__restrict__ probes, const in
     const int g = __float_as_int(r) - 0x4B400000;
     const int e = expected[k];  // exact bin, or -1 / nbin when outside
     if (safe) {
-        const bool counted = static_cast<unsigned int>(g) < static_cast<unsigned int>(nbin);
+        const bool counted = __float_as_uint(nn) < __float_as_uint(static_cast<float>(nbin));
+        if (counted && (static_cast<unsigned int>(g) >= static_cast<unsigned int>(nbin))) atomicAdd(bad, 1u);
         const bool should = e >= 0 && e < nbin;
         if (counted != should || (counted && g != e)) atomicAdd(bad, 1u);
     }

@@ -18,13 +18,23 @@
 
 namespace agofrt {
 
+#ifndef AGOFRT_IPT
+#define AGOFRT_IPT 2
+#endif
+#ifndef AGOFRT_JU
+#define AGOFRT_JU 4
+#endif
+#ifndef AGOFRT_MINBLOCKS
+#define AGOFRT_MINBLOCKS 2
+#endif
 constexpr int kThreads = 256;               // threads per CTA
-constexpr int kIPT = 2;                     // i atoms held in registers per thread
+constexpr int kMinBlocks = AGOFRT_MINBLOCKS; // CTAs per SM the register budget is sized for
+constexpr int kIPT = AGOFRT_IPT;            // i atoms held in registers per thread
 constexpr int kTileI = kThreads * kIPT;     // i atoms per work unit
 constexpr int kTileJ = 512;                 // j atoms per shared-memory stage
 constexpr int kStages = 2;                  // bulk-copy stages
 constexpr int kPadGroup = 8;                // every type group is padded to a multiple of this
-constexpr int kJU = 4;                      // j atoms per inner step (two LDS.128 per coordinate)
+constexpr int kJU = AGOFRT_JU;              // j atoms per inner step (one LDS.128 per coordinate per two)
 constexpr int kWrapCap = 1 << 20;           // images the general minimum image may add per dimension
 
 struct Job {
@@ -56,8 +66,9 @@ struct PairParams {
 
 size_t pair_kernel_smem_bytes(int ntypes, int nbin, bool edges);
 
-// variant = TRI | FAST<<1 | MODE<<2, MODE: 0 thresholds, 1 thresholds + warp aggregation, 2 edges, 3 safe-zone
-enum { kModeThr = 0, kModeAgg = 1, kModeEdges = 2, kModeSafe = 3 };
+// variant = TRI | FAST<<1 | MODE<<2, MODE: 0 thresholds, 1 thresholds + warp aggregation, 2 edges, 3 safe-zone,
+// 4 safe-zone software-pipelined for dense in-range workloads
+enum { kModeThr = 0, kModeAgg = 1, kModeEdges = 2, kModeSafe = 3, kModeSafeDense = 4 };  // dense: FAST only (variants 18, 19)
 cudaError_t launch_pair_kernel(int variant, int grid, size_t smem, cudaStream_t stream, const PairParams &p);
 cudaError_t prepare_pair_kernels(size_t max_smem_optin);
 

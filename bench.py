@@ -24,6 +24,7 @@ block are sharded over the ranks, one NCCL all-reduce of the integer histograms 
 ("strong" scaling: the total work per step is fixed).
 """
 import argparse
+import dataclasses
 import json
 import os
 import subprocess
@@ -57,8 +58,14 @@ def block_spec(name, quick=False):
         nts = 1899 if not quick else 64
         return w, nts, 0
     if name == "C3":
+        if quick:
+            w = dataclasses.replace(w, tmax=4, skip=15)
+            return w, 120, 0
         return w, 960, 0
     if name == "C4":
+        if quick:
+            w = dataclasses.replace(w, tmax=4, skip=12)
+            return w, 48, 0
         return w, 768, 0
     raise SystemExit("workload %s is not a single-block bench workload" % name)
 

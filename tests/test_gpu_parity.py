@@ -52,7 +52,7 @@ def test_gofr_notebook_golden(ctx):
                        skip=int(skip))
     assert np.array_equal(c, z["counts"])
     assert st["jobs_fast"] == st["jobs"]  # wrapped orthorhombic input: single-pass minimum image proven
-    assert st["kernel_modes"] == 1 << 3   # ... binned by the safe-zone kernel
+    assert st["kernel_modes"] in (1 << 3, 1 << 4)   # ... binned by a safe-zone kernel
 
 
 def test_min_image_and_pbc_golden(ctx):
@@ -77,7 +77,8 @@ def test_min_image_and_pbc_golden(ctx):
 
 
 @pytest.mark.parametrize("name", LIVE_CASES)
-@pytest.mark.parametrize("options", [0, cabi.OPT_FORCE_GENERAL, cabi.OPT_AGGREGATE, cabi.OPT_NO_SAFE])
+@pytest.mark.parametrize("options", [0, cabi.OPT_FORCE_GENERAL, cabi.OPT_AGGREGATE, cabi.OPT_NO_SAFE,
+                                     cabi.OPT_DENSE, cabi.OPT_SPARSE])
 def test_live_reference_cases(ctx, name, options):
     """Fixtures computed by the compiled reference: triclinic, NPT, unwrapped, big tilt, ragged loops."""
     d = live_case(name)
@@ -152,6 +153,9 @@ def test_multi_tile_random(ctx, triclinic):
     assert np.array_equal(c2, co)
     c3, st3 = gpu_counts(ctx, pos, bi, types, 2, *args, skip=2, options=cabi.OPT_NO_SAFE)
     assert np.array_equal(c3, co) and st3["kernel_modes"] == 1
+    for opt, bit in ((cabi.OPT_DENSE, 4), (cabi.OPT_SPARSE, 3)):
+        c4, st4 = gpu_counts(ctx, pos, bi, types, 2, *args, skip=2, options=opt)
+        assert np.array_equal(c4, co) and st4["kernel_modes"] == 1 << bit
     # every ordered pair with d2 in range lands somewhere: lag 0, self slot, bin 0 holds exactly N per origin
     n0, n1 = int((types == 0).sum()), int((types == 1).sum())
     assert c[0, 3 + 2, 0] == 2 * n0 and c[0, 3 + 1, 0] == 2 * n1
