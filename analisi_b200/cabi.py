@@ -14,7 +14,7 @@ LIB_PATH = os.environ.get("AGOFRT_LIB", os.path.join(_HERE, "libagofrt.so"))  # 
 
 OK = 0
 ERR_ARG, ERR_CUDA, ERR_WINDOW, ERR_NCCL, ERR_NONFINITE, ERR_TOO_LARGE, ERR_INTERNAL = -1, -2, -3, -4, -5, -6, -7
-OPT_EDGES, OPT_FORCE_GENERAL, OPT_NO_AGGREGATE, OPT_AGGREGATE, OPT_NO_SAFE, OPT_DENSE, OPT_SPARSE = 1, 2, 4, 8, 16, 32, 64
+OPT_EDGES, OPT_FORCE_GENERAL, OPT_NO_AGGREGATE, OPT_AGGREGATE, OPT_NO_SAFE, OPT_DENSE, OPT_SPARSE, OPT_NO_UBOX = 1, 2, 4, 8, 16, 32, 64, 128
 COMM_ID_BYTES = 128
 
 # every symbol include/agofrt.h declares (tests check the library exports all of them)

@@ -995,6 +995,10 @@ extern "C" int agofrt_block(agofrt_plan *p, size_t primo, unsigned ntimesteps, u
         }
         if (!(reach / p->dr < p->q_reach)) use_safe = false;
     }
+    // one box for the whole window (NVT / NVE)?  Then it travels as a kernel parameter.
+    bool same_box = t->nframes > 0;
+    for (size_t f = 1; f < t->nframes && same_box; ++f)
+        same_box = memcmp(&t->box6[f * 6], &t->box6[0], 6 * sizeof(double)) == 0;
     // dense or sparse?  The share of pairs within rmax, from the sphere / cell volume ratio of the
     // smallest cell of the window; above ~15% nearly every group of 8 pairs holds an in-range pair.
     bool dense = false;
@@ -1006,7 +1010,7 @@ extern "C" int agofrt_block(agofrt_plan *p, size_t primo, unsigned ntimesteps, u
         }
         const double rm = std::max(p->rmax, 0.0), r0 = std::max(p->rmin, 0.0);
         const double share = 4.18879020478639 * (rm * rm * rm - r0 * r0 * r0) / vmin;
-        dense = share > 0.15;
+        (void)share;   // the software-pipelined kernel is measured slower on B200 even at 44% in range: opt-in only
         if (options & AGOFRT_OPT_DENSE) dense = true;
         if (options & AGOFRT_OPT_SPARSE) dense = false;
     }
@@ -1100,7 +1104,16 @@ extern "C" int agofrt_block(agofrt_plan *p, size_t primo, unsigned ntimesteps, u
                     mode = kModeAgg;
                 else if (pass == 0 && use_safe)
                     mode = dense ? kModeSafeDense : kModeSafe;
-                const int variant = (tri ? 1 : 0) | (pass == 0 ? 2 : 0) | (mode << 2);
+                const bool ubox = same_box && pass == 0 && !(options & AGOFRT_OPT_NO_UBOX) &&
+                                  (mode == kModeThr || mode == kModeSafe || mode == kModeSafeDense);
+                if (ubox) {
+                    const double *b = &t->box6[0];
+                    for (int k = 0; k < 6; ++k) pp.ubox[k] = b[k];
+                    for (int k = 0; k < 3; ++k) pp.ubox[6 + k] = -2.0 * b[k];
+                } else {
+                    for (int k = 0; k < 9; ++k) pp.ubox[k] = 0.0;
+                }
+                const int variant = (tri ? 1 : 0) | (pass == 0 ? 2 : 0) | (mode << 2) | (ubox ? 32 : 0);
                 const int grid = static_cast<int>(std::min<uint64_t>(ue - ub, static_cast<uint64_t>(kMinBlocks) * dv.sm_count));
                 CU(cudaMemsetAsync(pd.counter, 0, sizeof(unsigned int), dv.stream));
                 CU(launch_pair_kernel(variant, grid, smem, dv.stream, pp));

@@ -484,7 +484,13 @@ __device__ __forceinline__ void process_group(const PairParams &p, const PairCon
     }
 }
 
-template <bool TRI, bool FAST, int MODE>
+// UBOX: every frame of the window has the same box, passed as a kernel parameter.  The half edges,
+// the -2*l_half constants and the tilt factors then reach the FP64 instructions as constant-bank /
+// uniform-register operands instead of per-thread registers.  B200's register file delivers one even
+// and one odd 32-bit register per cycle, so a DFMA with three distinct register pairs holds the issue
+// port for 3 cycles and a DSETP with two for 2 (tools/pipe_probe2.cu); with uniform constants they cost
+// 2 and 1, which frees issue cycles for the integer / FP32 instructions of the binning.
+template <bool TRI, bool FAST, int MODE, bool UBOX>
 __global__ void __launch_bounds__(kThreads, kMinBlocks) pair_kernel(const PairParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
     constexpr bool EDGES = MODE == MODE_EDGES;
@@ -583,16 +589,28 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) pair_kernel(const PairPa
         acc_pairs += unit_pairs;
 
         // ---- the box of frame fi (used for both atoms, reference basetrajectory.h:190-191) ----
-        const double *bx = p.box + static_cast<size_t>(job.fi) * 6;
-        c.box.lhx = __ldg(bx + 0);
-        c.box.lhy = __ldg(bx + 1);
-        c.box.lhz = __ldg(bx + 2);
-        c.box.xy = __ldg(bx + 3);
-        c.box.xz = __ldg(bx + 4);
-        c.box.yz = __ldg(bx + 5);
-        c.nLx = __dmul_rn(c.box.lhx, -2.0);
-        c.nLy = __dmul_rn(c.box.lhy, -2.0);
-        c.nLz = __dmul_rn(c.box.lhz, -2.0);
+        if (UBOX) {
+            c.box.lhx = p.ubox[0];
+            c.box.lhy = p.ubox[1];
+            c.box.lhz = p.ubox[2];
+            c.box.xy = p.ubox[3];
+            c.box.xz = p.ubox[4];
+            c.box.yz = p.ubox[5];
+            c.nLx = p.ubox[6];
+            c.nLy = p.ubox[7];
+            c.nLz = p.ubox[8];
+        } else {
+            const double *bx = p.box + static_cast<size_t>(job.fi) * 6;
+            c.box.lhx = __ldg(bx + 0);
+            c.box.lhy = __ldg(bx + 1);
+            c.box.lhz = __ldg(bx + 2);
+            c.box.xy = __ldg(bx + 3);
+            c.box.xz = __ldg(bx + 4);
+            c.box.yz = __ldg(bx + 5);
+            c.nLx = __dmul_rn(c.box.lhx, -2.0);
+            c.nLy = __dmul_rn(c.box.lhy, -2.0);
+            c.nLz = __dmul_rn(c.box.lhz, -2.0);
+        }
 
         // ---- this thread's i atoms (frame fi) ----
         double xi[kIPT], yi[kIPT], zi[kIPT];
@@ -707,26 +725,28 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) pair_kernel(const PairPa
     if (!wrap_ok) atomicExch(p.error_flag, 1u);
 }
 
-// variant = TRI | FAST<<1 | MODE<<2
+// variant = TRI | FAST<<1 | MODE<<2 | UBOX<<5   (UBOX only with FAST and MODE in {THR, SAFE, SAFE_DENSE})
 template <int V>
 static cudaError_t launch_variant(int grid, size_t smem, cudaStream_t stream, const PairParams &p) {
-    pair_kernel<(V & 1) != 0, (V & 2) != 0, (V >> 2)><<<grid, kThreads, smem, stream>>>(p);
+    pair_kernel<(V & 1) != 0, (V & 2) != 0, ((V >> 2) & 7), (V & 32) != 0><<<grid, kThreads, smem, stream>>>(p);
     return cudaGetLastError();
 }
 
 template <int V>
 static cudaError_t prepare_variant(size_t max_smem) {
-    return cudaFuncSetAttribute(pair_kernel<(V & 1) != 0, (V & 2) != 0, (V >> 2)>,
+    return cudaFuncSetAttribute(pair_kernel<(V & 1) != 0, (V & 2) != 0, ((V >> 2) & 7), (V & 32) != 0>,
                                 cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(max_smem));
 }
+
+#define AGOFRT_VARIANTS(X)                                                                              \
+    X(0) X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(12) X(13) X(14) X(15) X(18) X(19) \
+    X(32 + 2) X(32 + 3) X(32 + 14) X(32 + 15) X(32 + 18) X(32 + 19)
 
 cudaError_t launch_pair_kernel(int variant, int grid, size_t smem, cudaStream_t stream, const PairParams &p) {
     switch (variant) {
 #define AGOFRT_CASE(V) \
     case V: return launch_variant<V>(grid, smem, stream, p);
-        AGOFRT_CASE(0) AGOFRT_CASE(1) AGOFRT_CASE(2) AGOFRT_CASE(3) AGOFRT_CASE(4) AGOFRT_CASE(5) AGOFRT_CASE(6)
-        AGOFRT_CASE(7) AGOFRT_CASE(8) AGOFRT_CASE(9) AGOFRT_CASE(10) AGOFRT_CASE(11) AGOFRT_CASE(12) AGOFRT_CASE(13)
-        AGOFRT_CASE(14) AGOFRT_CASE(15) AGOFRT_CASE(18) AGOFRT_CASE(19)
+        AGOFRT_VARIANTS(AGOFRT_CASE)
 #undef AGOFRT_CASE
         default: return cudaErrorInvalidValue;
     }
@@ -737,9 +757,7 @@ cudaError_t prepare_pair_kernels(size_t max_smem) {
 #define AGOFRT_PREP(V)                \
     e = prepare_variant<V>(max_smem); \
     if (e != cudaSuccess) return e;
-    AGOFRT_PREP(0) AGOFRT_PREP(1) AGOFRT_PREP(2) AGOFRT_PREP(3) AGOFRT_PREP(4) AGOFRT_PREP(5) AGOFRT_PREP(6)
-    AGOFRT_PREP(7) AGOFRT_PREP(8) AGOFRT_PREP(9) AGOFRT_PREP(10) AGOFRT_PREP(11) AGOFRT_PREP(12) AGOFRT_PREP(13)
-    AGOFRT_PREP(14) AGOFRT_PREP(15) AGOFRT_PREP(18) AGOFRT_PREP(19)
+    AGOFRT_VARIANTS(AGOFRT_PREP)
 #undef AGOFRT_PREP
     return cudaSuccess;
 }

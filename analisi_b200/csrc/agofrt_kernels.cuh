@@ -56,6 +56,7 @@ struct PairParams {
     const double *thr;          // [nbin+1] thresholds folded with the rmin2/rmax2 test
     const double *thr_full;     // [nbin+1] plain thresholds (EDGES variant)
     double rmin2, rmax2;
+    double ubox[9];             // UBOX variants: lx/2, ly/2, lz/2, xy, xz, yz, -lx, -ly, -lz of the one box of the window
     unsigned unit_begin, unit_end;
     int npad, ntypes, nbin;
     int n_itiles, n_jchunks, jchunk;  // jchunk is a multiple of kTileJ
@@ -66,7 +67,7 @@ struct PairParams {
 
 size_t pair_kernel_smem_bytes(int ntypes, int nbin, bool edges);
 
-// variant = TRI | FAST<<1 | MODE<<2, MODE: 0 thresholds, 1 thresholds + warp aggregation, 2 edges, 3 safe-zone,
+// variant = TRI | FAST<<1 | MODE<<2 | UBOX<<5, MODE: 0 thresholds, 1 thresholds + warp aggregation, 2 edges, 3 safe-zone,
 // 4 safe-zone software-pipelined for dense in-range workloads
 enum { kModeThr = 0, kModeAgg = 1, kModeEdges = 2, kModeSafe = 3, kModeSafeDense = 4 };  // dense: FAST only (variants 18, 19)
 cudaError_t launch_pair_kernel(int variant, int grid, size_t smem, cudaStream_t stream, const PairParams &p);

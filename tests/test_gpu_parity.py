@@ -78,7 +78,7 @@ def test_min_image_and_pbc_golden(ctx):
 
 @pytest.mark.parametrize("name", LIVE_CASES)
 @pytest.mark.parametrize("options", [0, cabi.OPT_FORCE_GENERAL, cabi.OPT_AGGREGATE, cabi.OPT_NO_SAFE,
-                                     cabi.OPT_DENSE, cabi.OPT_SPARSE])
+                                     cabi.OPT_DENSE, cabi.OPT_SPARSE, cabi.OPT_NO_UBOX, cabi.OPT_NO_UBOX | cabi.OPT_NO_SAFE])
 def test_live_reference_cases(ctx, name, options):
     """Fixtures computed by the compiled reference: triclinic, NPT, unwrapped, big tilt, ragged loops."""
     d = live_case(name)
