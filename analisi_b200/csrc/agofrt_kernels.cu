@@ -103,48 +103,56 @@ __device__ __forceinline__ bool min_image_general(double &dx, double &dy, double
 // Single-pass form, used only for (lag, origin) jobs whose coordinate bounds PROVE that one image
 // per dimension is enough (agofrt_cabi.cu: job_is_single_pass).
 //
-// The reference's loop body is odd-symmetric: every operation it performs (add, subtract, |x|
-// compare, round-to-nearest) commutes with a global sign flip of the vector, and the vector is only
-// ever squared afterwards.  So instead of choosing between "+= 2*l_half" and "-= 2*l_half" by the
-// sign of the component, flip the sign of the WHOLE remaining vector so that the component is
-// positive (one LOP3 on the high word of each lower component, nothing at all for the component
-// itself: |x| is an operand modifier) and always subtract.  fl(-a-b) == -fl(a+b), so every
-// intermediate is, up to that global sign, bit-identical to the reference's.
+// The reference's step for a component x with |x| > l_half is  x -= sign(x) * 2*l_half  (and the
+// same signed subtraction of the tilt factors from the lower components).  A component whose lower
+// neighbours do not depend on its sign (orthorhombic cells; the last, x, component of triclinic
+// ones) only feeds its square, so |x| - 2*l_half serves as well: (-a)^2 == a^2 exactly.
 // The wrap of one component is  x = fma(m, -2*l_half, |x|)  with m = 1.0 or 0.0 from the compare:
 // m*c is exact, so the fused operation rounds once, exactly like the reference's "x -= 2*l_half"
 // (m = 1) or leaves |x| untouched (m = 0).  Building m costs one 32-bit select (its low word is
 // the constant 0), and the same m serves the tilt corrections of the lower components:
 // 2 FP64 instructions + 1 select per wrapped component, nothing on the other pipes.
-__device__ __forceinline__ double flip_by(double v, double sign_source) {
-    const int hi = __double2hiint(v) ^ (__double2hiint(sign_source) & 0x80000000);
-    return __hiloint2double(hi, __double2loint(v));
-}
 __device__ __forceinline__ double mask01(bool p) { return __hiloint2double(p ? 0x3FF00000 : 0, 0); }
+// +-1.0 with the sign of s when p, else 0.0: one LOP3 (sign | exponent of 1.0) and one select, each
+// reading a single register
+__device__ __forceinline__ double mask_signed(bool p, double s) {
+    const int one = (__double2hiint(s) & 0x80000000) | 0x3FF00000;
+    return __hiloint2double(p ? one : 0, 0);
+}
 
 template <bool TRI>
 __device__ __forceinline__ void min_image_single(double &dx, double &dy, double &dz, const BoxRegs &b,
                                                  double nLx, double nLy, double nLz) {  // nL = -(2*l_half)
     if (TRI) {
-        dy = flip_by(dy, dz);
-        dx = flip_by(dx, dz);
-    }
-    {
-        const double m = mask01(fabs(dz) > b.lhz);
-        dz = __fma_rn(m, nLz, fabs(dz));
-        if (TRI) {
+        // reference: z<0 ? (z+=L, y+=yz, x+=xz) : (z-=L, y-=yz, x-=xz)  ==  v -= sign(z) * (L, yz, xz)
+        {
+            const double m = mask_signed(fabs(dz) > b.lhz, dz);
+            dz = __fma_rn(m, nLz, dz);
             dy = __fma_rn(m, -b.yz, dy);
             dx = __fma_rn(m, -b.xz, dx);
         }
-    }
-    if (TRI) dx = flip_by(dx, dy);
-    {
-        const double m = mask01(fabs(dy) > b.lhy);
-        dy = __fma_rn(m, nLy, fabs(dy));
-        if (TRI) dx = __fma_rn(m, -b.xy, dx);
-    }
-    {
-        const double m = mask01(fabs(dx) > b.lhx);
-        dx = __fma_rn(m, nLx, fabs(dx));
+        {
+            const double m = mask_signed(fabs(dy) > b.lhy, dy);
+            dy = __fma_rn(m, nLy, dy);
+            dx = __fma_rn(m, -b.xy, dx);
+        }
+        {
+            const double m = mask01(fabs(dx) > b.lhx);   // last component: only its square is used
+            dx = __fma_rn(m, nLx, fabs(dx));
+        }
+    } else {
+        {
+            const double m = mask01(fabs(dz) > b.lhz);
+            dz = __fma_rn(m, nLz, fabs(dz));
+        }
+        {
+            const double m = mask01(fabs(dy) > b.lhy);
+            dy = __fma_rn(m, nLy, fabs(dy));
+        }
+        {
+            const double m = mask01(fabs(dx) > b.lhx);
+            dx = __fma_rn(m, nLx, fabs(dx));
+        }
     }
 }
 
