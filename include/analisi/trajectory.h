@@ -1,0 +1,113 @@
+// trajectory.h -- Trajectory: a LAMMPS binary dump read through mmap with a sliding window.
+//
+// Mirrors the reference's lib/include/trajectory.h:37-139 / lib/src/trajectory.cpp:44-707 for what
+// the g(r,t) path and its callers use: open + atom-id map + types from frame 0, window size
+// (set_data_access_block_size), window position (set_access_at: lazy frame index, overlap reuse,
+// per-atom scatter by id, box conversion, optional wrap), window-relative accessors.
+// Differences that are this repository's design, not the reference's:
+//   * window buffers are page-locked (agofrt_host_alloc) so the upload to the GPUs is one DMA;
+//   * the wrap of freshly read frames runs on the GPU (BaseTrajectory::pbc_wrap_frames);
+//   * velocities and per-type centres of mass are only read when asked for
+//     (set_load_velocities; g(r,t) never touches them -- at 1M atoms they would double the I/O);
+//   * one stderr summary line per type instead of one line per atom.
+#ifndef ANALISI_B200_TRAJECTORY_H
+#define ANALISI_B200_TRAJECTORY_H
+
+#include <cstdint>
+#include <sstream>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "analisi/basetrajectory.h"
+
+class Trajectory : public BaseTrajectory<Trajectory> {
+public:
+    explicit Trajectory(std::string filename);
+    ~Trajectory();
+
+    template <bool SAFE = true>
+    double *positions(const size_t &timestep, const size_t &atomo) {
+        return window_ptr<SAFE, true>(buffer_positions, timestep, atomo, 3 * natoms, 3);
+    }
+    template <bool SAFE = true>
+    double *velocity(const size_t &timestep, const size_t &atomo) {
+        if (!buffer_velocity) return nullptr;
+        return window_ptr<SAFE, true>(buffer_velocity, timestep, atomo, 3 * natoms, 3);
+    }
+    template <bool SAFE = true>
+    double *box(const size_t &timestep) {
+        return window_ptr<SAFE, false>(buffer_boxes, timestep, 0, buffer_boxes_stride, 0);
+    }
+    template <bool SAFE = true>
+    double *positions_cm(const size_t &timestep, const size_t &tipo) {
+        if (!cm_pos.data()) return nullptr;
+        return window_ptr<SAFE, false>(cm_pos.data(), timestep, tipo, 3 * ntypes, 3);
+    }
+    template <bool SAFE = true>
+    double *velocity_cm(const size_t &timestep, const size_t &tipo) {
+        if (!cm_vel.data()) return nullptr;
+        return window_ptr<SAFE, false>(cm_vel.data(), timestep, tipo, 3 * ntypes, 3);
+    }
+    double *box_last() {
+        if (loaded_timesteps > 0 && buffer_boxes) return buffer_boxes + buffer_boxes_stride * (loaded_timesteps - 1);
+        throw std::runtime_error("No data is loaded!\n");
+    }
+
+    using BaseTrajectory<Trajectory>::Errori;
+    Errori set_data_access_block_size(const size_t &timesteps);
+    Errori set_access_at(const size_t &timestep);
+    int64_t get_timestep_lammps(size_t timestep);
+    void index_all();
+    int *get_lammps_id();     // new int[natoms], caller owns (as in the reference)
+    int *get_lammps_type();   // new int[natoms], caller owns
+
+    // default true (what the reference always does); the CLI g(r,t) branch turns it off
+    void set_load_velocities(bool v) { load_velocities = v; }
+
+private:
+    template <bool SAFE, bool ATOM>
+    double *window_ptr(double *base, const size_t &timestep, const size_t &atomo, const size_t &stride1,
+                       const size_t &stride2) {
+        if constexpr (SAFE) {
+            if constexpr (ATOM) {
+                if (atomo >= static_cast<size_t>(natoms)) {
+                    std::stringstream ss;
+                    ss << "Requested atom index (" << atomo << ") is not in the range [0, " << natoms - 1 << "]\n";
+                    throw std::runtime_error(ss.str());
+                }
+            }
+            const bool inside = window_loaded && timestep >= static_cast<size_t>(current_timestep) &&
+                                timestep - current_timestep < static_cast<size_t>(loaded_timesteps);
+            if (!inside) {
+                // like the reference: an access outside the window moves the window there
+                if (!set_access_at(timestep)) throw std::runtime_error("Error loading the file\n");
+                if (timestep < static_cast<size_t>(current_timestep) ||
+                    timestep - current_timestep >= static_cast<size_t>(loaded_timesteps))
+                    throw std::runtime_error("requested timestep is out of range");
+            }
+        }
+        return base + (timestep - current_timestep) * stride1 + atomo * stride2;
+    }
+
+    size_t frame_bytes(size_t offset, LammpsFrameHeader &head, std::vector<LammpsChunk> *chunks);
+    void ensure_indexed(size_t upto);
+    void read_frame_into_slot(size_t frame, size_t slot);
+
+    int fd = -1;
+    char *file = nullptr;
+    size_t fsize = 0;
+    std::vector<size_t> offsets;          // byte offset of frame k, valid for k <= indexed_upto
+    std::vector<int64_t> lammps_steps;    // LAMMPS timestep of frame k, valid once the frame was parsed
+    size_t indexed_upto = 0;
+    bool window_loaded = false;
+    bool load_velocities = true;
+    std::unordered_map<int, int> id_to_slot;
+    std::vector<int> slot_to_id;
+    std::vector<int> raw_type, type_id;
+    analisi_device::PinnedBuffer pos_buf, vel_buf;
+    std::vector<double> boxes, cm_pos, cm_vel;
+    size_t window_capacity = 0;
+};
+
+#endif

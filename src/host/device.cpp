@@ -1,0 +1,71 @@
+// device.cpp -- see include/analisi/device.h
+#include "analisi/device.h"
+
+#include <cstdlib>
+#include <sstream>
+
+namespace analisi_device {
+
+Context &Context::instance() {
+    static Context c;
+    return c;
+}
+
+Context::Context() {
+    const char *env = std::getenv("ANALISI_DEVICES");
+    if (env && *env) {
+        std::vector<int> ids;
+        std::stringstream ss(env);
+        std::string tok;
+        while (std::getline(ss, tok, ',')) {
+            if (!tok.empty()) ids.push_back(std::atoi(tok.c_str()));
+        }
+        check(agofrt_ctx_create(&ctx_, ids.data(), static_cast<int>(ids.size())), "agofrt_ctx_create");
+    } else {
+        check(agofrt_ctx_create(&ctx_, nullptr, -1), "agofrt_ctx_create");
+    }
+}
+
+Context::~Context() {
+    if (ctx_) agofrt_ctx_destroy(ctx_);
+}
+
+void PinnedBuffer::resize(size_t ndoubles) {
+    if (ndoubles == n_ && ptr_) return;
+    release();
+    void *p = nullptr;
+    check(agofrt_host_alloc(&p, ndoubles * sizeof(double)), "agofrt_host_alloc");
+    ptr_ = static_cast<double *>(p);
+    n_ = ndoubles;
+}
+
+void PinnedBuffer::release() {
+    if (ptr_) agofrt_host_free(ptr_);
+    ptr_ = nullptr;
+    n_ = 0;
+}
+
+void Window::create(size_t natoms, int box_stride, const int *type_id, int ntypes, size_t max_frames) {
+    release();
+    check(agofrt_traj_create(&traj_, Context::instance().handle(), natoms, box_stride, type_id, ntypes, max_frames),
+          "agofrt_traj_create");
+    cap_ = max_frames;
+    ++generation_;
+}
+
+void Window::release() {
+    if (traj_) agofrt_traj_destroy(traj_);
+    traj_ = nullptr;
+    cap_ = 0;
+}
+
+void Window::upload(size_t first, size_t n, const double *pos_aos, const double *box_internal) {
+    check(agofrt_traj_upload(traj_, first, n, pos_aos, box_internal), "agofrt_traj_upload");
+}
+
+void pbc_wrap(double *pos_aos, size_t nframes, size_t natoms, const double *box_internal, int box_stride) {
+    check(agofrt_pbc_wrap(Context::instance().handle(), pos_aos, nframes, natoms, box_internal, box_stride),
+          "agofrt_pbc_wrap");
+}
+
+}  // namespace analisi_device

@@ -1,0 +1,292 @@
+// trajectory.cpp -- see include/analisi/trajectory.h
+#include "analisi/trajectory.h"
+
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <chrono>
+#include <cmath>
+#include <cstring>
+
+// Size in bytes of the frame that starts at `offset`; fills the header and, when asked, the chunk
+// table (reference lib/src/trajectory.cpp:260-317).
+size_t Trajectory::frame_bytes(size_t offset, LammpsFrameHeader &head, std::vector<LammpsChunk> *chunks) {
+    if (offset >= fsize) throw std::runtime_error("Error: trying to read beyond the end of file");
+    const char *end = file + fsize;
+    size_t used = head.parse(file + offset, end);
+    if (natoms != 0 && natoms != head.natoms) {
+        std::stringstream ss;
+        ss << "Error: at the LAMMPS timestep " << head.timestep << " the number of atoms has changed \n";
+        throw std::runtime_error(ss.str());
+    }
+    if (head.nchunk <= 0) throw std::runtime_error("Error: the number of chunks of the timestep cannot be <= 0");
+    if (chunks) chunks->clear();
+    for (int c = 0; c < head.nchunk; ++c) {
+        int ndouble = 0;
+        if (file + offset + used + sizeof(int) > end) throw std::runtime_error("Error: end of file reached");
+        std::memcpy(&ndouble, file + offset + used, sizeof(int));
+        if (ndouble < 0 || ndouble % kLammpsDoublesPerAtom != 0)
+            throw std::runtime_error("Number of bytes of the chunk is not a multiple of the number of atoms\n");
+        used += sizeof(int);
+        const size_t bytes = static_cast<size_t>(ndouble) * sizeof(double);
+        if (file + offset + used + bytes > end) throw std::runtime_error("Error: end of file reached");
+        if (chunks) chunks->push_back({file + offset + used, ndouble / kLammpsDoublesPerAtom});
+        used += bytes;
+    }
+    return used;
+}
+
+Trajectory::Trajectory(std::string filename) {
+    wrap_pbc = false;   // the reference's constructor resets it (lib/src/trajectory.cpp:73): callers set it afterwards
+    fd = open(filename.c_str(), O_RDONLY);
+    if (fd == -1) throw std::runtime_error("Error opening the trajectory \"" + filename + "\"\n");
+    struct stat sb;
+    if (fstat(fd, &sb) == -1) {
+        close(fd);
+        fd = -1;
+        throw std::runtime_error("Error in finding trajectory file size \"" + filename + "\"\n");
+    }
+    fsize = static_cast<size_t>(sb.st_size);
+    std::cerr << "Trajectory file size \"" << filename << "\": " << fsize << "\n";
+    void *m = fsize ? mmap(nullptr, fsize, PROT_READ, MAP_PRIVATE, fd, 0) : MAP_FAILED;
+    if (m == MAP_FAILED) {
+        close(fd);
+        fd = -1;
+        throw std::runtime_error("mmap failed for file \"" + filename + "\".\n");
+    }
+    file = static_cast<char *>(m);
+
+    // frame 0: number of atoms, cell kind, id -> slot map in order of first appearance, raw types
+    LammpsFrameHeader h0;
+    std::vector<LammpsChunk> chunks;
+    const size_t frame0 = frame_bytes(0, h0, &chunks);
+    natoms = h0.natoms;
+    triclinic = h0.triclinic != 0;
+    buffer_boxes_stride = triclinic ? 9 : 6;
+    box_format = triclinic ? BoxFormat::Lammps_triclinic : BoxFormat::Lammps_ortho;
+    raw_type.assign(natoms, -1);
+    type_id.assign(natoms, -1);
+    buffer_type = raw_type.data();
+    buffer_type_id = type_id.data();
+    slot_to_id.reserve(natoms);
+    id_to_slot.reserve(static_cast<size_t>(natoms) * 2);
+    for (const LammpsChunk &c : chunks) {
+        for (int a = 0; a < c.natoms; ++a) {
+            double rec[2];
+            std::memcpy(rec, c.data + static_cast<size_t>(a) * kLammpsDoublesPerAtom * sizeof(double), sizeof(rec));
+            const int id = static_cast<int>(std::round(rec[0]));
+            if (id < 0) throw std::runtime_error("Error: found a negative atomic id in the trajectory");
+            if (static_cast<ssize_t>(slot_to_id.size()) >= natoms && id_to_slot.find(id) == id_to_slot.end())
+                throw std::runtime_error(
+                    "Error: the number of atoms does not correspond to the sum of the number of atoms of each chunk\n");
+            auto ins = id_to_slot.emplace(id, static_cast<int>(slot_to_id.size()));
+            if (ins.second) slot_to_id.push_back(id);
+            raw_type[ins.first->second] = static_cast<int>(std::round(rec[1]));
+        }
+    }
+    get_ntypes();
+    std::cerr << "Types of atoms (" << natoms << " atoms):";
+    {
+        std::vector<size_t> cnt(ntypes, 0);
+        for (ssize_t i = 0; i < natoms; ++i) cnt[type_id[i]]++;
+        for (ssize_t k = 0; k < ntypes; ++k) std::cerr << "  type " << types[k] << " -> index " << k << " (" << cnt[k] << ")";
+        std::cerr << "\n";
+    }
+    // estimate of the number of frames from the size of the first one (reference :114)
+    n_timesteps = static_cast<ssize_t>(fsize / frame0);
+    offsets.assign(static_cast<size_t>(n_timesteps) + 1, 0);
+    lammps_steps.assign(static_cast<size_t>(n_timesteps) + 1, 0);
+    indexed_upto = 0;
+    lammps_steps[0] = h0.timestep;
+}
+
+Trajectory::~Trajectory() {
+    if (file) munmap(file, fsize);
+    if (fd != -1) close(fd);
+    buffer_positions = buffer_velocity = buffer_boxes = nullptr;
+}
+
+Trajectory::Errori Trajectory::set_data_access_block_size(const size_t &n) {
+    if (!file) {
+        std::cerr << "mmap not correctly initialized!\n";
+        return non_inizializzato;
+    }
+    if (static_cast<size_t>(loaded_timesteps) == n && window_capacity == n) return Ok;
+    window_loaded = false;
+    pos_buf.resize(n * natoms * 3);
+    buffer_positions = pos_buf.data();
+    if (load_velocities) {
+        vel_buf.resize(n * natoms * 3);
+        buffer_velocity = vel_buf.data();
+        cm_pos.assign(n * ntypes * 3, 0.0);
+        cm_vel.assign(n * ntypes * 3, 0.0);
+    } else {
+        vel_buf.release();
+        buffer_velocity = nullptr;
+        cm_pos.clear();
+        cm_vel.clear();
+    }
+    boxes.assign(n * buffer_boxes_stride, 0.0);
+    buffer_boxes = boxes.data();
+    window_capacity = n;
+    loaded_timesteps = static_cast<ssize_t>(n);
+    mark_window_changed();
+    return Ok;
+}
+
+// lazily index frame offsets up to frame `upto` by walking the headers (reference :481-494)
+void Trajectory::ensure_indexed(size_t upto) {
+    if (upto + 1 > offsets.size()) {
+        offsets.resize(upto + 2, 0);
+        lammps_steps.resize(upto + 2, 0);
+    }
+    while (indexed_upto < upto) {
+        LammpsFrameHeader h;
+        const size_t sz = frame_bytes(offsets[indexed_upto], h, nullptr);
+        lammps_steps[indexed_upto] = h.timestep;
+        offsets[indexed_upto + 1] = offsets[indexed_upto] + sz;
+        ++indexed_upto;
+    }
+}
+
+void Trajectory::index_all() {
+    if (n_timesteps > 0) ensure_indexed(static_cast<size_t>(n_timesteps) - 1);
+    if (n_timesteps > 0) {
+        LammpsFrameHeader h;
+        frame_bytes(offsets[n_timesteps - 1], h, nullptr);
+        lammps_steps[n_timesteps - 1] = h.timestep;
+    }
+}
+
+// one frame of the file -> window slot: box row (internal format), per-atom scatter by id
+// (reference :593-662)
+void Trajectory::read_frame_into_slot(size_t frame, size_t slot) {
+    ensure_indexed(frame);
+    LammpsFrameHeader h;
+    std::vector<LammpsChunk> chunks;
+    const size_t sz = frame_bytes(offsets[frame], h, &chunks);
+    lammps_steps[frame] = h.timestep;
+    if (frame + 1 < offsets.size() && indexed_upto <= frame) {
+        offsets[frame + 1] = offsets[frame] + sz;
+        indexed_upto = frame + 1;
+    }
+    if ((h.triclinic != 0) != triclinic) throw std::runtime_error("Error: the cell kind (triclinic flag) changes along the trajectory\n");
+    double *b = buffer_boxes + slot * buffer_boxes_stride;
+    std::memcpy(b, h.box, 6 * sizeof(double));
+    if (triclinic) std::memcpy(b + 6, h.xy_xz_yz, 3 * sizeof(double));
+    lammps_to_internal(b);
+    double *P = buffer_positions + slot * natoms * 3;
+    double *V = buffer_velocity ? buffer_velocity + slot * natoms * 3 : nullptr;
+    std::vector<size_t> cnt;
+    double *cp = nullptr, *cv = nullptr;
+    if (V) {
+        cnt.assign(ntypes, 0);
+        cp = cm_pos.data() + slot * ntypes * 3;
+        cv = cm_vel.data() + slot * ntypes * 3;
+        std::fill(cp, cp + ntypes * 3, 0.0);
+        std::fill(cv, cv + ntypes * 3, 0.0);
+    }
+    for (const LammpsChunk &c : chunks) {
+        const char *p = c.data;
+        for (int a = 0; a < c.natoms; ++a, p += kLammpsDoublesPerAtom * sizeof(double)) {
+            double rec[kLammpsDoublesPerAtom];
+            std::memcpy(rec, p, sizeof(rec));
+            const int id = static_cast<int>(std::round(rec[0]));
+            auto it = id_to_slot.find(id);
+            if (it == id_to_slot.end()) throw std::out_of_range("atom id that was not in the first frame");
+            const size_t s = static_cast<size_t>(it->second);
+            P[3 * s] = rec[2];
+            P[3 * s + 1] = rec[3];
+            P[3 * s + 2] = rec[4];
+            const int tipo = static_cast<int>(std::round(rec[1]));
+            if (raw_type[s] != tipo) {
+                std::cerr << "WARNING: atomic type for atom with id " << s << " is changing from " << raw_type[s] << " to "
+                          << tipo << " !\n";
+                raw_type[s] = tipo;
+            }
+            if (V) {
+                V[3 * s] = rec[5];
+                V[3 * s + 1] = rec[6];
+                V[3 * s + 2] = rec[7];
+                // running per-type mean, same update as the reference (:648-657)
+                const int k = type_id[s];
+                cnt[k]++;
+                for (int d = 0; d < 3; ++d) {
+                    cp[3 * k + d] += (P[3 * s + d] - cp[3 * k + d]) / cnt[k];
+                    cv[3 * k + d] += (V[3 * s + d] - cv[3 * k + d]) / cnt[k];
+                }
+            }
+        }
+    }
+}
+
+Trajectory::Errori Trajectory::set_access_at(const size_t &timestep) {
+    const auto t_begin = std::chrono::steady_clock::now();
+    if (!file) {
+        std::cerr << "mmap not initialized correctly!\n";
+        return non_inizializzato;
+    }
+    if (loaded_timesteps <= 0 || !buffer_positions) throw std::runtime_error("set_data_access_block_size must be called first\n");
+    if (timestep == static_cast<size_t>(current_timestep) && window_loaded) return Ok;
+    const size_t W = static_cast<size_t>(loaded_timesteps);
+
+    // overlap with what is already in the window: move it instead of reading it again (reference :542-586)
+    size_t read_begin = timestep, read_end = timestep + W;   // frames to read from the file
+    if (window_loaded) {
+        const ssize_t shift = static_cast<ssize_t>(current_timestep) - static_cast<ssize_t>(timestep);  // old slot + shift = new slot
+        const size_t ashift = static_cast<size_t>(shift < 0 ? -shift : shift);
+        if (ashift < W) {
+            const size_t keep = W - ashift;
+            const size_t src = shift < 0 ? ashift : 0, dst = shift < 0 ? 0 : ashift;
+            auto move_rows = [&](double *base, size_t row) {
+                if (base) std::memmove(base + dst * row, base + src * row, keep * row * sizeof(double));
+            };
+            move_rows(buffer_positions, natoms * 3);
+            move_rows(buffer_velocity, natoms * 3);
+            move_rows(buffer_boxes, buffer_boxes_stride);
+            if (buffer_velocity) {
+                move_rows(cm_pos.data(), ntypes * 3);
+                move_rows(cm_vel.data(), ntypes * 3);
+            }
+            if (shift < 0) {
+                read_begin = current_timestep + W;   // the tail is new
+            } else {
+                read_end = current_timestep;         // the head is new
+            }
+        }
+    }
+    window_loaded = false;
+    ensure_indexed(timestep);
+    // tell the kernel what we are done with and what comes next (reference :497-528)
+    madvise(file, offsets[timestep] & ~static_cast<size_t>(sysconf(_SC_PAGESIZE) - 1), MADV_DONTNEED);
+    for (size_t f = read_begin; f < read_end; ++f) read_frame_into_slot(f, f - timestep);
+    if (wrap_pbc && read_end > read_begin) pbc_wrap_frames(static_cast<ssize_t>(read_begin - timestep), read_end - read_begin);
+    current_timestep = static_cast<ssize_t>(timestep);
+    window_loaded = true;
+    mark_window_changed();
+    const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_begin).count();
+    std::cerr << "Reading time: " << dt << "s.\n";
+    return Ok;
+}
+
+int64_t Trajectory::get_timestep_lammps(size_t timestep) {
+    if (timestep < static_cast<size_t>(n_timesteps) && timestep < lammps_steps.size()) return lammps_steps[timestep];
+    std::stringstream ss;
+    ss << "Error: requested to read a timestep that probably is beyond the end of the file (" << timestep << ", "
+       << n_timesteps << " letti)\n";
+    throw std::runtime_error(ss.str());
+}
+
+int *Trajectory::get_lammps_id() {
+    int *out = new int[natoms];
+    for (ssize_t i = 0; i < natoms; ++i) out[i] = slot_to_id[i];
+    return out;
+}
+
+int *Trajectory::get_lammps_type() {
+    int *out = new int[natoms];
+    for (ssize_t i = 0; i < natoms; ++i) out[i] = raw_type[i];
+    return out;
+}
