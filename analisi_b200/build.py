@@ -73,5 +73,63 @@ def build(force=False, verbose=False, defs=None, out=None):
     return LIB
 
 
+# ---- host side: the C++ classes mirroring the reference API (include/analisi, src/host), the CLI and
+# the pybind11 module.  Plain g++ (no CUDA headers needed: they only see include/agofrt.h). ----------
+HOST_SOURCES = ["device.cpp", "trajectory.cpp", "trajectory_numpy.cpp"]
+CLI = os.path.join(ROOT, "bin", "analisi")
+HOST_FLAGS = ["-O2", "-std=c++17", "-fPIC", "-ffp-contract=off", "-Wall", "-Wno-sign-compare", "-Wno-unused-variable"]
+
+
+def host_cxx():
+    # $CXX in this image is /opt/gcc/bin/g++, a wrapper that links libstdc++ statically: a python
+    # extension built with it crashes as soon as another libstdc++ is in the process.  ANALISI_CXX overrides.
+    for cand in (os.environ.get("ANALISI_CXX"), "/usr/bin/g++", "g++"):
+        if cand and (not os.path.isabs(cand) or os.path.exists(cand)):
+            return cand
+    raise RuntimeError("g++ not found")
+
+
+def pyext_path():
+    import sysconfig
+    return os.path.join(ROOT, "python", "pyanalisi" + sysconfig.get_config_var("EXT_SUFFIX"))
+
+
+def _host_deps():
+    deps = [os.path.abspath(__file__), LIB, os.path.join(ROOT, "include", "agofrt.h")]
+    for d in (os.path.join(ROOT, "include", "analisi"), os.path.join(ROOT, "src", "host")):
+        deps += [os.path.join(d, f) for f in os.listdir(d)]
+    return deps
+
+
+def _run(cmd):
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("host build failed:\n" + " ".join(cmd) + "\n" + r.stdout)
+    return r.stdout
+
+
+def build_host(force=False):
+    """Compile bin/analisi (the CLI) and python/pyanalisi*.so (pybind11) against libagofrt.so; return both paths."""
+    build()
+    ext = pyext_path()
+    srcs = [os.path.join(ROOT, "src", "host", s) for s in HOST_SOURCES]
+    link = ["-L", HERE, "-lagofrt", "-Wl,-rpath,$ORIGIN/../analisi_b200"]
+    inc = ["-I", os.path.join(ROOT, "include")]
+    os.makedirs(os.path.dirname(CLI), exist_ok=True)
+    main = os.path.join(ROOT, "cli", "main.cpp")
+    deps = _host_deps()
+    if force or not os.path.exists(CLI) or any(os.path.getmtime(d) > os.path.getmtime(CLI) for d in deps + [main]):
+        _run([host_cxx()] + HOST_FLAGS + inc + [main] + srcs + link + ["-o", CLI])
+    mod = os.path.join(ROOT, "python", "pyanalisi.cpp")
+    if force or not os.path.exists(ext) or any(os.path.getmtime(d) > os.path.getmtime(ext) for d in deps + [mod]):
+        import pybind11
+        import sysconfig
+        _run([host_cxx()] + HOST_FLAGS + ["-shared", "-fvisibility=hidden", "-DANALISI_WITH_PYBIND11"] + inc +
+             ["-I", pybind11.get_include(), "-I", sysconfig.get_paths()["include"], mod] + srcs + link + ["-o", ext])
+    return CLI, ext
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    if "--host" in sys.argv:
+        print(build_host(force="--force" in sys.argv))

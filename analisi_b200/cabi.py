@@ -22,7 +22,7 @@ SYMBOLS = [
     "agofrt_version", "agofrt_last_error", "agofrt_device_count", "agofrt_host_alloc", "agofrt_host_free",
     "agofrt_ctx_create", "agofrt_ctx_destroy", "agofrt_ctx_ndev", "agofrt_comm_unique_id", "agofrt_comm_join",
     "agofrt_ctx_set_shard", "agofrt_shard_range", "agofrt_traj_create", "agofrt_traj_destroy", "agofrt_traj_upload",
-    "agofrt_traj_download_frame", "agofrt_pbc_wrap", "agofrt_traj_d2_all", "agofrt_plan_create",
+    "agofrt_traj_download_frame", "agofrt_pbc_wrap", "agofrt_traj_d2_all", "agofrt_traj_d2_pair", "agofrt_plan_create",
     "agofrt_plan_destroy", "agofrt_plan_thresholds", "agofrt_block", "agofrt_fp64_peak",
 ]
 
@@ -84,6 +84,7 @@ def lib():
     L.agofrt_traj_download_frame.argtypes = [vp, C.c_size_t, dp]
     L.agofrt_pbc_wrap.argtypes = [vp, vp, C.c_size_t, C.c_size_t, dp, C.c_int]
     L.agofrt_traj_d2_all.argtypes = [vp, C.c_size_t, C.c_size_t, dp]
+    L.agofrt_traj_d2_pair.argtypes = [vp, C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t, dp]
     L.agofrt_plan_create.argtypes = [C.POINTER(vp), vp, C.c_double, C.c_double, C.c_uint]
     L.agofrt_plan_destroy.argtypes = [vp]
     L.agofrt_plan_thresholds.argtypes = [vp, dp]
@@ -223,6 +224,11 @@ class DeviceTrajectory:
     def d2_all(self, frame_i, frame_j):
         out = np.zeros((self.natoms, self.natoms, 4), dtype=np.float64)
         _check(lib().agofrt_traj_d2_all(self._h, int(frame_i), int(frame_j), _dp(out)))
+        return out
+
+    def d2_pair(self, i, j, frame_i, frame_j):
+        out = np.zeros(4, dtype=np.float64)
+        _check(lib().agofrt_traj_d2_pair(self._h, int(i), int(j), int(frame_i), int(frame_j), _dp(out)))
         return out
 
     def close(self):

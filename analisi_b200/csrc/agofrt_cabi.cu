@@ -13,11 +13,14 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <memory>
+#include <mutex>
 #include <numeric>
 #include <string>
+#include <unordered_set>
 #include <vector>
 
 using namespace agofrt;
@@ -127,6 +130,7 @@ struct TrajDev {
     int *type_pad = nullptr;     // [npad]
     int *type_start = nullptr;   // [ntypes+1]
     unsigned int *flags = nullptr;  // [4]: 0 = inf seen, 1 = wrap cap hit
+    double *probe = nullptr;        // [4]: result of agofrt_traj_d2_pair
 };
 
 struct agofrt_traj {
@@ -143,6 +147,9 @@ struct agofrt_traj {
     bool has_inf = false;
     bool has_nan = false;   // NaN coordinates in the input (they are never in range, as in the reference)
     bool bad_box = false;
+    std::vector<int> slot_of;    // atom -> device slot (built on demand by agofrt_traj_d2_pair)
+    size_t slot_of_first = 0;
+    bool slot_of_stale = true;
 };
 
 struct PlanDev {
@@ -191,13 +198,40 @@ extern "C" int agofrt_device_count(int *count) {
     return AGOFRT_OK;
 }
 
+// Page-locked when a CUDA driver is present.  Without one (authoring container, CPU-only tests of the
+// file reader) the buffer is plain aligned memory: allocation is not computation, and every entry point
+// that computes still fails with AGOFRT_ERR_CUDA.
+static std::mutex g_pageable_mutex;
+static std::unordered_set<void *> g_pageable;
+
 extern "C" int agofrt_host_alloc(void **ptr, size_t bytes) {
     if (!ptr) return fail(AGOFRT_ERR_ARG, "ptr is NULL");
-    CU(cudaHostAlloc(ptr, bytes ? bytes : 1, cudaHostAllocPortable));
-    return AGOFRT_OK;
+    *ptr = nullptr;
+    const cudaError_t e = cudaHostAlloc(ptr, bytes ? bytes : 1, cudaHostAllocPortable);
+    if (e == cudaSuccess) return AGOFRT_OK;
+    cudaGetLastError();
+    if (e == cudaErrorInsufficientDriver || e == cudaErrorNoDevice) {
+        void *p = nullptr;
+        if (posix_memalign(&p, 4096, bytes ? bytes : 1) != 0) return fail(AGOFRT_ERR_INTERNAL, "out of host memory (%zu bytes)", bytes);
+        std::lock_guard<std::mutex> lock(g_pageable_mutex);
+        g_pageable.insert(p);
+        *ptr = p;
+        return AGOFRT_OK;
+    }
+    return fail(AGOFRT_ERR_CUDA, "cudaHostAlloc of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
 }
 extern "C" int agofrt_host_free(void *ptr) {
-    if (ptr) CU(cudaFreeHost(ptr));
+    if (!ptr) return AGOFRT_OK;
+    {
+        std::lock_guard<std::mutex> lock(g_pageable_mutex);
+        auto it = g_pageable.find(ptr);
+        if (it != g_pageable.end()) {
+            g_pageable.erase(it);
+            free(ptr);
+            return AGOFRT_OK;
+        }
+    }
+    CU(cudaFreeHost(ptr));
     return AGOFRT_OK;
 }
 
@@ -349,6 +383,7 @@ static void free_traj_dev(agofrt_traj *t) {
         cudaFree(d.type_pad);
         cudaFree(d.type_start);
         cudaFree(d.flags);
+        cudaFree(d.probe);
     }
 }
 
@@ -410,6 +445,7 @@ extern "C" int agofrt_traj_create(agofrt_traj **out, agofrt_ctx *ctx, size_t nat
         CU(cudaMalloc(&d.type_pad, npad1 * sizeof(int)));
         CU(cudaMalloc(&d.type_start, (ntypes + 1) * sizeof(int)));
         CU(cudaMalloc(&d.flags, 4 * sizeof(unsigned int)));
+        CU(cudaMalloc(&d.probe, 4 * sizeof(double)));
         CU(cudaMemset(d.flags, 0, 4 * sizeof(unsigned int)));
         if (t->npad > 0) CU(cudaMemcpy(d.type_pad, t->type_pad.data(), t->npad * sizeof(int), cudaMemcpyHostToDevice));
         CU(cudaMemcpy(d.type_start, t->type_start.data(), (ntypes + 1) * sizeof(int), cudaMemcpyHostToDevice));
@@ -505,6 +541,7 @@ extern "C" int agofrt_traj_upload(agofrt_traj *t, size_t first_frame, size_t nfr
             if (!std::isfinite(o[k])) t->bad_box = true;
     }
     if (t->natoms > 0) build_perm(t, pos_aos, box_internal);
+    t->slot_of_stale = true;
 
     const size_t frame_elems = t->natoms * 3;
     for (size_t i = 0; i < t->dev.size(); ++i) {
@@ -641,6 +678,39 @@ extern "C" int agofrt_traj_d2_all(agofrt_traj *t, size_t frame_i, size_t frame_j
     const int rc = body();
     cudaFree(dout);
     return rc;
+}
+
+extern "C" int agofrt_traj_d2_pair(agofrt_traj *t, size_t atom_i, size_t atom_j, size_t frame_i, size_t frame_j,
+                                   double *out4) {
+    if (!t || !out4) return fail(AGOFRT_ERR_ARG, "NULL argument");
+    for (size_t f : {frame_i, frame_j})
+        if (f < t->first_frame || f >= t->first_frame + t->nframes)
+            return fail(AGOFRT_ERR_WINDOW, "frame %zu is not in the uploaded window", f);
+    if (atom_i >= t->natoms || atom_j >= t->natoms) return fail(AGOFRT_ERR_ARG, "Atom index out of range");
+    if (t->bad_box || t->has_inf) return fail(AGOFRT_ERR_NONFINITE, "non-finite coordinates or invalid box");
+    // slot of an atom = inverse of the upload's permutation
+    if (t->slot_of.size() != t->natoms || t->slot_of_first != t->first_frame || t->slot_of_stale) {
+        t->slot_of.assign(t->natoms, -1);
+        for (int s = 0; s < t->npad; ++s)
+            if (t->perm[s] >= 0) t->slot_of[t->perm[s]] = s;
+        t->slot_of_first = t->first_frame;
+        t->slot_of_stale = false;
+    }
+    Dev &dv = t->ctx->devs[0];
+    TrajDev &d = t->dev[0];
+    CU(cudaSetDevice(dv.id));
+    const size_t ri = frame_i - t->first_frame, rj = frame_j - t->first_frame;
+    // the AoS staging buffer is free between uploads: 4 doubles of it receive the result
+    CU(cudaMemsetAsync(d.flags + 1, 0, sizeof(unsigned int), dv.stream));
+    CU(launch_d2_pair(d.pos + ri * 3 * static_cast<size_t>(t->npad), d.pos + rj * 3 * static_cast<size_t>(t->npad),
+                      d.box6 + ri * 6, t->stride == 9, t->slot_of[atom_i], t->slot_of[atom_j], t->npad, d.probe,
+                      d.flags + 1, dv.stream));
+    unsigned int flag = 0;
+    CU(cudaMemcpyAsync(out4, d.probe, 4 * sizeof(double), cudaMemcpyDeviceToHost, dv.stream));
+    CU(cudaMemcpyAsync(&flag, d.flags + 1, sizeof(flag), cudaMemcpyDeviceToHost, dv.stream));
+    CU(cudaStreamSynchronize(dv.stream));
+    if (flag) return fail(AGOFRT_ERR_NONFINITE, "minimum image did not converge");
+    return AGOFRT_OK;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -984,6 +984,35 @@ cudaError_t launch_d2_all(const double *pos_i, const double *pos_j, const double
     return cudaGetLastError();
 }
 
+// BaseTrajectory::d2_minImage(i,j,it,jt,x) of ONE pair given by device slots (host-class probe)
+__global__ void d2_pair_kernel(const double *__restrict__ pi, const double *__restrict__ pj,
+                               const double *__restrict__ box6, int triclinic, int si, int sj, int npad,
+                               double *__restrict__ out, unsigned int *error_flag) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    BoxRegs b;
+    b.lhx = box6[0];
+    b.lhy = box6[1];
+    b.lhz = box6[2];
+    b.xy = box6[3];
+    b.xz = box6[4];
+    b.yz = box6[5];
+    double dx = __dsub_rn(pi[si], pj[sj]);
+    double dy = __dsub_rn(pi[npad + si], pj[npad + sj]);
+    double dz = __dsub_rn(pi[2 * static_cast<size_t>(npad) + si], pj[2 * static_cast<size_t>(npad) + sj]);
+    const bool ok = triclinic ? min_image_general<true>(dx, dy, dz, b) : min_image_general<false>(dx, dy, dz, b);
+    out[0] = dx;
+    out[1] = dy;
+    out[2] = dz;
+    out[3] = d2_of(dx, dy, dz);
+    if (!ok) atomicExch(error_flag, 1u);
+}
+
+cudaError_t launch_d2_pair(const double *pos_i, const double *pos_j, const double *box6, int triclinic, int slot_i,
+                           int slot_j, int npad, double *out4, unsigned int *error_flag, cudaStream_t stream) {
+    d2_pair_kernel<<<1, 32, 0, stream>>>(pos_i, pos_j, box6, triclinic, slot_i, slot_j, npad, out4, error_flag);
+    return cudaGetLastError();
+}
+
 // ---------------------------------------------------------------------------------------------
 // FP64 issue-rate microbenchmark: 8 independent DFMA chains per thread
 // ---------------------------------------------------------------------------------------------

@@ -92,6 +92,9 @@ cudaError_t launch_pbc_wrap(double *pos_aos, int natoms, int nframes, const doub
 cudaError_t launch_d2_all(const double *pos_i, const double *pos_j, const double *box6, int triclinic,
                           const int *perm, int natoms, int npad, double *out, unsigned int *error_flag,
                           cudaStream_t stream);
+// one pair, by device slots: out4 = dx,dy,dz,d2
+cudaError_t launch_d2_pair(const double *pos_i, const double *pos_j, const double *box6, int triclinic, int slot_i,
+                           int slot_j, int npad, double *out4, unsigned int *error_flag, cudaStream_t stream);
 // MODE_SAFE validation: bad += number of probes whose unflagged float guess differs from expected[]
 cudaError_t launch_validate_safe(const double *probes, const int *expected, int n, float inv_dr, float c0h, float lim,
                                  int nbin, unsigned int *bad, cudaStream_t stream);

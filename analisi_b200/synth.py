@@ -138,3 +138,56 @@ def lammps_rows_to_internal(box_lammps):
     out[..., 4] = (b[..., 3] - b[..., 2]) / 2
     out[..., 5] = (b[..., 5] - b[..., 4]) / 2
     return out
+
+
+def write_lammps_binary(path, pos, box_lammps, raw_types, vel=None, ids=None, format2020=False, nchunk=1,
+                        shuffle_seed=None, first_step=0, step_stride=1):
+    """Write frames as a LAMMPS binary dump "id type xu yu zu vx vy vz" (8 doubles per atom).
+
+    ``box_lammps`` rows are [xlo,xhi,ylo,yhi,zlo,zhi(,xy,xz,yz)]; 9 columns make the file triclinic.
+    ``format2020`` writes the header flavour with the magic string / revision 2 / unit style / column
+    names (the layout reference lib/include/lammps_struct.h:127-189 reads), otherwise the older one
+    (:31-101).  ``nchunk`` splits the atoms of every frame over several chunks and ``shuffle_seed``
+    permutes their order per frame (after frame 0), as a parallel LAMMPS run does; readers must
+    scatter by atom id."""
+    import struct
+    pos = np.asarray(pos, dtype=np.float64)
+    nfr, n, _ = pos.shape
+    box = np.asarray(box_lammps, dtype=np.float64).reshape(nfr, -1)
+    tri = box.shape[1] == 9
+    vel = np.zeros_like(pos) if vel is None else np.asarray(vel, dtype=np.float64)
+    ids = np.arange(n, dtype=np.int64) if ids is None else np.asarray(ids, dtype=np.int64)
+    raw_types = np.asarray(raw_types)
+    rng = np.random.default_rng(shuffle_seed) if shuffle_seed is not None else None
+    with open(path, "wb") as f:
+        for t in range(nfr):
+            step = first_step + t * step_stride
+            if format2020:
+                magic = b"DUMPCUSTOM"
+                f.write(struct.pack("<q", -len(magic)) + magic + struct.pack("<ii", 1, 2))
+            f.write(struct.pack("<qq", step, n))
+            f.write(struct.pack("<i6i", 1 if tri else 0, 0, 0, 0, 0, 0, 0))
+            f.write(box[t, :6].tobytes())
+            if tri:
+                f.write(box[t, 6:9].tobytes())
+            f.write(struct.pack("<i", 8))
+            if format2020:
+                units, cols = b"lj", b"id type xu yu zu vx vy vz"
+                f.write(struct.pack("<i", len(units)) + units)
+                f.write(struct.pack("<c", b"\x00"))
+                f.write(struct.pack("<i", len(cols)) + cols)
+            f.write(struct.pack("<i", nchunk))
+            order = np.arange(n)
+            if rng is not None and t > 0:
+                order = rng.permutation(n)
+            rows = np.empty((n, 8), dtype=np.float64)
+            rows[:, 0] = ids[order]
+            rows[:, 1] = raw_types[order]
+            rows[:, 2:5] = pos[t, order]
+            rows[:, 5:8] = vel[t, order]
+            cuts = np.linspace(0, n, nchunk + 1).astype(int)
+            for c in range(nchunk):
+                part = rows[cuts[c]:cuts[c + 1]]
+                f.write(struct.pack("<i", part.size))
+                f.write(part.tobytes())
+    return path

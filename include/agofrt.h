@@ -116,6 +116,11 @@ AGOFRT_API int agofrt_pbc_wrap(agofrt_ctx *ctx, double *pos_aos, size_t nframes,
 /* All N^2 (dx,dy,dz,d2) of BaseTrajectory::d2_minImage(i,j,frame_i,frame_j,x) for small N
  * (the probe tests/src/test_trajectory.cpp:21-41 dumps); out is [natoms][natoms][4]. */
 AGOFRT_API int agofrt_traj_d2_all(agofrt_traj *traj, size_t frame_i, size_t frame_j, double *out);
+/* One BaseTrajectory::d2_minImage(i,j,frame_i,frame_j,x) (lib/include/basetrajectory.h:168-194) on the
+ * device copy of the window, atoms in the caller's numbering: out4 = dx,dy,dz,d2.  A probe for the host
+ * classes' d2_minImage accessor, not a hot path. */
+AGOFRT_API int agofrt_traj_d2_pair(agofrt_traj *traj, size_t atom_i, size_t atom_j, size_t frame_i,
+                                   size_t frame_j, double *out4);
 
 /* ---- plan ---------------------------------------------------------------------------------- */
 AGOFRT_API int agofrt_plan_create(agofrt_plan **plan, agofrt_traj *traj, double rmin, double rmax,

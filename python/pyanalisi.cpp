@@ -1,0 +1,189 @@
+// pyanalisi -- pybind11 module with the g(r,t) part of the reference's python interface.
+//
+// Same class and method names as the reference's pyanalisi/src/pyanalisi.cpp for this path:
+//   Trajectory  (numpy buffers, reference :487-528)      Traj  (LAMMPS binary through mmap, :375-450)
+//   Gofrt / Gofrt_lammps (reference :65-82, :535-538): ctor (traj, rmin, rmax, nbin, tmax, nthreads, skip,
+//       every, debug), reset, getNumberOfExtraTimestepsNeeded, calculate, buffer protocol
+//       (leff, ntypes*(ntypes+1), nbin) float64
+//   BoxFormat enum, info(), has_mmap(), and the common trajectory methods (:283-372).
+// The calculation itself runs on the GPUs through libagofrt.so; there is no CPU path, so calculate()
+// raises RuntimeError on a machine without a B200.  Types are registered module_local so the module can
+// share a process with the compiled reference's own module (the parity tests import both).  Additions (not in the reference): Gofrt.counts()
+// (raw integer histogram) and Gofrt.last_stats().  The GIL is released while the device job runs.
+#include <cstring>
+#include <string>
+
+#include "pybind11/numpy.h"
+#include "pybind11/pybind11.h"
+#include "pybind11/stl.h"
+
+#include "analisi/gofrt.h"
+#include "analisi/trajectory.h"
+#include "analisi/trajectory_numpy.h"
+
+namespace py = pybind11;
+
+namespace {
+
+template <class T>
+py::array_t<T> owned_copy(const T *src, std::vector<ssize_t> shape) {
+    py::array_t<T> a(shape);
+    size_t n = 1;
+    for (ssize_t s : shape) n *= static_cast<size_t>(s);
+    if (n) std::memcpy(a.mutable_data(), src, n * sizeof(T));
+    return a;
+}
+
+template <class Tk, class C>
+C &common_trajectory_methods(C &c) {
+    c.def("write_lammps_binary", &Tk::dump_lammps_bin_traj,
+          "file name, starting timestep, end timestep (if < 0 all the trajectory)")
+        .def("get_positions_copy",
+             [](Tk &t) {
+                 double *p = t.positions_data();
+                 if (!p || t.get_nloaded_timesteps() == 0) return py::array_t<double>();
+                 return owned_copy<double>(p, {static_cast<ssize_t>(t.get_nloaded_timesteps()), static_cast<ssize_t>(t.get_natoms()), 3});
+             })
+        .def("get_velocities_copy",
+             [](Tk &t) {
+                 double *p = t.velocity_data();
+                 if (!p || t.get_nloaded_timesteps() == 0) return py::array_t<double>();
+                 return owned_copy<double>(p, {static_cast<ssize_t>(t.get_nloaded_timesteps()), static_cast<ssize_t>(t.get_natoms()), 3});
+             })
+        .def("get_box_copy",
+             [](Tk &t) {
+                 if (t.get_nloaded_timesteps() == 0) return py::array_t<double>();
+                 double *p = t.box(static_cast<int>(t.get_current_timestep()));
+                 if (!p) return py::array_t<double>();
+                 return owned_copy<double>(p, {static_cast<ssize_t>(t.get_nloaded_timesteps()), static_cast<ssize_t>(t.get_box_stride())});
+             })
+        .def("get_type", &Tk::get_type, "get the type used for the internal representation")
+        .def("get_ntypes", [](Tk &t) { return t.get_ntypes(); })
+        .def("get_natoms", [](Tk &t) { return t.get_natoms(); })
+        .def("get_type_ids",
+             [](Tk &t) {
+                 py::array_t<int> a(static_cast<ssize_t>(t.get_natoms()));
+                 t.get_ntypes();
+                 for (size_t i = 0; i < t.get_natoms(); ++i) a.mutable_data()[i] = static_cast<int>(t.get_type(static_cast<unsigned int>(i)));
+                 return a;
+             })
+        .def("get_nloaded_timesteps", &Tk::get_nloaded_timesteps)
+        .def("getNtimesteps", &Tk::get_ntimesteps, "returns estimated number of timesteps from the file size")
+        .def("get_current_timestep", &Tk::get_current_timestep,
+             "return the first timestep currently loaded in this object (meaningful for the lammps binary trajectory interface)")
+        .def("getWrapPbc", &Tk::get_pbc_wrap, "return the pbc wrapping of the trajectory around the center of the cell flag")
+        .def("is_triclinic", &Tk::is_triclinic)
+        .def("minImage", [](Tk &t, size_t i, size_t j, size_t it, size_t jt) {
+            py::array_t<double> out(4);
+            double *x = out.mutable_data();
+            x[3] = t.d2_minImage(i, j, it, jt, x);
+            return out;
+        });
+    return c;
+}
+
+template <class T>
+void define_gofrt(py::module &m, const std::string &suffix) {
+    using G = Gofrt<double, T>;
+    py::class_<G>(m, ("Gofrt" + suffix).c_str(), py::buffer_protocol(), py::module_local())
+        .def(py::init<T *, double, double, unsigned int, unsigned int, unsigned int, unsigned int, unsigned int, bool>(),
+             py::keep_alive<1, 2>(),
+             "calculates g(r) and, in general, g(r,t).  Parameters: Trajectory instance, rmin, rmax, nbin, maximum time lag, "
+             "number of threads (ignored: the GPUs own the parallelism), time skip, every time, debug flag")
+        .def("reset", &G::reset)
+        .def("getNumberOfExtraTimestepsNeeded", &G::nExtraTimesteps)
+        .def("calculate", &G::calculate, py::call_guard<py::gil_scoped_release>())
+        .def("get_columns_description", &G::get_columns_description)
+        .def("counts",
+             [](G &g) {
+                 const std::vector<ssize_t> sh = g.get_shape();
+                 if (g.counts().empty()) return py::array_t<uint64_t>();
+                 return owned_copy<uint64_t>(g.counts().data(), sh);
+             },
+             "raw integer bin counts of the last calculate(): the histogram before the multiplication by incr")
+        .def("last_stats",
+             [](G &g) {
+                 const agofrt_stats &s = g.last_stats();
+                 py::dict d;
+                 d["kernel_ms"] = s.kernel_ms;
+                 d["total_ms"] = s.total_ms;
+                 d["pair_evals"] = s.pair_evals;
+                 d["pair_evals_total"] = s.pair_evals_total;
+                 d["jobs"] = s.jobs;
+                 d["jobs_fast"] = s.jobs_fast;
+                 d["launches"] = s.launches;
+                 d["ndev_local"] = s.ndev_local;
+                 d["world"] = s.world;
+                 d["incr"] = g.get_incr();
+                 return d;
+             })
+        .def_buffer([](G &g) -> py::buffer_info {
+            return py::buffer_info(g.access_vdata(), sizeof(double), py::format_descriptor<double>::format(),
+                                   static_cast<ssize_t>(g.get_shape().size()), g.get_shape(), g.get_stride());
+        });
+}
+
+}  // namespace
+
+PYBIND11_MODULE(pyanalisi, m) {
+    m.doc() = "B200-native g(r,t) behind the pyanalisi interface of rikigigi/analisi";
+
+    py::class_<Trajectory> traj(m, "Traj", py::buffer_protocol(), py::module_local());
+    common_trajectory_methods<Trajectory>(traj)
+        .def(py::init<std::string>(), "name of the binary file to open")
+        .def("setWrapPbc", &Trajectory::set_pbc_wrap, "wrap all the atomic coordinates inside the simulation box read from the binary file")
+        .def("setAccessWindowSize", [](Trajectory &t, int ts) { return static_cast<int>(t.set_data_access_block_size(ts)); },
+             "sets the size of the read block. Must fit in memory.  Returns 1 on success")
+        .def("setAccessStart", [](Trajectory &t, int ts) { return static_cast<int>(t.set_access_at(ts)); },
+             "sets the first timestep to read, and reads the full block")
+        .def("setLoadVelocities", &Trajectory::set_load_velocities,
+             "addition: skip velocities and centres of mass when reading windows (g(r,t) does not use them)")
+        .def("get_lammps_id",
+             [](Trajectory &t) {
+                 int *p = t.get_lammps_id();
+                 py::array_t<int> a = owned_copy<int>(p, {static_cast<ssize_t>(t.get_natoms())});
+                 delete[] p;
+                 return a;
+             })
+        .def("get_lammps_type",
+             [](Trajectory &t) {
+                 int *p = t.get_lammps_type();
+                 py::array_t<int> a = owned_copy<int>(p, {static_cast<ssize_t>(t.get_natoms())});
+                 delete[] p;
+                 return a;
+             })
+        .def_buffer([](Trajectory &g) -> py::buffer_info {
+            return py::buffer_info(g.positions_data(), sizeof(double), py::format_descriptor<double>::format(),
+                                   static_cast<ssize_t>(g.get_shape().size()), g.get_shape(), g.get_stride());
+        });
+
+    py::class_<Trajectory_numpy> trn(m, "Trajectory", py::module_local());
+    common_trajectory_methods<Trajectory_numpy>(trn)
+        .def(py::init<py::buffer, py::buffer, py::buffer, py::buffer, Trajectory_numpy::BoxFormat, bool, bool>(),
+             py::keep_alive<1, 2>(), py::keep_alive<1, 3>(), py::keep_alive<1, 4>(), py::keep_alive<1, 5>(),
+             "positions (double) (ntimesteps,natoms,3); velocities (double) (ntimesteps,natoms,3); types (int) (natoms); "
+             "lattice vectors (double); format of lattice vectors (BoxFormat); wrap atoms inside the cell using pbc; "
+             "save rotation matrix if triclinic format is used and a rotation is needed")
+        .def("get_rotation_matrix", [](Trajectory_numpy &t) {
+            double *q = t.get_rotation_matrix(0);
+            if (!q) return py::array_t<double>();
+            return owned_copy<double>(q, {static_cast<ssize_t>(t.get_ntimesteps()), 3, 3});
+        });
+
+    py::enum_<Trajectory_numpy::BoxFormat>(m, "BoxFormat", py::arithmetic(), py::module_local())
+        .value("Invalid", Trajectory_numpy::BoxFormat::Invalid)
+        .value("CellVectors", Trajectory_numpy::BoxFormat::Cell_vectors)
+        .value("LammpsOrtho", Trajectory_numpy::BoxFormat::Lammps_ortho)
+        .value("LammpsTriclinic", Trajectory_numpy::BoxFormat::Lammps_triclinic);
+
+    define_gofrt<Trajectory>(m, "_lammps");
+    define_gofrt<Trajectory_numpy>(m, "");
+
+    m.def("info", []() -> std::string { return std::string("analisi g(r,t), B200-native: ") + agofrt_version(); });
+    m.def("has_mmap", []() -> bool { return true; });
+    m.def("device_count", []() {
+        int n = 0;
+        agofrt_device_count(&n);
+        return n;
+    });
+}

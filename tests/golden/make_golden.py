@@ -165,14 +165,63 @@ def live_reference_cases(m):
     np.savez_compressed(os.path.join(HERE, "live_reference.npz"), **flat)
 
 
+def cell_vectors_rotation(m):
+    """Trajectory_numpy with BoxFormat.CellVectors and general (rotated) cells: the reference QR-rotates
+    cell, positions and velocities into the LAMMPS frame (lib/include/triclinic.h:10-73 with Eigen's
+    Householder QR, lib/src/trajectory_numpy.cpp:89-172).  Pins the host mirror's hand-written QR and,
+    on the GPU, g(r,t) through that input format."""
+    rng = np.random.default_rng(31)
+    nfr, n = 7, 60
+    cell = np.array([[7.0, 0.0, 0.0], [1.2, 6.5, 0.0], [0.9, -0.7, 6.0]]).T.copy()  # columns = cell vectors
+    cells = []
+    for f in range(nfr):
+        if f in (0, 3, 5):  # runs of identical cells, a new random orientation per run
+            q, _ = np.linalg.qr(rng.normal(size=(3, 3)))
+            cur = q @ (cell * (1.0 + 0.01 * f))
+        cells.append(cur)
+    cells = np.ascontiguousarray(np.stack(cells))
+    frac = rng.random(size=(nfr, n, 3))
+    pos = np.ascontiguousarray(np.einsum("fij,fnj->fni", cells, frac))
+    vel = rng.normal(size=pos.shape)
+    types = (np.arange(n) % 2 * 4 + 1).astype(np.int32)
+    out = dict(pos=pos, vel=vel, types=types, cells=cells)
+    for wrap in (False, True):
+        tr = m.Trajectory(pos, vel, types, cells, m.BoxFormat.CellVectors, wrap, True)
+        tag = "wrap" if wrap else "nowrap"
+        out["pos_" + tag] = tr.get_positions_copy()
+        if not wrap:
+            out["box_internal"] = tr.get_box_copy()
+            out["rotation"] = tr.get_rotation_matrix()
+            out["type_ids"] = tr.get_type_ids()
+        else:
+            g = m.Gofrt(tr, 0.0, 3.0, 30, 3, 2, 1, 1, False)
+            g.reset(4)
+            g.calculate(1)
+            v = np.array(g, copy=True)
+            out["vdata"] = v
+            out["counts"] = np.rint(v * 4).astype(np.uint64)
+            out["params"] = np.array([0.0, 3.0, 30, 3, 1, 1, 4, 1], dtype=np.float64)
+    np.savez_compressed(os.path.join(HERE, "cell_vectors_rotation.npz"), **out)
+
+
+def cli_golden_text():
+    """The reference's CLI golden output for the g(r,t) branch (tests/test_cli.sh:33-34), copied as is:
+    analisi -i tests/data/lammps2020.bin -g 100 -F 0.0 4.0 -S {1,10} -s 8  (20 blocks, mean and variance)."""
+    import shutil
+    for name in ("pair_corr_no_t", "pair_corr_t"):
+        shutil.copyfile(os.path.join(REF, "tests/data/cli", name), os.path.join(HERE, "cli_" + name + ".txt"))
+
+
 def main():
     m = ref_module()
     gofr_numpy(m)
     gofr_notebook(m)
     min_image_and_pbc(m)
     live_reference_cases(m)
+    cell_vectors_rotation(m)
+    cli_golden_text()
     for f in sorted(os.listdir(HERE)):
-        if f.endswith(".npz"):
+        if f.endswith(".npz") or f.endswith(".txt"):
             print("%-24s %8d bytes" % (f, os.path.getsize(os.path.join(HERE, f))))
 
 

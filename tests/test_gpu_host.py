@@ -1,0 +1,229 @@
+"""GPU: the reference-facing layers -- the pybind11 module (python/pyanalisi.cpp) and the CLI (cli/main.cpp),
+both host C++ over the C ABI -- against the reference's golden outputs, the fixtures made by the
+compiled reference, and the oracle.  The tests read like the reference's own (tests/test_gofrt.py,
+tests/test_notebook.py, tests/test_cli.sh)."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import oracle
+from analisi_b200 import build as b
+from analisi_b200 import cabi, synth
+from conftest import GOLDEN, LIVE_CASES, ROOT, live_case, load_golden
+
+pytestmark = pytest.mark.gpu
+
+REL_TOL = 1e-12   # north_star: normalised g(r,t) within 1e-12 relative
+REFDATA = os.path.join(ROOT, "tests", "_refdata")   # copies of the reference's test trajectories (git-ignored)
+
+
+@pytest.fixture(scope="module")
+def host():
+    cli, ext = b.build_host()
+    d = os.path.dirname(ext)
+    if d not in sys.path:
+        sys.path.insert(0, d)
+    import pyanalisi
+    return cli, pyanalisi
+
+
+def close(v, ref):
+    scale = np.maximum(np.abs(ref), 1e-300)
+    return (np.abs(v - ref) <= REL_TOL * scale).all()
+
+
+def test_pyanalisi_gofrt_numpy_golden(host, tmp_path, monkeypatch):
+    """reference tests/test_gofrt.py verbatim: Gofrt(traj,0.0,3.8,200,10,4,10,False,1); reset(700); calculate(0)
+    -- including the positional-argument trap (every=False -> 1, debug=1 -> a gofrt.dump appears)."""
+    _, pa = host
+    monkeypatch.chdir(tmp_path)
+    z = load_golden("gofr_numpy.npz")
+    pos = z["pos"]
+    boxl = oracle.internal_to_lammps(z["box_internal"])
+    tr = pa.Trajectory(pos, np.zeros_like(pos), z["types"].astype(np.int32), boxl, pa.BoxFormat.LammpsOrtho, False, False)
+    g = pa.Gofrt(tr, 0.0, 3.8, 200, 10, 4, 10, False, 1)
+    g.reset(700)
+    g.calculate(0)
+    v = np.array(g, copy=True)
+    assert v.shape == (10, 12, 200)
+    assert np.array_equal(g.counts(), z["counts"])
+    nz = z["csv"] != 0
+    assert np.abs(v[nz] - z["csv"][nz]).max() <= 1e-11   # the CSV holds the reference's 4-thread float sums
+    assert (v[~nz] == 0).all()
+    assert os.path.exists(tmp_path / "gofrt.dump")
+    rows = open(tmp_path / "gofrt.dump").read().split("\n")
+    assert len(rows) == 10 * 200 + 3 and len(rows[0].split()) == 14
+
+
+def test_pyanalisi_gofrt_lammps_notebook_golden(host, tmp_path):
+    """reference tests/test_notebook.py / notebooks/calc_inspector.ipynb: Traj + setWrapPbc(True) +
+    Gofrt_lammps(traj,0.5,3.8,100,1,4,10,False,1).  The fixture keeps every 10th frame, so skip is 1 here."""
+    _, pa = host
+    z = load_golden("gofr_notebook.npz")
+    boxl = oracle.internal_to_lammps(z["box_internal"])
+    path = str(tmp_path / "nb.bin")
+    synth.write_lammps_binary(path, z["pos_unwrapped"], boxl, z["types"])
+    tr = pa.Traj(path)
+    tr.setWrapPbc(True)
+    tr.setAccessWindowSize(100)
+    tr.setAccessStart(0)
+    assert np.array_equal(tr.get_positions_copy(), z["pos_wrapped"])
+    g = pa.Gofrt_lammps(tr, 0.5, 3.8, 100, 1, 4, 1, 1, False)
+    g.reset(99)
+    g.calculate(0)
+    assert np.array_equal(g.counts(), z["counts"])
+    assert close(np.array(g), z["csv"]) or np.abs(np.array(g) - z["csv"]).max() < 1e-11
+
+
+@pytest.mark.parametrize("name", LIVE_CASES)
+def test_pyanalisi_live_reference_cases(host, name):
+    """triclinic / NPT / unwrapped / big tilt / ragged loops through pyanalisi.Trajectory + Gofrt: counts
+    bit-exact, count*incr within 1e-12 relative of the reference's own vdata (fixtures by the compiled reference)."""
+    _, pa = host
+    d = live_case(name)
+    rmin, rmax, nbin, tmax, skip, every, nts, primo = d["params"]
+    fmt = pa.BoxFormat.LammpsTriclinic if d["box_lammps"].shape[1] == 9 else pa.BoxFormat.LammpsOrtho
+    pos = np.ascontiguousarray(d["pos_in"])
+    tr = pa.Trajectory(pos, np.zeros_like(pos), d["raw_types"].astype(np.int32), d["box_lammps"], fmt, bool(d["wrap"]), False)
+    assert np.array_equal(tr.get_positions_copy(), d["pos_ref"])
+    assert np.array_equal(tr.get_box_copy(), d["box_internal"])
+    assert np.array_equal(tr.get_type_ids(), d["type_ids"])
+    g = pa.Gofrt(tr, rmin, rmax, int(nbin), int(tmax), 3, int(skip), int(every), False)
+    g.reset(int(nts))
+    g.calculate(int(primo))
+    assert np.array_equal(g.counts(), d["counts"])
+    assert close(np.array(g), d["vdata"])
+
+
+def test_pyanalisi_cell_vectors_rotation(host):
+    """CellVectors input with rotated cells: QR on the host, wrap + g(r,t) on the GPU, vs the compiled reference"""
+    _, pa = host
+    z = load_golden("cell_vectors_rotation.npz")
+    tr = pa.Trajectory(z["pos"], z["vel"], z["types"], z["cells"], pa.BoxFormat.CellVectors, True, True)
+    assert np.array_equal(tr.get_positions_copy(), z["pos_wrap"])
+    rmin, rmax, nbin, tmax, skip, every, nts, primo = z["params"]
+    g = pa.Gofrt(tr, rmin, rmax, int(nbin), int(tmax), 2, int(skip), int(every), False)
+    g.reset(int(nts))
+    g.calculate(int(primo))
+    assert np.array_equal(g.counts(), z["counts"])
+    assert close(np.array(g), z["vdata"])
+    # the minImage probe of the trajectory classes (reference pyanalisi.cpp:356-371)
+    bi = z["box_internal"]
+    d = oracle.d2_all(z["pos_wrap"][2], z["pos_wrap"][4], bi[2])
+    for i, j in ((0, 0), (3, 17), (59, 1)):
+        assert np.array_equal(tr.minImage(i, j, 2, 4), d[i, j])
+
+
+def _rows(text):
+    return [l for l in text.split("\n") if l and not l.startswith("#")]
+
+
+def _g(x):
+    return "%g" % x
+
+
+def _cli_text(mean, var, leff, every, nbin, ncol):
+    lines = []
+    for t in range(0, leff, every):
+        for r in range(nbin):
+            row = "%d %d" % (t, r)
+            for k in range(ncol):
+                row += " %s %s" % (_g(mean[t, k, r]), _g(var[t, k, r]))
+            lines.append(row)
+    return lines
+
+
+@pytest.mark.parametrize("tri,ntypes,args", [
+    (False, 2, dict(g=40, F=(0.0, 2.5), S=5, s=3, e=1, B=4)),
+    (True, 3, dict(g=25, F=(0.4, 2.2), S=6, s=2, e=2, B=3)),
+    (True, 1, dict(g=30, F=(0.0, 2.0), S=0, s=1, e=1, B=5)),
+])
+def test_cli_blocks_vs_oracle(host, tmp_path, tri, ntypes, args):
+    """analisi -i f -g nbin -F rmin rmax -S lmax -s skip -e every -B blocks: mmap reader + GPU wrap + Gofrt +
+    BlockAverage + MediaVar + printing, against the oracle's restatement of the same chain (the oracle is
+    pinned by the reference's CLI goldens in test_oracle_golden.py)."""
+    cli, _ = host
+    nfr = 46
+    pos, box, types = synth.small_case(21, (4, 4, 3), 1.05, ntypes, tri, nfr, "parity", (0.2, -0.1, 0.15), False)
+    path = str(tmp_path / "c.bin")
+    synth.write_lammps_binary(path, pos, box, types * 2 + 1, nchunk=2, shuffle_seed=3)
+    argv = ["-i", path, "-g", str(args["g"]), "-F", str(args["F"][0]), str(args["F"][1]), "-S", str(args["S"]),
+            "-s", str(args["s"]), "-e", str(args["e"]), "-B", str(args["B"]), "-N", "3"]
+    r = subprocess.run([cli] + argv, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, cwd=str(tmp_path), timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    # the same chain with the oracle
+    bi = synth.lammps_rows_to_internal(box)
+    wrapped = oracle.pbc_wrap(pos, bi)
+    n_b, lmax = args["B"], args["S"]
+    nextra = oracle.nextra(nfr, n_b, lmax)
+    s = (nfr - nextra) // n_b
+    blocks = []
+    for ib in range(n_b):
+        lo = ib * s
+        blocks.append(oracle.vdata(wrapped[lo:lo + s + nextra], bi[lo:lo + s + nextra], types, args["F"][0], args["F"][1],
+                                   args["g"], lmax, s, primo=lo, skip=args["s"], every=args["e"], ntypes=ntypes,
+                                   first_frame=lo, total_frames=nfr, ref_nthreads=1))
+    mean, var = oracle.mediavar(np.array(blocks))
+    leff = oracle.leff(s, lmax)
+    want = _cli_text(mean, var, leff, args["e"], args["g"], ntypes * (ntypes + 1))
+    got = _rows(r.stdout)
+    assert len(got) == len(want)
+    assert got == want
+    head = [l for l in r.stdout.split("\n") if l.startswith("#")]
+    assert head[0].startswith("# The first column is the time difference") and len(head) == 3 + ntypes * (ntypes + 1)
+
+
+@pytest.mark.parametrize("name,S", [("pair_corr_no_t", 1), ("pair_corr_t", 10)])
+def test_cli_reference_golden_text(host, tmp_path, name, S):
+    """reference tests/test_cli.sh:33-34 verbatim: analisi -i lammps2020.bin -g 100 -F 0.0 4.0 -S {1,10} -s 8,
+    stdout compared with the reference's golden text (tests/golden/cli_*.txt) the way the script does.
+    Needs the 51 MB input, copied to tests/_refdata by build() where the reference tree exists."""
+    cli, _ = host
+    path = os.path.join(REFDATA, "lammps2020.bin")
+    if not os.path.exists(path):
+        pytest.skip("tests/_refdata/lammps2020.bin not present")
+    r = subprocess.run([cli, "-i", path, "-g", "100", "-F", "0.0", "4.0", "-S", str(S), "-s", "8"], stdout=subprocess.PIPE,
+                       stderr=subprocess.PIPE, text=True, cwd=str(tmp_path), timeout=900)
+    assert r.returncode == 0, r.stderr[-2000:]
+    gold = open(os.path.join(GOLDEN, "cli_" + name + ".txt")).read()
+    assert r.stdout.rstrip("\n") == gold.rstrip("\n")   # `$(...)` strips trailing newlines in the script
+
+
+def test_cli_c1_bundled_trajectory(host, tmp_path):
+    """BASELINE.json configs[0]: analisi -i tests/data/lammps.bin -g 200 -F 0.7 3.5 (56 atoms, 7958 frames,
+    20 blocks of 378 steps, 378 lags: 8.96e9 pair evaluations; 1064 s with the reference on 8 cores).
+    First and last block are recomputed by the oracle; the text rows of lag 0 and lag 377 must carry the
+    block-averaged values of an independent numpy Welford over the python-side block results."""
+    cli, pa = host
+    path = os.path.join(REFDATA, "lammps.bin")
+    if not os.path.exists(path):
+        pytest.skip("tests/_refdata/lammps.bin not present")
+    r = subprocess.run([cli, "-i", path, "-g", "200", "-F", "0.7", "3.5"], stdout=subprocess.PIPE, stderr=subprocess.PIPE,
+                       text=True, cwd=str(tmp_path), timeout=1500)
+    assert r.returncode == 0, r.stderr[-2000:]
+    got = _rows(r.stdout)
+    tr = pa.Traj(path)
+    tr.setWrapPbc(True)
+    nts, n_b, nbin = tr.getNtimesteps(), 20, 200
+    g = pa.Gofrt_lammps(tr, 0.7, 3.5, nbin, 0, 2, 1, 1, False)
+    nextra = g.getNumberOfExtraTimestepsNeeded(n_b)
+    s = (nts - nextra) // n_b
+    assert (nts, nextra, s) == (7958, 379, 378)
+    assert len(got) == s * nbin
+    tr.setAccessWindowSize(s + nextra)
+    blocks = []
+    for ib in range(n_b):
+        tr.setAccessStart(ib * s)
+        g.reset(s)
+        g.calculate(ib * s)
+        blocks.append(np.array(g, copy=True))
+        if ib in (0, n_b - 1):   # oracle on a subset of lags of this block (full block: 4.5e8 pair evaluations)
+            c = oracle.counts(tr.get_positions_copy(), tr.get_box_copy(), tr.get_type_ids(), 0.7, 3.5, nbin, 3, s,
+                              primo=ib * s, skip=1, ntypes=2, first_frame=ib * s, total_frames=nts)
+            assert np.array_equal(g.counts()[:3], c)
+    mean, var = oracle.mediavar(np.array(blocks))
+    want = _cli_text(mean, var, s, 1, nbin, 6)
+    assert got == want
