@@ -193,6 +193,7 @@ def main():
     ap.add_argument("--quick", action="store_true", help="tiny block (smoke/profiling), not a bench number")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--options", type=int, default=0)
+    ap.add_argument("--cpu-seconds", type=float, default=None, help="size of the CPU sample (default 12 s; 8 s per step for --impl reference)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -220,7 +221,7 @@ def main():
         vals = []
         res = None
         for k in range(args.warmup + args.steps):
-            res = cpu_sample(w, pos, box_lammps, box_internal, types, target_s=8.0)
+            res = cpu_sample(w, pos, box_lammps, box_internal, types, target_s=args.cpu_seconds or 8.0)
             if k >= args.warmup:
                 vals.append(res["value"])
             if k == 0 and args.warmup > 1:
@@ -239,20 +240,10 @@ def main():
 
     # ------------------------------------------------------------------ native arm
     from analisi_b200 import cabi
-    dist = None
-    if world > 1:
-        import torch
-        import torch.distributed as dist
-        torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from analisi_b200 import dist as adist
+    ranks = adist.Ranks()
     ctx = cabi.Context([local_rank])
-    if world > 1:
-        import torch
-        idt = torch.zeros(cabi.COMM_ID_BYTES, dtype=torch.uint8, device="cuda")
-        if rank == 0:
-            idt.copy_(torch.frombuffer(bytearray(cabi.Context.unique_id()), dtype=torch.uint8))
-        dist.broadcast(idt, 0)
-        ctx.join(bytes(idt.cpu().numpy().tobytes()), rank, world)
+    adist.join_communicator(ranks, ctx)
 
     pos, box_lammps, box_internal, types = make_window(w, nframes)
     # wrap=True, as the reference callers do (analisi/main.cpp:558): the wrap runs on the GPU
@@ -264,19 +255,7 @@ def main():
     tr = cabi.DeviceTrajectory(ctx, w.natoms, box_internal.shape[1], types, w.ntypes, nframes)
     plan = cabi.Plan(tr, w.rmin, w.rmax, w.nbin)
 
-    def barrier():
-        if dist is not None:
-            import torch
-            torch.cuda.synchronize()
-            dist.barrier()
-
-    def maxrank(x):
-        if dist is None:
-            return x
-        import torch
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+    barrier, maxrank = ranks.barrier, ranks.max_over_ranks
 
     # roofline denominator, measured in this run
     peak = ctx.fp64_peak(1.0)
@@ -347,7 +326,7 @@ def main():
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
-            line["cpu_baseline"] = cpu_sample(w, pos, box_lammps, box_internal, types)
+            line["cpu_baseline"] = cpu_sample(w, pos, box_lammps, box_internal, types, target_s=args.cpu_seconds or 12.0)
         except Exception as e:  # the baseline is a report, never a reason to lose the GPU number
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": host_threads(), "kind": "unavailable",
                                     "sample": "failed: %r" % (e,)}
@@ -356,8 +335,7 @@ def main():
     plan.close()
     tr.close()
     ctx.close()
-    if dist is not None:
-        dist.destroy_process_group()
+    ranks.close()
     return 0
 
 

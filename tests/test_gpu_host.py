@@ -41,8 +41,11 @@ def test_pyanalisi_gofrt_numpy_golden(host, tmp_path, monkeypatch):
     _, pa = host
     monkeypatch.chdir(tmp_path)
     z = load_golden("gofr_numpy.npz")
-    pos = z["pos"]
-    boxl = oracle.internal_to_lammps(z["box_internal"])
+    # the fixture keeps the 700 frames the loops touch (origins 0..690, lags 0..9) of the 7958 the reference
+    # test loads; the length check of calculate() (gofrt.cpp:81) wants leff + ntimesteps <= frames + 1,
+    # so pad with frames that are never read
+    pos = np.concatenate([z["pos"], np.repeat(z["pos"][-1:], 10, axis=0)])
+    boxl = oracle.internal_to_lammps(np.concatenate([z["box_internal"], np.repeat(z["box_internal"][-1:], 10, axis=0)]))
     tr = pa.Trajectory(pos, np.zeros_like(pos), z["types"].astype(np.int32), boxl, pa.BoxFormat.LammpsOrtho, False, False)
     g = pa.Gofrt(tr, 0.0, 3.8, 200, 10, 4, 10, False, 1)
     g.reset(700)
@@ -72,10 +75,11 @@ def test_pyanalisi_gofrt_lammps_notebook_golden(host, tmp_path):
     tr.setAccessStart(0)
     assert np.array_equal(tr.get_positions_copy(), z["pos_wrapped"])
     g = pa.Gofrt_lammps(tr, 0.5, 3.8, 100, 1, 4, 1, 1, False)
-    g.reset(99)
+    g.reset(100)   # the 100 kept frames = the 100 origins 0,10,..,990 of reset(999) with skip 10
     g.calculate(0)
     assert np.array_equal(g.counts(), z["counts"])
-    assert close(np.array(g), z["csv"]) or np.abs(np.array(g) - z["csv"]).max() < 1e-11
+    # the reference normalises by int(999/10) = 99 (gofrt.cpp:91), this run by 100
+    assert np.abs(np.array(g) * (100.0 / 99.0) - z["csv"]).max() < 1e-11
 
 
 @pytest.mark.parametrize("name", LIVE_CASES)
