@@ -70,6 +70,9 @@ static NcclApi &nccl_api() {
     static bool tried = false;
     if (tried) return api;
     tried = true;
+    // NCCL writes its version banner / debug lines to stdout unless told otherwise; stdout belongs to the
+    // caller's data (the CLI prints g(r,t) there), so default the debug stream to stderr.
+    setenv("NCCL_DEBUG_FILE", "/dev/stderr", 0);
     const char *names[] = {"libnccl.so.2", "libnccl.so"};
     for (const char *n : names) {
         api.handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
@@ -171,6 +174,8 @@ struct agofrt_plan {
     unsigned hlo = 0, hspan = 0;
     float inv_dr = 0, c0 = 0;
     float c0h = 0, lim = 0;      // safe-zone binning: c0 - 0.5, 0.5 - eps
+    float qmax = 0;              // ... clamp of the bin coordinate: nbin + 0.25
+    int glo = 0;                 // ... guard bins below bin 0 in every shared-memory histogram row
     bool safe_ok = false;        // validated on the device when the plan was made
     double q_reach = 0;          // largest bin coordinate the float path may meet before it must give up
     std::vector<PlanDev> dev;
@@ -808,7 +813,10 @@ static int validate_safe_zone(agofrt_plan *p) {
     }
     const double top = p->thr[nbin];
     if (std::isfinite(top))
-        for (double f : {1.0000001, 1.001, 1.5, 4.0, 100.0, 1e6}) probes.push_back(top * f + 1e-300);
+        for (double f : {1.0000001, 1.001, 1.5, 4.0, 100.0, 1e6, 1e30, 1e300}) probes.push_back(top * f + 1e-300);
+    probes.push_back(std::numeric_limits<double>::infinity());
+    probes.push_back(std::numeric_limits<double>::quiet_NaN());   // ghost slots
+    for (double tiny : {4.9e-324, 1e-310, 1e-300, 1e-45, 1e-38, 1e-30}) probes.push_back(tiny);
     std::vector<int> expected(probes.size());
     for (size_t i = 0; i < probes.size(); ++i) expected[i] = exact_bin(p->thr, nbin, probes[i]);
 
@@ -825,8 +833,8 @@ static int validate_safe_zone(agofrt_plan *p) {
         CU(cudaMemcpyAsync(dprobe, probes.data(), probes.size() * sizeof(double), cudaMemcpyHostToDevice, dv.stream));
         CU(cudaMemcpyAsync(dexp, expected.data(), probes.size() * sizeof(int), cudaMemcpyHostToDevice, dv.stream));
         CU(cudaMemsetAsync(dbad, 0, sizeof(unsigned int), dv.stream));
-        CU(launch_validate_safe(dprobe, dexp, static_cast<int>(probes.size()), p->inv_dr, p->c0h, p->lim,
-                                static_cast<int>(nbin), dbad, dv.stream));
+        CU(launch_validate_safe(dprobe, dexp, static_cast<int>(probes.size()), p->inv_dr, p->c0h, p->lim, p->qmax,
+                                static_cast<int>(nbin), p->glo, dbad, dv.stream));
         CU(cudaMemcpyAsync(&bad, dbad, sizeof(bad), cudaMemcpyDeviceToHost, dv.stream));
         CU(cudaStreamSynchronize(dv.stream));
         return AGOFRT_OK;
@@ -836,7 +844,10 @@ static int validate_safe_zone(agofrt_plan *p) {
     cudaFree(dexp);
     cudaFree(dbad);
     if (rc != AGOFRT_OK) return rc;
-    if (bad != 0) p->safe_ok = false;
+    if (bad != 0) {
+        p->safe_ok = false;
+        p->glo = 0;
+    }
     return AGOFRT_OK;
 }
 
@@ -855,13 +866,6 @@ extern "C" int agofrt_plan_create(agofrt_plan **out, agofrt_traj *traj, double r
     p->rmin2 = rmin * rmin;
 
     const int nt = traj->ntypes;
-    const size_t smem = pair_kernel_smem_bytes(nt, static_cast<int>(nbin), true);
-    for (const Dev &d : traj->ctx->devs)
-        if (smem > d.smem_optin)
-            return fail(AGOFRT_ERR_TOO_LARGE,
-                        "histogram of %d type-pair rows x %u bins needs %zu bytes of shared memory (> %zu)",
-                        nt * (nt + 1), nbin, smem, d.smem_optin);
-
     if (p->dr > 0 && std::isfinite(p->dr) && std::isfinite(rmin)) {
         build_thresholds(rmin, p->dr, nbin, p->thr_full);
     } else {
@@ -902,9 +906,28 @@ extern "C" int agofrt_plan_create(agofrt_plan **out, agofrt_traj *traj, double r
         if (eps <= std::ldexp(1.0, -6) && q_top < std::ldexp(1.0, 21)) {
             p->c0h = static_cast<float>(-rmin / p->dr - 0.5);
             p->lim = static_cast<float>(0.5 - eps);
+            p->qmax = static_cast<float>(nbin) + 0.25f;
             p->q_reach = std::ldexp(1.0, 21);
-            p->safe_ok = true;
+            // the smallest guess is the one of d2 = 0: rint(c0h); two spare words for its roundings
+            const double lowest = std::floor(static_cast<double>(p->c0h));
+            const double guards = lowest < 0 ? -lowest + 2 : 2;
+            if (guards <= 4096) {
+                p->glo = static_cast<int>(guards);
+                p->safe_ok = true;
+            }
         }
+    }
+    // shared-memory budget; the guard bins are given up before the plan is refused
+    for (const Dev &d : traj->ctx->devs) {
+        if (pair_kernel_smem_bytes(nt, static_cast<int>(nbin), p->glo, true) > d.smem_optin && p->glo > 0) {
+            p->glo = 0;
+            p->safe_ok = false;
+        }
+        const size_t smem = pair_kernel_smem_bytes(nt, static_cast<int>(nbin), p->glo, true);
+        if (smem > d.smem_optin)
+            return fail(AGOFRT_ERR_TOO_LARGE,
+                        "histogram of %d type-pair rows x %u bins needs %zu bytes of shared memory (> %zu)",
+                        nt * (nt + 1), nbin, smem, d.smem_optin);
     }
 
     p->dev.resize(traj->ctx->devs.size());
@@ -1080,11 +1103,11 @@ extern "C" int agofrt_block(agofrt_plan *p, size_t primo, unsigned ntimesteps, u
         }
         const double rm = std::max(p->rmax, 0.0), r0 = std::max(p->rmin, 0.0);
         const double share = 4.18879020478639 * (rm * rm * rm - r0 * r0 * r0) / vmin;
-        (void)share;   // the software-pipelined kernel is measured slower on B200 even at 44% in range: opt-in only
+        dense = share > 0.15;   // the dense kernel only drops the group filter
         if (options & AGOFRT_OPT_DENSE) dense = true;
         if (options & AGOFRT_OPT_SPARSE) dense = false;
     }
-    const size_t smem = pair_kernel_smem_bytes(nt, static_cast<int>(p->nbin), want_edges);
+    const size_t smem = pair_kernel_smem_bytes(nt, static_cast<int>(p->nbin), p->glo, want_edges);
 
     // ---- pinned read-back buffer ----
     if (len > p->host_counts_len) {
@@ -1166,6 +1189,8 @@ extern "C" int agofrt_block(agofrt_plan *p, size_t primo, unsigned ntimesteps, u
                 pp.hspan = p->hspan;
                 pp.c0h = p->c0h;
                 pp.lim = p->lim;
+                pp.qmax = p->qmax;
+                pp.glo = p->glo;
                 pp.hhi = p->hlo + p->hspan;
                 int mode = kModeThr;
                 if (want_edges)

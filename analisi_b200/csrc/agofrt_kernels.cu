@@ -107,17 +107,32 @@ __device__ __forceinline__ bool min_image_general(double &dx, double &dy, double
 // same signed subtraction of the tilt factors from the lower components).  A component whose lower
 // neighbours do not depend on its sign (orthorhombic cells; the last, x, component of triclinic
 // ones) only feeds its square, so |x| - 2*l_half serves as well: (-a)^2 == a^2 exactly.
-// The wrap of one component is  x = fma(m, -2*l_half, |x|)  with m = 1.0 or 0.0 from the compare:
+// The wrap of a component whose sign matters (z and y of a triclinic cell: the tilt corrections of the
+// lower components follow it) is  x = fma(m, -2*l_half, x)  with m = +-1.0 or 0.0 from the compare:
 // m*c is exact, so the fused operation rounds once, exactly like the reference's "x -= 2*l_half"
-// (m = 1) or leaves |x| untouched (m = 0).  Building m costs one 32-bit select (its low word is
-// the constant 0), and the same m serves the tilt corrections of the lower components:
-// 2 FP64 instructions + 1 select per wrapped component, nothing on the other pipes.
-__device__ __forceinline__ double mask01(bool p) { return __hiloint2double(p ? 0x3FF00000 : 0, 0); }
+// (m = 1) or leaves x untouched (m = 0), and the same m serves the tilt corrections.
 // +-1.0 with the sign of s when p, else 0.0: one LOP3 (sign | exponent of 1.0) and one select, each
 // reading a single register
 __device__ __forceinline__ double mask_signed(bool p, double s) {
     const int one = (__double2hiint(s) & 0x80000000) | 0x3FF00000;
     return __hiloint2double(p ? one : 0, 0);
+}
+
+// A component that only feeds its square (all three of an orthorhombic cell; the last, x, of a triclinic
+// one):  if |x| > l_half then x = |x| - 2*l_half  -- one DSETP and one PREDICATED DADD, nothing on the
+// other pipes (no select, no mask register).  When the predicate is false x keeps its sign; (-a)^2 == a^2.
+// Written as a branch over one instruction: ptxas if-converts it to "@P DADD" (a "@p add" in PTX comes
+// back as DADD + 2 FSEL, two more issue slots).
+__device__ __forceinline__ void wrap_abs(double &x, double lh, double nL) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .f64 a;\n\t"
+        "abs.f64 a, %0;\n\t"
+        "setp.gt.f64 p, a, %1;\n\t"
+        "@!p bra.uni WRAP_SKIP%=;\n\t"
+        "add.rn.f64 %0, a, %2;\n\t"
+        "WRAP_SKIP%=:\n\t}"
+        : "+d"(x)
+        : "d"(lh), "d"(nL));
 }
 
 template <bool TRI>
@@ -136,23 +151,11 @@ __device__ __forceinline__ void min_image_single(double &dx, double &dy, double 
             dy = __fma_rn(m, nLy, dy);
             dx = __fma_rn(m, -b.xy, dx);
         }
-        {
-            const double m = mask01(fabs(dx) > b.lhx);   // last component: only its square is used
-            dx = __fma_rn(m, nLx, fabs(dx));
-        }
+        wrap_abs(dx, b.lhx, nLx);   // last component: only its square is used
     } else {
-        {
-            const double m = mask01(fabs(dz) > b.lhz);
-            dz = __fma_rn(m, nLz, fabs(dz));
-        }
-        {
-            const double m = mask01(fabs(dy) > b.lhy);
-            dy = __fma_rn(m, nLy, fabs(dy));
-        }
-        {
-            const double m = mask01(fabs(dx) > b.lhx);
-            dx = __fma_rn(m, nLx, fabs(dx));
-        }
+        wrap_abs(dz, b.lhz, nLz);
+        wrap_abs(dy, b.lhy, nLy);
+        wrap_abs(dx, b.lhx, nLx);
     }
 }
 
@@ -259,39 +262,87 @@ __device__ __forceinline__ unsigned int bin_pair_thr(double v, uint32_t thr2_add
     return miss;
 }
 
-// MODE_SAFE fast path for one pair.  qh = sqrtf(d2)*inv_dr + (c0 - 0.5) is the bin coordinate minus
-// one half; adding 1.5*2^23 rounds it to the nearest integer n (the guessed bin) in the low mantissa
-// bits, and |qh - n| < 0.5 - eps says the guess is more than eps bins away from both edges of bin n.
-// min.f32 returns the non-NaN operand: NaN (ghost slots) and absurdly large values land on QMAX,
-// which is "safe" and outside every histogram.  `mask |= bit` marks the pairs that need the exact
-// search.
-__device__ __forceinline__ void bin_pair_safe(double v, uint32_t row_addr_adj, uint32_t dump_addr, float inv_dr,
-                                              float c0h, float lim, unsigned int nbin_fbits, unsigned int &mask,
-                                              unsigned int bit) {
+// MODE_SAFE fast path.  qh = sqrtf(d2)*inv_dr + (c0 - 0.5) is the bin coordinate minus one half; adding
+// 1.5*2^23 rounds it to the nearest integer n (the guessed bin) in the low mantissa bits, and
+// |qh - n| < 0.5 - eps says the guess is more than eps bins away from both edges of bin n.
+//
+// The fast path is UNCONDITIONAL: every pair increments hist[row + n], whatever n is.  Rows of the
+// shared histogram carry guard bins -- `glo` below bin 0 (qh >= c0 - 0.5, so n >= -glo) and one above
+// (min.f32 clamps qh to nbin + 0.25, which also catches NaN ghosts and far pairs) -- so out-of-range
+// pairs land in words that are never merged.  No range compare, no address select, no predicated atomic
+// (ptxas turns those into branches).  What the fast path cannot decide is left to a group-level test:
+// the largest |qh - n| of the group (FMNMX3, half an instruction per pair) against lim.  If it fails --
+// about 3 pairs in 10^4 -- the group's pairs are re-examined and each pair within eps of an edge is
+// CORRECTED: its fast-path increment is taken back and the exact bin (bracket search in the threshold
+// table) is incremented instead.  Sums are integers modulo 2^32 and a CTA merges its rows only at
+// barriers, so the order of +1 / -1 does not matter.
+struct SafeGuess {
+    float dl;   // qh - n (signed)
+    int n;      // guessed bin, in [-glo, nbin]
+};
+__device__ __forceinline__ SafeGuess safe_guess(double v, float inv_dr, float c0h, float qmax) {
     float f;
     asm("cvt.rz.f32.f64 %0, %1;" : "=f"(f) : "d"(v));   // +inf for huge, NaN stays NaN; sqrt.ftz flushes denormals
     const float s = sqrt_approx(f);
-    // ptxas turns every predicated shared atomic into a branch around it (4 issue slots); an
-    // UNCONDITIONAL atomic whose address is switched to a per-lane dump word costs 2.
+    float q, r;
+    asm("{\n\t.reg .f32 t;\n\t"
+        "fma.rn.f32 t, %2, %3, %4;\n\t"
+        "min.f32 %0, t, %5;\n\t"                 // NaN -> qmax
+        "add.rn.f32 %1, %0, 0f4B400000;\n\t}"    // 1.5 * 2^23: r = 1.5*2^23 + n, n = rint(q)
+        : "=f"(q), "=f"(r)
+        : "f"(s), "f"(inv_dr), "f"(c0h), "f"(qmax));
+    SafeGuess g;
+    g.dl = __fsub_rn(q, __fadd_rn(r, -12582912.0f));
+    g.n = __float_as_int(r) - 0x4B400000;
+    return g;
+}
+
+// one pair: returns qh - n; row_addr_adj = shared address of hist[row] - 4 * 0x4B400000
+__device__ __forceinline__ float bin_pair_safe(double v, uint32_t row_addr_adj, float inv_dr, float c0h, float qmax) {
+    float f;
+    asm("cvt.rz.f32.f64 %0, %1;" : "=f"(f) : "d"(v));
+    const float s = sqrt_approx(f);
+    float dl;
     asm volatile(
-        "{\n\t.reg .pred ps, pu;\n\t.reg .f32 q, r, n, dl;\n\t.reg .b32 ri, ni, ad;\n\t"
+        "{\n\t.reg .f32 q, r, n;\n\t.reg .b32 ri, ad;\n\t"
         "fma.rn.f32 q, %1, %2, %3;\n\t"
-        "min.f32 q, q, 0f4A800000;\n\t"          // 4194304.0; NaN -> 4194304.0
-        "add.rn.f32 r, q, 0f4B400000;\n\t"       // 1.5 * 2^23: r = 1.5*2^23 + n, n = rint(q)
+        "min.f32 q, q, %4;\n\t"
+        "add.rn.f32 r, q, 0f4B400000;\n\t"
         "add.rn.f32 n, r, 0fCB400000;\n\t"
-        "sub.rn.f32 dl, q, n;\n\t"
-        "abs.f32 dl, dl;\n\t"
-        "setp.lt.f32 ps|pu, dl, %4;\n\t"
-        "mov.b32 ni, n;\n\t"
-        "setp.lt.and.u32 ps, ni, %5, ps;\n\t"    // 0 <= n < nbin on the bit patterns (negative n: sign bit set)
+        "sub.rn.f32 %0, q, n;\n\t"
         "mov.b32 ri, r;\n\t"
-        "mad.lo.u32 ad, ri, 4, %6;\n\t"
-        "selp.b32 ad, ad, %8, ps;\n\t"
-        "red.shared.add.u32 [ad], 1;\n\t"
-        "@pu or.b32 %0, %0, %7;\n\t}"
-        : "+r"(mask)
-        : "f"(s), "f"(inv_dr), "f"(c0h), "f"(lim), "r"(nbin_fbits), "r"(row_addr_adj), "r"(bit), "r"(dump_addr)
+        "mad.lo.u32 ad, ri, 4, %5;\n\t"
+        "red.shared.add.u32 [ad], 1;\n\t}"
+        : "=f"(dl)
+        : "f"(s), "f"(inv_dr), "f"(c0h), "f"(qmax), "r"(row_addr_adj)
         : "memory");
+    return dl;
+}
+
+__device__ __forceinline__ float max3abs(float a, float b, float c) {
+    float d;
+    asm("{\n\t.reg .f32 x, y;\n\tabs.f32 x, %2;\n\tabs.f32 y, %3;\n\tmax.f32 %0, %1, x, y;\n\t}"
+        : "=f"(d)
+        : "f"(a), "f"(b), "f"(c));
+    return d;
+}
+
+// Rare path of MODE_SAFE: the pair's guess is within eps of a bin edge (or is NaN-like): take the
+// fast-path increment back and count the pair where the exact table says.
+__device__ __noinline__ void bin_pair_fix(double d2, const double2 *__restrict__ thr2, int nbin, float inv_dr, float c0,
+                                          float c0h, float qmax, float lim, unsigned int *hist_row) {
+    const SafeGuess sg = safe_guess(d2, inv_dr, c0h, qmax);
+    if (fabsf(sg.dl) < lim) return;   // this pair of the group was safe
+    int g = -1;
+    if ((d2 >= thr2[1].x) && (d2 < thr2[nbin].y)) {
+        g = static_cast<int>(bin_guess1(d2, inv_dr, c0, static_cast<unsigned int>(nbin) + 2u)) - 1;
+        g = min(max(g, 0), nbin - 1);
+        while (d2 < thr2[g + 1].x) --g;
+        while (d2 >= thr2[g + 1].y) ++g;
+    }
+    if (g == sg.n) return;
+    atomicAdd(hist_row + sg.n, 0xffffffffu);   // -1 modulo 2^32 (sg.n may be a guard bin)
+    if (g >= 0) atomicAdd(hist_row + g, 1u);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -303,7 +354,10 @@ struct SmemLayout {
 
 __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-__host__ __device__ inline SmemLayout smem_layout(int ntypes, int nbin, bool edges) {
+// every histogram row: glo guard bins, nbin bins, one guard bin
+__host__ __device__ inline int row_stride(int nbin, int glo) { return glo + nbin + 1; }
+
+__host__ __device__ inline SmemLayout smem_layout(int ntypes, int nbin, int glo, bool edges) {
     SmemLayout L;
     size_t o = 0;
     L.stage = o;
@@ -315,7 +369,7 @@ __host__ __device__ inline SmemLayout smem_layout(int ntypes, int nbin, bool edg
     L.bars = align_up(o, 8);
     o = L.bars + kStages * sizeof(uint64_t);
     L.hist = o;
-    o += static_cast<size_t>(ntypes) * (ntypes + 1) * nbin * sizeof(unsigned int);
+    o += static_cast<size_t>(ntypes) * (ntypes + 1) * row_stride(nbin, glo) * sizeof(unsigned int);
     L.dump = o;
     o += 32 * sizeof(unsigned int);
     L.rowtab = o;
@@ -328,14 +382,15 @@ __host__ __device__ inline SmemLayout smem_layout(int ntypes, int nbin, bool edg
     return L;
 }
 
-size_t pair_kernel_smem_bytes(int ntypes, int nbin, bool edges) { return smem_layout(ntypes, nbin, edges).total; }
+size_t pair_kernel_smem_bytes(int ntypes, int nbin, int glo, bool edges) {
+    return smem_layout(ntypes, nbin, glo, edges).total;
+}
 
 struct PairConst {
     BoxRegs box;
     double nLx, nLy, nLz;   // -(2*l_half), exact
     uint32_t thr2_addr;     // shared-window address of thr2[0]
     uint32_t hist_addr;     // shared-window address of hist[0]
-    uint32_t dump_addr;     // this lane's dump word (unconditional atomics of pairs that are not counted)
 };
 
 // One group = kIPT i atoms (registers) x kJU j atoms (shared memory): all d2 first (straight-line,
@@ -379,13 +434,12 @@ __device__ __forceinline__ void group_distances(const PairConst &c, const double
     }
 }
 
-// Safe-zone binning of one group: no branch except the rare exact search.
+// Safe-zone binning of one group: straight-line, one group-level test for the rare correction.
 template <bool DIAG>
 __device__ __forceinline__ void group_bin_safe(const PairParams &p, const PairConst &c, const double (&d2)[kIPT][kJU],
                                                const int (&ii)[kIPT], const unsigned int (&row)[kIPT], int j,
                                                const double2 *s_thr2, unsigned int *s_hist, unsigned int self_off) {
-    unsigned int mask = 0;
-    const unsigned int nbin_fbits = __float_as_uint(static_cast<float>(p.nbin));
+    float dl[kIPT * kJU];
 #pragma unroll
     for (int k = 0; k < kIPT; ++k) {
 #pragma unroll
@@ -393,17 +447,21 @@ __device__ __forceinline__ void group_bin_safe(const PairParams &p, const PairCo
             const unsigned int r = row[k] + ((DIAG && ii[k] == j + q) ? self_off : 0u);
             // byte address of hist[r + n] = hist_addr + 4*(r + bits(rounded) - 0x4B400000)
             const uint32_t adj = c.hist_addr + 4u * r - 4u * 0x4B400000u;
-            bin_pair_safe(d2[k][q], adj, c.dump_addr, p.inv_dr, p.c0h, p.lim, nbin_fbits, mask, 1u << (k * kJU + q));
+            dl[k * kJU + q] = bin_pair_safe(d2[k][q], adj, p.inv_dr, p.c0h, p.qmax);
         }
     }
-    if (mask) {
+    float m = 0.0f;
+#pragma unroll
+    for (int t = 0; t + 1 < kIPT * kJU; t += 2) m = max3abs(m, dl[t], dl[t + 1]);
+    if (kIPT * kJU % 2) m = fmaxf(m, fabsf(dl[kIPT * kJU - 1]));
+    if (!(m < p.lim)) {
 #pragma unroll
         for (int k = 0; k < kIPT; ++k) {
 #pragma unroll
-            for (int q = 0; q < kJU; ++q) {
-                if (mask & (1u << (k * kJU + q))) {
+            for (int q = 0; q < kJU; ++q) {   // fully unrolled: the distances stay in registers
+                if (!(fabsf(dl[k * kJU + q]) < p.lim)) {
                     const unsigned int r = row[k] + ((DIAG && ii[k] == j + q) ? self_off : 0u);
-                    bin_pair_slow<false>(d2[k][q], s_thr2, p.nbin, p.inv_dr, p.c0, s_hist, r);
+                    bin_pair_fix(d2[k][q], s_thr2, p.nbin, p.inv_dr, p.c0, p.c0h, p.qmax, p.lim, s_hist + r);
                 }
             }
         }
@@ -502,7 +560,7 @@ template <bool TRI, bool FAST, int MODE, bool UBOX>
 __global__ void __launch_bounds__(kThreads, kMinBlocks) pair_kernel(const PairParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
     constexpr bool EDGES = MODE == MODE_EDGES;
-    const SmemLayout L = smem_layout(p.ntypes, p.nbin, EDGES);
+    const SmemLayout L = smem_layout(p.ntypes, p.nbin, p.glo, EDGES);
     double *s_stage = reinterpret_cast<double *>(smem + L.stage);
     double2 *s_thr2 = reinterpret_cast<double2 *>(smem + L.thr2);
     double *s_thrf = reinterpret_cast<double *>(smem + L.thr_full);
@@ -516,10 +574,11 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) pair_kernel(const PairPa
     const int lane = tid & 31, warp = tid >> 5;
     const int nt = p.ntypes, nbin = p.nbin;
     const int P = nt * (nt + 1) / 2;
-    const int hlen = 2 * P * nbin;
-    const unsigned int self_off = static_cast<unsigned int>(P * nbin);
+    const int hlen = 2 * P * nbin;                 // words of one lag in the global histogram
+    const int rstride = row_stride(nbin, p.glo);   // words of one row in shared memory (with its guard bins)
+    const unsigned int self_off = static_cast<unsigned int>(P * rstride);
 
-    for (int k = tid; k < hlen; k += kThreads) s_hist[k] = 0u;
+    for (int k = tid; k < 2 * P * rstride; k += kThreads) s_hist[k] = 0u;
     for (int k = tid; k < nbin + 3; k += kThreads) {
         // slot k <-> bin g = k-1
         const int g = k - 1;
@@ -542,7 +601,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) pair_kernel(const PairPa
             a = b;
             b = c;
         }
-        s_rowtab[k] = static_cast<unsigned int>((P - (b + 1) * (b + 2) / 2 + a) * nbin);
+        s_rowtab[k] = static_cast<unsigned int>((P - (b + 1) * (b + 2) / 2 + a) * rstride + p.glo);
     }
     for (int k = tid; k <= nt; k += kThreads) s_tstart[k] = p.type_start[k];
     if (tid == 0) {
@@ -554,7 +613,6 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) pair_kernel(const PairPa
     PairConst c;
     c.thr2_addr = smem_u32(s_thr2);
     c.hist_addr = smem_u32(s_hist);
-    c.dump_addr = smem_u32(smem + L.dump) + 4u * static_cast<uint32_t>(lane);
     const uint32_t stage_addr = smem_u32(s_stage);
 
     int cur_t = -1;
@@ -583,10 +641,11 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) pair_kernel(const PairPa
             if (cur_t >= 0) {
                 unsigned long long *g = p.ghist + static_cast<size_t>(cur_t) * hlen;
                 for (int k = tid; k < hlen; k += kThreads) {
-                    const unsigned int v = s_hist[k];
+                    unsigned int *w = s_hist + (k / nbin) * rstride + p.glo + (k % nbin);
+                    const unsigned int v = *w;
                     if (v) {
                         atomicAdd(g + k, static_cast<unsigned long long>(v));
-                        s_hist[k] = 0u;
+                        *w = 0u;
                     }
                 }
                 __syncthreads();
@@ -604,9 +663,13 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) pair_kernel(const PairPa
             c.box.xy = p.ubox[3];
             c.box.xz = p.ubox[4];
             c.box.yz = p.ubox[5];
-            c.nLx = p.ubox[6];
-            c.nLy = p.ubox[7];
-            c.nLz = p.ubox[8];
+            // the predicated DADDs of wrap_abs want -2*l_half in REGISTERS: as a constant-bank operand ptxas
+            // re-loads it (a predicated LDC.64) next to every wrap.  The xor with a run-time zero keeps it
+            // from folding the value back into the constant bank.
+            const int zero = p.npad >> 31;
+            c.nLx = __hiloint2double(__double2hiint(p.ubox[6]) ^ zero, __double2loint(p.ubox[6]));
+            c.nLy = __hiloint2double(__double2hiint(p.ubox[7]) ^ zero, __double2loint(p.ubox[7]));
+            c.nLz = __hiloint2double(__double2hiint(p.ubox[8]) ^ zero, __double2loint(p.ubox[8]));
         } else {
             const double *bx = p.box + static_cast<size_t>(job.fi) * 6;
             c.box.lhx = __ldg(bx + 0);
@@ -675,32 +738,6 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) pair_kernel(const PairPa
                 // [lo,hi) = before | overlap with this warp's own atoms | after   (all multiples of kPadGroup)
                 const int da = min(max(wi0, lo), hi);
                 const int db = min(max(wi0 + 32 * kIPT, lo), hi);
-                if (MODE == MODE_SAFE_DENSE) {
-                    // off-diagonal ranges: software-pipelined; the (at most 32*kIPT wide) diagonal range: plain
-                    auto run = [&](int a, int b) {
-                        if (a >= b) return;
-                        double cur[kIPT][kJU];
-                        group_distances<TRI, FAST>(c, xi, yi, zi, sx_addr, a - j0, cur, wrap_ok);
-#pragma unroll 1
-                        for (int j = a; j < b; j += kJU) {
-                            double nxt[kIPT][kJU];
-                            const int jn = min(j + kJU, b - kJU);  // last turn: recompute the last group, unused
-                            group_distances<TRI, FAST>(c, xi, yi, zi, sx_addr, jn - j0, nxt, wrap_ok);
-                            group_bin_safe<false>(p, c, cur, ii, row, j, s_thr2, s_hist, self_off);
-#pragma unroll
-                            for (int k = 0; k < kIPT; ++k)
-#pragma unroll
-                                for (int q = 0; q < kJU; ++q) cur[k][q] = nxt[k][q];
-                        }
-                    };
-                    run(lo, da);
-#pragma unroll 1
-                    for (int j = da; j < db; j += kJU)
-                        process_group<TRI, FAST, MODE, true>(p, c, xi, yi, zi, ii, row, sx_addr, j - j0, j, s_thr2,
-                                                             s_thrf, s_hist, self_off, edges, wrap_ok);
-                    run(db, hi);
-                    continue;
-                }
 #pragma unroll 1
                 for (int j = lo; j < da; j += kJU)
                     process_group<TRI, FAST, MODE, false>(p, c, xi, yi, zi, ii, row, sx_addr, j - j0, j, s_thr2, s_thrf,
@@ -722,7 +759,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) pair_kernel(const PairPa
     if (cur_t >= 0) {
         unsigned long long *g = p.ghist + static_cast<size_t>(cur_t) * hlen;
         for (int k = tid; k < hlen; k += kThreads) {
-            const unsigned int v = s_hist[k];
+            const unsigned int v = s_hist[(k / nbin) * rstride + p.glo + (k % nbin)];
             if (v) atomicAdd(g + k, static_cast<unsigned long long>(v));
         }
     }
@@ -773,31 +810,25 @@ cudaError_t prepare_pair_kernels(size_t max_smem) {
 // Device-side validation of MODE_SAFE's float guess (run once per plan): for every probe value the
 // guess must either be flagged "within eps of an edge" or equal the exact bin expected[k].
 __global__ void validate_safe_kernel(const double *__restrict__ probes, const int *__restrict__ expected, int n,
-                                     float inv_dr, float c0h, float lim, int nbin, unsigned int *bad) {
+                                     float inv_dr, float c0h, float lim, float qmax, int nbin, int glo,
+                                     unsigned int *bad) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
-    float f;
-    asm("cvt.rz.f32.f64 %0, %1;" : "=f"(f) : "d"(probes[k]));
-    const float s = sqrt_approx(f);
-    float q = fminf(fmaf(s, inv_dr, c0h), 4194304.0f);
-    const float r = __fadd_rn(q, 12582912.0f);
-    const float nn = __fadd_rn(r, -12582912.0f);
-    const float dl = fabsf(__fsub_rn(q, nn));
-    const bool safe = dl < lim;
-    const int g = __float_as_int(r) - 0x4B400000;
-    const int e = expected[k];  // exact bin, or -1 / nbin when outside
-    if (safe) {
-        const bool counted = __float_as_uint(nn) < __float_as_uint(static_cast<float>(nbin));
-        if (counted && (static_cast<unsigned int>(g) >= static_cast<unsigned int>(nbin))) atomicAdd(bad, 1u);
+    const SafeGuess sg = safe_guess(probes[k], inv_dr, c0h, qmax);
+    const int e = expected[k];  // exact bin, or -1 when the reference does not count the pair
+    if (sg.n < -glo || sg.n > nbin) atomicAdd(bad, 1u);   // would leave the row and its guard bins
+    if (fabsf(sg.dl) < lim) {
+        // an unflagged guess is final: it must be the exact bin, or a guard bin when the pair is not counted
+        const bool counted = sg.n >= 0 && sg.n < nbin;
         const bool should = e >= 0 && e < nbin;
-        if (counted != should || (counted && g != e)) atomicAdd(bad, 1u);
+        if (counted != should || (counted && sg.n != e)) atomicAdd(bad, 1u);
     }
 }
 
 cudaError_t launch_validate_safe(const double *probes, const int *expected, int n, float inv_dr, float c0h, float lim,
-                                 int nbin, unsigned int *bad, cudaStream_t stream) {
+                                 float qmax, int nbin, int glo, unsigned int *bad, cudaStream_t stream) {
     if (n <= 0) return cudaSuccess;
-    validate_safe_kernel<<<(n + 255) / 256, 256, 0, stream>>>(probes, expected, n, inv_dr, c0h, lim, nbin, bad);
+    validate_safe_kernel<<<(n + 255) / 256, 256, 0, stream>>>(probes, expected, n, inv_dr, c0h, lim, qmax, nbin, glo, bad);
     return cudaGetLastError();
 }
 

@@ -61,14 +61,15 @@ struct PairParams {
     int npad, ntypes, nbin;
     int n_itiles, n_jchunks, jchunk;  // jchunk is a multiple of kTileJ
     float inv_dr, c0;                 // bin guess = floor(sqrtf(d2) * inv_dr + c0)
-    float c0h, lim;                   // MODE_SAFE: c0 - 0.5 and 0.5 - eps
+    float c0h, lim, qmax;             // MODE_SAFE: c0 - 0.5, 0.5 - eps, nbin + 0.25 (clamp of the bin coordinate)
+    int glo;                          // guard bins below bin 0 in every shared-memory histogram row
     unsigned hlo, hspan, hhi;         // candidate tests on the high word of d2 (hhi = hlo + hspan)
 };
 
-size_t pair_kernel_smem_bytes(int ntypes, int nbin, bool edges);
+size_t pair_kernel_smem_bytes(int ntypes, int nbin, int glo, bool edges);
 
 // variant = TRI | FAST<<1 | MODE<<2 | UBOX<<5, MODE: 0 thresholds, 1 thresholds + warp aggregation, 2 edges, 3 safe-zone,
-// 4 safe-zone software-pipelined for dense in-range workloads
+// 4 safe-zone without the group filter (dense in-range workloads: nearly every group holds an in-range pair)
 enum { kModeThr = 0, kModeAgg = 1, kModeEdges = 2, kModeSafe = 3, kModeSafeDense = 4 };  // dense: FAST only (variants 18, 19)
 cudaError_t launch_pair_kernel(int variant, int grid, size_t smem, cudaStream_t stream, const PairParams &p);
 cudaError_t prepare_pair_kernels(size_t max_smem_optin);
@@ -97,7 +98,7 @@ cudaError_t launch_d2_pair(const double *pos_i, const double *pos_j, const doubl
                            int slot_j, int npad, double *out4, unsigned int *error_flag, cudaStream_t stream);
 // MODE_SAFE validation: bad += number of probes whose unflagged float guess differs from expected[]
 cudaError_t launch_validate_safe(const double *probes, const int *expected, int n, float inv_dr, float c0h, float lim,
-                                 int nbin, unsigned int *bad, cudaStream_t stream);
+                                 float qmax, int nbin, int glo, unsigned int *bad, cudaStream_t stream);
 // DFMA chains; *count_per_launch receives the number of lane-level DFMAs one launch executes
 cudaError_t launch_dfma_peak(double *sink, int blocks, int iters, cudaStream_t stream,
                              unsigned long long *count_per_launch);

@@ -137,7 +137,7 @@ enum {
     AGOFRT_OPT_NO_AGGREGATE = 4,   /* plain shared atomics instead of __match_any_sync merging   */
     AGOFRT_OPT_AGGREGATE = 8,      /* force warp-aggregated shared atomics                       */
     AGOFRT_OPT_NO_SAFE = 16,       /* bracket every guess against the exact thresholds (no safe-zone shortcut) */
-    AGOFRT_OPT_DENSE = 32,         /* force the software-pipelined kernel meant for dense in-range workloads   */
+    AGOFRT_OPT_DENSE = 32,         /* force the kernel without the group filter (dense in-range workloads)      */
     AGOFRT_OPT_SPARSE = 64,        /* force the group-filtered kernel meant for sparse in-range workloads      */
     AGOFRT_OPT_NO_UBOX = 128       /* never pass a constant box as kernel parameter (uniform operands)         */
 };

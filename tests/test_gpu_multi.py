@@ -1,0 +1,109 @@
+"""GPU, two or more devices: the multi-GPU path of agofrt_block -- work units sharded over the GPUs, ONE NCCL
+all-reduce (ncclUint64, sum) of the integer histograms -- must return the very same integers as one GPU.
+Skipped on a one-GPU box (the driver's -m gpu run); run with `gpurun --gpus 2`."""
+import json
+import os
+import subprocess
+import sys
+import textwrap
+
+import numpy as np
+import pytest
+
+import oracle
+from analisi_b200 import cabi, synth
+from conftest import GOLDEN, ROOT
+from test_multirank_gloo import torchrun
+
+pytestmark = pytest.mark.gpu
+
+needs2 = pytest.mark.skipif(cabi.device_count() < 2, reason="needs two GPUs")
+
+
+def case():
+    pos, box, types = synth.small_case(51, (10, 9, 8), 1.05, 2, True, 8)
+    bi = synth.lammps_rows_to_internal(box)
+    return np.ascontiguousarray(pos), bi, types
+
+
+def block(ctx, pos, bi, types, options=0):
+    tr = cabi.DeviceTrajectory(ctx, pos.shape[1], bi.shape[1], types, 2, pos.shape[0])
+    tr.upload(0, pos, bi)
+    plan = cabi.Plan(tr, 0.0, 3.1, 60)
+    c, st = plan.block(1, 5, 3, 2, 1, options=options)
+    plan.close()
+    tr.close()
+    return c, st
+
+
+@needs2
+def test_single_process_all_devices_equals_one_device():
+    """a context with several local devices is its own communicator (what the CLI uses on a multi-GPU box)"""
+    pos, bi, types = case()
+    one = cabi.Context([0])
+    one.pbc_wrap(pos, bi)
+    c1, st1 = block(one, pos, bi, types)
+    one.close()
+    allc = cabi.Context("all")
+    assert allc.ndev >= 2
+    cn, stn = block(allc, pos, bi, types)
+    allc.close()
+    assert np.array_equal(cn, c1)
+    assert stn["world"] == stn["ndev_local"] >= 2 and stn["pair_evals_total"] == st1["pair_evals_total"]
+    assert np.array_equal(c1, oracle.counts(pos, bi, types, 0.0, 3.1, 60, 3, 5, primo=1, skip=2, ntypes=2))
+
+
+WORKER = textwrap.dedent('''
+    import json, os
+    import numpy as np
+    import oracle
+    from analisi_b200 import cabi, dist, synth
+    ranks = dist.Ranks()
+    assert ranks.backend == "nccl"
+    ctx = cabi.Context([ranks.local_rank])
+    dist.join_communicator(ranks, ctx)
+    pos, box, types = synth.small_case(51, (10, 9, 8), 1.05, 2, True, 8)
+    bi = synth.lammps_rows_to_internal(box)
+    pos = np.ascontiguousarray(pos)
+    ctx.pbc_wrap(pos, bi)
+    tr = cabi.DeviceTrajectory(ctx, pos.shape[1], 9, types, 2, pos.shape[0])
+    tr.upload(0, pos, bi)
+    plan = cabi.Plan(tr, 0.0, 3.1, 60)
+    ok = True
+    for opt in (0, cabi.OPT_FORCE_GENERAL, cabi.OPT_NO_SAFE):
+        c, st, e = plan.block(1, 5, 3, 2, 1, options=opt, edges=True) if opt == 0 else plan.block(1, 5, 3, 2, 1, options=opt) + (None,)
+        ref, eref = oracle.counts(pos, bi, types, 0.0, 3.1, 60, 3, 5, primo=1, skip=2, ntypes=2, return_edges=True)
+        ok = ok and bool(np.array_equal(c, ref)) and st["world"] == ranks.world and (e is None or e == eref)
+        ok = ok and 0 < st["pair_evals"] < st["pair_evals_total"]
+    ranks.barrier()
+    print(json.dumps({"rank": ranks.rank, "ok": ok, "world": ranks.world}))
+    plan.close(); tr.close(); ctx.close(); ranks.close()
+''')
+
+
+@needs2
+def test_one_process_per_gpu_nccl(tmp_path):
+    """torchrun, one rank per GPU: unique id broadcast, agofrt_comm_join, every rank ends up with the whole
+    (all-reduced) histogram, equal to the oracle's -- also the edge-pair counter."""
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER)
+    r = torchrun(2, [str(script)])
+    assert r.returncode == 0, r.stderr[-3000:]
+    lines = [json.loads(l) for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 2 and all(l["ok"] and l["world"] == 2 for l in lines)
+
+
+@needs2
+def test_cli_on_all_gpus_matches_reference_golden(tmp_path):
+    """the CLI on every GPU of the box: same text as the reference's golden (counts are integers, the
+    block order of MediaVar does not depend on the GPU count)"""
+    from analisi_b200 import build as b
+    cli, _ = b.build_host()
+    path = os.path.join(ROOT, "tests", "_refdata", "lammps2020.bin")
+    if not os.path.exists(path):
+        pytest.skip("tests/_refdata/lammps2020.bin not present")
+    r = subprocess.run([cli, "-i", path, "-g", "100", "-F", "0.0", "4.0", "-S", "10", "-s", "8"], stdout=subprocess.PIPE,
+                       stderr=subprocess.PIPE, text=True, cwd=str(tmp_path), timeout=900)
+    assert r.returncode == 0, r.stderr[-2000:]
+    gold = open(os.path.join(GOLDEN, "cli_pair_corr_t.txt")).read()
+    assert r.stdout.rstrip("\n") == gold.rstrip("\n")
