@@ -150,6 +150,8 @@ struct agofrt_traj {
     bool has_inf = false;
     bool has_nan = false;   // NaN coordinates in the input (they are never in range, as in the reference)
     bool bad_box = false;
+    bool perm_valid = false;     // the permutation is kept over uploads and refreshed every kPermRefresh frames
+    size_t perm_frame = 0;       // first frame of the window it was built from
     std::vector<int> slot_of;    // atom -> device slot (built on demand by agofrt_traj_d2_pair)
     size_t slot_of_first = 0;
     bool slot_of_stale = true;
@@ -545,8 +547,18 @@ extern "C" int agofrt_traj_upload(agofrt_traj *t, size_t first_frame, size_t nfr
         for (int k = 3; k < 6; ++k)
             if (!std::isfinite(o[k])) t->bad_box = true;
     }
-    if (t->natoms > 0) build_perm(t, pos_aos, box_internal);
-    t->slot_of_stale = true;
+    // The spatial sort only serves locality (the group filter of the sparse kernels); atoms of a condensed
+    // phase move little over a few hundred frames, so the permutation of an earlier window is kept --
+    // at 1M atoms the host sort costs as much as a whole block on 8 GPUs.
+    constexpr size_t kPermRefresh = 256;
+    const size_t moved = first_frame > t->perm_frame ? first_frame - t->perm_frame : t->perm_frame - first_frame;
+    const bool new_perm = t->natoms > 0 && (!t->perm_valid || moved >= kPermRefresh);
+    if (new_perm) {
+        build_perm(t, pos_aos, box_internal);
+        t->perm_valid = true;
+        t->perm_frame = first_frame;
+        t->slot_of_stale = true;
+    }
 
     const size_t frame_elems = t->natoms * 3;
     for (size_t i = 0; i < t->dev.size(); ++i) {
@@ -554,7 +566,7 @@ extern "C" int agofrt_traj_upload(agofrt_traj *t, size_t first_frame, size_t nfr
         TrajDev &d = t->dev[i];
         CU(cudaSetDevice(dv.id));
         CU(cudaMemsetAsync(d.flags, 0, 4 * sizeof(unsigned int), dv.stream));
-        if (t->npad > 0)
+        if (t->npad > 0 && new_perm)
             CU(cudaMemcpyAsync(d.perm, t->perm.data(), t->npad * sizeof(int), cudaMemcpyHostToDevice, dv.stream));
         CU(cudaMemcpyAsync(d.box_stage, box_internal, nframes * t->stride * sizeof(double), cudaMemcpyHostToDevice,
                            dv.stream));

@@ -70,6 +70,110 @@ def block_spec(name, quick=False):
     raise SystemExit("workload %s is not a single-block bench workload" % name)
 
 
+def run_c5(args, rank, world):
+    """BASELINE.json configs[4]: 1M-atom 2-type melt, 200 frames, block-averaged with variance (MediaBlocchi,
+    8 blocks) -- the whole reference-facing chain in one process: LAMMPS binary file -> mmap Trajectory (window
+    reads, wrap on the GPU) -> BlockAverageG<Gofrt> -> mean and variance, on the first ``--gpus`` devices of
+    the box (work units of every block sharded over them, one NCCL all-reduce per block).  The host C++ classes
+    own the devices, so under torchrun rank 0 drives all N GPUs and the other ranks exit."""
+    if rank != 0:
+        return 0
+    import tempfile
+    w = synth.WORKLOADS["C5"]
+    if args.quick:
+        w = dataclasses.replace(w, cells=(40, 40, 40), name=w.name + " [quick: 64k atoms]")
+    os.environ["ANALISI_DEVICES"] = ",".join(str(i) for i in range(max(1, args.gpus)))
+    from analisi_b200 import build as b
+    _, ext = b.build_host()
+    sys.path.insert(0, os.path.dirname(ext))
+    import pyanalisi as pa
+    tmpdir = os.environ.get("AGOFRT_TMP", tempfile.gettempdir())
+    path = os.path.join(tmpdir, "agofrt_c5_%d_%d.bin" % (w.natoms, os.getpid()))
+    t0 = time.time()
+    nbytes = synth.write_workload_lammps(path, w)
+    log("[bench] wrote %s: %.2f GB in %.1f s" % (path, nbytes / 1e9, time.time() - t0))
+    try:
+        def one_pass():
+            tr = pa.Traj(path)
+            tr.setLoadVelocities(False)
+            tr.setWrapPbc(True)
+            ba = pa.GofrtBlockAverage_lammps(tr, w.nblocks)
+            t0 = time.time()
+            ba.calculate(w.rmin, w.rmax, w.nbin, w.tmax, 1, w.skip, w.every, False)
+            return ba, time.time() - t0
+        sampler = ClockSampler(0)
+        walls, devs, kers, st = [], [], [], None
+        mean0 = None
+        for k in range(args.warmup + args.steps):
+            if k == args.warmup:
+                sampler.start()
+                tt0 = time.time()
+            ba, wall = one_pass()
+            st = ba.stats()
+            log("[bench] pass %d: wall %.2f s, device %.2f s, kernels %.2f s, %d blocks on %d GPU(s)"
+                % (k, wall, st["device_ms"] / 1e3, st["kernel_ms"] / 1e3, st["blocks"], st["ndev"]))
+            if k >= args.warmup:
+                walls.append(wall)
+                devs.append(st["device_ms"] / 1e3)
+                kers.append(st["kernel_ms"] / 1e3)
+            mean, var = ba.mean(), ba.variance()
+            if mean0 is not None and not (np.array_equal(mean, mean0)):
+                raise SystemExit("non-deterministic block averages between passes")
+            mean0 = mean
+        clocks = sampler.stop(tt0, time.time())
+        # size-independent checks: every atom meets itself at distance 0 once per origin -> self row, bin 0 =
+        # atoms of the type, in every block (variance 0); nothing else in the self rows at lag 0
+        nt, P = w.ntypes, w.ntypes * (w.ntypes + 1) // 2
+        per_type = np.bincount(synth.lattice_types(w), minlength=nt)
+        for a in range(nt):
+            slot = P - (a + 1) * (a + 2) // 2 + a + P
+            assert mean[0, slot, 0] == per_type[a] and var[0, slot, 0] == 0.0, (a, mean[0, slot, 0])
+            assert mean[0, slot, 1:].sum() == 0.0
+        pairs = float(st["pair_evals"])
+        ops = 16
+        peak = None
+        try:
+            from analisi_b200 import cabi
+            c = cabi.Context([0])
+            peak = c.fp64_peak(1.0)
+            c.close()
+        except Exception as e:
+            log("[bench] fp64 peak not measured: %r" % (e,))
+        ngpu = int(st["ndev"])
+        value = pairs / float(np.mean(devs))
+        e2e = pairs / float(np.mean(walls))
+        kernel_rate = pairs / float(np.mean(kers)) / ngpu
+        s_blk = ba.block_size()
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": ngpu, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": float(np.mean(devs)) * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": w.name, "natoms": w.natoms, "frames": w.nframes, "ntypes": w.ntypes, "triclinic": False,
+                       "rmin": w.rmin, "rmax": w.rmax, "nbin": w.nbin, "lags": w.tmax, "skip": w.skip, "blocks": w.nblocks,
+                       "block_size": int(s_blk), "pair_evals_per_step": pairs,
+                       "parallelism": "one process, %d GPU(s): work units of each block sharded, 1 NCCL all-reduce/block; "
+                                      "MediaVar on the host in block order" % ngpu,
+                       "step": "file -> 8 block windows -> mean and variance (the analisi -g ... -B 8 chain)",
+                       "l2": "every block window (%.0f MB) is larger than L2" % ((s_blk + 1) * w.natoms * 24 / 1e6)},
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(w.nblocks * (s_blk + 1) * w.natoms * 24 * 2),
+                    "d2h_bytes_per_step": int(w.nblocks * ((s_blk + 1) * w.natoms * 24 + mean.size * 8)),
+                    "ms_per_step": float(np.mean(walls)) * 1e3,
+                    "includes": "mmap read + id scatter (host threads), wrap round trip, window upload, kernels, read-back, Welford"},
+            "gpu_launches": int(st["blocks"]) * ngpu, "clocks": clocks,
+            "roofline": {"bound": "fp64", "achieved": kernel_rate * ops / 1e12, "peak": peak / 1e12 if peak else None,
+                         "unit": "T FP64-op/s per GPU", "frac": kernel_rate * ops / peak if peak else None, "traffic": None,
+                         "ops_per_pair_eval": ops, "kernel_ms_per_step": float(np.mean(kers)) * 1e3,
+                         "pair_evals_per_s_per_gpu": kernel_rate},
+        }
+        print(json.dumps(line), flush=True)
+    finally:
+        try:
+            os.remove(path)
+        except OSError:
+            pass
+    return 0
+
+
 def jobs_of(nts, leff, skip, every):
     return ((leff + every - 1) // every) * ((nts + skip - 1) // skip)
 
@@ -189,7 +293,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--workload", default=None, help="C2 (default at N=1), C3, C4")
+    ap.add_argument("--workload", default=None, help="C2 (default), C3, C4 (one Gofrt block per step); C5 (block-averaged chain from a file)")
     ap.add_argument("--quick", action="store_true", help="tiny block (smoke/profiling), not a bench number")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--options", type=int, default=0)
@@ -200,6 +304,8 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     name = args.workload or "C2"
+    if name == "C5":
+        return run_c5(args, rank, world)
     w, nts, primo = block_spec(name, args.quick)
     leff = min(nts, w.tmax) if w.tmax else nts
     nframes = primo + (nts - 1) // w.skip * w.skip + (leff - 1) // w.every * w.every + 1
@@ -307,6 +413,18 @@ def main():
     kernel_rate = args.steps * pairs_per_step / (ker_ms * 1e-3) / world   # per GPU
     achieved = kernel_rate * ops
     in_range = float(counts.sum()) / float(pairs_per_step)
+    # DRAM bytes of one launch of this kernel from the committed ncu capture (per launch, like `achieved`);
+    # only for the exact workload that was captured, on one GPU
+    traffic, traffic_extra = None, {}
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        key = name if not args.quick else None
+        if key in tj and world == 1:
+            traffic = tj[key]["dram_bytes_read"] + tj[key]["dram_bytes_write"]
+            traffic_extra = {"traffic_unit": "DRAM bytes per launch (ncu)", "traffic_source": tj[key]["source"],
+                             "algorithmic_bytes_per_launch": int(njobs) * 2 * int(w.natoms) * 24}
+    except Exception:
+        traffic = None
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -317,10 +435,11 @@ def main():
         "clocks": clocks,
         "roofline": {
             "bound": "fp64", "achieved": achieved / 1e12, "peak": peak / 1e12, "unit": "T FP64-op/s per GPU",
-            "frac": achieved / peak, "traffic": None,
+            "frac": achieved / peak, "traffic": traffic,
             "ops_per_pair_eval": ops, "kernel_ms_per_step": ker_ms / args.steps,
             "pair_evals_per_s_per_gpu": kernel_rate, "in_range_fraction": in_range,
             "peak_source": "DFMA-chain microbenchmark in this run (agofrt_fp64_peak); MEASURED_PEAKS.json has no FP64 entry",
+            **traffic_extra,
         },
         "wall_ms_per_step": wall_ms / args.steps,
     }

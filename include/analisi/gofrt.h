@@ -134,6 +134,10 @@ public:
                                                static_cast<unsigned>(skip), static_cast<unsigned>(every), AGOFRT_OPT_DEFAULT,
                                                counts_buf.data(), nullptr, &stats),
                                   "agofrt_block");
+            sum_kernel_ms += stats.kernel_ms;
+            sum_total_ms += stats.total_ms;
+            sum_pair_evals += stats.pair_evals_total;
+            ++ncalls;
             // the reference adds incr once per counted pair; count*incr is that sum with one rounding
             for (unsigned int k = 0; k < data_length; ++k) vdata[k] = static_cast<TFLOAT>(counts_buf[k]) * incr;
         }
@@ -144,6 +148,11 @@ public:
     const std::vector<uint64_t> &counts() const { return counts_buf; }
     const agofrt_stats &last_stats() const { return stats; }
     TFLOAT get_incr() const { return incr; }
+    // ... and the sums over every calculate() of this object (BlockAverageG runs all blocks on one object)
+    double total_kernel_ms() const { return sum_kernel_ms; }
+    double total_device_ms() const { return sum_total_ms; }
+    uint64_t total_pair_evals() const { return sum_pair_evals; }
+    unsigned int total_calls() const { return ncalls; }
 
 private:
     using VectorOp_T::data_length;
@@ -189,6 +198,9 @@ private:
     uint64_t plan_generation = 0;
     std::vector<uint64_t> counts_buf;
     agofrt_stats stats{};
+    double sum_kernel_ms = 0, sum_total_ms = 0;
+    uint64_t sum_pair_evals = 0;
+    unsigned int ncalls = 0;
 };
 
 #endif

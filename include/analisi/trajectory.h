@@ -9,7 +9,10 @@
 //   * the wrap of freshly read frames runs on the GPU (BaseTrajectory::pbc_wrap_frames);
 //   * velocities and per-type centres of mass are only read when asked for
 //     (set_load_velocities; g(r,t) never touches them -- at 1M atoms they would double the I/O);
-//   * one stderr summary line per type instead of one line per atom.
+//   * one stderr summary line per type instead of one line per atom;
+//   * the frames of a window are parsed and scattered by several host threads, ids resolved through a
+//     flat table when they are compact (the reference does one std::map::at per atom and frame,
+//     lib/src/trajectory.cpp:633, single-threaded).
 #ifndef ANALISI_B200_TRAJECTORY_H
 #define ANALISI_B200_TRAJECTORY_H
 
@@ -104,6 +107,7 @@ private:
     bool load_velocities = true;
     std::unordered_map<int, int> id_to_slot;
     std::vector<int> slot_to_id;
+    std::vector<int> dense_slot;          // id -> slot when the ids are compact (else id_to_slot is used)
     std::vector<int> raw_type, type_id;
     analisi_device::PinnedBuffer pos_buf, vel_buf;
     std::vector<double> boxes, cm_pos, cm_vel;

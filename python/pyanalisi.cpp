@@ -17,6 +17,7 @@
 #include "pybind11/pybind11.h"
 #include "pybind11/stl.h"
 
+#include "analisi/blockaverage.h"
 #include "analisi/gofrt.h"
 #include "analisi/trajectory.h"
 #include "analisi/trajectory_numpy.h"
@@ -123,6 +124,40 @@ void define_gofrt(py::module &m, const std::string &suffix) {
         });
 }
 
+// Addition (the reference keeps BlockAverage on the C++ side, used by its CLI only): the block-averaged
+// g(r,t) -- mean and variance of the mean over n blocks (reference lib/include/blockaverage.h:83-221,
+// calcoliblocchi.h:21-65) -- for python callers and for bench.py's MediaBlocchi workload.
+template <class TR>
+void define_block_average(py::module &m, const std::string &suffix) {
+    using G = Gofrt<double, TR>;
+    using BA = BlockAverageG<TR, G, double, double, unsigned int, unsigned int, unsigned int, unsigned int, unsigned int, bool>;
+    auto as_array = [](G *g) {
+        return owned_copy<double>(g->access_vdata(), g->get_shape());
+    };
+    py::class_<BA>(m, ("GofrtBlockAverage" + suffix).c_str(), py::module_local())
+        .def(py::init<TR *, unsigned int>(), py::keep_alive<1, 2>(), "trajectory, number of blocks")
+        .def("calculate",
+             [](BA &b, double rmin, double rmax, unsigned int nbin, unsigned int tmax, unsigned int nthreads, unsigned int skip,
+                unsigned int every, bool debug) { b.calculate(rmin, rmax, nbin, tmax, nthreads, skip, every, debug); },
+             py::call_guard<py::gil_scoped_release>(),
+             "rmin, rmax, nbin, maximum time lag, number of threads (ignored), time skip, every time, debug flag: the arguments "
+             "of Gofrt; what `analisi -g nbin -F rmin rmax -S tmax -s skip -e every -B blocks` computes")
+        .def("mean", [as_array](BA &b) { return as_array(b.media()); })
+        .def("variance", [as_array](BA &b) { return as_array(b.varianza()); })
+        .def("block_size", &BA::block_size)
+        .def("get_columns_description", [](BA &b) { return b.puntatoreCalcolo()->get_columns_description(); })
+        .def("stats", [](BA &b) {
+            G *g = b.puntatoreCalcolo();
+            py::dict d;
+            d["blocks"] = g->total_calls();
+            d["kernel_ms"] = g->total_kernel_ms();
+            d["device_ms"] = g->total_device_ms();
+            d["pair_evals"] = g->total_pair_evals();
+            d["ndev"] = g->last_stats().ndev_local;
+            return d;
+        });
+}
+
 }  // namespace
 
 PYBIND11_MODULE(pyanalisi, m) {
@@ -178,6 +213,8 @@ PYBIND11_MODULE(pyanalisi, m) {
 
     define_gofrt<Trajectory>(m, "_lammps");
     define_gofrt<Trajectory_numpy>(m, "");
+    define_block_average<Trajectory>(m, "_lammps");
+    define_block_average<Trajectory_numpy>(m, "");
 
     m.def("info", []() -> std::string { return std::string("analisi g(r,t), B200-native: ") + agofrt_version(); });
     m.def("has_mmap", []() -> bool { return true; });

@@ -6,9 +6,11 @@
 #include <sys/stat.h>
 #include <unistd.h>
 
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <cstring>
+#include <thread>
 
 // Size in bytes of the frame that starts at `offset`; fills the header and, when asked, the chunk
 // table (reference lib/src/trajectory.cpp:260-317).
@@ -84,6 +86,15 @@ Trajectory::Trajectory(std::string filename) {
             auto ins = id_to_slot.emplace(id, static_cast<int>(slot_to_id.size()));
             if (ins.second) slot_to_id.push_back(id);
             raw_type[ins.first->second] = static_cast<int>(std::round(rec[1]));
+        }
+    }
+    // compact ids (the usual case): a flat table instead of a hash lookup per atom and frame
+    {
+        int max_id = 0;
+        for (int id : slot_to_id) max_id = std::max(max_id, id);
+        if (static_cast<size_t>(max_id) < static_cast<size_t>(natoms) * 8 + 1024) {
+            dense_slot.assign(static_cast<size_t>(max_id) + 1, -1);
+            for (size_t k = 0; k < slot_to_id.size(); ++k) dense_slot[slot_to_id[k]] = static_cast<int>(k);
         }
     }
     get_ntypes();
@@ -163,15 +174,12 @@ void Trajectory::index_all() {
 // one frame of the file -> window slot: box row (internal format), per-atom scatter by id
 // (reference :593-662)
 void Trajectory::read_frame_into_slot(size_t frame, size_t slot) {
-    ensure_indexed(frame);
+    // the caller has indexed the file up to `frame` (ensure_indexed): this function only reads, so
+    // several frames can be read by several threads at once
     LammpsFrameHeader h;
     std::vector<LammpsChunk> chunks;
-    const size_t sz = frame_bytes(offsets[frame], h, &chunks);
+    frame_bytes(offsets[frame], h, &chunks);
     lammps_steps[frame] = h.timestep;
-    if (frame + 1 < offsets.size() && indexed_upto <= frame) {
-        offsets[frame + 1] = offsets[frame] + sz;
-        indexed_upto = frame + 1;
-    }
     if ((h.triclinic != 0) != triclinic) throw std::runtime_error("Error: the cell kind (triclinic flag) changes along the trajectory\n");
     double *b = buffer_boxes + slot * buffer_boxes_stride;
     std::memcpy(b, h.box, 6 * sizeof(double));
@@ -194,9 +202,15 @@ void Trajectory::read_frame_into_slot(size_t frame, size_t slot) {
             double rec[kLammpsDoublesPerAtom];
             std::memcpy(rec, p, sizeof(rec));
             const int id = static_cast<int>(std::round(rec[0]));
-            auto it = id_to_slot.find(id);
-            if (it == id_to_slot.end()) throw std::out_of_range("atom id that was not in the first frame");
-            const size_t s = static_cast<size_t>(it->second);
+            int found = -1;
+            if (!dense_slot.empty()) {
+                if (id >= 0 && static_cast<size_t>(id) < dense_slot.size()) found = dense_slot[id];
+            } else {
+                auto it = id_to_slot.find(id);
+                if (it != id_to_slot.end()) found = it->second;
+            }
+            if (found < 0) throw std::out_of_range("atom id that was not in the first frame");
+            const size_t s = static_cast<size_t>(found);
             P[3 * s] = rec[2];
             P[3 * s + 1] = rec[3];
             P[3 * s + 2] = rec[4];
@@ -261,7 +275,32 @@ Trajectory::Errori Trajectory::set_access_at(const size_t &timestep) {
     ensure_indexed(timestep);
     // tell the kernel what we are done with and what comes next (reference :497-528)
     madvise(file, offsets[timestep] & ~static_cast<size_t>(sysconf(_SC_PAGESIZE) - 1), MADV_DONTNEED);
-    for (size_t f = read_begin; f < read_end; ++f) read_frame_into_slot(f, f - timestep);
+    if (read_end > read_begin) {
+        ensure_indexed(read_end - 1);
+        // Frames are independent (each fills its own slot of the window).  The per-type centres of mass are
+        // running means in file order inside ONE frame, so they do not constrain the split either.
+        const size_t nfr = read_end - read_begin;
+        size_t nth = std::min<size_t>({nfr, std::max(1u, std::thread::hardware_concurrency()), 32});
+        if (static_cast<size_t>(natoms) * nfr < 200000) nth = 1;
+        if (nth <= 1) {
+            for (size_t f = read_begin; f < read_end; ++f) read_frame_into_slot(f, f - timestep);
+        } else {
+            std::vector<std::thread> pool;
+            std::vector<std::exception_ptr> errors(nth);
+            std::atomic<size_t> next{read_begin};
+            for (size_t t = 0; t < nth; ++t)
+                pool.emplace_back([&, t]() {
+                    try {
+                        for (size_t f = next.fetch_add(1); f < read_end; f = next.fetch_add(1)) read_frame_into_slot(f, f - timestep);
+                    } catch (...) {
+                        errors[t] = std::current_exception();
+                    }
+                });
+            for (std::thread &th : pool) th.join();
+            for (const std::exception_ptr &e : errors)
+                if (e) std::rethrow_exception(e);   // first failure, on the caller's thread (as the reference does)
+        }
+    }
     if (wrap_pbc && read_end > read_begin) pbc_wrap_frames(static_cast<ssize_t>(read_begin - timestep), read_end - read_begin);
     current_timestep = static_cast<ssize_t>(timestep);
     window_loaded = true;
