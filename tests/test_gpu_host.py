@@ -231,3 +231,56 @@ def test_cli_c1_bundled_trajectory(host, tmp_path):
     mean, var = oracle.mediavar(np.array(blocks))
     want = _cli_text(mean, var, s, 1, nbin, 6)
     assert got == want
+
+
+@pytest.mark.parametrize("kind", ["numpy", "lammps"])
+def test_block_average_binding_vs_oracle(host, tmp_path, kind):
+    """GofrtBlockAverage (BlockAverageG<TR, Gofrt> from python; TraiettoriaF<Trajectory_numpy> is this
+    repository's addition): mean and variance of the mean over blocks, bit-identical to the oracle's MediaVar
+    over count*incr blocks (power-of-two incr: the blocks themselves are exact)."""
+    _, pa = host
+    nfr, n_b, lmax, skip, nbin = 41, 4, 3, 2, 24
+    pos, box, types = synth.small_case(33, (5, 4, 4), 1.08, 2, True, nfr)
+    bi = synth.lammps_rows_to_internal(box)
+    if kind == "numpy":
+        tr = pa.Trajectory(pos, np.zeros_like(pos), types.astype(np.int32), box, pa.BoxFormat.LammpsTriclinic, True, False)
+        ba = pa.GofrtBlockAverage(tr, n_b)
+    else:
+        path = str(tmp_path / "b.bin")
+        synth.write_lammps_binary(path, pos, box, types + 1, format2020=True, nchunk=3, shuffle_seed=5)
+        tr = pa.Traj(path)
+        tr.setLoadVelocities(False)
+        tr.setWrapPbc(True)
+        ba = pa.GofrtBlockAverage_lammps(tr, n_b)
+    ba.calculate(0.0, 2.4, nbin, lmax, 1, skip, 1, False)
+    nextra = oracle.nextra(nfr, n_b, lmax)
+    s = (nfr - nextra) // n_b
+    assert ba.block_size() == s == 9 and nextra == 3
+    wrapped = oracle.pbc_wrap(pos, bi)
+    blocks = []
+    for ib in range(n_b):
+        c = oracle.counts(wrapped, bi, types, 0.0, 2.4, nbin, lmax, s, primo=ib * s, skip=skip, ntypes=2)
+        blocks.append(c * cabi.gofrt_incr(s, skip))   # incr = 1/4
+    mean, var = oracle.mediavar(np.array(blocks))
+    assert np.array_equal(ba.mean(), mean)
+    assert np.array_equal(ba.variance(), var)
+    st = ba.stats()
+    assert st["blocks"] == n_b and st["pair_evals"] == n_b * lmax * 5 * len(types) ** 2
+
+
+def test_python_helpers_compute_gofr(host):
+    """compute_gofr over pyanalisi.Trajectory: segments, histogram vs normalised output"""
+    _, pa = host
+    from analisi_b200 import analysis
+    pos, box, types = synth.small_case(61, (4, 4, 4), 1.1, 1, False, 24)
+    tr = pa.Trajectory(pos, np.zeros_like(pos), types.astype(np.int32), box, pa.BoxFormat.LammpsOrtho, True, False)
+    h = analysis.compute_gofr(tr, 0.0, 2.0, 20, start=0, stop=24, tmax=4, tskip=4, return_histogram=True)
+    bi = synth.lammps_rows_to_internal(box)
+    ref = oracle.counts(oracle.pbc_wrap(pos, bi), bi, types, 0.0, 2.0, 20, 4, 20, primo=0, skip=4, ntypes=1)
+    assert np.array_equal(h, ref * cabi.gofrt_incr(20, 4))
+    g = analysis.compute_gofr(tr, 0.0, 2.0, 20, start=0, stop=24, tmax=4, tskip=4)
+    assert np.allclose(g, analysis.hist2gofr(20, 0.1, 0.0, h))
+    segs = analysis.compute_gofr(tr, 0.0, 2.0, 20, start=0, stop=24, tmax=4, tskip=2, n_segments=2, return_histogram=True)
+    assert len(segs) == 2
+    ref1 = oracle.counts(oracle.pbc_wrap(pos, bi), bi, types, 0.0, 2.0, 20, 4, 10, primo=10, skip=2, ntypes=1)
+    assert np.array_equal(segs[1], ref1 * cabi.gofrt_incr(10, 2))

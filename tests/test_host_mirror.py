@@ -202,3 +202,17 @@ def test_cli_option_handling(host, tmp_path):
     assert r.returncode == 1 and "Allowed options" in r.stdout
     r = run_cli(cli, ["-i", path])
     assert r.returncode == 1 and "Nothing to do" in r.stderr
+
+
+def test_python_helpers_host_arithmetic():
+    """max_l / hist2gofr of the reference's python wrappers (pyanalisi/analysis.py:77-105)"""
+    from analisi_b200 import analysis
+    assert analysis.max_l(0, 100, 0) == (50, 50)
+    assert analysis.max_l(10, 100, 20) == (20, 70)
+    assert analysis.max_l(0, 5, 9) == (4, 1)
+    with pytest.raises(RuntimeError):
+        analysis.max_l(5, 5, 1)
+    h = np.ones((1, 2, 4))
+    g = analysis.hist2gofr(4, 0.5, 1.0, h)
+    r = 1.0 + 0.5 * np.arange(5)
+    assert np.allclose(g[0, 0], 1.0 / (4 * np.pi / 3 * (r[1:] ** 3 - r[:-1] ** 3)))
