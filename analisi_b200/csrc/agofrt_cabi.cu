@@ -7,6 +7,7 @@
 #include "agofrt_kernels.cuh"
 
 #include <dlfcn.h>
+#include <unistd.h>
 #include <nccl.h>
 
 #include <algorithm>
@@ -323,12 +324,31 @@ static int comm_init(agofrt_ctx *ctx, const ncclUniqueId &u, int first_rank, int
     if (!api.ok) return fail(AGOFRT_ERR_NCCL, "libnccl.so.2 could not be loaded");
     const int nloc = static_cast<int>(ctx->devs.size());
     if (first_rank < 0 || first_rank + nloc > world) return fail(AGOFRT_ERR_ARG, "rank range outside world");
-    NC(api.GroupStart());
-    for (int i = 0; i < nloc; ++i) {
-        CU(cudaSetDevice(ctx->devs[i].id));
-        NC(api.CommInitRank(&ctx->devs[i].comm, world, u, first_rank + i));
+    // NCCL prints its version banner on stdout at NCCL_DEBUG=VERSION/WARN (NCCL_DEBUG_FILE is only honoured
+    // above that level).  stdout is the caller's data channel (the CLI prints g(r,t) there): point fd 1 at
+    // stderr while the communicator is created.
+    fflush(stdout);
+    const int saved_stdout = dup(1);
+    if (saved_stdout >= 0) dup2(2, 1);
+    auto restore = [&]() {
+        if (saved_stdout >= 0) {
+            fflush(stdout);
+            dup2(saved_stdout, 1);
+            close(saved_stdout);
+        }
+    };
+    ncclResult_t nr = api.GroupStart();
+    for (int i = 0; i < nloc && nr == ncclSuccess; ++i) {
+        if (cudaSetDevice(ctx->devs[i].id) != cudaSuccess) {
+            nr = ncclUnhandledCudaError;
+            break;
+        }
+        nr = api.CommInitRank(&ctx->devs[i].comm, world, u, first_rank + i);
     }
-    NC(api.GroupEnd());
+    const ncclResult_t ne = api.GroupEnd();
+    restore();
+    if (nr == ncclSuccess) nr = ne;
+    if (nr != ncclSuccess) return fail(AGOFRT_ERR_NCCL, "NCCL communicator creation failed: %s", api.GetErrorString(nr));
     ctx->first_rank = first_rank;
     ctx->world = world;
     ctx->comm_ready = true;
@@ -1334,19 +1354,20 @@ extern "C" int agofrt_fp64_peak(agofrt_ctx *ctx, int local_device, double second
     if (!(seconds > 0)) seconds = 0.5;
     const double per_launch_ms = std::max(ms, 1e-3f);
     int nlaunch = static_cast<int>(std::min(200.0, std::max(3.0, seconds * 1e3 / per_launch_ms)));
-    double best = 0, total_ms = 0;
-    unsigned long long total = 0;
+    // Sustained rate: the median launch of the run's last three quarters.  The first quarter is warm-up -- a GPU
+    // that idled while the host generated a trajectory needs a few hundred milliseconds to reach its clocks,
+    // and an average over that ramp under-reports the peak (and flatters every roofline fraction).
+    std::vector<double> rates;
+    rates.reserve(nlaunch);
     for (int k = 0; k < nlaunch; ++k) {
         CU(cudaEventRecord(dv.ev_k0, dv.stream));
         CU(launch_dfma_peak(dv.peak_sink, blocks, iters, dv.stream, &count));
         CU(cudaEventRecord(dv.ev_k1, dv.stream));
         CU(cudaStreamSynchronize(dv.stream));
         CU(cudaEventElapsedTime(&ms, dv.ev_k0, dv.ev_k1));
-        total_ms += ms;
-        total += count;
-        best = std::max(best, count / (ms * 1e-3));
+        if (k >= nlaunch / 4) rates.push_back(count / (std::max(ms, 1e-6f) * 1e-3));
     }
-    (void)best;
-    *dfma_per_second = total / (total_ms * 1e-3);  // sustained over the whole run
+    std::sort(rates.begin(), rates.end());
+    *dfma_per_second = rates[rates.size() / 2];
     return AGOFRT_OK;
 }

@@ -52,6 +52,14 @@ public:
     void release();
     double *data() { return ptr_; }
     size_t size() const { return n_; }
+    void swap(PinnedBuffer &o) {
+        double *p = ptr_;
+        ptr_ = o.ptr_;
+        o.ptr_ = p;
+        size_t n = n_;
+        n_ = o.n_;
+        o.n_ = n;
+    }
 
 private:
     double *ptr_ = nullptr;

@@ -10,6 +10,8 @@
 //   * velocities and per-type centres of mass are only read when asked for
 //     (set_load_velocities; g(r,t) never touches them -- at 1M atoms they would double the I/O);
 //   * one stderr summary line per type instead of one line per atom;
+//   * callers that walk the file in equal steps find the next window read ahead by a background thread
+//     (ANALISI_PREFETCH=0 turns it off);
 //   * the frames of a window are parsed and scattered by several host threads, ids resolved through a
 //     flat table when they are compact (the reference does one std::map::at per atom and frame,
 //     lib/src/trajectory.cpp:633, single-threaded).
@@ -17,8 +19,10 @@
 #define ANALISI_B200_TRAJECTORY_H
 
 #include <cstdint>
+#include <exception>
 #include <sstream>
 #include <string>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
@@ -96,6 +100,10 @@ private:
     size_t frame_bytes(size_t offset, LammpsFrameHeader &head, std::vector<LammpsChunk> *chunks);
     void ensure_indexed(size_t upto);
     void read_frame_into_slot(size_t frame, size_t slot);
+    void read_frame_to(size_t frame, double *P, double *box_row, double *V, double *cm_p, double *cm_v);
+    void read_frames(size_t first, size_t last, size_t origin, double *P0, double *B0, bool own_window);
+    void start_prefetch(size_t target);
+    void cancel_prefetch();
 
     int fd = -1;
     char *file = nullptr;
@@ -112,6 +120,13 @@ private:
     analisi_device::PinnedBuffer pos_buf, vel_buf;
     std::vector<double> boxes, cm_pos, cm_vel;
     size_t window_capacity = 0;
+    // read-ahead of the next window (see trajectory.cpp: start_prefetch)
+    analisi_device::PinnedBuffer pos_alt;
+    std::vector<double> boxes_alt;
+    std::thread prefetch_thread;
+    std::exception_ptr prefetch_error;
+    size_t prefetch_target = 0;
+    bool prefetch_valid = false, prefetch_enabled = true;
 };
 
 #endif

@@ -9,6 +9,7 @@
 #include <atomic>
 #include <chrono>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <thread>
 
@@ -107,6 +108,7 @@ Trajectory::Trajectory(std::string filename) {
     }
     // estimate of the number of frames from the size of the first one (reference :114)
     n_timesteps = static_cast<ssize_t>(fsize / frame0);
+    if (const char *e = std::getenv("ANALISI_PREFETCH")) prefetch_enabled = std::atoi(e) != 0;
     offsets.assign(static_cast<size_t>(n_timesteps) + 1, 0);
     lammps_steps.assign(static_cast<size_t>(n_timesteps) + 1, 0);
     indexed_upto = 0;
@@ -114,6 +116,7 @@ Trajectory::Trajectory(std::string filename) {
 }
 
 Trajectory::~Trajectory() {
+    cancel_prefetch();
     if (file) munmap(file, fsize);
     if (fd != -1) close(fd);
     buffer_positions = buffer_velocity = buffer_boxes = nullptr;
@@ -125,6 +128,7 @@ Trajectory::Errori Trajectory::set_data_access_block_size(const size_t &n) {
         return non_inizializzato;
     }
     if (static_cast<size_t>(loaded_timesteps) == n && window_capacity == n) return Ok;
+    cancel_prefetch();
     window_loaded = false;
     pos_buf.resize(n * natoms * 3);
     buffer_positions = pos_buf.data();
@@ -174,6 +178,13 @@ void Trajectory::index_all() {
 // one frame of the file -> window slot: box row (internal format), per-atom scatter by id
 // (reference :593-662)
 void Trajectory::read_frame_into_slot(size_t frame, size_t slot) {
+    read_frame_to(frame, buffer_positions + slot * natoms * 3, buffer_boxes + slot * buffer_boxes_stride,
+                  buffer_velocity ? buffer_velocity + slot * natoms * 3 : nullptr,
+                  buffer_velocity ? cm_pos.data() + slot * ntypes * 3 : nullptr,
+                  buffer_velocity ? cm_vel.data() + slot * ntypes * 3 : nullptr);
+}
+
+void Trajectory::read_frame_to(size_t frame, double *P, double *b, double *V, double *cp, double *cv) {
     // the caller has indexed the file up to `frame` (ensure_indexed): this function only reads, so
     // several frames can be read by several threads at once
     LammpsFrameHeader h;
@@ -181,18 +192,12 @@ void Trajectory::read_frame_into_slot(size_t frame, size_t slot) {
     frame_bytes(offsets[frame], h, &chunks);
     lammps_steps[frame] = h.timestep;
     if ((h.triclinic != 0) != triclinic) throw std::runtime_error("Error: the cell kind (triclinic flag) changes along the trajectory\n");
-    double *b = buffer_boxes + slot * buffer_boxes_stride;
     std::memcpy(b, h.box, 6 * sizeof(double));
     if (triclinic) std::memcpy(b + 6, h.xy_xz_yz, 3 * sizeof(double));
     lammps_to_internal(b);
-    double *P = buffer_positions + slot * natoms * 3;
-    double *V = buffer_velocity ? buffer_velocity + slot * natoms * 3 : nullptr;
     std::vector<size_t> cnt;
-    double *cp = nullptr, *cv = nullptr;
     if (V) {
         cnt.assign(ntypes, 0);
-        cp = cm_pos.data() + slot * ntypes * 3;
-        cv = cm_vel.data() + slot * ntypes * 3;
         std::fill(cp, cp + ntypes * 3, 0.0);
         std::fill(cv, cv + ntypes * 3, 0.0);
     }
@@ -236,6 +241,74 @@ void Trajectory::read_frame_into_slot(size_t frame, size_t slot) {
     }
 }
 
+// Frames [first, last) of the file -> rows (frame - origin) of a window buffer, by several host threads.
+// Frames are independent (each fills its own row).  The per-type centres of mass are running means in
+// file order inside ONE frame, so they do not constrain the split either.
+void Trajectory::read_frames(size_t first, size_t last, size_t origin, double *P0, double *B0, bool own_window) {
+    const size_t nfr = last - first;
+    auto one = [&](size_t f) {
+        if (own_window)
+            read_frame_into_slot(f, f - origin);
+        else
+            read_frame_to(f, P0 + (f - origin) * natoms * 3, B0 + (f - origin) * buffer_boxes_stride, nullptr, nullptr, nullptr);
+    };
+    size_t nth = std::min<size_t>({nfr, std::max(1u, std::thread::hardware_concurrency()), 32});
+    if (static_cast<size_t>(natoms) * nfr < 200000) nth = 1;
+    if (nth <= 1) {
+        for (size_t f = first; f < last; ++f) one(f);
+        return;
+    }
+    std::vector<std::thread> pool;
+    std::vector<std::exception_ptr> errors(nth);
+    std::atomic<size_t> next{first};
+    for (size_t t = 0; t < nth; ++t)
+        pool.emplace_back([&, t]() {
+            try {
+                for (size_t f = next.fetch_add(1); f < last; f = next.fetch_add(1)) one(f);
+            } catch (...) {
+                errors[t] = std::current_exception();
+            }
+        });
+    for (std::thread &th : pool) th.join();
+    for (const std::exception_ptr &e : errors)
+        if (e) std::rethrow_exception(e);   // first failure, on the caller's thread (as the reference does)
+}
+
+// Read-ahead: callers that walk the file in equal steps (BlockAverageG: block after block) find the next
+// window already parsed into a second page-locked buffer, read by a background thread while the GPUs were
+// busy with the current block.  Only the host part runs ahead (parse + scatter); wrap and upload stay on the
+// caller's thread, as the C ABI wants one host thread per context.
+void Trajectory::cancel_prefetch() {
+    if (prefetch_thread.joinable()) prefetch_thread.join();
+    prefetch_valid = false;
+    prefetch_error = nullptr;
+}
+
+void Trajectory::start_prefetch(size_t target) {
+    if (!prefetch_enabled || load_velocities) return;
+    const size_t W = static_cast<size_t>(loaded_timesteps);
+    if (target + W > static_cast<size_t>(n_timesteps)) return;
+    try {
+        ensure_indexed(target + W - 1);
+        LammpsFrameHeader h;
+        frame_bytes(offsets[target + W - 1], h, nullptr);   // the last frame must be complete
+    } catch (const std::exception &) {
+        return;   // the estimate of the number of frames was too generous: nothing to read ahead
+    }
+    pos_alt.resize(W * natoms * 3);
+    boxes_alt.assign(W * buffer_boxes_stride, 0.0);
+    prefetch_target = target;
+    prefetch_valid = true;
+    prefetch_error = nullptr;
+    prefetch_thread = std::thread([this, target, W]() {
+        try {
+            read_frames(target, target + W, target, pos_alt.data(), boxes_alt.data(), false);
+        } catch (...) {
+            prefetch_error = std::current_exception();
+        }
+    });
+}
+
 Trajectory::Errori Trajectory::set_access_at(const size_t &timestep) {
     const auto t_begin = std::chrono::steady_clock::now();
     if (!file) {
@@ -245,6 +318,34 @@ Trajectory::Errori Trajectory::set_access_at(const size_t &timestep) {
     if (loaded_timesteps <= 0 || !buffer_positions) throw std::runtime_error("set_data_access_block_size must be called first\n");
     if (timestep == static_cast<size_t>(current_timestep) && window_loaded) return Ok;
     const size_t W = static_cast<size_t>(loaded_timesteps);
+    const bool had_window = window_loaded;
+    const size_t previous = static_cast<size_t>(current_timestep);
+    auto finish = [&](const char *how) {
+        current_timestep = static_cast<ssize_t>(timestep);
+        window_loaded = true;
+        mark_window_changed();
+        // equal steps forward: read the next window ahead
+        if (had_window && timestep > previous) start_prefetch(timestep + (timestep - previous));
+        const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_begin).count();
+        std::cerr << "Reading time: " << dt << "s" << how << ".\n";
+        return Ok;
+    };
+    if (prefetch_thread.joinable() || prefetch_valid) {
+        if (prefetch_thread.joinable()) prefetch_thread.join();
+        const bool hit = prefetch_valid && !prefetch_error && prefetch_target == timestep && !load_velocities &&
+                         pos_alt.size() == W * static_cast<size_t>(natoms) * 3;
+        prefetch_valid = false;
+        prefetch_error = nullptr;
+        if (hit) {
+            pos_buf.swap(pos_alt);
+            boxes.swap(boxes_alt);
+            buffer_positions = pos_buf.data();
+            buffer_boxes = boxes.data();
+            window_loaded = false;
+            if (wrap_pbc) pbc_wrap_frames(0, W);
+            return finish(" (read ahead)");
+        }
+    }
 
     // overlap with what is already in the window: move it instead of reading it again (reference :542-586)
     size_t read_begin = timestep, read_end = timestep + W;   // frames to read from the file
@@ -277,37 +378,10 @@ Trajectory::Errori Trajectory::set_access_at(const size_t &timestep) {
     madvise(file, offsets[timestep] & ~static_cast<size_t>(sysconf(_SC_PAGESIZE) - 1), MADV_DONTNEED);
     if (read_end > read_begin) {
         ensure_indexed(read_end - 1);
-        // Frames are independent (each fills its own slot of the window).  The per-type centres of mass are
-        // running means in file order inside ONE frame, so they do not constrain the split either.
-        const size_t nfr = read_end - read_begin;
-        size_t nth = std::min<size_t>({nfr, std::max(1u, std::thread::hardware_concurrency()), 32});
-        if (static_cast<size_t>(natoms) * nfr < 200000) nth = 1;
-        if (nth <= 1) {
-            for (size_t f = read_begin; f < read_end; ++f) read_frame_into_slot(f, f - timestep);
-        } else {
-            std::vector<std::thread> pool;
-            std::vector<std::exception_ptr> errors(nth);
-            std::atomic<size_t> next{read_begin};
-            for (size_t t = 0; t < nth; ++t)
-                pool.emplace_back([&, t]() {
-                    try {
-                        for (size_t f = next.fetch_add(1); f < read_end; f = next.fetch_add(1)) read_frame_into_slot(f, f - timestep);
-                    } catch (...) {
-                        errors[t] = std::current_exception();
-                    }
-                });
-            for (std::thread &th : pool) th.join();
-            for (const std::exception_ptr &e : errors)
-                if (e) std::rethrow_exception(e);   // first failure, on the caller's thread (as the reference does)
-        }
+        read_frames(read_begin, read_end, timestep, buffer_positions, buffer_boxes, true);
     }
     if (wrap_pbc && read_end > read_begin) pbc_wrap_frames(static_cast<ssize_t>(read_begin - timestep), read_end - read_begin);
-    current_timestep = static_cast<ssize_t>(timestep);
-    window_loaded = true;
-    mark_window_changed();
-    const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_begin).count();
-    std::cerr << "Reading time: " << dt << "s.\n";
-    return Ok;
+    return finish("");
 }
 
 int64_t Trajectory::get_timestep_lammps(size_t timestep) {

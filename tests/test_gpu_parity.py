@@ -237,3 +237,48 @@ def test_size_independent_properties_large(ctx):
     assert np.array_equal(c, c2)
     # lag 0 distinct counts are even: (i,j) and (j,i) fall in the same bin
     assert (c[0, 0] % 2 == 0).all()
+
+
+@pytest.mark.parametrize("rmin,rmax,nbin,expect_safe", [
+    (1.5, 2.5, 500, True),      # rmin/dr = 750 guard bins below bin 0 in every shared-memory row
+    (-0.3, 2.0, 40, True),      # negative rmin: the lowest guess is positive, two guard words
+    (2.0, 2.2, 1000, False),    # rmin/dr = 10000 > the guard budget: the plan falls back to the threshold kernel
+    (0.0, 2.6, 3, True),        # three fat bins: almost every pair far from an edge
+])
+def test_guarded_rows_and_fallback(ctx, rmin, rmax, nbin, expect_safe):
+    """The unconditional safe-zone binning writes into guard bins for everything outside the histogram; the
+    counts must not depend on how many guard bins a row has, nor on the kernel that was chosen."""
+    pos, box, types = synth.small_case(71, (7, 6, 6), 1.07, 2, True, 6)
+    bi = synth.lammps_rows_to_internal(box)
+    ctx.pbc_wrap(pos, bi)
+    ref, eref = oracle.counts(pos, bi, types, rmin, rmax, nbin, 3, 3, ntypes=2, return_edges=True)
+    c, st = gpu_counts(ctx, pos, bi, types, 2, rmin, rmax, nbin, 3, 3)
+    assert np.array_equal(c, ref)
+    safe_ran = bool(st["kernel_modes"] & ((1 << 3) | (1 << 4)))
+    assert safe_ran == expect_safe
+    c2, st2 = gpu_counts(ctx, pos, bi, types, 2, rmin, rmax, nbin, 3, 3, options=cabi.OPT_NO_SAFE)
+    assert np.array_equal(c2, ref) and not (st2["kernel_modes"] & ((1 << 3) | (1 << 4)))
+    c3, st3, e3 = gpu_counts(ctx, pos, bi, types, 2, rmin, rmax, nbin, 3, 3, edges=True)
+    assert np.array_equal(c3, ref) and e3 == eref
+    for opt in (cabi.OPT_DENSE, cabi.OPT_SPARSE):
+        c4, _ = gpu_counts(ctx, pos, bi, types, 2, rmin, rmax, nbin, 3, 3, options=opt)
+        assert np.array_equal(c4, ref)
+
+
+def test_ghost_slots_and_nan_atoms(ctx):
+    """Type groups are padded to 8 slots with NaN ghosts; NaN coordinates of real atoms are never in range
+    (as in the reference: every comparison with NaN is false).  Both go through the min.f32 clamp of the
+    safe-zone guess or the exact path, never into a counted bin."""
+    pos, box, types = synth.small_case(72, (5, 5, 3), 1.1, 3, False, 5)   # 75 atoms, 25 per type: 7 ghosts each
+    bi = synth.lammps_rows_to_internal(box)
+    ctx.pbc_wrap(pos, bi)
+    ref = oracle.counts(pos, bi, types, 0.0, 2.5, 50, 2, 3, ntypes=3)
+    c, st = gpu_counts(ctx, pos, bi, types, 3, 0.0, 2.5, 50, 2, 3)
+    assert np.array_equal(c, ref)
+    bad = pos.copy()
+    bad[1, 7] = np.nan
+    bad[2, 30, 1] = np.nan
+    refn = oracle.counts(bad, bi, types, 0.0, 2.5, 50, 2, 3, ntypes=3)
+    cn, stn = gpu_counts(ctx, bad, bi, types, 3, 0.0, 2.5, 50, 2, 3)
+    assert np.array_equal(cn, refn)
+    assert refn.sum() < ref.sum()

@@ -216,3 +216,24 @@ def test_python_helpers_host_arithmetic():
     g = analysis.hist2gofr(4, 0.5, 1.0, h)
     r = 1.0 + 0.5 * np.arange(5)
     assert np.allclose(g[0, 0], 1.0 / (4 * np.pi / 3 * (r[1:] ** 3 - r[:-1] ** 3)))
+
+
+def test_mmap_trajectory_read_ahead(host, tmp_path, capfd):
+    """walking the file in equal steps (what BlockAverageG does): from the third window on the frames come
+    from the background read-ahead; contents identical, also after a jump that misses the prediction"""
+    _, pa = host
+    pos, box, types = synth.small_case(8, (4, 3, 3), 1.1, 2, False, 17)
+    path = str(tmp_path / "p.bin")
+    synth.write_lammps_binary(path, pos, box, types, nchunk=2, shuffle_seed=4)
+    tr = pa.Traj(path)
+    tr.setLoadVelocities(False)
+    tr.setWrapPbc(False)
+    tr.setAccessWindowSize(4)
+    capfd.readouterr()
+    for start in (0, 3, 6, 9, 12, 2, 5, 8):
+        assert tr.setAccessStart(start) == 1
+        assert np.array_equal(tr.get_positions_copy(), pos[start:start + 4])
+        assert np.array_equal(tr.get_box_copy(), synth.lammps_rows_to_internal(box[start:start + 4]))
+    err = capfd.readouterr().err
+    assert err.count("(read ahead)") == 4   # 6, 9, 12 and 8; 15 would run past the end and is never started
+    assert tr.get_velocities_copy().size == 0
