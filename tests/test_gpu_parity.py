@@ -241,9 +241,11 @@ def test_size_independent_properties_large(ctx):
 
 @pytest.mark.parametrize("rmin,rmax,nbin,expect_safe", [
     (1.5, 2.5, 500, True),      # rmin/dr = 750 guard bins below bin 0 in every shared-memory row
-    (-0.3, 2.0, 40, True),      # negative rmin: the lowest guess is positive, two guard words
+    (-0.3, 2.0, 40, False),     # negative rmin: pairs below rmin^2 are skipped by the reference but have a bin >= 0;
+                                # the device validation of the plan sees it and gives the safe-zone mode up
     (2.0, 2.2, 1000, False),    # rmin/dr = 10000 > the guard budget: the plan falls back to the threshold kernel
-    (0.0, 2.6, 3, True),        # three fat bins: almost every pair far from an edge
+    (0.0, 2.6, 3, False),       # 9 counters in all: the warp-aggregated threshold kernel is chosen instead
+    (0.0, 2.6, 30, True),       # the plain case
 ])
 def test_guarded_rows_and_fallback(ctx, rmin, rmax, nbin, expect_safe):
     """The unconditional safe-zone binning writes into guard bins for everything outside the histogram; the
