@@ -22,7 +22,7 @@ namespace agofrt {
 #define AGOFRT_IPT 2
 #endif
 #ifndef AGOFRT_JU
-#define AGOFRT_JU 4
+#define AGOFRT_JU 8
 #endif
 #ifndef AGOFRT_MINBLOCKS
 #define AGOFRT_MINBLOCKS 2

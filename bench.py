@@ -422,7 +422,14 @@ def main():
         if key in tj and world == 1:
             traffic = tj[key]["dram_bytes_read"] + tj[key]["dram_bytes_write"]
             traffic_extra = {"traffic_unit": "DRAM bytes per launch (ncu)", "traffic_source": tj[key]["source"],
-                             "algorithmic_bytes_per_launch": int(njobs) * 2 * int(w.natoms) * 24}
+                             "algorithmic_bytes_per_launch": int(njobs) * 2 * int(w.natoms) * 24,
+                             "hbm_gbs": traffic / (ker_ms / args.steps * 1e-3) / 1e9}
+            try:
+                mp = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+                traffic_extra["hbm_peak_gbs"] = mp["hbm_gbs"]
+                traffic_extra["hbm_frac"] = traffic_extra["hbm_gbs"] / mp["hbm_gbs"]
+            except Exception:
+                pass
     except Exception:
         traffic = None
     line = {
