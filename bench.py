@@ -70,7 +70,7 @@ def block_spec(name, quick=False):
     raise SystemExit("workload %s is not a single-block bench workload" % name)
 
 
-def run_c5(args, rank, world):
+def run_c5(args, rank, world, name="C5"):
     """BASELINE.json configs[4]: 1M-atom 2-type melt, 200 frames, block-averaged with variance (MediaBlocchi,
     8 blocks) -- the whole reference-facing chain in one process: LAMMPS binary file -> mmap Trajectory (window
     reads, wrap on the GPU) -> BlockAverageG<Gofrt> -> mean and variance, on the first ``--gpus`` devices of
@@ -79,9 +79,20 @@ def run_c5(args, rank, world):
     if rank != 0:
         return 0
     import tempfile
-    w = synth.WORKLOADS["C5"]
-    if args.quick:
-        w = dataclasses.replace(w, cells=(40, 40, 40), name=w.name + " [quick: 64k atoms]")
+    bundled = None
+    if name == "C1":
+        # BASELINE.json configs[0]: analisi -i tests/data/lammps.bin -g 200 -F 0.7 3.5 (56 atoms, 2 types, 7958
+        # frames, -B 20 -S 0 -s 1: 20 blocks of 378 steps x 378 lags = 8.96e9 pair evaluations).  The file is the
+        # reference's own test trajectory, copied to tests/_refdata by build() where the reference tree exists.
+        bundled = os.path.join(ROOT, "tests", "_refdata", "lammps.bin")
+        if not os.path.exists(bundled):
+            raise SystemExit("tests/_refdata/lammps.bin is not here (built where /root/reference exists)")
+        w = synth.Workload("C1 analisi -i tests/data/lammps.bin -g 200 -F 0.7 3.5 (bundled 56-atom trajectory, 20 blocks)",
+                           0, (56, 1, 1), 1.0, 2, "blocks", False, 7958, 0.7, 3.5, 200, 0, 1, 1, 20)
+    else:
+        w = synth.WORKLOADS["C5"]
+        if args.quick:
+            w = dataclasses.replace(w, cells=(40, 40, 40), name=w.name + " [quick: 64k atoms]")
     os.environ["ANALISI_DEVICES"] = ",".join(str(i) for i in range(max(1, args.gpus)))
     from analisi_b200 import build as b
     _, ext = b.build_host()
@@ -90,8 +101,11 @@ def run_c5(args, rank, world):
     tmpdir = os.environ.get("AGOFRT_TMP", tempfile.gettempdir())
     path = os.path.join(tmpdir, "agofrt_c5_%d_%d.bin" % (w.natoms, os.getpid()))
     t0 = time.time()
-    nbytes = synth.write_workload_lammps(path, w)
-    log("[bench] wrote %s: %.2f GB in %.1f s" % (path, nbytes / 1e9, time.time() - t0))
+    if bundled:
+        path = bundled
+    else:
+        nbytes = synth.write_workload_lammps(path, w)
+        log("[bench] wrote %s: %.2f GB in %.1f s" % (path, nbytes / 1e9, time.time() - t0))
     try:
         def one_pass():
             tr = pa.Traj(path)
@@ -125,7 +139,7 @@ def run_c5(args, rank, world):
         # atoms of the type, in every block (variance 0); nothing else in the self rows at lag 0
         nt, P = w.ntypes, w.ntypes * (w.ntypes + 1) // 2
         per_type = np.bincount(synth.lattice_types(w), minlength=nt)
-        for a in range(nt):
+        for a in range(nt if not bundled else 0):   # (C1 starts at rmin = 0.7: no self pairs at lag 0)
             slot = P - (a + 1) * (a + 2) // 2 + a + P
             assert mean[0, slot, 0] == per_type[a] and var[0, slot, 0] == 0.0, (a, mean[0, slot, 0])
             assert mean[0, slot, 1:].sum() == 0.0
@@ -144,19 +158,21 @@ def run_c5(args, rank, world):
         e2e = pairs / float(np.mean(walls))
         kernel_rate = pairs / float(np.mean(kers)) / ngpu
         s_blk = ba.block_size()
+        a_ = w.nframes // (w.nblocks + 1) + 1
+        win = s_blk + (a_ if (a_ < w.tmax or w.tmax == 0) else w.tmax)   # frames of one block window (Gofrt::nExtraTimesteps)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": ngpu, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": float(np.mean(devs)) * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic",
+            "dtype": "f64", "data": "synthetic" if not bundled else "reference test trajectory",
             "config": {"workload": w.name, "natoms": w.natoms, "frames": w.nframes, "ntypes": w.ntypes, "triclinic": False,
                        "rmin": w.rmin, "rmax": w.rmax, "nbin": w.nbin, "lags": w.tmax, "skip": w.skip, "blocks": w.nblocks,
                        "block_size": int(s_blk), "pair_evals_per_step": pairs,
                        "parallelism": "one process, %d GPU(s): work units of each block sharded, 1 NCCL all-reduce/block; "
                                       "MediaVar on the host in block order" % ngpu,
-                       "step": "file -> 8 block windows -> mean and variance (the analisi -g ... -B 8 chain)",
-                       "l2": "every block window (%.0f MB) is larger than L2" % ((s_blk + 1) * w.natoms * 24 / 1e6)},
-            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(w.nblocks * (s_blk + 1) * w.natoms * 24 * 2),
-                    "d2h_bytes_per_step": int(w.nblocks * ((s_blk + 1) * w.natoms * 24 + mean.size * 8)),
+                       "step": "file -> %d block windows -> mean and variance (the analisi -g ... -B %d chain)" % (w.nblocks, w.nblocks),
+                       "l2": "block window: %.1f MB%s" % (win * w.natoms * 24 / 1e6, " (larger than L2)" if win * w.natoms * 24 > 126e6 else " (fits in L2; 56 atoms: the workload is launch- and tile-bound, not FP64-bound)")},
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(w.nblocks * win * w.natoms * 24 * 2),
+                    "d2h_bytes_per_step": int(w.nblocks * (win * w.natoms * 24 + mean.size * 8)),
                     "ms_per_step": float(np.mean(walls)) * 1e3,
                     "includes": "mmap read + id scatter (host threads), wrap round trip, window upload, kernels, read-back, Welford"},
             "gpu_launches": int(st["blocks"]) * ngpu, "clocks": clocks,
@@ -167,10 +183,11 @@ def run_c5(args, rank, world):
         }
         print(json.dumps(line), flush=True)
     finally:
-        try:
-            os.remove(path)
-        except OSError:
-            pass
+        if not bundled:
+            try:
+                os.remove(path)
+            except OSError:
+                pass
     return 0
 
 
@@ -304,8 +321,8 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     name = args.workload or "C2"
-    if name == "C5":
-        return run_c5(args, rank, world)
+    if name in ("C1", "C5"):
+        return run_c5(args, rank, world, name)
     w, nts, primo = block_spec(name, args.quick)
     leff = min(nts, w.tmax) if w.tmax else nts
     nframes = primo + (nts - 1) // w.skip * w.skip + (leff - 1) // w.every * w.every + 1
