@@ -284,3 +284,30 @@ def test_python_helpers_compute_gofr(host):
     assert len(segs) == 2
     ref1 = oracle.counts(oracle.pbc_wrap(pos, bi), bi, types, 0.0, 2.0, 20, 4, 10, primo=10, skip=2, ntypes=1)
     assert np.array_equal(segs[1], ref1 * cabi.gofrt_incr(10, 2))
+
+
+@pytest.mark.parametrize("nth,tmax", [(1, 1), (3, 1), (3, 4), (1, 4)])
+def test_reference_cpp_fixture_gofr(host, nth, tmax):
+    """reference tests/src/test_lammps2020.cpp:27-90 (GofrFixture<NTH,TMAX>): Gofrt<double,Trajectory>(traj, 0.9, 2.0,
+    20, TMAX, NTH, skip=70) on lammps2020.bin (4000 atoms, wrap OFF, window of 150 frames at 0); reset(75-primo);
+    calculate(primo) for primo = 0 and 13.  The reference's golden files for it hold `inf`, so
+    the oracle is the checker; the result must not depend on the thread-count argument."""
+    _, pa = host
+    path = os.path.join(REFDATA, "lammps2020.bin")
+    if not os.path.exists(path):
+        pytest.skip("tests/_refdata/lammps2020.bin not present")
+    tr = pa.Traj(path)
+    tr.setWrapPbc(False)
+    tr.setAccessWindowSize(150)
+    tr.setAccessStart(0)
+    g = pa.Gofrt_lammps(tr, 0.9, 2.0, 20, tmax, nth, 70, 1, False)
+    pos, box, ids = tr.get_positions_copy(), tr.get_box_copy(), tr.get_type_ids()
+    for primo in (0, 13):
+        g.reset(75 - primo)
+        g.calculate(primo)
+        ref = oracle.counts(pos, box, ids, 0.9, 2.0, 20, tmax, 75 - primo, primo=primo, skip=70, ntypes=2,
+                            total_frames=tr.getNtimesteps())
+        assert np.array(g).shape == (min(tmax, 75 - primo), 6, 20)
+        assert np.array_equal(g.counts(), ref)
+        assert np.array_equal(np.array(g), ref * cabi.gofrt_incr(75 - primo, 70))   # incr = 1
+        assert ref[:, :3].sum() > 0 and ref[:, 3:].sum() == 0   # rmin 0.9: no self pairs at these lags
