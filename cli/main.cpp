@@ -28,7 +28,7 @@ struct Options {
     unsigned int gofrt = 0;
     std::vector<double> factors;
     int stop_acf = 0, skip = 1, every = 1, blocknumber = 20, nthreads = 2;
-    bool dump = false, help = false;
+    bool dump = false, help = false, edges = false;
 };
 
 const char *kUsage =
@@ -46,6 +46,7 @@ const char *kUsage =
     "  -B [ --blocknumber ] arg (=20) number of blocks for averages and variances (and for reading the trajectory)\n"
     "  -N [ --thread ] arg           accepted for compatibility (the GPUs own the parallelism)\n"
     "  -d [ --dump-block ]           append the histogram of each block to ./gofrt.dump\n"
+    "  --edge-pairs                  (addition) report on stderr, per block, the pairs within 1 ulp of a bin edge\n"
     "Environment: ANALISI_DEVICES=0,1,... selects the GPUs (default: all visible).\n";
 
 struct Spec {
@@ -55,7 +56,7 @@ struct Spec {
 };
 const Spec kSpecs[] = {{'i', "input", 1},   {'h', "help", 0},        {'g', "gofrt", 1},  {'F', "factors", -1},
                        {'S', "stop", 1},    {'s', "skip", 1},        {'e', "every", 1},  {'B', "blocknumber", 1},
-                       {'N', "thread", 1},  {'d', "dump-block", 0}};
+                       {'N', "thread", 1},  {'d', "dump-block", 0}, {'\1', "edge-pairs", 0}};
 
 // options of the reference that select or tune calculations this front end does not provide
 const char *kForeign = "lVvMHaDzqQukYIEACf";
@@ -105,6 +106,7 @@ void assign(Options &o, const Spec &sp, const std::vector<std::string> &vals) {
         case 'B': o.blocknumber = static_cast<int>(to_long(vals[0], sp.longname)); break;
         case 'N': o.nthreads = static_cast<int>(to_long(vals[0], sp.longname)); break;
         case 'd': o.dump = true; break;
+        case '\1': o.edges = true; break;
     }
 }
 
@@ -184,6 +186,7 @@ int main(int argc, char **argv) {
         if (o.gofrt > 0) {
             if (o.factors.size() != 2) throw std::runtime_error("You have to specify the distance range with the option -F.\n");
             std::cerr << "Calculation of g(r,t) -- distinctive and non distinctive part of the van Hove function...\n";
+            if (o.edges) setenv("ANALISI_EDGE_PAIRS", "1", 1);
             Trajectory tr(o.input);
             tr.set_load_velocities(false);   // g(r,t) reads positions only
             tr.set_pbc_wrap(true);           // the minimum image needs wrapped coordinates (reference main.cpp:558)

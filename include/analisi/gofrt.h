@@ -55,7 +55,10 @@ public:
     Gofrt(T *t, TFLOAT rmin, TFLOAT rmax, unsigned int nbin, unsigned int tmax = 0, unsigned int nthreads = 0,
           unsigned int skip = 1, unsigned int every = 1, bool debug = false)
         : CalculateMultiThread_T(nthreads, skip, t->get_natoms(), every), rmin(rmin), rmax(rmax), incr(1),
-          debug(debug), traiettoria(t), nbin(nbin), lmax(tmax) {}
+          debug(debug), traiettoria(t), nbin(nbin), lmax(tmax) {
+        // ANALISI_EDGE_PAIRS=1 (the CLI's --edge-pairs): report the pairs within 1 ulp of a bin edge per block
+        if (const char *e = std::getenv("ANALISI_EDGE_PAIRS")) report_edges = std::atoi(e) != 0;
+    }
     ~Gofrt() { drop_plan(); }
     Gofrt(const This &) = delete;
 
@@ -130,10 +133,15 @@ public:
                 plan_generation = traiettoria->device_generation();
             }
             counts_buf.resize(data_length);
+            edge_count = 0;
             analisi_device::check(agofrt_block(plan, primo, static_cast<unsigned>(ntimesteps), static_cast<unsigned>(leff),
-                                               static_cast<unsigned>(skip), static_cast<unsigned>(every), AGOFRT_OPT_DEFAULT,
-                                               counts_buf.data(), nullptr, &stats),
+                                               static_cast<unsigned>(skip), static_cast<unsigned>(every),
+                                               report_edges ? AGOFRT_OPT_EDGES : AGOFRT_OPT_DEFAULT, counts_buf.data(),
+                                               report_edges ? &edge_count : nullptr, &stats),
                                   "agofrt_block");
+            if (report_edges)
+                std::cerr << "pairs within 1 ulp of a bin edge in this block: " << edge_count << " of "
+                          << stats.pair_evals_total << " pair evaluations\n";
             sum_kernel_ms += stats.kernel_ms;
             sum_total_ms += stats.total_ms;
             sum_pair_evals += stats.pair_evals_total;
@@ -148,6 +156,11 @@ public:
     const std::vector<uint64_t> &counts() const { return counts_buf; }
     const agofrt_stats &last_stats() const { return stats; }
     TFLOAT get_incr() const { return incr; }
+    // Pairs whose squared distance is a bin threshold or the double just below one: a 1-ulp change of d2 would move
+    // them to the neighbouring bin (or in / out of the range).  Counting them selects the kernel that compares
+    // against the plain threshold table (slower); off by default.
+    void set_report_edges(bool on) { report_edges = on; }
+    uint64_t edge_pairs() const { return edge_count; }
     // ... and the sums over every calculate() of this object (BlockAverageG runs all blocks on one object)
     double total_kernel_ms() const { return sum_kernel_ms; }
     double total_device_ms() const { return sum_total_ms; }
@@ -198,6 +211,8 @@ private:
     uint64_t plan_generation = 0;
     std::vector<uint64_t> counts_buf;
     agofrt_stats stats{};
+    bool report_edges = false;
+    uint64_t edge_count = 0;
     double sum_kernel_ms = 0, sum_total_ms = 0;
     uint64_t sum_pair_evals = 0;
     unsigned int ncalls = 0;

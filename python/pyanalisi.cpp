@@ -95,6 +95,9 @@ void define_gofrt(py::module &m, const std::string &suffix) {
         .def("getNumberOfExtraTimestepsNeeded", &G::nExtraTimesteps)
         .def("calculate", &G::calculate, py::call_guard<py::gil_scoped_release>())
         .def("get_columns_description", &G::get_columns_description)
+        .def("setReportEdges", &G::set_report_edges,
+             "addition: also count the pairs within 1 ulp of a bin edge in the next calculate() (slower kernel)")
+        .def("edge_pairs", &G::edge_pairs, "pairs within 1 ulp of a bin edge found by the last calculate()")
         .def("counts",
              [](G &g) {
                  const std::vector<ssize_t> sh = g.get_shape();

@@ -311,3 +311,53 @@ def test_reference_cpp_fixture_gofr(host, nth, tmax):
         assert np.array_equal(g.counts(), ref)
         assert np.array_equal(np.array(g), ref * cabi.gofrt_incr(75 - primo, 70))   # incr = 1
         assert ref[:, :3].sum() > 0 and ref[:, 3:].sum() == 0   # rmin 0.9: no self pairs at these lags
+
+
+def test_edge_pairs_through_host_layers(host, ctx, tmp_path):
+    """north_star: "any pair within 1 ulp of a bin edge is reported separately" -- Gofrt.setReportEdges / edge_pairs()
+    and the CLI's --edge-pairs, against the oracle's count.  Random liquids almost never hold such a pair, so a few
+    are built: atoms on the x axis at distances whose SQUARE is exactly a bin threshold (or the double below it)."""
+    cli, pa = host
+    rmin, rmax, nbin = 0.0, 2.0, 16
+    types = np.zeros(2, dtype=np.int32)
+    probe = cabi.DeviceTrajectory(ctx, 2, 6, types, 1, 1)
+    plan = cabi.Plan(probe, rmin, rmax, nbin)
+    thr = plan.thresholds()
+    plan.close()
+    probe.close()
+    xs = []
+    for k in range(1, nbin):
+        for target in (thr[k], np.nextafter(thr[k], 0.0)):
+            x0 = np.sqrt(target)
+            for x in (x0, np.nextafter(x0, 0.0), np.nextafter(x0, 4.0)):
+                if x * x == target:
+                    xs.append(x)
+                    break
+    assert len(xs) >= 6   # not every threshold is a representable square; a handful is plenty
+    pos1 = np.zeros((1 + len(xs), 3))
+    pos1[1:, 0] = xs
+    pos1 += np.array([0.25, 3.0, 3.0])
+    nfr = 5
+    pos = np.ascontiguousarray(np.repeat(pos1[None], nfr, axis=0))
+    box = np.tile([0.0, 6.0, 0.0, 6.0, 0.0, 6.0], (nfr, 1))
+    types = np.zeros(pos.shape[1], dtype=np.int32)
+    tr = pa.Trajectory(pos, np.zeros_like(pos), types, box, pa.BoxFormat.LammpsOrtho, False, False)
+    gof = pa.Gofrt(tr, rmin, rmax, nbin, 2, 1, 1, 1, False)
+    gof.setReportEdges(True)
+    gof.reset(3)
+    gof.calculate(0)
+    bi = synth.lammps_rows_to_internal(box)
+    ref, eref = oracle.counts(pos, bi, types, rmin, rmax, nbin, 2, 3, ntypes=1, return_edges=True)
+    assert np.array_equal(gof.counts(), ref)
+    assert gof.edge_pairs() == eref
+    assert eref >= 2 * 2 * 3 * len(xs) // 2   # (0,k) and (k,0), two lags, three origins; some x are "just below" ones
+    gof.setReportEdges(False)
+    gof.calculate(0)
+    assert np.array_equal(gof.counts(), ref) and gof.edge_pairs() == 0
+    path = str(tmp_path / "edge.bin")
+    synth.write_lammps_binary(path, pos, box, types + 1)
+    r = subprocess.run([cli, "-i", path, "-g", str(nbin), "-F", str(rmin), str(rmax), "-S", "1", "-B", "2", "--edge-pairs"],
+                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, cwd=str(tmp_path), timeout=300)
+    assert r.returncode == 0, r.stderr[-1500:]
+    lines = [l for l in r.stderr.splitlines() if l.startswith("pairs within 1 ulp of a bin edge")]
+    assert len(lines) == 2 and all(int(l.split(":")[1].split()[0]) > 0 for l in lines)
