@@ -21,7 +21,7 @@ COMM_ID_BYTES = 128
 SYMBOLS = [
     "agofrt_version", "agofrt_last_error", "agofrt_device_count", "agofrt_host_alloc", "agofrt_host_free",
     "agofrt_ctx_create", "agofrt_ctx_destroy", "agofrt_ctx_ndev", "agofrt_comm_unique_id", "agofrt_comm_join",
-    "agofrt_ctx_set_shard", "agofrt_shard_range", "agofrt_traj_create", "agofrt_traj_destroy", "agofrt_traj_upload",
+    "agofrt_ctx_set_shard", "agofrt_shard_range", "agofrt_traj_create", "agofrt_traj_destroy", "agofrt_traj_upload", "agofrt_traj_upload_wrap", "agofrt_plan_retarget",
     "agofrt_traj_download_frame", "agofrt_pbc_wrap", "agofrt_traj_d2_all", "agofrt_traj_d2_pair", "agofrt_plan_create",
     "agofrt_plan_destroy", "agofrt_plan_thresholds", "agofrt_block", "agofrt_fp64_peak",
 ]
@@ -81,6 +81,8 @@ def lib():
     L.agofrt_traj_create.argtypes = [C.POINTER(vp), vp, C.c_size_t, C.c_int, ip, C.c_int, C.c_size_t]
     L.agofrt_traj_destroy.argtypes = [vp]
     L.agofrt_traj_upload.argtypes = [vp, C.c_size_t, C.c_size_t, vp, vp]
+    L.agofrt_traj_upload_wrap.argtypes = [vp, C.c_size_t, C.c_size_t, vp, vp]
+    L.agofrt_plan_retarget.argtypes = [vp, vp]
     L.agofrt_traj_download_frame.argtypes = [vp, C.c_size_t, dp]
     L.agofrt_pbc_wrap.argtypes = [vp, vp, C.c_size_t, C.c_size_t, dp, C.c_int]
     L.agofrt_traj_d2_all.argtypes = [vp, C.c_size_t, C.c_size_t, dp]
@@ -216,6 +218,14 @@ class DeviceTrajectory:
         assert box.shape == (pos.shape[0], self.box_stride)
         _check(lib().agofrt_traj_upload(self._h, int(first_frame), pos.shape[0], pos.ctypes.data, box.ctypes.data))
 
+    def upload_wrap(self, first_frame, pos, box_internal):
+        """Upload with BaseTrajectory::pbc_wrap applied on the device; ``pos`` is wrapped in place."""
+        assert pos.dtype == np.float64 and pos.flags.c_contiguous and pos.flags.writeable
+        assert pos.ndim == 3 and pos.shape[1] == self.natoms and pos.shape[2] == 3
+        box = np.ascontiguousarray(box_internal, dtype=np.float64)
+        assert box.shape == (pos.shape[0], self.box_stride)
+        _check(lib().agofrt_traj_upload_wrap(self._h, int(first_frame), pos.shape[0], pos.ctypes.data, box.ctypes.data))
+
     def download_frame(self, frame):
         out = np.empty((self.natoms, 3), dtype=np.float64)
         _check(lib().agofrt_traj_download_frame(self._h, int(frame), _dp(out)))
@@ -249,6 +259,10 @@ class Plan:
         self.nbin = int(nbin)
         self._h = C.c_void_p()
         _check(lib().agofrt_plan_create(C.byref(self._h), traj._h, float(rmin), float(rmax), self.nbin))
+
+    def retarget(self, traj):
+        _check(lib().agofrt_plan_retarget(self._h, traj._h))
+        self.traj = traj
 
     def thresholds(self):
         out = np.empty(self.nbin + 1, dtype=np.float64)

@@ -135,6 +135,8 @@ struct TrajDev {
     int *type_start = nullptr;   // [ntypes+1]
     unsigned int *flags = nullptr;  // [4]: 0 = inf seen, 1 = wrap cap hit
     double *probe = nullptr;        // [4]: result of agofrt_traj_d2_pair
+    cudaStream_t up = nullptr;      // uploads of THIS window run here: they can overlap the pair kernels of another
+                                    // window of the same context (which run on the device's main stream)
 };
 
 struct agofrt_traj {
@@ -169,6 +171,7 @@ struct PlanDev {
 };
 
 struct agofrt_plan {
+    agofrt_ctx *ctx = nullptr;   // outlives windows: the plan may be retargeted or destroyed after its first window is gone
     agofrt_traj *traj = nullptr;
     double rmin = 0, rmax = 0, dr = 0, rmin2 = 0, rmax2 = 0;
     unsigned nbin = 0;
@@ -177,6 +180,7 @@ struct agofrt_plan {
     unsigned hlo = 0, hspan = 0;
     float inv_dr = 0, c0 = 0;
     float c0h = 0, lim = 0;      // safe-zone binning: c0 - 0.5, 0.5 - eps
+    int ntypes = 0;
     float qmax = 0;              // ... clamp of the bin coordinate: nbin + 0.25
     int glo = 0;                 // ... guard bins below bin 0 in every shared-memory histogram row
     bool safe_ok = false;        // validated on the device when the plan was made
@@ -411,6 +415,7 @@ static void free_traj_dev(agofrt_traj *t) {
         cudaFree(d.type_start);
         cudaFree(d.flags);
         cudaFree(d.probe);
+        if (d.up) cudaStreamDestroy(d.up);
     }
 }
 
@@ -473,6 +478,7 @@ extern "C" int agofrt_traj_create(agofrt_traj **out, agofrt_ctx *ctx, size_t nat
         CU(cudaMalloc(&d.type_start, (ntypes + 1) * sizeof(int)));
         CU(cudaMalloc(&d.flags, 4 * sizeof(unsigned int)));
         CU(cudaMalloc(&d.probe, 4 * sizeof(double)));
+        CU(cudaStreamCreateWithFlags(&d.up, cudaStreamNonBlocking));
         CU(cudaMemset(d.flags, 0, 4 * sizeof(unsigned int)));
         if (t->npad > 0) CU(cudaMemcpy(d.type_pad, t->type_pad.data(), t->npad * sizeof(int), cudaMemcpyHostToDevice));
         CU(cudaMemcpy(d.type_start, t->type_start.data(), (ntypes + 1) * sizeof(int), cudaMemcpyHostToDevice));
@@ -539,11 +545,13 @@ static void build_perm(agofrt_traj *t, const double *pos0, const double *box_row
     }
 }
 
-extern "C" int agofrt_traj_upload(agofrt_traj *t, size_t first_frame, size_t nframes, const double *pos_aos,
-                                  const double *box_internal) {
+// pos_in: the frames to upload; wrap: apply BaseTrajectory::pbc_wrap on the device before the SoA gather (every
+// device wraps its own copy -- same arithmetic, same bits) and hand the wrapped frames back in pos_back.
+static int upload_impl(agofrt_traj *t, size_t first_frame, size_t nframes, const double *pos_in, const double *box_internal,
+                       bool wrap, double *pos_back) {
     if (!t) return fail(AGOFRT_ERR_ARG, "traj is NULL");
     if (nframes > t->max_frames) return fail(AGOFRT_ERR_ARG, "window of %zu frames > max_frames %zu", nframes, t->max_frames);
-    if (nframes > 0 && (!box_internal || (t->natoms > 0 && !pos_aos))) return fail(AGOFRT_ERR_ARG, "NULL buffer");
+    if (nframes > 0 && (!box_internal || (t->natoms > 0 && !pos_in))) return fail(AGOFRT_ERR_ARG, "NULL buffer");
     t->first_frame = first_frame;
     t->nframes = nframes;
     t->box6.assign(nframes * 6, 0.0);
@@ -567,6 +575,10 @@ extern "C" int agofrt_traj_upload(agofrt_traj *t, size_t first_frame, size_t nfr
         for (int k = 3; k < 6; ++k)
             if (!std::isfinite(o[k])) t->bad_box = true;
     }
+    if (wrap && t->bad_box) {
+        t->nframes = 0;
+        return fail(AGOFRT_ERR_NONFINITE, "a box edge of the window is not positive and finite (the reference's wrap would not terminate)");
+    }
     // The spatial sort only serves locality (the group filter of the sparse kernels); atoms of a condensed
     // phase move little over a few hundred frames, so the permutation of an earlier window is kept --
     // at 1M atoms the host sort costs as much as a whole block on 8 GPUs.
@@ -574,7 +586,7 @@ extern "C" int agofrt_traj_upload(agofrt_traj *t, size_t first_frame, size_t nfr
     const size_t moved = first_frame > t->perm_frame ? first_frame - t->perm_frame : t->perm_frame - first_frame;
     const bool new_perm = t->natoms > 0 && (!t->perm_valid || moved >= kPermRefresh);
     if (new_perm) {
-        build_perm(t, pos_aos, box_internal);
+        build_perm(t, pos_in, box_internal);
         t->perm_valid = true;
         t->perm_frame = first_frame;
         t->slot_of_stale = true;
@@ -585,12 +597,11 @@ extern "C" int agofrt_traj_upload(agofrt_traj *t, size_t first_frame, size_t nfr
         Dev &dv = t->ctx->devs[i];
         TrajDev &d = t->dev[i];
         CU(cudaSetDevice(dv.id));
-        CU(cudaMemsetAsync(d.flags, 0, 4 * sizeof(unsigned int), dv.stream));
+        CU(cudaMemsetAsync(d.flags, 0, 4 * sizeof(unsigned int), d.up));
         if (t->npad > 0 && new_perm)
-            CU(cudaMemcpyAsync(d.perm, t->perm.data(), t->npad * sizeof(int), cudaMemcpyHostToDevice, dv.stream));
-        CU(cudaMemcpyAsync(d.box_stage, box_internal, nframes * t->stride * sizeof(double), cudaMemcpyHostToDevice,
-                           dv.stream));
-        CU(launch_pack_box(d.box_stage, t->stride, static_cast<int>(nframes), d.box6, dv.stream));
+            CU(cudaMemcpyAsync(d.perm, t->perm.data(), t->npad * sizeof(int), cudaMemcpyHostToDevice, d.up));
+        CU(cudaMemcpyAsync(d.box_stage, box_internal, nframes * t->stride * sizeof(double), cudaMemcpyHostToDevice, d.up));
+        CU(launch_pack_box(d.box_stage, t->stride, static_cast<int>(nframes), d.box6, d.up));
     }
     if (t->npad > 0) {
         for (size_t f0 = 0; f0 < nframes; f0 += t->stage_frames) {
@@ -599,29 +610,50 @@ extern "C" int agofrt_traj_upload(agofrt_traj *t, size_t first_frame, size_t nfr
                 Dev &dv = t->ctx->devs[i];
                 TrajDev &d = t->dev[i];
                 CU(cudaSetDevice(dv.id));
-                CU(cudaMemcpyAsync(d.stage, pos_aos + f0 * frame_elems, nf * frame_elems * sizeof(double),
-                                   cudaMemcpyHostToDevice, dv.stream));
+                CU(cudaMemcpyAsync(d.stage, pos_in + f0 * frame_elems, nf * frame_elems * sizeof(double),
+                                   cudaMemcpyHostToDevice, d.up));
+                if (wrap) {
+                    CU(launch_pbc_wrap(d.stage, static_cast<int>(t->natoms), static_cast<int>(nf),
+                                       d.box_stage + f0 * t->stride, t->stride, d.flags + 3, d.up));
+                    if (i == 0 && pos_back)
+                        CU(cudaMemcpyAsync(pos_back + f0 * frame_elems, d.stage, nf * frame_elems * sizeof(double),
+                                           cudaMemcpyDeviceToHost, d.up));
+                }
                 CU(launch_gather_soa(d.stage, d.perm, static_cast<int>(t->natoms), t->npad, static_cast<int>(nf),
-                                     d.pos + f0 * 3 * static_cast<size_t>(t->npad), dv.stream));
+                                     d.pos + f0 * 3 * static_cast<size_t>(t->npad), d.up));
             }
         }
         // coordinate bounds per frame (device 0 is enough: every device holds the same window)
         Dev &dv = t->ctx->devs[0];
         TrajDev &d = t->dev[0];
         CU(cudaSetDevice(dv.id));
-        CU(launch_frame_bounds(d.pos, d.perm, t->npad, static_cast<int>(nframes), d.bounds, d.flags, dv.stream));
+        CU(launch_frame_bounds(d.pos, d.perm, t->npad, static_cast<int>(nframes), d.bounds, d.flags, d.up));
         unsigned int flags[4] = {0, 0, 0, 0};
-        CU(cudaMemcpyAsync(t->bounds.data(), d.bounds, nframes * 6 * sizeof(double), cudaMemcpyDeviceToHost, dv.stream));
-        CU(cudaMemcpyAsync(flags, d.flags, sizeof(flags), cudaMemcpyDeviceToHost, dv.stream));
-        CU(cudaStreamSynchronize(dv.stream));
+        CU(cudaMemcpyAsync(t->bounds.data(), d.bounds, nframes * 6 * sizeof(double), cudaMemcpyDeviceToHost, d.up));
+        CU(cudaMemcpyAsync(flags, d.flags, sizeof(flags), cudaMemcpyDeviceToHost, d.up));
+        CU(cudaStreamSynchronize(d.up));
         t->has_inf = flags[0] != 0;
         t->has_nan = flags[2] != 0;
+        if (flags[3]) {
+            t->nframes = 0;
+            return fail(AGOFRT_ERR_NONFINITE, "minimum image did not converge while wrapping (non-finite or absurdly far coordinate)");
+        }
     }
     for (size_t i = 0; i < t->dev.size(); ++i) {
         CU(cudaSetDevice(t->ctx->devs[i].id));
-        CU(cudaStreamSynchronize(t->ctx->devs[i].stream));
+        CU(cudaStreamSynchronize(t->dev[i].up));
     }
     return AGOFRT_OK;
+}
+
+extern "C" int agofrt_traj_upload(agofrt_traj *t, size_t first_frame, size_t nframes, const double *pos_aos,
+                                  const double *box_internal) {
+    return upload_impl(t, first_frame, nframes, pos_aos, box_internal, false, nullptr);
+}
+
+extern "C" int agofrt_traj_upload_wrap(agofrt_traj *t, size_t first_frame, size_t nframes, double *pos_aos_inout,
+                                       const double *box_internal) {
+    return upload_impl(t, first_frame, nframes, pos_aos_inout, box_internal, true, pos_aos_inout);
 }
 
 extern "C" int agofrt_traj_download_frame(agofrt_traj *t, size_t frame, double *pos_aos) {
@@ -889,6 +921,8 @@ extern "C" int agofrt_plan_create(agofrt_plan **out, agofrt_traj *traj, double r
     if (nbin == 0 || nbin > (1u << 24)) return fail(AGOFRT_ERR_ARG, "nbin must be in [1, 2^24]");
     auto p = std::make_unique<agofrt_plan>();
     p->traj = traj;
+    p->ctx = traj->ctx;
+    p->ntypes = traj->ntypes;
     p->rmin = rmin;
     p->rmax = rmax;
     p->nbin = nbin;
@@ -985,10 +1019,19 @@ extern "C" int agofrt_plan_create(agofrt_plan **out, agofrt_traj *traj, double r
     return AGOFRT_OK;
 }
 
+extern "C" int agofrt_plan_retarget(agofrt_plan *p, agofrt_traj *traj) {
+    if (!p || !traj) return fail(AGOFRT_ERR_ARG, "NULL argument");
+    if (traj == p->traj) return AGOFRT_OK;
+    if (traj->ctx != p->ctx || traj->ntypes != p->ntypes)
+        return fail(AGOFRT_ERR_ARG, "the new window belongs to another context or has another number of types");
+    p->traj = traj;
+    return AGOFRT_OK;
+}
+
 extern "C" int agofrt_plan_destroy(agofrt_plan *p) {
     if (!p) return AGOFRT_OK;
     for (size_t i = 0; i < p->dev.size(); ++i) {
-        cudaSetDevice(p->traj->ctx->devs[i].id);
+        cudaSetDevice(p->ctx->devs[i].id);
         PlanDev &d = p->dev[i];
         cudaFree(d.thr);
         cudaFree(d.thr_full);

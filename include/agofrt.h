@@ -30,7 +30,8 @@
  * Conventions: every function returns 0 (AGOFRT_OK) or a negative agofrt_status; the message of the
  * last failure on the calling thread is agofrt_last_error().  Host pointers passed in are only read
  * (or written, for outputs) during the call; no ownership is transferred.  All calls on one context
- * must come from one host thread at a time.
+ * must come from one host thread at a time, with one exception: agofrt_traj_upload / agofrt_traj_upload_wrap
+ * on one window may run on a second host thread while the first is inside agofrt_block on ANOTHER window.
  */
 #ifndef AGOFRT_H
 #define AGOFRT_H
@@ -107,6 +108,13 @@ AGOFRT_API int agofrt_traj_destroy(agofrt_traj *traj);
  * type-major, spatially sorted, padded SoA layout (a permutation: counts do not depend on it). */
 AGOFRT_API int agofrt_traj_upload(agofrt_traj *traj, size_t first_frame, size_t nframes,
                                   const double *pos_aos, const double *box_internal);
+/* The same with BaseTrajectory::pbc_wrap (lib/include/basetrajectory.h:145-161) applied ON THE DEVICE before the
+ * layout change: pos_aos_inout holds the unwrapped frames on entry and the wrapped ones on return (what
+ * Trajectory::set_access_at leaves in its window when wrapping is on, lib/src/trajectory.cpp:664-670).
+ * Uploads run on a stream of their own: a second window of the same context may be uploaded by another host
+ * thread while agofrt_block works on the first one (read-ahead of the next block). */
+AGOFRT_API int agofrt_traj_upload_wrap(agofrt_traj *traj, size_t first_frame, size_t nframes,
+                                       double *pos_aos_inout, const double *box_internal);
 /* Read one frame back in the caller's atom order (tests: the layout round-trips bit-exactly). */
 AGOFRT_API int agofrt_traj_download_frame(agofrt_traj *traj, size_t frame, double *pos_aos);
 /* In-place BaseTrajectory::pbc_wrap on a host buffer through the GPU (frames with their own box
@@ -126,6 +134,8 @@ AGOFRT_API int agofrt_traj_d2_pair(agofrt_traj *traj, size_t atom_i, size_t atom
 AGOFRT_API int agofrt_plan_create(agofrt_plan **plan, agofrt_traj *traj, double rmin, double rmax,
                                   unsigned nbin);
 AGOFRT_API int agofrt_plan_destroy(agofrt_plan *plan);
+/* Point the plan at another window of the same context with the same number of types (double-buffered windows). */
+AGOFRT_API int agofrt_plan_retarget(agofrt_plan *plan, agofrt_traj *traj);
 /* thresholds[nbin+1]: thresholds[k] = the smallest d2 (>=0) whose reference bin index
  * (int)floorf((sqrt(d2)-rmin)/dr) is >= k (+inf if none). */
 AGOFRT_API int agofrt_plan_thresholds(const agofrt_plan *plan, double *thresholds);

@@ -208,6 +208,7 @@ public:
             dev_window.create(natoms, static_cast<int>(buffer_boxes_stride), buffer_type_id, static_cast<int>(ntypes),
                               loaded_timesteps);
             dev_uploaded_epoch = 0;
+            ++dev_epoch;
         }
         if (dev_uploaded_epoch != host_epoch) {
             dev_window.upload(current_timestep, loaded_timesteps, buffer_positions, buffer_boxes);
@@ -215,12 +216,41 @@ public:
         }
         return dev_window.handle();
     }
-    // changes whenever the device handle is re-created (Gofrt rebuilds its plan then)
-    uint64_t device_generation() const { return dev_window.generation(); }
+    // changes whenever a device handle is created or destroyed (Gofrt rebuilds its plan then; between such
+    // events it only re-points the plan at the handle device_window() returns: the windows are double-buffered)
+    uint64_t device_generation() const { return dev_epoch; }
 
 protected:
     ~BaseTrajectory() = default;
     void mark_window_changed() { ++host_epoch; }
+
+    // ---- read-ahead of the NEXT window onto the devices (derived containers with a background reader) ----
+    // Gofrt has already used this trajectory on the GPUs: reading ahead may upload as well
+    bool device_active() const { return dev_window.valid(); }
+    // Called on the reader thread while the caller's thread may be inside Gofrt::calculate on the current
+    // window: frames [first, first+n) go to the SECOND device window (wrapped there when asked; pos comes
+    // back wrapped).  The C ABI allows exactly this concurrency (include/agofrt.h).
+    void upload_next_window(size_t first, size_t n, double *pos_aos_inout, const double *box_internal, bool wrap) {
+        if (!dev_window_next.valid() || dev_window_next.capacity() < n) {
+            dev_window_next.create(natoms, static_cast<int>(buffer_boxes_stride), buffer_type_id, static_cast<int>(ntypes),
+                                   std::max(n, dev_window.capacity()));
+            next_created = true;
+        }
+        if (wrap)
+            dev_window_next.upload_wrap(first, n, pos_aos_inout, box_internal);
+        else
+            dev_window_next.upload(first, n, pos_aos_inout, box_internal);
+    }
+    // Called on the caller's thread after the host buffers were swapped and mark_window_changed(): the device
+    // already holds this window
+    void adopt_next_window() {
+        dev_window.swap(dev_window_next);
+        dev_uploaded_epoch = host_epoch;
+        if (next_created) {
+            ++dev_epoch;
+            next_created = false;
+        }
+    }
 
     double *buffer_positions = nullptr;
     double *buffer_velocity = nullptr;
@@ -236,8 +266,9 @@ protected:
     std::map<int, unsigned int> type_map;
 
 private:
-    analisi_device::Window dev_window;
-    uint64_t host_epoch = 1, dev_uploaded_epoch = 0;
+    analisi_device::Window dev_window, dev_window_next;
+    uint64_t host_epoch = 1, dev_uploaded_epoch = 0, dev_epoch = 0;
+    bool next_created = false;
 };
 
 #endif

@@ -81,6 +81,16 @@ public:
     size_t capacity() const { return cap_; }
     // replace the device window by frames [first, first+n) from host buffers
     void upload(size_t first, size_t n, const double *pos_aos, const double *box_internal);
+    // the same with BaseTrajectory::pbc_wrap applied on the device; pos_aos comes back wrapped
+    void upload_wrap(size_t first, size_t n, double *pos_aos_inout, const double *box_internal);
+    void swap(Window &o) {
+        agofrt_traj *t = traj_;
+        traj_ = o.traj_;
+        o.traj_ = t;
+        size_t c = cap_;
+        cap_ = o.cap_;
+        o.cap_ = c;
+    }
     agofrt_traj *handle() { return traj_; }
     // bumped on every create(): plans made on an older handle must be rebuilt
     uint64_t generation() const { return generation_; }

@@ -132,6 +132,8 @@ public:
                 analisi_device::check(agofrt_plan_create(&plan, win, rmin, rmax, nbin), "agofrt_plan_create");
                 plan_generation = traiettoria->device_generation();
             }
+            // the trajectory double-buffers its device windows (read-ahead): follow the current one
+            analisi_device::check(agofrt_plan_retarget(plan, win), "agofrt_plan_retarget");
             counts_buf.resize(data_length);
             edge_count = 0;
             analisi_device::check(agofrt_block(plan, primo, static_cast<unsigned>(ntimesteps), static_cast<unsigned>(leff),

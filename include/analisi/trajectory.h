@@ -126,7 +126,7 @@ private:
     std::thread prefetch_thread;
     std::exception_ptr prefetch_error;
     size_t prefetch_target = 0;
-    bool prefetch_valid = false, prefetch_enabled = true;
+    bool prefetch_valid = false, prefetch_enabled = true, prefetch_uploaded = false;
 };
 
 #endif

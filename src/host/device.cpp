@@ -63,6 +63,10 @@ void Window::upload(size_t first, size_t n, const double *pos_aos, const double 
     check(agofrt_traj_upload(traj_, first, n, pos_aos, box_internal), "agofrt_traj_upload");
 }
 
+void Window::upload_wrap(size_t first, size_t n, double *pos_aos_inout, const double *box_internal) {
+    check(agofrt_traj_upload_wrap(traj_, first, n, pos_aos_inout, box_internal), "agofrt_traj_upload_wrap");
+}
+
 void pbc_wrap(double *pos_aos, size_t nframes, size_t natoms, const double *box_internal, int box_stride) {
     check(agofrt_pbc_wrap(Context::instance().handle(), pos_aos, nframes, natoms, box_internal, box_stride),
           "agofrt_pbc_wrap");

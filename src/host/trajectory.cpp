@@ -300,9 +300,17 @@ void Trajectory::start_prefetch(size_t target) {
     prefetch_target = target;
     prefetch_valid = true;
     prefetch_error = nullptr;
-    prefetch_thread = std::thread([this, target, W]() {
+    prefetch_uploaded = false;
+    const bool to_device = device_active();   // decided on the caller's thread
+    prefetch_thread = std::thread([this, target, W, to_device]() {
         try {
             read_frames(target, target + W, target, pos_alt.data(), boxes_alt.data(), false);
+            if (to_device) {
+                // wrap on the device, lay the window out there, bring the wrapped frames back: all of it under
+                // the pair kernels of the block the caller is computing
+                upload_next_window(target, W, pos_alt.data(), boxes_alt.data(), wrap_pbc);
+                prefetch_uploaded = true;
+            }
         } catch (...) {
             prefetch_error = std::current_exception();
         }
@@ -320,10 +328,11 @@ Trajectory::Errori Trajectory::set_access_at(const size_t &timestep) {
     const size_t W = static_cast<size_t>(loaded_timesteps);
     const bool had_window = window_loaded;
     const size_t previous = static_cast<size_t>(current_timestep);
-    auto finish = [&](const char *how) {
+    auto finish = [&](const char *how, bool on_device) {
         current_timestep = static_cast<ssize_t>(timestep);
         window_loaded = true;
         mark_window_changed();
+        if (on_device) adopt_next_window();
         // equal steps forward: read the next window ahead
         if (had_window && timestep > previous) start_prefetch(timestep + (timestep - previous));
         const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_begin).count();
@@ -342,8 +351,9 @@ Trajectory::Errori Trajectory::set_access_at(const size_t &timestep) {
             buffer_positions = pos_buf.data();
             buffer_boxes = boxes.data();
             window_loaded = false;
+            if (prefetch_uploaded) return finish(" (read ahead, already on the GPUs)", true);
             if (wrap_pbc) pbc_wrap_frames(0, W);
-            return finish(" (read ahead)");
+            return finish(" (read ahead)", false);
         }
     }
 
@@ -381,7 +391,7 @@ Trajectory::Errori Trajectory::set_access_at(const size_t &timestep) {
         read_frames(read_begin, read_end, timestep, buffer_positions, buffer_boxes, true);
     }
     if (wrap_pbc && read_end > read_begin) pbc_wrap_frames(static_cast<ssize_t>(read_begin - timestep), read_end - read_begin);
-    return finish("");
+    return finish("", false);
 }
 
 int64_t Trajectory::get_timestep_lammps(size_t timestep) {
