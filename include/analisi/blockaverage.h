@@ -28,6 +28,7 @@ class TraiettoriaF {
 public:
     static void set_data_access_block_size(unsigned int, TR *) {}
     static void set_access_at(unsigned int, TR *) {}
+    static void hint_stride(unsigned int, TR *) {}
     static unsigned int get_ntimesteps(TR *t) { return static_cast<unsigned int>(t->get_ntimesteps()); }
 };
 
@@ -36,6 +37,9 @@ class TraiettoriaF<Trajectory> {
 public:
     static void set_data_access_block_size(unsigned int s, Trajectory *t) { t->set_data_access_block_size(s); }
     static void set_access_at(unsigned int s, Trajectory *t) { t->set_access_at(s); }
+    // this repository's addition: the block loop tells the reader how far apart its windows are, so the
+    // read-ahead can start with the first block instead of guessing the stride from the first two
+    static void hint_stride(unsigned int s, Trajectory *t) { t->set_access_stride_hint(s); }
     static unsigned int get_ntimesteps(Trajectory *t) { return static_cast<unsigned int>(t->get_ntimesteps()); }
 };
 
@@ -71,6 +75,7 @@ public:
         calcolo->reset(s);
         calc->calcola_begin(s, calcolo);
         TraiettoriaF<TR>::set_data_access_block_size(s + extra, traiettoria);
+        TraiettoriaF<TR>::hint_stride(s, traiettoria);
         cronometro cron;
         cron.set_expected(1.0 / double(n_b));
         cron.start();

@@ -71,6 +71,8 @@ public:
 
     // default true (what the reference always does); the CLI g(r,t) branch turns it off
     void set_load_velocities(bool v) { load_velocities = v; }
+    // the caller will ask for windows `stride` frames apart (BlockAverageG does): read ahead from the first one
+    void set_access_stride_hint(size_t stride) { stride_hint = stride; }
 
 private:
     template <bool SAFE, bool ATOM>
@@ -125,7 +127,7 @@ private:
     std::vector<double> boxes_alt;
     std::thread prefetch_thread;
     std::exception_ptr prefetch_error;
-    size_t prefetch_target = 0;
+    size_t prefetch_target = 0, stride_hint = 0;
     bool prefetch_valid = false, prefetch_enabled = true, prefetch_uploaded = false;
 };
 

@@ -333,8 +333,11 @@ Trajectory::Errori Trajectory::set_access_at(const size_t &timestep) {
         window_loaded = true;
         mark_window_changed();
         if (on_device) adopt_next_window();
-        // equal steps forward: read the next window ahead
-        if (had_window && timestep > previous) start_prefetch(timestep + (timestep - previous));
+        // equal steps forward (or the stride the block loop announced): read the next window ahead
+        if (had_window && timestep > previous)
+            start_prefetch(timestep + (timestep - previous));
+        else if (stride_hint > 0)
+            start_prefetch(timestep + stride_hint);
         const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_begin).count();
         std::cerr << "Reading time: " << dt << "s" << how << ".\n";
         return Ok;

@@ -76,7 +76,9 @@ WORKER = textwrap.dedent('''
         ok = ok and bool(np.array_equal(c, ref)) and st["world"] == ranks.world and (e is None or e == eref)
         ok = ok and 0 < st["pair_evals"] < st["pair_evals_total"]
     ranks.barrier()
-    print(json.dumps({"rank": ranks.rank, "ok": ok, "world": ranks.world}))
+    import sys
+    sys.stdout.write(json.dumps({"rank": ranks.rank, "ok": ok, "world": ranks.world}) + "\n")   # one write: ranks must not interleave
+    sys.stdout.flush()
     plan.close(); tr.close(); ctx.close(); ranks.close()
 ''')
 
@@ -89,7 +91,8 @@ def test_one_process_per_gpu_nccl(tmp_path):
     script.write_text(WORKER)
     r = torchrun(2, [str(script)])
     assert r.returncode == 0, r.stderr[-3000:]
-    lines = [json.loads(l) for l in r.stdout.splitlines() if l.startswith("{")]
+    import re
+    lines = [json.loads(m) for m in re.findall(r"\{[^{}]*\}", r.stdout)]
     assert len(lines) == 2 and all(l["ok"] and l["world"] == 2 for l in lines)
 
 

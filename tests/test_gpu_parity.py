@@ -334,3 +334,53 @@ def test_c4_size_bit_exact_vs_oracle(ctx):
     assert np.array_equal(c2, ref) and e2 == eref
     c3, st3 = gpu_counts(ctx, pos, bi, types, 1, *args, skip=2, options=cabi.OPT_FORCE_GENERAL | cabi.OPT_NO_SAFE)
     assert np.array_equal(c3, ref) and st3["jobs_fast"] == 0
+
+
+def test_upload_wrap_retarget_and_concurrent_upload(ctx):
+    """Double-buffered windows through the C ABI: agofrt_traj_upload_wrap (wrap on the device, wrapped frames handed
+    back) == oracle wrap + plain upload; agofrt_plan_retarget moves a plan between two windows; and the one
+    concurrency the header allows -- a second host thread uploading window B while agofrt_block runs on A."""
+    import threading
+    pos, box, types = synth.small_case(81, (12, 10, 10), 1.06, 2, True, 12)
+    bi = synth.lammps_rows_to_internal(box)
+    raw_a, raw_b = np.ascontiguousarray(pos[:6]), np.ascontiguousarray(pos[6:])
+    wa, wb = oracle.pbc_wrap(raw_a, bi[:6]), oracle.pbc_wrap(raw_b, bi[6:])
+    A = cabi.DeviceTrajectory(ctx, pos.shape[1], 9, types, 2, 6)
+    B = cabi.DeviceTrajectory(ctx, pos.shape[1], 9, types, 2, 6)
+    buf_a = raw_a.copy()
+    A.upload_wrap(0, buf_a, bi[:6])
+    assert np.array_equal(buf_a, wa)
+    assert np.array_equal(A.download_frame(3), wa[3])
+    plan = cabi.Plan(A, 0.0, 3.0, 60)
+    ref_a = oracle.counts(wa, bi[:6], types, 0.0, 3.0, 60, 3, 4, ntypes=2)
+    ref_b = oracle.counts(wb, bi[6:], types, 0.0, 3.0, 60, 3, 4, primo=6, ntypes=2, first_frame=6, total_frames=12)
+    out = {}
+    buf_b = raw_b.copy()
+
+    def compute():
+        for _ in range(20):   # keep the device busy on A while B is uploaded
+            out["a"] = plan.block(0, 4, 3)[0]
+
+    def upload():
+        for _ in range(5):
+            buf_b[...] = raw_b
+            B.upload_wrap(6, buf_b, bi[6:])
+
+    ta, tb = threading.Thread(target=compute), threading.Thread(target=upload)
+    ta.start()
+    tb.start()
+    ta.join()
+    tb.join()
+    assert np.array_equal(out["a"], ref_a)
+    assert np.array_equal(buf_b, wb)
+    plan.retarget(B)
+    cb, st = plan.block(6, 4, 3)
+    assert np.array_equal(cb, ref_b)
+    plan.retarget(A)
+    assert np.array_equal(plan.block(0, 4, 3)[0], ref_a)
+    other = cabi.DeviceTrajectory(ctx, pos.shape[1], 9, np.zeros(pos.shape[1], dtype=np.int32), 1, 6)
+    with pytest.raises(cabi.AgofrtError):
+        plan.retarget(other)   # another number of types
+    plan.close()
+    for t in (A, B, other):
+        t.close()
