@@ -77,7 +77,7 @@ WORKER = textwrap.dedent('''
         ok = ok and 0 < st["pair_evals"] < st["pair_evals_total"]
     ranks.barrier()
     import sys
-    sys.stdout.write(json.dumps({"rank": ranks.rank, "ok": ok, "world": ranks.world}) + "\n")   # one write: ranks must not interleave
+    sys.stdout.write("AGOFRT_RESULT " + json.dumps({"rank": ranks.rank, "ok": ok, "world": ranks.world}) + "\\n")   # one write: ranks must not interleave
     sys.stdout.flush()
     plan.close(); tr.close(); ctx.close(); ranks.close()
 ''')
@@ -92,8 +92,8 @@ def test_one_process_per_gpu_nccl(tmp_path):
     r = torchrun(2, [str(script)])
     assert r.returncode == 0, r.stderr[-3000:]
     import re
-    lines = [json.loads(m) for m in re.findall(r"\{[^{}]*\}", r.stdout)]
-    assert len(lines) == 2 and all(l["ok"] and l["world"] == 2 for l in lines)
+    lines = [json.loads(m) for m in re.findall(r"AGOFRT_RESULT (\{[^{}]*\})", r.stdout)]
+    assert len(lines) == 2 and all(l["ok"] and l["world"] == 2 for l in lines), (r.stdout[-1500:], r.stderr[-1500:])
 
 
 @needs2
