@@ -23,7 +23,7 @@ SYMBOLS = [
     "agofrt_ctx_create", "agofrt_ctx_destroy", "agofrt_ctx_ndev", "agofrt_comm_unique_id", "agofrt_comm_join",
     "agofrt_ctx_set_shard", "agofrt_shard_range", "agofrt_traj_create", "agofrt_traj_destroy", "agofrt_traj_upload", "agofrt_traj_upload_wrap", "agofrt_plan_retarget",
     "agofrt_traj_download_frame", "agofrt_pbc_wrap", "agofrt_traj_d2_all", "agofrt_traj_d2_pair", "agofrt_plan_create",
-    "agofrt_plan_destroy", "agofrt_plan_thresholds", "agofrt_block", "agofrt_fp64_peak",
+    "agofrt_plan_destroy", "agofrt_plan_thresholds", "agofrt_block", "agofrt_neighbour_hist", "agofrt_fp64_peak",
 ]
 
 
@@ -92,6 +92,7 @@ def lib():
     L.agofrt_plan_thresholds.argtypes = [vp, dp]
     L.agofrt_block.argtypes = [vp, C.c_size_t, C.c_uint, C.c_uint, C.c_uint, C.c_uint, C.c_uint, u64p, u64p,
                                C.POINTER(Stats)]
+    L.agofrt_neighbour_hist.argtypes = [vp, C.c_double, C.c_size_t, C.c_uint, C.c_uint, u64p, C.POINTER(Stats)]
     L.agofrt_fp64_peak.argtypes = [vp, C.c_int, C.c_double, dp]
     for name in SYMBOLS:
         fn = getattr(L, name)
@@ -235,6 +236,15 @@ class DeviceTrajectory:
         out = np.zeros((self.natoms, self.natoms, 4), dtype=np.float64)
         _check(lib().agofrt_traj_d2_all(self._h, int(frame_i), int(frame_j), _dp(out)))
         return out
+
+    def neighbour_hist(self, r, tstart, ntimesteps, skip=1, hist=None):
+        """IstogrammaAtomiRaggio::calculate on the uploaded window; returns (hist[ntypes][natoms+1], stats)."""
+        if hist is None:
+            hist = np.zeros((self.ntypes, self.natoms + 1), dtype=np.uint64)
+        st = Stats()
+        _check(lib().agofrt_neighbour_hist(self._h, float(r), int(tstart), int(ntimesteps), int(skip),
+                                           hist.ctypes.data_as(C.POINTER(C.c_uint64)), C.byref(st)))
+        return hist, st.as_dict()
 
     def d2_pair(self, i, j, frame_i, frame_j):
         out = np.zeros(4, dtype=np.float64)

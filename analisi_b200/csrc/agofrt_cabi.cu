@@ -135,6 +135,9 @@ struct TrajDev {
     int *type_start = nullptr;   // [ntypes+1]
     unsigned int *flags = nullptr;  // [4]: 0 = inf seen, 1 = wrap cap hit
     double *probe = nullptr;        // [4]: result of agofrt_traj_d2_pair
+    unsigned long long *nb_hist = nullptr;  // neighbour-count histogram [ntypes][natoms+1] (agofrt_neighbour_hist)
+    int *nb_frames = nullptr;
+    size_t nb_frames_cap = 0;
     cudaStream_t up = nullptr;      // uploads of THIS window run here: they can overlap the pair kernels of another
                                     // window of the same context (which run on the device's main stream)
 };
@@ -415,6 +418,8 @@ static void free_traj_dev(agofrt_traj *t) {
         cudaFree(d.type_start);
         cudaFree(d.flags);
         cudaFree(d.probe);
+        cudaFree(d.nb_hist);
+        cudaFree(d.nb_frames);
         if (d.up) cudaStreamDestroy(d.up);
     }
 }
@@ -1368,6 +1373,126 @@ extern "C" int agofrt_block(agofrt_plan *p, size_t primo, unsigned ntimesteps, u
         stats->ndev_local = static_cast<uint32_t>(nloc);
         stats->world = static_cast<uint32_t>(world);
         stats->kernel_modes = modes_used;
+    }
+    return AGOFRT_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// neighbour-count histogram (IstogrammaAtomiRaggio::calculate)
+// ---------------------------------------------------------------------------------------------
+extern "C" int agofrt_neighbour_hist(agofrt_traj *t, double r, size_t tstart, unsigned ntimesteps, unsigned skip,
+                                     uint64_t *hist_inout, agofrt_stats *stats) {
+    if (!t) return fail(AGOFRT_ERR_ARG, "traj is NULL");
+    agofrt_ctx *ctx = t->ctx;
+    if (skip < 1) skip = 1;   // reference lib/src/istogrammaatomiraggio.cpp:19
+    if (stats) memset(stats, 0, sizeof(*stats));
+    const size_t hstride = t->natoms + 1;
+    const size_t hlen = static_cast<size_t>(t->ntypes) * hstride;
+    if (ntimesteps == 0 || t->natoms == 0) return AGOFRT_OK;
+    if (!hist_inout) return fail(AGOFRT_ERR_ARG, "hist is NULL");
+    const size_t last = tstart + static_cast<size_t>((ntimesteps - 1) / skip) * skip;
+    if (tstart < t->first_frame || last >= t->first_frame + t->nframes)
+        return fail(AGOFRT_ERR_WINDOW, "frames [%zu,%zu] are not all in the device window [%zu,%zu)", tstart, last,
+                    t->first_frame, t->first_frame + t->nframes);
+    if (t->bad_box || t->has_inf)
+        return fail(AGOFRT_ERR_NONFINITE, "the window holds an infinite coordinate or a non-positive / non-finite box edge");
+    int rc = ensure_local_comm(ctx);
+    if (rc != AGOFRT_OK) return rc;
+    const int nloc = static_cast<int>(ctx->devs.size());
+    const int world = ctx->world > 0 ? ctx->world : nloc;
+    const int first_rank = ctx->world > 0 ? ctx->first_rank : 0;
+
+    std::vector<int> fr_fast, fr_gen;
+    for (size_t f = tstart; f <= last; f += skip) {
+        const size_t rel = f - t->first_frame;
+        (job_is_single_pass(t, rel, rel) && !t->has_nan ? fr_fast : fr_gen).push_back(static_cast<int>(rel));
+    }
+    const size_t nfr = fr_fast.size() + fr_gen.size();
+    const int tile = neighbour_tile_atoms();
+    const int n_itiles = std::max(1, (t->npad + tile - 1) / tile);
+    const bool tri = t->stride == 9;
+    double kernel_ms = 0;
+    unsigned launches = 0;
+    for (int i = 0; i < nloc; ++i) {
+        Dev &dv = ctx->devs[i];
+        TrajDev &td = t->dev[i];
+        CU(cudaSetDevice(dv.id));
+        if (!td.nb_hist) CU(cudaMalloc(&td.nb_hist, hlen * sizeof(unsigned long long)));
+        if (nfr > td.nb_frames_cap) {
+            cudaFree(td.nb_frames);
+            td.nb_frames = nullptr;
+            td.nb_frames_cap = 0;
+            CU(cudaMalloc(&td.nb_frames, nfr * sizeof(int)));
+            td.nb_frames_cap = nfr;
+        }
+        CU(cudaMemsetAsync(td.nb_hist, 0, hlen * sizeof(unsigned long long), dv.stream));
+        CU(cudaMemsetAsync(td.flags + 1, 0, sizeof(unsigned int), dv.stream));
+        if (!fr_fast.empty())
+            CU(cudaMemcpyAsync(td.nb_frames, fr_fast.data(), fr_fast.size() * sizeof(int), cudaMemcpyHostToDevice, dv.stream));
+        if (!fr_gen.empty())
+            CU(cudaMemcpyAsync(td.nb_frames + fr_fast.size(), fr_gen.data(), fr_gen.size() * sizeof(int),
+                               cudaMemcpyHostToDevice, dv.stream));
+        CU(cudaEventRecord(dv.ev_k0, dv.stream));
+        for (int pass = 0; pass < 2; ++pass) {
+            const std::vector<int> &list = pass == 0 ? fr_fast : fr_gen;
+            if (list.empty()) continue;
+            uint64_t ub = 0, ue = 0;
+            agofrt_shard_range(static_cast<uint64_t>(list.size()) * n_itiles, first_rank + i, world, &ub, &ue);
+            if (ue <= ub) continue;
+            NeighbourParams np;
+            np.pos = td.pos;
+            np.box = td.box6;
+            np.perm = td.perm;
+            np.type_start = td.type_start;
+            np.frames = td.nb_frames + (pass == 0 ? 0 : fr_fast.size());
+            np.hist = td.nb_hist;
+            np.error_flag = td.flags + 1;
+            np.r2 = r * r;   // reference lib/src/istogrammaatomiraggio.cpp:17
+            np.unit_begin = static_cast<unsigned>(ub);
+            np.unit_end = static_cast<unsigned>(ue);
+            np.npad = t->npad;
+            np.ntypes = t->ntypes;
+            np.n_itiles = n_itiles;
+            np.hist_stride = hstride;
+            const int grid = static_cast<int>(std::min<uint64_t>(ue - ub, static_cast<uint64_t>(dv.sm_count) * 8));
+            CU(launch_neighbour_kernel(tri, pass == 0, grid, dv.stream, np));
+            ++launches;
+        }
+        CU(cudaEventRecord(dv.ev_k1, dv.stream));
+    }
+    if (ctx->comm_ready && world > 1) {
+        NcclApi &api = nccl_api();
+        NC(api.GroupStart());
+        for (int i = 0; i < nloc; ++i)
+            NC(api.AllReduce(t->dev[i].nb_hist, t->dev[i].nb_hist, hlen, ncclUint64, ncclSum, ctx->devs[i].comm, ctx->devs[i].stream));
+        NC(api.GroupEnd());
+    }
+    std::vector<unsigned long long> host(hlen);
+    const int nread = (ctx->comm_ready && world > 1) ? 1 : nloc;   // without a communicator the local partials are summed here
+    for (int i = 0; i < nloc; ++i) {
+        Dev &dv = ctx->devs[i];
+        CU(cudaSetDevice(dv.id));
+        unsigned int flag = 0;
+        CU(cudaMemcpyAsync(&flag, t->dev[i].flags + 1, sizeof(flag), cudaMemcpyDeviceToHost, dv.stream));
+        if (i < nread) CU(cudaMemcpyAsync(host.data(), t->dev[i].nb_hist, hlen * sizeof(unsigned long long), cudaMemcpyDeviceToHost, dv.stream));
+        CU(cudaStreamSynchronize(dv.stream));
+        float ms = 0;
+        CU(cudaEventElapsedTime(&ms, dv.ev_k0, dv.ev_k1));
+        kernel_ms = std::max<double>(kernel_ms, ms);
+        if (flag) return fail(AGOFRT_ERR_NONFINITE, "minimum image did not converge within %d images", kWrapCap);
+        if (i < nread)
+            for (size_t k = 0; k < hlen; ++k) hist_inout[k] += host[k];
+    }
+    if (stats) {
+        stats->kernel_ms = kernel_ms;
+        stats->total_ms = kernel_ms;
+        stats->pair_evals_total = static_cast<uint64_t>(nfr) * t->natoms * t->natoms;
+        stats->pair_evals = stats->pair_evals_total / static_cast<uint64_t>(world) * nloc;
+        stats->jobs = nfr;
+        stats->jobs_fast = fr_fast.size();
+        stats->launches = launches;
+        stats->ndev_local = static_cast<uint32_t>(nloc);
+        stats->world = static_cast<uint32_t>(world);
     }
     return AGOFRT_OK;
 }

@@ -1045,6 +1045,106 @@ cudaError_t launch_d2_pair(const double *pos_i, const double *pos_j, const doubl
 }
 
 // ---------------------------------------------------------------------------------------------
+// Neighbour-count histogram (IstogrammaAtomiRaggio::calculate, reference lib/src/istogrammaatomiraggio.cpp:31-85):
+// for every listed frame and every atom i, the number of atoms j (j == i included) of each type with
+// d2_minImage(i,j,frame,frame) < r2, then hist[type][count] += 1.  Same distance arithmetic as the pair kernel;
+// the device layout is type-major, so the count of one type is a plain loop over that type's slot range.
+// One work unit = (frame, tile of kNbThreads*kNbIPT i atoms); j coordinates go through shared memory.
+// ---------------------------------------------------------------------------------------------
+constexpr int kNbThreads = 256;
+constexpr int kNbIPT = 2;
+constexpr int kNbTileJ = 512;
+
+template <bool TRI, bool FAST>
+__global__ void __launch_bounds__(kNbThreads) neighbour_kernel(const NeighbourParams p) {
+    __shared__ __align__(16) double sj[3][kNbTileJ];
+    const int tid = threadIdx.x;
+    unsigned int wrap_bad = 0;
+    for (unsigned int u = p.unit_begin + blockIdx.x; u < p.unit_end; u += gridDim.x) {
+        const int f = p.frames[u / static_cast<unsigned int>(p.n_itiles)];
+        const int itile = static_cast<int>(u % static_cast<unsigned int>(p.n_itiles));
+        const double *pf = p.pos + static_cast<size_t>(f) * 3 * p.npad;
+        const double *bx = p.box + static_cast<size_t>(f) * 6;
+        BoxRegs b;
+        b.lhx = bx[0];
+        b.lhy = bx[1];
+        b.lhz = bx[2];
+        b.xy = bx[3];
+        b.xz = bx[4];
+        b.yz = bx[5];
+        const double nLx = __dmul_rn(b.lhx, -2.0), nLy = __dmul_rn(b.lhy, -2.0), nLz = __dmul_rn(b.lhz, -2.0);
+        double xi[kNbIPT], yi[kNbIPT], zi[kNbIPT];
+        int slot[kNbIPT];
+        bool real[kNbIPT];
+#pragma unroll
+        for (int k = 0; k < kNbIPT; ++k) {
+            slot[k] = itile * (kNbThreads * kNbIPT) + k * kNbThreads + tid;
+            real[k] = slot[k] < p.npad && p.perm[slot[k]] >= 0;
+            if (slot[k] < p.npad) {
+                xi[k] = pf[slot[k]];
+                yi[k] = pf[p.npad + slot[k]];
+                zi[k] = pf[2 * static_cast<size_t>(p.npad) + slot[k]];
+            } else {
+                xi[k] = yi[k] = zi[k] = __longlong_as_double(0x7ff8000000000000ll);
+            }
+        }
+        for (int ty = 0; ty < p.ntypes; ++ty) {
+            const int jb = p.type_start[ty], je = p.type_start[ty + 1];
+            unsigned int cnt[kNbIPT];
+#pragma unroll
+            for (int k = 0; k < kNbIPT; ++k) cnt[k] = 0;
+            for (int j0 = jb; j0 < je; j0 += kNbTileJ) {
+                const int n = min(kNbTileJ, je - j0);
+                __syncthreads();
+                for (int q = tid; q < n; q += kNbThreads) {
+                    sj[0][q] = pf[j0 + q];
+                    sj[1][q] = pf[p.npad + j0 + q];
+                    sj[2][q] = pf[2 * static_cast<size_t>(p.npad) + j0 + q];
+                }
+                __syncthreads();
+#pragma unroll 4
+                for (int q = 0; q < n; ++q) {
+                    const double xj = sj[0][q], yj = sj[1][q], zj = sj[2][q];
+#pragma unroll
+                    for (int k = 0; k < kNbIPT; ++k) {
+                        double dx = __dsub_rn(xi[k], xj), dy = __dsub_rn(yi[k], yj), dz = __dsub_rn(zi[k], zj);
+                        if (FAST) {
+                            min_image_single<TRI>(dx, dy, dz, b, nLx, nLy, nLz);
+                        } else {
+                            if (!min_image_general<TRI>(dx, dy, dz, b)) wrap_bad = 1;
+                        }
+                        // NaN (ghost slots, NaN coordinates) compares false: never a neighbour, as in the reference
+                        cnt[k] += d2_of(dx, dy, dz) < p.r2 ? 1u : 0u;
+                    }
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < kNbIPT; ++k)
+                if (real[k]) atomicAdd(p.hist + static_cast<size_t>(ty) * p.hist_stride + cnt[k], 1ull);
+        }
+    }
+    if (wrap_bad) atomicExch(p.error_flag, 1u);
+}
+
+cudaError_t launch_neighbour_kernel(bool triclinic, bool fast, int grid, cudaStream_t stream, const NeighbourParams &p) {
+    if (grid <= 0) return cudaSuccess;
+    if (triclinic) {
+        if (fast)
+            neighbour_kernel<true, true><<<grid, kNbThreads, 0, stream>>>(p);
+        else
+            neighbour_kernel<true, false><<<grid, kNbThreads, 0, stream>>>(p);
+    } else {
+        if (fast)
+            neighbour_kernel<false, true><<<grid, kNbThreads, 0, stream>>>(p);
+        else
+            neighbour_kernel<false, false><<<grid, kNbThreads, 0, stream>>>(p);
+    }
+    return cudaGetLastError();
+}
+
+int neighbour_tile_atoms() { return kNbThreads * kNbIPT; }
+
+// ---------------------------------------------------------------------------------------------
 // FP64 issue-rate microbenchmark: 8 independent DFMA chains per thread
 // ---------------------------------------------------------------------------------------------
 constexpr int kPeakChains = 8;

@@ -96,6 +96,23 @@ cudaError_t launch_d2_all(const double *pos_i, const double *pos_j, const double
 // one pair, by device slots: out4 = dx,dy,dz,d2
 cudaError_t launch_d2_pair(const double *pos_i, const double *pos_j, const double *box6, int triclinic, int slot_i,
                            int slot_j, int npad, double *out4, unsigned int *error_flag, cudaStream_t stream);
+// neighbour-count histogram (IstogrammaAtomiRaggio)
+struct NeighbourParams {
+    const double *pos;         // [frames][3][npad]
+    const double *box;         // [frames][6]
+    const int *perm;           // [npad] slot -> atom, -1 = ghost
+    const int *type_start;     // [ntypes+1]
+    const int *frames;         // window-relative frames to visit
+    unsigned long long *hist;  // [ntypes][hist_stride], hist_stride = natoms + 1
+    unsigned int *error_flag;
+    double r2;
+    unsigned unit_begin, unit_end;   // units = (frame index, i tile)
+    int npad, ntypes, n_itiles;
+    unsigned long long hist_stride;
+};
+cudaError_t launch_neighbour_kernel(bool triclinic, bool fast, int grid, cudaStream_t stream, const NeighbourParams &p);
+int neighbour_tile_atoms();
+
 // MODE_SAFE validation: bad += number of probes whose unflagged float guess differs from expected[]
 cudaError_t launch_validate_safe(const double *probes, const int *expected, int n, float inv_dr, float c0h, float lim,
                                  float qmax, int nbin, int glo, unsigned int *bad, cudaStream_t stream);

@@ -174,6 +174,15 @@ AGOFRT_API int agofrt_block(agofrt_plan *plan, size_t primo, unsigned ntimesteps
                             unsigned skip, unsigned every, unsigned options, uint64_t *counts_out,
                             uint64_t *edge_pairs_out, agofrt_stats *stats);
 
+/* ---- next row of the scope table: the neighbour-count histogram ------------------------------ */
+/* IstogrammaAtomiRaggio::calculate (lib/src/istogrammaatomiraggio.cpp:31-85, `analisi --neighbour r`): for the
+ * frames tstart, tstart+skip, ... < tstart+ntimesteps of the uploaded window and every atom i, count the atoms j
+ * (j == i included) of each type with d2_minImage(i,j,frame,frame) < r*r, then hist[type][count] += 1.
+ * hist_inout is [ntypes][natoms+1] (host, uint64) and is ADDED to, as the reference's maps accumulate over calls.
+ * Same minimum-image arithmetic and multi-GPU sharding (frames x atom tiles, one all-reduce) as agofrt_block. */
+AGOFRT_API int agofrt_neighbour_hist(agofrt_traj *traj, double r, size_t tstart, unsigned ntimesteps, unsigned skip,
+                                     uint64_t *hist_inout, agofrt_stats *stats);
+
 /* ---- measurement --------------------------------------------------------------------------- */
 /* Sustained FP64 FMA issue rate of one device (DFMA chains, CUDA events): the roofline
  * denominator of SURVEY.md section 8(d).  Runs for about `seconds`. */

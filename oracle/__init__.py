@@ -12,6 +12,7 @@ from .oracle import (  # noqa: F401
     counts,
     vdata,
     mediavar,
+    neighbour_hist,
     min_image,
     d2_all,
     pbc_wrap,

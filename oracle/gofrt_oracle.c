@@ -339,3 +339,73 @@ void gofrt_oracle_mediavar(const double *blocks, unsigned n_b, size_t len, doubl
     const double norm = (double)((n_b - 1) * n_b);
     for (size_t i = 0; i < len; ++i) var[i] /= norm;
 }
+
+
+/* ---- lib/src/istogrammaatomiraggio.cpp:31-85 --------------------------------------------------
+ * hist[type][count] += 1 per atom and frame; threads split the atoms as the reference does (the
+ * result does not depend on the split: integer counts). */
+typedef struct {
+    const gofrt_oracle_traj *tr;
+    double r2;
+    size_t tstart;
+    unsigned ntimesteps, skip;
+    size_t a0, a1;
+    uint64_t *hist; /* private [ntypes][natoms+1] */
+} nb_worker_t;
+
+static void *nb_worker(void *arg) {
+    nb_worker_t *w = (nb_worker_t *)arg;
+    const gofrt_oracle_traj *tr = w->tr;
+    const size_t N = tr->natoms, stride = tr->triclinic ? 9 : 6;
+    const int nt = tr->ntypes;
+    unsigned *cont = (unsigned *)calloc((size_t)nt, sizeof(unsigned));
+    for (size_t f = w->tstart; f < w->tstart + w->ntimesteps; f += w->skip) {
+        const size_t rel = f - tr->first_frame;
+        const double *p = tr->pos + rel * N * 3;
+        const double *bx = tr->box + rel * stride;
+        for (size_t i = w->a0; i < w->a1; ++i) {
+            for (int k = 0; k < nt; ++k) cont[k] = 0;
+            for (size_t j = 0; j < N; ++j) {
+                double x[3];
+                if (gofrt_oracle_d2(p + 3 * i, p + 3 * j, bx + 3, bx + 6, tr->triclinic, x) < w->r2) cont[tr->type_id[j]]++;
+            }
+            for (int k = 0; k < nt; ++k) w->hist[(size_t)k * (N + 1) + cont[k]] += 1;
+        }
+    }
+    free(cont);
+    return NULL;
+}
+
+int gofrt_oracle_neighbour_hist(const gofrt_oracle_traj *tr, double r, size_t tstart, unsigned ntimesteps,
+                                unsigned skip, uint64_t *hist, unsigned nthreads) {
+    if (!tr || !hist || tr->ntypes <= 0) return GOFRT_ORACLE_BAD_ARG;
+    if (skip < 1) skip = 1; /* istogrammaatomiraggio.cpp:19 */
+    if (nthreads < 1) nthreads = 1;
+    if (ntimesteps == 0 || tr->natoms == 0) return GOFRT_ORACLE_OK;
+    const size_t last = tstart + ((size_t)(ntimesteps - 1) / skip) * skip;
+    if (tstart < tr->first_frame || last >= tr->first_frame + tr->nframes) return GOFRT_ORACLE_TOO_SHORT;
+    const size_t N = tr->natoms, len = (size_t)tr->ntypes * (N + 1);
+    if (nthreads > N) nthreads = (unsigned)N;
+    nb_worker_t *w = (nb_worker_t *)calloc(nthreads, sizeof(nb_worker_t));
+    pthread_t *th = (pthread_t *)calloc(nthreads, sizeof(pthread_t));
+    const size_t per = N / nthreads;
+    for (unsigned k = 0; k < nthreads; ++k) {
+        w[k].tr = tr;
+        w[k].r2 = r * r; /* istogrammaatomiraggio.cpp:17 */
+        w[k].tstart = tstart;
+        w[k].ntimesteps = ntimesteps;
+        w[k].skip = skip;
+        w[k].a0 = per * k;
+        w[k].a1 = (k != nthreads - 1) ? per * (k + 1) : N;
+        w[k].hist = (uint64_t *)calloc(len, sizeof(uint64_t));
+        pthread_create(&th[k], NULL, nb_worker, &w[k]);
+    }
+    for (unsigned k = 0; k < nthreads; ++k) {
+        pthread_join(th[k], NULL);
+        for (size_t q = 0; q < len; ++q) hist[q] += w[k].hist[q];
+        free(w[k].hist);
+    }
+    free(w);
+    free(th);
+    return GOFRT_ORACLE_OK;
+}

@@ -91,6 +91,15 @@ int gofrt_oracle_vdata(const gofrt_oracle_traj *tr, const gofrt_oracle_params *p
  * `len` values laid out blocks[n_b][len]. */
 void gofrt_oracle_mediavar(const double *blocks, unsigned n_b, size_t len, double *mean, double *var);
 
+/* Next row of the scope table: the neighbour-count histogram of
+ * IstogrammaAtomiRaggio::calculate (lib/src/istogrammaatomiraggio.cpp:31-85, driven by `analisi --neighbour r`,
+ * analisi/main.cpp:620-642).  For every frame tstart, tstart+skip, ... < tstart+ntimesteps and every atom i:
+ * cont[type(j)]++ for every j (j == i included) with d2_minImage(i,j,frame,frame) < r*r, then
+ * hist[type][cont[type]]++ for every type.  hist is [ntypes][natoms+1], ADDED to (the reference's maps
+ * accumulate over calculate() calls).  Pinned by the reference's golden text tests/data/cli/neighbours. */
+int gofrt_oracle_neighbour_hist(const gofrt_oracle_traj *tr, double r, size_t tstart, unsigned ntimesteps,
+                                unsigned skip, uint64_t *hist, unsigned nthreads);
+
 #ifdef __cplusplus
 }
 #endif

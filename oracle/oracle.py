@@ -83,6 +83,8 @@ def _load():
     build()
     lib = C.CDLL(_LIB_PATH)
     dp = C.POINTER(C.c_double)
+    lib.gofrt_oracle_neighbour_hist.argtypes = [C.c_void_p, C.c_double, C.c_size_t, C.c_uint, C.c_uint,
+                                                C.POINTER(C.c_uint64), C.c_uint]
     lib.gofrt_oracle_lammps_to_internal.argtypes = [dp]
     lib.gofrt_oracle_internal_to_lammps.argtypes = [dp]
     lib.gofrt_oracle_min_image.argtypes = [dp, dp, dp, C.c_int]
@@ -184,6 +186,23 @@ def mediavar(blocks):
     var = np.zeros(flat.shape[1])
     lib.gofrt_oracle_mediavar(_dp(flat), n_b, flat.shape[1], _dp(mean), _dp(var))
     return mean.reshape(b.shape[1:]), var.reshape(b.shape[1:])
+
+
+def neighbour_hist(pos, box_internal, type_id, r, tstart, ntimesteps, skip=1, ntypes=None, first_frame=0, nthreads=None,
+                   hist=None):
+    """IstogrammaAtomiRaggio::calculate (lib/src/istogrammaatomiraggio.cpp:31-85): hist[type][count] over frames
+    tstart, tstart+skip, ... < tstart+ntimesteps; returns (and adds to) a uint64 array [ntypes][natoms+1]."""
+    lib = _load()
+    t, keep, ntypes = _traj(pos, box_internal, type_id, ntypes, first_frame, None)
+    if hist is None:
+        hist = np.zeros((ntypes, pos.shape[1] + 1), dtype=np.uint64)
+    if nthreads is None:
+        nthreads = os.cpu_count() or 1
+    rc = lib.gofrt_oracle_neighbour_hist(C.byref(t), float(r), int(tstart), int(ntimesteps), int(skip),
+                                         hist.ctypes.data_as(C.POINTER(C.c_uint64)), int(nthreads))
+    _check(rc)
+    del keep
+    return hist
 
 
 def min_image(delta, box_row):
