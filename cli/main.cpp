@@ -19,6 +19,7 @@
 
 #include "analisi/blockaverage.h"
 #include "analisi/gofrt.h"
+#include "analisi/istogrammaatomiraggio.h"
 #include "analisi/trajectory.h"
 
 namespace {
@@ -29,6 +30,7 @@ struct Options {
     std::vector<double> factors;
     int stop_acf = 0, skip = 1, every = 1, blocknumber = 20, nthreads = 2;
     bool dump = false, help = false, edges = false;
+    double neighbour_r = 0.0;
 };
 
 const char *kUsage =
@@ -46,6 +48,7 @@ const char *kUsage =
     "  -B [ --blocknumber ] arg (=20) number of blocks for averages and variances (and for reading the trajectory)\n"
     "  -N [ --thread ] arg           accepted for compatibility (the GPUs own the parallelism)\n"
     "  -d [ --dump-block ]           append the histogram of each block to ./gofrt.dump\n"
+    "  --neighbour arg (=0)          calculate the histogram of the neighbours up to the specified distance\n"
     "  --edge-pairs                  (addition) report on stderr, per block, the pairs within 1 ulp of a bin edge\n"
     "Environment: ANALISI_DEVICES=0,1,... selects the GPUs (default: all visible).\n";
 
@@ -56,7 +59,7 @@ struct Spec {
 };
 const Spec kSpecs[] = {{'i', "input", 1},   {'h', "help", 0},        {'g', "gofrt", 1},  {'F', "factors", -1},
                        {'S', "stop", 1},    {'s', "skip", 1},        {'e', "every", 1},  {'B', "blocknumber", 1},
-                       {'N', "thread", 1},  {'d', "dump-block", 0}, {'\1', "edge-pairs", 0}};
+                       {'N', "thread", 1},  {'d', "dump-block", 0}, {'\1', "edge-pairs", 0}, {'\2', "neighbour", 1}};
 
 // options of the reference that select or tune calculations this front end does not provide
 const char *kForeign = "lVvMHaDzqQukYIEACf";
@@ -64,7 +67,7 @@ const char *kForeignLong[] = {"loginput", "vibrational-spectrum", "velocity-hist
                               "heat-transport-coefficient", "headers", "dt", "covariance", "mean-square-displacement",
                               "mean-square-displacement-cm", "mean-square-displacement-self", "subtract-mean",
                               "subtract-mean-start", "subBlock", "kk", "kk-range", "binary-convert",
-                              "binary-convert-gromacs", "neighbour", "spherical-harmonics-correlation", "buffer-size", "lt",
+                              "binary-convert-gromacs", "spherical-harmonics-correlation", "buffer-size", "lt",
                               "cut", "write-mass-currents", "fpe", "test-debug"};
 
 bool looks_like_option(const char *a) {
@@ -107,6 +110,7 @@ void assign(Options &o, const Spec &sp, const std::vector<std::string> &vals) {
         case 'N': o.nthreads = static_cast<int>(to_long(vals[0], sp.longname)); break;
         case 'd': o.dump = true; break;
         case '\1': o.edges = true; break;
+        case '\2': o.neighbour_r = to_double(vals[0], sp.longname); break;
     }
 }
 
@@ -172,7 +176,7 @@ int main(int argc, char **argv) {
         const int default_threads = o.nthreads;
         o = parse(argc, argv);
         if (o.nthreads <= 0) o.nthreads = default_threads;
-        if (argc <= 1 || o.help || o.skip <= 0 || o.stop_acf < 0) {
+        if (argc <= 1 || o.help || o.skip <= 0 || o.stop_acf < 0 || o.neighbour_r < 0) {
             std::cout << kUsage << "\n";
             return o.help ? 0 : 1;
         }
@@ -211,6 +215,31 @@ int main(int argc, char **argv) {
                     }
                     std::cout << "\n";
                 }
+                std::cout << "\n\n";
+            }
+        } else if (o.neighbour_r > 0) {
+            // reference analisi/main.cpp:620-642: histogram of the number of neighbours within r, per type
+            std::cerr << "Beginning of calculation of neighbour histogram\n";
+            Trajectory test(o.input);
+            test.set_load_velocities(false);
+            test.set_pbc_wrap(true);
+            IstogrammaAtomiRaggio h(&test, o.neighbour_r, static_cast<unsigned int>(o.skip), static_cast<unsigned int>(o.nthreads));
+            const unsigned int nt = static_cast<unsigned int>(test.get_ntimesteps());
+            const unsigned int nb = static_cast<unsigned int>(o.blocknumber);
+            if (nb == 0 || (nt - 1) / nb == 0) throw std::runtime_error("Cannot divide the trajectory in that many blocks!\n");
+            const unsigned int s = (nt - 1) / nb;
+            h.reset(s);
+            test.set_data_access_block_size(s);
+            test.set_access_stride_hint(s);
+            for (unsigned int i = 0; i < nb; i++) {
+                const unsigned int t = s * i;
+                test.set_access_at(t);
+                h.calculate(t);
+            }
+            std::map<unsigned int, unsigned int> *hist = h.get_hist();
+            for (unsigned int i = 0; i < test.get_ntypes(); i++) {
+                std::cout << "\"" << i << "\"\n";
+                for (auto it = hist[i].begin(); it != hist[i].end(); ++it) std::cout << it->first << " " << it->second << "\n";
                 std::cout << "\n\n";
             }
         } else {

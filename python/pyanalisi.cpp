@@ -19,6 +19,7 @@
 
 #include "analisi/blockaverage.h"
 #include "analisi/gofrt.h"
+#include "analisi/istogrammaatomiraggio.h"
 #include "analisi/trajectory.h"
 #include "analisi/trajectory_numpy.h"
 
@@ -161,6 +162,22 @@ void define_block_average(py::module &m, const std::string &suffix) {
         });
 }
 
+// Addition: the neighbour-count histogram (the reference only reaches it from its CLI, --neighbour)
+template <class TR>
+void define_neighbour_hist(py::module &m, const std::string &suffix) {
+    using H = IstogrammaAtomiRaggioG<TR>;
+    py::class_<H>(m, ("NeighbourHistogram" + suffix).c_str(), py::module_local())
+        .def(py::init<TR *, double, unsigned int, unsigned int>(), py::keep_alive<1, 2>(), py::arg("traj"), py::arg("r"),
+             py::arg("skip") = 1, py::arg("nthreads") = 0)
+        .def("reset", &H::reset)
+        .def("calculate", &H::calculate, py::call_guard<py::gil_scoped_release>())
+        .def("get_hist", [](H &h, unsigned int type) {
+            std::map<unsigned int, unsigned int> *hist = h.get_hist();
+            if (!hist) throw std::runtime_error("reset() was not called");
+            return hist[type];   // dict {number of neighbours: occurrences}
+        });
+}
+
 }  // namespace
 
 PYBIND11_MODULE(pyanalisi, m) {
@@ -216,6 +233,8 @@ PYBIND11_MODULE(pyanalisi, m) {
 
     define_gofrt<Trajectory>(m, "_lammps");
     define_gofrt<Trajectory_numpy>(m, "");
+    define_neighbour_hist<Trajectory>(m, "_lammps");
+    define_neighbour_hist<Trajectory_numpy>(m, "");
     define_block_average<Trajectory>(m, "_lammps");
     define_block_average<Trajectory_numpy>(m, "");
 

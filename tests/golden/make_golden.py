@@ -208,7 +208,8 @@ def cli_golden_text():
     """The reference's CLI golden output for the g(r,t) branch (tests/test_cli.sh:33-34), copied as is:
     analisi -i tests/data/lammps2020.bin -g 100 -F 0.0 4.0 -S {1,10} -s 8  (20 blocks, mean and variance)."""
     import shutil
-    for name in ("pair_corr_no_t", "pair_corr_t"):
+    # ... and the neighbour-count histogram of the next scope row (tests/test_cli.sh:35: --neighbour 10)
+    for name in ("pair_corr_no_t", "pair_corr_t", "neighbours"):
         shutil.copyfile(os.path.join(REF, "tests/data/cli", name), os.path.join(HERE, "cli_" + name + ".txt"))
 
 

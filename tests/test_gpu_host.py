@@ -361,3 +361,33 @@ def test_edge_pairs_through_host_layers(host, ctx, tmp_path):
     assert r.returncode == 0, r.stderr[-1500:]
     lines = [l for l in r.stderr.splitlines() if l.startswith("pairs within 1 ulp of a bin edge")]
     assert len(lines) == 2 and all(int(l.split(":")[1].split()[0]) > 0 for l in lines)
+
+
+def test_cli_neighbour_reference_golden_text(host, tmp_path):
+    """reference tests/test_cli.sh:35 verbatim: analisi -i lammps2020.bin --neighbour 10, stdout against the
+    reference's golden text (tests/golden/cli_neighbours.txt); and the same numbers through the python class."""
+    cli, pa = host
+    path = os.path.join(REFDATA, "lammps2020.bin")
+    if not os.path.exists(path):
+        pytest.skip("tests/_refdata/lammps2020.bin not present")
+    r = subprocess.run([cli, "-i", path, "--neighbour", "10"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True,
+                       cwd=str(tmp_path), timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    gold = open(os.path.join(GOLDEN, "cli_neighbours.txt")).read()
+    assert r.stdout.rstrip("\n") == gold.rstrip("\n")
+    tr = pa.Traj(path)
+    tr.setLoadVelocities(False)
+    tr.setWrapPbc(True)
+    s = (tr.getNtimesteps() - 1) // 20
+    tr.setAccessWindowSize(s)
+    h = pa.NeighbourHistogram_lammps(tr, 10.0, 1, 1)
+    h.reset(s)
+    for i in range(20):
+        tr.setAccessStart(s * i)
+        h.calculate(s * i)
+    rows = []
+    for ty in range(tr.get_ntypes()):
+        rows.append('"%d"' % ty)
+        rows += ["%d %d" % kv for kv in sorted(h.get_hist(ty).items())]
+        rows += ["", ""]
+    assert ("\n".join(rows) + "\n").rstrip("\n") == gold.rstrip("\n")

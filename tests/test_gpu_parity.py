@@ -384,3 +384,29 @@ def test_upload_wrap_retarget_and_concurrent_upload(ctx):
     plan.close()
     for t in (A, B, other):
         t.close()
+
+
+@pytest.mark.parametrize("triclinic,ntypes,wrap", [(False, 1, True), (True, 3, True), (True, 2, False)])
+def test_neighbour_histogram_vs_oracle(ctx, triclinic, ntypes, wrap):
+    """next scope row (SURVEY.md 8f-2): IstogrammaAtomiRaggio::calculate through agofrt_neighbour_hist --
+    orthorhombic / triclinic, several types (ghost slots), wrapped (single-pass kernel) and unwrapped input (general
+    minimum image), skip, and accumulation over calls, bit-exact against the oracle."""
+    pos, box, types = synth.small_case(91, (7, 6, 5), 1.08, ntypes, triclinic, 9)
+    bi = synth.lammps_rows_to_internal(box)
+    pos = np.ascontiguousarray(pos)
+    if wrap:
+        ctx.pbc_wrap(pos, bi)
+    tr = cabi.DeviceTrajectory(ctx, pos.shape[1], bi.shape[1], types, ntypes, 9)
+    tr.upload(0, pos, bi)
+    r = 2.3
+    h, st = tr.neighbour_hist(r, 1, 7, 3)            # frames 1, 4, 7
+    ref = oracle.neighbour_hist(pos, bi, types, r, 1, 7, 3, ntypes=ntypes)
+    assert np.array_equal(h, ref)
+    assert h.sum() == 3 * pos.shape[1] * ntypes and st["jobs"] == 3
+    assert st["jobs_fast"] == (3 if wrap else 0) or not wrap
+    h, _ = tr.neighbour_hist(r, 0, 2, 1, hist=h)      # accumulates, like the reference's maps
+    ref = oracle.neighbour_hist(pos, bi, types, r, 0, 2, 1, ntypes=ntypes, hist=ref)
+    assert np.array_equal(h, ref)
+    with pytest.raises(cabi.AgofrtError):
+        tr.neighbour_hist(r, 5, 9, 1)                 # runs past the uploaded window
+    tr.close()

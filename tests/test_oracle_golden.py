@@ -142,3 +142,37 @@ def test_cli_golden_blocks(name, tmax):
     rows = [l for l in _cli_text(mean, var, leff, nbin, nt * (nt + 1)) if l]
     assert len(rows) == len(gold_rows)
     assert rows == gold_rows
+
+
+def neighbour_text(hist):
+    # the CLI's printing loop, reference analisi/main.cpp:636-642
+    lines = []
+    for k in range(hist.shape[0]):
+        lines.append('"%d"' % k)
+        for c in np.nonzero(hist[k])[0]:
+            lines.append("%d %d" % (c, hist[k][c]))
+        lines += ["", ""]
+    return "\n".join(lines) + "\n"
+
+
+def test_neighbour_histogram_cli_golden():
+    """reference tests/test_cli.sh:35: analisi -i lammps2020.bin --neighbour 10 (20 blocks of 9 frames, wrap on):
+    the oracle's restatement of IstogrammaAtomiRaggio reproduces the reference's golden text."""
+    m = oracle.load_ref()
+    path = os.path.join(REFERENCE, "tests/data/lammps2020.bin")
+    if m is None or not os.path.exists(path):
+        pytest.skip("reference tree not available")
+    from conftest import GOLDEN
+    tr = m.Traj(path)
+    tr.setWrapPbc(True)
+    nt, n_b = tr.get_ntimesteps(), 20
+    s = (nt - 1) // n_b
+    tr.setAccessWindowSize(s)
+    hist = None
+    for i in range(n_b):
+        tr.setAccessStart(s * i)
+        hist = oracle.neighbour_hist(tr.get_positions_copy(), tr.get_box_copy(), tr.get_type_ids(), 10.0, s * i, s, 1,
+                                     ntypes=int(tr.get_ntypes()), first_frame=s * i, hist=hist)
+    assert hist.sum() == 2 * 4000 * n_b * s
+    gold = open(os.path.join(GOLDEN, "cli_neighbours.txt")).read()
+    assert neighbour_text(hist).rstrip("\n") == gold.rstrip("\n")
