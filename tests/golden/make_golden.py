@@ -204,6 +204,37 @@ def cell_vectors_rotation(m):
     np.savez_compressed(os.path.join(HERE, "cell_vectors_rotation.npz"), **out)
 
 
+def qr_many(m):
+    """200 general cell matrices (random scales, triangular, partly zero, negative, nearly degenerate first
+    column) through the reference's Trajectory_numpy: internal box rows, rotation matrices and one rotated
+    position per frame.  Pins the hand-written 3x3 Householder QR of include/analisi/triclinic.h bit for bit."""
+    rng = np.random.default_rng(77)
+    cells = []
+    for k in range(200):
+        M = rng.normal(size=(3, 3)) * rng.choice([0.5, 3.0, 20.0])
+        if k % 10 == 1:
+            M = np.tril(M)
+        if k % 10 == 2:
+            M = np.triu(M)
+        if k % 10 == 3:
+            M[1, 0] = 0
+            M[2, 0] = 0
+        if k % 10 == 4:
+            M[2, 1] = 0
+        if k % 10 == 5:
+            M = -np.abs(M)
+        if k % 10 == 6:
+            M = np.diag(np.abs(rng.normal(size=3)) + 1) @ np.array([[1, 0.3, 0.2], [0, 1, 0.1], [0, 0, 1.0]])
+        if k % 10 == 7:
+            M[:, 0] = [1e-9, 2.0, 0]
+        cells.append(M)
+    cells = np.ascontiguousarray(np.stack(cells))
+    pos = np.ascontiguousarray(rng.normal(size=(len(cells), 2, 3)))
+    tr = m.Trajectory(pos, np.zeros_like(pos), np.zeros(2, dtype=np.int32), cells, m.BoxFormat.CellVectors, False, True)
+    np.savez_compressed(os.path.join(HERE, "qr_many.npz"), cells=cells, pos=pos, box_internal=tr.get_box_copy(),
+                        rotation=tr.get_rotation_matrix(), pos_rotated=tr.get_positions_copy())
+
+
 def cli_golden_text():
     """The reference's CLI golden output for the g(r,t) branch (tests/test_cli.sh:33-34), copied as is:
     analisi -i tests/data/lammps2020.bin -g 100 -F 0.0 4.0 -S {1,10} -s 8  (20 blocks, mean and variance)."""
@@ -220,6 +251,7 @@ def main():
     min_image_and_pbc(m)
     live_reference_cases(m)
     cell_vectors_rotation(m)
+    qr_many(m)
     cli_golden_text()
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz") or f.endswith(".txt"):

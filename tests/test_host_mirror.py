@@ -237,3 +237,16 @@ def test_mmap_trajectory_read_ahead(host, tmp_path, capfd):
     err = capfd.readouterr().err
     assert err.count("(read ahead)") == 4   # 6, 9, 12 and 8; 15 would run past the end and is never started
     assert tr.get_velocities_copy().size == 0
+
+
+def test_householder_qr_200_cells(host):
+    """200 general cells (scales 0.5-20, triangular, partly zero, all-negative, nearly degenerate first column):
+    internal box, Q and rotated positions bit-identical to the reference's Eigen-based TriclinicLammpsCell
+    (fixture tests/golden/qr_many.npz made by the compiled reference)."""
+    _, pa = host
+    z = load_golden("qr_many.npz")
+    pos = z["pos"]
+    tr = pa.Trajectory(pos, np.zeros_like(pos), np.zeros(2, dtype=np.int32), z["cells"], pa.BoxFormat.CellVectors, False, True)
+    assert np.array_equal(tr.get_box_copy(), z["box_internal"])
+    assert np.array_equal(tr.get_rotation_matrix(), z["rotation"])
+    assert np.array_equal(tr.get_positions_copy(), z["pos_rotated"])
