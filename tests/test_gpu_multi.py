@@ -53,6 +53,23 @@ def test_single_process_all_devices_equals_one_device():
     assert np.array_equal(c1, oracle.counts(pos, bi, types, 0.0, 3.1, 60, 3, 5, primo=1, skip=2, ntypes=2))
 
 
+@needs2
+def test_neighbour_histogram_on_all_devices():
+    """agofrt_neighbour_hist shards (frame, atom tile) units over the devices and all-reduces the histogram"""
+    pos, bi, types = case()
+    one = cabi.Context([0])
+    one.pbc_wrap(pos, bi)
+    ref = oracle.neighbour_hist(pos, bi, types, 2.6, 1, 6, 2, ntypes=2)
+    for c in (one, cabi.Context("all")):
+        tr = cabi.DeviceTrajectory(c, pos.shape[1], 9, types, 2, pos.shape[0])
+        tr.upload(0, pos, bi)
+        h, st = tr.neighbour_hist(2.6, 1, 6, 2)
+        assert np.array_equal(h, ref)
+        assert st["world"] == c.ndev
+        tr.close()
+        c.close()
+
+
 WORKER = textwrap.dedent('''
     import json, os
     import numpy as np
