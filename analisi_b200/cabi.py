@@ -23,7 +23,7 @@ SYMBOLS = [
     "agofrt_ctx_create", "agofrt_ctx_destroy", "agofrt_ctx_ndev", "agofrt_comm_unique_id", "agofrt_comm_join",
     "agofrt_ctx_set_shard", "agofrt_shard_range", "agofrt_traj_create", "agofrt_traj_destroy", "agofrt_traj_upload", "agofrt_traj_upload_wrap", "agofrt_plan_retarget",
     "agofrt_traj_download_frame", "agofrt_pbc_wrap", "agofrt_traj_d2_all", "agofrt_traj_d2_pair", "agofrt_plan_create",
-    "agofrt_plan_destroy", "agofrt_plan_thresholds", "agofrt_block", "agofrt_neighbour_hist", "agofrt_fp64_peak",
+    "agofrt_plan_destroy", "agofrt_plan_thresholds", "agofrt_block", "agofrt_neighbour_hist", "agofrt_traj_set_cm", "agofrt_msd", "agofrt_fp64_peak",
 ]
 
 
@@ -93,6 +93,8 @@ def lib():
     L.agofrt_block.argtypes = [vp, C.c_size_t, C.c_uint, C.c_uint, C.c_uint, C.c_uint, C.c_uint, u64p, u64p,
                                C.POINTER(Stats)]
     L.agofrt_neighbour_hist.argtypes = [vp, C.c_double, C.c_size_t, C.c_uint, C.c_uint, u64p, C.POINTER(Stats)]
+    L.agofrt_traj_set_cm.argtypes = [vp, C.c_size_t, C.c_size_t, dp]
+    L.agofrt_msd.argtypes = [vp, C.c_size_t, C.c_uint, C.c_uint, C.c_uint, C.c_int, C.c_int, dp, C.POINTER(Stats)]
     L.agofrt_fp64_peak.argtypes = [vp, C.c_int, C.c_double, dp]
     for name in SYMBOLS:
         fn = getattr(L, name)
@@ -148,6 +150,8 @@ class PinnedArray:
 
 class Context:
     def __init__(self, devices=None):
+        import weakref
+        self._children = weakref.WeakSet()   # windows and plans: they must be destroyed before the context
         self._h = C.c_void_p()
         if devices is None:
             rc = lib().agofrt_ctx_create(C.byref(self._h), None, 0)
@@ -190,6 +194,8 @@ class Context:
 
     def close(self):
         if self._h:
+            for child in list(self._children):
+                child.close()
             lib().agofrt_ctx_destroy(self._h)
             self._h = None
 
@@ -211,6 +217,7 @@ class DeviceTrajectory:
         self._h = C.c_void_p()
         _check(lib().agofrt_traj_create(C.byref(self._h), ctx._h, self.natoms, self.box_stride,
                                         tid.ctypes.data_as(C.POINTER(C.c_int)), self.ntypes, int(max_frames)))
+        ctx._children.add(self)
 
     def upload(self, first_frame, pos, box_internal):
         assert pos.dtype == np.float64 and pos.flags.c_contiguous
@@ -246,6 +253,20 @@ class DeviceTrajectory:
                                            hist.ctypes.data_as(C.POINTER(C.c_uint64)), C.byref(st)))
         return hist, st.as_dict()
 
+    def set_cm(self, first_frame, cm):
+        cm = np.ascontiguousarray(cm, dtype=np.float64)
+        assert cm.ndim == 3 and cm.shape[1:] == (self.ntypes, 3)
+        _check(lib().agofrt_traj_set_cm(self._h, int(first_frame), cm.shape[0], _dp(cm)))
+
+    def msd(self, primo, ntimesteps, lmax=0, skip=1, cm_msd=False, cm_self=False):
+        """MSD<T>::calculate(primo) after reset(ntimesteps); returns (vdata [leff][f_cm][ntypes], stats)."""
+        leff = gofrt_leff(int(ntimesteps), int(lmax))
+        out = np.zeros((leff, 2 if cm_msd else 1, self.ntypes), dtype=np.float64)
+        st = Stats()
+        _check(lib().agofrt_msd(self._h, int(primo), int(ntimesteps), leff, int(skip), int(bool(cm_msd)), int(bool(cm_self)),
+                                _dp(out), C.byref(st)))
+        return out, st.as_dict()
+
     def d2_pair(self, i, j, frame_i, frame_j):
         out = np.zeros(4, dtype=np.float64)
         _check(lib().agofrt_traj_d2_pair(self._h, int(i), int(j), int(frame_i), int(frame_j), _dp(out)))
@@ -269,6 +290,7 @@ class Plan:
         self.nbin = int(nbin)
         self._h = C.c_void_p()
         _check(lib().agofrt_plan_create(C.byref(self._h), traj._h, float(rmin), float(rmax), self.nbin))
+        traj.ctx._children.add(self)
 
     def retarget(self, traj):
         _check(lib().agofrt_plan_retarget(self._h, traj._h))

@@ -156,6 +156,8 @@ struct agofrt_traj {
     bool has_inf = false;
     bool has_nan = false;   // NaN coordinates in the input (they are never in range, as in the reference)
     bool bad_box = false;
+    std::vector<double> cm;      // per-type centres of mass of the window frames [nframes][ntypes][3] (agofrt_traj_set_cm)
+    size_t cm_first = 0, cm_frames = 0;
     bool perm_valid = false;     // the permutation is kept over uploads and refreshed every kPermRefresh frames
     size_t perm_frame = 0;       // first frame of the window it was built from
     std::vector<int> slot_of;    // atom -> device slot (built on demand by agofrt_traj_d2_pair)
@@ -1493,6 +1495,116 @@ extern "C" int agofrt_neighbour_hist(agofrt_traj *t, double r, size_t tstart, un
         stats->launches = launches;
         stats->ndev_local = static_cast<uint32_t>(nloc);
         stats->world = static_cast<uint32_t>(world);
+    }
+    return AGOFRT_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// mean square displacement (MSD<T>::calculate)
+// ---------------------------------------------------------------------------------------------
+extern "C" int agofrt_traj_set_cm(agofrt_traj *t, size_t first_frame, size_t nframes, const double *cm) {
+    if (!t) return fail(AGOFRT_ERR_ARG, "traj is NULL");
+    if (nframes > 0 && !cm) return fail(AGOFRT_ERR_ARG, "cm is NULL");
+    t->cm.assign(cm, cm + nframes * static_cast<size_t>(t->ntypes) * 3);
+    t->cm_first = first_frame;
+    t->cm_frames = nframes;
+    return AGOFRT_OK;
+}
+
+extern "C" int agofrt_msd(agofrt_traj *t, size_t primo, unsigned ntimesteps, unsigned leff, unsigned skip, int cm_msd,
+                          int cm_self, double *out, agofrt_stats *stats) {
+    if (!t) return fail(AGOFRT_ERR_ARG, "traj is NULL");
+    if (skip < 1) skip = 1;
+    if (stats) memset(stats, 0, sizeof(*stats));
+    const int nt = t->ntypes, f_cm = cm_msd ? 2 : 1;
+    const size_t olen = static_cast<size_t>(leff) * f_cm * nt;
+    if (olen == 0) return AGOFRT_OK;
+    if (!out) return fail(AGOFRT_ERR_ARG, "out is NULL");
+    if (ntimesteps == 0) {
+        std::fill(out, out + olen, 0.0);
+        return AGOFRT_OK;
+    }
+    const size_t last = primo + static_cast<size_t>((ntimesteps - 1) / skip) * skip + (leff - 1);
+    if (primo < t->first_frame || last >= t->first_frame + t->nframes)
+        return fail(AGOFRT_ERR_WINDOW, "the calculation needs frames [%zu,%zu] but the device window holds [%zu,%zu)", primo, last,
+                    t->first_frame, t->first_frame + t->nframes);
+    const bool need_cm = cm_msd || cm_self;
+    if (need_cm && (t->cm_first != t->first_frame || t->cm_frames < t->nframes))
+        return fail(AGOFRT_ERR_ARG, "centres of mass of the uploaded window were not set (agofrt_traj_set_cm)");
+    // tiles of 256 real atoms, never across a type boundary (real atoms come first in every type group)
+    std::vector<int> type_count(nt, 0);
+    for (size_t a = 0; a < t->natoms; ++a) type_count[t->type_id[a]]++;
+    const int tile = msd_tile_atoms();
+    std::vector<int> tile_type, tile_start, tile_count;
+    for (int ty = 0; ty < nt; ++ty)
+        for (int o = 0; o < type_count[ty]; o += tile) {
+            tile_type.push_back(ty);
+            tile_start.push_back(t->type_start[ty] + o);
+            tile_count.push_back(std::min(tile, type_count[ty] - o));
+        }
+    const int ntiles = static_cast<int>(tile_type.size());
+    Dev &dv = t->ctx->devs[0];   // a bandwidth-bound O(N) pass per (lag, origin): one device is plenty
+    TrajDev &td = t->dev[0];
+    CU(cudaSetDevice(dv.id));
+    int *d_tiles = nullptr;
+    double *d_cm = nullptr, *d_partial = nullptr, *d_out = nullptr;
+    auto body = [&]() -> int {
+        CU(cudaMalloc(&d_tiles, (3 * static_cast<size_t>(std::max(ntiles, 1)) + nt) * sizeof(int)));
+        CU(cudaMalloc(&d_partial, std::max<size_t>(1, static_cast<size_t>(leff) * ntiles) * sizeof(double)));
+        CU(cudaMalloc(&d_out, olen * sizeof(double)));
+        if (need_cm) {
+            CU(cudaMalloc(&d_cm, std::max<size_t>(1, t->cm.size()) * sizeof(double)));
+            CU(cudaMemcpyAsync(d_cm, t->cm.data(), t->cm.size() * sizeof(double), cudaMemcpyHostToDevice, dv.stream));
+        }
+        if (ntiles > 0) {
+            CU(cudaMemcpyAsync(d_tiles, tile_type.data(), ntiles * sizeof(int), cudaMemcpyHostToDevice, dv.stream));
+            CU(cudaMemcpyAsync(d_tiles + ntiles, tile_start.data(), ntiles * sizeof(int), cudaMemcpyHostToDevice, dv.stream));
+            CU(cudaMemcpyAsync(d_tiles + 2 * ntiles, tile_count.data(), ntiles * sizeof(int), cudaMemcpyHostToDevice, dv.stream));
+        }
+        CU(cudaMemcpyAsync(d_tiles + 3 * static_cast<size_t>(std::max(ntiles, 1)), type_count.data(), nt * sizeof(int),
+                           cudaMemcpyHostToDevice, dv.stream));
+        MsdParams mp;
+        mp.pos = td.pos;
+        mp.cm = d_cm;
+        mp.tile_type = d_tiles;
+        mp.tile_start = d_tiles + ntiles;
+        mp.tile_count = d_tiles + 2 * ntiles;
+        mp.type_count = d_tiles + 3 * static_cast<size_t>(std::max(ntiles, 1));
+        mp.partial = d_partial;
+        mp.out = d_out;
+        mp.npad = t->npad;
+        mp.ntypes = nt;
+        mp.ntiles = ntiles;
+        mp.leff = static_cast<int>(leff);
+        mp.f0 = static_cast<int>(primo - t->first_frame);
+        mp.ntimesteps = static_cast<int>(ntimesteps);
+        mp.skip = static_cast<int>(skip);
+        mp.cm_msd = cm_msd ? 1 : 0;
+        mp.cm_self = cm_self ? 1 : 0;
+        CU(cudaEventRecord(dv.ev_k0, dv.stream));
+        CU(launch_msd(mp, dv.stream));
+        CU(cudaEventRecord(dv.ev_k1, dv.stream));
+        CU(cudaMemcpyAsync(out, d_out, olen * sizeof(double), cudaMemcpyDeviceToHost, dv.stream));
+        CU(cudaStreamSynchronize(dv.stream));
+        return AGOFRT_OK;
+    };
+    const int rc = body();
+    float ms = 0;
+    if (rc == AGOFRT_OK) cudaEventElapsedTime(&ms, dv.ev_k0, dv.ev_k1);
+    cudaFree(d_tiles);
+    cudaFree(d_cm);
+    cudaFree(d_partial);
+    cudaFree(d_out);
+    if (rc != AGOFRT_OK) return rc;
+    if (stats) {
+        const uint64_t norig = (ntimesteps + skip - 1) / skip;
+        stats->kernel_ms = ms;
+        stats->total_ms = ms;
+        stats->jobs = static_cast<uint64_t>(leff) * norig;
+        stats->pair_evals = stats->pair_evals_total = stats->jobs * t->natoms;   // displacement evaluations
+        stats->launches = 2;
+        stats->ndev_local = 1;
+        stats->world = 1;
     }
     return AGOFRT_OK;
 }

@@ -1145,6 +1145,91 @@ cudaError_t launch_neighbour_kernel(bool triclinic, bool fast, int grid, cudaStr
 int neighbour_tile_atoms() { return kNbThreads * kNbIPT; }
 
 // ---------------------------------------------------------------------------------------------
+// Mean square displacement (MSD<T>::calc_single_th, reference lib/src/msd.cpp:63-125): for lag t and type ty the
+// mean over origins and atoms of |x_i(o) - x_i(o+t)|^2 (optionally minus the displacement of the type's centre of
+// mass).  No minimum image: the reference works on the coordinates as stored.  HBM/L2-bound: 48 bytes read for
+// 9 FP64 operations per (atom, lag, origin).
+//   msd_partial_kernel: block = (tile of 256 slots of ONE type, lag); every thread walks the origins of its atom
+//                       (coalesced rows of the SoA window), then a fixed-order tree sum -> partial[lag][tile]
+//   msd_finish_kernel:  one thread per (lag, type): partials in tile order / count; and the centre-of-mass MSD as
+//                       the reference's own sequential running mean over the origins (bit-identical)
+// The atom part is a sum divided by a count where the reference keeps a running mean: equal to rounding
+// (tests: 1e-12 relative), deterministic from run to run.
+// ---------------------------------------------------------------------------------------------
+constexpr int kMsdThreads = 256;
+
+__global__ void __launch_bounds__(kMsdThreads) msd_partial_kernel(const MsdParams p) {
+    __shared__ double red[kMsdThreads];
+    const int tile = blockIdx.x, t = blockIdx.y, tid = threadIdx.x;
+    const int ty = p.tile_type[tile];
+    const int slot = p.tile_start[tile] + tid;
+    const bool live = tid < p.tile_count[tile];
+    double acc = 0.0;
+    if (live) {
+        for (int im = 0; im < p.ntimesteps; im += p.skip) {
+            const size_t fa = static_cast<size_t>(p.f0 + im), fb = fa + t;
+            const double *pa = p.pos + fa * 3 * p.npad, *pb = p.pos + fb * 3 * p.npad;
+            double dx = __dsub_rn(pa[slot], pb[slot]);
+            double dy = __dsub_rn(pa[p.npad + slot], pb[p.npad + slot]);
+            double dz = __dsub_rn(pa[2 * static_cast<size_t>(p.npad) + slot], pb[2 * static_cast<size_t>(p.npad) + slot]);
+            if (p.cm_self) {
+                const double *ca = p.cm + (fa * p.ntypes + ty) * 3, *cb = p.cm + (fb * p.ntypes + ty) * 3;
+                dx = __dsub_rn(dx, __dsub_rn(ca[0], cb[0]));
+                dy = __dsub_rn(dy, __dsub_rn(ca[1], cb[1]));
+                dz = __dsub_rn(dz, __dsub_rn(ca[2], cb[2]));
+            }
+            acc = __dadd_rn(acc, __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)));
+        }
+    }
+    red[tid] = acc;
+    __syncthreads();
+    for (int s = kMsdThreads / 2; s > 0; s >>= 1) {
+        if (tid < s) red[tid] = __dadd_rn(red[tid], red[tid + s]);
+        __syncthreads();
+    }
+    if (tid == 0) p.partial[static_cast<size_t>(t) * p.ntiles + tile] = red[0];
+}
+
+__global__ void msd_finish_kernel(const MsdParams p) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= p.leff * p.ntypes) return;
+    const int t = k / p.ntypes, ty = k % p.ntypes;
+    const int f_cm = p.cm_msd ? 2 : 1;
+    double sum = 0.0;
+    for (int tile = 0; tile < p.ntiles; ++tile)
+        if (p.tile_type[tile] == ty) sum = __dadd_rn(sum, p.partial[static_cast<size_t>(t) * p.ntiles + tile]);
+    const int norig = (p.ntimesteps + p.skip - 1) / p.skip;
+    const double count = static_cast<double>(static_cast<long long>(norig) * p.type_count[ty]);
+    p.out[(static_cast<size_t>(t) * f_cm) * p.ntypes + ty] = count > 0 ? __ddiv_rn(sum, count) : 0.0;
+    if (p.cm_msd) {
+        double v = 0.0;
+        unsigned long long cont = 0;
+        for (int im = 0; im < p.ntimesteps; im += p.skip) {
+            const size_t fa = static_cast<size_t>(p.f0 + im), fb = fa + t;
+            const double *ca = p.cm + (fa * p.ntypes + ty) * 3, *cb = p.cm + (fb * p.ntypes + ty) * 3;
+            const double dx = __dsub_rn(ca[0], cb[0]), dy = __dsub_rn(ca[1], cb[1]), dz = __dsub_rn(ca[2], cb[2]);
+            const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+            const double delta = __dsub_rn(d2, v);
+            v = __dadd_rn(v, __ddiv_rn(delta, static_cast<double>(++cont)));   // reference msd.cpp:111-117
+        }
+        p.out[(static_cast<size_t>(t) * f_cm + 1) * p.ntypes + ty] = v;
+    }
+}
+
+cudaError_t launch_msd(const MsdParams &p, cudaStream_t stream) {
+    if (p.leff <= 0 || p.ntypes <= 0) return cudaSuccess;
+    if (p.ntiles > 0) {
+        dim3 grid(p.ntiles, p.leff);
+        msd_partial_kernel<<<grid, kMsdThreads, 0, stream>>>(p);
+    }
+    const int n = p.leff * p.ntypes;
+    msd_finish_kernel<<<(n + 127) / 128, 128, 0, stream>>>(p);
+    return cudaGetLastError();
+}
+
+int msd_tile_atoms() { return kMsdThreads; }
+
+// ---------------------------------------------------------------------------------------------
 // FP64 issue-rate microbenchmark: 8 independent DFMA chains per thread
 // ---------------------------------------------------------------------------------------------
 constexpr int kPeakChains = 8;

@@ -113,6 +113,23 @@ struct NeighbourParams {
 cudaError_t launch_neighbour_kernel(bool triclinic, bool fast, int grid, cudaStream_t stream, const NeighbourParams &p);
 int neighbour_tile_atoms();
 
+// mean square displacement (MSD)
+struct MsdParams {
+    const double *pos;        // [frames][3][npad]
+    const double *cm;         // [frames][ntypes][3] (cm_self / cm_msd), else nullptr
+    const int *tile_type;     // [ntiles]
+    const int *tile_start;    // [ntiles] first slot
+    const int *tile_count;    // [ntiles] real atoms in the tile (<= 256)
+    const int *type_count;    // [ntypes] atoms of each type
+    double *partial;          // [leff][ntiles]
+    double *out;              // [leff][f_cm][ntypes]
+    int npad, ntypes, ntiles, leff;
+    int f0, ntimesteps, skip; // window-relative first origin, averaged steps, origin stride
+    int cm_msd, cm_self;
+};
+cudaError_t launch_msd(const MsdParams &p, cudaStream_t stream);
+int msd_tile_atoms();
+
 // MODE_SAFE validation: bad += number of probes whose unflagged float guess differs from expected[]
 cudaError_t launch_validate_safe(const double *probes, const int *expected, int n, float inv_dr, float c0h, float lim,
                                  float qmax, int nbin, int glo, unsigned int *bad, cudaStream_t stream);

@@ -20,6 +20,7 @@
 #include "analisi/blockaverage.h"
 #include "analisi/gofrt.h"
 #include "analisi/istogrammaatomiraggio.h"
+#include "analisi/msd.h"
 #include "analisi/trajectory.h"
 
 namespace {
@@ -31,6 +32,7 @@ struct Options {
     int stop_acf = 0, skip = 1, every = 1, blocknumber = 20, nthreads = 2;
     bool dump = false, help = false, edges = false;
     double neighbour_r = 0.0;
+    bool msd = false, msd_cm = false, msd_self = false;
 };
 
 const char *kUsage =
@@ -48,6 +50,9 @@ const char *kUsage =
     "  -B [ --blocknumber ] arg (=20) number of blocks for averages and variances (and for reading the trajectory)\n"
     "  -N [ --thread ] arg           accepted for compatibility (the GPUs own the parallelism)\n"
     "  -d [ --dump-block ]           append the histogram of each block to ./gofrt.dump\n"
+    "  -q [ --mean-square-displacement ]     compute atomic mean square displacement\n"
+    "  -Q [ --mean-square-displacement-cm ]  ... and the square displacement of the centre of mass of each atomic type\n"
+    "  --mean-square-displacement-self       ... in the reference system of the centre of mass of the atom's type\n"
     "  --neighbour arg (=0)          calculate the histogram of the neighbours up to the specified distance\n"
     "  --edge-pairs                  (addition) report on stderr, per block, the pairs within 1 ulp of a bin edge\n"
     "Environment: ANALISI_DEVICES=0,1,... selects the GPUs (default: all visible).\n";
@@ -59,13 +64,14 @@ struct Spec {
 };
 const Spec kSpecs[] = {{'i', "input", 1},   {'h', "help", 0},        {'g', "gofrt", 1},  {'F', "factors", -1},
                        {'S', "stop", 1},    {'s', "skip", 1},        {'e', "every", 1},  {'B', "blocknumber", 1},
-                       {'N', "thread", 1},  {'d', "dump-block", 0}, {'\1', "edge-pairs", 0}, {'\2', "neighbour", 1}};
+                       {'N', "thread", 1},  {'d', "dump-block", 0}, {'\1', "edge-pairs", 0}, {'\2', "neighbour", 1},
+                       {'q', "mean-square-displacement", 0}, {'Q', "mean-square-displacement-cm", 0},
+                       {'\3', "mean-square-displacement-self", 0}};
 
 // options of the reference that select or tune calculations this front end does not provide
-const char *kForeign = "lVvMHaDzqQukYIEACf";
+const char *kForeign = "lVvMHaDzukYIEACf";
 const char *kForeignLong[] = {"loginput", "vibrational-spectrum", "velocity-histogram", "histogram-minmax",
-                              "heat-transport-coefficient", "headers", "dt", "covariance", "mean-square-displacement",
-                              "mean-square-displacement-cm", "mean-square-displacement-self", "subtract-mean",
+                              "heat-transport-coefficient", "headers", "dt", "covariance", "subtract-mean",
                               "subtract-mean-start", "subBlock", "kk", "kk-range", "binary-convert",
                               "binary-convert-gromacs", "spherical-harmonics-correlation", "buffer-size", "lt",
                               "cut", "write-mass-currents", "fpe", "test-debug"};
@@ -111,6 +117,9 @@ void assign(Options &o, const Spec &sp, const std::vector<std::string> &vals) {
         case 'd': o.dump = true; break;
         case '\1': o.edges = true; break;
         case '\2': o.neighbour_r = to_double(vals[0], sp.longname); break;
+        case 'q': o.msd = true; break;
+        case 'Q': o.msd_cm = true; break;
+        case '\3': o.msd_self = true; break;
     }
 }
 
@@ -128,7 +137,7 @@ Options parse(int argc, char **argv) {
             if (!sp) {
                 for (const char *f : kForeignLong)
                     if (name == f)
-                        throw std::runtime_error("option '--" + name + "' belongs to a calculation this build does not provide: only g(r,t) (-g) runs on the GPU\n");
+                        throw std::runtime_error("option '--" + name + "' belongs to a calculation this build does not provide (it has g(r,t), the neighbour histogram and the MSD)\n");
                 throw std::runtime_error("unrecognised option '" + a + "'");
             }
             if (eq != std::string::npos) vals.push_back(a.substr(eq + 1));
@@ -138,7 +147,7 @@ Options parse(int argc, char **argv) {
                 if (a[1] == s.shortname) sp = &s;
             if (!sp) {
                 if (std::strchr(kForeign, a[1]))
-                    throw std::runtime_error("option '" + a + "' belongs to a calculation this build does not provide: only g(r,t) (-g) runs on the GPU\n");
+                    throw std::runtime_error("option '" + a + "' belongs to a calculation this build does not provide (it has g(r,t), the neighbour histogram and the MSD)\n");
                 throw std::runtime_error("unrecognised option '" + a + "'");
             }
             if (a.size() > 2) {
@@ -217,6 +226,25 @@ int main(int argc, char **argv) {
                 }
                 std::cout << "\n\n";
             }
+        } else if (o.msd || o.msd_cm || o.msd_self) {
+            // reference analisi/main.cpp:520-549
+            std::cerr << "Mean square displacement calculation ";
+            const unsigned int f_cm = o.msd_cm ? 2 : 1;
+            if (o.msd_cm)
+                std::cerr << "of the center of mass and of the atoms is beginning...\n";
+            else
+                std::cerr << " of the atoms is beginning...\n"
+                          << (o.msd_self ? "In the reference system of each atomic type center of mass...\n" : "In the cell coordinate system...\n");
+            Trajectory test(o.input);   // unwrapped, velocities (hence centres of mass) loaded, as in the reference
+            BlockAverage<MSD<Trajectory>, unsigned int, unsigned int, unsigned int, bool, bool, bool> Msd(&test, static_cast<unsigned int>(o.blocknumber));
+            Msd.calculate(static_cast<unsigned int>(o.skip), static_cast<unsigned int>(o.stop_acf), static_cast<unsigned int>(o.nthreads),
+                          o.msd_cm, o.msd_self, o.dump);
+            const unsigned int nt = static_cast<unsigned int>(test.get_ntypes());
+            for (unsigned int i = 0; i < Msd.media()->lunghezza() / nt / f_cm; i++) {
+                for (unsigned int j = 0; j < nt * f_cm; j++)
+                    std::cout << Msd.media()->elemento(i * nt * f_cm + j) << " " << Msd.varianza()->elemento(i * nt * f_cm + j) << " ";
+                std::cout << "\n";
+            }
         } else if (o.neighbour_r > 0) {
             // reference analisi/main.cpp:620-642: histogram of the number of neighbours within r, per type
             std::cerr << "Beginning of calculation of neighbour histogram\n";
@@ -243,7 +271,7 @@ int main(int argc, char **argv) {
                 std::cout << "\n\n";
             }
         } else {
-            throw std::runtime_error("Nothing to do: this build provides the g(r,t) calculation only (use -g <nbin> -F <rmin> <rmax>).\n");
+            throw std::runtime_error("Nothing to do: choose -g <nbin> -F <rmin> <rmax>, --neighbour <r>, -q or -Q.\n");
         }
     } catch (const std::exception &e) {
         std::cerr << e.what() << "\n";

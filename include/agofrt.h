@@ -183,6 +183,17 @@ AGOFRT_API int agofrt_block(agofrt_plan *plan, size_t primo, unsigned ntimesteps
 AGOFRT_API int agofrt_neighbour_hist(agofrt_traj *traj, double r, size_t tstart, unsigned ntimesteps, unsigned skip,
                                      uint64_t *hist_inout, agofrt_stats *stats);
 
+/* Mean square displacement: MSD<T>::calculate(primo) after reset(ntimesteps) (lib/src/msd.cpp:41-125; `analisi -q/-Q`,
+ * pyanalisi.MeanSquareDisplacement).  out is [leff][f_cm][ntypes] with f_cm = cm_msd ? 2 : 1: row 0 the per-type MSD
+ * of the atoms over the origins primo, primo+skip, ... < primo+ntimesteps (in the frame of the type's centre of mass
+ * when cm_self), row 1 the MSD of the per-type centres of mass.  The coordinates are used as uploaded (no minimum
+ * image, as in the reference); cm_msd / cm_self need agofrt_traj_set_cm for the uploaded window
+ * (cm [nframes][ntypes][3] = BaseTrajectory::positions_cm).  The atom rows are a sum / count where the reference keeps
+ * a running mean (equal to rounding); the centre-of-mass rows replay the reference's running mean exactly. */
+AGOFRT_API int agofrt_traj_set_cm(agofrt_traj *traj, size_t first_frame, size_t nframes, const double *cm);
+AGOFRT_API int agofrt_msd(agofrt_traj *traj, size_t primo, unsigned ntimesteps, unsigned leff, unsigned skip,
+                          int cm_msd, int cm_self, double *out, agofrt_stats *stats);
+
 /* ---- measurement --------------------------------------------------------------------------- */
 /* Sustained FP64 FMA issue rate of one device (DFMA chains, CUDA events): the roofline
  * denominator of SURVEY.md section 8(d).  Runs for about `seconds`. */

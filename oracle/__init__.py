@@ -13,6 +13,8 @@ from .oracle import (  # noqa: F401
     vdata,
     mediavar,
     neighbour_hist,
+    msd,
+    cm_positions,
     min_image,
     d2_all,
     pbc_wrap,

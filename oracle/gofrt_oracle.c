@@ -409,3 +409,64 @@ int gofrt_oracle_neighbour_hist(const gofrt_oracle_traj *tr, double r, size_t ts
     free(th);
     return GOFRT_ORACLE_OK;
 }
+
+
+/* ---- lib/src/trajectory_numpy.cpp:201-223 ----------------------------------------------------- */
+void gofrt_oracle_cm(const double *pos_frame, const int *type_id, size_t natoms, int ntypes, double *cm_out) {
+    unsigned *cont = (unsigned *)calloc((size_t)ntypes, sizeof(unsigned));
+    for (int k = 0; k < 3 * ntypes; ++k) cm_out[k] = 0.0;
+    for (size_t a = 0; a < natoms; ++a) {
+        const int ty = type_id[a];
+        cont[ty]++;
+        for (int c = 0; c < 3; ++c) cm_out[3 * ty + c] += (pos_frame[3 * a + c] - cm_out[3 * ty + c]) / (double)cont[ty];
+    }
+    free(cont);
+}
+
+/* ---- lib/src/msd.cpp:41-125 --------------------------------------------------------------------
+ * pow(x,2) is x*x exactly (one rounding); the sums are formed left to right as written there. */
+int gofrt_oracle_msd(const gofrt_oracle_traj *tr, const double *cm, size_t primo, unsigned ntimesteps, unsigned lmax,
+                     unsigned skip, int cm_msd, int cm_self, double *out) {
+    if (!tr || !out || tr->ntypes <= 0) return GOFRT_ORACLE_BAD_ARG;
+    if ((cm_msd || cm_self) && !cm) return GOFRT_ORACLE_BAD_ARG;
+    if (skip < 1) skip = 1;
+    const unsigned leff = (ntimesteps < lmax || lmax == 0) ? ntimesteps : lmax; /* msd.cpp:42 */
+    const size_t N = tr->natoms, nt = (size_t)tr->ntypes, f_cm = cm_msd ? 2 : 1;
+    if ((size_t)leff + ntimesteps + primo > tr->total_frames) return GOFRT_ORACLE_TOO_SHORT; /* msd.cpp:54 */
+    if (leff == 0) return GOFRT_ORACLE_OK;
+    if (primo < tr->first_frame || primo + (size_t)(ntimesteps - 1) / skip * skip + (leff - 1) >= tr->first_frame + tr->nframes)
+        return GOFRT_ORACLE_TOO_SHORT;
+    uint64_t *cont = (uint64_t *)calloc(nt * f_cm, sizeof(uint64_t));
+    for (size_t t = 0; t < leff; ++t) {
+        double *v = out + nt * t * f_cm;
+        for (size_t i = 0; i < nt * f_cm; ++i) {
+            v[i] = 0.0;
+            cont[i] = 0;
+        }
+        for (size_t im = 0; im < ntimesteps; im += skip) {
+            const size_t fa = primo + im - tr->first_frame, fb = fa + t;
+            const double *pa = tr->pos + fa * N * 3, *pb = tr->pos + fb * N * 3;
+            const double *ca = cm ? cm + fa * nt * 3 : NULL, *cb = cm ? cm + fb * nt * 3 : NULL;
+            for (size_t a = 0; a < N; ++a) {
+                const size_t ty = (size_t)tr->type_id[a];
+                double d[3];
+                for (int c = 0; c < 3; ++c) {
+                    d[c] = pa[3 * a + c] - pb[3 * a + c];
+                    if (cm_self) d[c] = d[c] - (ca[3 * ty + c] - cb[3 * ty + c]);
+                }
+                const double delta = (d[0] * d[0] + d[1] * d[1] + d[2] * d[2]) - v[ty];
+                v[ty] += delta / (double)(++cont[ty]);
+            }
+            if (cm_msd) {
+                for (size_t ty = 0; ty < nt; ++ty) {
+                    double d[3];
+                    for (int c = 0; c < 3; ++c) d[c] = ca[3 * ty + c] - cb[3 * ty + c];
+                    const double delta = (d[0] * d[0] + d[1] * d[1] + d[2] * d[2]) - v[nt + ty];
+                    v[nt + ty] += delta / (double)(++cont[nt + ty]);
+                }
+            }
+        }
+    }
+    free(cont);
+    return GOFRT_ORACLE_OK;
+}

@@ -100,6 +100,18 @@ void gofrt_oracle_mediavar(const double *blocks, unsigned n_b, size_t len, doubl
 int gofrt_oracle_neighbour_hist(const gofrt_oracle_traj *tr, double r, size_t tstart, unsigned ntimesteps,
                                 unsigned skip, uint64_t *hist, unsigned nthreads);
 
+/* Scope table rank 3: mean square displacement, MSD<T,FPE>::calc_single_th (lib/src/msd.cpp:63-125) driven by
+ * CalculateMultiThread (PARALLEL_SPLIT_TIME: lags are split over threads, every lag is computed by ONE thread in
+ * the order origins-then-atoms, so the result does not depend on the thread count).
+ *   cm [nframes][ntypes][3]: per-type centres of mass of the window frames (positions_cm), needed when cm_msd or
+ *                            cm_self is set (may be NULL otherwise)
+ *   out [leff][f_cm][ntypes], f_cm = cm_msd ? 2 : 1: the running means vdata[t][..] exactly as the reference forms them
+ * Per-type centre of mass of one frame = running mean over the atoms in index order
+ * (lib/src/trajectory_numpy.cpp:201-223; lib/src/trajectory.cpp:648-657 uses the file order of the atoms). */
+void gofrt_oracle_cm(const double *pos_frame, const int *type_id, size_t natoms, int ntypes, double *cm_out);
+int gofrt_oracle_msd(const gofrt_oracle_traj *tr, const double *cm, size_t primo, unsigned ntimesteps, unsigned lmax,
+                     unsigned skip, int cm_msd, int cm_self, double *out);
+
 #ifdef __cplusplus
 }
 #endif

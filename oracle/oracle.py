@@ -85,6 +85,9 @@ def _load():
     dp = C.POINTER(C.c_double)
     lib.gofrt_oracle_neighbour_hist.argtypes = [C.c_void_p, C.c_double, C.c_size_t, C.c_uint, C.c_uint,
                                                 C.POINTER(C.c_uint64), C.c_uint]
+    lib.gofrt_oracle_cm.argtypes = [dp, C.POINTER(C.c_int), C.c_size_t, C.c_int, dp]
+    lib.gofrt_oracle_cm.restype = None
+    lib.gofrt_oracle_msd.argtypes = [C.c_void_p, dp, C.c_size_t, C.c_uint, C.c_uint, C.c_uint, C.c_int, C.c_int, dp]
     lib.gofrt_oracle_lammps_to_internal.argtypes = [dp]
     lib.gofrt_oracle_internal_to_lammps.argtypes = [dp]
     lib.gofrt_oracle_min_image.argtypes = [dp, dp, dp, C.c_int]
@@ -203,6 +206,35 @@ def neighbour_hist(pos, box_internal, type_id, r, tstart, ntimesteps, skip=1, nt
     _check(rc)
     del keep
     return hist
+
+
+def cm_positions(pos, type_id, ntypes):
+    """Per-type centres of mass [F][ntypes][3], running mean in atom order (trajectory_numpy.cpp:201-223)."""
+    lib = _load()
+    pos = np.ascontiguousarray(pos, dtype=np.float64)
+    tid = np.ascontiguousarray(type_id, dtype=np.int32)
+    out = np.zeros((pos.shape[0], ntypes, 3), dtype=np.float64)
+    for f in range(pos.shape[0]):
+        lib.gofrt_oracle_cm(_dp(pos[f]), tid.ctypes.data_as(C.POINTER(C.c_int)), pos.shape[1], ntypes, _dp(out[f]))
+    return out
+
+
+def msd(pos, type_id, ntimesteps, lmax=0, primo=0, skip=1, cm_msd=False, cm_self=False, ntypes=None, cm=None,
+        first_frame=0, total_frames=None):
+    """MSD<T>::calc_single_th over all lags (lib/src/msd.cpp:63-125): returns vdata [leff][f_cm][ntypes]."""
+    lib = _load()
+    box = np.tile([0.0, 0.0, 0.0, 1.0, 1.0, 1.0], (pos.shape[0], 1))   # not used by the MSD
+    t, keep, ntypes = _traj(pos, box, type_id, ntypes, first_frame, total_frames)
+    if cm is None and (cm_msd or cm_self):
+        cm = cm_positions(pos, type_id, ntypes)
+    le = ntimesteps if (ntimesteps < lmax or lmax == 0) else lmax
+    out = np.zeros((le, 2 if cm_msd else 1, ntypes), dtype=np.float64)
+    cmp_ = _dp(np.ascontiguousarray(cm)) if cm is not None else None
+    rc = lib.gofrt_oracle_msd(C.byref(t), cmp_, int(primo), int(ntimesteps), int(lmax), int(skip), int(bool(cm_msd)),
+                              int(bool(cm_self)), _dp(out))
+    _check(rc)
+    del keep
+    return out
 
 
 def min_image(delta, box_row):

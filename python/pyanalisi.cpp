@@ -20,6 +20,7 @@
 #include "analisi/blockaverage.h"
 #include "analisi/gofrt.h"
 #include "analisi/istogrammaatomiraggio.h"
+#include "analisi/msd.h"
 #include "analisi/trajectory.h"
 #include "analisi/trajectory_numpy.h"
 
@@ -162,6 +163,23 @@ void define_block_average(py::module &m, const std::string &suffix) {
         });
 }
 
+// MeanSquareDisplacement / MeanSquareDisplacement_lammps (reference pyanalisi/src/pyanalisi.cpp:123-151)
+template <class TR>
+void define_msd(py::module &m, const std::string &suffix) {
+    using M = MSD<TR>;
+    py::class_<M>(m, ("MeanSquareDisplacement" + suffix).c_str(), py::buffer_protocol(), py::module_local())
+        .def(py::init<TR *, unsigned int, unsigned int, unsigned int, bool, bool, bool>(), py::keep_alive<1, 2>(),
+             "Trajectory instance, time skip for the average computation, max time, number of threads (ignored), calculate "
+             "center of mass MSD, calculate the atomic msd in the center of mass reference system of each specie, debug flag")
+        .def("reset", &M::reset)
+        .def("getNumberOfExtraTimestepsNeeded", &M::nExtraTimesteps)
+        .def("calculate", &M::calculate, py::call_guard<py::gil_scoped_release>())
+        .def_buffer([](M &g) -> py::buffer_info {
+            return py::buffer_info(g.access_vdata(), sizeof(double), py::format_descriptor<double>::format(),
+                                   static_cast<ssize_t>(g.get_shape().size()), g.get_shape(), g.get_stride());
+        });
+}
+
 // Addition: the neighbour-count histogram (the reference only reaches it from its CLI, --neighbour)
 template <class TR>
 void define_neighbour_hist(py::module &m, const std::string &suffix) {
@@ -233,6 +251,8 @@ PYBIND11_MODULE(pyanalisi, m) {
 
     define_gofrt<Trajectory>(m, "_lammps");
     define_gofrt<Trajectory_numpy>(m, "");
+    define_msd<Trajectory>(m, "_lammps");
+    define_msd<Trajectory_numpy>(m, "");
     define_neighbour_hist<Trajectory>(m, "_lammps");
     define_neighbour_hist<Trajectory_numpy>(m, "");
     define_block_average<Trajectory>(m, "_lammps");

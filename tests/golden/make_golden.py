@@ -240,7 +240,8 @@ def cli_golden_text():
     analisi -i tests/data/lammps2020.bin -g 100 -F 0.0 4.0 -S {1,10} -s 8  (20 blocks, mean and variance)."""
     import shutil
     # ... and the neighbour-count histogram of the next scope row (tests/test_cli.sh:35: --neighbour 10)
-    for name in ("pair_corr_no_t", "pair_corr_t", "neighbours"):
+    # ... and the mean square displacement (tests/test_cli.sh:24-27: -Q; -Q -s 10 -S 50; -q -s 10 -S 50; -Q --mean-square-displacement-self)
+    for name in ("pair_corr_no_t", "pair_corr_t", "neighbours", "MSD_normal_full", "MSD_normal", "MSD_cm", "MSD_cm_reference"):
         shutil.copyfile(os.path.join(REF, "tests/data/cli", name), os.path.join(HERE, "cli_" + name + ".txt"))
 
 

@@ -391,3 +391,39 @@ def test_cli_neighbour_reference_golden_text(host, tmp_path):
         rows += ["%d %d" % kv for kv in sorted(h.get_hist(ty).items())]
         rows += ["", ""]
     assert ("\n".join(rows) + "\n").rstrip("\n") == gold.rstrip("\n")
+
+
+@pytest.mark.parametrize("name,args", [("MSD_normal_full", ["-Q"]), ("MSD_normal", ["-Q", "-s", "10", "-S", "50"]),
+                                       ("MSD_cm", ["-q", "-s", "10", "-S", "50"]),
+                                       ("MSD_cm_reference", ["-Q", "--mean-square-displacement-self"])])
+def test_cli_msd_reference_golden_text(host, tmp_path, name, args):
+    """reference tests/test_cli.sh:24-27 verbatim: analisi -i lammps2020.bin -Q | -Q -s 10 -S 50 | -q -s 10 -S 50 |
+    -Q --mean-square-displacement-self, stdout against the reference's golden text."""
+    cli, _ = host
+    path = os.path.join(REFDATA, "lammps2020.bin")
+    if not os.path.exists(path):
+        pytest.skip("tests/_refdata/lammps2020.bin not present")
+    r = subprocess.run([cli, "-i", path] + args, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, cwd=str(tmp_path),
+                       timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    gold = open(os.path.join(GOLDEN, "cli_%s.txt" % name)).read()
+    assert r.stdout.rstrip("\n") == gold.rstrip("\n")
+
+
+def test_pyanalisi_msd(host):
+    """pyanalisi.MeanSquareDisplacement(traj, skip, tmax, nthreads, cm_msd, cm_self, debug) as the reference's
+    Analysis.compute_msd calls it (pyanalisi/analysis.py:91-98) against the oracle"""
+    _, pa = host
+    pos, box, types = synth.small_case(96, (6, 6, 5), 1.1, 2, True, 40)
+    tr = pa.Trajectory(pos, np.zeros_like(pos), types.astype(np.int32), box, pa.BoxFormat.LammpsTriclinic, False, False)
+    msd = pa.MeanSquareDisplacement(tr, 10, 12, 4, True, False, False)
+    msd.reset(20)
+    msd.calculate(3)
+    v = np.array(msd, copy=True)
+    assert v.shape == (12, 2, 2)
+    ref = oracle.msd(pos, types, 20, 12, primo=3, skip=10, cm_msd=True, ntypes=2)
+    assert (np.abs(v[:, 0] - ref[:, 0]) <= 1e-12 * np.maximum(np.abs(ref[:, 0]), 1e-300)).all()
+    assert np.array_equal(v[:, 1], ref[:, 1])
+    with pytest.raises(RuntimeError, match="trajectory is too short"):
+        msd.reset(30)
+        msd.calculate(5)

@@ -410,3 +410,29 @@ def test_neighbour_histogram_vs_oracle(ctx, triclinic, ntypes, wrap):
     with pytest.raises(cabi.AgofrtError):
         tr.neighbour_hist(r, 5, 9, 1)                 # runs past the uploaded window
     tr.close()
+
+
+@pytest.mark.parametrize("cm_msd,cm_self,lmax,skip", [(False, False, 0, 1), (True, False, 5, 3), (True, True, 4, 2), (False, True, 6, 1)])
+def test_msd_vs_oracle(ctx, cm_msd, cm_self, lmax, skip):
+    """scope row 8f-3: MSD<T>::calculate through agofrt_msd against the oracle -- the atom rows within 1e-12 relative
+    (a sum / count on the device, a running mean in the reference), the centre-of-mass rows bit for bit."""
+    pos, box, types = synth.small_case(95, (9, 8, 7), 1.1, 3, False, 32)   # 504 atoms in 3 types: several tiles per type
+    bi = synth.lammps_rows_to_internal(box)
+    pos = np.ascontiguousarray(pos)            # unwrapped, as the MSD wants them
+    tr = cabi.DeviceTrajectory(ctx, pos.shape[1], 6, types, 3, pos.shape[0])
+    tr.upload(0, pos, bi)
+    cm = oracle.cm_positions(pos, types, 3)
+    tr.set_cm(0, cm)
+    nts, primo = 14, 3
+    v, st = tr.msd(primo, nts, lmax, skip, cm_msd, cm_self)
+    ref = oracle.msd(pos, types, nts, lmax, primo=primo, skip=skip, cm_msd=cm_msd, cm_self=cm_self, ntypes=3, cm=cm)
+    assert v.shape == ref.shape
+    assert np.array_equal(v[0, 0], np.zeros(3)) or cm_self is False or np.abs(v[0, 0]).max() < 1e-20
+    scale = np.maximum(np.abs(ref[:, 0]), 1e-300)
+    assert (np.abs(v[:, 0] - ref[:, 0]) <= 1e-12 * scale).all()
+    if cm_msd:
+        assert np.array_equal(v[:, 1], ref[:, 1])
+    assert st["jobs"] == v.shape[0] * ((nts + skip - 1) // skip)
+    with pytest.raises(cabi.AgofrtError):
+        tr.msd(20, 14, 0, 1)   # needs frames beyond the window
+    tr.close()

@@ -176,3 +176,37 @@ def test_neighbour_histogram_cli_golden():
     assert hist.sum() == 2 * 4000 * n_b * s
     gold = open(os.path.join(GOLDEN, "cli_neighbours.txt")).read()
     assert neighbour_text(hist).rstrip("\n") == gold.rstrip("\n")
+
+
+MSD_CASES = [("MSD_normal_full", 1, 0, True, False), ("MSD_normal", 10, 50, True, False), ("MSD_cm", 10, 50, False, False),
+             ("MSD_cm_reference", 1, 0, True, True)]   # name, -s, -S, -Q (centre-of-mass rows), --mean-square-displacement-self
+
+
+def msd_text(mean, var):
+    # the CLI's printing loop, reference analisi/main.cpp:541-546: "mean var " per column, row per lag
+    return ["".join("%s %s " % (_g(m), _g(v)) for m, v in zip(mean[i].ravel(), var[i].ravel())) for i in range(mean.shape[0])]
+
+
+@pytest.mark.parametrize("name,skip,lmax,cm_msd,cm_self", MSD_CASES)
+def test_msd_cli_golden(name, skip, lmax, cm_msd, cm_self):
+    """reference tests/test_cli.sh:24-27 on lammps2020.bin (unwrapped, 20 blocks): the oracle's restatement of
+    MSD<T>::calc_single_th + MediaVar reproduces the reference's golden text for all four flag combinations."""
+    m = oracle.load_ref()
+    path = os.path.join(REFERENCE, "tests/data/lammps2020.bin")
+    if m is None or not os.path.exists(path):
+        pytest.skip("reference tree not available")
+    from conftest import GOLDEN
+    tr = m.Traj(path)
+    tr.setWrapPbc(False)
+    nts, n_b = tr.get_ntimesteps(), 20
+    nextra = oracle.nextra(nts, n_b, lmax)
+    s = (nts - nextra) // n_b
+    tr.setAccessWindowSize(s + nextra)
+    blocks = []
+    for ib in range(n_b):
+        tr.setAccessStart(ib * s)
+        blocks.append(oracle.msd(tr.get_positions_copy(), tr.get_type_ids(), s, lmax, primo=ib * s, skip=skip, cm_msd=cm_msd,
+                                 cm_self=cm_self, ntypes=int(tr.get_ntypes()), first_frame=ib * s, total_frames=nts))
+    mean, var = oracle.mediavar(np.array(blocks))
+    gold = open(os.path.join(GOLDEN, "cli_%s.txt" % name)).read().rstrip("\n").split("\n")
+    assert msd_text(mean, var) == gold
