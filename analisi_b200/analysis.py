@@ -2,6 +2,7 @@
 (``python/pyanalisi*.so``): the counterparts of the reference's pure-python wrappers
 
     Analysis.max_l / Analysis.hist2gofr / Analysis.compute_gofr   (pyanalisi/analysis.py:77-144)
+    Analysis.compute_msd                                           (pyanalisi/analysis.py:91-98)
     analyze_gofr                                                   (pyanalisi/common.py:186-204)
 
 with the same argument meaning.  Nothing here computes pairs: ``Gofrt.calculate`` runs on the GPU.
@@ -78,3 +79,15 @@ def analyze_gofr(traj, start, stop, startr, endr, nbin, tmax=1, nthreads=1, tski
     """The raw-histogram variant (common.py:186-204)."""
     return compute_gofr(traj, startr, endr, nbin, start=start, stop=stop, tmax=tmax, tskip=tskip, n_segments=n_segments,
                         nthreads=nthreads, return_histogram=True)
+
+
+def compute_msd(traj, start=0, stop=-1, tmax=0, tskip_msd=10, center_of_mass_MSD=True, center_of_mass_frame=False, nthreads=1):
+    """Mean square displacement per type (and of the per-type centres of mass) of an UNWRAPPED trajectory
+    (analysis.py:91-98): array (tmax, 2 if center_of_mass_MSD else 1, ntypes)."""
+    if stop < 0:
+        stop = traj.get_nloaded_timesteps()
+    tmax, n_ave = max_l(start, stop, tmax)
+    msd = wrapper_name(traj, "MeanSquareDisplacement")(traj, tskip_msd, tmax, nthreads, center_of_mass_MSD, center_of_mass_frame, False)
+    msd.reset(n_ave)
+    msd.calculate(start)
+    return np.array(msd, copy=True)

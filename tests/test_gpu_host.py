@@ -427,3 +427,7 @@ def test_pyanalisi_msd(host):
     with pytest.raises(RuntimeError, match="trajectory is too short"):
         msd.reset(30)
         msd.calculate(5)
+    from analisi_b200 import analysis
+    w = analysis.compute_msd(tr, start=2, stop=40, tmax=8, tskip_msd=5)
+    ref2 = oracle.msd(pos, types, 30, 8, primo=2, skip=5, cm_msd=True, ntypes=2)
+    assert w.shape == (8, 2, 2) and np.allclose(w, ref2, rtol=1e-12, atol=0) and np.array_equal(w[:, 1], ref2[:, 1])
