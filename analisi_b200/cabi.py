@@ -15,6 +15,8 @@ LIB_PATH = os.environ.get("AGOFRT_LIB", os.path.join(_HERE, "libagofrt.so"))  # 
 OK = 0
 ERR_ARG, ERR_CUDA, ERR_WINDOW, ERR_NCCL, ERR_NONFINITE, ERR_TOO_LARGE, ERR_INTERNAL = -1, -2, -3, -4, -5, -6, -7
 OPT_EDGES, OPT_FORCE_GENERAL, OPT_NO_AGGREGATE, OPT_AGGREGATE, OPT_NO_SAFE, OPT_DENSE, OPT_SPARSE, OPT_NO_UBOX = 1, 2, 4, 8, 16, 32, 64, 128
+OPT_NO_SMALL, OPT_ON_DEVICE = 256, 512
+MODE_BIT_SMALL = 1 << 8   # Stats.kernel_modes: the small-system kernel ran
 COMM_ID_BYTES = 128
 
 # every symbol include/agofrt.h declares (tests check the library exports all of them)
@@ -24,6 +26,8 @@ SYMBOLS = [
     "agofrt_ctx_set_shard", "agofrt_shard_range", "agofrt_traj_create", "agofrt_traj_destroy", "agofrt_traj_upload", "agofrt_traj_upload_wrap", "agofrt_plan_retarget",
     "agofrt_traj_download_frame", "agofrt_pbc_wrap", "agofrt_traj_d2_all", "agofrt_traj_d2_pair", "agofrt_plan_create",
     "agofrt_plan_destroy", "agofrt_plan_thresholds", "agofrt_block", "agofrt_neighbour_hist", "agofrt_traj_set_cm", "agofrt_msd", "agofrt_fp64_peak",
+    "agofrt_blockavg_create", "agofrt_blockavg_destroy", "agofrt_blockavg_begin", "agofrt_blockavg_push", "agofrt_blockavg_end",
+    "agofrt_plan_last_counts",
 ]
 
 
@@ -96,6 +100,12 @@ def lib():
     L.agofrt_traj_set_cm.argtypes = [vp, C.c_size_t, C.c_size_t, dp]
     L.agofrt_msd.argtypes = [vp, C.c_size_t, C.c_uint, C.c_uint, C.c_uint, C.c_int, C.c_int, dp, C.POINTER(Stats)]
     L.agofrt_fp64_peak.argtypes = [vp, C.c_int, C.c_double, dp]
+    L.agofrt_blockavg_create.argtypes = [C.POINTER(vp), vp]
+    L.agofrt_blockavg_destroy.argtypes = [vp]
+    L.agofrt_blockavg_begin.argtypes = [vp, C.c_size_t]
+    L.agofrt_blockavg_push.argtypes = [vp, vp, C.c_double]
+    L.agofrt_blockavg_end.argtypes = [vp, C.c_uint, dp, dp]
+    L.agofrt_plan_last_counts.argtypes = [vp, u64p, C.c_size_t]
     for name in SYMBOLS:
         fn = getattr(L, name)
         if name not in ("agofrt_version", "agofrt_last_error"):
@@ -304,23 +314,66 @@ class Plan:
     def block(self, primo, ntimesteps, leff, skip=1, every=1, options=0, edges=False):
         """Integer counts [leff][ntypes*(ntypes+1)][nbin] of one calculate(primo) after reset(ntimesteps).
 
-        Returns (counts, stats dict[, edge_pairs])."""
+        Returns (counts, stats dict[, edge_pairs]).  With OPT_ON_DEVICE the counts stay on the device (for
+        BlockAverage.push / last_counts) and ``counts`` is None."""
         nt = self.traj.ntypes
-        counts = np.zeros((int(leff), nt * (nt + 1), self.nbin), dtype=np.uint64)
+        on_device = bool(int(options) & OPT_ON_DEVICE)
+        counts = None if on_device else np.zeros((int(leff), nt * (nt + 1), self.nbin), dtype=np.uint64)
         st = Stats()
         e = C.c_uint64(0)
         rc = lib().agofrt_block(self._h, int(primo), int(ntimesteps), int(leff), int(skip), int(every),
                                 int(options) | (OPT_EDGES if edges else 0),
-                                counts.ctypes.data_as(C.POINTER(C.c_uint64)),
+                                None if on_device else counts.ctypes.data_as(C.POINTER(C.c_uint64)),
                                 C.byref(e) if edges else None, C.byref(st))
         _check(rc)
         if edges:
             return counts, st.as_dict(), int(e.value)
         return counts, st.as_dict()
 
+    def last_counts(self, leff):
+        """The counts of the last block() from the device (what a block without OPT_ON_DEVICE returns)."""
+        nt = self.traj.ntypes
+        counts = np.zeros((int(leff), nt * (nt + 1), self.nbin), dtype=np.uint64)
+        _check(lib().agofrt_plan_last_counts(self._h, counts.ctypes.data_as(C.POINTER(C.c_uint64)), counts.size))
+        return counts
+
     def close(self):
         if self._h:
             lib().agofrt_plan_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class BlockAverage:
+    """MediaVar over blocks on the device (agofrt_blockavg_*): mean and variance of the mean of count*incr."""
+
+    def __init__(self, ctx):
+        self._h = C.c_void_p()
+        _check(lib().agofrt_blockavg_create(C.byref(self._h), ctx._h))
+        ctx._children.add(self)
+        self.len = 0
+
+    def begin(self, length):
+        self.len = int(length)
+        _check(lib().agofrt_blockavg_begin(self._h, self.len))
+
+    def push(self, plan, incr):
+        _check(lib().agofrt_blockavg_push(self._h, plan._h, float(incr)))
+
+    def end(self, n_b):
+        mean = np.empty(self.len, dtype=np.float64)
+        var = np.empty(self.len, dtype=np.float64)
+        _check(lib().agofrt_blockavg_end(self._h, int(n_b), _dp(mean), _dp(var)))
+        return mean, var
+
+    def close(self):
+        if self._h:
+            lib().agofrt_blockavg_destroy(self._h)
             self._h = None
 
     def __del__(self):

@@ -171,6 +171,8 @@ struct PlanDev {
     size_t ghist_len = 0;
     Job *jobs = nullptr;
     size_t jobs_cap = 0;
+    SmallUnit *units = nullptr;           // work units of the small-system kernel
+    size_t units_cap = 0;
     unsigned int *counter = nullptr;      // [1]
     unsigned long long *edges = nullptr;  // [1]
 };
@@ -195,6 +197,8 @@ struct agofrt_plan {
     size_t host_counts_len = 0;
     unsigned long long *host_edges = nullptr;   // pinned [ndev]
     unsigned int *host_flags = nullptr;         // pinned [ndev]
+    size_t last_len = 0;                        // words of the counts the last agofrt_block left in dev[0].ghist
+    bool last_valid = false;                    // ... and whether they are the complete (all-reduced) counts
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -1044,6 +1048,7 @@ extern "C" int agofrt_plan_destroy(agofrt_plan *p) {
         cudaFree(d.thr_full);
         cudaFree(d.ghist);
         cudaFree(d.jobs);
+        cudaFree(d.units);
         cudaFree(d.counter);
         cudaFree(d.edges);
     }
@@ -1097,7 +1102,9 @@ extern "C" int agofrt_block(agofrt_plan *p, size_t primo, unsigned ntimesteps, u
     const int nt = t->ntypes;
     const size_t rowlen = static_cast<size_t>(nt) * (nt + 1) * p->nbin;
     const size_t len = static_cast<size_t>(leff) * rowlen;
-    if (len > 0 && !counts_out) return fail(AGOFRT_ERR_ARG, "counts_out is NULL");
+    const bool on_device = (options & AGOFRT_OPT_ON_DEVICE) != 0;
+    if (len > 0 && !counts_out && !on_device) return fail(AGOFRT_ERR_ARG, "counts_out is NULL");
+    p->last_valid = false;
     if (stats) memset(stats, 0, sizeof(*stats));
     if (edge_pairs_out) *edge_pairs_out = 0;
     const bool want_edges = (options & AGOFRT_OPT_EDGES) != 0 || edge_pairs_out != nullptr;
@@ -1154,6 +1161,36 @@ extern "C" int agofrt_block(agofrt_plan *p, size_t primo, unsigned ntimesteps, u
     const uint64_t per_job = static_cast<uint64_t>(n_itiles) * n_jchunks;
     if (njobs * per_job >= 0xF0000000ull) return fail(AGOFRT_ERR_ARG, "too many work units in one block (%llu)",
                                                       static_cast<unsigned long long>(njobs * per_job));
+
+    // ---- small systems: runs of jobs of one lag, dealt to the warps of a CTA (pair_small_kernel) ----
+    const bool small = t->npad > 0 && t->npad <= kSmallJ && !(options & AGOFRT_OPT_NO_SMALL);
+    const int nsub = small ? (t->npad + 32 * kIPT - 1) / (32 * kIPT) : 1;
+    std::vector<SmallUnit> units_fast, units_gen;
+    if (small && !nothing) {
+        // a unit should dwarf the merge of the CTA's histogram rows that ends it (rowlen words scanned,
+        // up to as many global atomics), keep every warp busy, and there should be several units per CTA
+        const uint64_t pairs_per_job = static_cast<uint64_t>(t->npad) * t->npad;
+        const uint64_t by_merge = (128ull * rowlen + pairs_per_job - 1) / pairs_per_job;
+        const uint64_t by_ctas = (njobs + 6ull * total_ctas - 1) / (6ull * total_ctas);
+        const uint64_t wave = static_cast<uint64_t>(kThreads / 32 / nsub);   // jobs the warps of a CTA take at a time
+        uint64_t chunk = std::max<uint64_t>(std::max(by_merge, by_ctas), wave);
+        chunk = std::min<uint64_t>((chunk + wave - 1) / wave * wave, 65536);   // a unit's counts stay far below 2^32
+        for (int pass = 0; pass < 2; ++pass) {
+            const std::vector<Job> &list = pass == 0 ? jobs_fast : jobs_gen;
+            std::vector<SmallUnit> &units = pass == 0 ? units_fast : units_gen;
+            size_t a = 0;
+            while (a < list.size()) {
+                size_t b = a;
+                while (b < list.size() && list[b].tout == list[a].tout) ++b;   // jobs are in lag-major order
+                const uint64_t run = b - a, nch = (run + chunk - 1) / chunk;
+                const uint64_t each = ((run + nch - 1) / nch + wave - 1) / wave * wave;   // equal shares, whole rounds
+                for (size_t c0 = a; c0 < b; c0 += each)
+                    units.push_back(SmallUnit{static_cast<int>(c0), static_cast<int>(std::min<size_t>(each, b - c0)),
+                                              list[a].tout});
+                a = b;
+            }
+        }
+    }
 
     bool aggregate = p->nbin * static_cast<unsigned>(nt * (nt + 1) / 2) < 64;  // few counters: collisions are the rule
     if (options & AGOFRT_OPT_AGGREGATE) aggregate = true;
@@ -1224,8 +1261,22 @@ extern "C" int agofrt_block(agofrt_plan *p, size_t primo, unsigned ntimesteps, u
             CU(cudaMalloc(&pd.jobs, njall * sizeof(Job)));
             pd.jobs_cap = njall;
         }
+        const size_t nuall = units_fast.size() + units_gen.size();
+        if (nuall > pd.units_cap) {
+            cudaFree(pd.units);
+            pd.units = nullptr;
+            pd.units_cap = 0;
+            CU(cudaMalloc(&pd.units, nuall * sizeof(SmallUnit)));
+            pd.units_cap = nuall;
+        }
         CU(cudaEventRecord(dv.ev_begin, dv.stream));
         if (len > 0) CU(cudaMemsetAsync(pd.ghist, 0, len * sizeof(unsigned long long), dv.stream));
+        if (!units_fast.empty())
+            CU(cudaMemcpyAsync(pd.units, units_fast.data(), units_fast.size() * sizeof(SmallUnit), cudaMemcpyHostToDevice,
+                               dv.stream));
+        if (!units_gen.empty())
+            CU(cudaMemcpyAsync(pd.units + units_fast.size(), units_gen.data(), units_gen.size() * sizeof(SmallUnit),
+                               cudaMemcpyHostToDevice, dv.stream));
         CU(cudaMemsetAsync(pd.edges, 0, sizeof(unsigned long long), dv.stream));
         CU(cudaMemsetAsync(td.flags + 1, 0, sizeof(unsigned int), dv.stream));
         if (!jobs_fast.empty())
@@ -1239,11 +1290,13 @@ extern "C" int agofrt_block(agofrt_plan *p, size_t primo, unsigned ntimesteps, u
             for (int pass = 0; pass < 2; ++pass) {
                 const std::vector<Job> &list = pass == 0 ? jobs_fast : jobs_gen;
                 if (list.empty()) continue;
-                const uint64_t units = list.size() * per_job;
+                const std::vector<SmallUnit> &ulist = pass == 0 ? units_fast : units_gen;
+                const uint64_t units = small ? ulist.size() : list.size() * per_job;
                 uint64_t ub = 0, ue = 0;
                 agofrt_shard_range(units, g, world, &ub, &ue);
                 if (ue <= ub) continue;
                 PairParams pp;
+                pp.units = small ? pd.units + (pass == 0 ? 0 : units_fast.size()) : nullptr;
                 pp.pos = td.pos;
                 pp.box = td.box6;
                 pp.type_pad = td.type_pad;
@@ -1262,7 +1315,7 @@ extern "C" int agofrt_block(agofrt_plan *p, size_t primo, unsigned ntimesteps, u
                 pp.npad = t->npad;
                 pp.ntypes = nt;
                 pp.nbin = static_cast<int>(p->nbin);
-                pp.n_itiles = n_itiles;
+                pp.n_itiles = small ? nsub : n_itiles;
                 pp.n_jchunks = n_jchunks;
                 pp.jchunk = jchunk;
                 pp.inv_dr = p->inv_dr;
@@ -1290,14 +1343,21 @@ extern "C" int agofrt_block(agofrt_plan *p, size_t primo, unsigned ntimesteps, u
                 } else {
                     for (int k = 0; k < 9; ++k) pp.ubox[k] = 0.0;
                 }
-                const int variant = (tri ? 1 : 0) | (pass == 0 ? 2 : 0) | (mode << 2) | (ubox ? 32 : 0);
+                const int variant = (tri ? 1 : 0) | (pass == 0 ? 2 : 0) | (mode << 2) | (ubox ? 32 : 0) | (small ? 64 : 0);
                 const int grid = static_cast<int>(std::min<uint64_t>(ue - ub, static_cast<uint64_t>(kMinBlocks) * dv.sm_count));
                 CU(cudaMemsetAsync(pd.counter, 0, sizeof(unsigned int), dv.stream));
                 CU(launch_pair_kernel(variant, grid, smem, dv.stream, pp));
                 ++launches;
                 modes_used |= 1u << mode;
-                // pair evaluations of this shard, counted on real atoms: units are equal-sized
-                my_pairs += static_cast<uint64_t>(static_cast<double>(ue - ub) / static_cast<double>(per_job) * n2 + 0.5);
+                if (small) {
+                    modes_used |= 1u << 8;
+                    uint64_t nj = 0;
+                    for (uint64_t u = ub; u < ue; ++u) nj += static_cast<uint64_t>(ulist[u].count);
+                    my_pairs += nj * n2;
+                } else {
+                    // pair evaluations of this shard, counted on real atoms: units are equal-sized
+                    my_pairs += static_cast<uint64_t>(static_cast<double>(ue - ub) / static_cast<double>(per_job) * n2 + 0.5);
+                }
             }
         }
         CU(cudaEventRecord(dv.ev_k1, dv.stream));
@@ -1319,7 +1379,7 @@ extern "C" int agofrt_block(agofrt_plan *p, size_t primo, unsigned ntimesteps, u
         Dev &dv = ctx->devs[0];
         PlanDev &pd = p->dev[0];
         CU(cudaSetDevice(dv.id));
-        if (len > 0)
+        if (len > 0 && counts_out)
             CU(cudaMemcpyAsync(p->host_counts, pd.ghist, len * sizeof(unsigned long long), cudaMemcpyDeviceToHost, dv.stream));
     }
     for (int i = 0; i < nloc; ++i) {
@@ -1344,7 +1404,13 @@ extern "C" int agofrt_block(agofrt_plan *p, size_t primo, unsigned ntimesteps, u
     }
     // a sharded context without communicator and several local devices: partial counts are summed
     // here only because they are all in this process (integer sum, order-free)
-    if (len > 0) {
+    // the counts in dev[0].ghist are the whole job's when one device did it all or the all-reduce ran
+    p->last_len = len;
+    p->last_valid = nloc == 1 ? (world == 1 || (ctx->comm_ready && world > 1)) : ctx->comm_ready;
+    if (on_device && !p->last_valid)
+        return fail(AGOFRT_ERR_ARG, "AGOFRT_OPT_ON_DEVICE needs the complete counts on the device: a sharded context "
+                                    "without communicator only holds partial counts");
+    if (len > 0 && counts_out) {
         memcpy(counts_out, p->host_counts, len * sizeof(uint64_t));
         if (!ctx->comm_ready && nloc > 1) {
             for (int i = 1; i < nloc; ++i) {
@@ -1376,6 +1442,106 @@ extern "C" int agofrt_block(agofrt_plan *p, size_t primo, unsigned ntimesteps, u
         stats->world = static_cast<uint32_t>(world);
         stats->kernel_modes = modes_used;
     }
+    return AGOFRT_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// block averages on the device (MediaVar<Gofrt>, reference lib/include/calcoliblocchi.h:21-65)
+// ---------------------------------------------------------------------------------------------
+struct agofrt_blockavg {
+    agofrt_ctx *ctx = nullptr;
+    double *mean = nullptr, *var = nullptr;   // device 0 of the context
+    size_t cap = 0, len = 0;
+    unsigned blocks = 0;                      // MediaVar::iblock
+    bool begun = false;
+};
+
+extern "C" int agofrt_blockavg_create(agofrt_blockavg **acc, agofrt_ctx *ctx) {
+    if (!acc || !ctx) return fail(AGOFRT_ERR_ARG, "NULL argument");
+    *acc = new agofrt_blockavg;
+    (*acc)->ctx = ctx;
+    return AGOFRT_OK;
+}
+
+extern "C" int agofrt_blockavg_destroy(agofrt_blockavg *a) {
+    if (!a) return AGOFRT_OK;
+    cudaSetDevice(a->ctx->devs[0].id);
+    cudaFree(a->mean);
+    cudaFree(a->var);
+    delete a;
+    return AGOFRT_OK;
+}
+
+extern "C" int agofrt_blockavg_begin(agofrt_blockavg *a, size_t len) {
+    if (!a) return fail(AGOFRT_ERR_ARG, "acc is NULL");
+    Dev &dv = a->ctx->devs[0];
+    CU(cudaSetDevice(dv.id));
+    if (len > a->cap) {
+        cudaFree(a->mean);
+        cudaFree(a->var);
+        a->mean = a->var = nullptr;
+        a->cap = 0;
+        CU(cudaMalloc(&a->mean, len * sizeof(double)));
+        CU(cudaMalloc(&a->var, len * sizeof(double)));
+        a->cap = len;
+    }
+    a->len = len;
+    a->blocks = 0;
+    a->begun = true;
+    if (len > 0) {
+        CU(cudaMemsetAsync(a->mean, 0, len * sizeof(double), dv.stream));   // +0.0, VectorOp::azzera
+        CU(cudaMemsetAsync(a->var, 0, len * sizeof(double), dv.stream));
+    }
+    return AGOFRT_OK;
+}
+
+extern "C" int agofrt_blockavg_push(agofrt_blockavg *a, agofrt_plan *p, double incr) {
+    if (!a || !p) return fail(AGOFRT_ERR_ARG, "NULL argument");
+    if (!a->begun) return fail(AGOFRT_ERR_ARG, "agofrt_blockavg_push before agofrt_blockavg_begin");
+    if (p->ctx != a->ctx) return fail(AGOFRT_ERR_ARG, "plan and accumulator belong to different contexts");
+    if (!p->last_valid) return fail(AGOFRT_ERR_ARG, "the plan holds no complete block on the device (run agofrt_block first)");
+    // VectorOp's "Trying to operate on VectorOp of different sizes!" (reference lib/include/operazionisulista.h:48)
+    if (p->last_len != a->len)
+        return fail(AGOFRT_ERR_ARG, "block of %zu elements pushed into an average of %zu", p->last_len, a->len);
+    Dev &dv = a->ctx->devs[0];
+    CU(cudaSetDevice(dv.id));
+    // same stream as the pair kernels and the all-reduce of the block: ordered after them, and before the next
+    // agofrt_block zeroes the counts
+    CU(launch_blockavg_push(p->dev[0].ghist, incr, a->blocks, a->mean, a->var, a->len, dv.sm_count, dv.stream));
+    ++a->blocks;
+    return AGOFRT_OK;
+}
+
+extern "C" int agofrt_blockavg_end(agofrt_blockavg *a, unsigned n_b, double *mean_out, double *var_out) {
+    if (!a) return fail(AGOFRT_ERR_ARG, "acc is NULL");
+    if (!a->begun) return fail(AGOFRT_ERR_ARG, "agofrt_blockavg_end before agofrt_blockavg_begin");
+    Dev &dv = a->ctx->devs[0];
+    CU(cudaSetDevice(dv.id));
+    if (a->len > 0 && mean_out)
+        CU(cudaMemcpyAsync(mean_out, a->mean, a->len * sizeof(double), cudaMemcpyDeviceToHost, dv.stream));
+    if (a->len > 0 && var_out)
+        CU(cudaMemcpyAsync(var_out, a->var, a->len * sizeof(double), cudaMemcpyDeviceToHost, dv.stream));
+    CU(cudaStreamSynchronize(dv.stream));
+    // MediaVar::calcola_end: *Tvar /= ((n_b-1)*n_b), unsigned arithmetic, one pass over the result -- on the host, so
+    // that even the degenerate n_b = 1 (0/0) gives the host's own NaN
+    if (var_out) {
+        const double denom = static_cast<double>((n_b - 1u) * n_b);
+        for (size_t k = 0; k < a->len; ++k) var_out[k] /= denom;
+    }
+    a->begun = false;
+    return AGOFRT_OK;
+}
+
+extern "C" int agofrt_plan_last_counts(agofrt_plan *p, uint64_t *counts_out, size_t len) {
+    if (!p || (len > 0 && !counts_out)) return fail(AGOFRT_ERR_ARG, "NULL argument");
+    if (!p->last_valid) return fail(AGOFRT_ERR_ARG, "the plan holds no complete block on the device (run agofrt_block first)");
+    if (len != p->last_len) return fail(AGOFRT_ERR_ARG, "the last block has %zu words, not %zu", p->last_len, len);
+    if (len == 0) return AGOFRT_OK;
+    Dev &dv = p->ctx->devs[0];
+    CU(cudaSetDevice(dv.id));
+    CU(cudaMemcpyAsync(p->host_counts, p->dev[0].ghist, len * sizeof(unsigned long long), cudaMemcpyDeviceToHost, dv.stream));
+    CU(cudaStreamSynchronize(dv.stream));
+    memcpy(counts_out, p->host_counts, len * sizeof(uint64_t));
     return AGOFRT_OK;
 }
 

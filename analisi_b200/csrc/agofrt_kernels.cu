@@ -398,7 +398,8 @@ struct PairConst {
 // the binning of the group's pairs without per-pair branches.
 //   DIAG: the j atoms may include one of this thread's own i atoms (i == j goes to the "self" rows).
 // All kIPT x kJU squared distances of one group (straight-line, independent FP64 chains).
-template <bool TRI, bool FAST>
+//   JROW: doubles between the x, y and z rows of the staged j coordinates
+template <bool TRI, bool FAST, int JROW>
 __device__ __forceinline__ void group_distances(const PairConst &c, const double (&xi)[kIPT], const double (&yi)[kIPT],
                                                 const double (&zi)[kIPT], uint32_t sx_addr, int jrel,
                                                 double (&d2)[kIPT][kJU], bool &wrap_ok) {
@@ -407,8 +408,8 @@ __device__ __forceinline__ void group_distances(const PairConst &c, const double
     for (int q = 0; q < kJU; q += 2) {
         const uint32_t a = sx_addr + static_cast<uint32_t>(jrel + q) * 8u;
         const double2 vx = lds_f64x2(a);
-        const double2 vy = lds_f64x2(a + kTileJ * 8u);
-        const double2 vz = lds_f64x2(a + 2u * kTileJ * 8u);
+        const double2 vy = lds_f64x2(a + JROW * 8u);
+        const double2 vz = lds_f64x2(a + 2u * JROW * 8u);
         xj[q] = vx.x;
         xj[q + 1] = vx.y;
         yj[q] = vy.x;
@@ -468,7 +469,7 @@ __device__ __forceinline__ void group_bin_safe(const PairParams &p, const PairCo
     }
 }
 
-template <bool TRI, bool FAST, int MODE, bool DIAG>
+template <bool TRI, bool FAST, int MODE, bool DIAG, int JROW = kTileJ>
 __device__ __forceinline__ void process_group(const PairParams &p, const PairConst &c, const double (&xi)[kIPT],
                                               const double (&yi)[kIPT], const double (&zi)[kIPT],
                                               const int (&ii)[kIPT], const unsigned int (&row)[kIPT],
@@ -476,7 +477,7 @@ __device__ __forceinline__ void process_group(const PairParams &p, const PairCon
                                               const double *s_thrf, unsigned int *s_hist, unsigned int self_off,
                                               unsigned long long &edges, bool &wrap_ok) {
     double d2[kIPT][kJU];
-    group_distances<TRI, FAST>(c, xi, yi, zi, sx_addr, jrel, d2, wrap_ok);
+    group_distances<TRI, FAST, JROW>(c, xi, yi, zi, sx_addr, jrel, d2, wrap_ok);
     if (MODE == MODE_EDGES) {
 #pragma unroll
         for (int k = 0; k < kIPT; ++k) {
@@ -550,6 +551,55 @@ __device__ __forceinline__ void process_group(const PairParams &p, const PairCon
     }
 }
 
+// Shared-memory tables every pair kernel starts from: zeroed histogram rows, the threshold pairs, the
+// (type_i, type_j) -> row table of Gofrt::get_itype, and the first slot of every type group.
+template <bool EDGES>
+__device__ __forceinline__ void cta_tables(const PairParams &p, int tid, int P, int rstride, unsigned int *s_hist,
+                                           double2 *s_thr2, double *s_thrf, unsigned int *s_rowtab, int *s_tstart) {
+    const int nt = p.ntypes, nbin = p.nbin;
+    for (int k = tid; k < 2 * P * rstride; k += kThreads) s_hist[k] = 0u;
+    for (int k = tid; k < nbin + 3; k += kThreads) {
+        // slot k <-> bin g = k-1
+        const int g = k - 1;
+        double2 t;
+        if (g >= 0 && g < nbin) {
+            t.x = p.thr[g];
+            t.y = p.thr[g + 1];
+        } else {
+            t.x = t.y = INFINITY;
+        }
+        s_thr2[k] = t;
+    }
+    if (EDGES)
+        for (int k = tid; k <= nbin; k += kThreads) s_thrf[k] = p.thr_full[k];
+    for (int k = tid; k < nt * nt; k += kThreads) {
+        // Gofrt::get_itype, reference lib/include/gofrt.h:86-104
+        int a = k / nt, b = k % nt;
+        if (b < a) {
+            const int c = a;
+            a = b;
+            b = c;
+        }
+        s_rowtab[k] = static_cast<unsigned int>((P - (b + 1) * (b + 2) / 2 + a) * rstride + p.glo);
+    }
+    for (int k = tid; k <= nt; k += kThreads) s_tstart[k] = p.type_start[k];
+}
+
+// Merge the CTA's shared-memory rows (guard bins left out) into lag row `lag` of the global histogram and
+// zero them.  Called between barriers.
+__device__ __forceinline__ void cta_flush(const PairParams &p, int tid, int lag, int hlen, int rstride,
+                                          unsigned int *s_hist) {
+    unsigned long long *g = p.ghist + static_cast<size_t>(lag) * hlen;
+    for (int k = tid; k < hlen; k += kThreads) {
+        unsigned int *w = s_hist + (k / p.nbin) * rstride + p.glo + (k % p.nbin);
+        const unsigned int v = *w;
+        if (v) {
+            atomicAdd(g + k, static_cast<unsigned long long>(v));
+            *w = 0u;
+        }
+    }
+}
+
 // UBOX: every frame of the window has the same box, passed as a kernel parameter.  The half edges,
 // the -2*l_half constants and the tilt factors then reach the FP64 instructions as constant-bank /
 // uniform-register operands instead of per-thread registers.  B200's register file delivers one even
@@ -578,32 +628,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) pair_kernel(const PairPa
     const int rstride = row_stride(nbin, p.glo);   // words of one row in shared memory (with its guard bins)
     const unsigned int self_off = static_cast<unsigned int>(P * rstride);
 
-    for (int k = tid; k < 2 * P * rstride; k += kThreads) s_hist[k] = 0u;
-    for (int k = tid; k < nbin + 3; k += kThreads) {
-        // slot k <-> bin g = k-1
-        const int g = k - 1;
-        double2 t;
-        if (g >= 0 && g < nbin) {
-            t.x = p.thr[g];
-            t.y = p.thr[g + 1];
-        } else {
-            t.x = t.y = INFINITY;
-        }
-        s_thr2[k] = t;
-    }
-    if (EDGES)
-        for (int k = tid; k <= nbin; k += kThreads) s_thrf[k] = p.thr_full[k];
-    for (int k = tid; k < nt * nt; k += kThreads) {
-        // Gofrt::get_itype, reference lib/include/gofrt.h:86-104
-        int a = k / nt, b = k % nt;
-        if (b < a) {
-            const int c = a;
-            a = b;
-            b = c;
-        }
-        s_rowtab[k] = static_cast<unsigned int>((P - (b + 1) * (b + 2) / 2 + a) * rstride + p.glo);
-    }
-    for (int k = tid; k <= nt; k += kThreads) s_tstart[k] = p.type_start[k];
+    cta_tables<EDGES>(p, tid, P, rstride, s_hist, s_thr2, s_thrf, s_rowtab, s_tstart);
     if (tid == 0) {
         for (int s = 0; s < kStages; ++s) mbar_init(&s_bar[s], 1);
         mbar_fence_init();
@@ -639,15 +664,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) pair_kernel(const PairPa
 
         if (job.tout != cur_t || acc_pairs + unit_pairs > 0xF0000000ull) {
             if (cur_t >= 0) {
-                unsigned long long *g = p.ghist + static_cast<size_t>(cur_t) * hlen;
-                for (int k = tid; k < hlen; k += kThreads) {
-                    unsigned int *w = s_hist + (k / nbin) * rstride + p.glo + (k % nbin);
-                    const unsigned int v = *w;
-                    if (v) {
-                        atomicAdd(g + k, static_cast<unsigned long long>(v));
-                        *w = 0u;
-                    }
-                }
+                cta_flush(p, tid, cur_t, hlen, rstride, s_hist);
                 __syncthreads();
             }
             cur_t = job.tout;
@@ -770,22 +787,181 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) pair_kernel(const PairPa
     if (!wrap_ok) atomicExch(p.error_flag, 1u);
 }
 
-// variant = TRI | FAST<<1 | MODE<<2 | UBOX<<5   (UBOX only with FAST and MODE in {THR, SAFE, SAFE_DENSE})
+// ---------------------------------------------------------------------------------------------
+// the pair kernel for SMALL systems (npad <= kSmallJ slots, e.g. the 56 atoms of the reference's bundled
+// tests/data/lammps.bin)
+//
+// pair_kernel gives a whole CTA (512 i slots) to one (lag, origin) job; with a few dozen atoms nine lanes in
+// ten hold no atom, and because consecutive tickets go to different CTAs nearly every job ends with a merge
+// of the CTA's histogram into the global row of its lag.  Here the work unit is a RUN OF JOBS OF ONE LAG
+// (SmallUnit, cut by the host) and the jobs of a unit are dealt to the WARPS of the CTA: a warp holds the
+// (up to 64) i atoms of its job in registers, copies the j frame into its own 3 KB slice of the stage area
+// with coalesced loads and walks it with the same process_group as the large kernel -- same arithmetic,
+// same binning modes, same shared-memory histogram rows.  Warps never wait for each other inside a unit;
+// the CTA meets once per unit, to merge its rows into the global row of the unit's lag.
+// Systems of 65..128 slots use two warps (two i sub-tiles) per job.
+// ---------------------------------------------------------------------------------------------
+constexpr int kWarps = kThreads / 32;
+static_assert(kWarps * 3 * kSmallJ <= kStages * 3 * kTileJ, "the warp slices live in the stage area of pair_kernel");
+static_assert(kSmallJ % (32 * kIPT) == 0 && kWarps % (kSmallJ / (32 * kIPT)) == 0,
+              "a warp keeps the same i sub-tile for every job it takes");
+
+template <bool TRI, bool FAST, int MODE, bool UBOX>
+__global__ void __launch_bounds__(kThreads, kMinBlocks) pair_small_kernel(const PairParams p) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    constexpr bool EDGES = MODE == MODE_EDGES;
+    const SmemLayout L = smem_layout(p.ntypes, p.nbin, p.glo, EDGES);
+    double *s_stage = reinterpret_cast<double *>(smem + L.stage);
+    double2 *s_thr2 = reinterpret_cast<double2 *>(smem + L.thr2);
+    double *s_thrf = reinterpret_cast<double *>(smem + L.thr_full);
+    unsigned int *s_hist = reinterpret_cast<unsigned int *>(smem + L.hist);
+    unsigned int *s_rowtab = reinterpret_cast<unsigned int *>(smem + L.rowtab);
+    int *s_tstart = reinterpret_cast<int *>(smem + L.tstart);
+    unsigned int *s_sched = reinterpret_cast<unsigned int *>(smem + L.sched);
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    const int nt = p.ntypes, nbin = p.nbin;
+    const int P = nt * (nt + 1) / 2;
+    const int hlen = 2 * P * nbin;
+    const int rstride = row_stride(nbin, p.glo);
+    const unsigned int self_off = static_cast<unsigned int>(P * rstride);
+
+    cta_tables<EDGES>(p, tid, P, rstride, s_hist, s_thr2, s_thrf, s_rowtab, s_tstart);
+    __syncthreads();
+
+    PairConst c;
+    c.thr2_addr = smem_u32(s_thr2);
+    c.hist_addr = smem_u32(s_hist);
+    double *slice = s_stage + static_cast<size_t>(warp) * 3 * kSmallJ;   // this warp's copy of the j frame
+    const uint32_t slice_addr = smem_u32(slice);
+
+    // this warp's i slots: sub-tile `sub` of every job it takes
+    const int nsub = p.n_itiles;
+    const int wi0 = (warp % nsub) * (32 * kIPT);
+    int ii[kIPT], ti[kIPT];
+#pragma unroll
+    for (int k = 0; k < kIPT; ++k) {
+        ii[k] = wi0 + k * 32 + lane;
+        ti[k] = ii[k] < p.npad ? p.type_pad[ii[k]] : 0;
+    }
+    if (UBOX) {
+        c.box.lhx = p.ubox[0];
+        c.box.lhy = p.ubox[1];
+        c.box.lhz = p.ubox[2];
+        c.box.xy = p.ubox[3];
+        c.box.xz = p.ubox[4];
+        c.box.yz = p.ubox[5];
+        const int zero = p.npad >> 31;   // see pair_kernel: keeps -2*l_half in registers
+        c.nLx = __hiloint2double(__double2hiint(p.ubox[6]) ^ zero, __double2loint(p.ubox[6]));
+        c.nLy = __hiloint2double(__double2hiint(p.ubox[7]) ^ zero, __double2loint(p.ubox[7]));
+        c.nLz = __hiloint2double(__double2hiint(p.ubox[8]) ^ zero, __double2loint(p.ubox[8]));
+    }
+
+    unsigned long long edges = 0;
+    bool wrap_ok = true;
+
+    for (;;) {
+        if (tid == 0) s_sched[0] = p.unit_begin + atomicAdd(p.counter, 1u);
+        __syncthreads();   // also: every thread is past the merge of the previous unit
+        const unsigned int u = s_sched[0];
+        __syncthreads();
+        if (u >= p.unit_end) break;
+        const SmallUnit un = p.units[u];
+        const int ntask = un.count * nsub;
+
+        for (int task = warp; task < ntask; task += kWarps) {
+            const Job job = p.jobs[un.begin + task / nsub];
+            if (!UBOX) {
+                const double *bx = p.box + static_cast<size_t>(job.fi) * 6;
+                c.box.lhx = __ldg(bx + 0);
+                c.box.lhy = __ldg(bx + 1);
+                c.box.lhz = __ldg(bx + 2);
+                c.box.xy = __ldg(bx + 3);
+                c.box.xz = __ldg(bx + 4);
+                c.box.yz = __ldg(bx + 5);
+                c.nLx = __dmul_rn(c.box.lhx, -2.0);
+                c.nLy = __dmul_rn(c.box.lhy, -2.0);
+                c.nLz = __dmul_rn(c.box.lhz, -2.0);
+            }
+            double xi[kIPT], yi[kIPT], zi[kIPT];
+            const double *pi = p.pos + static_cast<size_t>(job.fi) * 3 * p.npad;
+#pragma unroll
+            for (int k = 0; k < kIPT; ++k) {
+                if (ii[k] < p.npad) {
+                    xi[k] = pi[ii[k]];
+                    yi[k] = pi[p.npad + ii[k]];
+                    zi[k] = pi[2 * p.npad + ii[k]];
+                } else {
+                    xi[k] = yi[k] = zi[k] = __longlong_as_double(0x7ff8000000000000ll);
+                }
+            }
+            const double *pj = p.pos + static_cast<size_t>(job.fj) * 3 * p.npad;
+            __syncwarp();   // every lane is done with the previous job's copy
+            for (int q = lane; q < p.npad; q += 32) {
+                slice[q] = pj[q];
+                slice[kSmallJ + q] = pj[p.npad + q];
+                slice[2 * kSmallJ + q] = pj[2 * p.npad + q];
+            }
+            __syncwarp();
+
+            for (int ty = 0; ty < nt; ++ty) {
+                const int lo = s_tstart[ty], hi = s_tstart[ty + 1];
+                if (lo >= hi) continue;
+                unsigned int row[kIPT];
+#pragma unroll
+                for (int k = 0; k < kIPT; ++k) row[k] = s_rowtab[ti[k] * nt + ty];
+                const int da = min(max(wi0, lo), hi);
+                const int db = min(max(wi0 + 32 * kIPT, lo), hi);
+#pragma unroll 1
+                for (int j = lo; j < da; j += kJU)
+                    process_group<TRI, FAST, MODE, false, kSmallJ>(p, c, xi, yi, zi, ii, row, slice_addr, j, j, s_thr2,
+                                                                   s_thrf, s_hist, self_off, edges, wrap_ok);
+#pragma unroll 1
+                for (int j = da; j < db; j += kJU)
+                    process_group<TRI, FAST, MODE, true, kSmallJ>(p, c, xi, yi, zi, ii, row, slice_addr, j, j, s_thr2,
+                                                                  s_thrf, s_hist, self_off, edges, wrap_ok);
+#pragma unroll 1
+                for (int j = db; j < hi; j += kJU)
+                    process_group<TRI, FAST, MODE, false, kSmallJ>(p, c, xi, yi, zi, ii, row, slice_addr, j, j, s_thr2,
+                                                                   s_thrf, s_hist, self_off, edges, wrap_ok);
+            }
+        }
+        __syncthreads();
+        cta_flush(p, tid, un.lag, hlen, rstride, s_hist);
+    }
+    if (EDGES) {
+        for (int o = 16; o > 0; o >>= 1) edges += __shfl_xor_sync(0xffffffffu, edges, o);
+        if (lane == 0 && edges) atomicAdd(p.edges, edges);
+    }
+    if (!wrap_ok) atomicExch(p.error_flag, 1u);
+}
+
+// variant = TRI | FAST<<1 | MODE<<2 | UBOX<<5 | SMALL<<6   (UBOX only with FAST and MODE in {THR, SAFE, SAFE_DENSE})
 template <int V>
 static cudaError_t launch_variant(int grid, size_t smem, cudaStream_t stream, const PairParams &p) {
-    pair_kernel<(V & 1) != 0, (V & 2) != 0, ((V >> 2) & 7), (V & 32) != 0><<<grid, kThreads, smem, stream>>>(p);
+    if constexpr ((V & 64) != 0)
+        pair_small_kernel<(V & 1) != 0, (V & 2) != 0, ((V >> 2) & 7), (V & 32) != 0><<<grid, kThreads, smem, stream>>>(p);
+    else
+        pair_kernel<(V & 1) != 0, (V & 2) != 0, ((V >> 2) & 7), (V & 32) != 0><<<grid, kThreads, smem, stream>>>(p);
     return cudaGetLastError();
 }
 
 template <int V>
 static cudaError_t prepare_variant(size_t max_smem) {
-    return cudaFuncSetAttribute(pair_kernel<(V & 1) != 0, (V & 2) != 0, ((V >> 2) & 7), (V & 32) != 0>,
+    if constexpr ((V & 64) != 0)
+        return cudaFuncSetAttribute(pair_small_kernel<(V & 1) != 0, (V & 2) != 0, ((V >> 2) & 7), (V & 32) != 0>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(max_smem));
+    else
+        return cudaFuncSetAttribute(pair_kernel<(V & 1) != 0, (V & 2) != 0, ((V >> 2) & 7), (V & 32) != 0>,
                                 cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(max_smem));
 }
 
-#define AGOFRT_VARIANTS(X)                                                                              \
-    X(0) X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(12) X(13) X(14) X(15) X(18) X(19) \
-    X(32 + 2) X(32 + 3) X(32 + 14) X(32 + 15) X(32 + 18) X(32 + 19)
+#define AGOFRT_VARIANTS_OF(X, S)                                                                              \
+    X(S + 0) X(S + 1) X(S + 2) X(S + 3) X(S + 4) X(S + 5) X(S + 6) X(S + 7) X(S + 8) X(S + 9) X(S + 10)     \
+    X(S + 11) X(S + 12) X(S + 13) X(S + 14) X(S + 15) X(S + 18) X(S + 19)                                   \
+    X(S + 32 + 2) X(S + 32 + 3) X(S + 32 + 14) X(S + 32 + 15) X(S + 32 + 18) X(S + 32 + 19)
+#define AGOFRT_VARIANTS(X) AGOFRT_VARIANTS_OF(X, 0) AGOFRT_VARIANTS_OF(X, 64)
 
 cudaError_t launch_pair_kernel(int variant, int grid, size_t smem, cudaStream_t stream, const PairParams &p) {
     switch (variant) {
@@ -1228,6 +1404,37 @@ cudaError_t launch_msd(const MsdParams &p, cudaStream_t stream) {
 }
 
 int msd_tile_atoms() { return kMsdThreads; }
+
+// ---------------------------------------------------------------------------------------------
+// Block averages on the device: MediaVar<T>::calculate (reference lib/include/calcoliblocchi.h:35-56) per
+// element, on the integer counts of the block that has just been computed.  The reference runs it as eight
+// whole-vector VectorOp passes on the host (delta = x; delta -= mean; tmp = delta; tmp /= k+1; mean += tmp;
+// tmp = x; tmp -= mean; tmp *= delta; var += tmp); per element that is the sequence below, every operation
+// rounded on its own (no FMA), so mean and var are bit-identical to the host's.  HBM-bound: 40 bytes per element
+// (8 read for the count, 16 read and 16 written for mean and var).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) blockavg_push_kernel(const unsigned long long *__restrict__ counts, double incr,
+                                                            double kp1, double *__restrict__ mean,
+                                                            double *__restrict__ var, size_t len) {
+    const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+    for (size_t k = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; k < len; k += stride) {
+        const double x = __dmul_rn(__ull2double_rn(counts[k]), incr);   // Gofrt: vdata = count * incr
+        const double m0 = mean[k];
+        const double delta = __dsub_rn(x, m0);
+        const double m1 = __dadd_rn(m0, __ddiv_rn(delta, kp1));
+        mean[k] = m1;
+        var[k] = __dadd_rn(var[k], __dmul_rn(__dsub_rn(x, m1), delta));
+    }
+}
+
+cudaError_t launch_blockavg_push(const unsigned long long *counts, double incr, unsigned block_index, double *mean,
+                                 double *var, size_t len, int sm_count, cudaStream_t stream) {
+    if (len == 0) return cudaSuccess;
+    const size_t want = (len + 255) / 256;
+    const int grid = static_cast<int>(want < static_cast<size_t>(8 * sm_count) ? want : static_cast<size_t>(8 * sm_count));
+    blockavg_push_kernel<<<grid, 256, 0, stream>>>(counts, incr, static_cast<double>(block_index + 1u), mean, var, len);
+    return cudaGetLastError();
+}
 
 // ---------------------------------------------------------------------------------------------
 // FP64 issue-rate microbenchmark: 8 independent DFMA chains per thread

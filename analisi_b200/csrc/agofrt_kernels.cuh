@@ -36,11 +36,19 @@ constexpr int kStages = 2;                  // bulk-copy stages
 constexpr int kPadGroup = 8;                // every type group is padded to a multiple of this
 constexpr int kJU = AGOFRT_JU;              // j atoms per inner step (one LDS.128 per coordinate per two)
 constexpr int kWrapCap = 1 << 20;           // images the general minimum image may add per dimension
+constexpr int kSmallJ = 128;                // systems of up to this many slots go to pair_small_kernel
 
 struct Job {
     int fi;    // window-relative frame of the i atoms (its box is used)
     int fj;    // window-relative frame of the j atoms
     int tout;  // output lag row
+};
+
+// pair_small_kernel: a run of jobs of ONE lag, dealt to the warps of a CTA
+struct SmallUnit {
+    int begin;   // first job of the run (index into PairParams::jobs)
+    int count;   // jobs in the run
+    int lag;     // their common output lag row
 };
 
 struct PairParams {
@@ -49,6 +57,7 @@ struct PairParams {
     const int *type_pad;      // [npad] dense type of every slot (ghosts: the type of their group)
     const int *type_start;    // [ntypes+1] first slot of every type group
     const Job *jobs;
+    const SmallUnit *units;   // pair_small_kernel only: the work units (pair_kernel derives them from jobs)
     unsigned long long *ghist;  // [leff][2P][nbin]
     unsigned long long *edges;  // [1] (EDGES variant)
     unsigned int *counter;      // work-unit ticket
@@ -59,7 +68,8 @@ struct PairParams {
     double ubox[9];             // UBOX variants: lx/2, ly/2, lz/2, xy, xz, yz, -lx, -ly, -lz of the one box of the window
     unsigned unit_begin, unit_end;
     int npad, ntypes, nbin;
-    int n_itiles, n_jchunks, jchunk;  // jchunk is a multiple of kTileJ
+    int n_itiles, n_jchunks, jchunk;  // jchunk is a multiple of kTileJ; pair_small_kernel: n_itiles = i sub-tiles of
+                                      // 32*kIPT slots per job (1 or 2), the other two unused
     float inv_dr, c0;                 // bin guess = floor(sqrtf(d2) * inv_dr + c0)
     float c0h, lim, qmax;             // MODE_SAFE: c0 - 0.5, 0.5 - eps, nbin + 0.25 (clamp of the bin coordinate)
     int glo;                          // guard bins below bin 0 in every shared-memory histogram row
@@ -68,7 +78,7 @@ struct PairParams {
 
 size_t pair_kernel_smem_bytes(int ntypes, int nbin, int glo, bool edges);
 
-// variant = TRI | FAST<<1 | MODE<<2 | UBOX<<5, MODE: 0 thresholds, 1 thresholds + warp aggregation, 2 edges, 3 safe-zone,
+// variant = TRI | FAST<<1 | MODE<<2 | UBOX<<5 | SMALL<<6, MODE: 0 thresholds, 1 thresholds + warp aggregation, 2 edges, 3 safe-zone,
 // 4 safe-zone without the group filter (dense in-range workloads: nearly every group holds an in-range pair)
 enum { kModeThr = 0, kModeAgg = 1, kModeEdges = 2, kModeSafe = 3, kModeSafeDense = 4 };  // dense: FAST only (variants 18, 19)
 cudaError_t launch_pair_kernel(int variant, int grid, size_t smem, cudaStream_t stream, const PairParams &p);
@@ -129,6 +139,10 @@ struct MsdParams {
 };
 cudaError_t launch_msd(const MsdParams &p, cudaStream_t stream);
 int msd_tile_atoms();
+
+// MediaVar::calculate on the device: block `block_index` (0-based) with x = counts * incr folded into mean / var
+cudaError_t launch_blockavg_push(const unsigned long long *counts, double incr, unsigned block_index, double *mean,
+                                 double *var, size_t len, int sm_count, cudaStream_t stream);
 
 // MODE_SAFE validation: bad += number of probes whose unflagged float guess differs from expected[]
 cudaError_t launch_validate_safe(const double *probes, const int *expected, int n, float inv_dr, float c0h, float lim,

@@ -158,6 +158,9 @@ def run_c5(args, rank, world, name="C5"):
         e2e = pairs / float(np.mean(walls))
         kernel_rate = pairs / float(np.mean(kers)) / ngpu
         s_blk = ba.block_size()
+        # block averages on the device (MediaVarDevice) unless ANALISI_DEVICE_BLOCKS=0: one more kernel per block,
+        # and only mean, variance and the last block come back instead of every block's counts
+        dev_blocks = os.environ.get("ANALISI_DEVICE_BLOCKS", "1") != "0"
         a_ = w.nframes // (w.nblocks + 1) + 1
         win = s_blk + (a_ if (a_ < w.tmax or w.tmax == 0) else w.tmax)   # frames of one block window (Gofrt::nExtraTimesteps)
         line = {
@@ -168,14 +171,14 @@ def run_c5(args, rank, world, name="C5"):
                        "rmin": w.rmin, "rmax": w.rmax, "nbin": w.nbin, "lags": w.tmax, "skip": w.skip, "blocks": w.nblocks,
                        "block_size": int(s_blk), "pair_evals_per_step": pairs,
                        "parallelism": "one process, %d GPU(s): work units of each block sharded, 1 NCCL all-reduce/block; "
-                                      "MediaVar on the host in block order" % ngpu,
+                                      "MediaVar %s in block order" % (ngpu, "on the device" if dev_blocks else "on the host"),
                        "step": "file -> %d block windows -> mean and variance (the analisi -g ... -B %d chain)" % (w.nblocks, w.nblocks),
-                       "l2": "block window: %.1f MB%s" % (win * w.natoms * 24 / 1e6, " (larger than L2)" if win * w.natoms * 24 > 126e6 else " (fits in L2; 56 atoms: the workload is launch- and tile-bound, not FP64-bound)")},
+                       "l2": "block window: %.1f MB%s" % (win * w.natoms * 24 / 1e6, " (larger than L2)" if win * w.natoms * 24 > 126e6 else " (fits in L2; 56 atoms: one (lag, origin) job per warp, small-system kernel)")},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(w.nblocks * win * w.natoms * 24 * 2),
-                    "d2h_bytes_per_step": int(w.nblocks * (win * w.natoms * 24 + mean.size * 8)),
+                    "d2h_bytes_per_step": int(w.nblocks * win * w.natoms * 24 + (3 if dev_blocks else w.nblocks) * mean.size * 8),
                     "ms_per_step": float(np.mean(walls)) * 1e3,
                     "includes": "mmap read + id scatter (host threads), wrap round trip, window upload, kernels, read-back, Welford"},
-            "gpu_launches": int(st["blocks"]) * ngpu, "clocks": clocks,
+            "gpu_launches": int(st["blocks"]) * ngpu + (int(st["blocks"]) if dev_blocks else 0), "clocks": clocks,
             "roofline": {"bound": "fp64", "achieved": kernel_rate * ops / 1e12, "peak": peak / 1e12 if peak else None,
                          "unit": "T FP64-op/s per GPU", "frac": kernel_rate * ops / peak if peak else None, "traffic": None,
                          "ops_per_pair_eval": ops, "kernel_ms_per_step": float(np.mean(kers)) * 1e3,

@@ -149,7 +149,10 @@ enum {
     AGOFRT_OPT_NO_SAFE = 16,       /* bracket every guess against the exact thresholds (no safe-zone shortcut) */
     AGOFRT_OPT_DENSE = 32,         /* force the kernel without the group filter (dense in-range workloads)      */
     AGOFRT_OPT_SPARSE = 64,        /* force the group-filtered kernel meant for sparse in-range workloads      */
-    AGOFRT_OPT_NO_UBOX = 128       /* never pass a constant box as kernel parameter (uniform operands)         */
+    AGOFRT_OPT_NO_UBOX = 128,      /* never pass a constant box as kernel parameter (uniform operands)         */
+    AGOFRT_OPT_NO_SMALL = 256,     /* never take the small-system kernel (warp-per-job, up to 128 device slots) */
+    AGOFRT_OPT_ON_DEVICE = 512     /* leave the counts on the device for agofrt_blockavg_push: counts_out may be NULL
+                                      and is not written */
 };
 
 typedef struct {
@@ -162,7 +165,8 @@ typedef struct {
     uint32_t launches;         /* kernels launched by this call on this context                    */
     uint32_t ndev_local;
     uint32_t world;
-    uint32_t kernel_modes;     /* bit m set: a pair kernel of binning mode m ran (0 thresholds, 1 aggregated, 2 edges, 3 safe-zone) */
+    uint32_t kernel_modes;     /* bit m set: a pair kernel of binning mode m ran (0 thresholds, 1 aggregated, 2 edges,
+                                  3 safe-zone, 4 safe-zone dense); bit 8: the small-system kernel ran */
 } agofrt_stats;
 
 /* counts_out [leff][ntypes*(ntypes+1)][nbin] (host, uint64): the number of ordered pairs (i,j)
@@ -173,6 +177,27 @@ typedef struct {
 AGOFRT_API int agofrt_block(agofrt_plan *plan, size_t primo, unsigned ntimesteps, unsigned leff,
                             unsigned skip, unsigned every, unsigned options, uint64_t *counts_out,
                             uint64_t *edge_pairs_out, agofrt_stats *stats);
+
+/* ---- block averages on the device (MediaVar) ------------------------------------------------- */
+/* MediaVar<T> (lib/include/calcoliblocchi.h:21-65) for T = Gofrt, on the counts agofrt_block leaves on the device:
+ * mean and variance-of-the-mean over blocks with the reference's own sequence of rounded operations per element
+ *     x = count * incr;  delta = x - mean;  mean += delta / (k+1);  var += (x - mean) * delta      (block k = 0, 1, ...)
+ * and var /= (n_b - 1) * n_b at the end, so the result is bit-identical to the host MediaVar fed with the same
+ * blocks in the same order -- without reading every block back and without the eight whole-vector VectorOp passes
+ * per block of BlockAverageG::calcola_custom (lib/include/blockaverage.h:128-144).  The accumulator belongs to a
+ * context and lives on its first device (after the all-reduce every device holds the same counts).
+ *   begin = calcola_begin: len = leff * ntypes*(ntypes+1) * nbin elements, zeroed, k = 0;
+ *   push  = calculate on the counts of the plan's LAST agofrt_block (which must have produced len words);
+ *   end   = calcola_end + read-back into mean_out / var_out (host, [len] doubles each; either may be NULL).
+ * agofrt_plan_last_counts copies the counts of the plan's last agofrt_block to the host (what counts_out would
+ * have received), for callers that ran the block with AGOFRT_OPT_ON_DEVICE and want one block after all. */
+typedef struct agofrt_blockavg agofrt_blockavg;
+AGOFRT_API int agofrt_blockavg_create(agofrt_blockavg **acc, agofrt_ctx *ctx);
+AGOFRT_API int agofrt_blockavg_destroy(agofrt_blockavg *acc);
+AGOFRT_API int agofrt_blockavg_begin(agofrt_blockavg *acc, size_t len);
+AGOFRT_API int agofrt_blockavg_push(agofrt_blockavg *acc, agofrt_plan *plan, double incr);
+AGOFRT_API int agofrt_blockavg_end(agofrt_blockavg *acc, unsigned n_b, double *mean_out, double *var_out);
+AGOFRT_API int agofrt_plan_last_counts(agofrt_plan *plan, uint64_t *counts_out, size_t len);
 
 /* ---- next row of the scope table: the neighbour-count histogram ------------------------------ */
 /* IstogrammaAtomiRaggio::calculate (lib/src/istogrammaatomiraggio.cpp:31-85, `analisi --neighbour r`): for the

@@ -97,8 +97,19 @@ public:
         delete Tvar;
         delete delta;
         delete tmp;
+        delta = tmp = nullptr;
         Tmedio = new T(traiettoria, arg...);
         Tvar = new T(traiettoria, arg...);
+        // Blocks born on the GPU are averaged there (MediaVarDevice: same rounded operations, bit-identical
+        // result, no per-block read-back); ANALISI_DEVICE_BLOCKS=0 keeps the host MediaVar.
+        if constexpr (HasDeviceBlocks<T>::value) {
+            const char *e = std::getenv("ANALISI_DEVICE_BLOCKS");
+            if (!e || std::atoi(e) != 0) {
+                MediaVarDevice<T> media_var(Tmedio, Tvar);
+                calcola_custom<MediaVarDevice<T>>(&media_var, arg...);
+                return;
+            }
+        }
         delta = new T(traiettoria, arg...);
         tmp = new T(traiettoria, arg...);
         MediaVar<T> media_var(Tmedio, Tvar, delta, tmp);

@@ -58,6 +58,9 @@ public:
           debug(debug), traiettoria(t), nbin(nbin), lmax(tmax) {
         // ANALISI_EDGE_PAIRS=1 (the CLI's --edge-pairs): report the pairs within 1 ulp of a bin edge per block
         if (const char *e = std::getenv("ANALISI_EDGE_PAIRS")) report_edges = std::atoi(e) != 0;
+        // ANALISI_KERNEL_OPTIONS=<AGOFRT_OPT_* bits>: kernel selection for A/B measurements (e.g. 256 = never the
+        // small-system kernel); the counts do not depend on it
+        if (const char *e = std::getenv("ANALISI_KERNEL_OPTIONS")) kernel_options = static_cast<unsigned>(std::strtoul(e, nullptr, 0));
     }
     ~Gofrt() { drop_plan(); }
     Gofrt(const This &) = delete;
@@ -134,11 +137,16 @@ public:
             }
             // the trajectory double-buffers its device windows (read-ahead): follow the current one
             analisi_device::check(agofrt_plan_retarget(plan, win), "agofrt_plan_retarget");
-            counts_buf.resize(data_length);
+            // block averages on the device (MediaVarDevice, calcoliblocchi.h): the counts stay on the GPU and this
+            // object's buffer is filled once, after the last block (fetch_block).  The debug dump needs every block.
+            const bool on_device = keep_on_device && !debug;
+            if (!on_device) counts_buf.resize(data_length);
             edge_count = 0;
+            const unsigned options = kernel_options | (report_edges ? AGOFRT_OPT_EDGES : AGOFRT_OPT_DEFAULT) |
+                                     (on_device ? AGOFRT_OPT_ON_DEVICE : AGOFRT_OPT_DEFAULT);
             analisi_device::check(agofrt_block(plan, primo, static_cast<unsigned>(ntimesteps), static_cast<unsigned>(leff),
-                                               static_cast<unsigned>(skip), static_cast<unsigned>(every),
-                                               report_edges ? AGOFRT_OPT_EDGES : AGOFRT_OPT_DEFAULT, counts_buf.data(),
+                                               static_cast<unsigned>(skip), static_cast<unsigned>(every), options,
+                                               on_device ? nullptr : counts_buf.data(),
                                                report_edges ? &edge_count : nullptr, &stats),
                                   "agofrt_block");
             if (report_edges)
@@ -149,9 +157,23 @@ public:
             sum_pair_evals += stats.pair_evals_total;
             ++ncalls;
             // the reference adds incr once per counted pair; count*incr is that sum with one rounding
-            for (unsigned int k = 0; k < data_length; ++k) vdata[k] = static_cast<TFLOAT>(counts_buf[k]) * incr;
+            if (!on_device)
+                for (unsigned int k = 0; k < data_length; ++k) vdata[k] = static_cast<TFLOAT>(counts_buf[k]) * incr;
         }
         if (debug) dump_block();
+    }
+
+    // this repository's addition -- block averages on the device (MediaVarDevice in calcoliblocchi.h drives these):
+    // while keep_on_device is set calculate() leaves the block's counts on the GPU (this object's buffer stays
+    // zero), device_plan() is the plan that holds them, and fetch_block() brings the last block into the buffer
+    // (what calculate() would have left there).
+    void set_keep_on_device(bool on) { keep_on_device = on; }
+    agofrt_plan *device_plan() { return plan; }
+    void fetch_block() {
+        if (!plan || data_length == 0) return;
+        counts_buf.resize(data_length);
+        analisi_device::check(agofrt_plan_last_counts(plan, counts_buf.data(), data_length), "agofrt_plan_last_counts");
+        for (unsigned int k = 0; k < data_length; ++k) vdata[k] = static_cast<TFLOAT>(counts_buf[k]) * incr;
     }
 
     // this repository's additions: the raw integer counts of the last calculate() and its device timings
@@ -214,6 +236,8 @@ private:
     std::vector<uint64_t> counts_buf;
     agofrt_stats stats{};
     bool report_edges = false;
+    bool keep_on_device = false;
+    unsigned kernel_options = 0;
     uint64_t edge_count = 0;
     double sum_kernel_ms = 0, sum_total_ms = 0;
     uint64_t sum_pair_evals = 0;

@@ -150,6 +150,8 @@ void define_block_average(py::module &m, const std::string &suffix) {
         .def("mean", [as_array](BA &b) { return as_array(b.media()); })
         .def("variance", [as_array](BA &b) { return as_array(b.varianza()); })
         .def("block_size", &BA::block_size)
+        .def("last_block", [as_array](BA &b) { return as_array(b.puntatoreCalcolo()); },
+             "the last block as the calculation object holds it (puntatoreCalcolo)")
         .def("get_columns_description", [](BA &b) { return b.puntatoreCalcolo()->get_columns_description(); })
         .def("stats", [](BA &b) {
             G *g = b.puntatoreCalcolo();

@@ -180,8 +180,9 @@ def test_cli_blocks_vs_oracle(host, tmp_path, tri, ntypes, args):
     assert head[0].startswith("# The first column is the time difference") and len(head) == 3 + ntypes * (ntypes + 1)
 
 
+@pytest.mark.parametrize("device_blocks", ["1", "0"], ids=["MediaVarDevice", "MediaVar"])
 @pytest.mark.parametrize("name,S", [("pair_corr_no_t", 1), ("pair_corr_t", 10)])
-def test_cli_reference_golden_text(host, tmp_path, name, S):
+def test_cli_reference_golden_text(host, tmp_path, name, S, device_blocks):
     """reference tests/test_cli.sh:33-34 verbatim: analisi -i lammps2020.bin -g 100 -F 0.0 4.0 -S {1,10} -s 8,
     stdout compared with the reference's golden text (tests/golden/cli_*.txt) the way the script does.
     Needs the 51 MB input, copied to tests/_refdata by build() where the reference tree exists."""
@@ -189,8 +190,10 @@ def test_cli_reference_golden_text(host, tmp_path, name, S):
     path = os.path.join(REFDATA, "lammps2020.bin")
     if not os.path.exists(path):
         pytest.skip("tests/_refdata/lammps2020.bin not present")
+    # the block averages run on the device by default (MediaVarDevice) and on the host with ANALISI_DEVICE_BLOCKS=0
     r = subprocess.run([cli, "-i", path, "-g", "100", "-F", "0.0", "4.0", "-S", str(S), "-s", "8"], stdout=subprocess.PIPE,
-                       stderr=subprocess.PIPE, text=True, cwd=str(tmp_path), timeout=900)
+                       stderr=subprocess.PIPE, text=True, cwd=str(tmp_path), timeout=900,
+                       env=dict(os.environ, ANALISI_DEVICE_BLOCKS=device_blocks))
     assert r.returncode == 0, r.stderr[-2000:]
     gold = open(os.path.join(GOLDEN, "cli_" + name + ".txt")).read()
     assert r.stdout.rstrip("\n") == gold.rstrip("\n")   # `$(...)` strips trailing newlines in the script
@@ -233,12 +236,14 @@ def test_cli_c1_bundled_trajectory(host, tmp_path):
     assert got == want
 
 
+@pytest.mark.parametrize("device_blocks", ["1", "0"], ids=["MediaVarDevice", "MediaVar"])
 @pytest.mark.parametrize("kind", ["numpy", "lammps"])
-def test_block_average_binding_vs_oracle(host, tmp_path, kind):
+def test_block_average_binding_vs_oracle(host, tmp_path, kind, device_blocks, monkeypatch):
     """GofrtBlockAverage (BlockAverageG<TR, Gofrt> from python; TraiettoriaF<Trajectory_numpy> is this
     repository's addition): mean and variance of the mean over blocks, bit-identical to the oracle's MediaVar
     over count*incr blocks (power-of-two incr: the blocks themselves are exact)."""
     _, pa = host
+    monkeypatch.setenv("ANALISI_DEVICE_BLOCKS", device_blocks)   # read by BlockAverageG::calculate
     nfr, n_b, lmax, skip, nbin = 41, 4, 3, 2, 24
     pos, box, types = synth.small_case(33, (5, 4, 4), 1.08, 2, True, nfr)
     bi = synth.lammps_rows_to_internal(box)
@@ -264,6 +269,8 @@ def test_block_average_binding_vs_oracle(host, tmp_path, kind):
     mean, var = oracle.mediavar(np.array(blocks))
     assert np.array_equal(ba.mean(), mean)
     assert np.array_equal(ba.variance(), var)
+    # the calculation object is left holding its last block, whichever class consumed the blocks
+    assert np.array_equal(np.asarray(ba.last_block()), blocks[-1])
     st = ba.stats()
     assert st["blocks"] == n_b and st["pair_evals"] == n_b * lmax * 5 * len(types) ** 2
 

@@ -25,13 +25,24 @@ def gpu_counts(ctx, pos, box_internal, ids, ntypes, rmin, rmax, nbin, tmax, nts,
     return out
 
 
-def test_gofr_numpy_golden(ctx):
+# systems of up to 128 device slots take the small-system kernel (one job per warp) unless told otherwise: the
+# small fixtures run through both kernels
+BOTH_KERNELS = pytest.mark.parametrize("no_small", [0, cabi.OPT_NO_SMALL], ids=["small-kernel", "tile-kernel"])
+
+
+def ran_small(st):
+    return bool(st["kernel_modes"] & cabi.MODE_BIT_SMALL)
+
+
+@BOTH_KERNELS
+def test_gofr_numpy_golden(ctx, no_small):
     """reference tests/test_gofrt.py: ortho, UNWRAPPED input (many images per pair), 3 types, 10 lags."""
     z = load_golden("gofr_numpy.npz")
     rmin, rmax, nbin, tmax, skip, nts = z["params"]
     c, st = gpu_counts(ctx, z["pos"], z["box_internal"], z["types"], 3, rmin, rmax, int(nbin), int(tmax), int(nts),
-                       skip=int(skip))
+                       skip=int(skip), options=no_small)
     assert np.array_equal(c, z["counts"])
+    assert ran_small(st) == (no_small == 0)
     incr = cabi.gofrt_incr(int(nts), int(skip))
     v = c * incr
     nz = z["csv"] != 0
@@ -40,7 +51,8 @@ def test_gofr_numpy_golden(ctx):
     assert st["pair_evals_total"] == 10 * 70 * 56 * 56
 
 
-def test_gofr_notebook_golden(ctx):
+@BOTH_KERNELS
+def test_gofr_notebook_golden(ctx, no_small):
     """reference tests/test_notebook.py: mmap trajectory, wrap on; the wrap itself runs on the GPU."""
     z = load_golden("gofr_notebook.npz")
     pos = z["pos_unwrapped"].copy()
@@ -49,10 +61,11 @@ def test_gofr_notebook_golden(ctx):
     rmin, rmax, nbin, tmax, skip, nts = z["params"]
     nt = int(z["types"].max()) + 1
     c, st = gpu_counts(ctx, pos, z["box_internal"], z["types"], nt, rmin, rmax, int(nbin), int(tmax), int(nts),
-                       skip=int(skip))
+                       skip=int(skip), options=no_small)
     assert np.array_equal(c, z["counts"])
     assert st["jobs_fast"] == st["jobs"]  # wrapped orthorhombic input: single-pass minimum image proven
-    assert st["kernel_modes"] in (1 << 3, 1 << 4)   # ... binned by a safe-zone kernel
+    assert st["kernel_modes"] & 0xff in (1 << 3, 1 << 4)   # ... binned by a safe-zone kernel
+    assert ran_small(st) == (no_small == 0)
 
 
 def test_min_image_and_pbc_golden(ctx):
@@ -79,7 +92,8 @@ def test_min_image_and_pbc_golden(ctx):
 @pytest.mark.parametrize("name", LIVE_CASES)
 @pytest.mark.parametrize("options", [0, cabi.OPT_FORCE_GENERAL, cabi.OPT_AGGREGATE, cabi.OPT_NO_SAFE,
                                      cabi.OPT_DENSE, cabi.OPT_SPARSE, cabi.OPT_NO_UBOX, cabi.OPT_NO_UBOX | cabi.OPT_NO_SAFE])
-def test_live_reference_cases(ctx, name, options):
+@BOTH_KERNELS
+def test_live_reference_cases(ctx, name, options, no_small):
     """Fixtures computed by the compiled reference: triclinic, NPT, unwrapped, big tilt, ragged loops."""
     d = live_case(name)
     rmin, rmax, nbin, tmax, skip, every, nts, primo = d["params"]
@@ -89,8 +103,9 @@ def test_live_reference_cases(ctx, name, options):
         ctx.pbc_wrap(pos, d["box_internal"])
     assert np.array_equal(pos, d["pos_ref"])
     c, st = gpu_counts(ctx, pos, d["box_internal"], ids, nt, rmin, rmax, int(nbin), int(tmax), int(nts),
-                       primo=int(primo), skip=int(skip), every=int(every), options=options)
+                       primo=int(primo), skip=int(skip), every=int(every), options=options | no_small)
     assert np.array_equal(c, d["counts"])
+    assert ran_small(st) == (no_small == 0)   # every live fixture has at most 120 atoms
     incr = cabi.gofrt_incr(int(nts), int(skip))
     v, ref = c * incr, d["vdata"]
     nz = ref != 0
@@ -103,14 +118,15 @@ def test_live_reference_cases(ctx, name, options):
 
 
 @pytest.mark.parametrize("name", LIVE_CASES)
-def test_edge_pairs_match_oracle(ctx, name):
+@BOTH_KERNELS
+def test_edge_pairs_match_oracle(ctx, name, no_small):
     """Pairs whose d2 is a bin threshold or the double just below one are reported separately."""
     d = live_case(name)
     rmin, rmax, nbin, tmax, skip, every, nts, primo = d["params"]
     ids, nt = d["type_ids"], int(d["type_ids"].max()) + 1
     pos = d["pos_ref"]
     c, st, e = gpu_counts(ctx, pos, d["box_internal"], ids, nt, rmin, rmax, int(nbin), int(tmax), int(nts),
-                          primo=int(primo), skip=int(skip), every=int(every), edges=True)
+                          primo=int(primo), skip=int(skip), every=int(every), edges=True, options=no_small)
     co, eo = oracle.counts(pos, d["box_internal"], ids, rmin, rmax, int(nbin), int(tmax), int(nts), primo=int(primo),
                            skip=int(skip), every=int(every), ntypes=nt, return_edges=True)
     assert np.array_equal(c, co)
@@ -152,7 +168,7 @@ def test_multi_tile_random(ctx, triclinic):
     c2, st2 = gpu_counts(ctx, pos, bi, types, 2, *args, skip=2, options=cabi.OPT_FORCE_GENERAL | cabi.OPT_AGGREGATE)
     assert np.array_equal(c2, co)
     c3, st3 = gpu_counts(ctx, pos, bi, types, 2, *args, skip=2, options=cabi.OPT_NO_SAFE)
-    assert np.array_equal(c3, co) and st3["kernel_modes"] == 1
+    assert np.array_equal(c3, co) and st3["kernel_modes"] == 1   # 1320 atoms: never the small-system kernel
     for opt, bit in ((cabi.OPT_DENSE, 4), (cabi.OPT_SPARSE, 3)):
         c4, st4 = gpu_counts(ctx, pos, bi, types, 2, *args, skip=2, options=opt)
         assert np.array_equal(c4, co) and st4["kernel_modes"] == 1 << bit
@@ -435,4 +451,128 @@ def test_msd_vs_oracle(ctx, cm_msd, cm_self, lmax, skip):
     assert st["jobs"] == v.shape[0] * ((nts + skip - 1) // skip)
     with pytest.raises(cabi.AgofrtError):
         tr.msd(20, 14, 0, 1)   # needs frames beyond the window
+    tr.close()
+
+
+# ---- the small-system kernel (up to 128 device slots: one (lag, origin) job per warp) -----------------------------
+def _small_system(seed, natoms, ntypes, triclinic, nframes, npt=False):
+    """`natoms` atoms cut out of a jittered lattice (the box shrunk to match), random types of unequal share."""
+    rng = np.random.default_rng([seed, natoms, ntypes])
+    cells = (6, 5, 5)
+    pos, box, _ = synth.small_case(seed, cells, 1.1, 1, triclinic, nframes, npt=npt)
+    pick = np.sort(rng.choice(pos.shape[1], natoms, replace=False))
+    pos = np.ascontiguousarray(pos[:, pick])
+    types = np.minimum((rng.random(natoms) ** 2 * ntypes).astype(np.int32), ntypes - 1)
+    types[:ntypes] = np.arange(ntypes)   # every type present
+    bi = synth.lammps_rows_to_internal(box)
+    return pos, bi, types.astype(np.int32)
+
+
+@pytest.mark.parametrize("natoms,ntypes,triclinic", [(5, 1, False), (33, 2, True), (56, 2, False), (64, 1, True),
+                                                     (65, 3, False), (97, 2, True), (128, 1, False), (122, 3, True)])
+def test_small_system_kernel(ctx, natoms, ntypes, triclinic):
+    """One job per warp, runs of one lag per CTA: same counts as the oracle and as the tile kernel, for one and two
+    i sub-tiles per job, ghost slots in every type group, many units per lag and ragged lag / origin loops."""
+    nframes = 40
+    pos, bi, types = _small_system(400 + natoms, natoms, ntypes, triclinic, nframes)
+    ctx.pbc_wrap(pos, bi)
+    args = (0.3, 2.9, 64, 9, 30)   # rmin, rmax, nbin, tmax, ntimesteps: 9 lags x 30 origins
+    co = oracle.counts(pos, bi, types, *args, ntypes=ntypes)
+    c, st = gpu_counts(ctx, pos, bi, types, ntypes, *args)
+    assert np.array_equal(c, co)
+    assert ran_small(st) and st["jobs"] == 9 * 30 and st["pair_evals"] == 9 * 30 * natoms * natoms
+    c2, st2 = gpu_counts(ctx, pos, bi, types, ntypes, *args, options=cabi.OPT_NO_SMALL)
+    assert np.array_equal(c2, co) and not ran_small(st2)
+    # ragged loops (skip does not divide ntimesteps, every > 1) and a block that does not start at frame 0
+    kw = dict(primo=3, skip=4, every=2)
+    co3 = oracle.counts(pos, bi, types, 0.3, 2.9, 64, 7, 27, ntypes=ntypes, **kw)
+    c3, st3 = gpu_counts(ctx, pos, bi, types, ntypes, 0.3, 2.9, 64, 7, 27, **kw)
+    assert np.array_equal(c3, co3) and ran_small(st3)
+    # every binning mode and both minimum-image paths of the small-system kernel
+    for opt in (cabi.OPT_FORCE_GENERAL, cabi.OPT_AGGREGATE, cabi.OPT_NO_SAFE, cabi.OPT_DENSE, cabi.OPT_SPARSE,
+                cabi.OPT_NO_UBOX, cabi.OPT_NO_UBOX | cabi.OPT_FORCE_GENERAL | cabi.OPT_NO_SAFE):
+        c4, st4 = gpu_counts(ctx, pos, bi, types, ntypes, *args, options=opt)
+        assert np.array_equal(c4, co), opt
+        assert ran_small(st4)
+    c5, st5, e5 = gpu_counts(ctx, pos, bi, types, ntypes, *args, edges=True)
+    _, eo = oracle.counts(pos, bi, types, *args, ntypes=ntypes, return_edges=True)
+    assert np.array_equal(c5, co) and e5 == eo and ran_small(st5)
+
+
+@pytest.mark.parametrize("natoms,triclinic,wrap", [(56, False, False), (90, True, False), (70, True, True)])
+def test_small_system_kernel_npt_and_unwrapped(ctx, natoms, triclinic, wrap):
+    """A box that changes every frame (the box of the ORIGIN frame serves both atoms) and unwrapped input (the
+    literal minimum-image loops) through the small-system kernel."""
+    pos, bi, types = _small_system(500 + natoms, natoms, 2, triclinic, 24, npt=True)
+    if wrap:
+        ctx.pbc_wrap(pos, bi)
+    else:
+        # every atom whole cells away from where it was, a different number for each atom
+        shift = np.random.default_rng(natoms).integers(-2, 3, size=(1, natoms, 3))
+        pos = pos + shift * bi[:, None, 3:6] * 2
+    args = (0.0, 3.1, 50, 6, 18)
+    co = oracle.counts(pos, bi, types, *args, ntypes=2)
+    c, st = gpu_counts(ctx, pos, bi, types, 2, *args)
+    assert np.array_equal(c, co) and ran_small(st)
+    if not wrap:
+        assert st["jobs_fast"] < st["jobs"]
+
+
+def test_small_system_many_units_per_lag(ctx):
+    """Enough origins that every lag is cut into several runs, each merged by a different CTA."""
+    pos, bi, types = _small_system(77, 56, 2, False, 1500)
+    ctx.pbc_wrap(pos, bi)
+    args = (0.7, 3.5, 200, 3, 1400)   # 3 lags x 1400 origins
+    co = oracle.counts(pos, bi, types, *args, ntypes=2)
+    c, st = gpu_counts(ctx, pos, bi, types, 2, *args)
+    assert np.array_equal(c, co) and ran_small(st)
+    assert int(c.sum()) == int(co.sum())
+
+
+# ---- block averages on the device (MediaVar) ------------------------------------------------------------------------
+def test_block_average_on_device(ctx):
+    """agofrt_blockavg_*: mean and variance of the mean over blocks, bit-identical to the oracle's MediaVar
+    (reference lib/include/calcoliblocchi.h:21-65) fed with count*incr of the same blocks."""
+    pos, bi, types = _small_system(91, 80, 2, True, 70)
+    ctx.pbc_wrap(pos, bi)
+    rmin, rmax, nbin, tmax = 0.2, 3.0, 48, 4
+    n_b, s, skip = 6, 10, 3
+    incr = cabi.gofrt_incr(s, skip)
+    tr = cabi.DeviceTrajectory(ctx, pos.shape[1], bi.shape[1], types, 2, pos.shape[0])
+    tr.upload(0, np.ascontiguousarray(pos), bi)
+    plan = cabi.Plan(tr, rmin, rmax, nbin)
+    leff = cabi.gofrt_leff(s, tmax)
+    acc = cabi.BlockAverage(ctx)
+    with pytest.raises(cabi.AgofrtError):
+        acc.push(plan, incr)                      # before begin
+    acc.begin(leff * 6 * nbin)
+    with pytest.raises(cabi.AgofrtError):
+        acc.push(plan, incr)                      # no block on the device yet
+    blocks = []
+    for b in range(n_b):
+        none, st = plan.block(b * s, s, leff, skip, 1, options=cabi.OPT_ON_DEVICE)
+        assert none is None
+        acc.push(plan, incr)
+        got = plan.last_counts(leff)
+        ref = oracle.counts(pos, bi, types, rmin, rmax, nbin, tmax, s, primo=b * s, skip=skip, ntypes=2)
+        assert np.array_equal(got, ref)
+        blocks.append(ref * incr)
+    mean, var = acc.end(n_b)
+    omean, ovar = oracle.mediavar(np.array(blocks))
+    assert np.array_equal(mean, omean.ravel())    # bit-identical
+    assert np.array_equal(var, ovar.ravel())
+    assert (var > 0).any()
+    # a block of another size is refused, as VectorOp refuses operands of different sizes
+    acc.begin(leff * 6 * nbin)
+    plan.block(0, s, leff - 1, skip, 1, options=cabi.OPT_ON_DEVICE)
+    with pytest.raises(cabi.AgofrtError):
+        acc.push(plan, incr)
+    # the accumulator starts over at begin(): one block -> mean = the block, variance 0/0
+    acc.begin(leff * 6 * nbin)
+    plan.block(0, s, leff, skip, 1, options=cabi.OPT_ON_DEVICE)
+    acc.push(plan, incr)
+    mean1, var1 = acc.end(1)
+    assert np.array_equal(mean1, blocks[0].ravel()) and np.isnan(var1).all()
+    acc.close()
+    plan.close()
     tr.close()
