@@ -1091,6 +1091,34 @@ static bool job_is_single_pass(const agofrt_traj *t, size_t fi, size_t fj) {
     return true;
 }
 
+// The same proof for EVERY pair of frames in [f0, f1] at once, from the bounds of the whole range: the rounded
+// difference is monotone in its operands, so the per-job D of job_is_single_pass never exceeds max - min over
+// the range, and a range that passes here would pass job by job (the converse need not hold: the caller then
+// falls back to the per-job test).  Turns the classification of a block of 10^5 small jobs from one test per
+// job into one test per frame.
+static bool range_is_single_pass(const agofrt_traj *t, size_t f0, size_t f1) {
+    double lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (size_t f = f0; f <= f1; ++f)
+        for (int c = 0; c < 3; ++c) {
+            lo[c] = std::min(lo[c], t->bounds[f * 6 + c]);
+            hi[c] = std::max(hi[c], t->bounds[f * 6 + 3 + c]);
+        }
+    double D[3];
+    for (int c = 0; c < 3; ++c) {
+        D[c] = std::fabs(hi[c] - lo[c]);
+        if (!std::isfinite(D[c])) return false;
+    }
+    const double m = 2.99;
+    for (size_t f = f0; f <= f1; ++f) {
+        const double *b = &t->box6[f * 6];
+        const double xy = std::fabs(b[3]), xz = std::fabs(b[4]), yz = std::fabs(b[5]);
+        if (!(D[2] <= m * b[2])) return false;
+        if (!(D[1] + yz <= m * b[1])) return false;
+        if (!(D[0] + xz + xy <= m * b[0])) return false;
+    }
+    return true;
+}
+
 extern "C" int agofrt_block(agofrt_plan *p, size_t primo, unsigned ntimesteps, unsigned leff, unsigned skip,
                             unsigned every, unsigned options, uint64_t *counts_out, uint64_t *edge_pairs_out,
                             agofrt_stats *stats) {
@@ -1130,11 +1158,15 @@ extern "C" int agofrt_block(agofrt_plan *p, size_t primo, unsigned ntimesteps, u
             return fail(AGOFRT_ERR_NONFINITE,
                         "the window holds an infinite coordinate or a non-positive / non-finite box edge "
                         "(the reference's minimum image would not terminate)");
+        const bool may_fast = !(options & AGOFRT_OPT_FORCE_GENERAL);
+        const bool all_fast = may_fast && range_is_single_pass(t, primo - t->first_frame, last - t->first_frame);
+        const size_t expect = static_cast<size_t>((leff + every - 1) / every) * ((ntimesteps + skip - 1) / skip);
+        (may_fast ? jobs_fast : jobs_gen).reserve(expect);
         for (unsigned tl = 0; tl < leff; tl += every)
             for (unsigned im = 0; im < ntimesteps; im += skip) {
                 const size_t fi = primo + im - t->first_frame;
                 Job j{static_cast<int>(fi), static_cast<int>(fi + tl), static_cast<int>(tl)};
-                const bool fast = !(options & AGOFRT_OPT_FORCE_GENERAL) && job_is_single_pass(t, fi, fi + tl);
+                const bool fast = all_fast || (may_fast && job_is_single_pass(t, fi, fi + tl));
                 (fast ? jobs_fast : jobs_gen).push_back(j);
                 ++njobs;
             }

@@ -126,7 +126,9 @@ public:
             throw std::runtime_error(
                 "trajectory is too short for this kind of calculation. Select a different starting timestep or lower the "
                 "size of the average or the lenght of the time lag");
-        azzera();
+        // blocks kept on the device (MediaVarDevice): this object's buffer is only filled by fetch_block()
+        const bool on_device = keep_on_device && !debug;
+        if (!on_device) azzera();
         incr = (ntimesteps / skip > 0) ? 1.0 / static_cast<int>(ntimesteps / skip) : 1.0;
         if (data_length > 0) {
             agofrt_traj *win = traiettoria->device_window();
@@ -139,7 +141,6 @@ public:
             analisi_device::check(agofrt_plan_retarget(plan, win), "agofrt_plan_retarget");
             // block averages on the device (MediaVarDevice, calcoliblocchi.h): the counts stay on the GPU and this
             // object's buffer is filled once, after the last block (fetch_block).  The debug dump needs every block.
-            const bool on_device = keep_on_device && !debug;
             if (!on_device) counts_buf.resize(data_length);
             edge_count = 0;
             const unsigned options = kernel_options | (report_edges ? AGOFRT_OPT_EDGES : AGOFRT_OPT_DEFAULT) |
@@ -164,8 +165,8 @@ public:
     }
 
     // this repository's addition -- block averages on the device (MediaVarDevice in calcoliblocchi.h drives these):
-    // while keep_on_device is set calculate() leaves the block's counts on the GPU (this object's buffer stays
-    // zero), device_plan() is the plan that holds them, and fetch_block() brings the last block into the buffer
+    // while keep_on_device is set calculate() leaves the block's counts on the GPU (this object's buffer is not
+    // touched), device_plan() is the plan that holds them, and fetch_block() brings the last block into the buffer
     // (what calculate() would have left there).
     void set_keep_on_device(bool on) { keep_on_device = on; }
     agofrt_plan *device_plan() { return plan; }
