@@ -1195,8 +1195,8 @@ extern "C" int agofrt_block(agofrt_plan *p, size_t primo, unsigned ntimesteps, u
                                                       static_cast<unsigned long long>(njobs * per_job));
 
     // ---- small systems: runs of jobs of one lag, dealt to the warps of a CTA (pair_small_kernel) ----
-    const bool small = t->npad > 0 && t->npad <= kSmallJ && !(options & AGOFRT_OPT_NO_SMALL);
-    const int nsub = small ? (t->npad + 32 * kIPT - 1) / (32 * kIPT) : 1;
+    const bool small = t->npad > 0 && t->npad <= kSmallMax && !(options & AGOFRT_OPT_NO_SMALL);
+    const int nsub = small ? (t->npad + 32 * kIPT - 1) / (32 * kIPT) : 1;   // warps per job
     std::vector<SmallUnit> units_fast, units_gen;
     if (small && !nothing) {
         // a unit should dwarf the merge of the CTA's histogram rows that ends it (rowlen words scanned,
@@ -1204,7 +1204,7 @@ extern "C" int agofrt_block(agofrt_plan *p, size_t primo, unsigned ntimesteps, u
         const uint64_t pairs_per_job = static_cast<uint64_t>(t->npad) * t->npad;
         const uint64_t by_merge = (128ull * rowlen + pairs_per_job - 1) / pairs_per_job;
         const uint64_t by_ctas = (njobs + 6ull * total_ctas - 1) / (6ull * total_ctas);
-        const uint64_t wave = static_cast<uint64_t>(kThreads / 32 / nsub);   // jobs the warps of a CTA take at a time
+        const uint64_t wave = static_cast<uint64_t>(kThreads / 32 / nsub);   // jobs a CTA works on at a time
         uint64_t chunk = std::max<uint64_t>(std::max(by_merge, by_ctas), wave);
         chunk = std::min<uint64_t>((chunk + wave - 1) / wave * wave, 65536);   // a unit's counts stay far below 2^32
         for (int pass = 0; pass < 2; ++pass) {

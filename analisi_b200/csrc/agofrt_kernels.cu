@@ -398,18 +398,18 @@ struct PairConst {
 // the binning of the group's pairs without per-pair branches.
 //   DIAG: the j atoms may include one of this thread's own i atoms (i == j goes to the "self" rows).
 // All kIPT x kJU squared distances of one group (straight-line, independent FP64 chains).
-//   JROW: doubles between the x, y and z rows of the staged j coordinates
-template <bool TRI, bool FAST, int JROW>
+//   jrow_bytes: bytes between the x, y and z rows of the staged j coordinates (a literal in pair_kernel)
+template <bool TRI, bool FAST>
 __device__ __forceinline__ void group_distances(const PairConst &c, const double (&xi)[kIPT], const double (&yi)[kIPT],
-                                                const double (&zi)[kIPT], uint32_t sx_addr, int jrel,
+                                                const double (&zi)[kIPT], uint32_t sx_addr, uint32_t jrow_bytes, int jrel,
                                                 double (&d2)[kIPT][kJU], bool &wrap_ok) {
     double xj[kJU], yj[kJU], zj[kJU];
 #pragma unroll
     for (int q = 0; q < kJU; q += 2) {
         const uint32_t a = sx_addr + static_cast<uint32_t>(jrel + q) * 8u;
         const double2 vx = lds_f64x2(a);
-        const double2 vy = lds_f64x2(a + JROW * 8u);
-        const double2 vz = lds_f64x2(a + 2u * JROW * 8u);
+        const double2 vy = lds_f64x2(a + jrow_bytes);
+        const double2 vz = lds_f64x2(a + 2u * jrow_bytes);
         xj[q] = vx.x;
         xj[q + 1] = vx.y;
         yj[q] = vy.x;
@@ -469,15 +469,15 @@ __device__ __forceinline__ void group_bin_safe(const PairParams &p, const PairCo
     }
 }
 
-template <bool TRI, bool FAST, int MODE, bool DIAG, int JROW = kTileJ>
+template <bool TRI, bool FAST, int MODE, bool DIAG>
 __device__ __forceinline__ void process_group(const PairParams &p, const PairConst &c, const double (&xi)[kIPT],
                                               const double (&yi)[kIPT], const double (&zi)[kIPT],
                                               const int (&ii)[kIPT], const unsigned int (&row)[kIPT],
-                                              uint32_t sx_addr, int jrel, int j, const double2 *s_thr2,
+                                              uint32_t sx_addr, uint32_t jrow_bytes, int jrel, int j, const double2 *s_thr2,
                                               const double *s_thrf, unsigned int *s_hist, unsigned int self_off,
                                               unsigned long long &edges, bool &wrap_ok) {
     double d2[kIPT][kJU];
-    group_distances<TRI, FAST, JROW>(c, xi, yi, zi, sx_addr, jrel, d2, wrap_ok);
+    group_distances<TRI, FAST>(c, xi, yi, zi, sx_addr, jrow_bytes, jrel, d2, wrap_ok);
     if (MODE == MODE_EDGES) {
 #pragma unroll
         for (int k = 0; k < kIPT; ++k) {
@@ -757,15 +757,15 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) pair_kernel(const PairPa
                 const int db = min(max(wi0 + 32 * kIPT, lo), hi);
 #pragma unroll 1
                 for (int j = lo; j < da; j += kJU)
-                    process_group<TRI, FAST, MODE, false>(p, c, xi, yi, zi, ii, row, sx_addr, j - j0, j, s_thr2, s_thrf,
+                    process_group<TRI, FAST, MODE, false>(p, c, xi, yi, zi, ii, row, sx_addr, kTileJ * 8u, j - j0, j, s_thr2, s_thrf,
                                                           s_hist, self_off, edges, wrap_ok);
 #pragma unroll 1
                 for (int j = da; j < db; j += kJU)
-                    process_group<TRI, FAST, MODE, true>(p, c, xi, yi, zi, ii, row, sx_addr, j - j0, j, s_thr2, s_thrf,
+                    process_group<TRI, FAST, MODE, true>(p, c, xi, yi, zi, ii, row, sx_addr, kTileJ * 8u, j - j0, j, s_thr2, s_thrf,
                                                          s_hist, self_off, edges, wrap_ok);
 #pragma unroll 1
                 for (int j = db; j < hi; j += kJU)
-                    process_group<TRI, FAST, MODE, false>(p, c, xi, yi, zi, ii, row, sx_addr, j - j0, j, s_thr2, s_thrf,
+                    process_group<TRI, FAST, MODE, false>(p, c, xi, yi, zi, ii, row, sx_addr, kTileJ * 8u, j - j0, j, s_thr2, s_thrf,
                                                           s_hist, self_off, edges, wrap_ok);
             }
         }
@@ -788,23 +788,24 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) pair_kernel(const PairPa
 }
 
 // ---------------------------------------------------------------------------------------------
-// the pair kernel for SMALL systems (npad <= kSmallJ slots, e.g. the 56 atoms of the reference's bundled
-// tests/data/lammps.bin)
+// the pair kernel for SMALL systems (npad <= kSmallMax = 512 slots: the 56 atoms of the reference's bundled
+// tests/data/lammps.bin, ab-initio cells of a few hundred atoms)
 //
 // pair_kernel gives a whole CTA (512 i slots) to one (lag, origin) job; with a few dozen atoms nine lanes in
 // ten hold no atom, and because consecutive tickets go to different CTAs nearly every job ends with a merge
 // of the CTA's histogram into the global row of its lag.  Here the work unit is a RUN OF JOBS OF ONE LAG
-// (SmallUnit, cut by the host) and the jobs of a unit are dealt to the WARPS of the CTA: a warp holds the
-// (up to 64) i atoms of its job in registers, copies the j frame into its own 3 KB slice of the stage area
-// with coalesced loads and walks it with the same process_group as the large kernel -- same arithmetic,
-// same binning modes, same shared-memory histogram rows.  Warps never wait for each other inside a unit;
-// the CTA meets once per unit, to merge its rows into the global row of the unit's lag.
-// Systems of 65..128 slots use two warps (two i sub-tiles) per job.
+// (SmallUnit, cut by the host) and the jobs of a unit are dealt to GROUPS OF W WARPS, W = ceil(npad / 64):
+// every warp of a group holds one sub-tile of 64 i slots of the group's job in registers, the group copies the
+// j frame into its own slice of the stage area (64*W slots per coordinate row, coalesced loads) and every warp
+// walks it with the same process_group as the large kernel -- same arithmetic, same binning modes, same
+// shared-memory histogram rows.  A CTA works on 8 / W jobs at a time; groups only meet their own warps (a named
+// barrier, or __syncwarp when W = 1) around the copy of a j frame, and the CTA meets once per unit, to merge
+// its rows into the global row of the unit's lag.
 // ---------------------------------------------------------------------------------------------
 constexpr int kWarps = kThreads / 32;
-static_assert(kWarps * 3 * kSmallJ <= kStages * 3 * kTileJ, "the warp slices live in the stage area of pair_kernel");
-static_assert(kSmallJ % (32 * kIPT) == 0 && kWarps % (kSmallJ / (32 * kIPT)) == 0,
-              "a warp keeps the same i sub-tile for every job it takes");
+constexpr int kSubTile = 32 * kIPT;   // i slots per warp
+static_assert(kWarps * kSubTile >= kSmallMax, "one job must fit the warps of a CTA");
+static_assert(kWarps * kSubTile * 3 <= kStages * 3 * kTileJ, "the group slices live in the stage area of pair_kernel");
 
 template <bool TRI, bool FAST, int MODE, bool UBOX>
 __global__ void __launch_bounds__(kThreads, kMinBlocks) pair_small_kernel(const PairParams p) {
@@ -833,12 +834,35 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) pair_small_kernel(const 
     PairConst c;
     c.thr2_addr = smem_u32(s_thr2);
     c.hist_addr = smem_u32(s_hist);
-    double *slice = s_stage + static_cast<size_t>(warp) * 3 * kSmallJ;   // this warp's copy of the j frame
-    const uint32_t slice_addr = smem_u32(slice);
 
-    // this warp's i slots: sub-tile `sub` of every job it takes
-    const int nsub = p.n_itiles;
-    const int wi0 = (warp % nsub) * (32 * kIPT);
+    // groups of W warps: group `grp` takes jobs grp, grp + G, ... of a unit; warp `sub` of the group holds the
+    // i slots [sub*64, sub*64 + 64) of every job the group takes.  Warps beyond G*W (W = 3, 5, 6, 7) only take
+    // part in the CTA-wide steps.
+    const int W = p.n_itiles;                // warps per job
+    const int G = kWarps / W;                // jobs a CTA works on at a time
+    const int grp = warp / W, sub = warp - grp * W;
+    const bool working = grp < G;
+    const int srow = W * kSubTile;           // slots per coordinate row of a group slice
+    double *slice = s_stage + static_cast<size_t>(grp) * 3 * srow;
+    const uint32_t slice_addr = smem_u32(slice);
+    const uint32_t jrow_bytes = static_cast<uint32_t>(srow) * 8u;
+    const int gtid = sub * 32 + lane;        // thread within the group
+    const int gthreads = W * 32;
+    // named barriers 1..4, one per group (W >= 2 leaves at most 4 groups); literal ids, so that the CTA reserves
+    // five barriers and not all sixteen
+    auto group_sync = [&]() {
+        __syncwarp();
+        if (W > 1) {
+            switch (grp) {
+                case 0: asm volatile("bar.sync 1, %0;" ::"r"(gthreads) : "memory"); break;
+                case 1: asm volatile("bar.sync 2, %0;" ::"r"(gthreads) : "memory"); break;
+                case 2: asm volatile("bar.sync 3, %0;" ::"r"(gthreads) : "memory"); break;
+                default: asm volatile("bar.sync 4, %0;" ::"r"(gthreads) : "memory"); break;
+            }
+        }
+    };
+
+    const int wi0 = sub * kSubTile;
     int ii[kIPT], ti[kIPT];
 #pragma unroll
     for (int k = 0; k < kIPT; ++k) {
@@ -868,63 +892,65 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) pair_small_kernel(const 
         __syncthreads();
         if (u >= p.unit_end) break;
         const SmallUnit un = p.units[u];
-        const int ntask = un.count * nsub;
 
-        for (int task = warp; task < ntask; task += kWarps) {
-            const Job job = p.jobs[un.begin + task / nsub];
-            if (!UBOX) {
-                const double *bx = p.box + static_cast<size_t>(job.fi) * 6;
-                c.box.lhx = __ldg(bx + 0);
-                c.box.lhy = __ldg(bx + 1);
-                c.box.lhz = __ldg(bx + 2);
-                c.box.xy = __ldg(bx + 3);
-                c.box.xz = __ldg(bx + 4);
-                c.box.yz = __ldg(bx + 5);
-                c.nLx = __dmul_rn(c.box.lhx, -2.0);
-                c.nLy = __dmul_rn(c.box.lhy, -2.0);
-                c.nLz = __dmul_rn(c.box.lhz, -2.0);
-            }
-            double xi[kIPT], yi[kIPT], zi[kIPT];
-            const double *pi = p.pos + static_cast<size_t>(job.fi) * 3 * p.npad;
-#pragma unroll
-            for (int k = 0; k < kIPT; ++k) {
-                if (ii[k] < p.npad) {
-                    xi[k] = pi[ii[k]];
-                    yi[k] = pi[p.npad + ii[k]];
-                    zi[k] = pi[2 * p.npad + ii[k]];
-                } else {
-                    xi[k] = yi[k] = zi[k] = __longlong_as_double(0x7ff8000000000000ll);
+        if (working) {
+            for (int jb = grp; jb < un.count; jb += G) {
+                const Job job = p.jobs[un.begin + jb];
+                if (!UBOX) {
+                    const double *bx = p.box + static_cast<size_t>(job.fi) * 6;
+                    c.box.lhx = __ldg(bx + 0);
+                    c.box.lhy = __ldg(bx + 1);
+                    c.box.lhz = __ldg(bx + 2);
+                    c.box.xy = __ldg(bx + 3);
+                    c.box.xz = __ldg(bx + 4);
+                    c.box.yz = __ldg(bx + 5);
+                    c.nLx = __dmul_rn(c.box.lhx, -2.0);
+                    c.nLy = __dmul_rn(c.box.lhy, -2.0);
+                    c.nLz = __dmul_rn(c.box.lhz, -2.0);
                 }
-            }
-            const double *pj = p.pos + static_cast<size_t>(job.fj) * 3 * p.npad;
-            __syncwarp();   // every lane is done with the previous job's copy
-            for (int q = lane; q < p.npad; q += 32) {
-                slice[q] = pj[q];
-                slice[kSmallJ + q] = pj[p.npad + q];
-                slice[2 * kSmallJ + q] = pj[2 * p.npad + q];
-            }
-            __syncwarp();
-
-            for (int ty = 0; ty < nt; ++ty) {
-                const int lo = s_tstart[ty], hi = s_tstart[ty + 1];
-                if (lo >= hi) continue;
-                unsigned int row[kIPT];
+                double xi[kIPT], yi[kIPT], zi[kIPT];
+                const double *pi = p.pos + static_cast<size_t>(job.fi) * 3 * p.npad;
 #pragma unroll
-                for (int k = 0; k < kIPT; ++k) row[k] = s_rowtab[ti[k] * nt + ty];
-                const int da = min(max(wi0, lo), hi);
-                const int db = min(max(wi0 + 32 * kIPT, lo), hi);
+                for (int k = 0; k < kIPT; ++k) {
+                    if (ii[k] < p.npad) {
+                        xi[k] = pi[ii[k]];
+                        yi[k] = pi[p.npad + ii[k]];
+                        zi[k] = pi[2 * p.npad + ii[k]];
+                    } else {
+                        xi[k] = yi[k] = zi[k] = __longlong_as_double(0x7ff8000000000000ll);
+                    }
+                }
+                const double *pj = p.pos + static_cast<size_t>(job.fj) * 3 * p.npad;
+                group_sync();   // every warp of the group is done with the previous job's copy
+                for (int q = gtid; q < p.npad; q += gthreads) {
+                    slice[q] = pj[q];
+                    slice[srow + q] = pj[p.npad + q];
+                    slice[2 * srow + q] = pj[2 * p.npad + q];
+                }
+                group_sync();
+
+                for (int ty = 0; ty < nt; ++ty) {
+                    const int lo = s_tstart[ty], hi = s_tstart[ty + 1];
+                    if (lo >= hi) continue;
+                    unsigned int row[kIPT];
+#pragma unroll
+                    for (int k = 0; k < kIPT; ++k) row[k] = s_rowtab[ti[k] * nt + ty];
+                    // [lo,hi) = before | overlap with this warp's own atoms | after   (all multiples of kPadGroup)
+                    const int da = min(max(wi0, lo), hi);
+                    const int db = min(max(wi0 + kSubTile, lo), hi);
 #pragma unroll 1
-                for (int j = lo; j < da; j += kJU)
-                    process_group<TRI, FAST, MODE, false, kSmallJ>(p, c, xi, yi, zi, ii, row, slice_addr, j, j, s_thr2,
-                                                                   s_thrf, s_hist, self_off, edges, wrap_ok);
+                    for (int j = lo; j < da; j += kJU)
+                        process_group<TRI, FAST, MODE, false>(p, c, xi, yi, zi, ii, row, slice_addr, jrow_bytes, j, j,
+                                                              s_thr2, s_thrf, s_hist, self_off, edges, wrap_ok);
 #pragma unroll 1
-                for (int j = da; j < db; j += kJU)
-                    process_group<TRI, FAST, MODE, true, kSmallJ>(p, c, xi, yi, zi, ii, row, slice_addr, j, j, s_thr2,
-                                                                  s_thrf, s_hist, self_off, edges, wrap_ok);
+                    for (int j = da; j < db; j += kJU)
+                        process_group<TRI, FAST, MODE, true>(p, c, xi, yi, zi, ii, row, slice_addr, jrow_bytes, j, j,
+                                                             s_thr2, s_thrf, s_hist, self_off, edges, wrap_ok);
 #pragma unroll 1
-                for (int j = db; j < hi; j += kJU)
-                    process_group<TRI, FAST, MODE, false, kSmallJ>(p, c, xi, yi, zi, ii, row, slice_addr, j, j, s_thr2,
-                                                                   s_thrf, s_hist, self_off, edges, wrap_ok);
+                    for (int j = db; j < hi; j += kJU)
+                        process_group<TRI, FAST, MODE, false>(p, c, xi, yi, zi, ii, row, slice_addr, jrow_bytes, j, j,
+                                                              s_thr2, s_thrf, s_hist, self_off, edges, wrap_ok);
+                }
             }
         }
         __syncthreads();

@@ -36,7 +36,7 @@ constexpr int kStages = 2;                  // bulk-copy stages
 constexpr int kPadGroup = 8;                // every type group is padded to a multiple of this
 constexpr int kJU = AGOFRT_JU;              // j atoms per inner step (one LDS.128 per coordinate per two)
 constexpr int kWrapCap = 1 << 20;           // images the general minimum image may add per dimension
-constexpr int kSmallJ = 128;                // systems of up to this many slots go to pair_small_kernel
+constexpr int kSmallMax = 512;              // systems of up to this many slots go to pair_small_kernel
 
 struct Job {
     int fi;    // window-relative frame of the i atoms (its box is used)
@@ -44,7 +44,7 @@ struct Job {
     int tout;  // output lag row
 };
 
-// pair_small_kernel: a run of jobs of ONE lag, dealt to the warps of a CTA
+// pair_small_kernel: a run of jobs of ONE lag, dealt to the warp groups of a CTA
 struct SmallUnit {
     int begin;   // first job of the run (index into PairParams::jobs)
     int count;   // jobs in the run
@@ -68,8 +68,8 @@ struct PairParams {
     double ubox[9];             // UBOX variants: lx/2, ly/2, lz/2, xy, xz, yz, -lx, -ly, -lz of the one box of the window
     unsigned unit_begin, unit_end;
     int npad, ntypes, nbin;
-    int n_itiles, n_jchunks, jchunk;  // jchunk is a multiple of kTileJ; pair_small_kernel: n_itiles = i sub-tiles of
-                                      // 32*kIPT slots per job (1 or 2), the other two unused
+    int n_itiles, n_jchunks, jchunk;  // jchunk is a multiple of kTileJ; pair_small_kernel: n_itiles = warps per job
+                                      // (i sub-tiles of 32*kIPT slots, 1..8), the other two unused
     float inv_dr, c0;                 // bin guess = floor(sqrtf(d2) * inv_dr + c0)
     float c0h, lim, qmax;             // MODE_SAFE: c0 - 0.5, 0.5 - eps, nbin + 0.25 (clamp of the bin coordinate)
     int glo;                          // guard bins below bin 0 in every shared-memory histogram row

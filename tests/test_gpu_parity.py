@@ -25,8 +25,8 @@ def gpu_counts(ctx, pos, box_internal, ids, ntypes, rmin, rmax, nbin, tmax, nts,
     return out
 
 
-# systems of up to 128 device slots take the small-system kernel (one job per warp) unless told otherwise: the
-# small fixtures run through both kernels
+# systems of up to 512 device slots take the small-system kernel (one job per group of warps) unless told
+# otherwise: the small fixtures run through both kernels
 BOTH_KERNELS = pytest.mark.parametrize("no_small", [0, cabi.OPT_NO_SMALL], ids=["small-kernel", "tile-kernel"])
 
 
@@ -263,27 +263,30 @@ def test_size_independent_properties_large(ctx):
     (0.0, 2.6, 3, False),       # 9 counters in all: the warp-aggregated threshold kernel is chosen instead
     (0.0, 2.6, 30, True),       # the plain case
 ])
-def test_guarded_rows_and_fallback(ctx, rmin, rmax, nbin, expect_safe):
+@BOTH_KERNELS
+def test_guarded_rows_and_fallback(ctx, rmin, rmax, nbin, expect_safe, no_small):
     """The unconditional safe-zone binning writes into guard bins for everything outside the histogram; the
     counts must not depend on how many guard bins a row has, nor on the kernel that was chosen."""
     pos, box, types = synth.small_case(71, (7, 6, 6), 1.07, 2, True, 6)
     bi = synth.lammps_rows_to_internal(box)
     ctx.pbc_wrap(pos, bi)
     ref, eref = oracle.counts(pos, bi, types, rmin, rmax, nbin, 3, 3, ntypes=2, return_edges=True)
-    c, st = gpu_counts(ctx, pos, bi, types, 2, rmin, rmax, nbin, 3, 3)
+    c, st = gpu_counts(ctx, pos, bi, types, 2, rmin, rmax, nbin, 3, 3, options=no_small)
+    assert ran_small(st) == (no_small == 0)   # 252 atoms: four warps per job
     assert np.array_equal(c, ref)
     safe_ran = bool(st["kernel_modes"] & ((1 << 3) | (1 << 4)))
     assert safe_ran == expect_safe
-    c2, st2 = gpu_counts(ctx, pos, bi, types, 2, rmin, rmax, nbin, 3, 3, options=cabi.OPT_NO_SAFE)
+    c2, st2 = gpu_counts(ctx, pos, bi, types, 2, rmin, rmax, nbin, 3, 3, options=cabi.OPT_NO_SAFE | no_small)
     assert np.array_equal(c2, ref) and not (st2["kernel_modes"] & ((1 << 3) | (1 << 4)))
-    c3, st3, e3 = gpu_counts(ctx, pos, bi, types, 2, rmin, rmax, nbin, 3, 3, edges=True)
+    c3, st3, e3 = gpu_counts(ctx, pos, bi, types, 2, rmin, rmax, nbin, 3, 3, edges=True, options=no_small)
     assert np.array_equal(c3, ref) and e3 == eref
     for opt in (cabi.OPT_DENSE, cabi.OPT_SPARSE):
-        c4, _ = gpu_counts(ctx, pos, bi, types, 2, rmin, rmax, nbin, 3, 3, options=opt)
+        c4, _ = gpu_counts(ctx, pos, bi, types, 2, rmin, rmax, nbin, 3, 3, options=opt | no_small)
         assert np.array_equal(c4, ref)
 
 
-def test_ghost_slots_and_nan_atoms(ctx):
+@BOTH_KERNELS
+def test_ghost_slots_and_nan_atoms(ctx, no_small):
     """Type groups are padded to 8 slots with NaN ghosts; NaN coordinates of real atoms are never in range
     (as in the reference: every comparison with NaN is false).  Both go through the min.f32 clamp of the
     safe-zone guess or the exact path, never into a counted bin."""
@@ -291,13 +294,13 @@ def test_ghost_slots_and_nan_atoms(ctx):
     bi = synth.lammps_rows_to_internal(box)
     ctx.pbc_wrap(pos, bi)
     ref = oracle.counts(pos, bi, types, 0.0, 2.5, 50, 2, 3, ntypes=3)
-    c, st = gpu_counts(ctx, pos, bi, types, 3, 0.0, 2.5, 50, 2, 3)
+    c, st = gpu_counts(ctx, pos, bi, types, 3, 0.0, 2.5, 50, 2, 3, options=no_small)
     assert np.array_equal(c, ref)
     bad = pos.copy()
     bad[1, 7] = np.nan
     bad[2, 30, 1] = np.nan
     refn = oracle.counts(bad, bi, types, 0.0, 2.5, 50, 2, 3, ntypes=3)
-    cn, stn = gpu_counts(ctx, bad, bi, types, 3, 0.0, 2.5, 50, 2, 3)
+    cn, stn = gpu_counts(ctx, bad, bi, types, 3, 0.0, 2.5, 50, 2, 3, options=no_small)
     assert np.array_equal(cn, refn)
     assert refn.sum() < ref.sum()
 
@@ -454,11 +457,11 @@ def test_msd_vs_oracle(ctx, cm_msd, cm_self, lmax, skip):
     tr.close()
 
 
-# ---- the small-system kernel (up to 128 device slots: one (lag, origin) job per warp) -----------------------------
+# ---- the small-system kernel (up to 512 device slots: one (lag, origin) job per group of ceil(slots/64) warps) -------
 def _small_system(seed, natoms, ntypes, triclinic, nframes, npt=False):
     """`natoms` atoms cut out of a jittered lattice (the box shrunk to match), random types of unequal share."""
     rng = np.random.default_rng([seed, natoms, ntypes])
-    cells = (6, 5, 5)
+    cells = (6, 5, 5) if natoms <= 150 else (8, 8, 8)
     pos, box, _ = synth.small_case(seed, cells, 1.1, 1, triclinic, nframes, npt=npt)
     pick = np.sort(rng.choice(pos.shape[1], natoms, replace=False))
     pos = np.ascontiguousarray(pos[:, pick])
@@ -468,11 +471,15 @@ def _small_system(seed, natoms, ntypes, triclinic, nframes, npt=False):
     return pos, bi, types.astype(np.int32)
 
 
-@pytest.mark.parametrize("natoms,ntypes,triclinic", [(5, 1, False), (33, 2, True), (56, 2, False), (64, 1, True),
-                                                     (65, 3, False), (97, 2, True), (128, 1, False), (122, 3, True)])
+@pytest.mark.parametrize("natoms,ntypes,triclinic", [
+    (5, 1, False), (33, 2, True), (56, 2, False), (64, 1, True),          # one warp per job
+    (65, 3, False), (97, 2, True), (128, 1, False), (110, 3, True),       # two
+    (150, 2, False), (256, 1, True), (300, 2, True), (380, 3, False),     # three, four, five, six
+    (440, 1, False), (490, 2, True), (512, 1, False)])                    # seven, eight
 def test_small_system_kernel(ctx, natoms, ntypes, triclinic):
-    """One job per warp, runs of one lag per CTA: same counts as the oracle and as the tile kernel, for one and two
-    i sub-tiles per job, ghost slots in every type group, many units per lag and ragged lag / origin loops."""
+    """One job per group of W = ceil(slots / 64) warps, runs of one lag per CTA: same counts as the oracle and as
+    the tile kernel, for every W, ghost slots in every type group, several units per lag and ragged lag / origin
+    loops."""
     nframes = 40
     pos, bi, types = _small_system(400 + natoms, natoms, ntypes, triclinic, nframes)
     ctx.pbc_wrap(pos, bi)
@@ -481,6 +488,15 @@ def test_small_system_kernel(ctx, natoms, ntypes, triclinic):
     c, st = gpu_counts(ctx, pos, bi, types, ntypes, *args)
     assert np.array_equal(c, co)
     assert ran_small(st) and st["jobs"] == 9 * 30 and st["pair_evals"] == 9 * 30 * natoms * natoms
+    if natoms > 150:   # the larger cases: the default kernel choice, the tile kernel and the edge count only
+        c2, st2 = gpu_counts(ctx, pos, bi, types, ntypes, *args, options=cabi.OPT_NO_SMALL)
+        assert np.array_equal(c2, co) and not ran_small(st2)
+        c4, st4 = gpu_counts(ctx, pos, bi, types, ntypes, *args, options=cabi.OPT_FORCE_GENERAL | cabi.OPT_NO_UBOX)
+        assert np.array_equal(c4, co) and ran_small(st4)
+        c5, st5, e5 = gpu_counts(ctx, pos, bi, types, ntypes, *args, edges=True)
+        _, eo = oracle.counts(pos, bi, types, *args, ntypes=ntypes, return_edges=True)
+        assert np.array_equal(c5, co) and e5 == eo and ran_small(st5)
+        return
     c2, st2 = gpu_counts(ctx, pos, bi, types, ntypes, *args, options=cabi.OPT_NO_SMALL)
     assert np.array_equal(c2, co) and not ran_small(st2)
     # ragged loops (skip does not divide ntimesteps, every > 1) and a block that does not start at frame 0
@@ -499,7 +515,8 @@ def test_small_system_kernel(ctx, natoms, ntypes, triclinic):
     assert np.array_equal(c5, co) and e5 == eo and ran_small(st5)
 
 
-@pytest.mark.parametrize("natoms,triclinic,wrap", [(56, False, False), (90, True, False), (70, True, True)])
+@pytest.mark.parametrize("natoms,triclinic,wrap", [(56, False, False), (90, True, False), (70, True, True),
+                                                   (200, True, False), (330, False, True)])
 def test_small_system_kernel_npt_and_unwrapped(ctx, natoms, triclinic, wrap):
     """A box that changes every frame (the box of the ORIGIN frame serves both atoms) and unwrapped input (the
     literal minimum-image loops) through the small-system kernel."""
