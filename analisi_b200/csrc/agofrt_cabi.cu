@@ -1195,7 +1195,11 @@ extern "C" int agofrt_block(agofrt_plan *p, size_t primo, unsigned ntimesteps, u
                                                       static_cast<unsigned long long>(njobs * per_job));
 
     // ---- small systems: runs of jobs of one lag, dealt to the warps of a CTA (pair_small_kernel) ----
-    const bool small = t->npad > 0 && t->npad <= kSmallMax && !(options & AGOFRT_OPT_NO_SMALL);
+    // Default up to kSmallDefault slots (at most four warps per job: two jobs or more in flight per CTA), where it is
+    // 1.7x - 2.3x the tile kernel; with one job in flight per CTA (five to eight warps) the two tie
+    // (profiles/r1p_small_rate.jsonl), so that range is opt-in.
+    const bool small = t->npad > 0 && !(options & AGOFRT_OPT_NO_SMALL) &&
+                       (t->npad <= kSmallDefault || ((options & AGOFRT_OPT_SMALL) && t->npad <= kSmallMax));
     const int nsub = small ? (t->npad + 32 * kIPT - 1) / (32 * kIPT) : 1;   // warps per job
     std::vector<SmallUnit> units_fast, units_gen;
     if (small && !nothing) {

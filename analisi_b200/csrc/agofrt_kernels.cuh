@@ -36,7 +36,8 @@ constexpr int kStages = 2;                  // bulk-copy stages
 constexpr int kPadGroup = 8;                // every type group is padded to a multiple of this
 constexpr int kJU = AGOFRT_JU;              // j atoms per inner step (one LDS.128 per coordinate per two)
 constexpr int kWrapCap = 1 << 20;           // images the general minimum image may add per dimension
-constexpr int kSmallMax = 512;              // systems of up to this many slots go to pair_small_kernel
+constexpr int kSmallMax = 512;              // systems of up to this many slots CAN go to pair_small_kernel
+constexpr int kSmallDefault = 256;          // ... and up to this many do by default
 
 struct Job {
     int fi;    // window-relative frame of the i atoms (its box is used)

@@ -150,9 +150,11 @@ enum {
     AGOFRT_OPT_DENSE = 32,         /* force the kernel without the group filter (dense in-range workloads)      */
     AGOFRT_OPT_SPARSE = 64,        /* force the group-filtered kernel meant for sparse in-range workloads      */
     AGOFRT_OPT_NO_UBOX = 128,      /* never pass a constant box as kernel parameter (uniform operands)         */
-    AGOFRT_OPT_NO_SMALL = 256,     /* never take the small-system kernel (warp groups per job, up to 512 device slots) */
-    AGOFRT_OPT_ON_DEVICE = 512     /* leave the counts on the device for agofrt_blockavg_push: counts_out may be NULL
+    AGOFRT_OPT_NO_SMALL = 256,     /* never take the small-system kernel (one job per group of warps) */
+    AGOFRT_OPT_ON_DEVICE = 512,    /* leave the counts on the device for agofrt_blockavg_push: counts_out may be NULL
                                       and is not written */
+    AGOFRT_OPT_SMALL = 1024        /* take the small-system kernel for up to 512 device slots (default: up to 256, one
+                                      to four warps per job, where it beats the tile kernel; measured equal above) */
 };
 
 typedef struct {

@@ -25,8 +25,8 @@ def gpu_counts(ctx, pos, box_internal, ids, ntypes, rmin, rmax, nbin, tmax, nts,
     return out
 
 
-# systems of up to 512 device slots take the small-system kernel (one job per group of warps) unless told
-# otherwise: the small fixtures run through both kernels
+# systems of up to 256 device slots take the small-system kernel (one job per group of warps) unless told
+# otherwise (up to 512 with OPT_SMALL): the small fixtures run through both kernels
 BOTH_KERNELS = pytest.mark.parametrize("no_small", [0, cabi.OPT_NO_SMALL], ids=["small-kernel", "tile-kernel"])
 
 
@@ -487,13 +487,18 @@ def test_small_system_kernel(ctx, natoms, ntypes, triclinic):
     co = oracle.counts(pos, bi, types, *args, ntypes=ntypes)
     c, st = gpu_counts(ctx, pos, bi, types, ntypes, *args)
     assert np.array_equal(c, co)
-    assert ran_small(st) and st["jobs"] == 9 * 30 and st["pair_evals"] == 9 * 30 * natoms * natoms
-    if natoms > 150:   # the larger cases: the default kernel choice, the tile kernel and the edge count only
+    assert st["jobs"] == 9 * 30 and st["pair_evals"] == 9 * 30 * natoms * natoms
+    # the default: up to 256 device slots (four warps per job); beyond, up to 512, on request
+    assert ran_small(st) == (cabi.device_slots(types) <= cabi.SMALL_DEFAULT_SLOTS)
+    if natoms > 150:   # the larger cases: both kernels, both minimum-image paths and the edge count only
+        sm = cabi.OPT_SMALL
+        c1, st1 = gpu_counts(ctx, pos, bi, types, ntypes, *args, options=sm)
+        assert np.array_equal(c1, co) and ran_small(st1) and st1["pair_evals"] == 9 * 30 * natoms * natoms
         c2, st2 = gpu_counts(ctx, pos, bi, types, ntypes, *args, options=cabi.OPT_NO_SMALL)
         assert np.array_equal(c2, co) and not ran_small(st2)
-        c4, st4 = gpu_counts(ctx, pos, bi, types, ntypes, *args, options=cabi.OPT_FORCE_GENERAL | cabi.OPT_NO_UBOX)
+        c4, st4 = gpu_counts(ctx, pos, bi, types, ntypes, *args, options=sm | cabi.OPT_FORCE_GENERAL | cabi.OPT_NO_UBOX)
         assert np.array_equal(c4, co) and ran_small(st4)
-        c5, st5, e5 = gpu_counts(ctx, pos, bi, types, ntypes, *args, edges=True)
+        c5, st5, e5 = gpu_counts(ctx, pos, bi, types, ntypes, *args, edges=True, options=sm)
         _, eo = oracle.counts(pos, bi, types, *args, ntypes=ntypes, return_edges=True)
         assert np.array_equal(c5, co) and e5 == eo and ran_small(st5)
         return
@@ -529,7 +534,7 @@ def test_small_system_kernel_npt_and_unwrapped(ctx, natoms, triclinic, wrap):
         pos = pos + shift * bi[:, None, 3:6] * 2
     args = (0.0, 3.1, 50, 6, 18)
     co = oracle.counts(pos, bi, types, *args, ntypes=2)
-    c, st = gpu_counts(ctx, pos, bi, types, 2, *args)
+    c, st = gpu_counts(ctx, pos, bi, types, 2, *args, options=cabi.OPT_SMALL)   # (330 atoms: beyond the default range)
     assert np.array_equal(c, co) and ran_small(st)
     if not wrap:
         assert st["jobs_fast"] < st["jobs"]

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Throughput of the two pair kernels on SMALL systems (56 .. 512 atoms, the sizes of ab-initio cells): the
-small-system kernel (one job per group of ceil(slots/64) warps, the default up to 512 device slots) against the tile
+small-system kernel (one job per group of ceil(slots/64) warps, the default up to 256 device slots) against the tile
 kernel (AGOFRT_OPT_NO_SMALL), pair evaluations per second from the library's own CUDA-event timing, one JSON
 line per size.  python tools/small_rate.py [sizes...]"""
 import json
@@ -30,13 +30,13 @@ for n in sizes:
     plan = cabi.Plan(tr, 0.0, 0.45 * float(2 * bi[0, 3]), 200)
     out = {"natoms": n, "jobs": LAGS * ORIGINS, "pair_evals": LAGS * ORIGINS * n * n}
     ref = None
-    for name, opt in (("small_kernel", 0), ("tile_kernel", cabi.OPT_NO_SMALL)):
+    for name, opt in (("small_kernel", cabi.OPT_SMALL), ("tile_kernel", cabi.OPT_NO_SMALL)):
         best = None
         for k in range(4):
             c, st = plan.block(0, ORIGINS, LAGS, 1, 1, options=opt)
             if k:
                 best = st["kernel_ms"] if best is None else min(best, st["kernel_ms"])
-        assert bool(st["kernel_modes"] & cabi.MODE_BIT_SMALL) == (opt == 0)
+        assert bool(st["kernel_modes"] & cabi.MODE_BIT_SMALL) == (opt == cabi.OPT_SMALL)
         if ref is None:
             ref = c
         assert np.array_equal(c, ref), "the two kernels disagree"
