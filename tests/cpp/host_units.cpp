@@ -14,6 +14,8 @@
 #include "analisi/operazionisulista.h"
 #include "analisi/trajectory_numpy.h"
 #include "analisi/triclinic.h"
+#include "analisi/gofrt.h"
+#include "analisi/msd.h"
 
 // A calculation with the interface BlockAverageG and MediaVar expect (what Gofrt offers), computed on the host:
 // element k of block `primo` is a fixed function of (primo, k) -- no trajectory access, no device.
@@ -46,6 +48,11 @@ static void print_vec(const char *name, const std::vector<double> &v, bool last 
     for (size_t i = 0; i < v.size(); ++i) std::printf("%s%.17g", i ? ", " : "", v[i]);
     std::printf("]%s\n", last ? "" : ",");
 }
+
+// BlockAverageG::calculate folds the blocks on the device only for calculations that can keep them there
+static_assert(HasDeviceBlocks<Gofrt<double, Trajectory>>::value && HasDeviceBlocks<Gofrt<double, Trajectory_numpy>>::value,
+              "Gofrt offers set_keep_on_device / device_plan / fetch_block");
+static_assert(!HasDeviceBlocks<MSD<Trajectory>>::value, "MSD blocks are averaged by the host MediaVar");
 
 int main() {
     std::printf("{\n");

@@ -51,6 +51,37 @@ def test_no_gpu_is_a_loud_error():
     assert "no CPU path" in str(e.value)
 
 
+def test_block_average_entry_points_check_their_arguments():
+    """agofrt_blockavg_* / agofrt_plan_last_counts: NULL handles are an argument error (no device needed to say so),
+    destroying nothing is fine -- the conventions of the rest of the ABI."""
+    L = cabi.lib()
+    assert L.agofrt_blockavg_create(None, None) == cabi.ERR_ARG
+    assert L.agofrt_blockavg_begin(None, 10) == cabi.ERR_ARG
+    assert L.agofrt_blockavg_push(None, None, 1.0) == cabi.ERR_ARG
+    assert L.agofrt_blockavg_end(None, 2, None, None) == cabi.ERR_ARG
+    assert L.agofrt_plan_last_counts(None, None, 0) == cabi.ERR_ARG
+    assert b"NULL" in L.agofrt_last_error()
+    assert L.agofrt_blockavg_destroy(None) == cabi.OK
+
+
+def test_device_slots_helper():
+    """every type group padded to 8 slots (kPadGroup): the sizes that pick the small-system kernel"""
+    assert cabi.device_slots(np.zeros(56, np.int32)) == 56
+    assert cabi.device_slots(np.array([0] * 32 + [1] * 24)) == 56
+    assert cabi.device_slots(np.array([0] * 33 + [1] * 23)) == 64
+    assert cabi.device_slots(np.arange(75) % 3) == 96
+    assert cabi.SMALL_DEFAULT_SLOTS == 256 and cabi.SMALL_MAX_SLOTS == 512
+    assert (cabi.OPT_NO_SMALL, cabi.OPT_ON_DEVICE, cabi.OPT_SMALL) == (256, 512, 1024)
+
+
+def test_option_bits_match_the_header():
+    text = open(os.path.join(ROOT, "include", "agofrt.h")).read()
+    bits = {k: int(v) for k, v in re.findall(r"AGOFRT_OPT_(\w+)\s*=\s*(\d+)", text)}
+    for name in ("EDGES", "FORCE_GENERAL", "NO_AGGREGATE", "AGGREGATE", "NO_SAFE", "DENSE", "SPARSE", "NO_UBOX",
+                 "NO_SMALL", "ON_DEVICE", "SMALL"):
+        assert getattr(cabi, "OPT_" + name) == bits[name], name
+
+
 def test_host_side_gofrt_arithmetic_matches_oracle():
     import oracle
     for nts, lmax in ((700, 10), (5, 10), (9, 0), (0, 3)):
