@@ -16,9 +16,11 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <exception>
 #include <limits>
 #include <memory>
 #include <mutex>
+#include <new>
 #include <numeric>
 #include <string>
 #include <unordered_set>
@@ -39,6 +41,20 @@ static int fail(int code, const char *fmt, ...) {
     va_end(ap);
     g_last_error = buf;
     return code;
+}
+
+// Nothing throws across the C ABI: every entry point is a function-try-block ending here (std::vector growth in
+// the planning code is the realistic source: a block of billions of jobs, a trajectory of billions of atoms).
+static int on_exception() noexcept {
+    try {
+        throw;
+    } catch (const std::bad_alloc &) {
+        return fail(AGOFRT_ERR_TOO_LARGE, "out of host memory while planning the call");
+    } catch (const std::exception &e) {
+        return fail(AGOFRT_ERR_INTERNAL, "unexpected exception: %s", e.what());
+    } catch (...) {
+        return fail(AGOFRT_ERR_INTERNAL, "unexpected exception");
+    }
 }
 
 #define CU(call)                                                                                         \
@@ -207,7 +223,7 @@ struct agofrt_plan {
 extern "C" const char *agofrt_version(void) { return "agofrt 0.1 (sm_100a)"; }
 extern "C" const char *agofrt_last_error(void) { return g_last_error.c_str(); }
 
-extern "C" int agofrt_device_count(int *count) {
+extern "C" int agofrt_device_count(int *count) try {
     if (!count) return fail(AGOFRT_ERR_ARG, "count is NULL");
     int n = 0;
     cudaError_t e = cudaGetDeviceCount(&n);
@@ -217,6 +233,8 @@ extern "C" int agofrt_device_count(int *count) {
     }
     *count = n;
     return AGOFRT_OK;
+} catch (...) {
+    return on_exception();
 }
 
 // Page-locked when a CUDA driver is present.  Without one (authoring container, CPU-only tests of the
@@ -225,7 +243,7 @@ extern "C" int agofrt_device_count(int *count) {
 static std::mutex g_pageable_mutex;
 static std::unordered_set<void *> g_pageable;
 
-extern "C" int agofrt_host_alloc(void **ptr, size_t bytes) {
+extern "C" int agofrt_host_alloc(void **ptr, size_t bytes) try {
     if (!ptr) return fail(AGOFRT_ERR_ARG, "ptr is NULL");
     *ptr = nullptr;
     const cudaError_t e = cudaHostAlloc(ptr, bytes ? bytes : 1, cudaHostAllocPortable);
@@ -240,8 +258,10 @@ extern "C" int agofrt_host_alloc(void **ptr, size_t bytes) {
         return AGOFRT_OK;
     }
     return fail(AGOFRT_ERR_CUDA, "cudaHostAlloc of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
+} catch (...) {
+    return on_exception();
 }
-extern "C" int agofrt_host_free(void *ptr) {
+extern "C" int agofrt_host_free(void *ptr) try {
     if (!ptr) return AGOFRT_OK;
     {
         std::lock_guard<std::mutex> lock(g_pageable_mutex);
@@ -254,12 +274,14 @@ extern "C" int agofrt_host_free(void *ptr) {
     }
     CU(cudaFreeHost(ptr));
     return AGOFRT_OK;
+} catch (...) {
+    return on_exception();
 }
 
 // ---------------------------------------------------------------------------------------------
 // context
 // ---------------------------------------------------------------------------------------------
-extern "C" int agofrt_ctx_create(agofrt_ctx **out, const int *devices, int ndev) {
+extern "C" int agofrt_ctx_create(agofrt_ctx **out, const int *devices, int ndev) try {
     if (!out) return fail(AGOFRT_ERR_ARG, "ctx is NULL");
     *out = nullptr;
     int avail = 0;
@@ -301,9 +323,11 @@ extern "C" int agofrt_ctx_create(agofrt_ctx **out, const int *devices, int ndev)
     }
     *out = ctx.release();
     return AGOFRT_OK;
+} catch (...) {
+    return on_exception();
 }
 
-extern "C" int agofrt_ctx_destroy(agofrt_ctx *ctx) {
+extern "C" int agofrt_ctx_destroy(agofrt_ctx *ctx) try {
     if (!ctx) return AGOFRT_OK;
     for (Dev &d : ctx->devs) {
         cudaSetDevice(d.id);
@@ -317,11 +341,13 @@ extern "C" int agofrt_ctx_destroy(agofrt_ctx *ctx) {
     }
     delete ctx;
     return AGOFRT_OK;
+} catch (...) {
+    return on_exception();
 }
 
 extern "C" int agofrt_ctx_ndev(const agofrt_ctx *ctx) { return ctx ? static_cast<int>(ctx->devs.size()) : 0; }
 
-extern "C" int agofrt_comm_unique_id(char id[AGOFRT_COMM_ID_BYTES]) {
+extern "C" int agofrt_comm_unique_id(char id[AGOFRT_COMM_ID_BYTES]) try {
     static_assert(AGOFRT_COMM_ID_BYTES == NCCL_UNIQUE_ID_BYTES, "id size");
     if (!id) return fail(AGOFRT_ERR_ARG, "id is NULL");
     NcclApi &api = nccl_api();
@@ -330,6 +356,8 @@ extern "C" int agofrt_comm_unique_id(char id[AGOFRT_COMM_ID_BYTES]) {
     NC(api.GetUniqueId(&u));
     memcpy(id, u.internal, NCCL_UNIQUE_ID_BYTES);
     return AGOFRT_OK;
+} catch (...) {
+    return on_exception();
 }
 
 static int comm_init(agofrt_ctx *ctx, const ncclUniqueId &u, int first_rank, int world) {
@@ -369,15 +397,17 @@ static int comm_init(agofrt_ctx *ctx, const ncclUniqueId &u, int first_rank, int
     return AGOFRT_OK;
 }
 
-extern "C" int agofrt_comm_join(agofrt_ctx *ctx, const char id[AGOFRT_COMM_ID_BYTES], int first_rank, int world) {
+extern "C" int agofrt_comm_join(agofrt_ctx *ctx, const char id[AGOFRT_COMM_ID_BYTES], int first_rank, int world) try {
     if (!ctx || !id) return fail(AGOFRT_ERR_ARG, "NULL argument");
     if (ctx->comm_ready) return fail(AGOFRT_ERR_ARG, "context already has a communicator");
     ncclUniqueId u;
     memcpy(u.internal, id, NCCL_UNIQUE_ID_BYTES);
     return comm_init(ctx, u, first_rank, world);
+} catch (...) {
+    return on_exception();
 }
 
-extern "C" int agofrt_ctx_set_shard(agofrt_ctx *ctx, int first_rank, int world) {
+extern "C" int agofrt_ctx_set_shard(agofrt_ctx *ctx, int first_rank, int world) try {
     if (!ctx) return fail(AGOFRT_ERR_ARG, "NULL argument");
     const int nloc = static_cast<int>(ctx->devs.size());
     if (world < nloc || first_rank < 0 || first_rank + nloc > world)
@@ -387,14 +417,18 @@ extern "C" int agofrt_ctx_set_shard(agofrt_ctx *ctx, int first_rank, int world) 
     ctx->world = world;
     ctx->shard_only = true;
     return AGOFRT_OK;
+} catch (...) {
+    return on_exception();
 }
 
-extern "C" int agofrt_shard_range(uint64_t units, int rank, int world, uint64_t *begin, uint64_t *end) {
+extern "C" int agofrt_shard_range(uint64_t units, int rank, int world, uint64_t *begin, uint64_t *end) try {
     if (!begin || !end || world <= 0 || rank < 0 || rank >= world) return fail(AGOFRT_ERR_ARG, "bad shard arguments");
     // 128-bit products: units * world never overflows
     *begin = static_cast<uint64_t>(static_cast<unsigned __int128>(units) * rank / world);
     *end = static_cast<uint64_t>(static_cast<unsigned __int128>(units) * (rank + 1) / world);
     return AGOFRT_OK;
+} catch (...) {
+    return on_exception();
 }
 
 // a multi-device context without a joined communicator is its own communicator
@@ -431,7 +465,7 @@ static void free_traj_dev(agofrt_traj *t) {
 }
 
 extern "C" int agofrt_traj_create(agofrt_traj **out, agofrt_ctx *ctx, size_t natoms, int box_stride,
-                                  const int *type_id, int ntypes, size_t max_frames) {
+                                  const int *type_id, int ntypes, size_t max_frames) try {
     if (!out || !ctx) return fail(AGOFRT_ERR_ARG, "NULL argument");
     *out = nullptr;
     if (box_stride != 6 && box_stride != 9) return fail(AGOFRT_ERR_ARG, "box_stride must be 6 or 9");
@@ -496,13 +530,17 @@ extern "C" int agofrt_traj_create(agofrt_traj **out, agofrt_ctx *ctx, size_t nat
     }
     *out = t.release();
     return AGOFRT_OK;
+} catch (...) {
+    return on_exception();
 }
 
-extern "C" int agofrt_traj_destroy(agofrt_traj *t) {
+extern "C" int agofrt_traj_destroy(agofrt_traj *t) try {
     if (!t) return AGOFRT_OK;
     free_traj_dev(t);
     delete t;
     return AGOFRT_OK;
+} catch (...) {
+    return on_exception();
 }
 
 static inline uint32_t spread3(uint32_t v) {  // 10 bits -> every third bit
@@ -658,16 +696,20 @@ static int upload_impl(agofrt_traj *t, size_t first_frame, size_t nframes, const
 }
 
 extern "C" int agofrt_traj_upload(agofrt_traj *t, size_t first_frame, size_t nframes, const double *pos_aos,
-                                  const double *box_internal) {
+                                  const double *box_internal) try {
     return upload_impl(t, first_frame, nframes, pos_aos, box_internal, false, nullptr);
+} catch (...) {
+    return on_exception();
 }
 
 extern "C" int agofrt_traj_upload_wrap(agofrt_traj *t, size_t first_frame, size_t nframes, double *pos_aos_inout,
-                                       const double *box_internal) {
+                                       const double *box_internal) try {
     return upload_impl(t, first_frame, nframes, pos_aos_inout, box_internal, true, pos_aos_inout);
+} catch (...) {
+    return on_exception();
 }
 
-extern "C" int agofrt_traj_download_frame(agofrt_traj *t, size_t frame, double *pos_aos) {
+extern "C" int agofrt_traj_download_frame(agofrt_traj *t, size_t frame, double *pos_aos) try {
     if (!t || !pos_aos) return fail(AGOFRT_ERR_ARG, "NULL argument");
     if (frame < t->first_frame || frame >= t->first_frame + t->nframes)
         return fail(AGOFRT_ERR_WINDOW, "frame %zu is not in the uploaded window", frame);
@@ -681,10 +723,12 @@ extern "C" int agofrt_traj_download_frame(agofrt_traj *t, size_t frame, double *
     CU(cudaMemcpyAsync(pos_aos, d.stage, t->natoms * 3 * sizeof(double), cudaMemcpyDeviceToHost, dv.stream));
     CU(cudaStreamSynchronize(dv.stream));
     return AGOFRT_OK;
+} catch (...) {
+    return on_exception();
 }
 
 extern "C" int agofrt_pbc_wrap(agofrt_ctx *ctx, double *pos_aos, size_t nframes, size_t natoms,
-                               const double *box_internal, int box_stride) {
+                               const double *box_internal, int box_stride) try {
     if (!ctx) return fail(AGOFRT_ERR_ARG, "ctx is NULL");
     if (box_stride != 6 && box_stride != 9) return fail(AGOFRT_ERR_ARG, "box_stride must be 6 or 9");
     if (nframes == 0 || natoms == 0) return AGOFRT_OK;
@@ -726,9 +770,11 @@ extern "C" int agofrt_pbc_wrap(agofrt_ctx *ctx, double *pos_aos, size_t nframes,
     cudaFree(dbox);
     cudaFree(dflag);
     return rc;
+} catch (...) {
+    return on_exception();
 }
 
-extern "C" int agofrt_traj_d2_all(agofrt_traj *t, size_t frame_i, size_t frame_j, double *out) {
+extern "C" int agofrt_traj_d2_all(agofrt_traj *t, size_t frame_i, size_t frame_j, double *out) try {
     if (!t || !out) return fail(AGOFRT_ERR_ARG, "NULL argument");
     for (size_t f : {frame_i, frame_j})
         if (f < t->first_frame || f >= t->first_frame + t->nframes)
@@ -758,10 +804,12 @@ extern "C" int agofrt_traj_d2_all(agofrt_traj *t, size_t frame_i, size_t frame_j
     const int rc = body();
     cudaFree(dout);
     return rc;
+} catch (...) {
+    return on_exception();
 }
 
 extern "C" int agofrt_traj_d2_pair(agofrt_traj *t, size_t atom_i, size_t atom_j, size_t frame_i, size_t frame_j,
-                                   double *out4) {
+                                   double *out4) try {
     if (!t || !out4) return fail(AGOFRT_ERR_ARG, "NULL argument");
     for (size_t f : {frame_i, frame_j})
         if (f < t->first_frame || f >= t->first_frame + t->nframes)
@@ -791,6 +839,8 @@ extern "C" int agofrt_traj_d2_pair(agofrt_traj *t, size_t atom_i, size_t atom_j,
     CU(cudaStreamSynchronize(dv.stream));
     if (flag) return fail(AGOFRT_ERR_NONFINITE, "minimum image did not converge");
     return AGOFRT_OK;
+} catch (...) {
+    return on_exception();
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -926,7 +976,7 @@ static int validate_safe_zone(agofrt_plan *p) {
     return AGOFRT_OK;
 }
 
-extern "C" int agofrt_plan_create(agofrt_plan **out, agofrt_traj *traj, double rmin, double rmax, unsigned nbin) {
+extern "C" int agofrt_plan_create(agofrt_plan **out, agofrt_traj *traj, double rmin, double rmax, unsigned nbin) try {
     if (!out || !traj) return fail(AGOFRT_ERR_ARG, "NULL argument");
     *out = nullptr;
     if (nbin == 0 || nbin > (1u << 24)) return fail(AGOFRT_ERR_ARG, "nbin must be in [1, 2^24]");
@@ -1028,18 +1078,22 @@ extern "C" int agofrt_plan_create(agofrt_plan **out, agofrt_traj *traj, double r
                      cudaHostAllocPortable));
     *out = p.release();
     return AGOFRT_OK;
+} catch (...) {
+    return on_exception();
 }
 
-extern "C" int agofrt_plan_retarget(agofrt_plan *p, agofrt_traj *traj) {
+extern "C" int agofrt_plan_retarget(agofrt_plan *p, agofrt_traj *traj) try {
     if (!p || !traj) return fail(AGOFRT_ERR_ARG, "NULL argument");
     if (traj == p->traj) return AGOFRT_OK;
     if (traj->ctx != p->ctx || traj->ntypes != p->ntypes)
         return fail(AGOFRT_ERR_ARG, "the new window belongs to another context or has another number of types");
     p->traj = traj;
     return AGOFRT_OK;
+} catch (...) {
+    return on_exception();
 }
 
-extern "C" int agofrt_plan_destroy(agofrt_plan *p) {
+extern "C" int agofrt_plan_destroy(agofrt_plan *p) try {
     if (!p) return AGOFRT_OK;
     for (size_t i = 0; i < p->dev.size(); ++i) {
         cudaSetDevice(p->ctx->devs[i].id);
@@ -1057,12 +1111,16 @@ extern "C" int agofrt_plan_destroy(agofrt_plan *p) {
     if (p->host_flags) cudaFreeHost(p->host_flags);
     delete p;
     return AGOFRT_OK;
+} catch (...) {
+    return on_exception();
 }
 
-extern "C" int agofrt_plan_thresholds(const agofrt_plan *p, double *thresholds) {
+extern "C" int agofrt_plan_thresholds(const agofrt_plan *p, double *thresholds) try {
     if (!p || !thresholds) return fail(AGOFRT_ERR_ARG, "NULL argument");
     memcpy(thresholds, p->thr_full.data(), (p->nbin + 1) * sizeof(double));
     return AGOFRT_OK;
+} catch (...) {
+    return on_exception();
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1121,7 +1179,7 @@ static bool range_is_single_pass(const agofrt_traj *t, size_t f0, size_t f1) {
 
 extern "C" int agofrt_block(agofrt_plan *p, size_t primo, unsigned ntimesteps, unsigned leff, unsigned skip,
                             unsigned every, unsigned options, uint64_t *counts_out, uint64_t *edge_pairs_out,
-                            agofrt_stats *stats) {
+                            agofrt_stats *stats) try {
     if (!p) return fail(AGOFRT_ERR_ARG, "plan is NULL");
     agofrt_traj *t = p->traj;
     agofrt_ctx *ctx = t->ctx;
@@ -1161,6 +1219,8 @@ extern "C" int agofrt_block(agofrt_plan *p, size_t primo, unsigned ntimesteps, u
         const bool may_fast = !(options & AGOFRT_OPT_FORCE_GENERAL);
         const bool all_fast = may_fast && range_is_single_pass(t, primo - t->first_frame, last - t->first_frame);
         const size_t expect = static_cast<size_t>((leff + every - 1) / every) * ((ntimesteps + skip - 1) / skip);
+        if (expect >= 0xF0000000ull)   // (the same limit as on the work units below, before any memory is asked for)
+            return fail(AGOFRT_ERR_ARG, "too many work units in one block (%zu (lag, origin) jobs)", expect);
         (may_fast ? jobs_fast : jobs_gen).reserve(expect);
         for (unsigned tl = 0; tl < leff; tl += every)
             for (unsigned im = 0; im < ntimesteps; im += skip) {
@@ -1479,6 +1539,8 @@ extern "C" int agofrt_block(agofrt_plan *p, size_t primo, unsigned ntimesteps, u
         stats->kernel_modes = modes_used;
     }
     return AGOFRT_OK;
+} catch (...) {
+    return on_exception();
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1492,23 +1554,27 @@ struct agofrt_blockavg {
     bool begun = false;
 };
 
-extern "C" int agofrt_blockavg_create(agofrt_blockavg **acc, agofrt_ctx *ctx) {
+extern "C" int agofrt_blockavg_create(agofrt_blockavg **acc, agofrt_ctx *ctx) try {
     if (!acc || !ctx) return fail(AGOFRT_ERR_ARG, "NULL argument");
     *acc = new agofrt_blockavg;
     (*acc)->ctx = ctx;
     return AGOFRT_OK;
+} catch (...) {
+    return on_exception();
 }
 
-extern "C" int agofrt_blockavg_destroy(agofrt_blockavg *a) {
+extern "C" int agofrt_blockavg_destroy(agofrt_blockavg *a) try {
     if (!a) return AGOFRT_OK;
     cudaSetDevice(a->ctx->devs[0].id);
     cudaFree(a->mean);
     cudaFree(a->var);
     delete a;
     return AGOFRT_OK;
+} catch (...) {
+    return on_exception();
 }
 
-extern "C" int agofrt_blockavg_begin(agofrt_blockavg *a, size_t len) {
+extern "C" int agofrt_blockavg_begin(agofrt_blockavg *a, size_t len) try {
     if (!a) return fail(AGOFRT_ERR_ARG, "acc is NULL");
     Dev &dv = a->ctx->devs[0];
     CU(cudaSetDevice(dv.id));
@@ -1529,9 +1595,11 @@ extern "C" int agofrt_blockavg_begin(agofrt_blockavg *a, size_t len) {
         CU(cudaMemsetAsync(a->var, 0, len * sizeof(double), dv.stream));
     }
     return AGOFRT_OK;
+} catch (...) {
+    return on_exception();
 }
 
-extern "C" int agofrt_blockavg_push(agofrt_blockavg *a, agofrt_plan *p, double incr) {
+extern "C" int agofrt_blockavg_push(agofrt_blockavg *a, agofrt_plan *p, double incr) try {
     if (!a || !p) return fail(AGOFRT_ERR_ARG, "NULL argument");
     if (!a->begun) return fail(AGOFRT_ERR_ARG, "agofrt_blockavg_push before agofrt_blockavg_begin");
     if (p->ctx != a->ctx) return fail(AGOFRT_ERR_ARG, "plan and accumulator belong to different contexts");
@@ -1546,9 +1614,11 @@ extern "C" int agofrt_blockavg_push(agofrt_blockavg *a, agofrt_plan *p, double i
     CU(launch_blockavg_push(p->dev[0].ghist, incr, a->blocks, a->mean, a->var, a->len, dv.sm_count, dv.stream));
     ++a->blocks;
     return AGOFRT_OK;
+} catch (...) {
+    return on_exception();
 }
 
-extern "C" int agofrt_blockavg_end(agofrt_blockavg *a, unsigned n_b, double *mean_out, double *var_out) {
+extern "C" int agofrt_blockavg_end(agofrt_blockavg *a, unsigned n_b, double *mean_out, double *var_out) try {
     if (!a) return fail(AGOFRT_ERR_ARG, "acc is NULL");
     if (!a->begun) return fail(AGOFRT_ERR_ARG, "agofrt_blockavg_end before agofrt_blockavg_begin");
     Dev &dv = a->ctx->devs[0];
@@ -1566,9 +1636,11 @@ extern "C" int agofrt_blockavg_end(agofrt_blockavg *a, unsigned n_b, double *mea
     }
     a->begun = false;
     return AGOFRT_OK;
+} catch (...) {
+    return on_exception();
 }
 
-extern "C" int agofrt_plan_last_counts(agofrt_plan *p, uint64_t *counts_out, size_t len) {
+extern "C" int agofrt_plan_last_counts(agofrt_plan *p, uint64_t *counts_out, size_t len) try {
     if (!p || (len > 0 && !counts_out)) return fail(AGOFRT_ERR_ARG, "NULL argument");
     if (!p->last_valid) return fail(AGOFRT_ERR_ARG, "the plan holds no complete block on the device (run agofrt_block first)");
     if (len != p->last_len) return fail(AGOFRT_ERR_ARG, "the last block has %zu words, not %zu", p->last_len, len);
@@ -1579,13 +1651,15 @@ extern "C" int agofrt_plan_last_counts(agofrt_plan *p, uint64_t *counts_out, siz
     CU(cudaStreamSynchronize(dv.stream));
     memcpy(counts_out, p->host_counts, len * sizeof(uint64_t));
     return AGOFRT_OK;
+} catch (...) {
+    return on_exception();
 }
 
 // ---------------------------------------------------------------------------------------------
 // neighbour-count histogram (IstogrammaAtomiRaggio::calculate)
 // ---------------------------------------------------------------------------------------------
 extern "C" int agofrt_neighbour_hist(agofrt_traj *t, double r, size_t tstart, unsigned ntimesteps, unsigned skip,
-                                     uint64_t *hist_inout, agofrt_stats *stats) {
+                                     uint64_t *hist_inout, agofrt_stats *stats) try {
     if (!t) return fail(AGOFRT_ERR_ARG, "traj is NULL");
     agofrt_ctx *ctx = t->ctx;
     if (skip < 1) skip = 1;   // reference lib/src/istogrammaatomiraggio.cpp:19
@@ -1699,22 +1773,26 @@ extern "C" int agofrt_neighbour_hist(agofrt_traj *t, double r, size_t tstart, un
         stats->world = static_cast<uint32_t>(world);
     }
     return AGOFRT_OK;
+} catch (...) {
+    return on_exception();
 }
 
 // ---------------------------------------------------------------------------------------------
 // mean square displacement (MSD<T>::calculate)
 // ---------------------------------------------------------------------------------------------
-extern "C" int agofrt_traj_set_cm(agofrt_traj *t, size_t first_frame, size_t nframes, const double *cm) {
+extern "C" int agofrt_traj_set_cm(agofrt_traj *t, size_t first_frame, size_t nframes, const double *cm) try {
     if (!t) return fail(AGOFRT_ERR_ARG, "traj is NULL");
     if (nframes > 0 && !cm) return fail(AGOFRT_ERR_ARG, "cm is NULL");
     t->cm.assign(cm, cm + nframes * static_cast<size_t>(t->ntypes) * 3);
     t->cm_first = first_frame;
     t->cm_frames = nframes;
     return AGOFRT_OK;
+} catch (...) {
+    return on_exception();
 }
 
 extern "C" int agofrt_msd(agofrt_traj *t, size_t primo, unsigned ntimesteps, unsigned leff, unsigned skip, int cm_msd,
-                          int cm_self, double *out, agofrt_stats *stats) {
+                          int cm_self, double *out, agofrt_stats *stats) try {
     if (!t) return fail(AGOFRT_ERR_ARG, "traj is NULL");
     if (skip < 1) skip = 1;
     if (stats) memset(stats, 0, sizeof(*stats));
@@ -1809,12 +1887,14 @@ extern "C" int agofrt_msd(agofrt_traj *t, size_t primo, unsigned ntimesteps, uns
         stats->world = 1;
     }
     return AGOFRT_OK;
+} catch (...) {
+    return on_exception();
 }
 
 // ---------------------------------------------------------------------------------------------
 // FP64 issue-rate microbenchmark
 // ---------------------------------------------------------------------------------------------
-extern "C" int agofrt_fp64_peak(agofrt_ctx *ctx, int local_device, double seconds, double *dfma_per_second) {
+extern "C" int agofrt_fp64_peak(agofrt_ctx *ctx, int local_device, double seconds, double *dfma_per_second) try {
     if (!ctx || !dfma_per_second) return fail(AGOFRT_ERR_ARG, "NULL argument");
     if (local_device < 0 || local_device >= static_cast<int>(ctx->devs.size()))
         return fail(AGOFRT_ERR_ARG, "local_device out of range");
@@ -1852,4 +1932,6 @@ extern "C" int agofrt_fp64_peak(agofrt_ctx *ctx, int local_device, double second
     std::sort(rates.begin(), rates.end());
     *dfma_per_second = rates[rates.size() / 2];
     return AGOFRT_OK;
+} catch (...) {
+    return on_exception();
 }
