@@ -57,6 +57,22 @@ WORKLOADS = {
 }
 
 
+# The default bench step (bench.py) for workloads whose full block is too long for one step: the same atoms,
+# frames, cell and bins, a regular SUBSET of the block's (lag, origin) jobs.  C4: every 8th lag x every 96th
+# origin = 26 x 8 = 208 jobs of 1e10 pair evaluations; int(768/96) = 8 keeps incr a power of two.  The counts of
+# exactly this subset from the unmodified reference are committed (tests/golden/c4_subset_counts.*).
+BENCH_SUBSET = {"C4": {"every": 8, "skip": 96, "ntimesteps": 768}}
+
+
+def bench_subset(name):
+    """(workload with the subset's skip / every, ntimesteps) of the default bench step of ``name``."""
+    import dataclasses
+    s = BENCH_SUBSET[name]
+    w = WORKLOADS[name]
+    return dataclasses.replace(w, skip=s["skip"], every=s["every"], name=w.name + " [subset: every %dth lag x every %dth origin]"
+                               % (s["every"], s["skip"])), s["ntimesteps"]
+
+
 def lattice_types(w: Workload):
     n = w.natoms
     idx = np.arange(n)

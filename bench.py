@@ -50,9 +50,13 @@ def log(*a):
 # ---------------------------------------------------------------------------------------------
 # workloads
 # ---------------------------------------------------------------------------------------------
-def block_spec(name, quick=False):
+def block_spec(name, quick=False, full=False):
     """(workload, ntimesteps, primo) of the step: SURVEY.md section 8(d)."""
     w = synth.WORKLOADS[name]
+    if name in synth.BENCH_SUBSET and not quick and not full:
+        # the default step of a workload whose full block takes minutes: a regular subset of its (lag, origin) jobs
+        w, nts = synth.bench_subset(name)
+        return w, nts, 0
     if name == "C2":
         # throughput run: reset(1899); calculate(0), skip 1, lags 0..100 -> 101*1899 jobs of 4096^2
         nts = 1899 if not quick else 64
@@ -292,7 +296,15 @@ def cpu_sample(w, pos, box_lammps, box_internal, types, target_s=12.0, threads=N
             dt = time.perf_counter() - t0
         return lags * origins * n2 / dt, dt
 
-    # calibrate on one lag x two origins, then size the sample for ~target_s
+    # calibrate on one lag x two origins, then size the sample for ~target_s; with 1e10 pairs per (lag, origin)
+    # job (C4) one job IS the sample
+    if n2 >= 2.5e9:
+        rate, dt = run(1, 1)
+        return {
+            "value": rate, "unit": UNIT, "cores": threads, "kind": "reference" if ref is not None else "port",
+            "sample": "%s: frames 0-1, lag 0 x 1 origin = 1 (lag,origin) job of %d^2 pairs, %.1f s, %d threads"
+                      % (w.name.split()[0], w.natoms, dt, threads),
+        }
     rate, dt = run(1, 2)
     jobs = int(max(2, min(4096, target_s * rate / n2)))
     lags = max(1, min(4, jobs // 2, pos.shape[0] // 2))
@@ -307,15 +319,87 @@ def cpu_sample(w, pos, box_lammps, box_internal, types, target_s=12.0, threads=N
 
 
 # ---------------------------------------------------------------------------------------------
+# DRAM traffic of the step's kernel, measured in this run: the same block once more under ncu
+# ---------------------------------------------------------------------------------------------
+# FP64 instructions the pair kernels ISSUE per pair evaluation (SASS of the shipped library,
+# profiles/r2_sass_counts.txt): the 16 / 19 algorithmic operations of SURVEY.md section 8(d) minus the two range
+# compares, which ride on the integer high word of d2.
+FP64_ISSUED = {False: 14, True: 17}
+
+
+def measure_traffic(args, name):
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the step's pair kernel: bench.py re-runs itself
+    (``--traffic-child``: same workload, one block, nothing timed) under ``ncu``.  None when ncu is not usable."""
+    import shutil
+    import tempfile
+    ncu = shutil.which("ncu") or "/usr/local/cuda/bin/ncu"
+    if not os.path.exists(ncu):
+        return None, "ncu not found"
+    log_path = os.path.join(tempfile.gettempdir(), "agofrt_traffic_%d.csv" % os.getpid())
+    cmd = [ncu, "--metrics", "dram__bytes_read.sum,dram__bytes_write.sum", "--clock-control", "none", "--print-units", "base",
+           "--csv", "--log-file", log_path, "-k", "regex:pair_", sys.executable, os.path.abspath(__file__),
+           "--traffic-child", "--workload", name, "--options", str(args.options)]
+    if args.quick:
+        cmd.append("--quick")
+    if args.full:
+        cmd.append("--full")
+    try:
+        r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=900)
+        if r.returncode != 0:
+            return None, "ncu run failed (rc %d): %s" % (r.returncode, (r.stderr or r.stdout)[-200:].replace("\n", " "))
+        import csv
+        rd = wr = 0.0
+        launches = set()
+        with open(log_path) as f:
+            rows = [row for row in csv.reader(f) if len(row) > 5]
+        hdr = next(k for k, row in enumerate(rows) if "Metric Name" in row)
+        col = {n: k for k, n in enumerate(rows[hdr])}
+        for row in rows[hdr + 1:]:
+            v = float(row[col["Metric Value"]].replace(",", ""))
+            launches.add(row[col["ID"]])
+            if row[col["Metric Name"]] == "dram__bytes_read.sum":
+                rd += v
+            elif row[col["Metric Name"]] == "dram__bytes_write.sum":
+                wr += v
+        if not launches:
+            return None, "no pair kernel in the ncu log"
+        return {"dram_bytes_read": rd / len(launches), "dram_bytes_write": wr / len(launches), "launches": len(launches)}, "ncu"
+    except Exception as e:
+        return None, "ncu: %r" % (e,)
+    finally:
+        try:
+            os.remove(log_path)
+        except OSError:
+            pass
+
+
+def golden_sha(name, w, nts):
+    """The committed checksum of the step's counts from the unmodified reference, when this exact step has one."""
+    path = os.path.join(ROOT, "tests", "golden", "%s_subset_counts.json" % name.lower())
+    try:
+        g = json.load(open(path))
+        if g["subset"] == {"ntimesteps": nts, "skip": w.skip, "every": w.every, "leff": min(nts, w.tmax)} and g["workload"] == w.name:
+            return g["counts_sha256"]
+    except Exception:
+        pass
+    return None
+
+
+# ---------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--workload", default=None, help="C2 (default), C3, C4 (one Gofrt block per step); C5 (block-averaged chain from a file)")
+    ap.add_argument("--workload", default=None,
+                    help="C4 (default: BASELINE.json configs[3], the north-star shape; a regular subset of its (lag, origin) "
+                         "jobs per step unless --full), C2, C3 (one Gofrt block per step); C1, C5 (block-averaged chain from a file)")
+    ap.add_argument("--full", action="store_true", help="the whole block of the workload instead of the bench subset (C4: 150 s/step)")
     ap.add_argument("--quick", action="store_true", help="tiny block (smoke/profiling), not a bench number")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-traffic", action="store_true", help="skip the ncu re-run that measures roofline.traffic")
+    ap.add_argument("--traffic-child", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--options", type=int, default=0)
     ap.add_argument("--cpu-seconds", type=float, default=None, help="size of the CPU sample (default 12 s; 8 s per step for --impl reference)")
     args = ap.parse_args()
@@ -323,10 +407,10 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    name = args.workload or "C2"
+    name = args.workload or "C4"
     if name in ("C1", "C5"):
         return run_c5(args, rank, world, name)
-    w, nts, primo = block_spec(name, args.quick)
+    w, nts, primo = block_spec(name, args.quick, args.full)
     leff = min(nts, w.tmax) if w.tmax else nts
     nframes = primo + (nts - 1) // w.skip * w.skip + (leff - 1) // w.every * w.every + 1
     njobs = jobs_of(nts, leff, w.skip, w.every)
@@ -343,16 +427,13 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        pos, box_lammps, box_internal, types = make_window(w, min(nframes, 80))
+        pos, box_lammps, box_internal, types = make_window(w, min(nframes, 80 if w.natoms < 50000 else 4))
         vals = []
         res = None
         for k in range(args.warmup + args.steps):
             res = cpu_sample(w, pos, box_lammps, box_internal, types, target_s=args.cpu_seconds or 8.0)
             if k >= args.warmup:
                 vals.append(res["value"])
-            if k == 0 and args.warmup > 1:
-                # the CPU path has no warm-up effects worth three full samples; keep the run short
-                vals_warm = res["value"]
         v = float(np.mean(vals))
         res["value"] = v
         line = {
@@ -380,6 +461,12 @@ def main():
 
     tr = cabi.DeviceTrajectory(ctx, w.natoms, box_internal.shape[1], types, w.ntypes, nframes)
     plan = cabi.Plan(tr, w.rmin, w.rmax, w.nbin)
+
+    if args.traffic_child:
+        # under ncu (measure_traffic): the step's block once, nothing timed, nothing printed
+        tr.upload(0, hpos, box_internal)
+        plan.block(primo, nts, leff, w.skip, w.every, options=args.options)
+        return 0
 
     barrier, maxrank = ranks.barrier, ranks.max_over_ranks
 
@@ -427,21 +514,40 @@ def main():
     if not np.array_equal(counts_e, counts):
         raise SystemExit("e2e counts differ from resident counts")
 
+    # ---- the counts themselves: one checksum that must not depend on the number of GPUs, and -- for the default
+    # step -- must equal the checksum of the unmodified reference's counts (tests/golden/c4_subset_counts.json)
+    import hashlib
+    sha = hashlib.sha256(np.ascontiguousarray(counts).astype("<u8").tobytes()).hexdigest()
+    gold = golden_sha(name, w, nts) if not (args.quick or args.full) else None
+    # size-independent property: at lag 0 every atom meets itself at distance 0 once per origin (rmin = 0)
+    P = w.ntypes * (w.ntypes + 1) // 2
+    per_type = np.bincount(synth.lattice_types(w), minlength=w.ntypes)
+    origins = (nts + w.skip - 1) // w.skip
+    self_ok = True
+    if w.rmin == 0.0:
+        for a in range(w.ntypes):
+            slot = P - (a + 1) * (a + 2) // 2 + a + P
+            self_ok &= int(counts[0, slot, 0]) == int(per_type[a]) * origins and int(counts[0, slot, 1:].sum()) == 0
+    if not self_ok:
+        raise SystemExit("self row of lag 0 is wrong")
+    if gold is not None and gold != sha:
+        raise SystemExit("counts differ from the reference's (sha256 %s, reference %s)" % (sha, gold))
+
     value = args.steps * pairs_per_step / (dev_ms * 1e-3)
     e2e_value = args.steps * pairs_per_step / (e2e_ms * 1e-3)
     ops = 19 if w.triclinic else 16
+    issued = FP64_ISSUED[bool(w.triclinic)]
     kernel_rate = args.steps * pairs_per_step / (ker_ms * 1e-3) / world   # per GPU
     achieved = kernel_rate * ops
     in_range = float(counts.sum()) / float(pairs_per_step)
-    # DRAM bytes of one launch of this kernel from the committed ncu capture (per launch, like `achieved`);
-    # only for the exact workload that was captured, on one GPU
     traffic, traffic_extra = None, {}
-    try:
-        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        key = name if not args.quick else None
-        if key in tj and world == 1:
-            traffic = tj[key]["dram_bytes_read"] + tj[key]["dram_bytes_write"]
-            traffic_extra = {"traffic_unit": "DRAM bytes per launch (ncu)", "traffic_source": tj[key]["source"],
+    if rank == 0 and world == 1 and not args.no_traffic:
+        # release the device window first: the child needs the same memory
+        tj, how = measure_traffic(args, name)
+        if tj is not None:
+            traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
+            traffic_extra = {"traffic_unit": "DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum)",
+                             "traffic_source": "ncu re-run of this step inside this bench run (%d launch(es))" % tj["launches"],
                              "algorithmic_bytes_per_launch": int(njobs) * 2 * int(w.natoms) * 24,
                              "hbm_gbs": traffic / (ker_ms / args.steps * 1e-3) / 1e9}
             try:
@@ -450,8 +556,8 @@ def main():
                 traffic_extra["hbm_frac"] = traffic_extra["hbm_gbs"] / mp["hbm_gbs"]
             except Exception:
                 pass
-    except Exception:
-        traffic = None
+        else:
+            traffic_extra = {"traffic_source": "not measured: %s" % how}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -460,10 +566,16 @@ def main():
                 "d2h_bytes_per_step": int(counts.nbytes), "ms_per_step": e2e_ms / args.steps},
         "gpu_launches": int(launches),
         "clocks": clocks,
+        "counts_sha256": sha,
+        "counts_check": {"reference_sha256": gold, "equal_to_reference": (gold == sha) if gold else None,
+                         "reference_source": "tests/golden/%s_subset_counts.json (unmodified reference, CPU)" % name.lower() if gold else None,
+                         "self_row_lag0": bool(self_ok), "counts_sum": int(counts.sum())},
         "roofline": {
             "bound": "fp64", "achieved": achieved / 1e12, "peak": peak / 1e12, "unit": "T FP64-op/s per GPU",
             "frac": achieved / peak, "traffic": traffic,
-            "ops_per_pair_eval": ops, "kernel_ms_per_step": ker_ms / args.steps,
+            "ops_per_pair_eval": ops, "fp64_instr_issued_per_pair_eval": issued,
+            "fp64_pipe_issued_frac": kernel_rate * issued / peak,
+            "kernel_ms_per_step": ker_ms / args.steps,
             "pair_evals_per_s_per_gpu": kernel_rate, "in_range_fraction": in_range,
             "peak_source": "DFMA-chain microbenchmark in this run (agofrt_fp64_peak); MEASURED_PEAKS.json has no FP64 entry",
             **traffic_extra,
