@@ -149,6 +149,7 @@ struct TrajDev {
     int *perm = nullptr;         // [npad]
     int *type_pad = nullptr;     // [npad]
     int *type_start = nullptr;   // [ntypes+1]
+    int *type_real_end = nullptr; // [ntypes] end of the real atoms of every type group
     unsigned int *flags = nullptr;  // [4]: 0 = inf seen, 1 = wrap cap hit
     double *probe = nullptr;        // [4]: result of agofrt_traj_d2_pair
     unsigned long long *nb_hist = nullptr;  // neighbour-count histogram [ntypes][natoms+1] (agofrt_neighbour_hist)
@@ -208,6 +209,8 @@ struct agofrt_plan {
     int glo = 0;                 // ... guard bins below bin 0 in every shared-memory histogram row
     bool safe_ok = false;        // validated on the device when the plan was made
     double q_reach = 0;          // largest bin coordinate the float path may meet before it must give up
+    bool safe2_ok = false;       // the two-floor form (MODE_SAFE2) is valid for this plan: integer c0, validated on the device
+    float inv_lo = 0, inv_hi = 0, bias0 = 0;
     std::vector<PlanDev> dev;
     unsigned long long *host_counts = nullptr;  // pinned
     size_t host_counts_len = 0;
@@ -456,6 +459,7 @@ static void free_traj_dev(agofrt_traj *t) {
         cudaFree(d.perm);
         cudaFree(d.type_pad);
         cudaFree(d.type_start);
+        cudaFree(d.type_real_end);
         cudaFree(d.flags);
         cudaFree(d.probe);
         cudaFree(d.nb_hist);
@@ -494,6 +498,8 @@ extern "C" int agofrt_traj_create(agofrt_traj **out, agofrt_ctx *ctx, size_t nat
     }
     t->type_start[ntypes] = static_cast<int>(off);
     t->npad = static_cast<int>(off);
+    std::vector<int> real_end(ntypes);
+    for (int k = 0; k < ntypes; ++k) real_end[k] = t->type_start[k] + static_cast<int>(cnt[k]);
     t->type_pad.assign(t->npad, 0);
     for (int k = 0; k < ntypes; ++k)
         for (int s = t->type_start[k]; s < t->type_start[k + 1]; ++s) t->type_pad[s] = k;
@@ -521,12 +527,14 @@ extern "C" int agofrt_traj_create(agofrt_traj **out, agofrt_ctx *ctx, size_t nat
         CU(cudaMalloc(&d.perm, npad1 * sizeof(int)));
         CU(cudaMalloc(&d.type_pad, npad1 * sizeof(int)));
         CU(cudaMalloc(&d.type_start, (ntypes + 1) * sizeof(int)));
+        CU(cudaMalloc(&d.type_real_end, ntypes * sizeof(int)));
         CU(cudaMalloc(&d.flags, 4 * sizeof(unsigned int)));
         CU(cudaMalloc(&d.probe, 4 * sizeof(double)));
         CU(cudaStreamCreateWithFlags(&d.up, cudaStreamNonBlocking));
         CU(cudaMemset(d.flags, 0, 4 * sizeof(unsigned int)));
         if (t->npad > 0) CU(cudaMemcpy(d.type_pad, t->type_pad.data(), t->npad * sizeof(int), cudaMemcpyHostToDevice));
         CU(cudaMemcpy(d.type_start, t->type_start.data(), (ntypes + 1) * sizeof(int), cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(d.type_real_end, real_end.data(), ntypes * sizeof(int), cudaMemcpyHostToDevice));
     }
     *out = t.release();
     return AGOFRT_OK;
@@ -964,16 +972,32 @@ static int validate_safe_zone(agofrt_plan *p) {
         CU(cudaStreamSynchronize(dv.stream));
         return AGOFRT_OK;
     };
-    const int rc = body();
+    int rc = body();
+    if (rc == AGOFRT_OK && bad != 0) {
+        p->safe_ok = false;
+        p->safe2_ok = false;
+        p->glo = 0;
+    }
+    // the two-floor form of the guess (MODE_SAFE2), on every probe the mode can meet: d2 up to the square of the
+    // distance whose bin coordinate is q_reach
+    if (rc == AGOFRT_OK && p->safe_ok && p->safe2_ok) {
+        unsigned int bad2 = 0;
+        const double rtop = p->q_reach * p->dr + std::fabs(p->rmin);
+        auto body2 = [&]() -> int {
+            CU(cudaMemsetAsync(dbad, 0, sizeof(unsigned int), dv.stream));
+            CU(launch_validate_safe2(dprobe, dexp, static_cast<int>(probes.size()), p->inv_lo, p->inv_hi, p->bias0, rtop * rtop,
+                                     static_cast<int>(nbin), p->glo, dbad, dv.stream));
+            CU(cudaMemcpyAsync(&bad2, dbad, sizeof(bad2), cudaMemcpyDeviceToHost, dv.stream));
+            CU(cudaStreamSynchronize(dv.stream));
+            return AGOFRT_OK;
+        };
+        rc = body2();
+        if (bad2 != 0) p->safe2_ok = false;
+    }
     cudaFree(dprobe);
     cudaFree(dexp);
     cudaFree(dbad);
-    if (rc != AGOFRT_OK) return rc;
-    if (bad != 0) {
-        p->safe_ok = false;
-        p->glo = 0;
-    }
-    return AGOFRT_OK;
+    return rc;
 }
 
 extern "C" int agofrt_plan_create(agofrt_plan **out, agofrt_traj *traj, double rmin, double rmax, unsigned nbin) try {
@@ -1041,16 +1065,26 @@ extern "C" int agofrt_plan_create(agofrt_plan **out, agofrt_traj *traj, double r
             if (guards <= 4096) {
                 p->glo = static_cast<int>(guards);
                 p->safe_ok = true;
+                // MODE_SAFE2 wants c0 = -rmin/dr to be an integer as a float (rmin = 0, or a multiple of dr): then
+                // 1.5*2^23 + c0 + row is an integer and one round-down FFMA yields the histogram word
+                if (p->c0 == std::floor(p->c0) && std::fabs(p->c0) < 4000.0f) {
+                    const double inv = 1.0 / p->dr, delta = std::ldexp(1.0, -20);
+                    p->inv_lo = static_cast<float>(inv * (1.0 - delta));
+                    p->inv_hi = static_cast<float>(inv * (1.0 + delta));
+                    p->bias0 = 12582912.0f + p->c0;
+                    p->safe2_ok = p->inv_lo < p->inv_hi && std::isfinite(p->inv_hi);
+                }
             }
         }
     }
     // shared-memory budget; the guard bins are given up before the plan is refused
     for (const Dev &d : traj->ctx->devs) {
-        if (pair_kernel_smem_bytes(nt, static_cast<int>(nbin), p->glo, true) > d.smem_optin && p->glo > 0) {
+        if (pair_kernel_smem_bytes(nt, static_cast<int>(nbin), static_cast<int>(nbin), p->glo, true) > d.smem_optin && p->glo > 0) {
             p->glo = 0;
             p->safe_ok = false;
+            p->safe2_ok = false;
         }
-        const size_t smem = pair_kernel_smem_bytes(nt, static_cast<int>(nbin), p->glo, true);
+        const size_t smem = pair_kernel_smem_bytes(nt, static_cast<int>(nbin), static_cast<int>(nbin), p->glo, true);
         if (smem > d.smem_optin)
             return fail(AGOFRT_ERR_TOO_LARGE,
                         "histogram of %d type-pair rows x %u bins needs %zu bytes of shared memory (> %zu)",
@@ -1204,6 +1238,7 @@ extern "C" int agofrt_block(agofrt_plan *p, size_t primo, unsigned ntimesteps, u
     // ---- the (lag, origin) jobs, in the reference's loop order (calculatemultithread.h:114-115) ----
     std::vector<Job> jobs_fast, jobs_gen;
     uint64_t njobs = 0;
+    bool all_fast = false;
     if (ntimesteps > 0 && leff > 0) {
         // the last frame the loops really touch: last origin + last lag
         const size_t last = primo + static_cast<size_t>((ntimesteps - 1) / skip) * skip +
@@ -1217,7 +1252,7 @@ extern "C" int agofrt_block(agofrt_plan *p, size_t primo, unsigned ntimesteps, u
                         "the window holds an infinite coordinate or a non-positive / non-finite box edge "
                         "(the reference's minimum image would not terminate)");
         const bool may_fast = !(options & AGOFRT_OPT_FORCE_GENERAL);
-        const bool all_fast = may_fast && range_is_single_pass(t, primo - t->first_frame, last - t->first_frame);
+        all_fast = may_fast && range_is_single_pass(t, primo - t->first_frame, last - t->first_frame);
         const size_t expect = static_cast<size_t>((leff + every - 1) / every) * ((ntimesteps + skip - 1) / skip);
         if (expect >= 0xF0000000ull)   // (the same limit as on the work units below, before any memory is asked for)
             return fail(AGOFRT_ERR_ARG, "too many work units in one block (%zu (lag, origin) jobs)", expect);
@@ -1322,7 +1357,40 @@ extern "C" int agofrt_block(agofrt_plan *p, size_t primo, unsigned ntimesteps, u
         if (options & AGOFRT_OPT_DENSE) dense = true;
         if (options & AGOFRT_OPT_SPARSE) dense = false;
     }
-    const size_t smem = pair_kernel_smem_bytes(nt, static_cast<int>(p->nbin), p->glo, want_edges);
+    size_t smem = pair_kernel_smem_bytes(nt, static_cast<int>(p->nbin), static_cast<int>(p->nbin), p->glo, want_edges);
+    // MODE_SAFE2 (dense windows): histogram rows long enough for EVERY distance the single-pass minimum image can
+    // produce on this window -- from the same coordinate bounds that prove the single pass -- so that the fast path
+    // needs no clamp.  |d_c| <= W_c = max(l_half_c, D_c - 2*l_half_c) after the wrap of component c, where D_c bounds
+    // the difference before it (coordinate spread, plus the tilt corrections of the components above).
+    int nhi = static_cast<int>(p->nbin);
+    bool use_safe2 = false;
+    if (use_safe && dense && p->safe2_ok && all_fast && !aggregate && !want_edges && !small && same_box && !nothing &&
+        !(options & AGOFRT_OPT_NO_SAFE2)) {
+        const size_t f0 = primo - t->first_frame;
+        const size_t f1 = f0 + static_cast<size_t>((ntimesteps - 1) / skip) * skip + static_cast<size_t>((leff - 1) / every) * every;
+        double lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+        for (size_t f = f0; f <= f1; ++f)
+            for (int c = 0; c < 3; ++c) {
+                lo[c] = std::min(lo[c], t->bounds[f * 6 + c]);
+                hi[c] = std::max(hi[c], t->bounds[f * 6 + 3 + c]);
+            }
+        const double *b = &t->box6[0];
+        const double Dz = hi[2] - lo[2], Dy = hi[1] - lo[1] + std::fabs(b[5]), Dx = hi[0] - lo[0] + std::fabs(b[3]) + std::fabs(b[4]);
+        const double Wz = std::max(b[2], Dz - 2 * b[2]), Wy = std::max(b[1], Dy - 2 * b[1]), Wx = std::max(b[0], Dx - 2 * b[0]);
+        const double reach = std::sqrt(Wx * Wx + Wy * Wy + Wz * Wz) * (1.0 + 1e-9);
+        const double qtop = (reach - p->rmin) / p->dr * (1.0 + 4e-6) + 2.0;
+        if (std::isfinite(qtop) && qtop < p->q_reach && qtop < 60000.0) {
+            const int want = std::max(static_cast<int>(p->nbin), static_cast<int>(std::ceil(qtop)) + 1);
+            const size_t need = pair_kernel_smem_bytes(nt, static_cast<int>(p->nbin), want, p->glo, false);
+            size_t cap = SIZE_MAX;
+            for (const Dev &d : ctx->devs) cap = std::min(cap, d.smem_optin);
+            if (need <= std::min<size_t>(cap, 100 * 1024)) {   // two CTAs per SM must still fit
+                use_safe2 = true;
+                nhi = want;
+                smem = need;
+            }
+        }
+    }
 
     // ---- pinned read-back buffer ----
     if (len > p->host_counts_len) {
@@ -1423,21 +1491,27 @@ extern "C" int agofrt_block(agofrt_plan *p, size_t primo, unsigned ntimesteps, u
                 pp.qmax = p->qmax;
                 pp.glo = p->glo;
                 pp.hhi = p->hlo + p->hspan;
+                pp.nhi = nhi;
+                pp.inv_lo = p->inv_lo;
+                pp.inv_hi = p->inv_hi;
+                pp.bias0 = p->bias0;
+                pp.type_real_end = td.type_real_end;
                 int mode = kModeThr;
                 if (want_edges)
                     mode = kModeEdges;
                 else if (aggregate)
                     mode = kModeAgg;
                 else if (pass == 0 && use_safe)
-                    mode = dense ? kModeSafeDense : kModeSafe;
+                    mode = use_safe2 ? kModeSafe2 : (dense ? kModeSafeDense : kModeSafe);
                 const bool ubox = same_box && pass == 0 && !(options & AGOFRT_OPT_NO_UBOX) &&
-                                  (mode == kModeThr || mode == kModeSafe || mode == kModeSafeDense);
+                                  (mode == kModeThr || mode == kModeSafe || mode == kModeSafeDense || mode == kModeSafe2);
                 if (ubox) {
                     const double *b = &t->box6[0];
                     for (int k = 0; k < 6; ++k) pp.ubox[k] = b[k];
                     for (int k = 0; k < 3; ++k) pp.ubox[6 + k] = -2.0 * b[k];
+                    for (int k = 0; k < 3; ++k) pp.ubox[9 + k] = -b[3 + k];
                 } else {
-                    for (int k = 0; k < 9; ++k) pp.ubox[k] = 0.0;
+                    for (int k = 0; k < 12; ++k) pp.ubox[k] = 0.0;
                 }
                 const int variant = (tri ? 1 : 0) | (pass == 0 ? 2 : 0) | (mode << 2) | (ubox ? 32 : 0) | (small ? 64 : 0);
                 const int grid = static_cast<int>(std::min<uint64_t>(ue - ub, static_cast<uint64_t>(kMinBlocks) * dv.sm_count));

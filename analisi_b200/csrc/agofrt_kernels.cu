@@ -56,6 +56,7 @@ __device__ __forceinline__ double2 lds_f64x2(uint32_t addr) {
 struct BoxRegs {
     double lhx, lhy, lhz;   // half edges
     double xy, xz, yz;      // tilt factors
+    double nxy, nxz, nyz;   // ... and their negatives (single-pass triclinic form)
 };
 
 template <bool TRI>
@@ -135,11 +136,58 @@ __device__ __forceinline__ void wrap_abs(double &x, double lh, double nL) {
         : "d"(lh), "d"(nL));
 }
 
+// Triclinic components whose SIGN feeds the tilt corrections of the lower ones (z, then y).  The reference's step
+//   if |v| > l_half:  (v, lower...) -= sign(v) * (2*l_half, tilt...)
+// is odd in the whole displacement vector (IEEE addition and the compares are sign-symmetric), and only squares of
+// the final components are used.  So instead of carrying sign(v) into the corrections (the r1 form built a +-1.0
+// multiplier with two LOP3 and a SEL per component and applied it with DFMAs), the LOWER components are multiplied
+// by sign(v) first -- one LOP3 on the high word each, exact -- and the step becomes the one-sided
+//   if |v| > l_half:  v = |v| - 2*l_half;  lower -= tilt
+// i.e. predicated DADDs with uniform constants.  The vector that comes out is the reference's times +-1 component
+// by component: the same squares, the same d2, bit for bit.
+__device__ __forceinline__ void flip_by_sign(double &x, double s) {   // x *= sign(s)  (xor of the sign bits)
+    asm volatile(
+        "{\n\t.reg .b32 xl, xh, sl, sh;\n\t"
+        "mov.b64 {xl, xh}, %0;\n\t"
+        "mov.b64 {sl, sh}, %1;\n\t"
+        "lop3.b32 xh, xh, sh, 0x80000000, 0x78;\n\t"   // xh ^ (sh & 0x80000000)
+        "mov.b64 %0, {xl, xh};\n\t}"
+        : "+d"(x)
+        : "d"(s));
+}
+// if |v| > lh: v = |v| + nL; a += na; b += nb   (nL = -2*lh, na / nb = minus the tilt factors)
+__device__ __forceinline__ void wrap_abs3(double &v, double &a, double &b, double lh, double nL, double na, double nb) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .f64 t;\n\t"
+        "abs.f64 t, %0;\n\t"
+        "setp.gt.f64 p, t, %3;\n\t"
+        "@!p bra WRAP3_SKIP%=;\n\t"
+        "add.rn.f64 %0, t, %4;\n\t"
+        "add.rn.f64 %1, %1, %5;\n\t"
+        "add.rn.f64 %2, %2, %6;\n\t"
+        "WRAP3_SKIP%=:\n\t}"
+        : "+d"(v), "+d"(a), "+d"(b)
+        : "d"(lh), "d"(nL), "d"(na), "d"(nb));
+}
+__device__ __forceinline__ void wrap_abs2(double &v, double &a, double lh, double nL, double na) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .f64 t;\n\t"
+        "abs.f64 t, %0;\n\t"
+        "setp.gt.f64 p, t, %2;\n\t"
+        "@!p bra WRAP2_SKIP%=;\n\t"
+        "add.rn.f64 %0, t, %3;\n\t"
+        "add.rn.f64 %1, %1, %4;\n\t"
+        "WRAP2_SKIP%=:\n\t}"
+        : "+d"(v), "+d"(a)
+        : "d"(lh), "d"(nL), "d"(na));
+}
+
 template <bool TRI>
 __device__ __forceinline__ void min_image_single(double &dx, double &dy, double &dz, const BoxRegs &b,
                                                  double nLx, double nLy, double nLz) {  // nL = -(2*l_half)
     if (TRI) {
         // reference: z<0 ? (z+=L, y+=yz, x+=xz) : (z-=L, y-=yz, x-=xz)  ==  v -= sign(z) * (L, yz, xz)
+#ifdef AGOFRT_OLD_TRIWRAP
         {
             const double m = mask_signed(fabs(dz) > b.lhz, dz);
             dz = __fma_rn(m, nLz, dz);
@@ -151,6 +199,13 @@ __device__ __forceinline__ void min_image_single(double &dx, double &dy, double 
             dy = __fma_rn(m, nLy, dy);
             dx = __fma_rn(m, -b.xy, dx);
         }
+#else
+        flip_by_sign(dy, dz);
+        flip_by_sign(dx, dz);
+        wrap_abs3(dz, dy, dx, b.lhz, nLz, b.nyz, b.nxz);
+        flip_by_sign(dx, dy);
+        wrap_abs2(dy, dx, b.lhy, nLy, b.nxy);
+#endif
         wrap_abs(dx, b.lhx, nLx);   // last component: only its square is used
     } else {
         wrap_abs(dz, b.lhz, nLz);
@@ -173,7 +228,12 @@ __device__ __forceinline__ double d2_of(double dx, double dy, double dz) {
 // MODE_SAFE  float guess accepted without looking at the thresholds when it is farther than `eps`
 //            bins from a bin edge (eps bounds the float error, validated on the device when the plan
 //            is made); the few pairs closer than eps to an edge go through the exact bracket search
-enum { MODE_THR = 0, MODE_AGG = 1, MODE_EDGES = 2, MODE_SAFE = 3, MODE_SAFE_DENSE = 4 };
+//   MODE_SAFE2 the dense path, second form (see group_dense2): the bin index AND its row come out of ONE
+//            round-down FFMA as the word index of the shared histogram, a second FFMA with a slightly larger
+//            slope says whether the guess sits within eps of an edge, and the binning of pair t-2 is interleaved
+//            with the distance of pair t.  Needs an integer c0 (rmin a multiple of dr, e.g. 0), histogram rows
+//            long enough for every distance the window can produce (no clamp) and no NaN in the fast groups.
+enum { MODE_THR = 0, MODE_AGG = 1, MODE_EDGES = 2, MODE_SAFE = 3, MODE_SAFE_DENSE = 4, MODE_SAFE2 = 5 };
 
 // float guess of the bin from the bits of d2 (no FP64 conversion instruction): rebias the
 // exponent, keep 23 mantissa bits, MUFU sqrt, one FFMA.  Returns guess+1 clamped to [0, nbin+2]:
@@ -349,15 +409,17 @@ __device__ __noinline__ void bin_pair_fix(double d2, const double2 *__restrict__
 // the pair kernel
 // ---------------------------------------------------------------------------------------------
 struct SmemLayout {
-    size_t thr2, thr_full, stage, hist, dump, rowtab, tstart, bars, sched, total;
+    size_t thr2, thr_full, stage, hist, dump, rowtab, tstart, treal, bars, sched, total;
 };
 
 __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-// every histogram row: glo guard bins, nbin bins, one guard bin
-__host__ __device__ inline int row_stride(int nbin, int glo) { return glo + nbin + 1; }
+// every histogram row: glo guard bins, nhi bins (the first nbin of them are merged; nhi > nbin when the row must
+// hold every distance the window can produce, MODE_SAFE2), one guard bin.  After the 2P rows of the type pairs comes
+// one more row that is never merged: ghost i slots of MODE_SAFE2 count there.
+__host__ __device__ inline int row_stride(int nhi, int glo) { return glo + nhi + 1; }
 
-__host__ __device__ inline SmemLayout smem_layout(int ntypes, int nbin, int glo, bool edges) {
+__host__ __device__ inline SmemLayout smem_layout(int ntypes, int nbin, int nhi, int glo, bool edges) {
     SmemLayout L;
     size_t o = 0;
     L.stage = o;
@@ -369,12 +431,14 @@ __host__ __device__ inline SmemLayout smem_layout(int ntypes, int nbin, int glo,
     L.bars = align_up(o, 8);
     o = L.bars + kStages * sizeof(uint64_t);
     L.hist = o;
-    o += static_cast<size_t>(ntypes) * (ntypes + 1) * row_stride(nbin, glo) * sizeof(unsigned int);
+    o += (static_cast<size_t>(ntypes) * (ntypes + 1) + 1) * row_stride(nhi, glo) * sizeof(unsigned int);
     L.dump = o;
     o += 32 * sizeof(unsigned int);
     L.rowtab = o;
     o += static_cast<size_t>(ntypes) * ntypes * sizeof(unsigned int);
     L.tstart = o;
+    o += static_cast<size_t>(ntypes + 1) * sizeof(int);
+    L.treal = o;
     o += static_cast<size_t>(ntypes + 1) * sizeof(int);
     L.sched = o;
     o += 4 * sizeof(unsigned int);
@@ -382,8 +446,8 @@ __host__ __device__ inline SmemLayout smem_layout(int ntypes, int nbin, int glo,
     return L;
 }
 
-size_t pair_kernel_smem_bytes(int ntypes, int nbin, int glo, bool edges) {
-    return smem_layout(ntypes, nbin, glo, edges).total;
+size_t pair_kernel_smem_bytes(int ntypes, int nbin, int nhi, int glo, bool edges) {
+    return smem_layout(ntypes, nbin, nhi, glo, edges).total;
 }
 
 struct PairConst {
@@ -465,6 +529,142 @@ __device__ __forceinline__ void group_bin_safe(const PairParams &p, const PairCo
                     bin_pair_fix(d2[k][q], s_thr2, p.nbin, p.inv_dr, p.c0, p.c0h, p.qmax, p.lim, s_hist + r);
                 }
             }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// MODE_SAFE2: distance and binning of one group, interleaved
+// ---------------------------------------------------------------------------------------------
+// Per pair:  f = (float)d2 (toward zero), s = sqrt.approx(f), and then
+//     ra = fma.rm(s, inv_lo, bias)      rb = fma.rm(s, inv_hi, bias)
+// with bias = 1.5*2^23 + c0 + (word index of bin 0 of the pair's histogram row), an integer: in [2^23, 2^24) floats
+// are the integers, so the round-down FFMA gives  1.5*2^23 + row + floor(s*inv + c0)  EXACTLY and the low mantissa
+// bits of ra are the word of the shared histogram to increment -- no clamp, no float->int conversion, no separate
+// row add.  inv_lo / inv_hi are inv_dr * (1 -+ 2^-20): the two floors differ exactly when an integer lies between the
+// two products, i.e. when the guess is within a relative 2^-20 of a bin edge (the float error of s and of the
+// reference's own rounding is below 2^-21.4; validated on the device for every plan, as MODE_SAFE is).  The group ORs
+// ra ^ rb; a nonzero OR (3 groups in 10^3) sends the group to group_fix2, which recomputes it and corrects the pairs
+// that are near an edge.  The instruction streams of "distance of pair t" (14 / 17 FP64 instructions) and "binning of
+// pair t-2" (7 instructions on the other pipes) are emitted alternately, so that every warp always has work for both
+// the FP64 pipe and the rest of the issue slots (in r1 a warp ran 224 FP64 instructions, then 190 others: four warps
+// per scheduler were too few to keep the FP64 pipe fed).
+struct IAtoms {
+    double x[kIPT], y[kIPT], z[kIPT];
+    float bias[kIPT];
+};
+
+__device__ __forceinline__ float cvt_rz(double v) {
+    float f;
+    asm volatile("cvt.rz.f32.f64 %0, %1;" : "=f"(f) : "d"(v));
+    return f;
+}
+__device__ __forceinline__ float sqrt_approx_v(float f) {
+    float s;
+    asm volatile("sqrt.approx.ftz.f32 %0, %1;" : "=f"(s) : "f"(f));
+    return s;
+}
+__device__ __forceinline__ void safe2_floors(float s, float inv_lo, float inv_hi, float bias, float &ra, float &rb) {
+    asm("fma.rm.f32 %0, %1, %2, %3;" : "=f"(ra) : "f"(s), "f"(inv_lo), "f"(bias));
+    asm("fma.rm.f32 %0, %1, %2, %3;" : "=f"(rb) : "f"(s), "f"(inv_hi), "f"(bias));
+}
+// kaddr = shared address of hist[0] - 4 * 0x4B400000 (mod 2^32).  (The OR into acc stays outside the asm block: with
+// acc as a read-write operand of a lop3 inside it, ptxas 12.9 crashes on the unrolled group.)
+__device__ __forceinline__ void safe2_bin(float s, float inv_lo, float inv_hi, float bias, uint32_t kaddr, unsigned int &acc) {
+    unsigned int x;
+    asm volatile(
+        "{\n\t.reg .f32 ra, rb;\n\t.reg .b32 ia, ib, ad;\n\t"
+        "fma.rm.f32 ra, %1, %2, %4;\n\t"
+        "fma.rm.f32 rb, %1, %3, %4;\n\t"
+        "mov.b32 ia, ra;\n\t"
+        "mov.b32 ib, rb;\n\t"
+        "xor.b32 %0, ia, ib;\n\t"
+        "shl.b32 ad, ia, 2;\n\t"
+        "add.u32 ad, ad, %5;\n\t"
+        "red.shared.add.u32 [ad], 1;\n\t}"
+        : "=r"(x)
+        : "f"(s), "f"(inv_lo), "f"(inv_hi), "f"(bias), "r"(kaddr)
+        : "memory");
+    acc |= x;
+}
+
+template <bool TRI>
+__device__ __forceinline__ double pair_d2_single(const PairConst &c, double xi, double yi, double zi, double xj, double yj,
+                                                 double zj) {
+    double dx = __dsub_rn(xi, xj);
+    double dy = __dsub_rn(yi, yj);
+    double dz = __dsub_rn(zi, zj);
+    min_image_single<TRI>(dx, dy, dz, c.box, c.nLx, c.nLy, c.nLz);
+    return d2_of(dx, dy, dz);
+}
+
+template <bool TRI>
+__device__ __forceinline__ unsigned int group_dense2(const PairParams &p, const PairConst &c, const double (&xi)[kIPT],
+                                                     const double (&yi)[kIPT], const double (&zi)[kIPT],
+                                                     const float (&bias)[kIPT], uint32_t kaddr, uint32_t sx_addr,
+                                                     uint32_t jrow_bytes, int jrel) {
+    double xj[kJU], yj[kJU], zj[kJU];
+#pragma unroll
+    for (int q = 0; q < kJU; q += 2) {
+        const uint32_t a = sx_addr + static_cast<uint32_t>(jrel + q) * 8u;
+        const double2 vx = lds_f64x2(a);
+        const double2 vy = lds_f64x2(a + jrow_bytes);
+        const double2 vz = lds_f64x2(a + 2u * jrow_bytes);
+        xj[q] = vx.x;
+        xj[q + 1] = vx.y;
+        yj[q] = vy.x;
+        yj[q + 1] = vy.y;
+        zj[q] = vz.x;
+        zj[q + 1] = vz.y;
+    }
+    constexpr int NP = kIPT * kJU;
+    constexpr int LAG_S = 1, LAG_B = 2;   // pairs between the distance, the root and the binning of a pair
+    float fv[NP];
+    unsigned int acc = 0;
+#pragma unroll
+    for (int t = 0; t < NP + LAG_B; ++t) {
+        if (t < NP) {
+            const int q = t / kIPT, k = t % kIPT;
+            fv[t] = cvt_rz(pair_d2_single<TRI>(c, xi[k], yi[k], zi[k], xj[q], yj[q], zj[q]));
+        }
+        if (t >= LAG_S && t - LAG_S < NP) fv[t - LAG_S] = sqrt_approx_v(fv[t - LAG_S]);
+        if (t >= LAG_B && t - LAG_B < NP) safe2_bin(fv[t - LAG_B], p.inv_lo, p.inv_hi, bias[(t - LAG_B) % kIPT], kaddr, acc);
+    }
+    return acc;
+}
+
+// Rare path of MODE_SAFE2: some pair of the group is within eps of a bin edge.  Recompute the group (same instructions,
+// same bits) and for every such pair take the fast-path increment back and count the pair where the exact threshold
+// table says (or nowhere).  Counters are integers modulo 2^32 and a CTA merges its rows only at barriers.
+template <bool TRI>
+__device__ __noinline__ void group_fix2(PairConst c, IAtoms ia, float inv_lo, float inv_hi, float bias0, uint32_t sx_addr,
+                                        uint32_t jrow_bytes, int jrel, const double2 *__restrict__ thr2, int nbin,
+                                        float inv_dr, float c0, unsigned int *s_hist) {
+    for (int q = 0; q < kJU; ++q) {
+        const uint32_t a = sx_addr + static_cast<uint32_t>(jrel + q) * 8u;
+        double xj, yj, zj;
+        asm volatile("ld.shared.f64 %0, [%1];" : "=d"(xj) : "r"(a));
+        asm volatile("ld.shared.f64 %0, [%1];" : "=d"(yj) : "r"(a + jrow_bytes));
+        asm volatile("ld.shared.f64 %0, [%1];" : "=d"(zj) : "r"(a + 2u * jrow_bytes));
+#pragma unroll
+        for (int k = 0; k < kIPT; ++k) {
+            const double d2 = pair_d2_single<TRI>(c, ia.x[k], ia.y[k], ia.z[k], xj, yj, zj);
+            const float s = sqrt_approx_v(cvt_rz(d2));
+            float ra, rb;
+            safe2_floors(s, inv_lo, inv_hi, ia.bias[k], ra, rb);
+            if (__float_as_int(ra) == __float_as_int(rb)) continue;
+            const int word = __float_as_int(ra) - 0x4B400000;                        // what the fast path incremented
+            const int row = static_cast<int>(__fsub_rn(ia.bias[k], bias0));         // exact: both are integers
+            int g = -1;
+            if ((d2 >= thr2[1].x) && (d2 < thr2[nbin].y)) {
+                g = static_cast<int>(bin_guess1(d2, inv_dr, c0, static_cast<unsigned int>(nbin) + 2u)) - 1;
+                g = min(max(g, 0), nbin - 1);
+                while (d2 < thr2[g + 1].x) --g;
+                while (d2 >= thr2[g + 1].y) ++g;
+            }
+            if (g >= 0 && row + g == word) continue;
+            atomicAdd(s_hist + word, 0xffffffffu);
+            if (g >= 0) atomicAdd(s_hist + row + g, 1u);
         }
     }
 }
@@ -555,9 +755,10 @@ __device__ __forceinline__ void process_group(const PairParams &p, const PairCon
 // (type_i, type_j) -> row table of Gofrt::get_itype, and the first slot of every type group.
 template <bool EDGES>
 __device__ __forceinline__ void cta_tables(const PairParams &p, int tid, int P, int rstride, unsigned int *s_hist,
-                                           double2 *s_thr2, double *s_thrf, unsigned int *s_rowtab, int *s_tstart) {
+                                           double2 *s_thr2, double *s_thrf, unsigned int *s_rowtab, int *s_tstart,
+                                           int *s_treal) {
     const int nt = p.ntypes, nbin = p.nbin;
-    for (int k = tid; k < 2 * P * rstride; k += kThreads) s_hist[k] = 0u;
+    for (int k = tid; k < (2 * P + 1) * rstride; k += kThreads) s_hist[k] = 0u;
     for (int k = tid; k < nbin + 3; k += kThreads) {
         // slot k <-> bin g = k-1
         const int g = k - 1;
@@ -583,6 +784,8 @@ __device__ __forceinline__ void cta_tables(const PairParams &p, int tid, int P, 
         s_rowtab[k] = static_cast<unsigned int>((P - (b + 1) * (b + 2) / 2 + a) * rstride + p.glo);
     }
     for (int k = tid; k <= nt; k += kThreads) s_tstart[k] = p.type_start[k];
+    // end of the REAL atoms of every type group (the slots from there to the next group's start are NaN ghosts)
+    for (int k = tid; k < nt; k += kThreads) s_treal[k] = p.type_real_end ? p.type_real_end[k] : p.type_start[k + 1];
 }
 
 // Merge the CTA's shared-memory rows (guard bins left out) into lag row `lag` of the global histogram and
@@ -610,7 +813,7 @@ template <bool TRI, bool FAST, int MODE, bool UBOX>
 __global__ void __launch_bounds__(kThreads, kMinBlocks) pair_kernel(const PairParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
     constexpr bool EDGES = MODE == MODE_EDGES;
-    const SmemLayout L = smem_layout(p.ntypes, p.nbin, p.glo, EDGES);
+    const SmemLayout L = smem_layout(p.ntypes, p.nbin, p.nhi, p.glo, EDGES);
     double *s_stage = reinterpret_cast<double *>(smem + L.stage);
     double2 *s_thr2 = reinterpret_cast<double2 *>(smem + L.thr2);
     double *s_thrf = reinterpret_cast<double *>(smem + L.thr_full);
@@ -618,6 +821,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) pair_kernel(const PairPa
     unsigned int *s_hist = reinterpret_cast<unsigned int *>(smem + L.hist);
     unsigned int *s_rowtab = reinterpret_cast<unsigned int *>(smem + L.rowtab);
     int *s_tstart = reinterpret_cast<int *>(smem + L.tstart);
+    int *s_treal = reinterpret_cast<int *>(smem + L.treal);
     unsigned int *s_sched = reinterpret_cast<unsigned int *>(smem + L.sched);
 
     const int tid = threadIdx.x;
@@ -625,10 +829,10 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) pair_kernel(const PairPa
     const int nt = p.ntypes, nbin = p.nbin;
     const int P = nt * (nt + 1) / 2;
     const int hlen = 2 * P * nbin;                 // words of one lag in the global histogram
-    const int rstride = row_stride(nbin, p.glo);   // words of one row in shared memory (with its guard bins)
+    const int rstride = row_stride(p.nhi, p.glo);   // words of one row in shared memory (with its guard bins)
     const unsigned int self_off = static_cast<unsigned int>(P * rstride);
 
-    cta_tables<EDGES>(p, tid, P, rstride, s_hist, s_thr2, s_thrf, s_rowtab, s_tstart);
+    cta_tables<EDGES>(p, tid, P, rstride, s_hist, s_thr2, s_thrf, s_rowtab, s_tstart, s_treal);
     if (tid == 0) {
         for (int s = 0; s < kStages; ++s) mbar_init(&s_bar[s], 1);
         mbar_fence_init();
@@ -687,6 +891,12 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) pair_kernel(const PairPa
             c.nLx = __hiloint2double(__double2hiint(p.ubox[6]) ^ zero, __double2loint(p.ubox[6]));
             c.nLy = __hiloint2double(__double2hiint(p.ubox[7]) ^ zero, __double2loint(p.ubox[7]));
             c.nLz = __hiloint2double(__double2hiint(p.ubox[8]) ^ zero, __double2loint(p.ubox[8]));
+        c.box.nxy = __hiloint2double(__double2hiint(p.ubox[9]) ^ zero, __double2loint(p.ubox[9]));
+        c.box.nxz = __hiloint2double(__double2hiint(p.ubox[10]) ^ zero, __double2loint(p.ubox[10]));
+        c.box.nyz = __hiloint2double(__double2hiint(p.ubox[11]) ^ zero, __double2loint(p.ubox[11]));
+            c.box.nxy = __hiloint2double(__double2hiint(p.ubox[9]) ^ zero, __double2loint(p.ubox[9]));
+            c.box.nxz = __hiloint2double(__double2hiint(p.ubox[10]) ^ zero, __double2loint(p.ubox[10]));
+            c.box.nyz = __hiloint2double(__double2hiint(p.ubox[11]) ^ zero, __double2loint(p.ubox[11]));
         } else {
             const double *bx = p.box + static_cast<size_t>(job.fi) * 6;
             c.box.lhx = __ldg(bx + 0);
@@ -695,6 +905,9 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) pair_kernel(const PairPa
             c.box.xy = __ldg(bx + 3);
             c.box.xz = __ldg(bx + 4);
             c.box.yz = __ldg(bx + 5);
+            c.box.nxy = -c.box.xy;
+            c.box.nxz = -c.box.xz;
+            c.box.nyz = -c.box.yz;
             c.nLx = __dmul_rn(c.box.lhx, -2.0);
             c.nLy = __dmul_rn(c.box.lhy, -2.0);
             c.nLz = __dmul_rn(c.box.lhz, -2.0);
@@ -703,6 +916,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) pair_kernel(const PairPa
         // ---- this thread's i atoms (frame fi) ----
         double xi[kIPT], yi[kIPT], zi[kIPT];
         int ii[kIPT], ti[kIPT];
+        bool ighost[kIPT];
         const double *pi = p.pos + static_cast<size_t>(job.fi) * 3 * p.npad;
         const int wi0 = itile * kTileI + warp * (32 * kIPT);  // this warp's i atoms: [wi0, wi0 + 32*kIPT)
 #pragma unroll
@@ -717,6 +931,17 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) pair_kernel(const PairPa
             } else {
                 xi[k] = yi[k] = zi[k] = __longlong_as_double(0x7ff8000000000000ll);
                 ti[k] = 0;
+            }
+            if (MODE == MODE_SAFE2) {
+                // no NaN in the fast groups: a ghost i slot takes the coordinates of slot 0 (a real atom) and counts
+                // into the row that is never merged
+                ighost[k] = xi[k] != xi[k];
+                if (ighost[k]) {
+                    xi[k] = pi[0];
+                    yi[k] = pi[p.npad];
+                    zi[k] = pi[2 * static_cast<size_t>(p.npad)];
+                    ii[k] = -1;
+                }
             }
         }
 
@@ -755,6 +980,52 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) pair_kernel(const PairPa
                 // [lo,hi) = before | overlap with this warp's own atoms | after   (all multiples of kPadGroup)
                 const int da = min(max(wi0, lo), hi);
                 const int db = min(max(wi0 + 32 * kIPT, lo), hi);
+                if (MODE == MODE_SAFE2) {
+                    // fast groups: no own atom (i == j goes to another row) and no ghost j slot (NaN) among the j atoms;
+                    // the groups that hold either -- the diagonal segment and the last group of a type -- take the
+                    // clamped form of MODE_SAFE_DENSE, which shares the histogram rows
+                    float bias[kIPT];
+#pragma unroll
+                    for (int k = 0; k < kIPT; ++k) {
+                        if (ighost[k]) row[k] = static_cast<unsigned int>(2 * P * rstride + p.glo);
+                        bias[k] = __fadd_rn(p.bias0, static_cast<float>(row[k]));
+                    }
+                    const uint32_t kaddr = c.hist_addr - 4u * 0x4B400000u;
+                    const int hc = max(lo, min(hi, s_treal[ty] & ~(kJU - 1)));   // [hc, hi): holds ghost j slots
+                    const int a1 = min(da, hc), b0 = min(max(db, lo), hc);
+                    auto fast = [&](int j) {
+                        const unsigned int near = group_dense2<TRI>(p, c, xi, yi, zi, bias, kaddr, sx_addr, kTileJ * 8u, j - j0);
+                        if (near) {
+                            IAtoms ia;
+#pragma unroll
+                            for (int k = 0; k < kIPT; ++k) {
+                                ia.x[k] = xi[k];
+                                ia.y[k] = yi[k];
+                                ia.z[k] = zi[k];
+                                ia.bias[k] = bias[k];
+                            }
+                            group_fix2<TRI>(c, ia, p.inv_lo, p.inv_hi, p.bias0, sx_addr, kTileJ * 8u, j - j0, s_thr2, p.nbin,
+                                            p.inv_dr, p.c0, s_hist);
+                        }
+                    };
+#pragma unroll 1
+                    for (int j = lo; j < a1; j += kJU) fast(j);
+#pragma unroll 1
+                    for (int j = a1; j < da; j += kJU)
+                        process_group<TRI, FAST, MODE_SAFE_DENSE, false>(p, c, xi, yi, zi, ii, row, sx_addr, kTileJ * 8u, j - j0, j,
+                                                                         s_thr2, s_thrf, s_hist, self_off, edges, wrap_ok);
+#pragma unroll 1
+                    for (int j = da; j < db; j += kJU)
+                        process_group<TRI, FAST, MODE_SAFE_DENSE, true>(p, c, xi, yi, zi, ii, row, sx_addr, kTileJ * 8u, j - j0, j,
+                                                                        s_thr2, s_thrf, s_hist, self_off, edges, wrap_ok);
+#pragma unroll 1
+                    for (int j = db; j < b0; j += kJU) fast(j);
+#pragma unroll 1
+                    for (int j = max(db, b0); j < hi; j += kJU)
+                        process_group<TRI, FAST, MODE_SAFE_DENSE, false>(p, c, xi, yi, zi, ii, row, sx_addr, kTileJ * 8u, j - j0, j,
+                                                                         s_thr2, s_thrf, s_hist, self_off, edges, wrap_ok);
+                    continue;
+                }
 #pragma unroll 1
                 for (int j = lo; j < da; j += kJU)
                     process_group<TRI, FAST, MODE, false>(p, c, xi, yi, zi, ii, row, sx_addr, kTileJ * 8u, j - j0, j, s_thr2, s_thrf,
@@ -811,13 +1082,14 @@ template <bool TRI, bool FAST, int MODE, bool UBOX>
 __global__ void __launch_bounds__(kThreads, kMinBlocks) pair_small_kernel(const PairParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
     constexpr bool EDGES = MODE == MODE_EDGES;
-    const SmemLayout L = smem_layout(p.ntypes, p.nbin, p.glo, EDGES);
+    const SmemLayout L = smem_layout(p.ntypes, p.nbin, p.nhi, p.glo, EDGES);
     double *s_stage = reinterpret_cast<double *>(smem + L.stage);
     double2 *s_thr2 = reinterpret_cast<double2 *>(smem + L.thr2);
     double *s_thrf = reinterpret_cast<double *>(smem + L.thr_full);
     unsigned int *s_hist = reinterpret_cast<unsigned int *>(smem + L.hist);
     unsigned int *s_rowtab = reinterpret_cast<unsigned int *>(smem + L.rowtab);
     int *s_tstart = reinterpret_cast<int *>(smem + L.tstart);
+    int *s_treal = reinterpret_cast<int *>(smem + L.treal);
     unsigned int *s_sched = reinterpret_cast<unsigned int *>(smem + L.sched);
 
     const int tid = threadIdx.x;
@@ -825,10 +1097,10 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) pair_small_kernel(const 
     const int nt = p.ntypes, nbin = p.nbin;
     const int P = nt * (nt + 1) / 2;
     const int hlen = 2 * P * nbin;
-    const int rstride = row_stride(nbin, p.glo);
+    const int rstride = row_stride(p.nhi, p.glo);
     const unsigned int self_off = static_cast<unsigned int>(P * rstride);
 
-    cta_tables<EDGES>(p, tid, P, rstride, s_hist, s_thr2, s_thrf, s_rowtab, s_tstart);
+    cta_tables<EDGES>(p, tid, P, rstride, s_hist, s_thr2, s_thrf, s_rowtab, s_tstart, s_treal);
     __syncthreads();
 
     PairConst c;
@@ -880,6 +1152,9 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) pair_small_kernel(const 
         c.nLx = __hiloint2double(__double2hiint(p.ubox[6]) ^ zero, __double2loint(p.ubox[6]));
         c.nLy = __hiloint2double(__double2hiint(p.ubox[7]) ^ zero, __double2loint(p.ubox[7]));
         c.nLz = __hiloint2double(__double2hiint(p.ubox[8]) ^ zero, __double2loint(p.ubox[8]));
+        c.box.nxy = __hiloint2double(__double2hiint(p.ubox[9]) ^ zero, __double2loint(p.ubox[9]));
+        c.box.nxz = __hiloint2double(__double2hiint(p.ubox[10]) ^ zero, __double2loint(p.ubox[10]));
+        c.box.nyz = __hiloint2double(__double2hiint(p.ubox[11]) ^ zero, __double2loint(p.ubox[11]));
     }
 
     unsigned long long edges = 0;
@@ -904,6 +1179,12 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) pair_small_kernel(const 
                     c.box.xy = __ldg(bx + 3);
                     c.box.xz = __ldg(bx + 4);
                     c.box.yz = __ldg(bx + 5);
+                    c.box.nxy = -c.box.xy;
+                    c.box.nxz = -c.box.xz;
+                    c.box.nyz = -c.box.yz;
+            c.box.nxy = -c.box.xy;
+            c.box.nxz = -c.box.xz;
+            c.box.nyz = -c.box.yz;
                     c.nLx = __dmul_rn(c.box.lhx, -2.0);
                     c.nLy = __dmul_rn(c.box.lhy, -2.0);
                     c.nLz = __dmul_rn(c.box.lhz, -2.0);
@@ -987,7 +1268,7 @@ static cudaError_t prepare_variant(size_t max_smem) {
     X(S + 0) X(S + 1) X(S + 2) X(S + 3) X(S + 4) X(S + 5) X(S + 6) X(S + 7) X(S + 8) X(S + 9) X(S + 10)     \
     X(S + 11) X(S + 12) X(S + 13) X(S + 14) X(S + 15) X(S + 18) X(S + 19)                                   \
     X(S + 32 + 2) X(S + 32 + 3) X(S + 32 + 14) X(S + 32 + 15) X(S + 32 + 18) X(S + 32 + 19)
-#define AGOFRT_VARIANTS(X) AGOFRT_VARIANTS_OF(X, 0) AGOFRT_VARIANTS_OF(X, 64)
+#define AGOFRT_VARIANTS(X) AGOFRT_VARIANTS_OF(X, 0) AGOFRT_VARIANTS_OF(X, 64) X(22) X(23) X(32 + 22) X(32 + 23)
 
 cudaError_t launch_pair_kernel(int variant, int grid, size_t smem, cudaStream_t stream, const PairParams &p) {
     switch (variant) {
@@ -1031,6 +1312,31 @@ cudaError_t launch_validate_safe(const double *probes, const int *expected, int 
                                  float qmax, int nbin, int glo, unsigned int *bad, cudaStream_t stream) {
     if (n <= 0) return cudaSuccess;
     validate_safe_kernel<<<(n + 255) / 256, 256, 0, stream>>>(probes, expected, n, inv_dr, c0h, lim, qmax, nbin, glo, bad);
+    return cudaGetLastError();
+}
+
+__global__ void validate_safe2_kernel(const double *__restrict__ probes, const int *__restrict__ expected, int n,
+                                      float inv_lo, float inv_hi, float bias0, double d2_max, int nbin, int glo,
+                                      unsigned int *bad) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const double d2 = probes[k];
+    if (!(d2 <= d2_max)) return;   // farther than any pair of a window the mode is used on (and NaN)
+    float ra, rb;
+    safe2_floors(sqrt_approx_v(cvt_rz(d2)), inv_lo, inv_hi, bias0, ra, rb);
+    const int g = __float_as_int(ra) - 0x4B400000 - (__float_as_int(bias0) - 0x4B400000);   // guessed bin
+    if (g < -glo) atomicAdd(bad, 1u);   // would leave the row below its guard bins
+    if (__float_as_int(ra) == __float_as_int(rb)) {
+        const int e = expected[k];
+        const bool counted = g >= 0 && g < nbin, should = e >= 0 && e < nbin;
+        if (counted != should || (counted && g != e)) atomicAdd(bad, 1u);
+    }
+}
+
+cudaError_t launch_validate_safe2(const double *probes, const int *expected, int n, float inv_lo, float inv_hi, float bias0,
+                                  double d2_max, int nbin, int glo, unsigned int *bad, cudaStream_t stream) {
+    if (n <= 0) return cudaSuccess;
+    validate_safe2_kernel<<<(n + 255) / 256, 256, 0, stream>>>(probes, expected, n, inv_lo, inv_hi, bias0, d2_max, nbin, glo, bad);
     return cudaGetLastError();
 }
 
@@ -1274,6 +1580,9 @@ __global__ void __launch_bounds__(kNbThreads) neighbour_kernel(const NeighbourPa
         b.xy = bx[3];
         b.xz = bx[4];
         b.yz = bx[5];
+        b.nxy = -b.xy;
+        b.nxz = -b.xz;
+        b.nyz = -b.yz;
         const double nLx = __dmul_rn(b.lhx, -2.0), nLy = __dmul_rn(b.lhy, -2.0), nLz = __dmul_rn(b.lhz, -2.0);
         double xi[kNbIPT], yi[kNbIPT], zi[kNbIPT];
         int slot[kNbIPT];

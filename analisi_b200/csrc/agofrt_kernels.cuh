@@ -66,7 +66,7 @@ struct PairParams {
     const double *thr;          // [nbin+1] thresholds folded with the rmin2/rmax2 test
     const double *thr_full;     // [nbin+1] plain thresholds (EDGES variant)
     double rmin2, rmax2;
-    double ubox[9];             // UBOX variants: lx/2, ly/2, lz/2, xy, xz, yz, -lx, -ly, -lz of the one box of the window
+    double ubox[12];            // UBOX variants: lx/2, ly/2, lz/2, xy, xz, yz, -lx, -ly, -lz, -xy, -xz, -yz of the one box of the window
     unsigned unit_begin, unit_end;
     int npad, ntypes, nbin;
     int n_itiles, n_jchunks, jchunk;  // jchunk is a multiple of kTileJ; pair_small_kernel: n_itiles = warps per job
@@ -74,14 +74,17 @@ struct PairParams {
     float inv_dr, c0;                 // bin guess = floor(sqrtf(d2) * inv_dr + c0)
     float c0h, lim, qmax;             // MODE_SAFE: c0 - 0.5, 0.5 - eps, nbin + 0.25 (clamp of the bin coordinate)
     int glo;                          // guard bins below bin 0 in every shared-memory histogram row
+    int nhi;                          // bins from bin 0 up in every shared-memory row (>= nbin; only the first nbin are merged)
+    float inv_lo, inv_hi, bias0;      // MODE_SAFE2: inv_dr * (1 -+ 2^-20), 1.5*2^23 + c0 (c0 an integer)
+    const int *type_real_end;         // [ntypes] end of the real atoms of every type group (MODE_SAFE2; may be NULL)
     unsigned hlo, hspan, hhi;         // candidate tests on the high word of d2 (hhi = hlo + hspan)
 };
 
-size_t pair_kernel_smem_bytes(int ntypes, int nbin, int glo, bool edges);
+size_t pair_kernel_smem_bytes(int ntypes, int nbin, int nhi, int glo, bool edges);
 
 // variant = TRI | FAST<<1 | MODE<<2 | UBOX<<5 | SMALL<<6, MODE: 0 thresholds, 1 thresholds + warp aggregation, 2 edges, 3 safe-zone,
 // 4 safe-zone without the group filter (dense in-range workloads: nearly every group holds an in-range pair)
-enum { kModeThr = 0, kModeAgg = 1, kModeEdges = 2, kModeSafe = 3, kModeSafeDense = 4 };  // dense: FAST only (variants 18, 19)
+enum { kModeThr = 0, kModeAgg = 1, kModeEdges = 2, kModeSafe = 3, kModeSafeDense = 4, kModeSafe2 = 5 };  // dense, safe2: FAST only; safe2: tile kernel only
 cudaError_t launch_pair_kernel(int variant, int grid, size_t smem, cudaStream_t stream, const PairParams &p);
 cudaError_t prepare_pair_kernels(size_t max_smem_optin);
 
@@ -148,6 +151,9 @@ cudaError_t launch_blockavg_push(const unsigned long long *counts, double incr, 
 // MODE_SAFE validation: bad += number of probes whose unflagged float guess differs from expected[]
 cudaError_t launch_validate_safe(const double *probes, const int *expected, int n, float inv_dr, float c0h, float lim,
                                  float qmax, int nbin, int glo, unsigned int *bad, cudaStream_t stream);
+// MODE_SAFE2 validation: the same for the two-floor guess, on the probes with d2 <= d2_max
+cudaError_t launch_validate_safe2(const double *probes, const int *expected, int n, float inv_lo, float inv_hi, float bias0,
+                                  double d2_max, int nbin, int glo, unsigned int *bad, cudaStream_t stream);
 // DFMA chains; *count_per_launch receives the number of lane-level DFMAs one launch executes
 cudaError_t launch_dfma_peak(double *sink, int blocks, int iters, cudaStream_t stream,
                              unsigned long long *count_per_launch);

@@ -153,8 +153,9 @@ enum {
     AGOFRT_OPT_NO_SMALL = 256,     /* never take the small-system kernel (one job per group of warps) */
     AGOFRT_OPT_ON_DEVICE = 512,    /* leave the counts on the device for agofrt_blockavg_push: counts_out may be NULL
                                       and is not written */
-    AGOFRT_OPT_SMALL = 1024        /* take the small-system kernel for up to 512 device slots (default: up to 256, one
+    AGOFRT_OPT_SMALL = 1024,       /* take the small-system kernel for up to 512 device slots (default: up to 256, one
                                       to four warps per job, where it beats the tile kernel; measured equal above) */
+    AGOFRT_OPT_NO_SAFE2 = 2048     /* dense windows: keep the clamped safe-zone kernel (no two-floor binning) */
 };
 
 typedef struct {
@@ -168,7 +169,7 @@ typedef struct {
     uint32_t ndev_local;
     uint32_t world;
     uint32_t kernel_modes;     /* bit m set: a pair kernel of binning mode m ran (0 thresholds, 1 aggregated, 2 edges,
-                                  3 safe-zone, 4 safe-zone dense); bit 8: the small-system kernel ran */
+                                  3 safe-zone, 4 safe-zone dense, 5 two-floor dense); bit 8: the small-system kernel ran */
 } agofrt_stats;
 
 /* counts_out [leff][ntypes*(ntypes+1)][nbin] (host, uint64): the number of ordered pairs (i,j)
