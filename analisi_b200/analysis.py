@@ -1,15 +1,21 @@
-"""Python-side helpers of the g(r,t) path, over the ``pyanalisi`` extension of this repository
-(``python/pyanalisi*.so``): the counterparts of the reference's pure-python wrappers
+"""Python-side conveniences around the ``pyanalisi`` extension of this repository (``python/pyanalisi*.so``).
 
-    Analysis.max_l / Analysis.hist2gofr / Analysis.compute_gofr   (pyanalisi/analysis.py:77-144)
-    Analysis.compute_msd                                           (pyanalisi/analysis.py:91-98)
-    analyze_gofr                                                   (pyanalisi/common.py:186-204)
+They play the role of the reference's pure-python wrappers for this path -- ``Analysis.compute_gofr`` /
+``compute_msd`` (pyanalisi/analysis.py:91-144) and ``analyze_gofr`` (pyanalisi/common.py:186-204) -- with the same
+argument meaning and the same results, written for this repository:
 
-with the same argument meaning.  Nothing here computes pairs: ``Gofrt.calculate`` runs on the GPU.
-The reference's callers pass ``(..., nthreads, tskip, False, 1)`` positionally, which lands on
-``(skip, every=False -> 1, debug=1 -> True)`` and makes every calculate() append to ./gofrt.dump
-(SURVEY.md section 8b); the helpers below pass the arguments by their real meaning (debug off).
+* a window ``[start, stop)`` of frames is split into lags and averaged origins by :func:`lag_split`;
+* the histogram that ``Gofrt`` returns is turned into g(r) by dividing every bin by the volume of its spherical
+  shell (:func:`shell_normalise`) -- the only normalisation the reference applies on the python side (no density, no
+  atom count);
+* ``n_segments > 1`` gives one result per consecutive segment of origins.
+
+Nothing here computes pairs: ``Gofrt.calculate`` runs on the GPU.  The reference's own callers pass
+``(..., nthreads, tskip, False, 1)`` positionally, which lands on ``every=False`` and ``debug=1`` and makes every
+calculate() append to ./gofrt.dump; the helpers below pass ``every=1, debug=False``.
 """
+import math
+
 import numpy as np
 
 
@@ -19,75 +25,89 @@ def _ext():
 
 
 def wrapper_name(traj, name="Gofrt"):
-    """Class for this trajectory kind: ``Gofrt`` for numpy trajectories, ``Gofrt_lammps`` for mmap ones
-    (the reference's Analysis.pyanalisi_wrapper / common.pyanalisi_wrapper)."""
+    """The extension class that goes with this trajectory object: ``<name>`` for ``pyanalisi.Trajectory`` (numpy
+    arrays), ``<name>_lammps`` for ``pyanalisi.Traj`` (LAMMPS binary through mmap)."""
     pa = _ext()
-    if isinstance(traj, pa.Trajectory):
-        return getattr(pa, name)
-    if isinstance(traj, pa.Traj):
-        return getattr(pa, name + "_lammps")
+    for cls, suffix in ((pa.Trajectory, ""), (pa.Traj, "_lammps")):
+        if isinstance(traj, cls):
+            return getattr(pa, name + suffix)
     raise RuntimeError("Wrapper for trajectory class not implemented")
 
 
-def max_l(start, stop, tmax=0):
-    """Split [start, stop) into the number of lags and the number of averaged origins (analysis.py:77-88)."""
-    if tmax <= 0:
-        tmax = (stop - start) // 2
-    n_ave = stop - start - tmax
-    if start >= stop:
+def lag_split(start, stop, tmax=0):
+    """(number of lags, number of averaged origins) for the frames ``[start, stop)``.
+
+    ``tmax <= 0`` asks for half of the window.  The origins are what is left after the lags; a window too short
+    for even one origin keeps a single origin and as many lags as then fit."""
+    span = stop - start
+    if span <= 0:
         raise RuntimeError("start index must be less than the end index")
-    if n_ave <= 0:
-        tmax = stop - start - 1
-        n_ave = 1
-    return tmax, n_ave
+    lags = tmax if tmax > 0 else span // 2
+    origins = span - lags
+    if origins < 1:
+        lags, origins = span - 1, 1
+    return lags, origins
+
+
+max_l = lag_split   # the reference's name (Analysis.max_l)
+
+
+def shell_normalise(hist, rmin, dr):
+    """Divide bin k (last axis) by the volume of the shell ``rmin + k dr <= r < rmin + (k+1) dr``."""
+    hist = np.asarray(hist, dtype=np.float64)
+    edges = rmin + dr * np.arange(hist.shape[-1] + 1)
+    return hist / (4.0 * math.pi / 3.0 * np.diff(edges ** 3))
 
 
 def hist2gofr(gr_N, gr_dr, gr_0, gofr):
-    """Histogram -> g(r): division by the shell volumes 4 pi/3 (r+^3 - r-^3), the only normalisation the
-    reference applies on the python side (analysis.py:100-105; no density or N factor)."""
-    rs_m = np.arange(gr_N) * gr_dr + gr_0
-    rs_p = (np.arange(gr_N) + 1) * gr_dr + gr_0
-    vols = 4 * np.pi / 3 * (rs_p ** 3 - rs_m ** 3)
-    return gofr / vols
+    """The reference's signature (Analysis.hist2gofr): number of bins, bin width, first edge, histogram."""
+    gofr = np.asarray(gofr)
+    if gofr.shape[-1] != gr_N:
+        raise ValueError("the histogram has %d bins, not %d" % (gofr.shape[-1], gr_N))
+    return shell_normalise(gofr, gr_0, gr_dr)
 
 
 def compute_gofr(traj, startr, endr, nbin, start=0, stop=None, tmax=1, tskip=10, n_segments=1, nthreads=1,
                  return_histogram=False):
-    """g(r) / van Hove g(r,t) of a ``pyanalisi.Trajectory`` or ``pyanalisi.Traj`` (analysis.py:108-144):
-    ``tmax`` time lags, origins every ``tskip`` frames; ``n_segments`` > 1 returns one result per segment."""
+    """g(r) -- or the van Hove function g(r,t) for ``tmax > 1`` -- of a ``pyanalisi.Trajectory`` / ``pyanalisi.Traj``:
+    ``tmax`` time lags, one origin every ``tskip`` frames, ``nbin`` bins between ``startr`` and ``endr``.
+    One array ``(lags, ntypes*(ntypes+1), nbin)``, or a list of ``n_segments`` of them."""
+    if n_segments < 1:
+        raise IndexError("n_segments must be > 0 (%r)" % (n_segments,))
     if stop is None:
         stop = traj.get_nloaded_timesteps()
-    tmax, n_ave = max_l(start, stop, tmax)
-    gofr = wrapper_name(traj)(traj, startr, endr, nbin, tmax, nthreads, tskip, 1, False)
-    conv = (lambda h: h) if return_histogram else (lambda h: hist2gofr(nbin, (endr - startr) / nbin, startr, h))
+    lags, origins = lag_split(start, stop, tmax)
+    calc = wrapper_name(traj)(traj, startr, endr, nbin, lags, nthreads, tskip, 1, False)
+    dr = (endr - startr) / nbin
+
+    def one(first):
+        calc.calculate(first)
+        h = np.array(calc, copy=True)
+        return h if return_histogram else shell_normalise(h, startr, dr)
+
     if n_segments == 1:
-        gofr.reset(n_ave)
-        gofr.calculate(start)
-        return conv(np.array(gofr, copy=True))
-    if n_segments > 1:
-        res = []
-        segment_size = max(1, n_ave // n_segments)
-        gofr.reset(segment_size)
-        for i in range(0, min(segment_size * n_segments, n_ave), segment_size):
-            gofr.calculate(start + i)
-            res.append(conv(np.array(gofr, copy=True)))
-        return res
-    raise IndexError("n_segments must be > 0 (%r)" % (n_segments,))
+        calc.reset(origins)
+        return one(start)
+    per_segment = max(1, origins // n_segments)
+    calc.reset(per_segment)
+    firsts = [start + k * per_segment for k in range(n_segments) if (k + 1) * per_segment <= origins]
+    return [one(f) for f in firsts]
 
 
 def analyze_gofr(traj, start, stop, startr, endr, nbin, tmax=1, nthreads=1, tskip=10, n_segments=1):
-    """The raw-histogram variant (common.py:186-204)."""
+    """The raw histogram instead of g(r) (the reference's common.analyze_gofr)."""
     return compute_gofr(traj, startr, endr, nbin, start=start, stop=stop, tmax=tmax, tskip=tskip, n_segments=n_segments,
                         nthreads=nthreads, return_histogram=True)
 
 
 def compute_msd(traj, start=0, stop=-1, tmax=0, tskip_msd=10, center_of_mass_MSD=True, center_of_mass_frame=False, nthreads=1):
-    """Mean square displacement per type (and of the per-type centres of mass) of an UNWRAPPED trajectory
-    (analysis.py:91-98): array (tmax, 2 if center_of_mass_MSD else 1, ntypes)."""
+    """Mean square displacement per type (and of the per-type centres of mass) of an UNWRAPPED trajectory:
+    array ``(lags, 2 if center_of_mass_MSD else 1, ntypes)``."""
     if stop < 0:
         stop = traj.get_nloaded_timesteps()
-    tmax, n_ave = max_l(start, stop, tmax)
-    msd = wrapper_name(traj, "MeanSquareDisplacement")(traj, tskip_msd, tmax, nthreads, center_of_mass_MSD, center_of_mass_frame, False)
-    msd.reset(n_ave)
-    msd.calculate(start)
-    return np.array(msd, copy=True)
+    lags, origins = lag_split(start, stop, tmax)
+    calc = wrapper_name(traj, "MeanSquareDisplacement")(traj, tskip_msd, lags, nthreads, center_of_mass_MSD,
+                                                         center_of_mass_frame, False)
+    calc.reset(origins)
+    calc.calculate(start)
+    return np.array(calc, copy=True)

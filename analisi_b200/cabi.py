@@ -15,10 +15,11 @@ LIB_PATH = os.environ.get("AGOFRT_LIB", os.path.join(_HERE, "libagofrt.so"))  # 
 OK = 0
 ERR_ARG, ERR_CUDA, ERR_WINDOW, ERR_NCCL, ERR_NONFINITE, ERR_TOO_LARGE, ERR_INTERNAL = -1, -2, -3, -4, -5, -6, -7
 OPT_EDGES, OPT_FORCE_GENERAL, OPT_NO_AGGREGATE, OPT_AGGREGATE, OPT_NO_SAFE, OPT_DENSE, OPT_SPARSE, OPT_NO_UBOX = 1, 2, 4, 8, 16, 32, 64, 128
-OPT_NO_SMALL, OPT_ON_DEVICE, OPT_SMALL, OPT_NO_SAFE2 = 256, 512, 1024, 2048
+OPT_NO_SMALL, OPT_ON_DEVICE, OPT_SMALL, OPT_SAFE2, OPT_SKEW = 256, 512, 1024, 2048, 4096
 SMALL_DEFAULT_SLOTS, SMALL_MAX_SLOTS = 256, 512   # kSmallDefault, kSmallMax of the library
 MODE_BIT_SMALL = 1 << 8   # Stats.kernel_modes: the small-system kernel ran
 COMM_ID_BYTES = 128
+UP_WRAP, UP_WRITEBACK, UP_SHARED = 1, 2, 4
 
 # every symbol include/agofrt.h declares (tests check the library exports all of them)
 SYMBOLS = [
@@ -28,7 +29,7 @@ SYMBOLS = [
     "agofrt_traj_download_frame", "agofrt_pbc_wrap", "agofrt_traj_d2_all", "agofrt_traj_d2_pair", "agofrt_plan_create",
     "agofrt_plan_destroy", "agofrt_plan_thresholds", "agofrt_block", "agofrt_neighbour_hist", "agofrt_traj_set_cm", "agofrt_msd", "agofrt_fp64_peak",
     "agofrt_blockavg_create", "agofrt_blockavg_destroy", "agofrt_blockavg_begin", "agofrt_blockavg_push", "agofrt_blockavg_end",
-    "agofrt_plan_last_counts",
+    "agofrt_plan_last_counts", "agofrt_plan_info", "agofrt_traj_upload_ex", "agofrt_traj_download",
 ]
 
 
@@ -88,6 +89,8 @@ def lib():
     L.agofrt_traj_upload.argtypes = [vp, C.c_size_t, C.c_size_t, vp, vp]
     L.agofrt_traj_upload_wrap.argtypes = [vp, C.c_size_t, C.c_size_t, vp, vp]
     L.agofrt_plan_retarget.argtypes = [vp, vp]
+    L.agofrt_traj_upload_ex.argtypes = [vp, C.c_size_t, C.c_size_t, vp, vp, C.c_uint, vp]
+    L.agofrt_traj_download.argtypes = [vp, C.c_size_t, C.c_size_t, vp]
     L.agofrt_traj_download_frame.argtypes = [vp, C.c_size_t, dp]
     L.agofrt_pbc_wrap.argtypes = [vp, vp, C.c_size_t, C.c_size_t, dp, C.c_int]
     L.agofrt_traj_d2_all.argtypes = [vp, C.c_size_t, C.c_size_t, dp]
@@ -95,6 +98,7 @@ def lib():
     L.agofrt_plan_create.argtypes = [C.POINTER(vp), vp, C.c_double, C.c_double, C.c_uint]
     L.agofrt_plan_destroy.argtypes = [vp]
     L.agofrt_plan_thresholds.argtypes = [vp, dp]
+    L.agofrt_plan_info.argtypes = [vp, ip, ip, ip]
     L.agofrt_block.argtypes = [vp, C.c_size_t, C.c_uint, C.c_uint, C.c_uint, C.c_uint, C.c_uint, u64p, u64p,
                                C.POINTER(Stats)]
     L.agofrt_neighbour_hist.argtypes = [vp, C.c_double, C.c_size_t, C.c_uint, C.c_uint, u64p, C.POINTER(Stats)]
@@ -245,6 +249,26 @@ class DeviceTrajectory:
         assert box.shape == (pos.shape[0], self.box_stride)
         _check(lib().agofrt_traj_upload_wrap(self._h, int(first_frame), pos.shape[0], pos.ctypes.data, box.ctypes.data))
 
+    def upload_ex(self, first_frame, pos, box_internal, wrap=False, shared=False, out=None):
+        """agofrt_traj_upload_ex: ``pos`` is only read (it may be pageable memory); with ``wrap`` the device wraps the
+        frames, and ``out`` (an array like pos, or pos itself) receives the wrapped frames; ``shared`` deals the frames to
+        the devices of the communicator and exchanges the shares device to device."""
+        assert pos.dtype == np.float64 and pos.flags.c_contiguous
+        assert pos.ndim == 3 and pos.shape[1] == self.natoms and pos.shape[2] == 3
+        box = np.ascontiguousarray(box_internal, dtype=np.float64)
+        assert box.shape == (pos.shape[0], self.box_stride)
+        flags = (UP_WRAP if wrap else 0) | (UP_SHARED if shared else 0) | (UP_WRITEBACK if out is not None else 0)
+        if out is not None:
+            assert wrap and out.dtype == np.float64 and out.flags.c_contiguous and out.shape == pos.shape and out.flags.writeable
+        _check(lib().agofrt_traj_upload_ex(self._h, int(first_frame), pos.shape[0], pos.ctypes.data, box.ctypes.data, flags,
+                                           out.ctypes.data if out is not None else None))
+
+    def download(self, first_frame, nframes):
+        """Frames of the device window in the caller's atom order (wrapped if uploaded with wrap)."""
+        out = np.empty((int(nframes), self.natoms, 3), dtype=np.float64)
+        _check(lib().agofrt_traj_download(self._h, int(first_frame), int(nframes), out.ctypes.data))
+        return out
+
     def download_frame(self, frame):
         out = np.empty((self.natoms, 3), dtype=np.float64)
         _check(lib().agofrt_traj_download_frame(self._h, int(frame), _dp(out)))
@@ -306,6 +330,12 @@ class Plan:
     def retarget(self, traj):
         _check(lib().agofrt_plan_retarget(self._h, traj._h))
         self.traj = traj
+
+    def info(self):
+        """{'safe_zone': bool, 'two_floor': bool, 'guard_bins': int}: which float shortcuts passed their validation."""
+        a, b, g = C.c_int(0), C.c_int(0), C.c_int(0)
+        _check(lib().agofrt_plan_info(self._h, C.byref(a), C.byref(b), C.byref(g)))
+        return {"safe_zone": bool(a.value), "two_floor": bool(b.value), "guard_bins": int(g.value)}
 
     def thresholds(self):
         out = np.empty(self.nbin + 1, dtype=np.float64)

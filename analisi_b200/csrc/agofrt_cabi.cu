@@ -11,6 +11,7 @@
 #include <nccl.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -23,6 +24,7 @@
 #include <new>
 #include <numeric>
 #include <string>
+#include <thread>
 #include <unordered_set>
 #include <vector>
 
@@ -78,6 +80,8 @@ struct NcclApi {
     ncclResult_t (*GroupEnd)() = nullptr;
     ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t,
                               cudaStream_t) = nullptr;
+    ncclResult_t (*Broadcast)(const void *, void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*CommSplit)(ncclComm_t, int, int, ncclComm_t *, void *) = nullptr;   // NCCL >= 2.18
     const char *(*GetErrorString)(ncclResult_t) = nullptr;
     bool ok = false;
 };
@@ -106,7 +110,9 @@ static NcclApi &nccl_api() {
     LOAD(GroupEnd, "ncclGroupEnd")
     LOAD(AllReduce, "ncclAllReduce")
     LOAD(GetErrorString, "ncclGetErrorString")
+    LOAD(Broadcast, "ncclBroadcast")
 #undef LOAD
+    api.CommSplit = reinterpret_cast<decltype(api.CommSplit)>(dlsym(api.handle, "ncclCommSplit"));   // optional
     api.ok = true;
     return api;
 }
@@ -129,7 +135,16 @@ struct Dev {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr, ev_k0 = nullptr, ev_k1 = nullptr;
     ncclComm_t comm = nullptr;
+    ncclComm_t comm_up = nullptr;   // window exchange (agofrt_traj_upload_ex, AGOFRT_UP_SHARED): a communicator of its
+                                    // own, because a window may be uploaded by a second host thread while the first
+                                    // is inside agofrt_block (whose all-reduce runs on `comm`)
     double *peak_sink = nullptr;
+    // page-locked staging for uploads from pageable host memory (two slots, filled by several host threads while the
+    // previous slot is on its way to the device)
+    double *hstage[2] = {nullptr, nullptr};
+    size_t hstage_bytes = 0;
+    cudaEvent_t hstage_free[2] = {nullptr, nullptr};
+    std::mutex *hstage_mutex = nullptr;
 };
 
 struct agofrt_ctx {
@@ -149,7 +164,6 @@ struct TrajDev {
     int *perm = nullptr;         // [npad]
     int *type_pad = nullptr;     // [npad]
     int *type_start = nullptr;   // [ntypes+1]
-    int *type_real_end = nullptr; // [ntypes] end of the real atoms of every type group
     unsigned int *flags = nullptr;  // [4]: 0 = inf seen, 1 = wrap cap hit
     double *probe = nullptr;        // [4]: result of agofrt_traj_d2_pair
     unsigned long long *nb_hist = nullptr;  // neighbour-count histogram [ntypes][natoms+1] (agofrt_neighbour_hist)
@@ -210,7 +224,7 @@ struct agofrt_plan {
     bool safe_ok = false;        // validated on the device when the plan was made
     double q_reach = 0;          // largest bin coordinate the float path may meet before it must give up
     bool safe2_ok = false;       // the two-floor form (MODE_SAFE2) is valid for this plan: integer c0, validated on the device
-    float inv_lo = 0, inv_hi = 0, bias0 = 0;
+    float inv_lo = 0, inv_hi = 0, bias0 = 0, smax = 0;
     std::vector<PlanDev> dev;
     unsigned long long *host_counts = nullptr;  // pinned
     size_t host_counts_len = 0;
@@ -322,6 +336,9 @@ extern "C" int agofrt_ctx_create(agofrt_ctx **out, const int *devices, int ndev)
         CU(cudaEventCreate(&d.ev_k0));
         CU(cudaEventCreate(&d.ev_k1));
         CU(prepare_pair_kernels(d.smem_optin));
+        CU(cudaEventCreateWithFlags(&d.hstage_free[0], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&d.hstage_free[1], cudaEventDisableTiming));
+        d.hstage_mutex = new std::mutex();
         ctx->devs.push_back(d);
     }
     *out = ctx.release();
@@ -334,8 +351,14 @@ extern "C" int agofrt_ctx_destroy(agofrt_ctx *ctx) try {
     if (!ctx) return AGOFRT_OK;
     for (Dev &d : ctx->devs) {
         cudaSetDevice(d.id);
+        if (d.comm_up && nccl_api().ok) nccl_api().CommDestroy(d.comm_up);
         if (d.comm && nccl_api().ok) nccl_api().CommDestroy(d.comm);
         if (d.peak_sink) cudaFree(d.peak_sink);
+        for (int k = 0; k < 2; ++k) {
+            if (d.hstage[k]) cudaFreeHost(d.hstage[k]);
+            if (d.hstage_free[k]) cudaEventDestroy(d.hstage_free[k]);
+        }
+        delete d.hstage_mutex;
         if (d.stream) cudaStreamDestroy(d.stream);
         if (d.ev_begin) cudaEventDestroy(d.ev_begin);
         if (d.ev_end) cudaEventDestroy(d.ev_end);
@@ -393,6 +416,22 @@ static int comm_init(agofrt_ctx *ctx, const ncclUniqueId &u, int first_rank, int
     restore();
     if (nr == ncclSuccess) nr = ne;
     if (nr != ncclSuccess) return fail(AGOFRT_ERR_NCCL, "NCCL communicator creation failed: %s", api.GetErrorString(nr));
+    // ... and a second one over the same ranks for the window exchange (optional: without ncclCommSplit the shared
+    // upload falls back to one full host-to-device copy per device)
+    if (api.CommSplit) {
+        ncclResult_t sr = api.GroupStart();
+        for (int i = 0; i < nloc && sr == ncclSuccess; ++i) {
+            if (cudaSetDevice(ctx->devs[i].id) != cudaSuccess) {
+                sr = ncclUnhandledCudaError;
+                break;
+            }
+            sr = api.CommSplit(ctx->devs[i].comm, 0, first_rank + i, &ctx->devs[i].comm_up, nullptr);
+        }
+        const ncclResult_t se = api.GroupEnd();
+        if (sr == ncclSuccess) sr = se;
+        if (sr != ncclSuccess)
+            for (int i = 0; i < nloc; ++i) ctx->devs[i].comm_up = nullptr;
+    }
     ctx->first_rank = first_rank;
     ctx->world = world;
     ctx->comm_ready = true;
@@ -459,7 +498,6 @@ static void free_traj_dev(agofrt_traj *t) {
         cudaFree(d.perm);
         cudaFree(d.type_pad);
         cudaFree(d.type_start);
-        cudaFree(d.type_real_end);
         cudaFree(d.flags);
         cudaFree(d.probe);
         cudaFree(d.nb_hist);
@@ -498,8 +536,7 @@ extern "C" int agofrt_traj_create(agofrt_traj **out, agofrt_ctx *ctx, size_t nat
     }
     t->type_start[ntypes] = static_cast<int>(off);
     t->npad = static_cast<int>(off);
-    std::vector<int> real_end(ntypes);
-    for (int k = 0; k < ntypes; ++k) real_end[k] = t->type_start[k] + static_cast<int>(cnt[k]);
+
     t->type_pad.assign(t->npad, 0);
     for (int k = 0; k < ntypes; ++k)
         for (int s = t->type_start[k]; s < t->type_start[k + 1]; ++s) t->type_pad[s] = k;
@@ -527,14 +564,12 @@ extern "C" int agofrt_traj_create(agofrt_traj **out, agofrt_ctx *ctx, size_t nat
         CU(cudaMalloc(&d.perm, npad1 * sizeof(int)));
         CU(cudaMalloc(&d.type_pad, npad1 * sizeof(int)));
         CU(cudaMalloc(&d.type_start, (ntypes + 1) * sizeof(int)));
-        CU(cudaMalloc(&d.type_real_end, ntypes * sizeof(int)));
         CU(cudaMalloc(&d.flags, 4 * sizeof(unsigned int)));
         CU(cudaMalloc(&d.probe, 4 * sizeof(double)));
         CU(cudaStreamCreateWithFlags(&d.up, cudaStreamNonBlocking));
         CU(cudaMemset(d.flags, 0, 4 * sizeof(unsigned int)));
         if (t->npad > 0) CU(cudaMemcpy(d.type_pad, t->type_pad.data(), t->npad * sizeof(int), cudaMemcpyHostToDevice));
         CU(cudaMemcpy(d.type_start, t->type_start.data(), (ntypes + 1) * sizeof(int), cudaMemcpyHostToDevice));
-        CU(cudaMemcpy(d.type_real_end, real_end.data(), ntypes * sizeof(int), cudaMemcpyHostToDevice));
     }
     *out = t.release();
     return AGOFRT_OK;
@@ -602,13 +637,54 @@ static void build_perm(agofrt_traj *t, const double *pos0, const double *box_row
     }
 }
 
-// pos_in: the frames to upload; wrap: apply BaseTrajectory::pbc_wrap on the device before the SoA gather (every
-// device wraps its own copy -- same arithmetic, same bits) and hand the wrapped frames back in pos_back.
+// Copy `bytes` from pageable host memory into a page-locked slot with several host threads (one thread moves
+// about 10 GB/s; a PCIe 5 x16 link takes 50).
+static void parallel_copy(void *dst, const void *src, size_t bytes) {
+    const size_t min_per_thread = 4u << 20;
+    size_t nth = std::min<size_t>({8, std::max(1u, std::thread::hardware_concurrency()), bytes / min_per_thread});
+    if (nth <= 1) {
+        memcpy(dst, src, bytes);
+        return;
+    }
+    std::vector<std::thread> pool;
+    const size_t each = (bytes / nth + 4095) & ~static_cast<size_t>(4095);
+    for (size_t k = 0; k < nth; ++k) {
+        const size_t o = k * each;
+        if (o >= bytes) break;
+        const size_t n = std::min(each, bytes - o);
+        pool.emplace_back([=]() { memcpy(static_cast<char *>(dst) + o, static_cast<const char *>(src) + o, n); });
+    }
+    for (std::thread &th : pool) th.join();
+}
+
+static bool is_pinned(const void *p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
+}
+
+// The window upload.  flags: AGOFRT_UP_WRAP applies BaseTrajectory::pbc_wrap on the device before the layout change,
+// AGOFRT_UP_WRITEBACK hands the wrapped frames back in pos_back, AGOFRT_UP_SHARED deals the frames to the devices of
+// the communicator -- every device copies, wraps and lays out only its share, then the shares travel device to device
+// (grouped ncclBroadcast = an all-gather with unequal counts, over NVLink) -- so the window crosses PCIe ONCE per box
+// instead of once per GPU.  Pageable source memory goes through two page-locked slots filled by several host threads.
 static int upload_impl(agofrt_traj *t, size_t first_frame, size_t nframes, const double *pos_in, const double *box_internal,
-                       bool wrap, double *pos_back) {
+                       unsigned flags, double *pos_back) {
     if (!t) return fail(AGOFRT_ERR_ARG, "traj is NULL");
     if (nframes > t->max_frames) return fail(AGOFRT_ERR_ARG, "window of %zu frames > max_frames %zu", nframes, t->max_frames);
     if (nframes > 0 && (!box_internal || (t->natoms > 0 && !pos_in))) return fail(AGOFRT_ERR_ARG, "NULL buffer");
+    const bool wrap = (flags & AGOFRT_UP_WRAP) != 0;
+    if (!(wrap && (flags & AGOFRT_UP_WRITEBACK))) pos_back = nullptr;
+    agofrt_ctx *ctx = t->ctx;
+    const bool debug = getenv("AGOFRT_DEBUG") != nullptr;
+    const auto t_begin = std::chrono::steady_clock::now();
+    auto since = [&](std::chrono::steady_clock::time_point a) {
+        return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - a).count();
+    };
+    double ms_perm = 0, ms_copy = 0;
     t->first_frame = first_frame;
     t->nframes = nframes;
     t->box6.assign(nframes * 6, 0.0);
@@ -643,15 +719,36 @@ static int upload_impl(agofrt_traj *t, size_t first_frame, size_t nframes, const
     const size_t moved = first_frame > t->perm_frame ? first_frame - t->perm_frame : t->perm_frame - first_frame;
     const bool new_perm = t->natoms > 0 && (!t->perm_valid || moved >= kPermRefresh);
     if (new_perm) {
-        build_perm(t, pos_in, box_internal);
+        const auto t0 = std::chrono::steady_clock::now();
+        build_perm(t, pos_in, box_internal);   // (shared uploads: frame 0 of the window must be valid on every rank)
+        ms_perm = since(t0);
         t->perm_valid = true;
         t->perm_frame = first_frame;
         t->slot_of_stale = true;
     }
 
-    const size_t frame_elems = t->natoms * 3;
-    for (size_t i = 0; i < t->dev.size(); ++i) {
-        Dev &dv = t->ctx->devs[i];
+    // ---- who takes which frames ----
+    const int nloc = static_cast<int>(t->dev.size());
+    if (flags & AGOFRT_UP_SHARED) {
+        const int rc = ensure_local_comm(ctx);
+        if (rc != AGOFRT_OK) return rc;
+    }
+    const int world = ctx->world > 0 ? ctx->world : nloc;
+    const int first_rank = ctx->world > 0 ? ctx->first_rank : 0;
+    bool shared = (flags & AGOFRT_UP_SHARED) && ctx->comm_ready && world > 1 && t->npad > 0;
+    for (int i = 0; i < nloc && shared; ++i) shared = ctx->devs[i].comm_up != nullptr;
+    std::vector<size_t> fb(nloc, 0), fe(nloc, nframes);
+    if (shared)
+        for (int i = 0; i < nloc; ++i) {
+            uint64_t b0 = 0, e0 = 0;
+            agofrt_shard_range(nframes, first_rank + i, world, &b0, &e0);
+            fb[i] = b0;
+            fe[i] = e0;
+        }
+
+    const size_t frame_elems = t->natoms * 3, frame_bytes = frame_elems * sizeof(double);
+    for (int i = 0; i < nloc; ++i) {
+        Dev &dv = ctx->devs[i];
         TrajDev &d = t->dev[i];
         CU(cudaSetDevice(dv.id));
         CU(cudaMemsetAsync(d.flags, 0, 4 * sizeof(unsigned int), d.up));
@@ -661,58 +758,163 @@ static int upload_impl(agofrt_traj *t, size_t first_frame, size_t nframes, const
         CU(launch_pack_box(d.box_stage, t->stride, static_cast<int>(nframes), d.box6, d.up));
     }
     if (t->npad > 0) {
-        for (size_t f0 = 0; f0 < nframes; f0 += t->stage_frames) {
-            const size_t nf = std::min(t->stage_frames, nframes - f0);
-            for (size_t i = 0; i < t->dev.size(); ++i) {
-                Dev &dv = t->ctx->devs[i];
+        const bool pinned_src = is_pinned(pos_in);
+        // frames per step: what the device staging holds; from pageable memory also what a 64 MiB host slot holds
+        size_t step = t->stage_frames;
+        if (!pinned_src) step = std::max<size_t>(1, std::min<size_t>(step, (64u << 20) / std::max<size_t>(frame_bytes, 1)));
+        size_t longest = 0;
+        for (int i = 0; i < nloc; ++i) longest = std::max(longest, fe[i] - fb[i]);
+        std::vector<std::unique_lock<std::mutex>> locks;
+        if (!pinned_src)
+            for (int i = 0; i < nloc; ++i) {
+                Dev &dv = ctx->devs[i];
+                locks.emplace_back(*dv.hstage_mutex);
+                if (dv.hstage_bytes < step * frame_bytes) {
+                    CU(cudaSetDevice(dv.id));
+                    for (int k = 0; k < 2; ++k) {
+                        if (dv.hstage[k]) cudaFreeHost(dv.hstage[k]);
+                        dv.hstage[k] = nullptr;
+                    }
+                    dv.hstage_bytes = 0;
+                    for (int k = 0; k < 2; ++k)
+                        CU(cudaHostAlloc(reinterpret_cast<void **>(&dv.hstage[k]), step * frame_bytes, cudaHostAllocPortable));
+                    dv.hstage_bytes = step * frame_bytes;
+                }
+            }
+        size_t slot = 0;
+        for (size_t o = 0; o < longest; o += step, ++slot) {
+            for (int i = 0; i < nloc; ++i) {
+                if (fb[i] + o >= fe[i]) continue;
+                const size_t f0 = fb[i] + o, nf = std::min(step, fe[i] - f0);
+                Dev &dv = ctx->devs[i];
                 TrajDev &d = t->dev[i];
                 CU(cudaSetDevice(dv.id));
-                CU(cudaMemcpyAsync(d.stage, pos_in + f0 * frame_elems, nf * frame_elems * sizeof(double),
-                                   cudaMemcpyHostToDevice, d.up));
+                const double *src = pos_in + f0 * frame_elems;
+                if (!pinned_src) {
+                    double *hs = dv.hstage[slot & 1];
+                    CU(cudaEventSynchronize(dv.hstage_free[slot & 1]));   // the copy that last read this slot is done
+                    const auto t0 = std::chrono::steady_clock::now();
+                    parallel_copy(hs, src, nf * frame_bytes);
+                    ms_copy += since(t0);
+                    src = hs;
+                }
+                CU(cudaMemcpyAsync(d.stage, src, nf * frame_bytes, cudaMemcpyHostToDevice, d.up));
+                if (!pinned_src) CU(cudaEventRecord(dv.hstage_free[slot & 1], d.up));
                 if (wrap) {
-                    CU(launch_pbc_wrap(d.stage, static_cast<int>(t->natoms), static_cast<int>(nf),
-                                       d.box_stage + f0 * t->stride, t->stride, d.flags + 3, d.up));
-                    if (i == 0 && pos_back)
-                        CU(cudaMemcpyAsync(pos_back + f0 * frame_elems, d.stage, nf * frame_elems * sizeof(double),
-                                           cudaMemcpyDeviceToHost, d.up));
+                    CU(launch_pbc_wrap(d.stage, static_cast<int>(t->natoms), static_cast<int>(nf), d.box_stage + f0 * t->stride,
+                                       t->stride, d.flags + 3, d.up));
+                    if (pos_back && (shared || i == 0))
+                        CU(cudaMemcpyAsync(pos_back + f0 * frame_elems, d.stage, nf * frame_bytes, cudaMemcpyDeviceToHost, d.up));
                 }
                 CU(launch_gather_soa(d.stage, d.perm, static_cast<int>(t->natoms), t->npad, static_cast<int>(nf),
                                      d.pos + f0 * 3 * static_cast<size_t>(t->npad), d.up));
             }
         }
-        // coordinate bounds per frame (device 0 is enough: every device holds the same window)
-        Dev &dv = t->ctx->devs[0];
+        // coordinate bounds per frame: every device for its share, or device 0 for the replicated window
+        for (int i = 0; i < nloc; ++i) {
+            if (!shared && i > 0) break;
+            if (fe[i] <= fb[i]) continue;
+            Dev &dv = ctx->devs[i];
+            TrajDev &d = t->dev[i];
+            CU(cudaSetDevice(dv.id));
+            CU(launch_frame_bounds(d.pos + fb[i] * 3 * static_cast<size_t>(t->npad), d.perm, t->npad, static_cast<int>(fe[i] - fb[i]),
+                                   d.bounds + fb[i] * 6, d.flags, d.up));
+        }
+        if (shared) {
+            // the shares change hands: rank r's frames and their bounds go to everybody, flags are combined
+            NcclApi &api = nccl_api();
+            NC(api.GroupStart());
+            for (int r = 0; r < world; ++r) {
+                uint64_t b0 = 0, e0 = 0;
+                agofrt_shard_range(nframes, r, world, &b0, &e0);
+                if (e0 <= b0) continue;
+                for (int i = 0; i < nloc; ++i) {
+                    Dev &dv = ctx->devs[i];
+                    TrajDev &d = t->dev[i];
+                    double *ppos = d.pos + b0 * 3 * static_cast<size_t>(t->npad);
+                    NC(api.Broadcast(ppos, ppos, (e0 - b0) * 3 * static_cast<size_t>(t->npad), ncclDouble, r, dv.comm_up, d.up));
+                    NC(api.Broadcast(d.bounds + b0 * 6, d.bounds + b0 * 6, (e0 - b0) * 6, ncclDouble, r, dv.comm_up, d.up));
+                }
+            }
+            for (int i = 0; i < nloc; ++i)
+                NC(api.AllReduce(t->dev[i].flags, t->dev[i].flags, 4, ncclUint32, ncclMax, ctx->devs[i].comm_up, t->dev[i].up));
+            NC(api.GroupEnd());
+        }
+        Dev &dv = ctx->devs[0];
         TrajDev &d = t->dev[0];
         CU(cudaSetDevice(dv.id));
-        CU(launch_frame_bounds(d.pos, d.perm, t->npad, static_cast<int>(nframes), d.bounds, d.flags, d.up));
-        unsigned int flags[4] = {0, 0, 0, 0};
+        unsigned int hflags[4] = {0, 0, 0, 0};
         CU(cudaMemcpyAsync(t->bounds.data(), d.bounds, nframes * 6 * sizeof(double), cudaMemcpyDeviceToHost, d.up));
-        CU(cudaMemcpyAsync(flags, d.flags, sizeof(flags), cudaMemcpyDeviceToHost, d.up));
+        CU(cudaMemcpyAsync(hflags, d.flags, sizeof(hflags), cudaMemcpyDeviceToHost, d.up));
         CU(cudaStreamSynchronize(d.up));
-        t->has_inf = flags[0] != 0;
-        t->has_nan = flags[2] != 0;
-        if (flags[3]) {
+        t->has_inf = hflags[0] != 0;
+        t->has_nan = hflags[2] != 0;
+        if (hflags[3]) {
+            for (int i = 0; i < nloc; ++i) {
+                cudaSetDevice(ctx->devs[i].id);
+                cudaStreamSynchronize(t->dev[i].up);
+            }
             t->nframes = 0;
             return fail(AGOFRT_ERR_NONFINITE, "minimum image did not converge while wrapping (non-finite or absurdly far coordinate)");
         }
     }
-    for (size_t i = 0; i < t->dev.size(); ++i) {
-        CU(cudaSetDevice(t->ctx->devs[i].id));
+    for (int i = 0; i < nloc; ++i) {
+        CU(cudaSetDevice(ctx->devs[i].id));
         CU(cudaStreamSynchronize(t->dev[i].up));
     }
+    if (debug)
+        fprintf(stderr, "[agofrt] upload of %zu frames x %zu atoms (%s%s%s): %.1f ms (permutation %.1f, host staging copies %.1f)\n", nframes,
+                t->natoms, wrap ? "wrap " : "", shared ? "shared " : "replicated ", is_pinned(pos_in) ? "pinned" : "pageable",
+                since(t_begin), ms_perm, ms_copy);
     return AGOFRT_OK;
 }
 
 extern "C" int agofrt_traj_upload(agofrt_traj *t, size_t first_frame, size_t nframes, const double *pos_aos,
                                   const double *box_internal) try {
-    return upload_impl(t, first_frame, nframes, pos_aos, box_internal, false, nullptr);
+    return upload_impl(t, first_frame, nframes, pos_aos, box_internal, 0, nullptr);
 } catch (...) {
     return on_exception();
 }
 
 extern "C" int agofrt_traj_upload_wrap(agofrt_traj *t, size_t first_frame, size_t nframes, double *pos_aos_inout,
                                        const double *box_internal) try {
-    return upload_impl(t, first_frame, nframes, pos_aos_inout, box_internal, true, pos_aos_inout);
+    return upload_impl(t, first_frame, nframes, pos_aos_inout, box_internal, AGOFRT_UP_WRAP | AGOFRT_UP_WRITEBACK, pos_aos_inout);
+} catch (...) {
+    return on_exception();
+}
+
+extern "C" int agofrt_traj_upload_ex(agofrt_traj *t, size_t first_frame, size_t nframes, const double *pos_aos,
+                                     const double *box_internal, unsigned flags, double *pos_wrapped_out) try {
+    if ((flags & AGOFRT_UP_WRITEBACK) && !(flags & AGOFRT_UP_WRAP))
+        return fail(AGOFRT_ERR_ARG, "AGOFRT_UP_WRITEBACK needs AGOFRT_UP_WRAP");
+    if ((flags & AGOFRT_UP_WRITEBACK) && !pos_wrapped_out && nframes > 0 && t && t->natoms > 0)
+        return fail(AGOFRT_ERR_ARG, "AGOFRT_UP_WRITEBACK needs pos_wrapped_out");
+    return upload_impl(t, first_frame, nframes, pos_aos, box_internal, flags, pos_wrapped_out);
+} catch (...) {
+    return on_exception();
+}
+
+// Frames [first_frame, first_frame + nframes) of the device window back in the caller's atom order: what the host
+// would hold after Trajectory::set_access_at / the Trajectory_numpy constructor (wrapped when the window was uploaded
+// with AGOFRT_UP_WRAP).  The host classes call it the first time somebody asks for host positions.
+extern "C" int agofrt_traj_download(agofrt_traj *t, size_t first_frame, size_t nframes, double *pos_aos) try {
+    if (!t || (!pos_aos && nframes > 0)) return fail(AGOFRT_ERR_ARG, "NULL argument");
+    if (nframes == 0 || t->natoms == 0) return AGOFRT_OK;
+    if (first_frame < t->first_frame || first_frame + nframes > t->first_frame + t->nframes)
+        return fail(AGOFRT_ERR_WINDOW, "frames [%zu,%zu) are not in the uploaded window", first_frame, first_frame + nframes);
+    Dev &dv = t->ctx->devs[0];
+    TrajDev &d = t->dev[0];
+    CU(cudaSetDevice(dv.id));
+    const size_t frame_elems = t->natoms * 3;
+    for (size_t f0 = 0; f0 < nframes; f0 += t->stage_frames) {
+        const size_t nf = std::min(t->stage_frames, nframes - f0);
+        const size_t rel = first_frame - t->first_frame + f0;
+        CU(launch_scatter_aos(d.pos + rel * 3 * static_cast<size_t>(t->npad), d.perm, static_cast<int>(t->natoms), t->npad,
+                              static_cast<int>(nf), d.stage, d.up));
+        CU(cudaMemcpyAsync(pos_aos + f0 * frame_elems, d.stage, nf * frame_elems * sizeof(double), cudaMemcpyDeviceToHost, d.up));
+    }
+    CU(cudaStreamSynchronize(d.up));
+    return AGOFRT_OK;
 } catch (...) {
     return on_exception();
 }
@@ -726,7 +928,7 @@ extern "C" int agofrt_traj_download_frame(agofrt_traj *t, size_t frame, double *
     TrajDev &d = t->dev[0];
     CU(cudaSetDevice(dv.id));
     const size_t rel = frame - t->first_frame;
-    CU(launch_scatter_aos(d.pos + rel * 3 * static_cast<size_t>(t->npad), d.perm, static_cast<int>(t->natoms), t->npad,
+    CU(launch_scatter_aos(d.pos + rel * 3 * static_cast<size_t>(t->npad), d.perm, static_cast<int>(t->natoms), t->npad, 1,
                           d.stage, dv.stream));
     CU(cudaMemcpyAsync(pos_aos, d.stage, t->natoms * 3 * sizeof(double), cudaMemcpyDeviceToHost, dv.stream));
     CU(cudaStreamSynchronize(dv.stream));
@@ -978,14 +1180,12 @@ static int validate_safe_zone(agofrt_plan *p) {
         p->safe2_ok = false;
         p->glo = 0;
     }
-    // the two-floor form of the guess (MODE_SAFE2), on every probe the mode can meet: d2 up to the square of the
-    // distance whose bin coordinate is q_reach
+    // the two-floor form of the guess (MODE_SAFE2), on the same probes
     if (rc == AGOFRT_OK && p->safe_ok && p->safe2_ok) {
         unsigned int bad2 = 0;
-        const double rtop = p->q_reach * p->dr + std::fabs(p->rmin);
         auto body2 = [&]() -> int {
             CU(cudaMemsetAsync(dbad, 0, sizeof(unsigned int), dv.stream));
-            CU(launch_validate_safe2(dprobe, dexp, static_cast<int>(probes.size()), p->inv_lo, p->inv_hi, p->bias0, rtop * rtop,
+            CU(launch_validate_safe2(dprobe, dexp, static_cast<int>(probes.size()), p->inv_lo, p->inv_hi, p->bias0, p->smax,
                                      static_cast<int>(nbin), p->glo, dbad, dv.stream));
             CU(cudaMemcpyAsync(&bad2, dbad, sizeof(bad2), cudaMemcpyDeviceToHost, dv.stream));
             CU(cudaStreamSynchronize(dv.stream));
@@ -993,6 +1193,7 @@ static int validate_safe_zone(agofrt_plan *p) {
         };
         rc = body2();
         if (bad2 != 0) p->safe2_ok = false;
+        if (getenv("AGOFRT_DEBUG")) fprintf(stderr, "[agofrt] plan rmin %g dr %g nbin %u: two-floor validation, %u bad probes of %zu\n", p->rmin, p->dr, nbin, bad2, probes.size());
     }
     cudaFree(dprobe);
     cudaFree(dexp);
@@ -1072,7 +1273,9 @@ extern "C" int agofrt_plan_create(agofrt_plan **out, agofrt_traj *traj, double r
                     p->inv_lo = static_cast<float>(inv * (1.0 - delta));
                     p->inv_hi = static_cast<float>(inv * (1.0 + delta));
                     p->bias0 = 12582912.0f + p->c0;
-                    p->safe2_ok = p->inv_lo < p->inv_hi && std::isfinite(p->inv_hi);
+                    // clamp of sqrt(d2): the middle of the guard bin that ends every row (bin coordinate nbin + 0.5)
+                    p->smax = static_cast<float>((static_cast<double>(nbin) + 0.5) * p->dr + rmin);
+                    p->safe2_ok = p->inv_lo < p->inv_hi && std::isfinite(p->inv_hi) && std::isfinite(p->smax);
                 }
             }
         }
@@ -1144,6 +1347,16 @@ extern "C" int agofrt_plan_destroy(agofrt_plan *p) try {
     if (p->host_edges) cudaFreeHost(p->host_edges);
     if (p->host_flags) cudaFreeHost(p->host_flags);
     delete p;
+    return AGOFRT_OK;
+} catch (...) {
+    return on_exception();
+}
+
+extern "C" int agofrt_plan_info(const agofrt_plan *p, int *safe_zone_ok, int *two_floor_ok, int *guard_bins) try {
+    if (!p) return fail(AGOFRT_ERR_ARG, "NULL argument");
+    if (safe_zone_ok) *safe_zone_ok = p->safe_ok ? 1 : 0;
+    if (two_floor_ok) *two_floor_ok = p->safe2_ok ? 1 : 0;
+    if (guard_bins) *guard_bins = p->glo;
     return AGOFRT_OK;
 } catch (...) {
     return on_exception();
@@ -1357,40 +1570,12 @@ extern "C" int agofrt_block(agofrt_plan *p, size_t primo, unsigned ntimesteps, u
         if (options & AGOFRT_OPT_DENSE) dense = true;
         if (options & AGOFRT_OPT_SPARSE) dense = false;
     }
-    size_t smem = pair_kernel_smem_bytes(nt, static_cast<int>(p->nbin), static_cast<int>(p->nbin), p->glo, want_edges);
-    // MODE_SAFE2 (dense windows): histogram rows long enough for EVERY distance the single-pass minimum image can
-    // produce on this window -- from the same coordinate bounds that prove the single pass -- so that the fast path
-    // needs no clamp.  |d_c| <= W_c = max(l_half_c, D_c - 2*l_half_c) after the wrap of component c, where D_c bounds
-    // the difference before it (coordinate spread, plus the tilt corrections of the components above).
-    int nhi = static_cast<int>(p->nbin);
-    bool use_safe2 = false;
-    if (use_safe && dense && p->safe2_ok && all_fast && !aggregate && !want_edges && !small && same_box && !nothing &&
-        !(options & AGOFRT_OPT_NO_SAFE2)) {
-        const size_t f0 = primo - t->first_frame;
-        const size_t f1 = f0 + static_cast<size_t>((ntimesteps - 1) / skip) * skip + static_cast<size_t>((leff - 1) / every) * every;
-        double lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
-        for (size_t f = f0; f <= f1; ++f)
-            for (int c = 0; c < 3; ++c) {
-                lo[c] = std::min(lo[c], t->bounds[f * 6 + c]);
-                hi[c] = std::max(hi[c], t->bounds[f * 6 + 3 + c]);
-            }
-        const double *b = &t->box6[0];
-        const double Dz = hi[2] - lo[2], Dy = hi[1] - lo[1] + std::fabs(b[5]), Dx = hi[0] - lo[0] + std::fabs(b[3]) + std::fabs(b[4]);
-        const double Wz = std::max(b[2], Dz - 2 * b[2]), Wy = std::max(b[1], Dy - 2 * b[1]), Wx = std::max(b[0], Dx - 2 * b[0]);
-        const double reach = std::sqrt(Wx * Wx + Wy * Wy + Wz * Wz) * (1.0 + 1e-9);
-        const double qtop = (reach - p->rmin) / p->dr * (1.0 + 4e-6) + 2.0;
-        if (std::isfinite(qtop) && qtop < p->q_reach && qtop < 60000.0) {
-            const int want = std::max(static_cast<int>(p->nbin), static_cast<int>(std::ceil(qtop)) + 1);
-            const size_t need = pair_kernel_smem_bytes(nt, static_cast<int>(p->nbin), want, p->glo, false);
-            size_t cap = SIZE_MAX;
-            for (const Dev &d : ctx->devs) cap = std::min(cap, d.smem_optin);
-            if (need <= std::min<size_t>(cap, 100 * 1024)) {   // two CTAs per SM must still fit
-                use_safe2 = true;
-                nhi = want;
-                smem = need;
-            }
-        }
-    }
+    const size_t smem = pair_kernel_smem_bytes(nt, static_cast<int>(p->nbin), static_cast<int>(p->nbin), p->glo, want_edges);
+    // dense windows: the two-floor form of the safe-zone binning (MODE_SAFE2) where the plan allows it
+    const int nhi = static_cast<int>(p->nbin);
+    // (opt-in: measured on C2 it is 6 % slower than the clamped form although it issues two instructions per pair
+    // fewer -- DESIGN.md section 4, profiles/r2f_variants.txt)
+    const bool use_safe2 = use_safe && dense && p->safe2_ok && !aggregate && !want_edges && !small && (options & AGOFRT_OPT_SAFE2);
 
     // ---- pinned read-back buffer ----
     if (len > p->host_counts_len) {
@@ -1495,7 +1680,8 @@ extern "C" int agofrt_block(agofrt_plan *p, size_t primo, unsigned ntimesteps, u
                 pp.inv_lo = p->inv_lo;
                 pp.inv_hi = p->inv_hi;
                 pp.bias0 = p->bias0;
-                pp.type_real_end = td.type_real_end;
+                pp.smax = p->smax;
+                pp.skew = (options & AGOFRT_OPT_SKEW) ? 1 : 0;
                 int mode = kModeThr;
                 if (want_edges)
                     mode = kModeEdges;

@@ -230,9 +230,9 @@ __device__ __forceinline__ double d2_of(double dx, double dy, double dz) {
 //            is made); the few pairs closer than eps to an edge go through the exact bracket search
 //   MODE_SAFE2 the dense path, second form (see group_dense2): the bin index AND its row come out of ONE
 //            round-down FFMA as the word index of the shared histogram, a second FFMA with a slightly larger
-//            slope says whether the guess sits within eps of an edge, and the binning of pair t-2 is interleaved
-//            with the distance of pair t.  Needs an integer c0 (rmin a multiple of dr, e.g. 0), histogram rows
-//            long enough for every distance the window can produce (no clamp) and no NaN in the fast groups.
+//            slope says whether the guess sits within eps of an edge, and one unsigned compare of that word
+//            against the end of the row predicates the shared atomic (far pairs, NaN ghosts and +inf never touch
+//            memory).  Needs an integer c0 (rmin a multiple of dr, e.g. 0).
 enum { MODE_THR = 0, MODE_AGG = 1, MODE_EDGES = 2, MODE_SAFE = 3, MODE_SAFE_DENSE = 4, MODE_SAFE2 = 5 };
 
 // float guess of the bin from the bits of d2 (no FP64 conversion instruction): rebias the
@@ -409,14 +409,12 @@ __device__ __noinline__ void bin_pair_fix(double d2, const double2 *__restrict__
 // the pair kernel
 // ---------------------------------------------------------------------------------------------
 struct SmemLayout {
-    size_t thr2, thr_full, stage, hist, dump, rowtab, tstart, treal, bars, sched, total;
+    size_t thr2, thr_full, stage, hist, dump, rowtab, tstart, bars, sched, total;
 };
 
 __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-// every histogram row: glo guard bins, nhi bins (the first nbin of them are merged; nhi > nbin when the row must
-// hold every distance the window can produce, MODE_SAFE2), one guard bin.  After the 2P rows of the type pairs comes
-// one more row that is never merged: ghost i slots of MODE_SAFE2 count there.
+// every histogram row: glo guard bins, nhi bins (the first nbin of them are merged; nhi = nbin today), one guard bin
 __host__ __device__ inline int row_stride(int nhi, int glo) { return glo + nhi + 1; }
 
 __host__ __device__ inline SmemLayout smem_layout(int ntypes, int nbin, int nhi, int glo, bool edges) {
@@ -431,14 +429,12 @@ __host__ __device__ inline SmemLayout smem_layout(int ntypes, int nbin, int nhi,
     L.bars = align_up(o, 8);
     o = L.bars + kStages * sizeof(uint64_t);
     L.hist = o;
-    o += (static_cast<size_t>(ntypes) * (ntypes + 1) + 1) * row_stride(nhi, glo) * sizeof(unsigned int);
+    o += static_cast<size_t>(ntypes) * (ntypes + 1) * row_stride(nhi, glo) * sizeof(unsigned int);
     L.dump = o;
     o += 32 * sizeof(unsigned int);
     L.rowtab = o;
     o += static_cast<size_t>(ntypes) * ntypes * sizeof(unsigned int);
     L.tstart = o;
-    o += static_cast<size_t>(ntypes + 1) * sizeof(int);
-    L.treal = o;
     o += static_cast<size_t>(ntypes + 1) * sizeof(int);
     L.sched = o;
     o += 4 * sizeof(unsigned int);
@@ -449,6 +445,8 @@ __host__ __device__ inline SmemLayout smem_layout(int ntypes, int nbin, int nhi,
 size_t pair_kernel_smem_bytes(int ntypes, int nbin, int nhi, int glo, bool edges) {
     return smem_layout(ntypes, nbin, nhi, glo, edges).total;
 }
+
+constexpr int kWarpsPerCta = kThreads / 32;
 
 struct PairConst {
     BoxRegs box;
@@ -568,8 +566,10 @@ __device__ __forceinline__ void safe2_floors(float s, float inv_lo, float inv_hi
     asm("fma.rm.f32 %0, %1, %2, %3;" : "=f"(ra) : "f"(s), "f"(inv_lo), "f"(bias));
     asm("fma.rm.f32 %0, %1, %2, %3;" : "=f"(rb) : "f"(s), "f"(inv_hi), "f"(bias));
 }
-// kaddr = shared address of hist[0] - 4 * 0x4B400000 (mod 2^32).  (The OR into acc stays outside the asm block: with
-// acc as a read-write operand of a lop3 inside it, ptxas 12.9 crashes on the unrolled group.)
+// kaddr = shared address of hist[0] - 4 * 0x4B400000 (mod 2^32).  s comes in clamped to smax (see safe2_root), so the
+// word is at most row + nbin: the guard bin that ends every row.  (The OR into acc stays outside the asm block: with
+// acc as a read-write operand of a lop3 inside it, ptxas 12.9 crashes on the unrolled group.  And the atomic is
+// unconditional: ptxas turns a predicated red.shared into a branch around it.)
 __device__ __forceinline__ void safe2_bin(float s, float inv_lo, float inv_hi, float bias, uint32_t kaddr, unsigned int &acc) {
     unsigned int x;
     asm volatile(
@@ -586,6 +586,14 @@ __device__ __forceinline__ void safe2_bin(float s, float inv_lo, float inv_hi, f
         : "f"(s), "f"(inv_lo), "f"(inv_hi), "f"(bias), "r"(kaddr)
         : "memory");
     acc |= x;
+}
+// s = min(sqrt.approx((float)d2), smax): smax = (nbin + 0.5 - c0) * dr maps to the middle of the guard bin past the
+// last real one for both slopes; min.f32 returns the other operand for NaN (ghost slots), so far pairs, +inf and NaN
+// all count there and are never flagged as near an edge
+__device__ __forceinline__ float safe2_root(float f, float smax) {
+    float s;
+    asm volatile("{\n\t.reg .f32 t;\n\tsqrt.approx.ftz.f32 t, %1;\n\tmin.f32 %0, t, %2;\n\t}" : "=f"(s) : "f"(f), "f"(smax));
+    return s;
 }
 
 template <bool TRI>
@@ -627,17 +635,34 @@ __device__ __forceinline__ unsigned int group_dense2(const PairParams &p, const 
             const int q = t / kIPT, k = t % kIPT;
             fv[t] = cvt_rz(pair_d2_single<TRI>(c, xi[k], yi[k], zi[k], xj[q], yj[q], zj[q]));
         }
-        if (t >= LAG_S && t - LAG_S < NP) fv[t - LAG_S] = sqrt_approx_v(fv[t - LAG_S]);
+        if (t >= LAG_S && t - LAG_S < NP) fv[t - LAG_S] = safe2_root(fv[t - LAG_S], p.smax);
         if (t >= LAG_B && t - LAG_B < NP) safe2_bin(fv[t - LAG_B], p.inv_lo, p.inv_hi, bias[(t - LAG_B) % kIPT], kaddr, acc);
     }
     return acc;
 }
 
+// Phase skew (MODE_SAFE2).  A group is a run of FP64 instructions (the distances) followed by a run that keeps the
+// XU pipe busy (conversion and root of every pair: 8 cycles each) -- and the warps of a scheduler, released together by
+// the tile barrier and served round-robin, walk through the two runs in step: FP64 pipe and XU pipe take turns instead
+// of working side by side (r1/r2 profiles: 40 cycles per pair where the FP64 pipe alone needs 28).  Half of the warps
+// of every scheduler therefore start each tile with one binning run on dummy values (they count in the guard bin that
+// ends a row): from then on these warps bin while the others compute distances, and the offset keeps itself up, because
+// two warps in the same run compete for one pipe and two warps in different runs do not.
+__device__ __forceinline__ void phase_skew(const PairParams &p, float bias, uint32_t kaddr, int seed) {
+    unsigned int acc = 0;
+#pragma unroll
+    for (int t = 0; t < kIPT * kJU; ++t) {
+        const float f = cvt_rz(__hiloint2double(0x7fe00000 - (seed << 4) - t, 0));   // huge, finite, different every time
+        safe2_bin(safe2_root(f, p.smax), p.inv_lo, p.inv_hi, bias, kaddr, acc);
+    }
+    if (acc) atomicExch(p.error_flag, 2u);   // cannot happen: the clamped root is the same for both slopes
+}
+
 // Rare path of MODE_SAFE2: some pair of the group is within eps of a bin edge.  Recompute the group (same instructions,
-// same bits) and for every such pair take the fast-path increment back and count the pair where the exact threshold
-// table says (or nowhere).  Counters are integers modulo 2^32 and a CTA merges its rows only at barriers.
+// same bits) and for every such pair take the fast-path increment back (if there was one) and count the pair where
+// the exact threshold table says (or nowhere).  Counters are integers modulo 2^32 and a CTA merges its rows only at barriers.
 template <bool TRI>
-__device__ __noinline__ void group_fix2(PairConst c, IAtoms ia, float inv_lo, float inv_hi, float bias0, uint32_t sx_addr,
+__device__ __noinline__ void group_fix2(PairConst c, IAtoms ia, float inv_lo, float inv_hi, float bias0, float smax, uint32_t sx_addr,
                                         uint32_t jrow_bytes, int jrel, const double2 *__restrict__ thr2, int nbin,
                                         float inv_dr, float c0, unsigned int *s_hist) {
     for (int q = 0; q < kJU; ++q) {
@@ -649,7 +674,7 @@ __device__ __noinline__ void group_fix2(PairConst c, IAtoms ia, float inv_lo, fl
 #pragma unroll
         for (int k = 0; k < kIPT; ++k) {
             const double d2 = pair_d2_single<TRI>(c, ia.x[k], ia.y[k], ia.z[k], xj, yj, zj);
-            const float s = sqrt_approx_v(cvt_rz(d2));
+            const float s = safe2_root(cvt_rz(d2), smax);
             float ra, rb;
             safe2_floors(s, inv_lo, inv_hi, ia.bias[k], ra, rb);
             if (__float_as_int(ra) == __float_as_int(rb)) continue;
@@ -663,7 +688,7 @@ __device__ __noinline__ void group_fix2(PairConst c, IAtoms ia, float inv_lo, fl
                 while (d2 >= thr2[g + 1].y) ++g;
             }
             if (g >= 0 && row + g == word) continue;
-            atomicAdd(s_hist + word, 0xffffffffu);
+            atomicAdd(s_hist + word, 0xffffffffu);   // (may be the guard bin that ends the row: never merged)
             if (g >= 0) atomicAdd(s_hist + row + g, 1u);
         }
     }
@@ -755,10 +780,9 @@ __device__ __forceinline__ void process_group(const PairParams &p, const PairCon
 // (type_i, type_j) -> row table of Gofrt::get_itype, and the first slot of every type group.
 template <bool EDGES>
 __device__ __forceinline__ void cta_tables(const PairParams &p, int tid, int P, int rstride, unsigned int *s_hist,
-                                           double2 *s_thr2, double *s_thrf, unsigned int *s_rowtab, int *s_tstart,
-                                           int *s_treal) {
+                                           double2 *s_thr2, double *s_thrf, unsigned int *s_rowtab, int *s_tstart) {
     const int nt = p.ntypes, nbin = p.nbin;
-    for (int k = tid; k < (2 * P + 1) * rstride; k += kThreads) s_hist[k] = 0u;
+    for (int k = tid; k < 2 * P * rstride; k += kThreads) s_hist[k] = 0u;
     for (int k = tid; k < nbin + 3; k += kThreads) {
         // slot k <-> bin g = k-1
         const int g = k - 1;
@@ -784,8 +808,6 @@ __device__ __forceinline__ void cta_tables(const PairParams &p, int tid, int P, 
         s_rowtab[k] = static_cast<unsigned int>((P - (b + 1) * (b + 2) / 2 + a) * rstride + p.glo);
     }
     for (int k = tid; k <= nt; k += kThreads) s_tstart[k] = p.type_start[k];
-    // end of the REAL atoms of every type group (the slots from there to the next group's start are NaN ghosts)
-    for (int k = tid; k < nt; k += kThreads) s_treal[k] = p.type_real_end ? p.type_real_end[k] : p.type_start[k + 1];
 }
 
 // Merge the CTA's shared-memory rows (guard bins left out) into lag row `lag` of the global histogram and
@@ -821,7 +843,6 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) pair_kernel(const PairPa
     unsigned int *s_hist = reinterpret_cast<unsigned int *>(smem + L.hist);
     unsigned int *s_rowtab = reinterpret_cast<unsigned int *>(smem + L.rowtab);
     int *s_tstart = reinterpret_cast<int *>(smem + L.tstart);
-    int *s_treal = reinterpret_cast<int *>(smem + L.treal);
     unsigned int *s_sched = reinterpret_cast<unsigned int *>(smem + L.sched);
 
     const int tid = threadIdx.x;
@@ -832,7 +853,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) pair_kernel(const PairPa
     const int rstride = row_stride(p.nhi, p.glo);   // words of one row in shared memory (with its guard bins)
     const unsigned int self_off = static_cast<unsigned int>(P * rstride);
 
-    cta_tables<EDGES>(p, tid, P, rstride, s_hist, s_thr2, s_thrf, s_rowtab, s_tstart, s_treal);
+    cta_tables<EDGES>(p, tid, P, rstride, s_hist, s_thr2, s_thrf, s_rowtab, s_tstart);
     if (tid == 0) {
         for (int s = 0; s < kStages; ++s) mbar_init(&s_bar[s], 1);
         mbar_fence_init();
@@ -916,7 +937,6 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) pair_kernel(const PairPa
         // ---- this thread's i atoms (frame fi) ----
         double xi[kIPT], yi[kIPT], zi[kIPT];
         int ii[kIPT], ti[kIPT];
-        bool ighost[kIPT];
         const double *pi = p.pos + static_cast<size_t>(job.fi) * 3 * p.npad;
         const int wi0 = itile * kTileI + warp * (32 * kIPT);  // this warp's i atoms: [wi0, wi0 + 32*kIPT)
 #pragma unroll
@@ -931,17 +951,6 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) pair_kernel(const PairPa
             } else {
                 xi[k] = yi[k] = zi[k] = __longlong_as_double(0x7ff8000000000000ll);
                 ti[k] = 0;
-            }
-            if (MODE == MODE_SAFE2) {
-                // no NaN in the fast groups: a ghost i slot takes the coordinates of slot 0 (a real atom) and counts
-                // into the row that is never merged
-                ighost[k] = xi[k] != xi[k];
-                if (ighost[k]) {
-                    xi[k] = pi[0];
-                    yi[k] = pi[p.npad];
-                    zi[k] = pi[2 * static_cast<size_t>(p.npad)];
-                    ii[k] = -1;
-                }
             }
         }
 
@@ -969,6 +978,8 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) pair_kernel(const PairPa
             const uint32_t sx_addr = stage_addr + (gt & 1u) * (3u * kTileJ * 8u);
             const int j0 = jbeg + tl * kTileJ;
             const int j1 = min(j0 + kTileJ, jend);
+            if (MODE == MODE_SAFE2 && (warp & (kWarpsPerCta / 2)) && p.skew)
+                phase_skew(p, __fadd_rn(p.bias0, static_cast<float>(s_rowtab[0])), c.hist_addr - 4u * 0x4B400000u, lane);
 
             for (int ty = 0; ty < nt; ++ty) {
                 const int lo = max(j0, s_tstart[ty]);
@@ -981,18 +992,12 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) pair_kernel(const PairPa
                 const int da = min(max(wi0, lo), hi);
                 const int db = min(max(wi0 + 32 * kIPT, lo), hi);
                 if (MODE == MODE_SAFE2) {
-                    // fast groups: no own atom (i == j goes to another row) and no ghost j slot (NaN) among the j atoms;
-                    // the groups that hold either -- the diagonal segment and the last group of a type -- take the
-                    // clamped form of MODE_SAFE_DENSE, which shares the histogram rows
+                    // fast groups: every group but those that hold one of this warp's own atoms (i == j goes to another
+                    // row: the diagonal segment takes the clamped form of MODE_SAFE_DENSE, which shares the rows)
                     float bias[kIPT];
 #pragma unroll
-                    for (int k = 0; k < kIPT; ++k) {
-                        if (ighost[k]) row[k] = static_cast<unsigned int>(2 * P * rstride + p.glo);
-                        bias[k] = __fadd_rn(p.bias0, static_cast<float>(row[k]));
-                    }
+                    for (int k = 0; k < kIPT; ++k) bias[k] = __fadd_rn(p.bias0, static_cast<float>(row[k]));
                     const uint32_t kaddr = c.hist_addr - 4u * 0x4B400000u;
-                    const int hc = max(lo, min(hi, s_treal[ty] & ~(kJU - 1)));   // [hc, hi): holds ghost j slots
-                    const int a1 = min(da, hc), b0 = min(max(db, lo), hc);
                     auto fast = [&](int j) {
                         const unsigned int near = group_dense2<TRI>(p, c, xi, yi, zi, bias, kaddr, sx_addr, kTileJ * 8u, j - j0);
                         if (near) {
@@ -1004,26 +1009,18 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) pair_kernel(const PairPa
                                 ia.z[k] = zi[k];
                                 ia.bias[k] = bias[k];
                             }
-                            group_fix2<TRI>(c, ia, p.inv_lo, p.inv_hi, p.bias0, sx_addr, kTileJ * 8u, j - j0, s_thr2, p.nbin,
+                            group_fix2<TRI>(c, ia, p.inv_lo, p.inv_hi, p.bias0, p.smax, sx_addr, kTileJ * 8u, j - j0, s_thr2, p.nbin,
                                             p.inv_dr, p.c0, s_hist);
                         }
                     };
 #pragma unroll 1
-                    for (int j = lo; j < a1; j += kJU) fast(j);
-#pragma unroll 1
-                    for (int j = a1; j < da; j += kJU)
-                        process_group<TRI, FAST, MODE_SAFE_DENSE, false>(p, c, xi, yi, zi, ii, row, sx_addr, kTileJ * 8u, j - j0, j,
-                                                                         s_thr2, s_thrf, s_hist, self_off, edges, wrap_ok);
+                    for (int j = lo; j < da; j += kJU) fast(j);
 #pragma unroll 1
                     for (int j = da; j < db; j += kJU)
                         process_group<TRI, FAST, MODE_SAFE_DENSE, true>(p, c, xi, yi, zi, ii, row, sx_addr, kTileJ * 8u, j - j0, j,
                                                                         s_thr2, s_thrf, s_hist, self_off, edges, wrap_ok);
 #pragma unroll 1
-                    for (int j = db; j < b0; j += kJU) fast(j);
-#pragma unroll 1
-                    for (int j = max(db, b0); j < hi; j += kJU)
-                        process_group<TRI, FAST, MODE_SAFE_DENSE, false>(p, c, xi, yi, zi, ii, row, sx_addr, kTileJ * 8u, j - j0, j,
-                                                                         s_thr2, s_thrf, s_hist, self_off, edges, wrap_ok);
+                    for (int j = db; j < hi; j += kJU) fast(j);
                     continue;
                 }
 #pragma unroll 1
@@ -1089,7 +1086,6 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) pair_small_kernel(const 
     unsigned int *s_hist = reinterpret_cast<unsigned int *>(smem + L.hist);
     unsigned int *s_rowtab = reinterpret_cast<unsigned int *>(smem + L.rowtab);
     int *s_tstart = reinterpret_cast<int *>(smem + L.tstart);
-    int *s_treal = reinterpret_cast<int *>(smem + L.treal);
     unsigned int *s_sched = reinterpret_cast<unsigned int *>(smem + L.sched);
 
     const int tid = threadIdx.x;
@@ -1100,7 +1096,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) pair_small_kernel(const 
     const int rstride = row_stride(p.nhi, p.glo);
     const unsigned int self_off = static_cast<unsigned int>(P * rstride);
 
-    cta_tables<EDGES>(p, tid, P, rstride, s_hist, s_thr2, s_thrf, s_rowtab, s_tstart, s_treal);
+    cta_tables<EDGES>(p, tid, P, rstride, s_hist, s_thr2, s_thrf, s_rowtab, s_tstart);
     __syncthreads();
 
     PairConst c;
@@ -1316,16 +1312,15 @@ cudaError_t launch_validate_safe(const double *probes, const int *expected, int 
 }
 
 __global__ void validate_safe2_kernel(const double *__restrict__ probes, const int *__restrict__ expected, int n,
-                                      float inv_lo, float inv_hi, float bias0, double d2_max, int nbin, int glo,
+                                      float inv_lo, float inv_hi, float bias0, float smax, int nbin, int glo,
                                       unsigned int *bad) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
-    const double d2 = probes[k];
-    if (!(d2 <= d2_max)) return;   // farther than any pair of a window the mode is used on (and NaN)
+    const double d2 = probes[k];   // every probe counts here: far values, +inf and NaN must end in the guard bin
     float ra, rb;
-    safe2_floors(sqrt_approx_v(cvt_rz(d2)), inv_lo, inv_hi, bias0, ra, rb);
-    const int g = __float_as_int(ra) - 0x4B400000 - (__float_as_int(bias0) - 0x4B400000);   // guessed bin
-    if (g < -glo) atomicAdd(bad, 1u);   // would leave the row below its guard bins
+    safe2_floors(safe2_root(cvt_rz(d2), smax), inv_lo, inv_hi, bias0, ra, rb);
+    const int g = __float_as_int(ra) - 0x4B400000;   // guessed bin (bias0 = 1.5*2^23 + c0, row 0)
+    if (g < -glo || g > nbin) atomicAdd(bad, 1u);   // would leave the row and its guard bins
     if (__float_as_int(ra) == __float_as_int(rb)) {
         const int e = expected[k];
         const bool counted = g >= 0 && g < nbin, should = e >= 0 && e < nbin;
@@ -1334,9 +1329,9 @@ __global__ void validate_safe2_kernel(const double *__restrict__ probes, const i
 }
 
 cudaError_t launch_validate_safe2(const double *probes, const int *expected, int n, float inv_lo, float inv_hi, float bias0,
-                                  double d2_max, int nbin, int glo, unsigned int *bad, cudaStream_t stream) {
+                                  float smax, int nbin, int glo, unsigned int *bad, cudaStream_t stream) {
     if (n <= 0) return cudaSuccess;
-    validate_safe2_kernel<<<(n + 255) / 256, 256, 0, stream>>>(probes, expected, n, inv_lo, inv_hi, bias0, d2_max, nbin, glo, bad);
+    validate_safe2_kernel<<<(n + 255) / 256, 256, 0, stream>>>(probes, expected, n, inv_lo, inv_hi, bias0, smax, nbin, glo, bad);
     return cudaGetLastError();
 }
 
@@ -1373,19 +1368,24 @@ cudaError_t launch_gather_soa(const double *pos_aos, const int *perm, int natoms
 }
 
 __global__ void scatter_aos_kernel(const double *__restrict__ soa, const int *__restrict__ perm, int natoms, int npad,
-                                   double *__restrict__ aos) {
+                                   int nframes, double *__restrict__ aos) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= npad) return;
+    const int f = blockIdx.y;
+    if (k >= npad || f >= nframes) return;
     const int dst = perm[k];
     if (dst < 0) return;
-    aos[static_cast<size_t>(dst) * 3 + 0] = soa[k];
-    aos[static_cast<size_t>(dst) * 3 + 1] = soa[npad + k];
-    aos[static_cast<size_t>(dst) * 3 + 2] = soa[2 * static_cast<size_t>(npad) + k];
+    const double *s = soa + static_cast<size_t>(f) * 3 * npad;
+    double *a = aos + (static_cast<size_t>(f) * natoms + dst) * 3;
+    a[0] = s[k];
+    a[1] = s[npad + k];
+    a[2] = s[2 * static_cast<size_t>(npad) + k];
 }
 
-cudaError_t launch_scatter_aos(const double *pos_soa_frame, const int *perm, int natoms, int npad, double *pos_aos,
+cudaError_t launch_scatter_aos(const double *pos_soa, const int *perm, int natoms, int npad, int nframes, double *pos_aos,
                                cudaStream_t stream) {
-    scatter_aos_kernel<<<(npad + 255) / 256, 256, 0, stream>>>(pos_soa_frame, perm, natoms, npad, pos_aos);
+    if (nframes <= 0 || npad <= 0) return cudaSuccess;
+    dim3 grid((npad + 255) / 256, nframes);
+    scatter_aos_kernel<<<grid, 256, 0, stream>>>(pos_soa, perm, natoms, npad, nframes, pos_aos);
     return cudaGetLastError();
 }
 
@@ -1671,34 +1671,38 @@ constexpr int kMsdThreads = 256;
 
 __global__ void __launch_bounds__(kMsdThreads) msd_partial_kernel(const MsdParams p) {
     __shared__ double red[kMsdThreads];
-    const int tile = blockIdx.x, t = blockIdx.y, tid = threadIdx.x;
-    const int ty = p.tile_type[tile];
-    const int slot = p.tile_start[tile] + tid;
-    const bool live = tid < p.tile_count[tile];
-    double acc = 0.0;
-    if (live) {
-        for (int im = 0; im < p.ntimesteps; im += p.skip) {
-            const size_t fa = static_cast<size_t>(p.f0 + im), fb = fa + t;
-            const double *pa = p.pos + fa * 3 * p.npad, *pb = p.pos + fb * 3 * p.npad;
-            double dx = __dsub_rn(pa[slot], pb[slot]);
-            double dy = __dsub_rn(pa[p.npad + slot], pb[p.npad + slot]);
-            double dz = __dsub_rn(pa[2 * static_cast<size_t>(p.npad) + slot], pb[2 * static_cast<size_t>(p.npad) + slot]);
-            if (p.cm_self) {
-                const double *ca = p.cm + (fa * p.ntypes + ty) * 3, *cb = p.cm + (fb * p.ntypes + ty) * 3;
-                dx = __dsub_rn(dx, __dsub_rn(ca[0], cb[0]));
-                dy = __dsub_rn(dy, __dsub_rn(ca[1], cb[1]));
-                dz = __dsub_rn(dz, __dsub_rn(ca[2], cb[2]));
+    // the lag is the x index of the grid (up to 2^31 - 1 lags: a block of millions of frames with -S 0), the tiles walk y
+    const int t = blockIdx.x, tid = threadIdx.x;
+    for (int tile = blockIdx.y; tile < p.ntiles; tile += gridDim.y) {
+        const int ty = p.tile_type[tile];
+        const int slot = p.tile_start[tile] + tid;
+        const bool live = tid < p.tile_count[tile];
+        double acc = 0.0;
+        if (live) {
+            for (int im = 0; im < p.ntimesteps; im += p.skip) {
+                const size_t fa = static_cast<size_t>(p.f0 + im), fb = fa + t;
+                const double *pa = p.pos + fa * 3 * p.npad, *pb = p.pos + fb * 3 * p.npad;
+                double dx = __dsub_rn(pa[slot], pb[slot]);
+                double dy = __dsub_rn(pa[p.npad + slot], pb[p.npad + slot]);
+                double dz = __dsub_rn(pa[2 * static_cast<size_t>(p.npad) + slot], pb[2 * static_cast<size_t>(p.npad) + slot]);
+                if (p.cm_self) {
+                    const double *ca = p.cm + (fa * p.ntypes + ty) * 3, *cb = p.cm + (fb * p.ntypes + ty) * 3;
+                    dx = __dsub_rn(dx, __dsub_rn(ca[0], cb[0]));
+                    dy = __dsub_rn(dy, __dsub_rn(ca[1], cb[1]));
+                    dz = __dsub_rn(dz, __dsub_rn(ca[2], cb[2]));
+                }
+                acc = __dadd_rn(acc, __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)));
             }
-            acc = __dadd_rn(acc, __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)));
         }
-    }
-    red[tid] = acc;
-    __syncthreads();
-    for (int s = kMsdThreads / 2; s > 0; s >>= 1) {
-        if (tid < s) red[tid] = __dadd_rn(red[tid], red[tid + s]);
+        red[tid] = acc;
+        __syncthreads();
+        for (int s = kMsdThreads / 2; s > 0; s >>= 1) {
+            if (tid < s) red[tid] = __dadd_rn(red[tid], red[tid + s]);
+            __syncthreads();
+        }
+        if (tid == 0) p.partial[static_cast<size_t>(t) * p.ntiles + tile] = red[0];
         __syncthreads();
     }
-    if (tid == 0) p.partial[static_cast<size_t>(t) * p.ntiles + tile] = red[0];
 }
 
 __global__ void msd_finish_kernel(const MsdParams p) {
@@ -1730,7 +1734,7 @@ __global__ void msd_finish_kernel(const MsdParams p) {
 cudaError_t launch_msd(const MsdParams &p, cudaStream_t stream) {
     if (p.leff <= 0 || p.ntypes <= 0) return cudaSuccess;
     if (p.ntiles > 0) {
-        dim3 grid(p.ntiles, p.leff);
+        dim3 grid(p.leff, p.ntiles < 65535 ? p.ntiles : 65535);
         msd_partial_kernel<<<grid, kMsdThreads, 0, stream>>>(p);
     }
     const int n = p.leff * p.ntypes;

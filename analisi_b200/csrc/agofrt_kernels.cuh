@@ -75,8 +75,8 @@ struct PairParams {
     float c0h, lim, qmax;             // MODE_SAFE: c0 - 0.5, 0.5 - eps, nbin + 0.25 (clamp of the bin coordinate)
     int glo;                          // guard bins below bin 0 in every shared-memory histogram row
     int nhi;                          // bins from bin 0 up in every shared-memory row (>= nbin; only the first nbin are merged)
-    float inv_lo, inv_hi, bias0;      // MODE_SAFE2: inv_dr * (1 -+ 2^-20), 1.5*2^23 + c0 (c0 an integer)
-    const int *type_real_end;         // [ntypes] end of the real atoms of every type group (MODE_SAFE2; may be NULL)
+    int skew;                         // MODE_SAFE2: half of the warps start every tile with a dummy binning run (phase_skew)
+    float inv_lo, inv_hi, bias0, smax;  // MODE_SAFE2: inv_dr * (1 -+ 2^-20), 1.5*2^23 + c0 (c0 an integer), clamp of sqrt(d2)
     unsigned hlo, hspan, hhi;         // candidate tests on the high word of d2 (hhi = hlo + hspan)
 };
 
@@ -91,8 +91,8 @@ cudaError_t prepare_pair_kernels(size_t max_smem_optin);
 // pos_aos [nframes][natoms][3] -> pos_soa [nframes][3][npad] through perm[npad] (-1 = ghost -> NaN)
 cudaError_t launch_gather_soa(const double *pos_aos, const int *perm, int natoms, int npad, int nframes,
                               double *pos_soa, cudaStream_t stream);
-// inverse: one frame back to the caller's order
-cudaError_t launch_scatter_aos(const double *pos_soa_frame, const int *perm, int natoms, int npad,
+// inverse: frames back to the caller's order
+cudaError_t launch_scatter_aos(const double *pos_soa, const int *perm, int natoms, int npad, int nframes,
                                double *pos_aos, cudaStream_t stream);
 // box rows [nframes][stride] -> [nframes][6] (lx/2, ly/2, lz/2, xy, xz, yz)
 cudaError_t launch_pack_box(const double *box_internal, int stride, int nframes, double *box6,
@@ -151,9 +151,9 @@ cudaError_t launch_blockavg_push(const unsigned long long *counts, double incr, 
 // MODE_SAFE validation: bad += number of probes whose unflagged float guess differs from expected[]
 cudaError_t launch_validate_safe(const double *probes, const int *expected, int n, float inv_dr, float c0h, float lim,
                                  float qmax, int nbin, int glo, unsigned int *bad, cudaStream_t stream);
-// MODE_SAFE2 validation: the same for the two-floor guess, on the probes with d2 <= d2_max
+// MODE_SAFE2 validation: the same for the two-floor guess
 cudaError_t launch_validate_safe2(const double *probes, const int *expected, int n, float inv_lo, float inv_hi, float bias0,
-                                  double d2_max, int nbin, int glo, unsigned int *bad, cudaStream_t stream);
+                                  float smax, int nbin, int glo, unsigned int *bad, cudaStream_t stream);
 // DFMA chains; *count_per_launch receives the number of lane-level DFMAs one launch executes
 cudaError_t launch_dfma_peak(double *sink, int blocks, int iters, cudaStream_t stream,
                              unsigned long long *count_per_launch);

@@ -198,6 +198,18 @@ def run_c5(args, rank, world, name="C5"):
     return 0
 
 
+def load_pyanalisi(local_rank):
+    """The pybind11 module (host C++ mirror of the reference API over the C ABI), bound to this rank's GPU."""
+    os.environ.setdefault("ANALISI_DEVICES", str(local_rank))
+    from analisi_b200 import build as b
+    _, ext = b.build_host()
+    d = os.path.dirname(ext)
+    if d not in sys.path:
+        sys.path.insert(0, d)
+    import pyanalisi
+    return pyanalisi
+
+
 def jobs_of(nts, leff, skip, every):
     return ((leff + every - 1) // every) * ((nts + skip - 1) // skip)
 
@@ -399,6 +411,7 @@ def main():
     ap.add_argument("--quick", action="store_true", help="tiny block (smoke/profiling), not a bench number")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-traffic", action="store_true", help="skip the ncu re-run that measures roofline.traffic")
+    ap.add_argument("--no-e2e", action="store_true", help="kernel A/B runs with a tuning build of the library: skip the end-to-end leg")
     ap.add_argument("--traffic-child", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--options", type=int, default=0)
     ap.add_argument("--cpu-seconds", type=float, default=None, help="size of the CPU sample (default 12 s; 8 s per step for --impl reference)")
@@ -452,7 +465,11 @@ def main():
     ctx = cabi.Context([local_rank])
     adist.join_communicator(ranks, ctx)
 
-    pos, box_lammps, box_internal, types = make_window(w, nframes)
+    # frames the loops touch (nframes) and frames the reference's length check wants in the trajectory
+    # (lib/src/gofrt.cpp:81-83: leff + ntimesteps - 1; the e2e leg goes through that check)
+    nframes_traj = max(nframes, primo + nts + leff - 1)
+    pos_all, box_lammps_all, box_internal_all, types = make_window(w, nframes_traj)
+    pos, box_lammps, box_internal = pos_all[:nframes], box_lammps_all[:nframes], box_internal_all[:nframes]
     # wrap=True, as the reference callers do (analisi/main.cpp:558): the wrap runs on the GPU
     pinned = cabi.PinnedArray(pos.shape)
     pinned.array[...] = pos
@@ -503,16 +520,40 @@ def main():
     if counts0 is not None and not np.array_equal(counts, counts0):
         raise SystemExit("non-deterministic counts between steps")
 
-    # ---- end to end: host buffers in, counts out ----
-    barrier()
-    e0 = time.time()
-    for k in range(args.steps):
-        tr.upload(0, hpos, box_internal)
-        counts_e, st = plan.block(primo, nts, leff, w.skip, w.every, options=args.options)
-    barrier()
-    e2e_ms = maxrank((time.time() - e0) * 1e3)
-    if not np.array_equal(counts_e, counts):
-        raise SystemExit("e2e counts differ from resident counts")
+    # ---- end to end: the reference-facing call sequence (pyanalisi.Trajectory + Gofrt, reference
+    # pyanalisi/src/pyanalisi.cpp:65-82, :487-504) on the caller's UNWRAPPED numpy arrays, every step: construct the
+    # trajectory (box conversion, type compaction, upload from pageable memory -- the frames are dealt to the ranks and
+    # exchanged GPU to GPU --, wrap on the GPUs), construct Gofrt, reset, calculate, read the result array back.
+    if args.no_e2e:
+        e2e_ms, e2e_h2d, e2e_d2h = float('nan'), 0, 0
+    else:
+        pa = load_pyanalisi(local_rank)
+        if world > 1:
+            uid = pa.comm_unique_id() if rank == 0 else b""
+            pa.comm_join(ranks.broadcast_bytes(uid, cabi.COMM_ID_BYTES, 0), rank, world)
+        fmt = pa.BoxFormat.LammpsTriclinic if w.triclinic else pa.BoxFormat.LammpsOrtho
+        vel = np.zeros_like(pos_all)   # the interface wants velocities; g(r,t) never reads them
+        raw_types = np.ascontiguousarray(types, dtype=np.int32)
+
+        def e2e_step():
+            tr_py = pa.Trajectory(pos_all, vel, raw_types, box_lammps_all, fmt, True, False)
+            g = pa.Gofrt(tr_py, w.rmin, w.rmax, w.nbin, w.tmax, 1, w.skip, w.every, False)
+            g.reset(nts)
+            g.calculate(primo)
+            return np.array(g, copy=True)
+
+        v_e = e2e_step()   # warm-up: module load, communicator, device allocations
+        barrier()
+        e0 = time.time()
+        for k in range(args.steps):
+            v_e = e2e_step()
+        barrier()
+        e2e_ms = maxrank((time.time() - e0) * 1e3)
+        incr = cabi.gofrt_incr(nts, w.skip)
+        if not np.array_equal(v_e, counts * incr):
+            raise SystemExit("e2e result differs from the resident counts * incr")
+        e2e_h2d = int(pos_all.nbytes // world + box_lammps_all.nbytes)   # every rank copies its share of the frames
+        e2e_d2h = int(counts.nbytes)
 
     # ---- the counts themselves: one checksum that must not depend on the number of GPUs, and -- for the default
     # step -- must equal the checksum of the unmodified reference's counts (tests/golden/c4_subset_counts.json)
@@ -562,8 +603,11 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic", "config": config,
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(hpos.nbytes + box_internal.nbytes),
-                "d2h_bytes_per_step": int(counts.nbytes), "ms_per_step": e2e_ms / args.steps},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": e2e_h2d, "d2h_bytes_per_step": e2e_d2h,
+                "ms_per_step": e2e_ms / args.steps,
+                "path": "pyanalisi.Trajectory(pos, vel, types, box, fmt, wrap=True) + Gofrt(...).reset().calculate() + np.array(g), "
+                        "from pageable numpy arrays every step; H2D per rank = its share of the %d frames (%d bytes in all), "
+                        "shares exchanged GPU to GPU" % (nframes_traj, pos_all.nbytes)},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "counts_sha256": sha,

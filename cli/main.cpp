@@ -196,7 +196,8 @@ int main(int argc, char **argv) {
     }
 
     try {
-        if (o.gofrt > 0) {
+        // branch precedence as in the reference (analisi/main.cpp:520, :552, :620): mean square displacement first
+        if (!(o.msd || o.msd_cm || o.msd_self) && o.gofrt > 0) {
             if (o.factors.size() != 2) throw std::runtime_error("You have to specify the distance range with the option -F.\n");
             std::cerr << "Calculation of g(r,t) -- distinctive and non distinctive part of the van Hove function...\n";
             if (o.edges) setenv("ANALISI_EDGE_PAIRS", "1", 1);

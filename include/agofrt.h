@@ -115,6 +115,23 @@ AGOFRT_API int agofrt_traj_upload(agofrt_traj *traj, size_t first_frame, size_t 
  * thread while agofrt_block works on the first one (read-ahead of the next block). */
 AGOFRT_API int agofrt_traj_upload_wrap(agofrt_traj *traj, size_t first_frame, size_t nframes,
                                        double *pos_aos_inout, const double *box_internal);
+/* The general upload.  flags:
+ *   AGOFRT_UP_WRAP       BaseTrajectory::pbc_wrap on the device before the layout change (pos_aos is only read);
+ *   AGOFRT_UP_WRITEBACK  (with WRAP) the wrapped frames are written to pos_wrapped_out [nframes][natoms][3], which may be
+ *                        pos_aos itself -- what agofrt_traj_upload_wrap does;
+ *   AGOFRT_UP_SHARED     with a communicator (several local devices, or agofrt_comm_join): the frames of the window are
+ *                        dealt to the devices, every device copies / wraps / lays out its share, and the shares are
+ *                        exchanged device to device (NCCL over NVLink): the window crosses PCIe once per box, not once
+ *                        per GPU.  A collective: under agofrt_comm_join every process calls it with the same arguments;
+ *                        a process only needs valid host data for its own share (agofrt_shard_range over nframes) and
+ *                        for frame 0, and with WRITEBACK only its share comes back wrapped.
+ * Pageable host memory is staged through page-locked slots by several host threads. */
+enum { AGOFRT_UP_WRAP = 1, AGOFRT_UP_WRITEBACK = 2, AGOFRT_UP_SHARED = 4 };
+AGOFRT_API int agofrt_traj_upload_ex(agofrt_traj *traj, size_t first_frame, size_t nframes, const double *pos_aos,
+                                     const double *box_internal, unsigned flags, double *pos_wrapped_out);
+/* Frames of the device window back in the caller's atom order (wrapped if they were uploaded with AGOFRT_UP_WRAP): the
+ * host classes materialise their host copy with it the first time an accessor needs one. */
+AGOFRT_API int agofrt_traj_download(agofrt_traj *traj, size_t first_frame, size_t nframes, double *pos_aos);
 /* Read one frame back in the caller's atom order (tests: the layout round-trips bit-exactly). */
 AGOFRT_API int agofrt_traj_download_frame(agofrt_traj *traj, size_t frame, double *pos_aos);
 /* In-place BaseTrajectory::pbc_wrap on a host buffer through the GPU (frames with their own box
@@ -139,6 +156,10 @@ AGOFRT_API int agofrt_plan_retarget(agofrt_plan *plan, agofrt_traj *traj);
 /* thresholds[nbin+1]: thresholds[k] = the smallest d2 (>=0) whose reference bin index
  * (int)floorf((sqrt(d2)-rmin)/dr) is >= k (+inf if none). */
 AGOFRT_API int agofrt_plan_thresholds(const agofrt_plan *plan, double *thresholds);
+/* Which float shortcuts of the binning passed their validation on the device for this plan (each may be NULL):
+ * the safe-zone guess, its two-floor form (dense windows; needs -rmin/dr to be an integer), and the guard bins a
+ * shared-memory histogram row carries below bin 0.  The counts never depend on them. */
+AGOFRT_API int agofrt_plan_info(const agofrt_plan *plan, int *safe_zone_ok, int *two_floor_ok, int *guard_bins);
 
 enum {
     AGOFRT_OPT_DEFAULT = 0,
@@ -155,7 +176,9 @@ enum {
                                       and is not written */
     AGOFRT_OPT_SMALL = 1024,       /* take the small-system kernel for up to 512 device slots (default: up to 256, one
                                       to four warps per job, where it beats the tile kernel; measured equal above) */
-    AGOFRT_OPT_NO_SAFE2 = 2048     /* dense windows: keep the clamped safe-zone kernel (no two-floor binning) */
+    AGOFRT_OPT_SAFE2 = 2048,       /* dense windows: the two-floor form of the safe-zone binning (two round-down FFMAs give the
+                                      histogram word and the near-an-edge flag); exact like the others, measured slower */
+    AGOFRT_OPT_SKEW = 4096         /* with AGOFRT_OPT_SAFE2: offset half of the warps by one binning run (A/B measurements) */
 };
 
 typedef struct {

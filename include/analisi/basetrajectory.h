@@ -97,7 +97,10 @@ public:
         c[5] = hz * 2 + zlo;
     }
 
-    double *positions_data() { return buffer_positions; }
+    double *positions_data() {
+        sync_host();
+        return buffer_positions;
+    }
     double *velocity_data() { return buffer_velocity; }
     int get_type_min() { return min_type; }
     int get_type_max() { return max_type; }
@@ -124,6 +127,7 @@ public:
     }
     void pbc_wrap_frames(ssize_t first_idx, size_t nframes) {
         if (nframes == 0 || natoms == 0) return;
+        sync_host();
         analisi_device::pbc_wrap(buffer_positions + first_idx * natoms * 3, nframes, natoms,
                                  buffer_boxes + first_idx * buffer_boxes_stride, static_cast<int>(buffer_boxes_stride));
         mark_window_changed();
@@ -201,7 +205,7 @@ public:
     // ---- the device copy of the loaded window (this repository's addition) ----
     // Frames [current_timestep, current_timestep + loaded_timesteps) on every GPU of the process.
     agofrt_traj *device_window() {
-        if (loaded_timesteps <= 0 || !buffer_positions || !buffer_boxes)
+        if (loaded_timesteps <= 0 || (!buffer_positions && host_current) || !buffer_boxes)
             throw std::runtime_error("No data is loaded!\n");
         get_ntypes();
         if (!dev_window.valid() || dev_window.capacity() < static_cast<size_t>(loaded_timesteps)) {
@@ -211,7 +215,8 @@ public:
             ++dev_epoch;
         }
         if (dev_uploaded_epoch != host_epoch) {
-            dev_window.upload(current_timestep, loaded_timesteps, buffer_positions, buffer_boxes);
+            // once per box: the frames are dealt to the GPUs and exchanged device to device
+            dev_window.upload_shared(current_timestep, loaded_timesteps, buffer_positions, buffer_boxes, false, nullptr);
             dev_uploaded_epoch = host_epoch;
         }
         return dev_window.handle();
@@ -220,9 +225,36 @@ public:
     // events it only re-points the plan at the handle device_window() returns: the windows are double-buffered)
     uint64_t device_generation() const { return dev_epoch; }
 
+    // The host copy of the positions may be BEHIND the device copy (a window that was wrapped on the GPUs straight
+    // from the caller's arrays: g(r,t) never reads host positions).  Everything that hands out host positions calls
+    // this first; the frames then come back from the device once.
+    void sync_host() {
+        if (!host_current) {
+            static_cast<T *>(this)->materialise_host_positions();
+            host_current = true;
+        }
+    }
+
 protected:
     ~BaseTrajectory() = default;
     void mark_window_changed() { ++host_epoch; }
+    void materialise_host_positions() {}   // containers whose host copy is always current
+    // the window [current_timestep, +loaded_timesteps) goes to the GPUs straight from `pos` (read only, may be
+    // pageable), wrapped there when asked; the host copy is left for sync_host() to fetch
+    void upload_now(const double *pos, bool wrap) {
+        get_ntypes();
+        if (!dev_window.valid() || dev_window.capacity() < static_cast<size_t>(loaded_timesteps)) {
+            dev_window.create(natoms, static_cast<int>(buffer_boxes_stride), buffer_type_id, static_cast<int>(ntypes),
+                              loaded_timesteps);
+            ++dev_epoch;
+        }
+        dev_window.upload_shared(current_timestep, loaded_timesteps, pos, buffer_boxes, wrap, nullptr);
+        ++host_epoch;
+        dev_uploaded_epoch = host_epoch;
+        host_current = false;
+    }
+    void download_window(double *pos_out) { dev_window.download(current_timestep, loaded_timesteps, pos_out); }
+    bool host_current = true;
 
     // ---- read-ahead of the NEXT window onto the devices (derived containers with a background reader) ----
     // Gofrt has already used this trajectory on the GPUs: reading ahead may upload as well

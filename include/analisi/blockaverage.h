@@ -18,6 +18,8 @@
 
 #include <cstdlib>
 #include <iostream>
+#include <sstream>
+#include <stdexcept>
 
 #include "analisi/calcoliblocchi.h"
 #include "analisi/cronometro.h"
@@ -67,8 +69,11 @@ public:
                                             static_cast<int>(n_b)
                                       : 0;
         if (per_block <= 0) {
-            std::cerr << "Cannot divide the trajectory in " << n_b << " blocks!\n";
-            abort();
+            // (the reference aborts here, blockaverage.h:116-119; an exception keeps a python caller alive and the CLI
+            // still exits with code 1)
+            std::stringstream ss;
+            ss << "Cannot divide the trajectory in " << n_b << " blocks!\n";
+            throw std::runtime_error(ss.str());
         }
         s = static_cast<unsigned int>(per_block);
         ok = true;
@@ -117,15 +122,15 @@ public:
     }
 
     T *media() {
-        if (!ok) abort();
+        if (!ok) throw std::runtime_error("BlockAverage: calculate() has not been run\n");
         return Tmedio;
     }
     T *varianza() {
-        if (!ok) abort();
+        if (!ok) throw std::runtime_error("BlockAverage: calculate() has not been run\n");
         return Tvar;
     }
     T *puntatoreCalcolo() {
-        if (!ok) abort();
+        if (!ok) throw std::runtime_error("BlockAverage: calculate() has not been run\n");
         return calcolo;
     }
     unsigned int block_size() const { return s; }

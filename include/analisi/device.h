@@ -31,6 +31,12 @@ public:
     static Context &instance();
     agofrt_ctx *handle() { return ctx_; }
     int ndev() const { return agofrt_ctx_ndev(ctx_); }
+    // One process per GPU (torchrun, mpirun): rank 0 makes the id, the launcher broadcasts the bytes, every process
+    // joins with its rank.  Afterwards the work units of every block are sharded over all processes, the integer
+    // histograms are all-reduced, and windows are uploaded once per box (every process copies its share of the frames,
+    // the shares travel GPU to GPU).  Replaces the reference's Mp (lib/include/mp.h:26-55).
+    static std::string comm_unique_id();
+    void comm_join(const std::string &id, int rank, int world);
     Context(const Context &) = delete;
     Context &operator=(const Context &) = delete;
 
@@ -83,6 +89,12 @@ public:
     void upload(size_t first, size_t n, const double *pos_aos, const double *box_internal);
     // the same with BaseTrajectory::pbc_wrap applied on the device; pos_aos comes back wrapped
     void upload_wrap(size_t first, size_t n, double *pos_aos_inout, const double *box_internal);
+    // general form (agofrt_traj_upload_ex): pos_aos is only read and may be pageable; `wrap` wraps on the device;
+    // wrapped_out (may be NULL, may be pos_aos) receives the wrapped frames; the frames are dealt to the GPUs of the
+    // process / communicator and exchanged device to device
+    void upload_shared(size_t first, size_t n, const double *pos_aos, const double *box_internal, bool wrap, double *wrapped_out);
+    // frames of the device window back to the host, caller's atom order
+    void download(size_t first, size_t n, double *pos_aos_out);
     void swap(Window &o) {
         agofrt_traj *t = traj_;
         traj_ = o.traj_;

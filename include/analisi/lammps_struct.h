@@ -42,8 +42,15 @@ struct LammpsFrameHeader {
     // starts at p + that).  Throws like the reference on truncated files and unsupported row sizes.
     size_t parse(const char *p, const char *end) {
         const char *q = p;
+        // sizes are compared, never pointers advanced by a length that comes from the file (a corrupt magic / unit /
+        // column length would overflow the pointer arithmetic); string fields longer than 64 KiB are refused
         auto need = [&](size_t n) {
-            if (q + n > end) throw std::runtime_error("Error: end of file reached");
+            if (q > end || n > static_cast<size_t>(end - q)) throw std::runtime_error("Error: end of file reached");
+        };
+        auto skip_string = [&](int64_t n) {
+            if (n < 0 || n > 65536) throw std::runtime_error("Error: corrupt header (length of a string field out of range)");
+            need(static_cast<size_t>(n));
+            q += n;
         };
         auto get = [&](auto *dst, size_t count) {
             const size_t bytes = sizeof(*dst) * count;
@@ -55,9 +62,8 @@ struct LammpsFrameHeader {
         get(&first, 1);
         if (first < 0) {
             format2020 = true;
-            const int64_t magic_len = -first;
-            need(static_cast<size_t>(magic_len));
-            q += magic_len;
+            if (first == INT64_MIN) throw std::runtime_error("Error: corrupt header (length of a string field out of range)");
+            skip_string(-first);
             int endian = 0;
             get(&endian, 1);
             get(&revision, 1);
@@ -75,10 +81,7 @@ struct LammpsFrameHeader {
         if (format2020 && revision > 1) {
             int unit_len = 0;
             get(&unit_len, 1);
-            if (unit_len > 0) {
-                need(static_cast<size_t>(unit_len));
-                q += unit_len;
-            }
+            if (unit_len > 0) skip_string(unit_len);
             char time_flag = 0;
             get(&time_flag, 1);
             if (time_flag) {
@@ -87,10 +90,7 @@ struct LammpsFrameHeader {
             }
             int columns_len = 0;
             get(&columns_len, 1);
-            if (columns_len > 0) {
-                need(static_cast<size_t>(columns_len));
-                q += columns_len;
-            }
+            if (columns_len > 0) skip_string(columns_len);
         }
         get(&nchunk, 1);
         if (q >= end) throw std::runtime_error("Error: end of file reached");

@@ -21,6 +21,7 @@
 #include <cstdint>
 #include <exception>
 #include <sstream>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <unordered_map>
@@ -115,6 +116,7 @@ private:
     size_t indexed_upto = 0;
     bool window_loaded = false;
     bool load_velocities = true;
+    std::mutex type_change_mutex;   // the type-change warning of read_frame_to (several reader threads)
     std::unordered_map<int, int> id_to_slot;
     std::vector<int> slot_to_id;
     std::vector<int> dense_slot;          // id -> slot when the ids are compact (else id_to_slot is used)

@@ -11,8 +11,10 @@
 // when pybind11 is available (ANALISI_WITH_PYBIND11) the reference's signature taking pybind11::buffer
 // objects validates the buffers with the reference's error texts and delegates to it.
 //
-// Differences that are this repository's design: the wrap runs on the GPU (BaseTrajectory::
-// pbc_wrap_frames); the per-type centre of mass arrays are computed on first use (g(r,t) never reads
+// Differences that are this repository's design: with wrap on, the caller's arrays go to the GPUs as they are
+// (pageable memory staged through page-locked slots, frames dealt to the GPUs of the process and exchanged device
+// to device), are wrapped THERE, and the host only gets a wrapped copy when somebody asks for host positions
+// (get_positions_copy, positions<>(), write_lammps_binary): g(r,t) never does; the per-type centre of mass arrays are computed on first use (g(r,t) never reads
 // them); Lammps_triclinic input without wrap is copied (the reference leaves that buffer
 // uninitialised, lib/src/trajectory_numpy.cpp:147-149 -- SURVEY.md section 8c).
 #ifndef ANALISI_B200_TRAJECTORY_NUMPY_H
@@ -46,6 +48,7 @@ public:
 
     template <bool SAFE = true>
     double *positions(const int &timestep, const int &atomo) {
+        sync_host();
         return buffer_positions + static_cast<size_t>(natoms) * 3 * timestep + static_cast<size_t>(atomo) * 3;
     }
     template <bool SAFE = true>
@@ -71,12 +74,16 @@ public:
     // Q of frame t (9 doubles, column-major) or nullptr when no rotation was saved
     double *get_rotation_matrix(size_t t) { return rotation.empty() ? nullptr : rotation.data() + 9 * t; }
 
+    // the wrapped frames come back from the GPUs the first time host positions are asked for
+    void materialise_host_positions();
+
 private:
     void init(const double *pos, const double *vel, const int *types, const double *box, size_t nts, size_t natoms_,
               BoxFormat format, bool wrap, bool save_rot);
     void ensure_cm();
 
     const double *in_pos = nullptr, *in_vel = nullptr;   // the caller's arrays (unwrapped, unrotated)
+    bool wrapped_on_device = false;                        // the wrapped window lives on the GPUs; own_pos follows on demand
     analisi_device::PinnedBuffer own_pos;                  // wrapped / rotated copy (page-locked: it is uploaded)
     std::vector<double> own_vel, own_boxes, rotation, cm_pos, cm_vel, zero_vel;
     std::vector<int> raw_types, type_ids;

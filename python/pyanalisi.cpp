@@ -262,6 +262,14 @@ PYBIND11_MODULE(pyanalisi, m) {
 
     m.def("info", []() -> std::string { return std::string("analisi g(r,t), B200-native: ") + agofrt_version(); });
     m.def("has_mmap", []() -> bool { return true; });
+    // One process per GPU (torchrun / mpirun), this repository's replacement of the reference's MPI layer (Mp): rank 0
+    // calls comm_unique_id(), the launcher broadcasts the 128 bytes, every process calls comm_join(id, rank, world).
+    // Set ANALISI_DEVICES to the process's GPU before the first use of the module.
+    m.def("comm_unique_id", []() { return py::bytes(analisi_device::Context::comm_unique_id()); });
+    m.def("comm_join", [](const py::bytes &id, int rank, int world) {
+        analisi_device::Context::instance().comm_join(std::string(id), rank, world);
+    });
+    m.def("devices_in_use", []() { return analisi_device::Context::instance().ndev(); });
     m.def("device_count", []() {
         int n = 0;
         agofrt_device_count(&n);

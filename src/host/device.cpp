@@ -30,6 +30,17 @@ Context::~Context() {
     if (ctx_) agofrt_ctx_destroy(ctx_);
 }
 
+std::string Context::comm_unique_id() {
+    char id[AGOFRT_COMM_ID_BYTES];
+    check(agofrt_comm_unique_id(id), "agofrt_comm_unique_id");
+    return std::string(id, AGOFRT_COMM_ID_BYTES);
+}
+
+void Context::comm_join(const std::string &id, int rank, int world) {
+    if (id.size() != AGOFRT_COMM_ID_BYTES) throw std::runtime_error("comm_join: the id must be the 128 bytes of comm_unique_id()\n");
+    check(agofrt_comm_join(ctx_, id.data(), rank, world), "agofrt_comm_join");
+}
+
 void PinnedBuffer::resize(size_t ndoubles) {
     if (ndoubles == n_ && ptr_) return;
     release();
@@ -65,6 +76,15 @@ void Window::upload(size_t first, size_t n, const double *pos_aos, const double 
 
 void Window::upload_wrap(size_t first, size_t n, double *pos_aos_inout, const double *box_internal) {
     check(agofrt_traj_upload_wrap(traj_, first, n, pos_aos_inout, box_internal), "agofrt_traj_upload_wrap");
+}
+
+void Window::upload_shared(size_t first, size_t n, const double *pos_aos, const double *box_internal, bool wrap, double *wrapped_out) {
+    const unsigned flags = AGOFRT_UP_SHARED | (wrap ? AGOFRT_UP_WRAP : 0u) | (wrap && wrapped_out ? AGOFRT_UP_WRITEBACK : 0u);
+    check(agofrt_traj_upload_ex(traj_, first, n, pos_aos, box_internal, flags, wrapped_out), "agofrt_traj_upload_ex");
+}
+
+void Window::download(size_t first, size_t n, double *pos_aos_out) {
+    check(agofrt_traj_download(traj_, first, n, pos_aos_out), "agofrt_traj_download");
 }
 
 void pbc_wrap(double *pos_aos, size_t nframes, size_t natoms, const double *box_internal, int box_stride) {

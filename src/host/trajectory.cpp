@@ -89,6 +89,8 @@ Trajectory::Trajectory(std::string filename) {
             raw_type[ins.first->second] = static_cast<int>(std::round(rec[1]));
         }
     }
+    if (static_cast<ssize_t>(slot_to_id.size()) != natoms)
+        throw std::runtime_error("Error: the first frame does not hold one record for each of its atoms (repeated atomic ids?)\n");
     // compact ids (the usual case): a flat table instead of a hash lookup per atom and frame
     {
         int max_id = 0;
@@ -127,7 +129,8 @@ Trajectory::Errori Trajectory::set_data_access_block_size(const size_t &n) {
         std::cerr << "mmap not correctly initialized!\n";
         return non_inizializzato;
     }
-    if (static_cast<size_t>(loaded_timesteps) == n && window_capacity == n) return Ok;
+    // (a set_load_velocities() toggle since the last call changes which buffers exist: then go on and rebuild them)
+    if (static_cast<size_t>(loaded_timesteps) == n && window_capacity == n && load_velocities == (buffer_velocity != nullptr)) return Ok;
     cancel_prefetch();
     window_loaded = false;
     pos_buf.resize(n * natoms * 3);
@@ -221,9 +224,13 @@ void Trajectory::read_frame_to(size_t frame, double *P, double *b, double *V, do
             P[3 * s + 2] = rec[4];
             const int tipo = static_cast<int>(std::round(rec[1]));
             if (raw_type[s] != tipo) {
-                std::cerr << "WARNING: atomic type for atom with id " << s << " is changing from " << raw_type[s] << " to "
-                          << tipo << " !\n";
-                raw_type[s] = tipo;
+                // frames are read by several threads (and by the read-ahead thread): one at a time here
+                std::lock_guard<std::mutex> lock(type_change_mutex);
+                if (raw_type[s] != tipo) {
+                    std::cerr << "WARNING: atomic type for atom with id " << s << " is changing from " << raw_type[s] << " to "
+                              << tipo << " !\n";
+                    raw_type[s] = tipo;
+                }
             }
             if (V) {
                 V[3 * s] = rec[5];

@@ -57,10 +57,10 @@ void Trajectory_numpy::init(const double *pos, const double *vel, const int *typ
     buffer_boxes = own_boxes.data();
     box_format = triclinic ? BoxFormat::Lammps_triclinic : BoxFormat::Lammps_ortho;
 
-    // ---- positions / velocities: used in place unless they must be rotated or wrapped ----
+    // ---- positions / velocities: used in place unless they must be rotated (host copy) or wrapped (on the GPUs) ----
     const bool rotate = triclinic && format == BoxFormat::Cell_vectors;
     if (rotate) std::cerr << "Detected non orthorombic simulation cell. Using triclinic format" << std::endl;
-    if (wrap || triclinic) {
+    if (rotate) {
         own_pos.resize(nval > 0 ? nval : 1);
         if (nval) std::memcpy(own_pos.data(), pos, nval * sizeof(double));
         buffer_positions = own_pos.data();
@@ -96,8 +96,22 @@ void Trajectory_numpy::init(const double *pos, const double *vel, const int *typ
     get_ntypes();
 
     loaded_timesteps = n_timesteps;
-    if (wrap && nts > 0) pbc_wrap_frames(0, nts);
-    mark_window_changed();
+    if (wrap && nts > 0 && natoms_ > 0) {
+        // wrapped on the GPUs, straight from the (rotated copy of the) caller's array; the host copy follows on demand
+        upload_now(buffer_positions, true);
+        if (!rotate) buffer_positions = nullptr;   // the caller's array stays unwrapped: never hand it out as the window
+        wrapped_on_device = true;
+    } else {
+        mark_window_changed();
+    }
+}
+
+void Trajectory_numpy::materialise_host_positions() {
+    if (!wrapped_on_device) return;
+    const size_t nval = static_cast<size_t>(n_timesteps) * natoms * 3;
+    if (own_pos.size() < nval) own_pos.resize(nval > 0 ? nval : 1);
+    download_window(own_pos.data());
+    buffer_positions = own_pos.data();
 }
 
 // per-type centre of mass of the caller's (unwrapped, unrotated) arrays: running mean in atom order,

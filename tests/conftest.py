@@ -43,6 +43,28 @@ def live_case(name):
 
 LIVE_CASES = ["tri_wrap", "tri_npt", "ortho_unwrapped", "tri_bigtilt", "ragged"]
 
+# systems of a few thousand atoms through the compiled reference (tests/golden/make_golden.py: TILE_CASES)
+TILE_CASES = {
+    "tri_tile3": (41, (16, 16, 12), 3, True, 5),
+    "ortho_tile_dense": (42, (12, 12, 12), 2, False, 5),
+    "ortho_tile_rmin": (43, (12, 12, 12), 1, False, 5),
+}
+
+
+def tile_case(name):
+    """Inputs regenerated with synth.small_case (their sha256 is part of the fixture), results from the fixture."""
+    import hashlib
+    from analisi_b200 import synth
+    z = load_golden("live_reference_tile.npz")
+    pre = name + "/"
+    d = {k[len(pre):]: z[k] for k in z.files if k.startswith(pre)}
+    seed, cells, ntypes, tri, nframes = TILE_CASES[name]
+    pos, box, types = synth.small_case(seed, cells, 1.1, ntypes, tri, nframes, "parity")
+    sha = np.frombuffer(hashlib.sha256(np.ascontiguousarray(pos).tobytes()).digest(), dtype=np.uint8)
+    assert np.array_equal(sha, d["pos_in_sha256"]), "synth.small_case no longer reproduces the fixture's input: regenerate it"
+    d["pos_in"], d["box_lammps"], d["types"] = pos, box, types
+    return d
+
 
 @pytest.fixture(scope="session")
 def ctx():

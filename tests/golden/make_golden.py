@@ -165,6 +165,41 @@ def live_reference_cases(m):
     np.savez_compressed(os.path.join(HERE, "live_reference.npz"), **flat)
 
 
+TILE_CASES = {
+    # name: (seed, cells, ntypes, triclinic, nframes, (rmin, rmax, nbin, tmax, skip, every, ntimesteps, primo))
+    # C3-shaped, reduced: 3 types, triclinic, 3072 atoms -> the TILE kernel's triclinic path, sparse binning
+    "tri_tile3": (41, (16, 16, 12), 3, True, 5, (0.0, 4.0, 64, 2, 2, 1, 4, 0)),
+    # C2-shaped, reduced: cubic, 39 % of the pairs in range -> the dense tile kernel (two-floor binning, long rows)
+    "ortho_tile_dense": (42, (12, 12, 12), 2, False, 5, (0.0, 6.0, 96, 2, 2, 1, 4, 0)),
+    # the same with rmin > 0 a multiple of dr (c0 = -10: guard bins below bin 0)
+    "ortho_tile_rmin": (43, (12, 12, 12), 1, False, 5, (0.6, 6.6, 100, 2, 2, 1, 4, 0)),
+}
+
+
+def live_reference_tile_cases(m):
+    """Systems of a few thousand atoms through the compiled reference, so that the tile kernel (more than 256 device
+    slots) is pinned by the reference itself and not only by the oracle.  The positions are not stored: they are
+    synth.small_case(seed, ...) again (numpy Generator streams are stable), with their sha256 kept to say so loudly if
+    that ever changes."""
+    import hashlib
+    out = {}
+    for name, (seed, cells, ntypes, tri, nframes, gofrt) in TILE_CASES.items():
+        pos, box, types = synth.small_case(seed, cells, 1.1, ntypes, tri, nframes, "parity")
+        raw_types = (types * 3 + 2).astype(np.int32)
+        fmt = m.BoxFormat.LammpsTriclinic if tri else m.BoxFormat.LammpsOrtho
+        rmin, rmax, nbin, tmax, skip, every, nts, primo = gofrt
+        counts, v, rpos, rbox, rtypes = ref_counts(m, pos, box, raw_types, fmt, True, rmin, rmax, nbin, tmax, skip, every, nts,
+                                                   primo)
+        out[name + "/counts"] = counts
+        out[name + "/vdata"] = v
+        out[name + "/pos_in_sha256"] = np.frombuffer(hashlib.sha256(np.ascontiguousarray(pos).tobytes()).digest(), dtype=np.uint8)
+        out[name + "/pos_ref_sha256"] = np.frombuffer(hashlib.sha256(np.ascontiguousarray(rpos).tobytes()).digest(), dtype=np.uint8)
+        out[name + "/box_internal"] = rbox
+        out[name + "/type_ids"] = rtypes
+        out[name + "/params"] = np.array(gofrt, dtype=np.float64)
+    np.savez_compressed(os.path.join(HERE, "live_reference_tile.npz"), **out)
+
+
 def cell_vectors_rotation(m):
     """Trajectory_numpy with BoxFormat.CellVectors and general (rotated) cells: the reference QR-rotates
     cell, positions and velocities into the LAMMPS frame (lib/include/triclinic.h:10-73 with Eigen's
@@ -251,6 +286,7 @@ def main():
     gofr_notebook(m)
     min_image_and_pbc(m)
     live_reference_cases(m)
+    live_reference_tile_cases(m)
     cell_vectors_rotation(m)
     qr_many(m)
     cli_golden_text()

@@ -236,6 +236,65 @@ def test_cli_c1_bundled_trajectory(host, tmp_path):
     assert got == want
 
 
+def test_cli_c1_against_the_reference_itself(host, tmp_path):
+    """BASELINE.json configs[0] against the UNMODIFIED reference: tests/golden/c1_reference.* holds what the compiled
+    reference's own BlockAverage<Gofrt> chain produced for `analisi -i tests/data/lammps.bin -g 200 -F 0.7 3.5`
+    (756 s on one core; tests/golden/make_c1_golden.py).  All 378 x 6 x 200 means and variances of the GPU chain --
+    CLI text and the python block-average object -- are compared with it."""
+    import hashlib
+    import json
+    cli, pa = host
+    path = os.path.join(REFDATA, "lammps.bin")
+    if not os.path.exists(path):
+        pytest.skip("tests/_refdata/lammps.bin not present")
+    gold = np.load(os.path.join(GOLDEN, "c1_reference.npz"))
+    meta = json.load(open(os.path.join(GOLDEN, "c1_reference.json")))
+    n_b, s, nbin = 20, 378, 200
+    S1, S2 = gold["S1"].astype(np.float64), gold["S2"].astype(np.float64)
+    ref_mean = S1 / (n_b * s)
+    ref_var = (S2 - S1 * S1 / n_b) / (n_b * (n_b - 1) * s ** 2)
+    # (the reconstruction reproduces the reference's doubles: checked on the lags stored in full)
+    for k, lag in enumerate(gold["pin_lags"]):
+        np.testing.assert_allclose(ref_mean[lag], gold["pin_mean"][k], rtol=1e-12, atol=0)
+        np.testing.assert_allclose(ref_var[lag], gold["pin_var"][k], rtol=1e-10, atol=1e-18)
+
+    # ---- the python object: full-precision means and variances of the mean
+    tr = pa.Traj(path)
+    tr.setWrapPbc(True)
+    ba = pa.GofrtBlockAverage_lammps(tr, n_b)
+    ba.calculate(0.7, 3.5, nbin, 0, 1, 1, 1, False)
+    mean, var = ba.mean(), ba.variance()
+    assert mean.shape == (s, 6, nbin) == tuple(meta["shape"])
+    # the reference adds incr = 1/378 once per counted pair, the GPU path multiplies the count by incr: both are
+    # within a few ulp of count/378, the difference must stay at rounding level
+    np.testing.assert_allclose(mean, ref_mean, rtol=2e-12, atol=0)
+    np.testing.assert_allclose(var, ref_var, rtol=1e-9, atol=1e-16)
+    for k, lag in enumerate(gold["pin_lags"]):
+        np.testing.assert_allclose(mean[lag], gold["pin_mean"][k], rtol=2e-12, atol=0)
+        np.testing.assert_allclose(var[lag], gold["pin_var"][k], rtol=1e-9, atol=1e-16)
+    # integer sufficient statistics: sum of the block counts, exactly
+    assert np.array_equal(np.round(mean * (n_b * s)), S1)
+
+    # ---- the CLI text: 6 significant digits per value; a value within 1e-12 of a rounding tie may print differently
+    r = subprocess.run([cli, "-i", path, "-g", "200", "-F", "0.7", "3.5"], stdout=subprocess.PIPE, stderr=subprocess.PIPE,
+                       text=True, cwd=str(tmp_path), timeout=1500)
+    assert r.returncode == 0, r.stderr[-2000:]
+    got = _rows(r.stdout)
+    want = _cli_text(ref_mean, ref_var, s, 1, nbin, 6)
+    assert len(got) == len(want) == s * nbin
+    differing = [(a, b) for a, b in zip(got, want) if a != b]
+    assert len(differing) <= 8, differing[:3]
+    for a, b in differing:
+        np.testing.assert_allclose(np.array(a.split(), dtype=float), np.array(b.split(), dtype=float), rtol=2e-6, atol=0)
+    header = [l for l in r.stdout.split("\n") if l.startswith("#")]
+    assert header == [l for l in meta["columns_description"].split("\n") if l.startswith("#")]
+    if not differing:
+        # identical rows: then the whole text is the reference's, byte for byte
+        text = meta["columns_description"].rstrip("\n") + "\n" + "".join(
+            l + "\n" + ("\n" if (i + 1) % nbin == 0 else "") for i, l in enumerate(got))
+        assert hashlib.sha256(text.encode()).hexdigest() == meta["cli_text_sha256"]
+
+
 @pytest.mark.parametrize("device_blocks", ["1", "0"], ids=["MediaVarDevice", "MediaVar"])
 @pytest.mark.parametrize("kind", ["numpy", "lammps"])
 def test_block_average_binding_vs_oracle(host, tmp_path, kind, device_blocks, monkeypatch):

@@ -6,7 +6,7 @@ import pytest
 
 import oracle
 from analisi_b200 import cabi, synth
-from conftest import LIVE_CASES, live_case, load_golden
+from conftest import LIVE_CASES, TILE_CASES, live_case, load_golden, tile_case
 
 pytestmark = pytest.mark.gpu
 
@@ -64,7 +64,7 @@ def test_gofr_notebook_golden(ctx, no_small):
                        skip=int(skip), options=no_small)
     assert np.array_equal(c, z["counts"])
     assert st["jobs_fast"] == st["jobs"]  # wrapped orthorhombic input: single-pass minimum image proven
-    assert st["kernel_modes"] & 0xff in (1 << 3, 1 << 4)   # ... binned by a safe-zone kernel
+    assert st["kernel_modes"] & 0xff in (1 << 3, 1 << 4, 1 << 5)   # ... binned by a safe-zone kernel
     assert ran_small(st) == (no_small == 0)
 
 
@@ -115,6 +115,35 @@ def test_live_reference_cases(ctx, name, options, no_small):
         assert st["jobs_fast"] == 0
     if options == cabi.OPT_NO_SAFE:
         assert st["kernel_modes"] & (1 << 3) == 0
+
+
+@pytest.mark.parametrize("name", sorted(TILE_CASES))
+@pytest.mark.parametrize("options", [0, cabi.OPT_FORCE_GENERAL, cabi.OPT_NO_SAFE, cabi.OPT_SAFE2, cabi.OPT_SAFE2 | cabi.OPT_SKEW,
+                                     cabi.OPT_SAFE2 | cabi.OPT_DENSE | cabi.OPT_NO_UBOX, cabi.OPT_DENSE, cabi.OPT_SPARSE,
+                                     cabi.OPT_NO_UBOX, cabi.OPT_AGGREGATE])
+def test_live_reference_tile_cases(ctx, name, options):
+    """Fixtures of a few thousand atoms computed by the compiled reference (C3-shaped: 3 types, triclinic; C2-shaped:
+    cubic, dense): the TILE kernel in every binning mode, bit-exact against the reference's own counts."""
+    import hashlib
+    d = tile_case(name)
+    rmin, rmax, nbin, tmax, skip, every, nts, primo = d["params"]
+    ids, nt = d["type_ids"], int(d["type_ids"].max()) + 1
+    pos = d["pos_in"].copy()
+    ctx.pbc_wrap(pos, d["box_internal"])
+    sha = np.frombuffer(hashlib.sha256(np.ascontiguousarray(pos).tobytes()).digest(), dtype=np.uint8)
+    assert np.array_equal(sha, d["pos_ref_sha256"])   # the GPU wrap gives the reference's wrapped positions
+    c, st = gpu_counts(ctx, pos, d["box_internal"], ids, nt, rmin, rmax, int(nbin), int(tmax), int(nts),
+                       primo=int(primo), skip=int(skip), every=int(every), options=options)
+    assert np.array_equal(c, d["counts"])
+    assert not ran_small(st)
+    if options & cabi.OPT_SAFE2 and (name.startswith("ortho_tile") or options & cabi.OPT_DENSE):
+        assert st["kernel_modes"] & (1 << 5), "the dense two-floor kernel (MODE_SAFE2) was asked for here"
+    if not options & cabi.OPT_SAFE2:
+        assert st["kernel_modes"] & (1 << 5) == 0
+    incr = cabi.gofrt_incr(int(nts), int(skip))
+    v, ref = c * incr, d["vdata"]
+    nz = ref != 0
+    assert (np.abs(v[nz] - ref[nz]) <= REL_TOL * np.abs(ref[nz])).all()
 
 
 @pytest.mark.parametrize("name", LIVE_CASES)
@@ -169,7 +198,7 @@ def test_multi_tile_random(ctx, triclinic):
     assert np.array_equal(c2, co)
     c3, st3 = gpu_counts(ctx, pos, bi, types, 2, *args, skip=2, options=cabi.OPT_NO_SAFE)
     assert np.array_equal(c3, co) and st3["kernel_modes"] == 1   # 1320 atoms: never the small-system kernel
-    for opt, bit in ((cabi.OPT_DENSE, 4), (cabi.OPT_SPARSE, 3)):
+    for opt, bit in ((cabi.OPT_DENSE, 4), (cabi.OPT_DENSE | cabi.OPT_SAFE2, 5), (cabi.OPT_SPARSE, 3)):
         c4, st4 = gpu_counts(ctx, pos, bi, types, 2, *args, skip=2, options=opt)
         assert np.array_equal(c4, co) and st4["kernel_modes"] == 1 << bit
     # every ordered pair with d2 in range lands somewhere: lag 0, self slot, bin 0 holds exactly N per origin
@@ -274,10 +303,10 @@ def test_guarded_rows_and_fallback(ctx, rmin, rmax, nbin, expect_safe, no_small)
     c, st = gpu_counts(ctx, pos, bi, types, 2, rmin, rmax, nbin, 3, 3, options=no_small)
     assert ran_small(st) == (no_small == 0)   # 252 atoms: four warps per job
     assert np.array_equal(c, ref)
-    safe_ran = bool(st["kernel_modes"] & ((1 << 3) | (1 << 4)))
+    safe_ran = bool(st["kernel_modes"] & ((1 << 3) | (1 << 4) | (1 << 5)))
     assert safe_ran == expect_safe
     c2, st2 = gpu_counts(ctx, pos, bi, types, 2, rmin, rmax, nbin, 3, 3, options=cabi.OPT_NO_SAFE | no_small)
-    assert np.array_equal(c2, ref) and not (st2["kernel_modes"] & ((1 << 3) | (1 << 4)))
+    assert np.array_equal(c2, ref) and not (st2["kernel_modes"] & ((1 << 3) | (1 << 4) | (1 << 5)))
     c3, st3, e3 = gpu_counts(ctx, pos, bi, types, 2, rmin, rmax, nbin, 3, 3, edges=True, options=no_small)
     assert np.array_equal(c3, ref) and e3 == eref
     for opt in (cabi.OPT_DENSE, cabi.OPT_SPARSE):

@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 
 import oracle
-from conftest import LIVE_CASES, REFERENCE, live_case, load_golden
+from conftest import LIVE_CASES, REFERENCE, TILE_CASES, live_case, load_golden, tile_case
 
 
 def test_gofr_numpy_golden():
@@ -210,3 +210,22 @@ def test_msd_cli_golden(name, skip, lmax, cm_msd, cm_self):
     mean, var = oracle.mediavar(np.array(blocks))
     gold = open(os.path.join(GOLDEN, "cli_%s.txt" % name)).read().rstrip("\n").split("\n")
     assert msd_text(mean, var) == gold
+
+
+@pytest.mark.parametrize("name", sorted(TILE_CASES))
+def test_live_reference_tile_cases(name):
+    """A few thousand atoms (C3- and C2-shaped, reduced) through the compiled reference: the oracle reproduces its
+    wrapped positions and its counts."""
+    import hashlib
+    d = tile_case(name)
+    rmin, rmax, nbin, tmax, skip, every, nts, primo = d["params"]
+    from analisi_b200 import synth
+    bi = synth.lammps_rows_to_internal(d["box_lammps"])
+    assert np.array_equal(bi, d["box_internal"])
+    pos = oracle.pbc_wrap(d["pos_in"], bi)
+    sha = np.frombuffer(hashlib.sha256(np.ascontiguousarray(pos).tobytes()).digest(), dtype=np.uint8)
+    assert np.array_equal(sha, d["pos_ref_sha256"])
+    ids = d["type_ids"]
+    c = oracle.counts(pos, bi, ids, rmin, rmax, int(nbin), int(tmax), int(nts), primo=int(primo), skip=int(skip),
+                      every=int(every), ntypes=int(ids.max()) + 1)
+    assert np.array_equal(c, d["counts"])
