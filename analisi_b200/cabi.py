@@ -15,7 +15,7 @@ LIB_PATH = os.environ.get("AGOFRT_LIB", os.path.join(_HERE, "libagofrt.so"))  # 
 OK = 0
 ERR_ARG, ERR_CUDA, ERR_WINDOW, ERR_NCCL, ERR_NONFINITE, ERR_TOO_LARGE, ERR_INTERNAL = -1, -2, -3, -4, -5, -6, -7
 OPT_EDGES, OPT_FORCE_GENERAL, OPT_NO_AGGREGATE, OPT_AGGREGATE, OPT_NO_SAFE, OPT_DENSE, OPT_SPARSE, OPT_NO_UBOX = 1, 2, 4, 8, 16, 32, 64, 128
-OPT_NO_SMALL, OPT_ON_DEVICE, OPT_SMALL, OPT_SAFE2, OPT_SKEW = 256, 512, 1024, 2048, 4096
+OPT_NO_SMALL, OPT_ON_DEVICE, OPT_SMALL, OPT_SAFE2, OPT_SKEW, OPT_EXPLICIT_JOBS = 256, 512, 1024, 2048, 4096, 8192
 SMALL_DEFAULT_SLOTS, SMALL_MAX_SLOTS = 256, 512   # kSmallDefault, kSmallMax of the library
 MODE_BIT_SMALL = 1 << 8   # Stats.kernel_modes: the small-system kernel ran
 COMM_ID_BYTES = 128

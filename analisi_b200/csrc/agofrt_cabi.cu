@@ -1450,8 +1450,8 @@ extern "C" int agofrt_block(agofrt_plan *p, size_t primo, unsigned ntimesteps, u
 
     // ---- the (lag, origin) jobs, in the reference's loop order (calculatemultithread.h:114-115) ----
     std::vector<Job> jobs_fast, jobs_gen;
-    uint64_t njobs = 0;
-    bool all_fast = false;
+    uint64_t njobs = 0, n_fast = 0, n_gen = 0;
+    bool all_fast = false, implicit = false;
     if (ntimesteps > 0 && leff > 0) {
         // the last frame the loops really touch: last origin + last lag
         const size_t last = primo + static_cast<size_t>((ntimesteps - 1) / skip) * skip +
@@ -1469,16 +1469,28 @@ extern "C" int agofrt_block(agofrt_plan *p, size_t primo, unsigned ntimesteps, u
         const size_t expect = static_cast<size_t>((leff + every - 1) / every) * ((ntimesteps + skip - 1) / skip);
         if (expect >= 0xF0000000ull)   // (the same limit as on the work units below, before any memory is asked for)
             return fail(AGOFRT_ERR_ARG, "too many work units in one block (%zu (lag, origin) jobs)", expect);
-        (may_fast ? jobs_fast : jobs_gen).reserve(expect);
-        for (unsigned tl = 0; tl < leff; tl += every)
-            for (unsigned im = 0; im < ntimesteps; im += skip) {
-                const size_t fi = primo + im - t->first_frame;
-                Job j{static_cast<int>(fi), static_cast<int>(fi + tl), static_cast<int>(tl)};
-                const bool fast = all_fast || (may_fast && job_is_single_pass(t, fi, fi + tl));
-                (fast ? jobs_fast : jobs_gen).push_back(j);
-                ++njobs;
-            }
+        // When every job takes the same kernel (the whole frame range proven single-pass, or the general kernel
+        // forced) the list is regular -- job k = (lag k / origins, origin k % origins) -- and the kernels derive it
+        // themselves: nothing is built or uploaded (C1: 142 884 jobs per block).  Otherwise: an explicit list per kernel.
+        implicit = (all_fast || !may_fast) && !(options & AGOFRT_OPT_EXPLICIT_JOBS);
+        if (implicit) {
+            njobs = expect;
+            (all_fast ? n_fast : n_gen) = expect;
+        } else {
+            (may_fast ? jobs_fast : jobs_gen).reserve(expect);
+            for (unsigned tl = 0; tl < leff; tl += every)
+                for (unsigned im = 0; im < ntimesteps; im += skip) {
+                    const size_t fi = primo + im - t->first_frame;
+                    Job j{static_cast<int>(fi), static_cast<int>(fi + tl), static_cast<int>(tl)};
+                    const bool fast = all_fast || (may_fast && job_is_single_pass(t, fi, fi + tl));
+                    (fast ? jobs_fast : jobs_gen).push_back(j);
+                    ++njobs;
+                }
+            n_fast = jobs_fast.size();
+            n_gen = jobs_gen.size();
+        }
     }
+    const unsigned norig = skip ? (ntimesteps + skip - 1) / skip : 0;
     const uint64_t n2 = static_cast<uint64_t>(t->natoms) * t->natoms;
     const bool nothing = njobs == 0 || t->natoms == 0 || p->empty_range || len == 0;
 
@@ -1510,6 +1522,7 @@ extern "C" int agofrt_block(agofrt_plan *p, size_t primo, unsigned ntimesteps, u
                        (t->npad <= kSmallDefault || ((options & AGOFRT_OPT_SMALL) && t->npad <= kSmallMax));
     const int nsub = small ? (t->npad + 32 * kIPT - 1) / (32 * kIPT) : 1;   // warps per job
     std::vector<SmallUnit> units_fast, units_gen;
+    uint64_t nu_fast = 0, nu_gen = 0, small_each = 0;
     if (small && !nothing) {
         // a unit should dwarf the merge of the CTA's histogram rows that ends it (rowlen words scanned,
         // up to as many global atomics), keep every warp busy, and there should be several units per CTA
@@ -1519,20 +1532,30 @@ extern "C" int agofrt_block(agofrt_plan *p, size_t primo, unsigned ntimesteps, u
         const uint64_t wave = static_cast<uint64_t>(kThreads / 32 / nsub);   // jobs a CTA works on at a time
         uint64_t chunk = std::max<uint64_t>(std::max(by_merge, by_ctas), wave);
         chunk = std::min<uint64_t>((chunk + wave - 1) / wave * wave, 65536);   // a unit's counts stay far below 2^32
-        for (int pass = 0; pass < 2; ++pass) {
-            const std::vector<Job> &list = pass == 0 ? jobs_fast : jobs_gen;
-            std::vector<SmallUnit> &units = pass == 0 ? units_fast : units_gen;
-            size_t a = 0;
-            while (a < list.size()) {
-                size_t b = a;
-                while (b < list.size() && list[b].tout == list[a].tout) ++b;   // jobs are in lag-major order
-                const uint64_t run = b - a, nch = (run + chunk - 1) / chunk;
-                const uint64_t each = ((run + nch - 1) / nch + wave - 1) / wave * wave;   // equal shares, whole rounds
-                for (size_t c0 = a; c0 < b; c0 += each)
-                    units.push_back(SmallUnit{static_cast<int>(c0), static_cast<int>(std::min<size_t>(each, b - c0)),
-                                              list[a].tout});
-                a = b;
+        if (implicit) {
+            // equal shares of the origins of one lag, whole rounds of the CTA's warp groups; unit u = (lag u / units_per_lag, share)
+            const uint64_t nch = (norig + chunk - 1) / chunk;
+            small_each = ((norig + nch - 1) / nch + wave - 1) / wave * wave;
+            const uint64_t upl = (norig + small_each - 1) / small_each;
+            (all_fast ? nu_fast : nu_gen) = upl * ((leff + every - 1) / every);
+        } else {
+            for (int pass = 0; pass < 2; ++pass) {
+                const std::vector<Job> &list = pass == 0 ? jobs_fast : jobs_gen;
+                std::vector<SmallUnit> &units = pass == 0 ? units_fast : units_gen;
+                size_t a = 0;
+                while (a < list.size()) {
+                    size_t b = a;
+                    while (b < list.size() && list[b].tout == list[a].tout) ++b;   // jobs are in lag-major order
+                    const uint64_t run = b - a, nch = (run + chunk - 1) / chunk;
+                    const uint64_t each = ((run + nch - 1) / nch + wave - 1) / wave * wave;   // equal shares, whole rounds
+                    for (size_t c0 = a; c0 < b; c0 += each)
+                        units.push_back(SmallUnit{static_cast<int>(c0), static_cast<int>(std::min<size_t>(each, b - c0)),
+                                                  list[a].tout});
+                    a = b;
+                }
             }
+            nu_fast = units_fast.size();
+            nu_gen = units_gen.size();
         }
     }
 
@@ -1602,7 +1625,7 @@ extern "C" int agofrt_block(agofrt_plan *p, size_t primo, unsigned ntimesteps, u
             CU(cudaMalloc(&pd.ghist, len * sizeof(unsigned long long)));
             pd.ghist_len = len;
         }
-        const size_t njall = jobs_fast.size() + jobs_gen.size();
+        const size_t njall = jobs_fast.size() + jobs_gen.size();   // (0 with implicit jobs)
         if (njall > pd.jobs_cap) {
             cudaFree(pd.jobs);
             pd.jobs = nullptr;
@@ -1637,10 +1660,10 @@ extern "C" int agofrt_block(agofrt_plan *p, size_t primo, unsigned ntimesteps, u
         if (!nothing) {
             const int g = first_rank + i;
             for (int pass = 0; pass < 2; ++pass) {
-                const std::vector<Job> &list = pass == 0 ? jobs_fast : jobs_gen;
-                if (list.empty()) continue;
+                const uint64_t nlist = pass == 0 ? n_fast : n_gen;
+                if (nlist == 0) continue;
                 const std::vector<SmallUnit> &ulist = pass == 0 ? units_fast : units_gen;
-                const uint64_t units = small ? ulist.size() : list.size() * per_job;
+                const uint64_t units = small ? (pass == 0 ? nu_fast : nu_gen) : nlist * per_job;
                 uint64_t ub = 0, ue = 0;
                 agofrt_shard_range(units, g, world, &ub, &ue);
                 if (ue <= ub) continue;
@@ -1651,6 +1674,12 @@ extern "C" int agofrt_block(agofrt_plan *p, size_t primo, unsigned ntimesteps, u
                 pp.type_pad = td.type_pad;
                 pp.type_start = td.type_start;
                 pp.jobs = pd.jobs + (pass == 0 ? 0 : jobs_fast.size());
+                pp.imp = implicit ? 1 : 0;
+                pp.imp_f0 = static_cast<int>(primo - t->first_frame);
+                pp.imp_norig = static_cast<int>(norig);
+                pp.imp_skip = static_cast<int>(skip);
+                pp.imp_every = static_cast<int>(every);
+                pp.imp_each = static_cast<int>(small_each);
                 pp.ghist = pd.ghist;
                 pp.edges = pd.edges;
                 pp.counter = pd.counter;
@@ -1708,7 +1737,12 @@ extern "C" int agofrt_block(agofrt_plan *p, size_t primo, unsigned ntimesteps, u
                 if (small) {
                     modes_used |= 1u << 8;
                     uint64_t nj = 0;
-                    for (uint64_t u = ub; u < ue; ++u) nj += static_cast<uint64_t>(ulist[u].count);
+                    if (implicit) {
+                        const uint64_t upl = (norig + small_each - 1) / small_each;
+                        for (uint64_t u = ub; u < ue; ++u) nj += std::min<uint64_t>(small_each, norig - (u % upl) * small_each);
+                    } else {
+                        for (uint64_t u = ub; u < ue; ++u) nj += static_cast<uint64_t>(ulist[u].count);
+                    }
                     my_pairs += nj * n2;
                 } else {
                     // pair evaluations of this shard, counted on real atoms: units are equal-sized
@@ -1792,7 +1826,7 @@ extern "C" int agofrt_block(agofrt_plan *p, size_t primo, unsigned ntimesteps, u
         stats->pair_evals = nothing ? 0 : my_pairs;
         stats->pair_evals_total = njobs * n2;
         stats->jobs = njobs;
-        stats->jobs_fast = jobs_fast.size();
+        stats->jobs_fast = n_fast;
         stats->launches = launches;
         stats->ndev_local = static_cast<uint32_t>(nloc);
         stats->world = static_cast<uint32_t>(world);

@@ -448,6 +448,27 @@ size_t pair_kernel_smem_bytes(int ntypes, int nbin, int nhi, int glo, bool edges
 
 constexpr int kWarpsPerCta = kThreads / 32;
 
+// the (lag, origin) job / the small-system work unit with this index: read from the list, or derived (implicit jobs)
+__device__ __forceinline__ Job job_at(const PairParams &p, unsigned int k) {
+    if (!p.imp) return p.jobs[k];
+    const unsigned int lag = k / static_cast<unsigned int>(p.imp_norig), o = k - lag * static_cast<unsigned int>(p.imp_norig);
+    Job j;
+    j.fi = p.imp_f0 + static_cast<int>(o) * p.imp_skip;
+    j.tout = static_cast<int>(lag) * p.imp_every;
+    j.fj = j.fi + j.tout;
+    return j;
+}
+__device__ __forceinline__ SmallUnit unit_at(const PairParams &p, unsigned int u) {
+    if (!p.imp) return p.units[u];
+    const unsigned int upl = static_cast<unsigned int>((p.imp_norig + p.imp_each - 1) / p.imp_each);
+    const unsigned int lag = u / upl, share = u - lag * upl;
+    SmallUnit un;
+    un.begin = static_cast<int>(lag) * p.imp_norig + static_cast<int>(share) * p.imp_each;
+    un.count = min(p.imp_each, p.imp_norig - static_cast<int>(share) * p.imp_each);
+    un.lag = static_cast<int>(lag) * p.imp_every;
+    return un;
+}
+
 struct PairConst {
     BoxRegs box;
     double nLx, nLy, nLz;   // -(2*l_half), exact
@@ -881,7 +902,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) pair_kernel(const PairPa
         const int jc = static_cast<int>(u % static_cast<unsigned int>(p.n_jchunks));
         const unsigned int u2 = u / static_cast<unsigned int>(p.n_jchunks);
         const int itile = static_cast<int>(u2 % static_cast<unsigned int>(p.n_itiles));
-        const Job job = p.jobs[u2 / static_cast<unsigned int>(p.n_itiles)];
+        const Job job = job_at(p, u2 / static_cast<unsigned int>(p.n_itiles));
 
         const int jbeg = jc * p.jchunk;
         const int jend = min(jbeg + p.jchunk, p.npad);
@@ -1162,11 +1183,11 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) pair_small_kernel(const 
         const unsigned int u = s_sched[0];
         __syncthreads();
         if (u >= p.unit_end) break;
-        const SmallUnit un = p.units[u];
+        const SmallUnit un = unit_at(p, u);
 
         if (working) {
             for (int jb = grp; jb < un.count; jb += G) {
-                const Job job = p.jobs[un.begin + jb];
+                const Job job = job_at(p, static_cast<unsigned int>(un.begin + jb));
                 if (!UBOX) {
                     const double *bx = p.box + static_cast<size_t>(job.fi) * 6;
                     c.box.lhx = __ldg(bx + 0);
@@ -1212,21 +1233,37 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) pair_small_kernel(const 
                     unsigned int row[kIPT];
 #pragma unroll
                     for (int k = 0; k < kIPT; ++k) row[k] = s_rowtab[ti[k] * nt + ty];
-                    // [lo,hi) = before | overlap with this warp's own atoms | after   (all multiples of kPadGroup)
-                    const int da = min(max(wi0, lo), hi);
-                    const int db = min(max(wi0 + kSubTile, lo), hi);
+                    // every pair, the atom with itself included, goes to the "different atoms" row here: with a few
+                    // dozen atoms EVERY group holds some of the warp's own atoms, and a per-pair i == j row select
+                    // would cost three instructions on each of the N^2 pairs; the N self pairs are moved below
 #pragma unroll 1
-                    for (int j = lo; j < da; j += kJU)
+                    for (int j = lo; j < hi; j += kJU)
                         process_group<TRI, FAST, MODE, false>(p, c, xi, yi, zi, ii, row, slice_addr, jrow_bytes, j, j,
                                                               s_thr2, s_thrf, s_hist, self_off, edges, wrap_ok);
-#pragma unroll 1
-                    for (int j = da; j < db; j += kJU)
-                        process_group<TRI, FAST, MODE, true>(p, c, xi, yi, zi, ii, row, slice_addr, jrow_bytes, j, j,
-                                                             s_thr2, s_thrf, s_hist, self_off, edges, wrap_ok);
-#pragma unroll 1
-                    for (int j = db; j < hi; j += kJU)
-                        process_group<TRI, FAST, MODE, false>(p, c, xi, yi, zi, ii, row, slice_addr, jrow_bytes, j, j,
-                                                              s_thr2, s_thrf, s_hist, self_off, edges, wrap_ok);
+                }
+                // the self pairs (i, frame fi) - (i, frame fj): from the "different atoms" row of the atom's type to its
+                // "same atom" row, at the exact bin of the threshold table (where the pass above -- fast path plus
+                // correction, or a bracket search -- has counted them)
+#pragma unroll
+                for (int k = 0; k < kIPT; ++k) {
+                    if (ii[k] >= p.npad) continue;
+                    double dx = __dsub_rn(xi[k], slice[ii[k]]);
+                    double dy = __dsub_rn(yi[k], slice[srow + ii[k]]);
+                    double dz = __dsub_rn(zi[k], slice[2 * srow + ii[k]]);
+                    if (FAST)
+                        min_image_single<TRI>(dx, dy, dz, c.box, c.nLx, c.nLy, c.nLz);
+                    else
+                        wrap_ok &= min_image_general<TRI>(dx, dy, dz, c.box);
+                    const double d2 = d2_of(dx, dy, dz);
+                    if ((d2 >= s_thr2[1].x) && (d2 < s_thr2[nbin].y)) {   // false for the NaN of a ghost slot
+                        int g = static_cast<int>(bin_guess1(d2, p.inv_dr, p.c0, static_cast<unsigned int>(nbin) + 2u)) - 1;
+                        g = min(max(g, 0), nbin - 1);
+                        while (d2 < s_thr2[g + 1].x) --g;
+                        while (d2 >= s_thr2[g + 1].y) ++g;
+                        unsigned int *w = s_hist + s_rowtab[ti[k] * nt + ti[k]] + g;
+                        atomicAdd(w, 0xffffffffu);
+                        atomicAdd(w + self_off, 1u);
+                    }
                 }
             }
         }

@@ -78,6 +78,10 @@ struct PairParams {
     int skew;                         // MODE_SAFE2: half of the warps start every tile with a dummy binning run (phase_skew)
     float inv_lo, inv_hi, bias0, smax;  // MODE_SAFE2: inv_dr * (1 -+ 2^-20), 1.5*2^23 + c0 (c0 an integer), clamp of sqrt(d2)
     unsigned hlo, hspan, hhi;         // candidate tests on the high word of d2 (hhi = hlo + hspan)
+    // implicit jobs (imp != 0; jobs / units are then not read): job k = lag (k / imp_norig) * imp_every, origin frame
+    // imp_f0 + (k % imp_norig) * imp_skip; pair_small_kernel: unit u = share (u % units_per_lag) of imp_each origins
+    // of lag u / units_per_lag
+    int imp, imp_f0, imp_norig, imp_skip, imp_every, imp_each;
 };
 
 size_t pair_kernel_smem_bytes(int ntypes, int nbin, int nhi, int glo, bool edges);

@@ -525,7 +525,7 @@ def main():
     # trajectory (box conversion, type compaction, upload from pageable memory -- the frames are dealt to the ranks and
     # exchanged GPU to GPU --, wrap on the GPUs), construct Gofrt, reset, calculate, read the result array back.
     if args.no_e2e:
-        e2e_ms, e2e_h2d, e2e_d2h = float('nan'), 0, 0
+        e2e_ms, e2e_h2d, e2e_d2h, e2e_parts = float('nan'), 0, 0, {}
     else:
         pa = load_pyanalisi(local_rank)
         if world > 1:
@@ -535,12 +535,24 @@ def main():
         vel = np.zeros_like(pos_all)   # the interface wants velocities; g(r,t) never reads them
         raw_types = np.ascontiguousarray(types, dtype=np.int32)
 
+        e2e_parts = {}
+
         def e2e_step():
+            t0 = time.perf_counter()
             tr_py = pa.Trajectory(pos_all, vel, raw_types, box_lammps_all, fmt, True, False)
+            t1 = time.perf_counter()
             g = pa.Gofrt(tr_py, w.rmin, w.rmax, w.nbin, w.tmax, 1, w.skip, w.every, False)
             g.reset(nts)
+            t2 = time.perf_counter()
             g.calculate(primo)
-            return np.array(g, copy=True)
+            t3 = time.perf_counter()
+            v = np.array(g, copy=True)
+            st = g.last_stats()
+            del g, tr_py
+            t4 = time.perf_counter()
+            e2e_parts.update(trajectory_ms=(t1 - t0) * 1e3, gofrt_ctor_reset_ms=(t2 - t1) * 1e3, calculate_ms=(t3 - t2) * 1e3,
+                             calculate_device_ms=st["total_ms"], result_and_teardown_ms=(t4 - t3) * 1e3)
+            return v
 
         v_e = e2e_step()   # warm-up: module load, communicator, device allocations
         barrier()
@@ -604,7 +616,7 @@ def main():
         "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic", "config": config,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": e2e_h2d, "d2h_bytes_per_step": e2e_d2h,
-                "ms_per_step": e2e_ms / args.steps,
+                "ms_per_step": e2e_ms / args.steps, "last_step_breakdown_ms": {k: round(v, 2) for k, v in e2e_parts.items()},
                 "path": "pyanalisi.Trajectory(pos, vel, types, box, fmt, wrap=True) + Gofrt(...).reset().calculate() + np.array(g), "
                         "from pageable numpy arrays every step; H2D per rank = its share of the %d frames (%d bytes in all), "
                         "shares exchanged GPU to GPU" % (nframes_traj, pos_all.nbytes)},

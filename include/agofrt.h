@@ -178,7 +178,8 @@ enum {
                                       to four warps per job, where it beats the tile kernel; measured equal above) */
     AGOFRT_OPT_SAFE2 = 2048,       /* dense windows: the two-floor form of the safe-zone binning (two round-down FFMAs give the
                                       histogram word and the near-an-edge flag); exact like the others, measured slower */
-    AGOFRT_OPT_SKEW = 4096         /* with AGOFRT_OPT_SAFE2: offset half of the warps by one binning run (A/B measurements) */
+    AGOFRT_OPT_SKEW = 4096,        /* with AGOFRT_OPT_SAFE2: offset half of the warps by one binning run (A/B measurements) */
+    AGOFRT_OPT_EXPLICIT_JOBS = 8192 /* always build and upload the (lag, origin) job list (default: derived on the device when regular) */
 };
 
 typedef struct {

@@ -54,6 +54,32 @@ def test_single_process_all_devices_equals_one_device():
 
 
 @needs2
+@pytest.mark.parametrize("wrap", [False, True])
+def test_shared_upload_exchanges_the_frames_between_devices(wrap):
+    """agofrt_traj_upload_ex(AGOFRT_UP_SHARED): every device copies (and wraps) only its share of the frames, the
+    shares are exchanged device to device; afterwards every device holds the whole window -- the block, whose work
+    units are spread over all devices, counts what one device counts."""
+    pos, bi, types = case()              # pageable numpy memory: staged through page-locked slots
+    wrapped = oracle.pbc_wrap(pos, bi)
+    allc = cabi.Context("all")
+    tr = cabi.DeviceTrajectory(allc, pos.shape[1], bi.shape[1], types, 2, pos.shape[0])
+    if wrap:
+        back = np.empty_like(pos)
+        tr.upload_ex(0, pos, bi, wrap=True, shared=True, out=back)
+        assert np.array_equal(back, wrapped)     # every device returned its share
+    else:
+        tr.upload_ex(0, wrapped, bi, shared=True)
+    assert np.array_equal(tr.download(0, pos.shape[0]), wrapped)
+    plan = cabi.Plan(tr, 0.0, 3.1, 60)
+    c, st = plan.block(1, 5, 3, 2, 1)
+    assert st["world"] == allc.ndev >= 2
+    assert np.array_equal(c, oracle.counts(wrapped, bi, types, 0.0, 3.1, 60, 3, 5, primo=1, skip=2, ntypes=2))
+    plan.close()
+    tr.close()
+    allc.close()
+
+
+@needs2
 def test_neighbour_histogram_on_all_devices():
     """agofrt_neighbour_hist shards (frame, atom tile) units over the devices and all-reduces the histogram"""
     pos, bi, types = case()
@@ -87,6 +113,16 @@ WORKER = textwrap.dedent('''
     tr.upload(0, pos, bi)
     plan = cabi.Plan(tr, 0.0, 3.1, 60)
     ok = True
+    # the shared upload as a collective over the processes: every rank copies and wraps its share of the UNWRAPPED
+    # frames, the shares are exchanged over NCCL; the window every rank ends up with is the wrapped one
+    raw, _, _ = synth.small_case(51, (10, 9, 8), 1.05, 2, True, 8)
+    tr2 = cabi.DeviceTrajectory(ctx, pos.shape[1], 9, types, 2, pos.shape[0])
+    tr2.upload_ex(0, np.ascontiguousarray(raw), bi, wrap=True, shared=True)
+    ok = ok and bool(np.array_equal(tr2.download(0, pos.shape[0]), pos))
+    plan2 = cabi.Plan(tr2, 0.0, 3.1, 60)
+    c2, _ = plan2.block(1, 5, 3, 2, 1)
+    ok = ok and bool(np.array_equal(c2, oracle.counts(pos, bi, types, 0.0, 3.1, 60, 3, 5, primo=1, skip=2, ntypes=2)))
+    plan2.close(); tr2.close()
     for opt in (0, cabi.OPT_FORCE_GENERAL, cabi.OPT_NO_SAFE):
         c, st, e = plan.block(1, 5, 3, 2, 1, options=opt, edges=True) if opt == 0 else plan.block(1, 5, 3, 2, 1, options=opt) + (None,)
         ref, eref = oracle.counts(pos, bi, types, 0.0, 3.1, 60, 3, 5, primo=1, skip=2, ntypes=2, return_edges=True)
@@ -127,3 +163,47 @@ def test_cli_on_all_gpus_matches_reference_golden(tmp_path):
     assert r.returncode == 0, r.stderr[-2000:]
     gold = open(os.path.join(GOLDEN, "cli_pair_corr_t.txt")).read()
     assert r.stdout.rstrip("\n") == gold.rstrip("\n")
+
+
+PY_WORKER = textwrap.dedent('''
+    import json, os, sys
+    import numpy as np
+    os.environ["ANALISI_DEVICES"] = os.environ.get("LOCAL_RANK", "0")
+    import oracle
+    from analisi_b200 import build as b, dist, synth
+    _, ext = b.build_host()
+    sys.path.insert(0, os.path.dirname(ext))
+    import pyanalisi as pa
+    ranks = dist.Ranks()
+    uid = pa.comm_unique_id() if ranks.rank == 0 else b""
+    pa.comm_join(ranks.broadcast_bytes(uid, 128, 0), ranks.rank, ranks.world)
+    pos, box, types = synth.small_case(52, (9, 9, 8), 1.05, 2, True, 9)
+    pos = np.ascontiguousarray(pos)
+    tr = pa.Trajectory(pos, np.zeros_like(pos), types.astype(np.int32), box, pa.BoxFormat.LammpsTriclinic, True, False)
+    g = pa.Gofrt(tr, 0.0, 3.0, 50, 3, 1, 2, 1, False)
+    g.reset(6)
+    g.calculate(1)
+    bi = synth.lammps_rows_to_internal(box)
+    wrapped = oracle.pbc_wrap(pos, bi)
+    ref = oracle.counts(wrapped, bi, types, 0.0, 3.0, 50, 3, 6, primo=1, skip=2, ntypes=2)
+    ok = bool(np.array_equal(g.counts(), ref)) and g.last_stats()["world"] == ranks.world
+    ok = ok and bool(np.array_equal(tr.get_positions_copy(), wrapped))   # the host copy arrives on demand, wrapped
+    ranks.barrier()
+    sys.stdout.write("AGOFRT_RESULT " + json.dumps({"rank": ranks.rank, "ok": ok, "world": ranks.world}) + "\\n")
+    sys.stdout.flush()
+    ranks.close()
+''')
+
+
+@needs2
+def test_pyanalisi_one_process_per_gpu(tmp_path):
+    """The reference-facing classes as an SPMD program (torchrun, one rank per GPU): pyanalisi.comm_join, then
+    Trajectory(..., wrap=True) uploads each rank's share of the frames and wraps it on its GPU, the shares are
+    exchanged, Gofrt.calculate shards the block and all-reduces: every rank holds the oracle's counts."""
+    script = tmp_path / "worker_py.py"
+    script.write_text(PY_WORKER)
+    r = torchrun(2, [str(script)])
+    assert r.returncode == 0, r.stderr[-3000:]
+    import re
+    lines = [json.loads(m) for m in re.findall(r"AGOFRT_RESULT (\{[^{}]*\})", r.stdout)]
+    assert len(lines) == 2 and all(l["ok"] and l["world"] == 2 for l in lines), (r.stdout[-1500:], r.stderr[-1500:])

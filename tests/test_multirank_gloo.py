@@ -83,7 +83,8 @@ def test_world2_shards_sum_to_the_whole_block(tmp_path):
 def test_reference_arm_under_torchrun_prints_once():
     """bench.py --impl reference with two ranks: rank 0 alone times the CPU path and prints ONE JSON line,
     rank 1 exits 0 without work (contract of the reference arm)."""
-    r = torchrun(2, ["bench.py", "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0", "--cpu-seconds", "1"])
+    r = torchrun(2, ["bench.py", "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0", "--cpu-seconds", "1",
+                     "--workload", "C2"])   # (the default workload, C4, is one 1e10-pair job per step: minutes on these cores)
     assert r.returncode == 0, r.stderr[-3000:]
     lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
     assert len(lines) == 1
