@@ -627,3 +627,31 @@ def test_block_average_on_device(ctx):
     acc.close()
     plan.close()
     tr.close()
+
+
+def test_c4_subset_against_the_reference_itself(ctx):
+    """The north-star shape at full size -- 100 000 atoms, triclinic, 500 bins -- on the (lag, origin) subset that is
+    bench.py's default step (26 lags x 8 origins = 2.08e12 pair evaluations): bit-exact against the counts of the
+    UNMODIFIED reference (69 minutes on 7 host threads; tests/golden/make_c4_subset_golden.py)."""
+    import hashlib
+    import json
+    import os
+    from conftest import GOLDEN
+    meta = json.load(open(os.path.join(GOLDEN, "c4_subset_counts.json")))
+    gold = np.load(os.path.join(GOLDEN, "c4_subset_counts.npz"))
+    w, nts = synth.bench_subset("C4")
+    assert meta["workload"] == w.name and meta["subset"] == {"ntimesteps": nts, "skip": w.skip, "every": w.every, "leff": 201}
+    leff = 201
+    nframes = (nts - 1) // w.skip * w.skip + (leff - 1) // w.every * w.every + 1
+    pos, box, types = synth.generate(w, nframes=nframes)
+    bi = synth.lammps_rows_to_internal(box)
+    tr = cabi.DeviceTrajectory(ctx, w.natoms, 9, types, 1, nframes)
+    tr.upload_ex(0, pos, bi, wrap=True)
+    plan = cabi.Plan(tr, w.rmin, w.rmax, w.nbin)
+    c, st = plan.block(0, nts, leff, w.skip, w.every)
+    plan.close()
+    tr.close()
+    assert st["jobs"] == meta["jobs"] == 208 and st["jobs_fast"] == 208
+    assert np.array_equal(c[gold["lags"]], gold["counts"])
+    assert hashlib.sha256(np.ascontiguousarray(c).astype("<u8").tobytes()).hexdigest() == meta["counts_sha256"]
+    assert int(c.sum()) == meta["counts_sum"]

@@ -229,3 +229,20 @@ def test_live_reference_tile_cases(name):
     c = oracle.counts(pos, bi, ids, rmin, rmax, int(nbin), int(tmax), int(nts), primo=int(primo), skip=int(skip),
                       every=int(every), ntypes=int(ids.max()) + 1)
     assert np.array_equal(c, d["counts"])
+
+
+def test_c4_subset_golden_is_self_consistent():
+    """tests/golden/c4_subset_counts.*: the stored lag rows reproduce the checksum bench.py compares with (the rows
+    between them are empty: every 8th lag), and the self row of lag 0 holds one count per atom and origin."""
+    import hashlib
+    import json
+    import os
+    from conftest import GOLDEN
+    meta = json.load(open(os.path.join(GOLDEN, "c4_subset_counts.json")))
+    z = np.load(os.path.join(GOLDEN, "c4_subset_counts.npz"))
+    full = np.zeros((meta["subset"]["leff"], 2, 500), dtype=np.uint64)
+    full[z["lags"]] = z["counts"]
+    assert hashlib.sha256(full.astype("<u8").tobytes()).hexdigest() == meta["counts_sha256"]
+    assert int(full.sum()) == meta["counts_sum"]
+    assert int(full[0, 1, 0]) == 100000 * 8 and int(full[0, 1, 1:].sum()) == 0
+    assert list(z["lags"]) == list(range(0, 201, 8))
