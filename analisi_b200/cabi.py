@@ -30,6 +30,7 @@ SYMBOLS = [
     "agofrt_plan_destroy", "agofrt_plan_thresholds", "agofrt_block", "agofrt_neighbour_hist", "agofrt_traj_set_cm", "agofrt_msd", "agofrt_fp64_peak",
     "agofrt_blockavg_create", "agofrt_blockavg_destroy", "agofrt_blockavg_begin", "agofrt_blockavg_push", "agofrt_blockavg_end",
     "agofrt_plan_last_counts", "agofrt_plan_info", "agofrt_traj_upload_ex", "agofrt_traj_download",
+    "agofrt_blocks", "agofrt_plan_block_counts", "agofrt_blockavg_push_blocks",
 ]
 
 
@@ -111,6 +112,9 @@ def lib():
     L.agofrt_blockavg_push.argtypes = [vp, vp, C.c_double]
     L.agofrt_blockavg_end.argtypes = [vp, C.c_uint, dp, dp]
     L.agofrt_plan_last_counts.argtypes = [vp, u64p, C.c_size_t]
+    L.agofrt_blocks.argtypes = [vp, C.c_size_t, C.c_size_t, C.c_uint, C.c_uint, C.c_uint, C.c_uint, C.c_uint, C.c_uint, C.POINTER(Stats)]
+    L.agofrt_plan_block_counts.argtypes = [vp, C.c_uint, u64p, C.c_size_t]
+    L.agofrt_blockavg_push_blocks.argtypes = [vp, vp, C.c_double]
     for name in SYMBOLS:
         fn = getattr(L, name)
         if name not in ("agofrt_version", "agofrt_last_error"):
@@ -361,6 +365,19 @@ class Plan:
             return counts, st.as_dict(), int(e.value)
         return counts, st.as_dict()
 
+    def blocks(self, primo0, stride, nblocks, ntimesteps, leff, skip=1, every=1, options=0):
+        """agofrt_blocks: nblocks whole blocks dealt to the devices; the counts stay on the devices.  Returns stats."""
+        st = Stats()
+        _check(lib().agofrt_blocks(self._h, int(primo0), int(stride), int(nblocks), int(ntimesteps), int(leff), int(skip),
+                                   int(every), int(options), C.byref(st)))
+        return st.as_dict()
+
+    def block_counts(self, block, leff):
+        nt = self.traj.ntypes
+        counts = np.zeros((int(leff), nt * (nt + 1), self.nbin), dtype=np.uint64)
+        _check(lib().agofrt_plan_block_counts(self._h, int(block), counts.ctypes.data_as(C.POINTER(C.c_uint64)), counts.size))
+        return counts
+
     def last_counts(self, leff):
         """The counts of the last block() from the device (what a block without OPT_ON_DEVICE returns)."""
         nt = self.traj.ntypes
@@ -395,6 +412,9 @@ class BlockAverage:
 
     def push(self, plan, incr):
         _check(lib().agofrt_blockavg_push(self._h, plan._h, float(incr)))
+
+    def push_blocks(self, plan, incr):
+        _check(lib().agofrt_blockavg_push_blocks(self._h, plan._h, float(incr)))
 
     def end(self, n_b):
         mean = np.empty(self.len, dtype=np.float64)

@@ -206,6 +206,8 @@ struct PlanDev {
     size_t units_cap = 0;
     unsigned int *counter = nullptr;      // [1]
     unsigned long long *edges = nullptr;  // [1]
+    unsigned long long *batch = nullptr;  // agofrt_blocks: [nblocks][len] counts of whole blocks
+    size_t batch_len = 0;
 };
 
 struct agofrt_plan {
@@ -232,6 +234,8 @@ struct agofrt_plan {
     unsigned int *host_flags = nullptr;         // pinned [ndev]
     size_t last_len = 0;                        // words of the counts the last agofrt_block left in dev[0].ghist
     bool last_valid = false;                    // ... and whether they are the complete (all-reduced) counts
+    unsigned batch_blocks = 0;                  // agofrt_blocks: blocks held in dev[*].batch, each batch_block_len words
+    size_t batch_block_len = 0;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -1342,6 +1346,7 @@ extern "C" int agofrt_plan_destroy(agofrt_plan *p) try {
         cudaFree(d.units);
         cudaFree(d.counter);
         cudaFree(d.edges);
+        cudaFree(d.batch);
     }
     if (p->host_counts) cudaFreeHost(p->host_counts);
     if (p->host_edges) cudaFreeHost(p->host_edges);
@@ -1424,9 +1429,17 @@ static bool range_is_single_pass(const agofrt_traj *t, size_t f0, size_t f1) {
     return true;
 }
 
-extern "C" int agofrt_block(agofrt_plan *p, size_t primo, unsigned ntimesteps, unsigned leff, unsigned skip,
-                            unsigned every, unsigned options, uint64_t *counts_out, uint64_t *edge_pairs_out,
-                            agofrt_stats *stats) try {
+// A whole block on ONE device, enqueued and not waited for (agofrt_blocks): where it runs and where its counts go
+struct BlockTarget {
+    int dev;                    // local device
+    unsigned long long *ghist;  // [len] on that device
+    bool first;                 // first block of the batch on this device: reset the error flag
+};
+constexpr int kNotBatchable = 1;   // block_impl with a target: the block has no regular job list (caller falls back)
+
+static int block_impl(agofrt_plan *p, size_t primo, unsigned ntimesteps, unsigned leff, unsigned skip, unsigned every,
+                      unsigned options, uint64_t *counts_out, uint64_t *edge_pairs_out, agofrt_stats *stats,
+                      const BlockTarget *tg) {
     if (!p) return fail(AGOFRT_ERR_ARG, "plan is NULL");
     agofrt_traj *t = p->traj;
     agofrt_ctx *ctx = t->ctx;
@@ -1436,7 +1449,7 @@ extern "C" int agofrt_block(agofrt_plan *p, size_t primo, unsigned ntimesteps, u
     const size_t rowlen = static_cast<size_t>(nt) * (nt + 1) * p->nbin;
     const size_t len = static_cast<size_t>(leff) * rowlen;
     const bool on_device = (options & AGOFRT_OPT_ON_DEVICE) != 0;
-    if (len > 0 && !counts_out && !on_device) return fail(AGOFRT_ERR_ARG, "counts_out is NULL");
+    if (len > 0 && !counts_out && !on_device && !tg) return fail(AGOFRT_ERR_ARG, "counts_out is NULL");
     p->last_valid = false;
     if (stats) memset(stats, 0, sizeof(*stats));
     if (edge_pairs_out) *edge_pairs_out = 0;
@@ -1445,8 +1458,9 @@ extern "C" int agofrt_block(agofrt_plan *p, size_t primo, unsigned ntimesteps, u
     int rc = ensure_local_comm(ctx);
     if (rc != AGOFRT_OK) return rc;
     const int nloc = static_cast<int>(ctx->devs.size());
-    const int world = ctx->world > 0 ? ctx->world : nloc;
-    const int first_rank = ctx->world > 0 ? ctx->first_rank : 0;
+    // (a target: the whole block on one device, no sharding)
+    const int world = tg ? 1 : (ctx->world > 0 ? ctx->world : nloc);
+    const int first_rank = tg ? 0 : (ctx->world > 0 ? ctx->first_rank : 0);
 
     // ---- the (lag, origin) jobs, in the reference's loop order (calculatemultithread.h:114-115) ----
     std::vector<Job> jobs_fast, jobs_gen;
@@ -1473,6 +1487,7 @@ extern "C" int agofrt_block(agofrt_plan *p, size_t primo, unsigned ntimesteps, u
         // forced) the list is regular -- job k = (lag k / origins, origin k % origins) -- and the kernels derive it
         // themselves: nothing is built or uploaded (C1: 142 884 jobs per block).  Otherwise: an explicit list per kernel.
         implicit = (all_fast || !may_fast) && !(options & AGOFRT_OPT_EXPLICIT_JOBS);
+        if (tg && !implicit) return kNotBatchable;
         if (implicit) {
             njobs = expect;
             (all_fast ? n_fast : n_gen) = expect;
@@ -1601,7 +1616,7 @@ extern "C" int agofrt_block(agofrt_plan *p, size_t primo, unsigned ntimesteps, u
     const bool use_safe2 = use_safe && dense && p->safe2_ok && !aggregate && !want_edges && !small && (options & AGOFRT_OPT_SAFE2);
 
     // ---- pinned read-back buffer ----
-    if (len > p->host_counts_len) {
+    if (!tg && len > p->host_counts_len) {
         if (p->host_counts) cudaFreeHost(p->host_counts);
         p->host_counts = nullptr;
         p->host_counts_len = 0;
@@ -1614,11 +1629,13 @@ extern "C" int agofrt_block(agofrt_plan *p, size_t primo, unsigned ntimesteps, u
     uint64_t my_pairs = 0;
     // ---- enqueue on every local device ----
     for (int i = 0; i < nloc; ++i) {
+        if (tg && i != tg->dev) continue;
         Dev &dv = ctx->devs[i];
         TrajDev &td = t->dev[i];
         PlanDev &pd = p->dev[i];
         CU(cudaSetDevice(dv.id));
-        if (len > pd.ghist_len) {
+        unsigned long long *const ghist = tg ? tg->ghist : nullptr;
+        if (!tg && len > pd.ghist_len) {
             cudaFree(pd.ghist);
             pd.ghist = nullptr;
             pd.ghist_len = 0;
@@ -1641,8 +1658,8 @@ extern "C" int agofrt_block(agofrt_plan *p, size_t primo, unsigned ntimesteps, u
             CU(cudaMalloc(&pd.units, nuall * sizeof(SmallUnit)));
             pd.units_cap = nuall;
         }
-        CU(cudaEventRecord(dv.ev_begin, dv.stream));
-        if (len > 0) CU(cudaMemsetAsync(pd.ghist, 0, len * sizeof(unsigned long long), dv.stream));
+        if (!tg) CU(cudaEventRecord(dv.ev_begin, dv.stream));
+        if (len > 0) CU(cudaMemsetAsync(tg ? ghist : pd.ghist, 0, len * sizeof(unsigned long long), dv.stream));
         if (!units_fast.empty())
             CU(cudaMemcpyAsync(pd.units, units_fast.data(), units_fast.size() * sizeof(SmallUnit), cudaMemcpyHostToDevice,
                                dv.stream));
@@ -1650,15 +1667,15 @@ extern "C" int agofrt_block(agofrt_plan *p, size_t primo, unsigned ntimesteps, u
             CU(cudaMemcpyAsync(pd.units + units_fast.size(), units_gen.data(), units_gen.size() * sizeof(SmallUnit),
                                cudaMemcpyHostToDevice, dv.stream));
         CU(cudaMemsetAsync(pd.edges, 0, sizeof(unsigned long long), dv.stream));
-        CU(cudaMemsetAsync(td.flags + 1, 0, sizeof(unsigned int), dv.stream));
+        if (!tg || tg->first) CU(cudaMemsetAsync(td.flags + 1, 0, sizeof(unsigned int), dv.stream));
         if (!jobs_fast.empty())
             CU(cudaMemcpyAsync(pd.jobs, jobs_fast.data(), jobs_fast.size() * sizeof(Job), cudaMemcpyHostToDevice, dv.stream));
         if (!jobs_gen.empty())
             CU(cudaMemcpyAsync(pd.jobs + jobs_fast.size(), jobs_gen.data(), jobs_gen.size() * sizeof(Job),
                                cudaMemcpyHostToDevice, dv.stream));
-        CU(cudaEventRecord(dv.ev_k0, dv.stream));
+        if (!tg) CU(cudaEventRecord(dv.ev_k0, dv.stream));
         if (!nothing) {
-            const int g = first_rank + i;
+            const int g = tg ? 0 : first_rank + i;
             for (int pass = 0; pass < 2; ++pass) {
                 const uint64_t nlist = pass == 0 ? n_fast : n_gen;
                 if (nlist == 0) continue;
@@ -1680,7 +1697,7 @@ extern "C" int agofrt_block(agofrt_plan *p, size_t primo, unsigned ntimesteps, u
                 pp.imp_skip = static_cast<int>(skip);
                 pp.imp_every = static_cast<int>(every);
                 pp.imp_each = static_cast<int>(small_each);
-                pp.ghist = pd.ghist;
+                pp.ghist = tg ? ghist : pd.ghist;
                 pp.edges = pd.edges;
                 pp.counter = pd.counter;
                 pp.error_flag = td.flags + 1;
@@ -1750,7 +1767,19 @@ extern "C" int agofrt_block(agofrt_plan *p, size_t primo, unsigned ntimesteps, u
                 }
             }
         }
-        CU(cudaEventRecord(dv.ev_k1, dv.stream));
+        if (!tg) CU(cudaEventRecord(dv.ev_k1, dv.stream));
+    }
+    if (tg) {
+        // enqueued; the caller waits, exchanges and checks the flags for the whole batch
+        if (stats) {
+            stats->pair_evals = nothing ? 0 : my_pairs;
+            stats->pair_evals_total = njobs * n2;
+            stats->jobs = njobs;
+            stats->jobs_fast = n_fast;
+            stats->launches = launches;
+            stats->kernel_modes = modes_used;
+        }
+        return AGOFRT_OK;
     }
     // ---- combine: one all-reduce of the integer histograms (replaces mp.h:35-41) ----
     if (ctx->comm_ready && world > 1 && len > 0) {
@@ -1833,6 +1862,149 @@ extern "C" int agofrt_block(agofrt_plan *p, size_t primo, unsigned ntimesteps, u
         stats->kernel_modes = modes_used;
     }
     return AGOFRT_OK;
+}
+
+extern "C" int agofrt_block(agofrt_plan *p, size_t primo, unsigned ntimesteps, unsigned leff, unsigned skip,
+                            unsigned every, unsigned options, uint64_t *counts_out, uint64_t *edge_pairs_out,
+                            agofrt_stats *stats) try {
+    return block_impl(p, primo, ntimesteps, leff, skip, every, options, counts_out, edge_pairs_out, stats, nullptr);
+} catch (...) {
+    return on_exception();
+}
+
+// Many small blocks: WHOLE blocks are dealt to the devices (block b to device b mod world), each block a launch of
+// its own on its device's stream, nothing waited for in between; then every device receives every block (grouped
+// ncclBroadcast over NVLink), so that the Welford update can run, in block order, wherever it likes.  Replaces the
+// round-robin of blocks over MPI ranks of the reference (lib/include/blockaverage.h:146-186).
+extern "C" int agofrt_blocks(agofrt_plan *p, size_t primo0, size_t stride, unsigned nblocks, unsigned ntimesteps, unsigned leff,
+                             unsigned skip, unsigned every, unsigned options, agofrt_stats *stats) try {
+    if (!p) return fail(AGOFRT_ERR_ARG, "plan is NULL");
+    if (options & (AGOFRT_OPT_EDGES)) return fail(AGOFRT_ERR_ARG, "agofrt_blocks does not count edge pairs (use agofrt_block)");
+    agofrt_traj *t = p->traj;
+    agofrt_ctx *ctx = t->ctx;
+    if (stats) memset(stats, 0, sizeof(*stats));
+    p->batch_blocks = 0;
+    p->last_valid = false;
+    int rc = ensure_local_comm(ctx);
+    if (rc != AGOFRT_OK) return rc;
+    const int nloc = static_cast<int>(ctx->devs.size());
+    const int world = ctx->world > 0 ? ctx->world : nloc;
+    const int first_rank = ctx->world > 0 ? ctx->first_rank : 0;
+    if (world > 1 && !ctx->comm_ready) return fail(AGOFRT_ERR_ARG, "agofrt_blocks on a sharded context needs a communicator");
+    const int nt = t->ntypes;
+    const size_t len = static_cast<size_t>(leff) * nt * (nt + 1) * p->nbin;
+    if (nblocks == 0 || len == 0) return AGOFRT_OK;
+    if (static_cast<double>(nblocks) * static_cast<double>(len) * 8.0 > 2.0e9)
+        return fail(AGOFRT_ERR_TOO_LARGE, "%u blocks of %zu counters do not fit the batch buffer (use agofrt_block)", nblocks, len);
+    for (int i = 0; i < nloc; ++i) {
+        PlanDev &pd = p->dev[i];
+        CU(cudaSetDevice(ctx->devs[i].id));
+        if (static_cast<size_t>(nblocks) * len > pd.batch_len) {
+            cudaFree(pd.batch);
+            pd.batch = nullptr;
+            pd.batch_len = 0;
+            CU(cudaMalloc(&pd.batch, static_cast<size_t>(nblocks) * len * sizeof(unsigned long long)));
+            pd.batch_len = static_cast<size_t>(nblocks) * len;
+        }
+        CU(cudaEventRecord(ctx->devs[i].ev_begin, ctx->devs[i].stream));
+    }
+    agofrt_stats sum;
+    memset(&sum, 0, sizeof(sum));
+    std::vector<char> first(nloc, 1);
+    for (unsigned b = 0; b < nblocks; ++b) {
+        const int g = static_cast<int>(b % static_cast<unsigned>(world));
+        if (g < first_rank || g >= first_rank + nloc) continue;
+        const int i = g - first_rank;
+        BlockTarget tg{i, p->dev[i].batch + static_cast<size_t>(b) * len, first[i] != 0};
+        first[i] = 0;
+        agofrt_stats st;
+        memset(&st, 0, sizeof(st));
+        rc = block_impl(p, primo0 + static_cast<size_t>(b) * stride, ntimesteps, leff, skip, every, options | AGOFRT_OPT_ON_DEVICE,
+                        nullptr, nullptr, &st, &tg);
+        if (rc == kNotBatchable)
+            return fail(AGOFRT_ERR_ARG, "block %u has no regular job list (single-pass minimum image not proven for its whole "
+                                        "frame range): run the blocks one by one with agofrt_block", b);
+        if (rc != AGOFRT_OK) return rc;
+        sum.pair_evals += st.pair_evals;
+        sum.jobs += st.jobs;
+        sum.jobs_fast += st.jobs_fast;
+        sum.launches += st.launches;
+        sum.kernel_modes |= st.kernel_modes;
+    }
+    for (int i = 0; i < nloc; ++i) {
+        CU(cudaSetDevice(ctx->devs[i].id));
+        CU(cudaEventRecord(ctx->devs[i].ev_k1, ctx->devs[i].stream));
+    }
+    // every device receives every block
+    if (world > 1) {
+        NcclApi &api = nccl_api();
+        NC(api.GroupStart());
+        for (unsigned b = 0; b < nblocks; ++b)
+            for (int i = 0; i < nloc; ++i) {
+                unsigned long long *q = p->dev[i].batch + static_cast<size_t>(b) * len;
+                NC(api.Broadcast(q, q, len, ncclUint64, static_cast<int>(b % static_cast<unsigned>(world)), ctx->devs[i].comm,
+                                 ctx->devs[i].stream));
+            }
+        NC(api.GroupEnd());
+    }
+    double kernel_ms = 0, total_ms = 0;
+    for (int i = 0; i < nloc; ++i) {
+        Dev &dv = ctx->devs[i];
+        CU(cudaSetDevice(dv.id));
+        // what agofrt_block leaves behind: the last block in the plan's own histogram (agofrt_plan_last_counts, agofrt_blockavg_push)
+        PlanDev &pd = p->dev[i];
+        if (len > pd.ghist_len) {
+            cudaFree(pd.ghist);
+            pd.ghist = nullptr;
+            pd.ghist_len = 0;
+            CU(cudaMalloc(&pd.ghist, len * sizeof(unsigned long long)));
+            pd.ghist_len = len;
+        }
+        CU(cudaMemcpyAsync(pd.ghist, pd.batch + static_cast<size_t>(nblocks - 1) * len, len * sizeof(unsigned long long),
+                           cudaMemcpyDeviceToDevice, dv.stream));
+        CU(cudaMemcpyAsync(&p->host_flags[i], t->dev[i].flags + 1, sizeof(unsigned int), cudaMemcpyDeviceToHost, dv.stream));
+        CU(cudaEventRecord(dv.ev_end, dv.stream));
+    }
+    for (int i = 0; i < nloc; ++i) {
+        Dev &dv = ctx->devs[i];
+        CU(cudaSetDevice(dv.id));
+        CU(cudaStreamSynchronize(dv.stream));
+        float a = 0, b = 0;
+        CU(cudaEventElapsedTime(&a, dv.ev_begin, dv.ev_k1));
+        CU(cudaEventElapsedTime(&b, dv.ev_begin, dv.ev_end));
+        kernel_ms = std::max<double>(kernel_ms, a);
+        total_ms = std::max<double>(total_ms, b);
+        if (p->host_flags[i]) return fail(AGOFRT_ERR_NONFINITE, "minimum image did not converge within %d images", kWrapCap);
+    }
+    p->batch_blocks = nblocks;
+    p->batch_block_len = len;
+    p->last_len = len;
+    p->last_valid = true;
+    if (stats) {
+        *stats = sum;
+        stats->kernel_ms = kernel_ms;
+        stats->total_ms = total_ms;
+        stats->pair_evals_total = static_cast<uint64_t>(nblocks) * static_cast<uint64_t>((leff + (every ? every : 1) - 1) / (every ? every : 1)) *
+                                  static_cast<uint64_t>((ntimesteps + (skip ? skip : 1) - 1) / (skip ? skip : 1)) *
+                                  static_cast<uint64_t>(t->natoms) * t->natoms;
+        stats->ndev_local = static_cast<uint32_t>(nloc);
+        stats->world = static_cast<uint32_t>(world);
+    }
+    return AGOFRT_OK;
+} catch (...) {
+    return on_exception();
+}
+
+extern "C" int agofrt_plan_block_counts(agofrt_plan *p, unsigned block, uint64_t *counts_out, size_t len) try {
+    if (!p || (!counts_out && len > 0)) return fail(AGOFRT_ERR_ARG, "NULL argument");
+    if (block >= p->batch_blocks) return fail(AGOFRT_ERR_ARG, "block %u is not one of the %u blocks of the last agofrt_blocks", block, p->batch_blocks);
+    if (len != p->batch_block_len) return fail(AGOFRT_ERR_ARG, "a block holds %zu counters, not %zu", p->batch_block_len, len);
+    if (len == 0) return AGOFRT_OK;
+    Dev &dv = p->ctx->devs[0];
+    CU(cudaSetDevice(dv.id));
+    CU(cudaMemcpyAsync(counts_out, p->dev[0].batch + static_cast<size_t>(block) * len, len * sizeof(uint64_t), cudaMemcpyDeviceToHost, dv.stream));
+    CU(cudaStreamSynchronize(dv.stream));
+    return AGOFRT_OK;
 } catch (...) {
     return on_exception();
 }
@@ -1907,6 +2079,23 @@ extern "C" int agofrt_blockavg_push(agofrt_blockavg *a, agofrt_plan *p, double i
     // agofrt_block zeroes the counts
     CU(launch_blockavg_push(p->dev[0].ghist, incr, a->blocks, a->mean, a->var, a->len, dv.sm_count, dv.stream));
     ++a->blocks;
+    return AGOFRT_OK;
+} catch (...) {
+    return on_exception();
+}
+
+// all the blocks of the plan's last agofrt_blocks, in block order, in one launch
+extern "C" int agofrt_blockavg_push_blocks(agofrt_blockavg *a, agofrt_plan *p, double incr) try {
+    if (!a || !p) return fail(AGOFRT_ERR_ARG, "NULL argument");
+    if (!a->begun) return fail(AGOFRT_ERR_ARG, "agofrt_blockavg_push_blocks before agofrt_blockavg_begin");
+    if (p->ctx != a->ctx) return fail(AGOFRT_ERR_ARG, "plan and accumulator belong to different contexts");
+    if (p->batch_blocks == 0) return fail(AGOFRT_ERR_ARG, "the plan holds no batch of blocks (run agofrt_blocks first)");
+    if (p->batch_block_len != a->len)
+        return fail(AGOFRT_ERR_ARG, "blocks of %zu elements pushed into an average of %zu", p->batch_block_len, a->len);
+    Dev &dv = a->ctx->devs[0];
+    CU(cudaSetDevice(dv.id));
+    CU(launch_blockavg_push_blocks(p->dev[0].batch, p->batch_blocks, incr, a->blocks, a->mean, a->var, a->len, dv.sm_count, dv.stream));
+    a->blocks += p->batch_blocks;
     return AGOFRT_OK;
 } catch (...) {
     return on_exception();

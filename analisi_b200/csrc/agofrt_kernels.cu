@@ -1812,6 +1812,34 @@ cudaError_t launch_blockavg_push(const unsigned long long *counts, double incr, 
     return cudaGetLastError();
 }
 
+// The same for a batch of blocks (agofrt_blocks): every element walks the blocks IN ORDER, so the sequence of rounded
+// operations per element is the one of nblocks single pushes -- in one launch.
+__global__ void __launch_bounds__(256) blockavg_push_blocks_kernel(const unsigned long long *__restrict__ counts, unsigned nblocks,
+                                                                   double incr, unsigned first_index, double *__restrict__ mean,
+                                                                   double *__restrict__ var, size_t len) {
+    const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+    for (size_t k = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; k < len; k += stride) {
+        double m = mean[k], v = var[k];
+        for (unsigned b = 0; b < nblocks; ++b) {
+            const double x = __dmul_rn(__ull2double_rn(counts[static_cast<size_t>(b) * len + k]), incr);
+            const double delta = __dsub_rn(x, m);
+            m = __dadd_rn(m, __ddiv_rn(delta, static_cast<double>(first_index + b + 1u)));
+            v = __dadd_rn(v, __dmul_rn(__dsub_rn(x, m), delta));
+        }
+        mean[k] = m;
+        var[k] = v;
+    }
+}
+
+cudaError_t launch_blockavg_push_blocks(const unsigned long long *counts, unsigned nblocks, double incr, unsigned first_index,
+                                        double *mean, double *var, size_t len, int sm_count, cudaStream_t stream) {
+    if (len == 0 || nblocks == 0) return cudaSuccess;
+    const size_t want = (len + 255) / 256;
+    const int grid = static_cast<int>(want < static_cast<size_t>(8 * sm_count) ? want : static_cast<size_t>(8 * sm_count));
+    blockavg_push_blocks_kernel<<<grid, 256, 0, stream>>>(counts, nblocks, incr, first_index, mean, var, len);
+    return cudaGetLastError();
+}
+
 // ---------------------------------------------------------------------------------------------
 // FP64 issue-rate microbenchmark: 8 independent DFMA chains per thread
 // ---------------------------------------------------------------------------------------------

@@ -152,6 +152,10 @@ int msd_tile_atoms();
 cudaError_t launch_blockavg_push(const unsigned long long *counts, double incr, unsigned block_index, double *mean,
                                  double *var, size_t len, int sm_count, cudaStream_t stream);
 
+// ... for nblocks blocks [nblocks][len] in block order, first of them block `first_index`
+cudaError_t launch_blockavg_push_blocks(const unsigned long long *counts, unsigned nblocks, double incr, unsigned first_index,
+                                        double *mean, double *var, size_t len, int sm_count, cudaStream_t stream);
+
 // MODE_SAFE validation: bad += number of probes whose unflagged float guess differs from expected[]
 cudaError_t launch_validate_safe(const double *probes, const int *expected, int n, float inv_dr, float c0h, float lim,
                                  float qmax, int nbin, int glo, unsigned int *bad, cudaStream_t stream);

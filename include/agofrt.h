@@ -205,6 +205,19 @@ AGOFRT_API int agofrt_block(agofrt_plan *plan, size_t primo, unsigned ntimesteps
                             unsigned skip, unsigned every, unsigned options, uint64_t *counts_out,
                             uint64_t *edge_pairs_out, agofrt_stats *stats);
 
+/* Many small blocks at once (BlockAverageG on systems of a few dozen atoms, where one block is a millisecond of kernel
+ * and sharding its work units over several GPUs buys nothing): block b = reset(ntimesteps); calculate(primo0 + b*stride),
+ * WHOLE blocks dealt to the devices (block b to device b mod world -- the round-robin of blocks over MPI ranks of
+ * lib/include/blockaverage.h:146-186), no host synchronisation between blocks, then every device receives every block
+ * (NCCL broadcasts).  The window must hold the frames of all the blocks; every block must have a regular job list (the
+ * single-pass minimum image proven for its frame range, or AGOFRT_OPT_FORCE_GENERAL), else AGOFRT_ERR_ARG: run them one by
+ * one.  The counts stay on the devices: agofrt_plan_block_counts reads one block back, agofrt_blockavg_push_blocks folds
+ * them all, in block order, into a device-resident mean / variance; the last block is also what agofrt_plan_last_counts
+ * returns.  Under agofrt_comm_join a collective. */
+AGOFRT_API int agofrt_blocks(agofrt_plan *plan, size_t primo0, size_t stride, unsigned nblocks, unsigned ntimesteps,
+                             unsigned leff, unsigned skip, unsigned every, unsigned options, agofrt_stats *stats);
+AGOFRT_API int agofrt_plan_block_counts(agofrt_plan *plan, unsigned block, uint64_t *counts_out, size_t len);
+
 /* ---- block averages on the device (MediaVar) ------------------------------------------------- */
 /* MediaVar<T> (lib/include/calcoliblocchi.h:21-65) for T = Gofrt, on the counts agofrt_block leaves on the device:
  * mean and variance-of-the-mean over blocks with the reference's own sequence of rounded operations per element
@@ -223,6 +236,8 @@ AGOFRT_API int agofrt_blockavg_create(agofrt_blockavg **acc, agofrt_ctx *ctx);
 AGOFRT_API int agofrt_blockavg_destroy(agofrt_blockavg *acc);
 AGOFRT_API int agofrt_blockavg_begin(agofrt_blockavg *acc, size_t len);
 AGOFRT_API int agofrt_blockavg_push(agofrt_blockavg *acc, agofrt_plan *plan, double incr);
+/* every block of the plan's last agofrt_blocks, in block order (one launch; the same rounded operations per element) */
+AGOFRT_API int agofrt_blockavg_push_blocks(agofrt_blockavg *acc, agofrt_plan *plan, double incr);
 AGOFRT_API int agofrt_blockavg_end(agofrt_blockavg *acc, unsigned n_b, double *mean_out, double *var_out);
 AGOFRT_API int agofrt_plan_last_counts(agofrt_plan *plan, uint64_t *counts_out, size_t len);
 

@@ -79,6 +79,26 @@ public:
         ok = true;
         calcolo->reset(s);
         calc->calcola_begin(s, calcolo);
+        // Many small blocks (this repository's addition): one window with the frames of all of them, whole blocks dealt
+        // to the GPUs and computed without coming back to the host in between, then folded in block order -- the
+        // reference's MPI branch deals blocks to ranks the same way (blockaverage.h:146-186).
+        if constexpr (HasBlockBatch<T>::value) {
+            if (calcolo->block_batch_wanted(n_b, s, extra)) {
+                cronometro cron;
+                cron.start();
+                TraiettoriaF<TR>::set_data_access_block_size(n_b * s + extra, traiettoria);
+                TraiettoriaF<TR>::set_access_at(0, traiettoria);
+                if (calcolo->calculate_blocks(0, s, n_b)) {
+                    calc->calculate_blocks(calcolo, n_b);
+                    calc->calcola_end(n_b);
+                    if constexpr (!HasDeviceBlocksEnd<Calcolo>::value) calcolo->fetch_block_of_batch(n_b - 1);
+                    cron.stop();
+                    std::cerr << "Time for " << n_b << " blocks of " << s << " steps, computed as one batch on the GPUs: " << cron.time()
+                              << "s.\n";
+                    return;
+                }
+            }
+        }
         TraiettoriaF<TR>::set_data_access_block_size(s + extra, traiettoria);
         TraiettoriaF<TR>::hint_stride(s, traiettoria);
         cronometro cron;

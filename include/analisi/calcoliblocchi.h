@@ -44,6 +44,16 @@ public:
         ++seen_;
     }
 
+    // every block of x's last calculate_blocks(), in block order (the blocks were computed on the GPUs in one go;
+    // each is fetched into x and folded in as above)
+    template <class U = T>
+    void calculate_blocks(U *x, unsigned int n_b) {
+        for (unsigned int b = 0; b < n_b; ++b) {
+            x->fetch_block_of_batch(b);
+            calculate(x);
+        }
+    }
+
     // variance of the mean: sum / ((n_b - 1) n_b)
     void calcola_end(unsigned int n_b) { *var_ /= static_cast<double>((n_b - 1) * n_b); }
 
@@ -59,9 +69,23 @@ template <class T>
 struct HasDeviceBlocks<T, std::void_t<decltype(&T::set_keep_on_device), decltype(&T::device_plan), decltype(&T::fetch_block)>>
     : std::true_type {};
 
+// calculations that can run a batch of blocks on the devices: block_batch_wanted / calculate_blocks / fetch_block_of_batch
+template <class T, class = void>
+struct HasBlockBatch : std::false_type {};
+template <class T>
+struct HasBlockBatch<T, std::void_t<decltype(&T::block_batch_wanted), decltype(&T::calculate_blocks), decltype(&T::fetch_block_of_batch)>>
+    : std::true_type {};
+
+// block consumers whose calcola_end() already leaves the last block in the calculation object (MediaVarDevice)
+template <class C, class = void>
+struct HasDeviceBlocksEnd : std::false_type {};
+template <class C>
+struct HasDeviceBlocksEnd<C, std::void_t<typename C::fetches_last_block>> : std::true_type {};
+
 template <class T>
 class MediaVarDevice {
 public:
+    using fetches_last_block = void;
     MediaVarDevice(T *mean, T *var) : mean_(mean), var_(var) {}
     ~MediaVarDevice() {
         if (calc_) calc_->set_keep_on_device(false);
@@ -87,6 +111,12 @@ public:
     void calculate(T *calc) {
         if (mean_->lunghezza() == 0) return;
         analisi_device::check(agofrt_blockavg_push(acc_, calc->device_plan(), calc->get_incr()), "agofrt_blockavg_push");
+    }
+
+    // every block of calc's last calculate_blocks(), in block order
+    void calculate_blocks(T *calc, unsigned int) {
+        if (mean_->lunghezza() == 0) return;
+        analisi_device::check(agofrt_blockavg_push_blocks(acc_, calc->device_plan(), calc->get_incr()), "agofrt_blockavg_push_blocks");
     }
 
     void calcola_end(unsigned int n_b) {

@@ -177,6 +177,54 @@ public:
         for (unsigned int k = 0; k < data_length; ++k) vdata[k] = static_cast<TFLOAT>(counts_buf[k]) * incr;
     }
 
+    // this repository's addition -- many small blocks at once (BlockAverageG::calcola_custom): whole blocks are dealt to
+    // the GPUs (block b to device b mod n, the reference's round-robin of blocks over MPI ranks,
+    // lib/include/blockaverage.h:146-186) and nothing returns to the host between them.  Worth it where one block is a
+    // millisecond of kernel: systems that take the small-system kernel, and a window with the frames of ALL the blocks
+    // that is small.  ANALISI_BLOCK_BATCH=0 turns it off.
+    bool block_batch_wanted(unsigned int n_b, unsigned int s, unsigned int extra) const {
+        if (const char *e = std::getenv("ANALISI_BLOCK_BATCH"))
+            if (std::atoi(e) == 0) return false;
+        if (debug || report_edges || n_b < 2) return false;
+        const double frames = static_cast<double>(n_b) * s + extra;
+        const unsigned int nt = static_cast<unsigned int>(traiettoria->get_ntypes());
+        const double result_words = static_cast<double>(n_b) * ((s < lmax || lmax == 0) ? s : lmax) * nt * (nt + 1) * nbin;
+        return traiettoria->get_natoms() <= 248 && frames * traiettoria->get_natoms() * 24.0 <= 512e6 && result_words * 8.0 <= 1.5e9;
+    }
+    // blocks b = 0 .. nblocks-1: reset(ntimesteps) (already done by the caller); calculate(primo0 + b*stride).  The counts
+    // stay on the devices: MediaVarDevice folds them there, fetch_block_of_batch(b) brings one into this object's buffer.
+    // Returns false (nothing done) when the blocks cannot be batched after all: the caller runs them one by one.
+    bool calculate_blocks(size_t primo0, size_t stride, unsigned int nblocks) {
+        if (nblocks == 0 || data_length == 0) return false;
+        const size_t last = primo0 + static_cast<size_t>(nblocks - 1) * stride;
+        if (static_cast<size_t>(leff) + static_cast<size_t>(ntimesteps) + last > static_cast<size_t>(traiettoria->get_ntimesteps()) + 1)
+            throw std::runtime_error(
+                "trajectory is too short for this kind of calculation. Select a different starting timestep or lower the "
+                "size of the average or the lenght of the time lag");
+        incr = (ntimesteps / skip > 0) ? 1.0 / static_cast<int>(ntimesteps / skip) : 1.0;
+        agofrt_traj *win = traiettoria->device_window();
+        if (!plan || plan_generation != traiettoria->device_generation()) {
+            drop_plan();
+            analisi_device::check(agofrt_plan_create(&plan, win, rmin, rmax, nbin), "agofrt_plan_create");
+            plan_generation = traiettoria->device_generation();
+        }
+        analisi_device::check(agofrt_plan_retarget(plan, win), "agofrt_plan_retarget");
+        const int rc = agofrt_blocks(plan, primo0, stride, nblocks, static_cast<unsigned>(ntimesteps), static_cast<unsigned>(leff),
+                                     static_cast<unsigned>(skip), static_cast<unsigned>(every), kernel_options, &stats);
+        if (rc == AGOFRT_ERR_ARG || rc == AGOFRT_ERR_TOO_LARGE) return false;   // not batchable: blocks one by one
+        analisi_device::check(rc, "agofrt_blocks");
+        sum_kernel_ms += stats.kernel_ms;
+        sum_total_ms += stats.total_ms;
+        sum_pair_evals += stats.pair_evals_total;
+        ncalls += nblocks;
+        return true;
+    }
+    void fetch_block_of_batch(unsigned int b) {
+        counts_buf.resize(data_length);
+        analisi_device::check(agofrt_plan_block_counts(plan, b, counts_buf.data(), data_length), "agofrt_plan_block_counts");
+        for (unsigned int k = 0; k < data_length; ++k) vdata[k] = static_cast<TFLOAT>(counts_buf[k]) * incr;
+    }
+
     // this repository's additions: the raw integer counts of the last calculate() and its device timings
     const std::vector<uint64_t> &counts() const { return counts_buf; }
     const agofrt_stats &last_stats() const { return stats; }

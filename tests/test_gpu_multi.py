@@ -80,6 +80,35 @@ def test_shared_upload_exchanges_the_frames_between_devices(wrap):
 
 
 @needs2
+def test_whole_blocks_are_dealt_to_the_devices():
+    """agofrt_blocks on a context with several devices: block b runs on device b mod n, every device receives every
+    block, the batch equals the blocks one device computes one by one."""
+    pos, box, types = synth.small_case(61, (4, 4, 4), 1.05, 2, True, 60)
+    bi = synth.lammps_rows_to_internal(box)
+    pos = np.ascontiguousarray(pos)
+    allc = cabi.Context("all")
+    allc.pbc_wrap(pos, bi)
+    tr = cabi.DeviceTrajectory(allc, pos.shape[1], 9, types, 2, pos.shape[0])
+    tr.upload_ex(0, pos, bi, shared=True)
+    plan = cabi.Plan(tr, 0.0, 2.5, 32)
+    n_b, s, leff = 7, 8, 3
+    st = plan.blocks(0, s, n_b, s, leff, 2, 1)
+    assert st["world"] == allc.ndev >= 2
+    blocks = []
+    for b in range(n_b):
+        ref = oracle.counts(pos, bi, types, 0.0, 2.5, 32, 3, s, primo=b * s, skip=2, ntypes=2)
+        assert np.array_equal(plan.block_counts(b, leff), ref)
+        blocks.append(ref * 0.25)
+    acc = cabi.BlockAverage(allc)
+    acc.begin(leff * 6 * 32)
+    acc.push_blocks(plan, 0.25)
+    mean, var = acc.end(n_b)
+    omean, ovar = oracle.mediavar(np.array(blocks))
+    assert np.array_equal(mean, omean.ravel()) and np.array_equal(var, ovar.ravel())
+    acc.close(); plan.close(); tr.close(); allc.close()
+
+
+@needs2
 def test_neighbour_histogram_on_all_devices():
     """agofrt_neighbour_hist shards (frame, atom tile) units over the devices and all-reduces the histogram"""
     pos, bi, types = case()

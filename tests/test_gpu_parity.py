@@ -629,6 +629,48 @@ def test_block_average_on_device(ctx):
     tr.close()
 
 
+@pytest.mark.parametrize("natoms,tri", [(80, True), (56, False), (300, True)])
+def test_batch_of_whole_blocks(ctx, natoms, tri):
+    """agofrt_blocks: every block of a batch equals the oracle's block, the device Welford over the batch
+    (one launch) is bit-identical to the oracle's MediaVar, and the last block is what agofrt_block would have left."""
+    pos, bi, types = _small_system(93, natoms, 2, tri, 70)
+    ctx.pbc_wrap(pos, bi)
+    rmin, rmax, nbin, tmax = 0.0, 3.0, 40, 5
+    n_b, s, skip = 6, 10, 3
+    incr = cabi.gofrt_incr(s, skip)
+    tr = cabi.DeviceTrajectory(ctx, pos.shape[1], bi.shape[1], types, 2, pos.shape[0])
+    tr.upload(0, np.ascontiguousarray(pos), bi)
+    plan = cabi.Plan(tr, rmin, rmax, nbin)
+    leff = cabi.gofrt_leff(s, tmax)
+    for options in (0, cabi.OPT_FORCE_GENERAL):
+        st = plan.blocks(0, s, n_b, s, leff, skip, 1, options=options)
+        assert st["jobs"] == n_b * leff * 4 and st["launches"] >= n_b
+        assert st["jobs_fast"] == (0 if options else st["jobs"])
+        blocks = []
+        for b in range(n_b):
+            ref = oracle.counts(pos, bi, types, rmin, rmax, nbin, tmax, s, primo=b * s, skip=skip, ntypes=2)
+            assert np.array_equal(plan.block_counts(b, leff), ref)
+            blocks.append(ref * incr)
+        assert np.array_equal(plan.last_counts(leff), plan.block_counts(n_b - 1, leff))
+        acc = cabi.BlockAverage(ctx)
+        acc.begin(leff * 6 * nbin)
+        acc.push_blocks(plan, incr)
+        mean, var = acc.end(n_b)
+        omean, ovar = oracle.mediavar(np.array(blocks))
+        assert np.array_equal(mean, omean.ravel()) and np.array_equal(var, ovar.ravel())
+        acc.close()
+    with pytest.raises(cabi.AgofrtError):
+        plan.block_counts(n_b, leff)
+    # a batch whose blocks have no regular job list is refused (the caller runs them one by one)
+    far = np.ascontiguousarray(pos).copy()
+    far[::2, 0, 0] += 5.0 * 2 * bi[0, 3]   # atom 0 far outside the cell in every other frame: no range-wide proof
+    tr.upload(0, far, bi)
+    with pytest.raises(cabi.AgofrtError):
+        plan.blocks(0, s, n_b, s, leff, skip, 1)
+    plan.close()
+    tr.close()
+
+
 def test_c4_subset_against_the_reference_itself(ctx):
     """The north-star shape at full size -- 100 000 atoms, triclinic, 500 bins -- on the (lag, origin) subset that is
     bench.py's default step (26 lags x 8 origins = 2.08e12 pair evaluations): bit-exact against the counts of the
