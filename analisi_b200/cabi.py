@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("AGOFRT_LIB", os.path.join(_HERE, "libagofrt.so"))  # AGOFRT_LIB: tuning builds only
 
 OK = 0
-ERR_ARG, ERR_CUDA, ERR_WINDOW, ERR_NCCL, ERR_NONFINITE, ERR_TOO_LARGE, ERR_INTERNAL = -1, -2, -3, -4, -5, -6, -7
+ERR_ARG, ERR_CUDA, ERR_WINDOW, ERR_NCCL, ERR_NONFINITE, ERR_TOO_LARGE, ERR_INTERNAL, ERR_RETYPED = -1, -2, -3, -4, -5, -6, -7, -8
 OPT_EDGES, OPT_FORCE_GENERAL, OPT_NO_AGGREGATE, OPT_AGGREGATE, OPT_NO_SAFE, OPT_DENSE, OPT_SPARSE, OPT_NO_UBOX = 1, 2, 4, 8, 16, 32, 64, 128
 OPT_NO_SMALL, OPT_ON_DEVICE, OPT_SMALL, OPT_SAFE2, OPT_SKEW, OPT_EXPLICIT_JOBS = 256, 512, 1024, 2048, 4096, 8192
 SMALL_DEFAULT_SLOTS, SMALL_MAX_SLOTS = 256, 512   # kSmallDefault, kSmallMax of the library
@@ -31,6 +31,7 @@ SYMBOLS = [
     "agofrt_blockavg_create", "agofrt_blockavg_destroy", "agofrt_blockavg_begin", "agofrt_blockavg_push", "agofrt_blockavg_end",
     "agofrt_plan_last_counts", "agofrt_plan_info", "agofrt_traj_upload_ex", "agofrt_traj_download",
     "agofrt_blocks", "agofrt_plan_block_counts", "agofrt_blockavg_push_blocks",
+    "agofrt_traj_set_ids", "agofrt_traj_upload_records",
 ]
 
 
@@ -92,6 +93,8 @@ def lib():
     L.agofrt_plan_retarget.argtypes = [vp, vp]
     L.agofrt_traj_upload_ex.argtypes = [vp, C.c_size_t, C.c_size_t, vp, vp, C.c_uint, vp]
     L.agofrt_traj_download.argtypes = [vp, C.c_size_t, C.c_size_t, vp]
+    L.agofrt_traj_set_ids.argtypes = [vp, ip, ip]
+    L.agofrt_traj_upload_records.argtypes = [vp, C.c_size_t, C.c_size_t, C.POINTER(vp), ip, C.POINTER(C.c_size_t), vp, C.c_uint, vp]
     L.agofrt_traj_download_frame.argtypes = [vp, C.c_size_t, dp]
     L.agofrt_pbc_wrap.argtypes = [vp, vp, C.c_size_t, C.c_size_t, dp, C.c_int]
     L.agofrt_traj_d2_all.argtypes = [vp, C.c_size_t, C.c_size_t, dp]
@@ -266,6 +269,27 @@ class DeviceTrajectory:
             assert wrap and out.dtype == np.float64 and out.flags.c_contiguous and out.shape == pos.shape and out.flags.writeable
         _check(lib().agofrt_traj_upload_ex(self._h, int(first_frame), pos.shape[0], pos.ctypes.data, box.ctypes.data, flags,
                                            out.ctypes.data if out is not None else None))
+
+    def set_ids(self, slot_to_id, slot_raw_type):
+        a = np.ascontiguousarray(slot_to_id, dtype=np.int32)
+        b = np.ascontiguousarray(slot_raw_type, dtype=np.int32)
+        assert a.shape == b.shape == (self.natoms,)
+        _check(lib().agofrt_traj_set_ids(self._h, a.ctypes.data_as(C.POINTER(C.c_int)), b.ctypes.data_as(C.POINTER(C.c_int))))
+
+    def upload_records(self, first_frame, frames, box_internal, wrap=False, shared=False, out=None):
+        """agofrt_traj_upload_records: ``frames`` is a list (one entry per frame) of lists of float64 arrays [n][8]
+        (the chunks of the frame: id type x y z vx vy vz per atom)."""
+        chunks = [np.ascontiguousarray(c, dtype=np.float64) for fr in frames for c in fr]
+        assert all(c.ndim == 2 and c.shape[1] == 8 for c in chunks)
+        ptrs = (C.c_void_p * max(len(chunks), 1))(*[c.ctypes.data for c in chunks])
+        atoms = (C.c_int * max(len(chunks), 1))(*[c.shape[0] for c in chunks])
+        begin = np.cumsum([0] + [len(fr) for fr in frames])
+        fc = (C.c_size_t * len(begin))(*[int(x) for x in begin])
+        box = np.ascontiguousarray(box_internal, dtype=np.float64)
+        assert box.shape == (len(frames), self.box_stride)
+        flags = (UP_WRAP if wrap else 0) | (UP_SHARED if shared else 0) | (UP_WRITEBACK if out is not None else 0)
+        _check(lib().agofrt_traj_upload_records(self._h, int(first_frame), len(frames), ptrs, atoms, fc, box.ctypes.data, flags,
+                                                out.ctypes.data if out is not None else None))
 
     def download(self, first_frame, nframes):
         """Frames of the device window in the caller's atom order (wrapped if uploaded with wrap)."""

@@ -145,7 +145,55 @@ struct Dev {
     size_t hstage_bytes = 0;
     cudaEvent_t hstage_free[2] = {nullptr, nullptr};
     std::mutex *hstage_mutex = nullptr;
+    // The two large buffers of a window (SoA positions, AoS staging) are kept when a window is destroyed and handed to
+    // the next one that fits: a caller that builds a trajectory object per analysis (python: Trajectory(...) per call)
+    // would otherwise pay cudaMalloc + cudaFree of gigabytes every time (measured: 0.2-0.7 s per 2.3 GB window).
+    struct Spare {
+        void *ptr = nullptr;
+        size_t bytes = 0;
+    };
+    Spare *spare = nullptr;   // [kSpares], guarded by hstage_mutex
 };
+constexpr int kSpares = 4;
+
+static void *spare_take(Dev &dv, size_t bytes) {
+    std::lock_guard<std::mutex> lock(*dv.hstage_mutex);
+    int best = -1;
+    for (int k = 0; k < kSpares; ++k)
+        if (dv.spare[k].ptr && dv.spare[k].bytes >= bytes && dv.spare[k].bytes <= bytes + bytes / 4 + (1u << 20) &&
+            (best < 0 || dv.spare[k].bytes < dv.spare[best].bytes))
+            best = k;
+    if (best < 0) return nullptr;
+    void *p = dv.spare[best].ptr;
+    dv.spare[best] = Dev::Spare();
+    return p;
+}
+
+// keeps the buffer if it is large enough to matter and a slot is free (or holds a smaller one); else frees it
+static void spare_give(Dev &dv, void *ptr, size_t bytes) {
+    if (!ptr) return;
+    if (bytes >= (16u << 20)) {
+        std::lock_guard<std::mutex> lock(*dv.hstage_mutex);
+        int slot = -1;
+        for (int k = 0; k < kSpares && slot < 0; ++k)
+            if (!dv.spare[k].ptr) slot = k;
+        if (slot < 0) {
+            int smallest = 0;
+            for (int k = 1; k < kSpares; ++k)
+                if (dv.spare[k].bytes < dv.spare[smallest].bytes) smallest = k;
+            if (dv.spare[smallest].bytes < bytes) {
+                cudaFree(dv.spare[smallest].ptr);
+                slot = smallest;
+            }
+        }
+        if (slot >= 0) {
+            dv.spare[slot].ptr = ptr;
+            dv.spare[slot].bytes = bytes;
+            return;
+        }
+    }
+    cudaFree(ptr);
+}
 
 struct agofrt_ctx {
     std::vector<Dev> devs;
@@ -164,11 +212,17 @@ struct TrajDev {
     int *perm = nullptr;         // [npad]
     int *type_pad = nullptr;     // [npad]
     int *type_start = nullptr;   // [ntypes+1]
-    unsigned int *flags = nullptr;  // [4]: 0 = inf seen, 1 = wrap cap hit
+    unsigned int *flags = nullptr;  // [8]: 0 inf seen, 1 wrap cap hit (block), 2 NaN in a real atom, 3 wrap cap hit (upload),
+                                    //      4 records with an unknown atom id, 5 records whose type changed (agofrt_traj_upload_records)
     double *probe = nullptr;        // [4]: result of agofrt_traj_d2_pair
     unsigned long long *nb_hist = nullptr;  // neighbour-count histogram [ntypes][natoms+1] (agofrt_neighbour_hist)
     int *nb_frames = nullptr;
     size_t nb_frames_cap = 0;
+    int *id_table = nullptr;        // LAMMPS atom id -> slot of the caller's atom order (agofrt_traj_set_ids), -1 = unknown id
+    int *slot_type = nullptr;       // [natoms] raw LAMMPS type every slot is expected to carry
+    size_t pos_bytes = 0, stage_bytes = 0;   // sizes of pos / stage as allocated (they may come from the context's spares)
+    double *raw = nullptr;          // staging of raw dump records, 8 doubles per atom (agofrt_traj_upload_records)
+    size_t raw_frames = 0;
     cudaStream_t up = nullptr;      // uploads of THIS window run here: they can overlap the pair kernels of another
                                     // window of the same context (which run on the device's main stream)
 };
@@ -191,6 +245,8 @@ struct agofrt_traj {
     size_t cm_first = 0, cm_frames = 0;
     bool perm_valid = false;     // the permutation is kept over uploads and refreshed every kPermRefresh frames
     size_t perm_frame = 0;       // first frame of the window it was built from
+    size_t id_table_len = 0;     // entries of the id -> slot table on the devices (0: agofrt_traj_set_ids not called)
+    std::vector<int> id_table_host;
     std::vector<int> slot_of;    // atom -> device slot (built on demand by agofrt_traj_d2_pair)
     size_t slot_of_first = 0;
     bool slot_of_stale = true;
@@ -343,6 +399,7 @@ extern "C" int agofrt_ctx_create(agofrt_ctx **out, const int *devices, int ndev)
         CU(cudaEventCreateWithFlags(&d.hstage_free[0], cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&d.hstage_free[1], cudaEventDisableTiming));
         d.hstage_mutex = new std::mutex();
+        d.spare = new Dev::Spare[kSpares];
         ctx->devs.push_back(d);
     }
     *out = ctx.release();
@@ -362,6 +419,9 @@ extern "C" int agofrt_ctx_destroy(agofrt_ctx *ctx) try {
             if (d.hstage[k]) cudaFreeHost(d.hstage[k]);
             if (d.hstage_free[k]) cudaEventDestroy(d.hstage_free[k]);
         }
+        if (d.spare)
+            for (int k = 0; k < kSpares; ++k) cudaFree(d.spare[k].ptr);
+        delete[] d.spare;
         delete d.hstage_mutex;
         if (d.stream) cudaStreamDestroy(d.stream);
         if (d.ev_begin) cudaEventDestroy(d.ev_begin);
@@ -494,10 +554,10 @@ static void free_traj_dev(agofrt_traj *t) {
     for (size_t i = 0; i < t->dev.size(); ++i) {
         cudaSetDevice(t->ctx->devs[i].id);
         TrajDev &d = t->dev[i];
-        cudaFree(d.pos);
+        spare_give(t->ctx->devs[i], d.pos, d.pos_bytes);
         cudaFree(d.box6);
         cudaFree(d.bounds);
-        cudaFree(d.stage);
+        spare_give(t->ctx->devs[i], d.stage, d.stage_bytes);
         cudaFree(d.box_stage);
         cudaFree(d.perm);
         cudaFree(d.type_pad);
@@ -506,6 +566,9 @@ static void free_traj_dev(agofrt_traj *t) {
         cudaFree(d.probe);
         cudaFree(d.nb_hist);
         cudaFree(d.nb_frames);
+        cudaFree(d.id_table);
+        cudaFree(d.slot_type);
+        cudaFree(d.raw);
         if (d.up) cudaStreamDestroy(d.up);
     }
 }
@@ -555,23 +618,40 @@ extern "C" int agofrt_traj_create(agofrt_traj **out, agofrt_ctx *ctx, size_t nat
     for (size_t i = 0; i < ctx->devs.size(); ++i) {
         CU(cudaSetDevice(ctx->devs[i].id));
         TrajDev &d = t->dev[i];
-        cudaError_t e = cudaMalloc(&d.pos, max_frames * 3 * npad1 * sizeof(double));
+        const size_t want_pos = max_frames * 3 * npad1 * sizeof(double), want_stage = t->stage_frames * frame_bytes;
+        d.pos = static_cast<double *>(spare_take(ctx->devs[i], want_pos));
+        cudaError_t e = d.pos ? cudaSuccess : cudaMalloc(&d.pos, want_pos);
+        if (e != cudaSuccess) {
+            // the spares of this device may be what is in the way: give them back to the driver and try once more
+            cudaGetLastError();
+            {
+                std::lock_guard<std::mutex> lock(*ctx->devs[i].hstage_mutex);
+                for (int k = 0; k < kSpares; ++k) {
+                    cudaFree(ctx->devs[i].spare[k].ptr);
+                    ctx->devs[i].spare[k] = Dev::Spare();
+                }
+            }
+            e = cudaMalloc(&d.pos, want_pos);
+        }
         if (e != cudaSuccess) {
             free_traj_dev(t.get());
             return fail(AGOFRT_ERR_CUDA, "cudaMalloc of the %zu-frame window (%zu bytes) failed: %s", max_frames,
                         max_frames * 3 * npad1 * sizeof(double), cudaGetErrorString(e));
         }
+        d.pos_bytes = want_pos;
         CU(cudaMalloc(&d.box6, max_frames * 6 * sizeof(double)));
         CU(cudaMalloc(&d.bounds, max_frames * 6 * sizeof(double)));
-        CU(cudaMalloc(&d.stage, t->stage_frames * frame_bytes));
+        d.stage = static_cast<double *>(spare_take(ctx->devs[i], want_stage));
+        if (!d.stage) CU(cudaMalloc(&d.stage, want_stage));
+        d.stage_bytes = want_stage;
         CU(cudaMalloc(&d.box_stage, max_frames * box_stride * sizeof(double)));
         CU(cudaMalloc(&d.perm, npad1 * sizeof(int)));
         CU(cudaMalloc(&d.type_pad, npad1 * sizeof(int)));
         CU(cudaMalloc(&d.type_start, (ntypes + 1) * sizeof(int)));
-        CU(cudaMalloc(&d.flags, 4 * sizeof(unsigned int)));
+        CU(cudaMalloc(&d.flags, 8 * sizeof(unsigned int)));
         CU(cudaMalloc(&d.probe, 4 * sizeof(double)));
         CU(cudaStreamCreateWithFlags(&d.up, cudaStreamNonBlocking));
-        CU(cudaMemset(d.flags, 0, 4 * sizeof(unsigned int)));
+        CU(cudaMemset(d.flags, 0, 8 * sizeof(unsigned int)));
         if (t->npad > 0) CU(cudaMemcpy(d.type_pad, t->type_pad.data(), t->npad * sizeof(int), cudaMemcpyHostToDevice));
         CU(cudaMemcpy(d.type_start, t->type_start.data(), (ntypes + 1) * sizeof(int), cudaMemcpyHostToDevice));
     }
@@ -675,13 +755,21 @@ static bool is_pinned(const void *p) {
 // the communicator -- every device copies, wraps and lays out only its share, then the shares travel device to device
 // (grouped ncclBroadcast = an all-gather with unequal counts, over NVLink) -- so the window crosses PCIe ONCE per box
 // instead of once per GPU.  Pageable source memory goes through two page-locked slots filled by several host threads.
+// raw dump records as the source of a window (agofrt_traj_upload_records): frame f = the chunks
+// [frame_chunk[f], frame_chunk[f+1]) of chunk_ptr / chunk_atoms, natoms records of 8 doubles in all
+struct RecordSource {
+    const void *const *chunk_ptr;
+    const int *chunk_atoms;
+    const size_t *frame_chunk;
+};
+
 static int upload_impl(agofrt_traj *t, size_t first_frame, size_t nframes, const double *pos_in, const double *box_internal,
-                       unsigned flags, double *pos_back) {
+                       unsigned flags, double *pos_back, const RecordSource *rec = nullptr) {
     if (!t) return fail(AGOFRT_ERR_ARG, "traj is NULL");
     if (nframes > t->max_frames) return fail(AGOFRT_ERR_ARG, "window of %zu frames > max_frames %zu", nframes, t->max_frames);
-    if (nframes > 0 && (!box_internal || (t->natoms > 0 && !pos_in))) return fail(AGOFRT_ERR_ARG, "NULL buffer");
+    if (nframes > 0 && (!box_internal || (t->natoms > 0 && !pos_in && !rec))) return fail(AGOFRT_ERR_ARG, "NULL buffer");
     const bool wrap = (flags & AGOFRT_UP_WRAP) != 0;
-    if (!(wrap && (flags & AGOFRT_UP_WRITEBACK))) pos_back = nullptr;
+    if (!(flags & AGOFRT_UP_WRITEBACK) || (!wrap && !rec)) pos_back = nullptr;
     agofrt_ctx *ctx = t->ctx;
     const bool debug = getenv("AGOFRT_DEBUG") != nullptr;
     const auto t_begin = std::chrono::steady_clock::now();
@@ -722,9 +810,26 @@ static int upload_impl(agofrt_traj *t, size_t first_frame, size_t nframes, const
     constexpr size_t kPermRefresh = 256;
     const size_t moved = first_frame > t->perm_frame ? first_frame - t->perm_frame : t->perm_frame - first_frame;
     const bool new_perm = t->natoms > 0 && (!t->perm_valid || moved >= kPermRefresh);
+    std::vector<double> frame0;
+    if (new_perm && rec) {
+        // the spatial sort wants the positions of the first frame in the caller's atom order: one frame parsed on the
+        // host (ids resolved through the host copy of the table)
+        frame0.assign(t->natoms * 3, 0.0);
+        for (size_t c = rec->frame_chunk[0]; c < rec->frame_chunk[1]; ++c) {
+            const double *r = static_cast<const double *>(rec->chunk_ptr[c]);
+            for (int a = 0; a < rec->chunk_atoms[c]; ++a, r += 8) {
+                const long id = std::lround(r[0]);
+                if (id < 0 || static_cast<size_t>(id) >= t->id_table_host.size() || t->id_table_host[id] < 0) continue;
+                double *o = &frame0[static_cast<size_t>(t->id_table_host[id]) * 3];
+                o[0] = r[2];
+                o[1] = r[3];
+                o[2] = r[4];
+            }
+        }
+    }
     if (new_perm) {
         const auto t0 = std::chrono::steady_clock::now();
-        build_perm(t, pos_in, box_internal);   // (shared uploads: frame 0 of the window must be valid on every rank)
+        build_perm(t, rec ? frame0.data() : pos_in, box_internal);   // (shared uploads: frame 0 of the window must be valid on every rank)
         ms_perm = since(t0);
         t->perm_valid = true;
         t->perm_frame = first_frame;
@@ -755,17 +860,23 @@ static int upload_impl(agofrt_traj *t, size_t first_frame, size_t nframes, const
         Dev &dv = ctx->devs[i];
         TrajDev &d = t->dev[i];
         CU(cudaSetDevice(dv.id));
-        CU(cudaMemsetAsync(d.flags, 0, 4 * sizeof(unsigned int), d.up));
+        {
+            // [1] belongs to the kernels of agofrt_block; the rest is this upload's
+            CU(cudaMemsetAsync(d.flags, 0, sizeof(unsigned int), d.up));
+            CU(cudaMemsetAsync(d.flags + 2, 0, 6 * sizeof(unsigned int), d.up));
+        }
         if (t->npad > 0 && new_perm)
             CU(cudaMemcpyAsync(d.perm, t->perm.data(), t->npad * sizeof(int), cudaMemcpyHostToDevice, d.up));
         CU(cudaMemcpyAsync(d.box_stage, box_internal, nframes * t->stride * sizeof(double), cudaMemcpyHostToDevice, d.up));
         CU(launch_pack_box(d.box_stage, t->stride, static_cast<int>(nframes), d.box6, d.up));
     }
     if (t->npad > 0) {
-        const bool pinned_src = is_pinned(pos_in);
+        const bool pinned_src = !rec && is_pinned(pos_in);
+        // bytes per frame on the host side of the copy: AoS positions, or the raw records (8 doubles per atom)
+        const size_t src_frame_bytes = rec ? t->natoms * 8 * sizeof(double) : frame_bytes;
         // frames per step: what the device staging holds; from pageable memory also what a 64 MiB host slot holds
         size_t step = t->stage_frames;
-        if (!pinned_src) step = std::max<size_t>(1, std::min<size_t>(step, (64u << 20) / std::max<size_t>(frame_bytes, 1)));
+        if (!pinned_src) step = std::max<size_t>(1, std::min<size_t>(step, (64u << 20) / std::max<size_t>(src_frame_bytes, 1)));
         size_t longest = 0;
         for (int i = 0; i < nloc; ++i) longest = std::max(longest, fe[i] - fb[i]);
         std::vector<std::unique_lock<std::mutex>> locks;
@@ -773,7 +884,7 @@ static int upload_impl(agofrt_traj *t, size_t first_frame, size_t nframes, const
             for (int i = 0; i < nloc; ++i) {
                 Dev &dv = ctx->devs[i];
                 locks.emplace_back(*dv.hstage_mutex);
-                if (dv.hstage_bytes < step * frame_bytes) {
+                if (dv.hstage_bytes < step * src_frame_bytes) {
                     CU(cudaSetDevice(dv.id));
                     for (int k = 0; k < 2; ++k) {
                         if (dv.hstage[k]) cudaFreeHost(dv.hstage[k]);
@@ -781,8 +892,20 @@ static int upload_impl(agofrt_traj *t, size_t first_frame, size_t nframes, const
                     }
                     dv.hstage_bytes = 0;
                     for (int k = 0; k < 2; ++k)
-                        CU(cudaHostAlloc(reinterpret_cast<void **>(&dv.hstage[k]), step * frame_bytes, cudaHostAllocPortable));
-                    dv.hstage_bytes = step * frame_bytes;
+                        CU(cudaHostAlloc(reinterpret_cast<void **>(&dv.hstage[k]), step * src_frame_bytes, cudaHostAllocPortable));
+                    dv.hstage_bytes = step * src_frame_bytes;
+                }
+            }
+        if (rec)
+            for (int i = 0; i < nloc; ++i) {
+                TrajDev &d = t->dev[i];
+                if (d.raw_frames < step) {
+                    CU(cudaSetDevice(ctx->devs[i].id));
+                    cudaFree(d.raw);
+                    d.raw = nullptr;
+                    d.raw_frames = 0;
+                    CU(cudaMalloc(&d.raw, step * src_frame_bytes));
+                    d.raw_frames = step;
                 }
             }
         size_t slot = 0;
@@ -793,23 +916,47 @@ static int upload_impl(agofrt_traj *t, size_t first_frame, size_t nframes, const
                 Dev &dv = ctx->devs[i];
                 TrajDev &d = t->dev[i];
                 CU(cudaSetDevice(dv.id));
-                const double *src = pos_in + f0 * frame_elems;
+                const double *src = rec ? nullptr : pos_in + f0 * frame_elems;
                 if (!pinned_src) {
                     double *hs = dv.hstage[slot & 1];
                     CU(cudaEventSynchronize(dv.hstage_free[slot & 1]));   // the copy that last read this slot is done
                     const auto t0 = std::chrono::steady_clock::now();
-                    parallel_copy(hs, src, nf * frame_bytes);
+                    if (rec) {
+                        // the chunks of every frame, one after the other: natoms records per frame
+                        char *w = reinterpret_cast<char *>(hs);
+                        for (size_t f = f0; f < f0 + nf; ++f) {
+                            size_t atoms = 0;
+                            for (size_t c = rec->frame_chunk[f]; c < rec->frame_chunk[f + 1]; ++c) {
+                                const size_t nb = static_cast<size_t>(rec->chunk_atoms[c]) * 8 * sizeof(double);
+                                atoms += static_cast<size_t>(rec->chunk_atoms[c]);
+                                if (atoms > t->natoms) return fail(AGOFRT_ERR_ARG, "frame %zu holds more records than atoms", first_frame + f);
+                                parallel_copy(w, rec->chunk_ptr[c], nb);
+                                w += nb;
+                            }
+                            if (atoms != t->natoms) return fail(AGOFRT_ERR_ARG, "frame %zu holds %zu records for %zu atoms", first_frame + f, atoms, t->natoms);
+                        }
+                    } else {
+                        parallel_copy(hs, src, nf * frame_bytes);
+                    }
                     ms_copy += since(t0);
                     src = hs;
                 }
-                CU(cudaMemcpyAsync(d.stage, src, nf * frame_bytes, cudaMemcpyHostToDevice, d.up));
-                if (!pinned_src) CU(cudaEventRecord(dv.hstage_free[slot & 1], d.up));
+                if (rec) {
+                    CU(cudaMemcpyAsync(d.raw, src, nf * src_frame_bytes, cudaMemcpyHostToDevice, d.up));
+                    CU(cudaEventRecord(dv.hstage_free[slot & 1], d.up));
+                    // header part of Trajectory::set_access_at's frame loop on the device: id -> slot, scatter x y z
+                    CU(launch_parse_records(d.raw, static_cast<int>(t->natoms), static_cast<int>(nf), d.id_table,
+                                            static_cast<int>(t->id_table_len), d.slot_type, d.stage, d.flags, d.up));
+                } else {
+                    CU(cudaMemcpyAsync(d.stage, src, nf * frame_bytes, cudaMemcpyHostToDevice, d.up));
+                    if (!pinned_src) CU(cudaEventRecord(dv.hstage_free[slot & 1], d.up));
+                }
                 if (wrap) {
                     CU(launch_pbc_wrap(d.stage, static_cast<int>(t->natoms), static_cast<int>(nf), d.box_stage + f0 * t->stride,
                                        t->stride, d.flags + 3, d.up));
-                    if (pos_back && (shared || i == 0))
-                        CU(cudaMemcpyAsync(pos_back + f0 * frame_elems, d.stage, nf * frame_bytes, cudaMemcpyDeviceToHost, d.up));
                 }
+                if (pos_back && (shared || i == 0))
+                    CU(cudaMemcpyAsync(pos_back + f0 * frame_elems, d.stage, nf * frame_bytes, cudaMemcpyDeviceToHost, d.up));
                 CU(launch_gather_soa(d.stage, d.perm, static_cast<int>(t->natoms), t->npad, static_cast<int>(nf),
                                      d.pos + f0 * 3 * static_cast<size_t>(t->npad), d.up));
             }
@@ -841,24 +988,27 @@ static int upload_impl(agofrt_traj *t, size_t first_frame, size_t nframes, const
                 }
             }
             for (int i = 0; i < nloc; ++i)
-                NC(api.AllReduce(t->dev[i].flags, t->dev[i].flags, 4, ncclUint32, ncclMax, ctx->devs[i].comm_up, t->dev[i].up));
+                NC(api.AllReduce(t->dev[i].flags, t->dev[i].flags, 8, ncclUint32, ncclMax, ctx->devs[i].comm_up, t->dev[i].up));
             NC(api.GroupEnd());
         }
         Dev &dv = ctx->devs[0];
         TrajDev &d = t->dev[0];
         CU(cudaSetDevice(dv.id));
-        unsigned int hflags[4] = {0, 0, 0, 0};
+        unsigned int hflags[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         CU(cudaMemcpyAsync(t->bounds.data(), d.bounds, nframes * 6 * sizeof(double), cudaMemcpyDeviceToHost, d.up));
         CU(cudaMemcpyAsync(hflags, d.flags, sizeof(hflags), cudaMemcpyDeviceToHost, d.up));
         CU(cudaStreamSynchronize(d.up));
         t->has_inf = hflags[0] != 0;
         t->has_nan = hflags[2] != 0;
-        if (hflags[3]) {
+        if (hflags[3] || hflags[4] || hflags[5]) {
             for (int i = 0; i < nloc; ++i) {
                 cudaSetDevice(ctx->devs[i].id);
                 cudaStreamSynchronize(t->dev[i].up);
             }
             t->nframes = 0;
+            if (hflags[4])
+                return fail(AGOFRT_ERR_ARG, "a record of the window carries an atom id that was not in the table (agofrt_traj_set_ids)");
+            if (hflags[5]) return fail(AGOFRT_ERR_RETYPED, "the type of an atom changes inside the window");
             return fail(AGOFRT_ERR_NONFINITE, "minimum image did not converge while wrapping (non-finite or absurdly far coordinate)");
         }
     }
@@ -894,6 +1044,51 @@ extern "C" int agofrt_traj_upload_ex(agofrt_traj *t, size_t first_frame, size_t 
     if ((flags & AGOFRT_UP_WRITEBACK) && !pos_wrapped_out && nframes > 0 && t && t->natoms > 0)
         return fail(AGOFRT_ERR_ARG, "AGOFRT_UP_WRITEBACK needs pos_wrapped_out");
     return upload_impl(t, first_frame, nframes, pos_aos, box_internal, flags, pos_wrapped_out);
+} catch (...) {
+    return on_exception();
+}
+
+// The id -> slot table of a LAMMPS dump (Trajectory's id_map, reference lib/src/trajectory.cpp:133-189) and the raw
+// type every slot carries, on the devices: what agofrt_traj_upload_records resolves records with.
+extern "C" int agofrt_traj_set_ids(agofrt_traj *t, const int *slot_to_id, const int *slot_raw_type) try {
+    if (!t || ((!slot_to_id || !slot_raw_type) && t->natoms > 0)) return fail(AGOFRT_ERR_ARG, "NULL argument");
+    int max_id = -1;
+    for (size_t k = 0; k < t->natoms; ++k) {
+        if (slot_to_id[k] < 0) return fail(AGOFRT_ERR_ARG, "negative atom id");
+        max_id = std::max(max_id, slot_to_id[k]);
+    }
+    if (static_cast<size_t>(max_id) > t->natoms * 8 + 1024) return fail(AGOFRT_ERR_TOO_LARGE, "atom ids are too sparse for a flat table (largest id %d for %zu atoms)", max_id, t->natoms);
+    t->id_table_host.assign(static_cast<size_t>(max_id + 1), -1);
+    for (size_t k = 0; k < t->natoms; ++k) {
+        if (t->id_table_host[slot_to_id[k]] >= 0) return fail(AGOFRT_ERR_ARG, "atom id %d appears twice", slot_to_id[k]);
+        t->id_table_host[slot_to_id[k]] = static_cast<int>(k);
+    }
+    t->id_table_len = t->id_table_host.size();
+    for (size_t i = 0; i < t->dev.size(); ++i) {
+        TrajDev &d = t->dev[i];
+        CU(cudaSetDevice(t->ctx->devs[i].id));
+        cudaFree(d.id_table);
+        cudaFree(d.slot_type);
+        d.id_table = d.slot_type = nullptr;
+        CU(cudaMalloc(&d.id_table, std::max<size_t>(t->id_table_len, 1) * sizeof(int)));
+        CU(cudaMalloc(&d.slot_type, std::max<size_t>(t->natoms, 1) * sizeof(int)));
+        if (t->id_table_len) CU(cudaMemcpy(d.id_table, t->id_table_host.data(), t->id_table_len * sizeof(int), cudaMemcpyHostToDevice));
+        if (t->natoms) CU(cudaMemcpy(d.slot_type, slot_raw_type, t->natoms * sizeof(int), cudaMemcpyHostToDevice));
+    }
+    return AGOFRT_OK;
+} catch (...) {
+    return on_exception();
+}
+
+extern "C" int agofrt_traj_upload_records(agofrt_traj *t, size_t first_frame, size_t nframes, const void *const *chunk_ptr,
+                                          const int *chunk_atoms, const size_t *frame_chunk, const double *box_internal,
+                                          unsigned flags, double *pos_out) try {
+    if (!t) return fail(AGOFRT_ERR_ARG, "traj is NULL");
+    if (nframes > 0 && (!chunk_ptr || !chunk_atoms || !frame_chunk)) return fail(AGOFRT_ERR_ARG, "NULL argument");
+    if (t->natoms > 0 && t->id_table_len == 0) return fail(AGOFRT_ERR_ARG, "agofrt_traj_set_ids must be called before agofrt_traj_upload_records");
+    if ((flags & AGOFRT_UP_WRITEBACK) && !pos_out && nframes > 0 && t->natoms > 0) return fail(AGOFRT_ERR_ARG, "AGOFRT_UP_WRITEBACK needs pos_out");
+    RecordSource rec{chunk_ptr, chunk_atoms, frame_chunk};
+    return upload_impl(t, first_frame, nframes, nullptr, box_internal, flags, pos_out, &rec);
 } catch (...) {
     return on_exception();
 }
@@ -2130,9 +2325,9 @@ extern "C" int agofrt_plan_last_counts(agofrt_plan *p, uint64_t *counts_out, siz
     if (len == 0) return AGOFRT_OK;
     Dev &dv = p->ctx->devs[0];
     CU(cudaSetDevice(dv.id));
-    CU(cudaMemcpyAsync(p->host_counts, p->dev[0].ghist, len * sizeof(unsigned long long), cudaMemcpyDeviceToHost, dv.stream));
+    // (straight into the caller's buffer: the pinned staging of agofrt_block need not exist -- agofrt_blocks has none)
+    CU(cudaMemcpyAsync(counts_out, p->dev[0].ghist, len * sizeof(unsigned long long), cudaMemcpyDeviceToHost, dv.stream));
     CU(cudaStreamSynchronize(dv.stream));
-    memcpy(counts_out, p->host_counts, len * sizeof(uint64_t));
     return AGOFRT_OK;
 } catch (...) {
     return on_exception();

@@ -1426,6 +1426,41 @@ cudaError_t launch_scatter_aos(const double *pos_soa, const int *perm, int natom
     return cudaGetLastError();
 }
 
+// The per-atom part of Trajectory::set_access_at's frame loop (reference lib/src/trajectory.cpp:629-646) for raw dump
+// records: id -> slot through the flat table, type check, x y z to the atom's slot of the AoS staging frame.
+// raw: [nframes][natoms][8] doubles (id type x y z vx vy vz) in file order; aos: [nframes][natoms][3].
+__global__ void parse_records_kernel(const double *__restrict__ raw, int natoms, int nframes, const int *__restrict__ id_table,
+                                     int table_len, const int *__restrict__ slot_type, double *__restrict__ aos,
+                                     unsigned int *flags) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    const int f = blockIdx.y;
+    if (r >= natoms || f >= nframes) return;
+    const double *rec = raw + (static_cast<size_t>(f) * natoms + r) * 8;
+    // two 32-byte halves of the record: one sector each
+    const double4 a = *reinterpret_cast<const double4 *>(rec);       // id type x y
+    const double z = rec[4];
+    const long long id = llrint(a.x);   // std::round of an integral double: the same integer
+    int slot = -1;
+    if (id >= 0 && id < table_len) slot = id_table[id];
+    if (slot < 0) {
+        atomicAdd(flags + 4, 1u);
+        return;
+    }
+    if (static_cast<int>(llrint(a.y)) != slot_type[slot]) atomicAdd(flags + 5, 1u);
+    double *o = aos + (static_cast<size_t>(f) * natoms + slot) * 3;
+    o[0] = a.z;
+    o[1] = a.w;
+    o[2] = z;
+}
+
+cudaError_t launch_parse_records(const double *raw, int natoms, int nframes, const int *id_table, int table_len,
+                                 const int *slot_type, double *aos, unsigned int *flags, cudaStream_t stream) {
+    if (nframes <= 0 || natoms <= 0) return cudaSuccess;
+    dim3 grid((natoms + 255) / 256, nframes);
+    parse_records_kernel<<<grid, 256, 0, stream>>>(raw, natoms, nframes, id_table, table_len, slot_type, aos, flags);
+    return cudaGetLastError();
+}
+
 __global__ void pack_box_kernel(const double *__restrict__ in, int stride, int nframes, double *__restrict__ out) {
     const int f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= nframes) return;

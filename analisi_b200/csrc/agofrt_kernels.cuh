@@ -98,6 +98,10 @@ cudaError_t launch_gather_soa(const double *pos_aos, const int *perm, int natoms
 // inverse: frames back to the caller's order
 cudaError_t launch_scatter_aos(const double *pos_soa, const int *perm, int natoms, int npad, int nframes,
                                double *pos_aos, cudaStream_t stream);
+// raw LAMMPS dump records [nframes][natoms][8] (id type x y z vx vy vz, file order) -> AoS positions [nframes][natoms][3]
+// in the caller's atom order through the id -> slot table; flags[4] counts unknown ids, flags[5] changed types
+cudaError_t launch_parse_records(const double *raw, int natoms, int nframes, const int *id_table, int table_len,
+                                 const int *slot_type, double *aos, unsigned int *flags, cudaStream_t stream);
 // box rows [nframes][stride] -> [nframes][6] (lx/2, ly/2, lz/2, xy, xz, yz)
 cudaError_t launch_pack_box(const double *box_internal, int stride, int nframes, double *box6,
                             cudaStream_t stream);

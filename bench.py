@@ -535,7 +535,7 @@ def main():
         vel = np.zeros_like(pos_all)   # the interface wants velocities; g(r,t) never reads them
         raw_types = np.ascontiguousarray(types, dtype=np.int32)
 
-        e2e_parts = {}
+        e2e_parts, e2e_log = {}, []
 
         def e2e_step():
             t0 = time.perf_counter()
@@ -550,6 +550,7 @@ def main():
             st = g.last_stats()
             del g, tr_py
             t4 = time.perf_counter()
+            e2e_log.append(round((t4 - t0) * 1e3, 1))
             e2e_parts.update(trajectory_ms=(t1 - t0) * 1e3, gofrt_ctor_reset_ms=(t2 - t1) * 1e3, calculate_ms=(t3 - t2) * 1e3,
                              calculate_device_ms=st["total_ms"], result_and_teardown_ms=(t4 - t3) * 1e3)
             return v
@@ -561,6 +562,7 @@ def main():
             v_e = e2e_step()
         barrier()
         e2e_ms = maxrank((time.time() - e0) * 1e3)
+        log("[bench] rank %d e2e steps (ms, the first is the warm-up): %s" % (rank, e2e_log))
         incr = cabi.gofrt_incr(nts, w.skip)
         if not np.array_equal(v_e, counts * incr):
             raise SystemExit("e2e result differs from the resident counts * incr")

@@ -57,7 +57,9 @@ typedef enum {
     AGOFRT_ERR_NCCL = -4,      /* NCCL missing or failed                                        */
     AGOFRT_ERR_NONFINITE = -5, /* an infinite coordinate or box entry (the reference would spin) */
     AGOFRT_ERR_TOO_LARGE = -6, /* histogram does not fit the shared-memory budget               */
-    AGOFRT_ERR_INTERNAL = -7
+    AGOFRT_ERR_INTERNAL = -7,
+    AGOFRT_ERR_RETYPED = -8    /* agofrt_traj_upload_records: an atom's type differs from the table's (the reference
+                                  warns and goes on, lib/src/trajectory.cpp:640-646: read the window on the host) */
 } agofrt_status;
 
 typedef struct agofrt_ctx agofrt_ctx;    /* a set of GPUs of this process (+ optional peers)   */
@@ -129,6 +131,23 @@ AGOFRT_API int agofrt_traj_upload_wrap(agofrt_traj *traj, size_t first_frame, si
 enum { AGOFRT_UP_WRAP = 1, AGOFRT_UP_WRITEBACK = 2, AGOFRT_UP_SHARED = 4 };
 AGOFRT_API int agofrt_traj_upload_ex(agofrt_traj *traj, size_t first_frame, size_t nframes, const double *pos_aos,
                                      const double *box_internal, unsigned flags, double *pos_wrapped_out);
+/* The window straight from the records of a LAMMPS binary dump: the frame loop of Trajectory::set_access_at
+ * (lib/src/trajectory.cpp:593-674) on the device.  Per atom the dump holds 8 doubles, id type x y z vx vy vz
+ * (lib/include/lammps_struct.h:105-125), in any order and split over any number of chunks per frame.
+ *   agofrt_traj_set_ids         the id -> slot map built from the first frame (slot_to_id[natoms], ids compact enough
+ *                               for a flat table) and the raw type of every slot;
+ *   agofrt_traj_upload_records  frame f of the window = chunks [frame_chunk[f], frame_chunk[f+1]) of chunk_ptr /
+ *                               chunk_atoms (records, e.g. addresses inside the mmap'd file); box_internal as for
+ *                               agofrt_traj_upload.  The raw bytes are staged through page-locked slots and copied as
+ *                               they are; a kernel resolves every record's id, checks its type and scatters x y z to the
+ *                               atom's slot; then wrap / layout / bounds / exchange as in agofrt_traj_upload_ex (same
+ *                               flags; AGOFRT_UP_WRITEBACK also without WRAP: pos_out receives the parsed frames).
+ * An unknown id is AGOFRT_ERR_ARG, a changed type AGOFRT_ERR_RETYPED (callers then read that window on the host, as the
+ * reference does, with its warning).  Velocities are not extracted (g(r,t) never reads them). */
+AGOFRT_API int agofrt_traj_set_ids(agofrt_traj *traj, const int *slot_to_id, const int *slot_raw_type);
+AGOFRT_API int agofrt_traj_upload_records(agofrt_traj *traj, size_t first_frame, size_t nframes, const void *const *chunk_ptr,
+                                          const int *chunk_atoms, const size_t *frame_chunk, const double *box_internal,
+                                          unsigned flags, double *pos_out);
 /* Frames of the device window back in the caller's atom order (wrapped if they were uploaded with AGOFRT_UP_WRAP): the
  * host classes materialise their host copy with it the first time an accessor needs one. */
 AGOFRT_API int agofrt_traj_download(agofrt_traj *traj, size_t first_frame, size_t nframes, double *pos_aos);

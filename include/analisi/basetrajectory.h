@@ -254,6 +254,34 @@ protected:
         host_current = false;
     }
     void download_window(double *pos_out) { dev_window.download(current_timestep, loaded_timesteps, pos_out); }
+    // the same from the raw records of a LAMMPS dump (parsed on the GPUs); false: an atom changed type, nothing uploaded
+    bool upload_records_now(const void *const *chunk_ptr, const int *chunk_atoms, const size_t *frame_chunk, bool wrap,
+                            const int *slot_to_id, const int *slot_raw_type) {
+        get_ntypes();
+        if (!dev_window.valid() || dev_window.capacity() < static_cast<size_t>(loaded_timesteps)) {
+            dev_window.create(natoms, static_cast<int>(buffer_boxes_stride), buffer_type_id, static_cast<int>(ntypes),
+                              loaded_timesteps);
+            ++dev_epoch;
+        }
+        if (!dev_window.ids_set()) dev_window.set_ids(slot_to_id, slot_raw_type);
+        if (!dev_window.upload_records(current_timestep, loaded_timesteps, chunk_ptr, chunk_atoms, frame_chunk, buffer_boxes, wrap))
+            return false;
+        ++host_epoch;
+        dev_uploaded_epoch = host_epoch;
+        host_current = false;
+        return true;
+    }
+    bool upload_next_window_records(size_t first, size_t n, const void *const *chunk_ptr, const int *chunk_atoms,
+                                    const size_t *frame_chunk, const double *box_internal, bool wrap, const int *slot_to_id,
+                                    const int *slot_raw_type) {
+        if (!dev_window_next.valid() || dev_window_next.capacity() < n) {
+            dev_window_next.create(natoms, static_cast<int>(buffer_boxes_stride), buffer_type_id, static_cast<int>(ntypes),
+                                   std::max(n, dev_window.capacity()));
+            next_created = true;
+        }
+        if (!dev_window_next.ids_set()) dev_window_next.set_ids(slot_to_id, slot_raw_type);
+        return dev_window_next.upload_records(first, n, chunk_ptr, chunk_atoms, frame_chunk, box_internal, wrap);
+    }
     bool host_current = true;
 
     // ---- read-ahead of the NEXT window onto the devices (derived containers with a background reader) ----
@@ -275,9 +303,10 @@ protected:
     }
     // Called on the caller's thread after the host buffers were swapped and mark_window_changed(): the device
     // already holds this window
-    void adopt_next_window() {
+    void adopt_next_window(bool host_copy_is_current = true) {
         dev_window.swap(dev_window_next);
         dev_uploaded_epoch = host_epoch;
+        host_current = host_copy_is_current;
         if (next_created) {
             ++dev_epoch;
             next_created = false;

@@ -95,6 +95,13 @@ public:
     void upload_shared(size_t first, size_t n, const double *pos_aos, const double *box_internal, bool wrap, double *wrapped_out);
     // frames of the device window back to the host, caller's atom order
     void download(size_t first, size_t n, double *pos_aos_out);
+    // LAMMPS dump records as the source (agofrt_traj_set_ids / agofrt_traj_upload_records): the id -> slot table once per
+    // window object, then frames as lists of chunks of raw records.  upload_records returns false when an atom's type
+    // changes inside the window (the caller then reads that window on the host, with the reference's warning).
+    bool ids_set() const { return ids_set_; }
+    void set_ids(const int *slot_to_id, const int *slot_raw_type);
+    bool upload_records(size_t first, size_t n, const void *const *chunk_ptr, const int *chunk_atoms, const size_t *frame_chunk,
+                        const double *box_internal, bool wrap);
     void swap(Window &o) {
         agofrt_traj *t = traj_;
         traj_ = o.traj_;
@@ -102,6 +109,9 @@ public:
         size_t c = cap_;
         cap_ = o.cap_;
         o.cap_ = c;
+        bool i = ids_set_;
+        ids_set_ = o.ids_set_;
+        o.ids_set_ = i;
     }
     agofrt_traj *handle() { return traj_; }
     // bumped on every create(): plans made on an older handle must be rebuilt
@@ -111,6 +121,7 @@ private:
     agofrt_traj *traj_ = nullptr;
     size_t cap_ = 0;
     uint64_t generation_ = 0;
+    bool ids_set_ = false;
 };
 
 // BaseTrajectory::pbc_wrap (reference lib/include/basetrajectory.h:145-161) of whole frames, on the GPU

@@ -36,7 +36,9 @@ public:
 
     template <bool SAFE = true>
     double *positions(const size_t &timestep, const size_t &atomo) {
-        return window_ptr<SAFE, true>(buffer_positions, timestep, atomo, 3 * natoms, 3);
+        double *p = window_ptr<SAFE, true>(buffer_positions, timestep, atomo, 3 * natoms, 3);
+        sync_host();   // a window parsed on the GPUs reaches the host the first time somebody asks for it
+        return p;
     }
     template <bool SAFE = true>
     double *velocity(const size_t &timestep, const size_t &atomo) {
@@ -74,6 +76,8 @@ public:
     void set_load_velocities(bool v) { load_velocities = v; }
     // the caller will ask for windows `stride` frames apart (BlockAverageG does): read ahead from the first one
     void set_access_stride_hint(size_t stride) { stride_hint = stride; }
+    // the window lives on the GPUs (parsed there from the raw records); fetch it for the host accessors
+    void materialise_host_positions() { download_window(pos_buf.data()); }
 
 private:
     template <bool SAFE, bool ATOM>
@@ -107,6 +111,16 @@ private:
     void read_frames(size_t first, size_t last, size_t origin, double *P0, double *B0, bool own_window);
     void start_prefetch(size_t target);
     void cancel_prefetch();
+    // Device-side ingest: the records of a window go to the GPUs as they are in the file and are parsed there (id -> slot,
+    // scatter, box rows from the headers, wrap).  Possible when positions are all that is wanted (no velocities, no
+    // centres of mass) and the ids are compact enough for a flat table.  ANALISI_DEVICE_PARSE=0 keeps the host parser.
+    bool device_parse_possible() const;
+    struct RecordTable {
+        std::vector<const void *> ptr;
+        std::vector<int> atoms;
+        std::vector<size_t> frame_chunk;
+    };
+    void gather_records(size_t first, size_t n, RecordTable &tab, double *B0);
 
     int fd = -1;
     char *file = nullptr;
@@ -130,7 +144,7 @@ private:
     std::thread prefetch_thread;
     std::exception_ptr prefetch_error;
     size_t prefetch_target = 0, stride_hint = 0;
-    bool prefetch_valid = false, prefetch_enabled = true, prefetch_uploaded = false;
+    bool prefetch_valid = false, prefetch_enabled = true, prefetch_uploaded = false, prefetch_records = false;
 };
 
 #endif

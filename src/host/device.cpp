@@ -61,6 +61,7 @@ void Window::create(size_t natoms, int box_stride, const int *type_id, int ntype
     check(agofrt_traj_create(&traj_, Context::instance().handle(), natoms, box_stride, type_id, ntypes, max_frames),
           "agofrt_traj_create");
     cap_ = max_frames;
+    ids_set_ = false;
     ++generation_;
 }
 
@@ -81,6 +82,20 @@ void Window::upload_wrap(size_t first, size_t n, double *pos_aos_inout, const do
 void Window::upload_shared(size_t first, size_t n, const double *pos_aos, const double *box_internal, bool wrap, double *wrapped_out) {
     const unsigned flags = AGOFRT_UP_SHARED | (wrap ? AGOFRT_UP_WRAP : 0u) | (wrap && wrapped_out ? AGOFRT_UP_WRITEBACK : 0u);
     check(agofrt_traj_upload_ex(traj_, first, n, pos_aos, box_internal, flags, wrapped_out), "agofrt_traj_upload_ex");
+}
+
+void Window::set_ids(const int *slot_to_id, const int *slot_raw_type) {
+    check(agofrt_traj_set_ids(traj_, slot_to_id, slot_raw_type), "agofrt_traj_set_ids");
+    ids_set_ = true;
+}
+
+bool Window::upload_records(size_t first, size_t n, const void *const *chunk_ptr, const int *chunk_atoms, const size_t *frame_chunk,
+                            const double *box_internal, bool wrap) {
+    const int rc = agofrt_traj_upload_records(traj_, first, n, chunk_ptr, chunk_atoms, frame_chunk, box_internal,
+                                              AGOFRT_UP_SHARED | (wrap ? AGOFRT_UP_WRAP : 0u), nullptr);
+    if (rc == AGOFRT_ERR_RETYPED) return false;
+    check(rc, "agofrt_traj_upload_records");
+    return true;
 }
 
 void Window::download(size_t first, size_t n, double *pos_aos_out) {

@@ -281,6 +281,40 @@ void Trajectory::read_frames(size_t first, size_t last, size_t origin, double *P
         if (e) std::rethrow_exception(e);   // first failure, on the caller's thread (as the reference does)
 }
 
+bool Trajectory::device_parse_possible() const {
+    if (load_velocities || dense_slot.empty() || natoms == 0) return false;
+    static const bool enabled = [] {
+        const char *e = std::getenv("ANALISI_DEVICE_PARSE");
+        return !e || std::atoi(e) != 0;
+    }();
+    return enabled;
+}
+
+// Headers of frames [first, first + n) -- box rows (internal format) into B0, LAMMPS timesteps -- and the table of their
+// chunks of raw records, which stay where they are in the mapping.  The caller has indexed the file up to the last
+// frame (ensure_indexed): this function only reads, like read_frame_to.
+void Trajectory::gather_records(size_t first, size_t n, RecordTable &tab, double *B0) {
+    tab.ptr.clear();
+    tab.atoms.clear();
+    tab.frame_chunk.assign(1, 0);
+    std::vector<LammpsChunk> chunks;
+    for (size_t f = first; f < first + n; ++f) {
+        LammpsFrameHeader h;
+        frame_bytes(offsets[f], h, &chunks);
+        lammps_steps[f] = h.timestep;
+        if ((h.triclinic != 0) != triclinic) throw std::runtime_error("Error: the cell kind (triclinic flag) changes along the trajectory\n");
+        double *b = B0 + (f - first) * buffer_boxes_stride;
+        std::memcpy(b, h.box, 6 * sizeof(double));
+        if (triclinic) std::memcpy(b + 6, h.xy_xz_yz, 3 * sizeof(double));
+        lammps_to_internal(b);
+        for (const LammpsChunk &c : chunks) {
+            tab.ptr.push_back(c.data);
+            tab.atoms.push_back(c.natoms);
+        }
+        tab.frame_chunk.push_back(tab.ptr.size());
+    }
+}
+
 // Read-ahead: callers that walk the file in equal steps (BlockAverageG: block after block) find the next
 // window already parsed into a second page-locked buffer, read by a background thread while the GPUs were
 // busy with the current block.  Only the host part runs ahead (parse + scatter); wrap and upload stay on the
@@ -309,8 +343,23 @@ void Trajectory::start_prefetch(size_t target) {
     prefetch_error = nullptr;
     prefetch_uploaded = false;
     const bool to_device = device_active();   // decided on the caller's thread
-    prefetch_thread = std::thread([this, target, W, to_device]() {
+    const bool records = to_device && device_parse_possible();
+    prefetch_records = false;
+    prefetch_thread = std::thread([this, target, W, to_device, records]() {
         try {
+            if (records) {
+                // the raw records go to the second device window and are parsed, wrapped and laid out there, under
+                // the pair kernels of the block the caller is computing; the host copy follows on demand
+                RecordTable tab;
+                gather_records(target, W, tab, boxes_alt.data());
+                if (upload_next_window_records(target, W, tab.ptr.data(), tab.atoms.data(), tab.frame_chunk.data(), boxes_alt.data(),
+                                               wrap_pbc, slot_to_id.data(), raw_type.data())) {
+                    prefetch_uploaded = true;
+                    prefetch_records = true;
+                    return;
+                }
+                // an atom changed type in that window: the host parser reads it (and warns, as the reference does)
+            }
             read_frames(target, target + W, target, pos_alt.data(), boxes_alt.data(), false);
             if (to_device) {
                 // wrap on the device, lay the window out there, bring the wrapped frames back: all of it under
@@ -335,11 +384,11 @@ Trajectory::Errori Trajectory::set_access_at(const size_t &timestep) {
     const size_t W = static_cast<size_t>(loaded_timesteps);
     const bool had_window = window_loaded;
     const size_t previous = static_cast<size_t>(current_timestep);
-    auto finish = [&](const char *how, bool on_device) {
+    auto finish = [&](const char *how, bool on_device, bool host_copy_is_current = true, bool uploaded_here = false) {
         current_timestep = static_cast<ssize_t>(timestep);
         window_loaded = true;
-        mark_window_changed();
-        if (on_device) adopt_next_window();
+        if (!uploaded_here) mark_window_changed();   // (upload_records_now has already matched the epochs)
+        if (on_device) adopt_next_window(host_copy_is_current);
         // equal steps forward (or the stride the block loop announced): read the next window ahead
         if (had_window && timestep > previous)
             start_prefetch(timestep + (timestep - previous));
@@ -361,10 +410,24 @@ Trajectory::Errori Trajectory::set_access_at(const size_t &timestep) {
             buffer_positions = pos_buf.data();
             buffer_boxes = boxes.data();
             window_loaded = false;
+            if (prefetch_uploaded && prefetch_records) return finish(" (read ahead: parsed on the GPUs)", true, false);
             if (prefetch_uploaded) return finish(" (read ahead, already on the GPUs)", true);
             if (wrap_pbc) pbc_wrap_frames(0, W);
             return finish(" (read ahead)", false);
         }
+    }
+
+    // Device-side ingest: the records of the window go to the GPUs as they are and are parsed there
+    if (device_parse_possible()) {
+        ensure_indexed(timestep + W - 1);
+        RecordTable tab;
+        gather_records(timestep, W, tab, buffer_boxes);
+        madvise(file, offsets[timestep] & ~static_cast<size_t>(sysconf(_SC_PAGESIZE) - 1), MADV_DONTNEED);
+        current_timestep = static_cast<ssize_t>(timestep);   // upload_records_now uploads [current_timestep, +loaded_timesteps)
+        if (upload_records_now(tab.ptr.data(), tab.atoms.data(), tab.frame_chunk.data(), wrap_pbc, slot_to_id.data(), raw_type.data()))
+            return finish(" (parsed on the GPUs)", false, false, true);
+        current_timestep = static_cast<ssize_t>(previous);    // an atom changed type: the host parser below reads the window
+        window_loaded = false;
     }
 
     // overlap with what is already in the window: move it instead of reading it again (reference :542-586)

@@ -236,6 +236,51 @@ def test_cli_c1_bundled_trajectory(host, tmp_path):
     assert got == want
 
 
+@pytest.mark.parametrize("format2020", [False, True])
+def test_cli_device_side_ingest_equals_host_reader(host, tmp_path, format2020):
+    """The window parsed on the GPUs from the raw dump records (agofrt_traj_upload_records: ids shuffled in every frame,
+    three chunks per frame, both header flavours) and the window parsed by the host reader give the same output, with
+    blocks one by one and as a batch; a trajectory in which an atom changes type falls back to the host reader, which
+    warns like the reference (lib/src/trajectory.cpp:640-646)."""
+    cli, _ = host
+    pos, box, types = synth.small_case(23, (5, 4, 3), 1.05, 2, True, 50, "parity")
+    path = str(tmp_path / "d.bin")
+    synth.write_lammps_binary(path, pos, box, types * 2 + 1, nchunk=3, shuffle_seed=11, format2020=format2020,
+                              ids=np.arange(pos.shape[1]) * 2 + 7)
+    argv = ["-i", path, "-g", "30", "-F", "0.0", "2.4", "-S", "4", "-s", "2", "-B", "5"]
+
+    def run(**env):
+        r = subprocess.run([cli] + argv, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, cwd=str(tmp_path), timeout=600,
+                           env=dict(os.environ, **env))
+        assert r.returncode == 0, r.stderr[-2000:]
+        return r
+    base = run(ANALISI_DEVICE_PARSE="0", ANALISI_BLOCK_BATCH="0")
+    assert "parsed on the GPUs" not in base.stderr
+    for env in (dict(ANALISI_DEVICE_PARSE="1", ANALISI_BLOCK_BATCH="0"), dict(ANALISI_DEVICE_PARSE="1", ANALISI_BLOCK_BATCH="1"),
+                dict(ANALISI_DEVICE_PARSE="0", ANALISI_BLOCK_BATCH="1"), dict(ANALISI_DEVICE_PARSE="1", ANALISI_PREFETCH="0")):
+        r = run(**env)
+        assert r.stdout == base.stdout, env
+        assert ("parsed on the GPUs" in r.stderr) == (env["ANALISI_DEVICE_PARSE"] == "1")
+        assert ("as one batch on the GPUs" in r.stderr) == (env.get("ANALISI_BLOCK_BATCH") == "1")
+    # an atom changes type in frame 20
+    raw = (types * 2 + 1).astype(np.int64)
+    path2 = str(tmp_path / "e.bin")
+    with open(path2, "wb") as out:
+        for f in range(pos.shape[0]):
+            t = raw.copy()
+            if f >= 20:
+                t[5] = 9 - t[5] if t[5] in (1, 3) else t[5]
+                t[5] = {1: 3, 3: 1}[int(raw[5])]
+            one = str(tmp_path / "one.bin")
+            synth.write_lammps_binary(one, pos[f:f + 1], box[f:f + 1], t, format2020=format2020, first_step=f)
+            out.write(open(one, "rb").read())
+    argv[1] = path2
+    a = run(ANALISI_DEVICE_PARSE="0", ANALISI_BLOCK_BATCH="0")
+    b = run(ANALISI_DEVICE_PARSE="1", ANALISI_BLOCK_BATCH="0")
+    assert a.stdout == b.stdout
+    assert "WARNING: atomic type for atom with id 5 is changing" in a.stderr and "WARNING: atomic type for atom with id 5 is changing" in b.stderr
+
+
 def test_cli_c1_against_the_reference_itself(host, tmp_path):
     """BASELINE.json configs[0] against the UNMODIFIED reference: tests/golden/c1_reference.* holds what the compiled
     reference's own BlockAverage<Gofrt> chain produced for `analisi -i tests/data/lammps.bin -g 200 -F 0.7 3.5`

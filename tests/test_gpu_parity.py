@@ -671,6 +671,55 @@ def test_batch_of_whole_blocks(ctx, natoms, tri):
     tr.close()
 
 
+@pytest.mark.parametrize("tri", [False, True])
+def test_window_from_raw_dump_records(ctx, tri):
+    """agofrt_traj_upload_records: the frame loop of Trajectory::set_access_at on the device -- records in a different
+    order in every frame, split over several chunks, ids that are not 0..N-1 -- gives the window the host reader gives."""
+    pos, box, types = synth.small_case(97, (6, 5, 4), 1.08, 2, tri, 9)
+    bi = synth.lammps_rows_to_internal(box)
+    n = pos.shape[1]
+    rng = np.random.default_rng(5)
+    ids = rng.permutation(3 * n)[:n].astype(np.int32) + 1        # sparse-ish, shuffled, starting above 0
+    raw_type = (types * 2 + 3).astype(np.int32)
+    frames = []
+    for f in range(pos.shape[0]):
+        order = rng.permutation(n)
+        rec = np.zeros((n, 8))
+        rec[:, 0] = ids[order]
+        rec[:, 1] = raw_type[order]
+        rec[:, 2:5] = pos[f, order]
+        rec[:, 5:8] = rng.normal(size=(n, 3))                    # velocities: ignored
+        cuts = [0, n // 3, n // 3 + 7, n]
+        frames.append([rec[cuts[k]:cuts[k + 1]] for k in range(3)])
+    tr = cabi.DeviceTrajectory(ctx, n, bi.shape[1], types, 2, pos.shape[0])
+    with pytest.raises(cabi.AgofrtError):
+        tr.upload_records(0, frames, bi)                         # no id table yet
+    tr.set_ids(ids, raw_type)
+    back = np.empty_like(pos)
+    tr.upload_records(0, frames, bi, wrap=True, out=back)
+    wrapped = oracle.pbc_wrap(pos, bi)
+    assert np.array_equal(back, wrapped) and np.array_equal(tr.download(0, pos.shape[0]), wrapped)
+    plan = cabi.Plan(tr, 0.0, 2.8, 48)
+    c, st = plan.block(1, 5, 3, 2, 1)
+    assert np.array_equal(c, oracle.counts(wrapped, bi, types, 0.0, 2.8, 48, 3, 5, primo=1, skip=2, ntypes=2))
+    # without the wrap the parsed frames come back as they are in the file
+    tr.upload_records(0, frames, bi, out=back)
+    assert np.array_equal(back, pos)
+    # an id that is not in the table, and a changed type
+    bad = [[c.copy() for c in fr] for fr in frames]
+    bad[4][1][2, 0] = 10 * n + 5
+    with pytest.raises(cabi.AgofrtError) as e:
+        tr.upload_records(0, bad, bi)
+    assert e.value.code == cabi.ERR_ARG
+    bad = [[c.copy() for c in fr] for fr in frames]
+    bad[7][0][0, 1] += 1
+    with pytest.raises(cabi.AgofrtError) as e:
+        tr.upload_records(0, bad, bi)
+    assert e.value.code == cabi.ERR_RETYPED
+    plan.close()
+    tr.close()
+
+
 def test_c4_subset_against_the_reference_itself(ctx):
     """The north-star shape at full size -- 100 000 atoms, triclinic, 500 bins -- on the (lag, origin) subset that is
     bench.py's default step (26 lags x 8 origins = 2.08e12 pair evaluations): bit-exact against the counts of the
