@@ -216,6 +216,8 @@ struct TrajDev {
                                     //      4 records with an unknown atom id, 5 records whose type changed (agofrt_traj_upload_records)
     double *probe = nullptr;        // [4]: result of agofrt_traj_d2_pair
     unsigned long long *nb_hist = nullptr;  // neighbour-count histogram [ntypes][natoms+1] (agofrt_neighbour_hist)
+    unsigned int *nb_counts = nullptr;      // per-atom neighbour counts [frames of the call][ntypes][npad]
+    size_t nb_counts_len = 0;
     int *nb_frames = nullptr;
     size_t nb_frames_cap = 0;
     int *id_table = nullptr;        // LAMMPS atom id -> slot of the caller's atom order (agofrt_traj_set_ids), -1 = unknown id
@@ -566,6 +568,7 @@ static void free_traj_dev(agofrt_traj *t) {
         cudaFree(d.probe);
         cudaFree(d.nb_hist);
         cudaFree(d.nb_frames);
+        cudaFree(d.nb_counts);
         cudaFree(d.id_table);
         cudaFree(d.slot_type);
         cudaFree(d.raw);
@@ -741,6 +744,32 @@ static void parallel_copy(void *dst, const void *src, size_t bytes) {
     for (std::thread &th : pool) th.join();
 }
 
+// the same for a list of pieces (the chunks of many small frames): the pieces are dealt to the threads by bytes
+struct CopyPiece {
+    void *dst;
+    const void *src;
+    size_t bytes;
+};
+static void parallel_copy_pieces(const std::vector<CopyPiece> &pieces) {
+    size_t total = 0;
+    for (const CopyPiece &p : pieces) total += p.bytes;
+    const size_t nth = std::min<size_t>({8, std::max(1u, std::thread::hardware_concurrency()), std::max<size_t>(1, total / (1u << 20))});
+    if (nth <= 1 || pieces.size() < 2 * nth) {
+        for (const CopyPiece &p : pieces) parallel_copy(p.dst, p.src, p.bytes);
+        return;
+    }
+    std::vector<std::thread> pool;
+    const size_t each = (pieces.size() + nth - 1) / nth;
+    for (size_t k = 0; k < nth; ++k) {
+        const size_t a = k * each, b = std::min(pieces.size(), a + each);
+        if (a >= b) break;
+        pool.emplace_back([&pieces, a, b]() {
+            for (size_t i = a; i < b; ++i) memcpy(pieces[i].dst, pieces[i].src, pieces[i].bytes);
+        });
+    }
+    for (std::thread &th : pool) th.join();
+}
+
 static bool is_pinned(const void *p) {
     cudaPointerAttributes a;
     if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
@@ -776,7 +805,7 @@ static int upload_impl(agofrt_traj *t, size_t first_frame, size_t nframes, const
     auto since = [&](std::chrono::steady_clock::time_point a) {
         return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - a).count();
     };
-    double ms_perm = 0, ms_copy = 0;
+    double ms_perm = 0, ms_copy = 0, ms_setup = 0, ms_loop = 0;
     t->first_frame = first_frame;
     t->nframes = nframes;
     t->box6.assign(nframes * 6, 0.0);
@@ -870,6 +899,7 @@ static int upload_impl(agofrt_traj *t, size_t first_frame, size_t nframes, const
         CU(cudaMemcpyAsync(d.box_stage, box_internal, nframes * t->stride * sizeof(double), cudaMemcpyHostToDevice, d.up));
         CU(launch_pack_box(d.box_stage, t->stride, static_cast<int>(nframes), d.box6, d.up));
     }
+    ms_setup = since(t_begin);
     if (t->npad > 0) {
         const bool pinned_src = !rec && is_pinned(pos_in);
         // bytes per frame on the host side of the copy: AoS positions, or the raw records (8 doubles per atom)
@@ -924,17 +954,19 @@ static int upload_impl(agofrt_traj *t, size_t first_frame, size_t nframes, const
                     if (rec) {
                         // the chunks of every frame, one after the other: natoms records per frame
                         char *w = reinterpret_cast<char *>(hs);
+                        std::vector<CopyPiece> pieces;
                         for (size_t f = f0; f < f0 + nf; ++f) {
                             size_t atoms = 0;
                             for (size_t c = rec->frame_chunk[f]; c < rec->frame_chunk[f + 1]; ++c) {
                                 const size_t nb = static_cast<size_t>(rec->chunk_atoms[c]) * 8 * sizeof(double);
                                 atoms += static_cast<size_t>(rec->chunk_atoms[c]);
                                 if (atoms > t->natoms) return fail(AGOFRT_ERR_ARG, "frame %zu holds more records than atoms", first_frame + f);
-                                parallel_copy(w, rec->chunk_ptr[c], nb);
+                                pieces.push_back({w, rec->chunk_ptr[c], nb});
                                 w += nb;
                             }
                             if (atoms != t->natoms) return fail(AGOFRT_ERR_ARG, "frame %zu holds %zu records for %zu atoms", first_frame + f, atoms, t->natoms);
                         }
+                        parallel_copy_pieces(pieces);
                     } else {
                         parallel_copy(hs, src, nf * frame_bytes);
                     }
@@ -961,6 +993,7 @@ static int upload_impl(agofrt_traj *t, size_t first_frame, size_t nframes, const
                                      d.pos + f0 * 3 * static_cast<size_t>(t->npad), d.up));
             }
         }
+        ms_loop = since(t_begin) - ms_setup;
         // coordinate bounds per frame: every device for its share, or device 0 for the replicated window
         for (int i = 0; i < nloc; ++i) {
             if (!shared && i > 0) break;
@@ -1017,9 +1050,9 @@ static int upload_impl(agofrt_traj *t, size_t first_frame, size_t nframes, const
         CU(cudaStreamSynchronize(t->dev[i].up));
     }
     if (debug)
-        fprintf(stderr, "[agofrt] upload of %zu frames x %zu atoms (%s%s%s): %.1f ms (permutation %.1f, host staging copies %.1f)\n", nframes,
-                t->natoms, wrap ? "wrap " : "", shared ? "shared " : "replicated ", is_pinned(pos_in) ? "pinned" : "pageable",
-                since(t_begin), ms_perm, ms_copy);
+        fprintf(stderr, "[agofrt] upload of %zu frames x %zu atoms (%s%s%s): %.1f ms (setup %.1f of which permutation %.1f, copy loop %.1f of which host staging copies %.1f)\n", nframes,
+                t->natoms, wrap ? "wrap " : "", shared ? "shared " : "replicated ", rec ? "records" : (is_pinned(pos_in) ? "pinned" : "pageable"),
+                since(t_begin), ms_setup, ms_perm, ms_loop, ms_copy);
     return AGOFRT_OK;
 }
 
@@ -2089,6 +2122,10 @@ extern "C" int agofrt_blocks(agofrt_plan *p, size_t primo0, size_t stride, unsig
     const int nt = t->ntypes;
     const size_t len = static_cast<size_t>(leff) * nt * (nt + 1) * p->nbin;
     if (nblocks == 0 || len == 0) return AGOFRT_OK;
+    const bool debug = getenv("AGOFRT_DEBUG") != nullptr;
+    const auto t_begin = std::chrono::steady_clock::now();
+    auto since0 = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count(); };
+    double ms_alloc = 0, ms_enqueue = 0;
     if (static_cast<double>(nblocks) * static_cast<double>(len) * 8.0 > 2.0e9)
         return fail(AGOFRT_ERR_TOO_LARGE, "%u blocks of %zu counters do not fit the batch buffer (use agofrt_block)", nblocks, len);
     for (int i = 0; i < nloc; ++i) {
@@ -2103,6 +2140,7 @@ extern "C" int agofrt_blocks(agofrt_plan *p, size_t primo0, size_t stride, unsig
         }
         CU(cudaEventRecord(ctx->devs[i].ev_begin, ctx->devs[i].stream));
     }
+    ms_alloc = since0();
     agofrt_stats sum;
     memset(&sum, 0, sizeof(sum));
     std::vector<char> first(nloc, 1);
@@ -2130,6 +2168,7 @@ extern "C" int agofrt_blocks(agofrt_plan *p, size_t primo0, size_t stride, unsig
         CU(cudaSetDevice(ctx->devs[i].id));
         CU(cudaEventRecord(ctx->devs[i].ev_k1, ctx->devs[i].stream));
     }
+    ms_enqueue = since0() - ms_alloc;
     // every device receives every block
     if (world > 1) {
         NcclApi &api = nccl_api();
@@ -2171,6 +2210,9 @@ extern "C" int agofrt_blocks(agofrt_plan *p, size_t primo0, size_t stride, unsig
         total_ms = std::max<double>(total_ms, b);
         if (p->host_flags[i]) return fail(AGOFRT_ERR_NONFINITE, "minimum image did not converge within %d images", kWrapCap);
     }
+    if (debug)
+        fprintf(stderr, "[agofrt] batch of %u blocks x %zu counters on %d device(s): %.1f ms (buffers %.1f, enqueue %.1f, device %.1f)\n", nblocks, len,
+                world, since0(), ms_alloc, ms_enqueue, total_ms);
     p->batch_blocks = nblocks;
     p->batch_block_len = len;
     p->last_len = len;
@@ -2366,6 +2408,15 @@ extern "C" int agofrt_neighbour_hist(agofrt_traj *t, double r, size_t tstart, un
     const size_t nfr = fr_fast.size() + fr_gen.size();
     const int tile = neighbour_tile_atoms();
     const int n_itiles = std::max(1, (t->npad + tile - 1) / tile);
+    // j chunks: enough work units for every SM of every device even when the call lists few frames
+    int total_ctas = 0;
+    for (const Dev &d : ctx->devs) total_ctas += 8 * d.sm_count;
+    total_ctas = total_ctas / nloc * world;
+    int n_jchunks = static_cast<int>(std::min<uint64_t>((t->npad + 1023) / 1024,
+                                                        (4ull * total_ctas + nfr * n_itiles - 1) / std::max<uint64_t>(1, nfr * n_itiles)));
+    n_jchunks = std::max(1, n_jchunks);
+    int jchunk = ((t->npad + n_jchunks - 1) / n_jchunks + 7) / 8 * 8;
+    n_jchunks = std::max(1, (t->npad + jchunk - 1) / jchunk);
     const bool tri = t->stride == 9;
     double kernel_ms = 0;
     unsigned launches = 0;
@@ -2381,7 +2432,16 @@ extern "C" int agofrt_neighbour_hist(agofrt_traj *t, double r, size_t tstart, un
             CU(cudaMalloc(&td.nb_frames, nfr * sizeof(int)));
             td.nb_frames_cap = nfr;
         }
+        const size_t ncounts = nfr * static_cast<size_t>(t->ntypes) * t->npad;
+        if (ncounts > td.nb_counts_len) {
+            cudaFree(td.nb_counts);
+            td.nb_counts = nullptr;
+            td.nb_counts_len = 0;
+            CU(cudaMalloc(&td.nb_counts, ncounts * sizeof(unsigned int)));
+            td.nb_counts_len = ncounts;
+        }
         CU(cudaMemsetAsync(td.nb_hist, 0, hlen * sizeof(unsigned long long), dv.stream));
+        CU(cudaMemsetAsync(td.nb_counts, 0, ncounts * sizeof(unsigned int), dv.stream));
         CU(cudaMemsetAsync(td.flags + 1, 0, sizeof(unsigned int), dv.stream));
         if (!fr_fast.empty())
             CU(cudaMemcpyAsync(td.nb_frames, fr_fast.data(), fr_fast.size() * sizeof(int), cudaMemcpyHostToDevice, dv.stream));
@@ -2392,9 +2452,11 @@ extern "C" int agofrt_neighbour_hist(agofrt_traj *t, double r, size_t tstart, un
         for (int pass = 0; pass < 2; ++pass) {
             const std::vector<int> &list = pass == 0 ? fr_fast : fr_gen;
             if (list.empty()) continue;
-            uint64_t ub = 0, ue = 0;
-            agofrt_shard_range(static_cast<uint64_t>(list.size()) * n_itiles, first_rank + i, world, &ub, &ue);
-            if (ue <= ub) continue;
+            // the (frame, i tile) pairs are dealt to the devices; all the j chunks of a pair run on its device, so the
+            // per-atom counts are complete there and only the histogram is all-reduced
+            uint64_t vb = 0, ve = 0;
+            agofrt_shard_range(static_cast<uint64_t>(list.size()) * n_itiles, first_rank + i, world, &vb, &ve);
+            if (ve <= vb) continue;
             NeighbourParams np;
             np.pos = td.pos;
             np.box = td.box6;
@@ -2402,17 +2464,24 @@ extern "C" int agofrt_neighbour_hist(agofrt_traj *t, double r, size_t tstart, un
             np.type_start = td.type_start;
             np.frames = td.nb_frames + (pass == 0 ? 0 : fr_fast.size());
             np.hist = td.nb_hist;
+            np.counts = td.nb_counts + (pass == 0 ? 0 : fr_fast.size()) * static_cast<size_t>(t->ntypes) * t->npad;
             np.error_flag = td.flags + 1;
             np.r2 = r * r;   // reference lib/src/istogrammaatomiraggio.cpp:17
-            np.unit_begin = static_cast<unsigned>(ub);
-            np.unit_end = static_cast<unsigned>(ue);
+            np.unit_begin = static_cast<unsigned>(vb * n_jchunks);
+            np.unit_end = static_cast<unsigned>(ve * n_jchunks);
             np.npad = t->npad;
             np.ntypes = t->ntypes;
             np.n_itiles = n_itiles;
+            np.n_jchunks = n_jchunks;
+            np.jchunk = jchunk;
             np.hist_stride = hstride;
-            const int grid = static_cast<int>(std::min<uint64_t>(ue - ub, static_cast<uint64_t>(dv.sm_count) * 8));
+            const uint64_t units = (ve - vb) * n_jchunks;
+            const int grid = static_cast<int>(std::min<uint64_t>(units, static_cast<uint64_t>(dv.sm_count) * 8));
             CU(launch_neighbour_kernel(tri, pass == 0, grid, dv.stream, np));
-            ++launches;
+            const uint64_t words = (ve - vb) * static_cast<uint64_t>(t->ntypes) * tile;
+            CU(launch_neighbour_finish(static_cast<int>(std::min<uint64_t>((words + 255) / 256, static_cast<uint64_t>(dv.sm_count) * 8)),
+                                       dv.stream, np, static_cast<unsigned>(vb), static_cast<unsigned>(ve)));
+            launches += 2;
         }
         CU(cudaEventRecord(dv.ev_k1, dv.stream));
     }

@@ -1635,14 +1635,22 @@ constexpr int kNbThreads = 256;
 constexpr int kNbIPT = 2;
 constexpr int kNbTileJ = 512;
 
+// Two steps, so that the j atoms of one (frame, i tile) can be spread over several work units (few frames of a large
+// system: 192 (frame, tile) units would leave most of the 148 SMs idle):
+//   neighbour_kernel        unit = (frame, tile of 512 i atoms, chunk of j atoms): per i atom and j type the number of j
+//                           of the chunk within r, added to counts[frame][type][slot] (u32, atomic: chunks meet there)
+//   neighbour_finish_kernel hist[type][counts[frame][type][slot]] += 1 for every real atom
 template <bool TRI, bool FAST>
 __global__ void __launch_bounds__(kNbThreads) neighbour_kernel(const NeighbourParams p) {
     __shared__ __align__(16) double sj[3][kNbTileJ];
     const int tid = threadIdx.x;
     unsigned int wrap_bad = 0;
+    const unsigned int per_frame = static_cast<unsigned int>(p.n_itiles) * static_cast<unsigned int>(p.n_jchunks);
     for (unsigned int u = p.unit_begin + blockIdx.x; u < p.unit_end; u += gridDim.x) {
-        const int f = p.frames[u / static_cast<unsigned int>(p.n_itiles)];
-        const int itile = static_cast<int>(u % static_cast<unsigned int>(p.n_itiles));
+        const unsigned int fidx = u / per_frame, rest = u - fidx * per_frame;
+        const int itile = static_cast<int>(rest / static_cast<unsigned int>(p.n_jchunks));
+        const int jc = static_cast<int>(rest % static_cast<unsigned int>(p.n_jchunks));
+        const int f = p.frames[fidx];
         const double *pf = p.pos + static_cast<size_t>(f) * 3 * p.npad;
         const double *bx = p.box + static_cast<size_t>(f) * 6;
         BoxRegs b;
@@ -1658,11 +1666,9 @@ __global__ void __launch_bounds__(kNbThreads) neighbour_kernel(const NeighbourPa
         const double nLx = __dmul_rn(b.lhx, -2.0), nLy = __dmul_rn(b.lhy, -2.0), nLz = __dmul_rn(b.lhz, -2.0);
         double xi[kNbIPT], yi[kNbIPT], zi[kNbIPT];
         int slot[kNbIPT];
-        bool real[kNbIPT];
 #pragma unroll
         for (int k = 0; k < kNbIPT; ++k) {
             slot[k] = itile * (kNbThreads * kNbIPT) + k * kNbThreads + tid;
-            real[k] = slot[k] < p.npad && p.perm[slot[k]] >= 0;
             if (slot[k] < p.npad) {
                 xi[k] = pf[slot[k]];
                 yi[k] = pf[p.npad + slot[k]];
@@ -1671,8 +1677,10 @@ __global__ void __launch_bounds__(kNbThreads) neighbour_kernel(const NeighbourPa
                 xi[k] = yi[k] = zi[k] = __longlong_as_double(0x7ff8000000000000ll);
             }
         }
+        const int cbeg = jc * p.jchunk, cend = min(cbeg + p.jchunk, p.npad);
         for (int ty = 0; ty < p.ntypes; ++ty) {
-            const int jb = p.type_start[ty], je = p.type_start[ty + 1];
+            const int jb = max(p.type_start[ty], cbeg), je = min(p.type_start[ty + 1], cend);
+            if (jb >= je) continue;
             unsigned int cnt[kNbIPT];
 #pragma unroll
             for (int k = 0; k < kNbIPT; ++k) cnt[k] = 0;
@@ -1703,10 +1711,27 @@ __global__ void __launch_bounds__(kNbThreads) neighbour_kernel(const NeighbourPa
             }
 #pragma unroll
             for (int k = 0; k < kNbIPT; ++k)
-                if (real[k]) atomicAdd(p.hist + static_cast<size_t>(ty) * p.hist_stride + cnt[k], 1ull);
+                if (slot[k] < p.npad && cnt[k])
+                    atomicAdd(p.counts + (static_cast<size_t>(fidx) * p.ntypes + ty) * p.npad + slot[k], cnt[k]);
         }
     }
     if (wrap_bad) atomicExch(p.error_flag, 1u);
+}
+
+// the (frame, i tile) pairs [v_begin, v_end) of this device: their counts are complete (all j chunks ran here)
+__global__ void neighbour_finish_kernel(const NeighbourParams p, unsigned int v_begin, unsigned int v_end) {
+    const int tile = kNbThreads * kNbIPT;
+    const size_t n = static_cast<size_t>(v_end - v_begin) * p.ntypes * tile;
+    for (size_t k = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; k < n; k += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const int s = static_cast<int>(k % tile);
+        const int ty = static_cast<int>((k / tile) % p.ntypes);
+        const unsigned int v = v_begin + static_cast<unsigned int>(k / (static_cast<size_t>(tile) * p.ntypes));
+        const unsigned int fidx = v / static_cast<unsigned int>(p.n_itiles), itile = v % static_cast<unsigned int>(p.n_itiles);
+        const int slot = static_cast<int>(itile) * tile + s;
+        if (slot >= p.npad || p.perm[slot] < 0) continue;   // past the end, or a ghost slot
+        const unsigned int c = p.counts[(static_cast<size_t>(fidx) * p.ntypes + ty) * p.npad + slot];
+        atomicAdd(p.hist + static_cast<size_t>(ty) * p.hist_stride + c, 1ull);
+    }
 }
 
 cudaError_t launch_neighbour_kernel(bool triclinic, bool fast, int grid, cudaStream_t stream, const NeighbourParams &p) {
@@ -1722,6 +1747,12 @@ cudaError_t launch_neighbour_kernel(bool triclinic, bool fast, int grid, cudaStr
         else
             neighbour_kernel<false, false><<<grid, kNbThreads, 0, stream>>>(p);
     }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_neighbour_finish(int grid, cudaStream_t stream, const NeighbourParams &p, unsigned int v_begin, unsigned int v_end) {
+    if (grid <= 0 || v_end <= v_begin) return cudaSuccess;
+    neighbour_finish_kernel<<<grid, 256, 0, stream>>>(p, v_begin, v_end);
     return cudaGetLastError();
 }
 
@@ -1741,39 +1772,71 @@ int neighbour_tile_atoms() { return kNbThreads * kNbIPT; }
 // ---------------------------------------------------------------------------------------------
 constexpr int kMsdThreads = 256;
 
+constexpr int kMsdLags = 16;   // lags one block walks together
+
+// block = (chunk of kMsdLags lags, tile of 256 atoms of one type).  A thread keeps one running sum per lag of the chunk and
+// walks the origins once: the frame of the origin is read once for the whole chunk, and the frames origin + lag of
+// neighbouring origins overlap (origin stride < chunk), so they come from L1/L2 -- a window larger than L2 streams from
+// HBM about (2 + stride) / kMsdLags... times per chunk instead of twice per LAG.  The sums of one lag are formed in the
+// same order as before (origins in order per thread, then the fixed tree): the same partials, bit for bit.
 __global__ void __launch_bounds__(kMsdThreads) msd_partial_kernel(const MsdParams p) {
     __shared__ double red[kMsdThreads];
-    // the lag is the x index of the grid (up to 2^31 - 1 lags: a block of millions of frames with -S 0), the tiles walk y
-    const int t = blockIdx.x, tid = threadIdx.x;
+    const int t0 = blockIdx.x * kMsdLags, tid = threadIdx.x;
+    const int nl = min(kMsdLags, p.leff - t0);
     for (int tile = blockIdx.y; tile < p.ntiles; tile += gridDim.y) {
         const int ty = p.tile_type[tile];
         const int slot = p.tile_start[tile] + tid;
         const bool live = tid < p.tile_count[tile];
-        double acc = 0.0;
+        double acc[kMsdLags];
+#pragma unroll
+        for (int l = 0; l < kMsdLags; ++l) acc[l] = 0.0;
         if (live) {
+            const size_t row = static_cast<size_t>(p.npad);
             for (int im = 0; im < p.ntimesteps; im += p.skip) {
-                const size_t fa = static_cast<size_t>(p.f0 + im), fb = fa + t;
-                const double *pa = p.pos + fa * 3 * p.npad, *pb = p.pos + fb * 3 * p.npad;
-                double dx = __dsub_rn(pa[slot], pb[slot]);
-                double dy = __dsub_rn(pa[p.npad + slot], pb[p.npad + slot]);
-                double dz = __dsub_rn(pa[2 * static_cast<size_t>(p.npad) + slot], pb[2 * static_cast<size_t>(p.npad) + slot]);
+                const size_t fa = static_cast<size_t>(p.f0 + im);
+                const double *pa = p.pos + fa * 3 * row;
+                const double xa = pa[slot], ya = pa[row + slot], za = pa[2 * row + slot];
+                double cax = 0, cay = 0, caz = 0;
                 if (p.cm_self) {
-                    const double *ca = p.cm + (fa * p.ntypes + ty) * 3, *cb = p.cm + (fb * p.ntypes + ty) * 3;
-                    dx = __dsub_rn(dx, __dsub_rn(ca[0], cb[0]));
-                    dy = __dsub_rn(dy, __dsub_rn(ca[1], cb[1]));
-                    dz = __dsub_rn(dz, __dsub_rn(ca[2], cb[2]));
+                    const double *ca = p.cm + (fa * p.ntypes + ty) * 3;
+                    cax = ca[0];
+                    cay = ca[1];
+                    caz = ca[2];
                 }
-                acc = __dadd_rn(acc, __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)));
+#pragma unroll
+                for (int l = 0; l < kMsdLags; ++l) {
+                    if (l < nl) {
+                        const size_t fb = fa + t0 + l;
+                        const double *pb = p.pos + fb * 3 * row;
+                        double dx = __dsub_rn(xa, pb[slot]);
+                        double dy = __dsub_rn(ya, pb[row + slot]);
+                        double dz = __dsub_rn(za, pb[2 * row + slot]);
+                        if (p.cm_self) {
+                            const double *cb = p.cm + (fb * p.ntypes + ty) * 3;
+                            dx = __dsub_rn(dx, __dsub_rn(cax, cb[0]));
+                            dy = __dsub_rn(dy, __dsub_rn(cay, cb[1]));
+                            dz = __dsub_rn(dz, __dsub_rn(caz, cb[2]));
+                        }
+                        acc[l] = __dadd_rn(acc[l], __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)));
+                    }
+                }
             }
         }
-        red[tid] = acc;
-        __syncthreads();
-        for (int s = kMsdThreads / 2; s > 0; s >>= 1) {
-            if (tid < s) red[tid] = __dadd_rn(red[tid], red[tid + s]);
+#pragma unroll 1
+        for (int l = 0; l < nl; ++l) {
+            double v = 0.0;
+#pragma unroll
+            for (int q = 0; q < kMsdLags; ++q)
+                if (q == l) v = acc[q];   // (static indexing keeps acc in registers)
+            red[tid] = v;
+            __syncthreads();
+            for (int s = kMsdThreads / 2; s > 0; s >>= 1) {
+                if (tid < s) red[tid] = __dadd_rn(red[tid], red[tid + s]);
+                __syncthreads();
+            }
+            if (tid == 0) p.partial[static_cast<size_t>(t0 + l) * p.ntiles + tile] = red[0];
             __syncthreads();
         }
-        if (tid == 0) p.partial[static_cast<size_t>(t) * p.ntiles + tile] = red[0];
-        __syncthreads();
     }
 }
 
@@ -1806,7 +1869,7 @@ __global__ void msd_finish_kernel(const MsdParams p) {
 cudaError_t launch_msd(const MsdParams &p, cudaStream_t stream) {
     if (p.leff <= 0 || p.ntypes <= 0) return cudaSuccess;
     if (p.ntiles > 0) {
-        dim3 grid(p.leff, p.ntiles < 65535 ? p.ntiles : 65535);
+        dim3 grid((p.leff + kMsdLags - 1) / kMsdLags, p.ntiles < 65535 ? p.ntiles : 65535);
         msd_partial_kernel<<<grid, kMsdThreads, 0, stream>>>(p);
     }
     const int n = p.leff * p.ntypes;

@@ -126,13 +126,16 @@ struct NeighbourParams {
     const int *type_start;     // [ntypes+1]
     const int *frames;         // window-relative frames to visit
     unsigned long long *hist;  // [ntypes][hist_stride], hist_stride = natoms + 1
+    unsigned int *counts;      // [listed frames][ntypes][npad] neighbours found so far (zeroed by the caller)
     unsigned int *error_flag;
     double r2;
-    unsigned unit_begin, unit_end;   // units = (frame index, i tile)
-    int npad, ntypes, n_itiles;
+    unsigned unit_begin, unit_end;   // units = (frame index, i tile, j chunk)
+    int npad, ntypes, n_itiles, n_jchunks, jchunk;
     unsigned long long hist_stride;
 };
 cudaError_t launch_neighbour_kernel(bool triclinic, bool fast, int grid, cudaStream_t stream, const NeighbourParams &p);
+// hist[type][counts[frame][type][slot]] += 1 for the real atoms of the (frame, i tile) pairs [v_begin, v_end)
+cudaError_t launch_neighbour_finish(int grid, cudaStream_t stream, const NeighbourParams &p, unsigned int v_begin, unsigned int v_end);
 int neighbour_tile_atoms();
 
 // mean square displacement (MSD)

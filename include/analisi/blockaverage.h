@@ -86,12 +86,23 @@ public:
             if (calcolo->block_batch_wanted(n_b, s, extra)) {
                 cronometro cron;
                 cron.start();
+                const bool debug_times = std::getenv("AGOFRT_DEBUG") != nullptr;
+                auto lap = [&](const char *what) {
+                    if (!debug_times) return;
+                    cron.stop();
+                    std::cerr << "[blocks] " << what << ": +" << cron.time_last() << "s\n";
+                    cron.start();
+                };
                 TraiettoriaF<TR>::set_data_access_block_size(n_b * s + extra, traiettoria);
+                lap("window buffers");
                 TraiettoriaF<TR>::set_access_at(0, traiettoria);
+                lap("window read");
                 if (calcolo->calculate_blocks(0, s, n_b)) {
+                    lap("blocks on the devices");
                     calc->calculate_blocks(calcolo, n_b);
                     calc->calcola_end(n_b);
                     if constexpr (!HasDeviceBlocksEnd<Calcolo>::value) calcolo->fetch_block_of_batch(n_b - 1);
+                    lap("mean, variance, last block");
                     cron.stop();
                     std::cerr << "Time for " << n_b << " blocks of " << s << " steps, computed as one batch on the GPUs: " << cron.time()
                               << "s.\n";

@@ -261,7 +261,7 @@ def test_cli_device_side_ingest_equals_host_reader(host, tmp_path, format2020):
         r = run(**env)
         assert r.stdout == base.stdout, env
         assert ("parsed on the GPUs" in r.stderr) == (env["ANALISI_DEVICE_PARSE"] == "1")
-        assert ("as one batch on the GPUs" in r.stderr) == (env.get("ANALISI_BLOCK_BATCH") == "1")
+        assert ("as one batch on the GPUs" in r.stderr) == (env.get("ANALISI_BLOCK_BATCH", "1") == "1")
     # an atom changes type in frame 20
     raw = (types * 2 + 1).astype(np.int64)
     path2 = str(tmp_path / "e.bin")
