@@ -31,7 +31,7 @@ SYMBOLS = [
     "agofrt_blockavg_create", "agofrt_blockavg_destroy", "agofrt_blockavg_begin", "agofrt_blockavg_push", "agofrt_blockavg_end",
     "agofrt_plan_last_counts", "agofrt_plan_info", "agofrt_traj_upload_ex", "agofrt_traj_download",
     "agofrt_blocks", "agofrt_plan_block_counts", "agofrt_blockavg_push_blocks",
-    "agofrt_traj_set_ids", "agofrt_traj_upload_records",
+    "agofrt_traj_set_ids", "agofrt_traj_upload_records", "agofrt_traj_set_rotation", "agofrt_traj_get_rotation",
 ]
 
 
@@ -94,6 +94,8 @@ def lib():
     L.agofrt_traj_upload_ex.argtypes = [vp, C.c_size_t, C.c_size_t, vp, vp, C.c_uint, vp]
     L.agofrt_traj_download.argtypes = [vp, C.c_size_t, C.c_size_t, vp]
     L.agofrt_traj_set_ids.argtypes = [vp, ip, ip]
+    L.agofrt_traj_set_rotation.argtypes = [vp, C.c_size_t, C.c_size_t, dp]
+    L.agofrt_traj_get_rotation.argtypes = [vp, C.c_size_t, dp]
     L.agofrt_traj_upload_records.argtypes = [vp, C.c_size_t, C.c_size_t, C.POINTER(vp), ip, C.POINTER(C.c_size_t), vp, C.c_uint, vp]
     L.agofrt_traj_download_frame.argtypes = [vp, C.c_size_t, dp]
     L.agofrt_pbc_wrap.argtypes = [vp, vp, C.c_size_t, C.c_size_t, dp, C.c_int]
@@ -290,6 +292,15 @@ class DeviceTrajectory:
         flags = (UP_WRAP if wrap else 0) | (UP_SHARED if shared else 0) | (UP_WRITEBACK if out is not None else 0)
         _check(lib().agofrt_traj_upload_records(self._h, int(first_frame), len(frames), ptrs, atoms, fc, box.ctypes.data, flags,
                                                 out.ctypes.data if out is not None else None))
+
+    def set_rotation(self, first_frame, q):
+        q = np.ascontiguousarray(q, dtype=np.float64).reshape(-1, 9)
+        _check(lib().agofrt_traj_set_rotation(self._h, int(first_frame), q.shape[0], _dp(q)))
+
+    def get_rotation(self, frame):
+        out = np.zeros(9, dtype=np.float64)
+        _check(lib().agofrt_traj_get_rotation(self._h, int(frame), _dp(out)))
+        return out
 
     def download(self, first_frame, nframes):
         """Frames of the device window in the caller's atom order (wrapped if uploaded with wrap)."""

@@ -172,7 +172,7 @@ static void *spare_take(Dev &dv, size_t bytes) {
 // keeps the buffer if it is large enough to matter and a slot is free (or holds a smaller one); else frees it
 static void spare_give(Dev &dv, void *ptr, size_t bytes) {
     if (!ptr) return;
-    if (bytes >= (16u << 20)) {
+    if (bytes >= (4u << 20)) {
         std::lock_guard<std::mutex> lock(*dv.hstage_mutex);
         int slot = -1;
         for (int k = 0; k < kSpares && slot < 0; ++k)
@@ -215,6 +215,7 @@ struct TrajDev {
     unsigned int *flags = nullptr;  // [8]: 0 inf seen, 1 wrap cap hit (block), 2 NaN in a real atom, 3 wrap cap hit (upload),
                                     //      4 records with an unknown atom id, 5 records whose type changed (agofrt_traj_upload_records)
     double *probe = nullptr;        // [4]: result of agofrt_traj_d2_pair
+    double *rot = nullptr;          // [max_frames][9] rotation matrix Q of every frame (agofrt_traj_set_rotation), or NULL
     unsigned long long *nb_hist = nullptr;  // neighbour-count histogram [ntypes][natoms+1] (agofrt_neighbour_hist)
     unsigned int *nb_counts = nullptr;      // per-atom neighbour counts [frames of the call][ntypes][npad]
     size_t nb_counts_len = 0;
@@ -243,6 +244,7 @@ struct agofrt_traj {
     bool has_inf = false;
     bool has_nan = false;   // NaN coordinates in the input (they are never in range, as in the reference)
     bool bad_box = false;
+    size_t rot_first = 0, rot_frames = 0;   // frames whose rotation matrices are on the devices
     std::vector<double> cm;      // per-type centres of mass of the window frames [nframes][ntypes][3] (agofrt_traj_set_cm)
     size_t cm_first = 0, cm_frames = 0;
     bool perm_valid = false;     // the permutation is kept over uploads and refreshed every kPermRefresh frames
@@ -566,6 +568,7 @@ static void free_traj_dev(agofrt_traj *t) {
         cudaFree(d.type_start);
         cudaFree(d.flags);
         cudaFree(d.probe);
+        cudaFree(d.rot);
         cudaFree(d.nb_hist);
         cudaFree(d.nb_frames);
         cudaFree(d.nb_counts);
@@ -1126,6 +1129,39 @@ extern "C" int agofrt_traj_upload_records(agofrt_traj *t, size_t first_frame, si
     return on_exception();
 }
 
+// Per-frame rotation matrices next to the window (Trajectory_numpy keeps Q of the QR rotation that brings a general cell
+// into the LAMMPS frame, reference lib/src/trajectory_numpy.cpp:120,131, lib/include/triclinic.h:71-73): device-resident
+// like positions and cells, for kernels that must rotate vectors back to the laboratory frame.  g(r,t) itself is
+// rotation-invariant and never reads them.
+extern "C" int agofrt_traj_set_rotation(agofrt_traj *t, size_t first_frame, size_t nframes, const double *q) try {
+    if (!t || (!q && nframes > 0)) return fail(AGOFRT_ERR_ARG, "NULL argument");
+    if (nframes > t->max_frames) return fail(AGOFRT_ERR_ARG, "%zu rotation matrices for a window of at most %zu frames", nframes, t->max_frames);
+    for (size_t i = 0; i < t->dev.size(); ++i) {
+        TrajDev &d = t->dev[i];
+        CU(cudaSetDevice(t->ctx->devs[i].id));
+        if (!d.rot) CU(cudaMalloc(&d.rot, t->max_frames * 9 * sizeof(double)));
+        if (nframes) CU(cudaMemcpyAsync(d.rot, q, nframes * 9 * sizeof(double), cudaMemcpyHostToDevice, d.up));
+        CU(cudaStreamSynchronize(d.up));
+    }
+    t->rot_first = first_frame;
+    t->rot_frames = nframes;
+    return AGOFRT_OK;
+} catch (...) {
+    return on_exception();
+}
+
+extern "C" int agofrt_traj_get_rotation(agofrt_traj *t, size_t frame, double *q9) try {
+    if (!t || !q9) return fail(AGOFRT_ERR_ARG, "NULL argument");
+    if (frame < t->rot_first || frame >= t->rot_first + t->rot_frames)
+        return fail(AGOFRT_ERR_WINDOW, "no rotation matrix on the device for frame %zu", frame);
+    TrajDev &d = t->dev[t->dev.size() - 1];   // (the last device: every device holds a copy)
+    CU(cudaSetDevice(t->ctx->devs[t->dev.size() - 1].id));
+    CU(cudaMemcpy(q9, d.rot + (frame - t->rot_first) * 9, 9 * sizeof(double), cudaMemcpyDeviceToHost));
+    return AGOFRT_OK;
+} catch (...) {
+    return on_exception();
+}
+
 // Frames [first_frame, first_frame + nframes) of the device window back in the caller's atom order: what the host
 // would hold after Trajectory::set_access_at / the Trajectory_numpy constructor (wrapped when the window was uploaded
 // with AGOFRT_UP_WRAP).  The host classes call it the first time somebody asks for host positions.
@@ -1574,7 +1610,7 @@ extern "C" int agofrt_plan_destroy(agofrt_plan *p) try {
         cudaFree(d.units);
         cudaFree(d.counter);
         cudaFree(d.edges);
-        cudaFree(d.batch);
+        spare_give(p->ctx->devs[i], d.batch, d.batch_len * sizeof(unsigned long long));
     }
     if (p->host_counts) cudaFreeHost(p->host_counts);
     if (p->host_edges) cudaFreeHost(p->host_edges);
@@ -2132,10 +2168,12 @@ extern "C" int agofrt_blocks(agofrt_plan *p, size_t primo0, size_t stride, unsig
         PlanDev &pd = p->dev[i];
         CU(cudaSetDevice(ctx->devs[i].id));
         if (static_cast<size_t>(nblocks) * len > pd.batch_len) {
-            cudaFree(pd.batch);
+            spare_give(ctx->devs[i], pd.batch, pd.batch_len * sizeof(unsigned long long));
             pd.batch = nullptr;
             pd.batch_len = 0;
-            CU(cudaMalloc(&pd.batch, static_cast<size_t>(nblocks) * len * sizeof(unsigned long long)));
+            const size_t want = static_cast<size_t>(nblocks) * len * sizeof(unsigned long long);
+            pd.batch = static_cast<unsigned long long *>(spare_take(ctx->devs[i], want));
+            if (!pd.batch) CU(cudaMalloc(&pd.batch, want));
             pd.batch_len = static_cast<size_t>(nblocks) * len;
         }
         CU(cudaEventRecord(ctx->devs[i].ev_begin, ctx->devs[i].stream));

@@ -151,6 +151,10 @@ AGOFRT_API int agofrt_traj_upload_records(agofrt_traj *traj, size_t first_frame,
 /* Frames of the device window back in the caller's atom order (wrapped if they were uploaded with AGOFRT_UP_WRAP): the
  * host classes materialise their host copy with it the first time an accessor needs one. */
 AGOFRT_API int agofrt_traj_download(agofrt_traj *traj, size_t first_frame, size_t nframes, double *pos_aos);
+/* Per-frame rotation matrices Q (9 doubles, as Trajectory_numpy::get_rotation_matrix hands them out; reference
+ * lib/src/trajectory_numpy.cpp:120,131) kept on the devices next to positions and cells. */
+AGOFRT_API int agofrt_traj_set_rotation(agofrt_traj *traj, size_t first_frame, size_t nframes, const double *q);
+AGOFRT_API int agofrt_traj_get_rotation(agofrt_traj *traj, size_t frame, double *q9);
 /* Read one frame back in the caller's atom order (tests: the layout round-trips bit-exactly). */
 AGOFRT_API int agofrt_traj_download_frame(agofrt_traj *traj, size_t frame, double *pos_aos);
 /* In-place BaseTrajectory::pbc_wrap on a host buffer through the GPU (frames with their own box

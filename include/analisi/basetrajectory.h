@@ -254,6 +254,11 @@ protected:
         host_current = false;
     }
     void download_window(double *pos_out) { dev_window.download(current_timestep, loaded_timesteps, pos_out); }
+    // rotation matrices of the loaded frames, device-resident next to positions and cells
+    void upload_rotation(const double *q9) {
+        if (dev_window.valid()) dev_window.set_rotation(current_timestep, loaded_timesteps, q9);
+    }
+    void download_rotation(size_t frame, double *q9) { dev_window.get_rotation(frame, q9); }
     // the same from the raw records of a LAMMPS dump (parsed on the GPUs); false: an atom changed type, nothing uploaded
     bool upload_records_now(const void *const *chunk_ptr, const int *chunk_atoms, const size_t *frame_chunk, bool wrap,
                             const int *slot_to_id, const int *slot_raw_type) {

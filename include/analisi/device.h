@@ -98,6 +98,9 @@ public:
     // LAMMPS dump records as the source (agofrt_traj_set_ids / agofrt_traj_upload_records): the id -> slot table once per
     // window object, then frames as lists of chunks of raw records.  upload_records returns false when an atom's type
     // changes inside the window (the caller then reads that window on the host, with the reference's warning).
+    // per-frame rotation matrices next to the window (agofrt_traj_set_rotation)
+    void set_rotation(size_t first, size_t n, const double *q9);
+    void get_rotation(size_t frame, double *q9);
     bool ids_set() const { return ids_set_; }
     void set_ids(const int *slot_to_id, const int *slot_raw_type);
     bool upload_records(size_t first, size_t n, const void *const *chunk_ptr, const int *chunk_atoms, const size_t *frame_chunk,

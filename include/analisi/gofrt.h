@@ -183,8 +183,14 @@ public:
     // millisecond of kernel: systems that take the small-system kernel, and a window with the frames of ALL the blocks
     // that is small.  ANALISI_BLOCK_BATCH=0 turns it off.
     bool block_batch_wanted(unsigned int n_b, unsigned int s, unsigned int extra) const {
-        if (const char *e = std::getenv("ANALISI_BLOCK_BATCH"))
+        // ANALISI_BLOCK_BATCH=1 / 0 forces it on / off.  Default: only with several GPUs -- on one GPU the block-by-block
+        // loop already hides reading and upload of block b+1 behind block b (read-ahead), and measured faster on C1
+        bool forced = false;
+        if (const char *e = std::getenv("ANALISI_BLOCK_BATCH")) {
             if (std::atoi(e) == 0) return false;
+            forced = true;
+        }
+        if (!forced && analisi_device::Context::instance().ndev() < 2) return false;
         if (debug || report_edges || n_b < 2) return false;
         const double frames = static_cast<double>(n_b) * s + extra;
         const unsigned int nt = static_cast<unsigned int>(traiettoria->get_ntypes());

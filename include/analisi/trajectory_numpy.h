@@ -73,6 +73,8 @@ public:
     double *box_last() { return buffer_boxes + (n_timesteps - 1) * buffer_boxes_stride; }
     // Q of frame t (9 doubles, column-major) or nullptr when no rotation was saved
     double *get_rotation_matrix(size_t t) { return rotation.empty() ? nullptr : rotation.data() + 9 * t; }
+    // the device-resident copy of Q of frame t (this repository's addition; throws when no rotation was saved)
+    void get_device_rotation_matrix(size_t t, double *q9) { download_rotation(t, q9); }
 
     // the wrapped frames come back from the GPUs the first time host positions are asked for
     void materialise_host_positions();

@@ -239,6 +239,11 @@ PYBIND11_MODULE(pyanalisi, m) {
              "positions (double) (ntimesteps,natoms,3); velocities (double) (ntimesteps,natoms,3); types (int) (natoms); "
              "lattice vectors (double); format of lattice vectors (BoxFormat); wrap atoms inside the cell using pbc; "
              "save rotation matrix if triclinic format is used and a rotation is needed")
+        .def("get_device_rotation_matrix", [](Trajectory_numpy &t, size_t frame) {
+            py::array_t<double> q({3, 3});
+            t.get_device_rotation_matrix(frame, q.mutable_data());
+            return q;
+        }, "addition: Q of one frame as the GPUs hold it (raises when no rotation matrix was saved)")
         .def("get_rotation_matrix", [](Trajectory_numpy &t) {
             double *q = t.get_rotation_matrix(0);
             if (!q) return py::array_t<double>();

@@ -84,6 +84,12 @@ void Window::upload_shared(size_t first, size_t n, const double *pos_aos, const 
     check(agofrt_traj_upload_ex(traj_, first, n, pos_aos, box_internal, flags, wrapped_out), "agofrt_traj_upload_ex");
 }
 
+void Window::set_rotation(size_t first, size_t n, const double *q9) {
+    check(agofrt_traj_set_rotation(traj_, first, n, q9), "agofrt_traj_set_rotation");
+}
+
+void Window::get_rotation(size_t frame, double *q9) { check(agofrt_traj_get_rotation(traj_, frame, q9), "agofrt_traj_get_rotation"); }
+
 void Window::set_ids(const int *slot_to_id, const int *slot_raw_type) {
     check(agofrt_traj_set_ids(traj_, slot_to_id, slot_raw_type), "agofrt_traj_set_ids");
     ids_set_ = true;

@@ -101,6 +101,7 @@ void Trajectory_numpy::init(const double *pos, const double *vel, const int *typ
         upload_now(buffer_positions, true);
         if (!rotate) buffer_positions = nullptr;   // the caller's array stays unwrapped: never hand it out as the window
         wrapped_on_device = true;
+        if (!rotation.empty()) upload_rotation(rotation.data());   // Q per frame, next to positions and cells on the GPUs
     } else {
         mark_window_changed();
     }
