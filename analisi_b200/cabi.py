@@ -32,6 +32,7 @@ SYMBOLS = [
     "agofrt_plan_last_counts", "agofrt_plan_info", "agofrt_traj_upload_ex", "agofrt_traj_download",
     "agofrt_blocks", "agofrt_plan_block_counts", "agofrt_blockavg_push_blocks",
     "agofrt_traj_set_ids", "agofrt_traj_upload_records", "agofrt_traj_set_rotation", "agofrt_traj_get_rotation",
+    "agofrt_neighbours", "agofrt_sh_density",
 ]
 
 
@@ -94,6 +95,8 @@ def lib():
     L.agofrt_traj_upload_ex.argtypes = [vp, C.c_size_t, C.c_size_t, vp, vp, C.c_uint, vp]
     L.agofrt_traj_download.argtypes = [vp, C.c_size_t, C.c_size_t, vp]
     L.agofrt_traj_set_ids.argtypes = [vp, ip, ip]
+    L.agofrt_neighbours.argtypes = [vp, C.c_size_t, u64p, dp, C.c_int, u64p, dp]
+    L.agofrt_sh_density.argtypes = [vp, C.c_size_t, C.c_int, C.c_uint, dp, dp, ip]
     L.agofrt_traj_set_rotation.argtypes = [vp, C.c_size_t, C.c_size_t, dp]
     L.agofrt_traj_get_rotation.argtypes = [vp, C.c_size_t, dp]
     L.agofrt_traj_upload_records.argtypes = [vp, C.c_size_t, C.c_size_t, C.POINTER(vp), ip, C.POINTER(C.c_size_t), vp, C.c_uint, vp]
@@ -292,6 +295,45 @@ class DeviceTrajectory:
         flags = (UP_WRAP if wrap else 0) | (UP_SHARED if shared else 0) | (UP_WRITEBACK if out is not None else 0)
         _check(lib().agofrt_traj_upload_records(self._h, int(first_frame), len(frames), ptrs, atoms, fc, box.ctypes.data, flags,
                                                 out.ctypes.data if out is not None else None))
+
+    def neighbours(self, frame, spec, sort=False):
+        """Neighbours::update_neigh: ``spec`` = [(max neighbours, cutoff^2), ...] per type.  Returns (counts [N][T],
+        indices [N][T][maxn] (-1 past the count), r [N][T][maxn][4]) unpacked from the reference's own layout."""
+        nn = np.array([s[0] for s in spec], dtype=np.uint64)
+        c2 = np.array([s[1] for s in spec], dtype=np.float64)
+        assert len(spec) == self.ntypes
+        n = self.natoms
+        words = int(((nn + 1) * n).sum())
+        doubles = int((nn * n * 4).sum())
+        lst = np.zeros(words, dtype=np.uint64)
+        rpos = np.zeros(max(doubles, 1), dtype=np.float64)
+        _check(lib().agofrt_neighbours(self._h, int(frame), nn.ctypes.data_as(C.POINTER(C.c_uint64)), _dp(c2), int(bool(sort)),
+                                       lst.ctypes.data_as(C.POINTER(C.c_uint64)), _dp(rpos)))
+        maxn = int(nn.max())
+        counts = np.zeros((n, self.ntypes), dtype=np.int64)
+        idx = -np.ones((n, self.ntypes, maxn), dtype=np.int64)
+        r = np.zeros((n, self.ntypes, maxn, 4))
+        lo = ro = 0
+        for t in range(self.ntypes):
+            k = int(nn[t])
+            blk = lst[lo:lo + (k + 1) * n].reshape(n, k + 1)
+            rb = rpos[ro:ro + k * n * 4].reshape(n, k, 4)
+            counts[:, t] = blk[:, 0]
+            for i in range(n):
+                c = int(blk[i, 0])
+                idx[i, t, :c] = blk[i, 1:1 + c]
+                r[i, t, :c] = rb[i, :c]
+            lo += (k + 1) * n
+            ro += k * n * 4
+        return counts, idx, r
+
+    def sh_density(self, frame, lmax, nbin, rminmax):
+        """SphericalBase::calc: (result [N][T][nbin][(lmax+1)^2], counter [N][T][nbin])."""
+        rm = np.ascontiguousarray(rminmax, dtype=np.float64).reshape(self.ntypes * self.ntypes, 2)
+        res = np.zeros((self.natoms, self.ntypes, int(nbin), (lmax + 1) ** 2), dtype=np.float64)
+        cnt = np.zeros((self.natoms, self.ntypes, int(nbin)), dtype=np.int32)
+        _check(lib().agofrt_sh_density(self._h, int(frame), int(lmax), int(nbin), _dp(rm), _dp(res), cnt.ctypes.data_as(C.POINTER(C.c_int))))
+        return res, cnt
 
     def set_rotation(self, first_frame, q):
         q = np.ascontiguousarray(q, dtype=np.float64).reshape(-1, 9)

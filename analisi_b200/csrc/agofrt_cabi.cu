@@ -2677,6 +2677,179 @@ extern "C" int agofrt_msd(agofrt_traj *t, size_t primo, unsigned ntimesteps, uns
 }
 
 // ---------------------------------------------------------------------------------------------
+// neighbour lists and spherical-harmonic densities of one frame (device 0)
+// ---------------------------------------------------------------------------------------------
+static int atom_tables(agofrt_traj *t, int **d_slot, int **d_type) {
+    // atom (caller's numbering) -> device slot, and its dense type
+    std::vector<int> slot(t->natoms, 0);
+    for (int s = 0; s < t->npad; ++s)
+        if (t->perm[s] >= 0) slot[t->perm[s]] = s;
+    CU(cudaMalloc(d_slot, std::max<size_t>(t->natoms, 1) * sizeof(int)));
+    CU(cudaMalloc(d_type, std::max<size_t>(t->natoms, 1) * sizeof(int)));
+    if (t->natoms) {
+        CU(cudaMemcpy(*d_slot, slot.data(), t->natoms * sizeof(int), cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(*d_type, t->type_id.data(), t->natoms * sizeof(int), cudaMemcpyHostToDevice));
+    }
+    return AGOFRT_OK;
+}
+
+extern "C" int agofrt_neighbours(agofrt_traj *t, size_t frame, const uint64_t *nneigh, const double *cutoff2, int sort,
+                                 uint64_t *list_out, double *rpos_out) try {
+    if (!t || !nneigh || !cutoff2 || !list_out || !rpos_out) return fail(AGOFRT_ERR_ARG, "NULL argument");
+    if (t->ntypes > kLsMaxTypes) return fail(AGOFRT_ERR_TOO_LARGE, "neighbour lists handle at most %d atom types", kLsMaxTypes);
+    if (frame < t->first_frame || frame >= t->first_frame + t->nframes)
+        return fail(AGOFRT_ERR_WINDOW, "frame %zu is not in the uploaded window", frame);
+    if (t->bad_box || t->has_inf) return fail(AGOFRT_ERR_NONFINITE, "the window holds an infinite coordinate or a non-positive / non-finite box edge");
+    NeighListParams p;
+    size_t words = 0, doubles = 0;
+    for (int k = 0; k < t->ntypes; ++k) {
+        p.nneigh[k] = nneigh[k];
+        p.cutoff2[k] = cutoff2[k];
+        p.list_offset[k] = words;
+        p.rpos_offset[k] = doubles;
+        words += (nneigh[k] + 1) * t->natoms;
+        doubles += nneigh[k] * t->natoms * 4;
+    }
+    if (t->natoms == 0) return AGOFRT_OK;
+    Dev &dv = t->ctx->devs[0];
+    TrajDev &td = t->dev[0];
+    CU(cudaSetDevice(dv.id));
+    int *d_slot = nullptr, *d_type = nullptr;
+    unsigned long long *d_list = nullptr;
+    double *d_rpos = nullptr;
+    unsigned int *d_flags = nullptr;
+    unsigned int flags[2] = {0, 0};
+    auto body = [&]() -> int {
+        int rc = atom_tables(t, &d_slot, &d_type);
+        if (rc != AGOFRT_OK) return rc;
+        CU(cudaMalloc(&d_list, words * sizeof(unsigned long long)));
+        CU(cudaMalloc(&d_rpos, std::max<size_t>(doubles, 1) * sizeof(double)));
+        CU(cudaMalloc(&d_flags, 2 * sizeof(unsigned int)));
+        CU(cudaMemsetAsync(d_list, 0, words * sizeof(unsigned long long), dv.stream));   // update_neigh zeroes the lists (neighbour.cpp:10-12)
+        CU(cudaMemsetAsync(d_rpos, 0, std::max<size_t>(doubles, 1) * sizeof(double), dv.stream));   // (the reference leaves these uninitialised)
+        CU(cudaMemsetAsync(d_flags, 0, 2 * sizeof(unsigned int), dv.stream));
+        p.pos = td.pos;
+        p.box = td.box6;
+        p.atom_slot = d_slot;
+        p.atom_type = d_type;
+        p.list = d_list;
+        p.rpos = d_rpos;
+        p.flags = d_flags;
+        p.natoms = static_cast<int>(t->natoms);
+        p.npad = t->npad;
+        p.ntypes = t->ntypes;
+        p.frame = static_cast<int>(frame - t->first_frame);
+        p.triclinic = t->stride == 9 ? 1 : 0;
+        p.sort = sort ? 1 : 0;
+        CU(launch_neigh_list(p, dv.stream));
+        CU(cudaMemcpyAsync(list_out, d_list, words * sizeof(unsigned long long), cudaMemcpyDeviceToHost, dv.stream));
+        if (doubles) CU(cudaMemcpyAsync(rpos_out, d_rpos, doubles * sizeof(double), cudaMemcpyDeviceToHost, dv.stream));
+        CU(cudaMemcpyAsync(flags, d_flags, sizeof(flags), cudaMemcpyDeviceToHost, dv.stream));
+        CU(cudaStreamSynchronize(dv.stream));
+        return AGOFRT_OK;
+    };
+    const int rc = body();
+    cudaFree(d_slot);
+    cudaFree(d_type);
+    cudaFree(d_list);
+    cudaFree(d_rpos);
+    cudaFree(d_flags);
+    if (rc != AGOFRT_OK) return rc;
+    if (flags[1]) return fail(AGOFRT_ERR_NONFINITE, "minimum image did not converge within %d images", kWrapCap);
+    if (flags[0]) return fail(AGOFRT_ERR_TOO_LARGE, "Too many neighbours in shell!");
+    return AGOFRT_OK;
+} catch (...) {
+    return on_exception();
+}
+
+// SpecialFunctions::realSpericalHarmonics_coeff<double>(l, m, l-m+1) (reference lib/include/specialfunctions.h:34-50),
+// the same operations in the same order; compiled without FMA contraction and fast-math (build.py)
+static double real_sh_coeff(int l, int m) {
+    const double pi = 3.14159265358979323846264338327950288419716939937510;
+    if (m == 0) return std::sqrt(static_cast<double>(2 * l + 1) / (4 * pi));
+    if (m < 0) m = -m;
+    double value = 1.0;
+    for (long v = l - m + 1; v <= l + m; ++v) value = value * static_cast<double>(v);
+    return std::sqrt(static_cast<double>(2 * l + 1) / (4 * pi) * 2 / value) * std::pow(-1, m);
+}
+
+extern "C" int agofrt_sh_density(agofrt_traj *t, size_t frame, int lmax, unsigned nbin, const double *rminmax, double *result_out,
+                                 int *counter_out) try {
+    if (!t || !rminmax || !result_out) return fail(AGOFRT_ERR_ARG, "NULL argument");
+    if (lmax < 0 || lmax > kShMaxL) return fail(AGOFRT_ERR_ARG, "lmax must be in [0, %d]", kShMaxL);
+    if (frame < t->first_frame || frame >= t->first_frame + t->nframes)
+        return fail(AGOFRT_ERR_WINDOW, "frame %zu is not in the uploaded window", frame);
+    if (t->bad_box || t->has_inf) return fail(AGOFRT_ERR_NONFINITE, "the window holds an infinite coordinate or a non-positive / non-finite box edge");
+    const int nt = t->ntypes, nl = (lmax + 1) * (lmax + 1);
+    const size_t cells = t->natoms * static_cast<size_t>(nt) * nbin;
+    if (cells == 0) return AGOFRT_OK;
+    std::vector<double> rmin(nt * nt), dr(nt * nt), coeff(nl, 0.0);
+    for (int k = 0; k < nt * nt; ++k) {
+        rmin[k] = rminmax[2 * k];
+        dr[k] = (rminmax[2 * k + 1] - rminmax[2 * k]) / static_cast<double>(nbin);   // sphericalbase.h:39-41
+    }
+    for (int l = 0; l <= lmax; ++l)
+        for (int m = 0; m <= l; ++m) coeff[l * (lmax + 1) + m] = real_sh_coeff(l, m);
+    Dev &dv = t->ctx->devs[0];
+    TrajDev &td = t->dev[0];
+    CU(cudaSetDevice(dv.id));
+    int *d_slot = nullptr, *d_type = nullptr, *d_counter = nullptr;
+    double *d_res = nullptr, *d_par = nullptr;
+    unsigned int *d_flags = nullptr;
+    unsigned int flags[2] = {0, 0};
+    auto body = [&]() -> int {
+        int rc = atom_tables(t, &d_slot, &d_type);
+        if (rc != AGOFRT_OK) return rc;
+        CU(cudaMalloc(&d_res, cells * nl * sizeof(double)));
+        CU(cudaMalloc(&d_counter, cells * sizeof(int)));
+        CU(cudaMalloc(&d_par, (2 * nt * nt + nl) * sizeof(double)));
+        CU(cudaMalloc(&d_flags, 2 * sizeof(unsigned int)));
+        CU(cudaMemsetAsync(d_res, 0, cells * nl * sizeof(double), dv.stream));
+        CU(cudaMemsetAsync(d_counter, 0, cells * sizeof(int), dv.stream));
+        CU(cudaMemsetAsync(d_flags, 0, 2 * sizeof(unsigned int), dv.stream));
+        CU(cudaMemcpyAsync(d_par, rmin.data(), nt * nt * sizeof(double), cudaMemcpyHostToDevice, dv.stream));
+        CU(cudaMemcpyAsync(d_par + nt * nt, dr.data(), nt * nt * sizeof(double), cudaMemcpyHostToDevice, dv.stream));
+        CU(cudaMemcpyAsync(d_par + 2 * nt * nt, coeff.data(), nl * sizeof(double), cudaMemcpyHostToDevice, dv.stream));
+        ShDensityParams p;
+        p.pos = td.pos;
+        p.box = td.box6;
+        p.atom_slot = d_slot;
+        p.atom_type = d_type;
+        p.rmin = d_par;
+        p.dr = d_par + nt * nt;
+        p.coeff = d_par + 2 * nt * nt;
+        p.result = d_res;
+        p.counter = d_counter;
+        p.flags = d_flags;
+        p.natoms = static_cast<int>(t->natoms);
+        p.npad = t->npad;
+        p.ntypes = nt;
+        p.frame = static_cast<int>(frame - t->first_frame);
+        p.triclinic = t->stride == 9 ? 1 : 0;
+        p.lmax = lmax;
+        p.nbin = static_cast<int>(nbin);
+        CU(launch_sh_density(p, dv.stream));
+        CU(cudaMemcpyAsync(result_out, d_res, cells * nl * sizeof(double), cudaMemcpyDeviceToHost, dv.stream));
+        if (counter_out) CU(cudaMemcpyAsync(counter_out, d_counter, cells * sizeof(int), cudaMemcpyDeviceToHost, dv.stream));
+        CU(cudaMemcpyAsync(flags, d_flags, sizeof(flags), cudaMemcpyDeviceToHost, dv.stream));
+        CU(cudaStreamSynchronize(dv.stream));
+        return AGOFRT_OK;
+    };
+    const int rc = body();
+    cudaFree(d_slot);
+    cudaFree(d_type);
+    cudaFree(d_res);
+    cudaFree(d_counter);
+    cudaFree(d_par);
+    cudaFree(d_flags);
+    if (rc != AGOFRT_OK) return rc;
+    if (flags[1]) return fail(AGOFRT_ERR_NONFINITE, "minimum image did not converge within %d images", kWrapCap);
+    return AGOFRT_OK;
+} catch (...) {
+    return on_exception();
+}
+
+// ---------------------------------------------------------------------------------------------
 // FP64 issue-rate microbenchmark
 // ---------------------------------------------------------------------------------------------
 extern "C" int agofrt_fp64_peak(agofrt_ctx *ctx, int local_device, double seconds, double *dfma_per_second) try {

@@ -1759,6 +1759,252 @@ cudaError_t launch_neighbour_finish(int grid, cudaStream_t stream, const Neighbo
 int neighbour_tile_atoms() { return kNbThreads * kNbIPT; }
 
 // ---------------------------------------------------------------------------------------------
+// Neighbour lists and spherical-harmonic densities: the other two pair loops over d2_minImage of the reference
+// (Neighbours::update_neigh, lib/src/neighbour.cpp:8-62; SphericalBase::calc, lib/src/sphericalbase.cpp:19-68).
+// Both need the minimum-image VECTOR xi - xj with its signs, so they take the literal minimum image; both are
+// order-dependent per atom (a list is filled in the order the partners come, a density is a floating-point sum over
+// the partners), so ONE THREAD WALKS ALL PARTNERS OF ITS ATOM IN THE REFERENCE'S ORDER (ascending atom index); the
+// partners' coordinates are staged through shared memory, every thread of the block reading the same one.
+// With 10^5 atoms that is 3000 warps of 10^5 pair evaluations each: enough to fill the FP64 pipes.
+// ---------------------------------------------------------------------------------------------
+constexpr int kLsThreads = 128;
+constexpr int kLsTile = 256;
+
+__global__ void __launch_bounds__(kLsThreads) neigh_list_kernel(const NeighListParams p) {
+    __shared__ double sj[3][kLsTile];
+    __shared__ int stype[kLsTile];
+    const int i = blockIdx.x * kLsThreads + threadIdx.x;
+    const bool live = i < p.natoms;
+    const double *pf = p.pos + static_cast<size_t>(p.frame) * 3 * p.npad;
+    const double *bx = p.box + static_cast<size_t>(p.frame) * 6;
+    BoxRegs b;
+    b.lhx = bx[0];
+    b.lhy = bx[1];
+    b.lhz = bx[2];
+    b.xy = bx[3];
+    b.xz = bx[4];
+    b.yz = bx[5];
+    b.nxy = b.nxz = b.nyz = 0.0;
+    double xi = 0, yi = 0, zi = 0;
+    int ti = 0;
+    if (live) {
+        const int s = p.atom_slot[i];
+        xi = pf[s];
+        yi = pf[p.npad + s];
+        zi = pf[2 * static_cast<size_t>(p.npad) + s];
+        ti = p.atom_type[i];
+    }
+    const double cut_i = live ? p.cutoff2[ti] : 0.0;
+    unsigned long long cnt[kLsMaxTypes];
+#pragma unroll
+    for (int k = 0; k < kLsMaxTypes; ++k) cnt[k] = 0;
+    bool bad = false, wrap_bad = false;
+    for (int j0 = 0; j0 < p.natoms; j0 += kLsTile) {
+        const int n = min(kLsTile, p.natoms - j0);
+        __syncthreads();
+        for (int q = threadIdx.x; q < n; q += kLsThreads) {
+            const int s = p.atom_slot[j0 + q];
+            sj[0][q] = pf[s];
+            sj[1][q] = pf[p.npad + s];
+            sj[2][q] = pf[2 * static_cast<size_t>(p.npad) + s];
+            stype[q] = p.atom_type[j0 + q];
+        }
+        __syncthreads();
+        if (!live) continue;
+        for (int q = 0; q < n; ++q) {
+            const int j = j0 + q;
+            if (j == i) continue;
+            // the reference evaluates the pair once, as (smaller index) - (larger index), and hands the larger one the
+            // negated vector (neighbour.cpp:18, :35-38); the minimum image is odd, so that IS minImage(xi - xj)
+            double dx = __dsub_rn(xi, sj[0][q]), dy = __dsub_rn(yi, sj[1][q]), dz = __dsub_rn(zi, sj[2][q]);
+            if (p.triclinic) {
+                if (!min_image_general<true>(dx, dy, dz, b)) wrap_bad = true;
+            } else {
+                if (!min_image_general<false>(dx, dy, dz, b)) wrap_bad = true;
+            }
+            const double d2 = d2_of(dx, dy, dz);
+            const int tj = stype[q];
+            const double cut_j = p.cutoff2[tj];
+            if (d2 <= cut_j || d2 <= cut_i) {
+                const unsigned long long n_here = cnt[tj];
+                if (n_here >= p.nneigh[tj]) {
+                    bad = true;   // "Too many neighbours in shell!"
+                } else {
+                    unsigned long long *li = p.list + p.list_offset[tj] + static_cast<size_t>(i) * (p.nneigh[tj] + 1) + 1;
+                    double *ri = p.rpos + p.rpos_offset[tj] + (static_cast<size_t>(i) * p.nneigh[tj] + n_here) * 4;
+                    li[n_here] = static_cast<unsigned long long>(j);
+                    ri[0] = __dsqrt_rn(d2);
+                    ri[1] = dx;
+                    ri[2] = dy;
+                    ri[3] = dz;
+                    if (d2 <= cut_j) cnt[tj] = n_here + 1;
+                }
+            }
+        }
+    }
+    if (live) {
+        for (int tj = 0; tj < p.ntypes; ++tj) {
+            unsigned long long *li = p.list + p.list_offset[tj] + static_cast<size_t>(i) * (p.nneigh[tj] + 1);
+            li[0] = cnt[tj];
+            if (p.sort && cnt[tj] > 1) {
+                // ascending distance (the reference: std::sort on the distances, neighbour.cpp:47-69); insertion sort, the
+                // lists hold a few dozen entries
+                double *r = p.rpos + p.rpos_offset[tj] + static_cast<size_t>(i) * p.nneigh[tj] * 4;
+                for (unsigned long long a = 1; a < cnt[tj]; ++a) {
+                    const double r0 = r[a * 4], r1 = r[a * 4 + 1], r2 = r[a * 4 + 2], r3 = r[a * 4 + 3];
+                    const unsigned long long id = li[1 + a];
+                    unsigned long long c = a;
+                    while (c > 0 && r[(c - 1) * 4] > r0) {
+                        r[c * 4] = r[(c - 1) * 4];
+                        r[c * 4 + 1] = r[(c - 1) * 4 + 1];
+                        r[c * 4 + 2] = r[(c - 1) * 4 + 2];
+                        r[c * 4 + 3] = r[(c - 1) * 4 + 3];
+                        li[1 + c] = li[c];
+                        --c;
+                    }
+                    r[c * 4] = r0;
+                    r[c * 4 + 1] = r1;
+                    r[c * 4 + 2] = r2;
+                    r[c * 4 + 3] = r3;
+                    li[1 + c] = id;
+                }
+            }
+        }
+    }
+    if (bad) atomicExch(p.flags, 1u);
+    if (wrap_bad) atomicExch(p.flags + 1, 1u);
+}
+
+cudaError_t launch_neigh_list(const NeighListParams &p, cudaStream_t stream) {
+    if (p.natoms <= 0) return cudaSuccess;
+    neigh_list_kernel<<<(p.natoms + kLsThreads - 1) / kLsThreads, kLsThreads, 0, stream>>>(p);
+    return cudaGetLastError();
+}
+
+// Real spherical harmonics of the direction (x, y, z) for l = 0 .. lmax, the operations of
+// SpecialFunctions::SphericalHarmonics<lmax,double,true,true>::calc (reference lib/include/specialfunctions.h:244-388)
+// one by one, each rounded on its own: cos(theta) = z/r, sin / cos(phi) = y, x over sqrt(x^2+y^2); associated Legendre
+// polynomials by the l,l / l+1,l / l+1,m recursions; cos(m phi), sin(m phi) by the Chebyshev recursion; then
+// (P * coeff) * trig.  out: the reference's dynamic layout, blocks l = lmax .. 0 of (l negative m's, then m = 0 .. l).
+// plm is a scratch of (lmax+1)^2 doubles indexed [l][m].
+__device__ void real_spherical_harmonics(int lmax, double x, double y, double z, const double *__restrict__ coeff,
+                                         double *__restrict__ plm, double *__restrict__ out) {
+    const double rxy = __dsqrt_rn(__dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y)));
+    const double r = __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y)), __dmul_rn(z, z)));
+    const double cost = __ddiv_rn(z, r), sinp = __ddiv_rn(y, rxy), cosp = __ddiv_rn(x, rxy);
+    const int L1 = lmax + 1;
+    // P^m_l: the diagonal first, then from each diagonal element the column m upwards in l
+    plm[0] = 1.0;
+    const double sq = __dsqrt_rn(__dsub_rn(1.0, __dmul_rn(cost, cost)));
+    for (int l = 1; l <= lmax; ++l)   // P^l_l = (-(2l-1) * sqrt(1-x^2)) * P^{l-1}_{l-1}
+        plm[l * L1 + l] = __dmul_rn(__dmul_rn(static_cast<double>(-(2 * l - 1)), sq), plm[(l - 1) * L1 + (l - 1)]);
+    for (int m = 0; m < lmax; ++m) {
+        // P^m_{m+1} = (P^m_m * x) * (2m+1)
+        plm[(m + 1) * L1 + m] = __dmul_rn(__dmul_rn(plm[m * L1 + m], cost), static_cast<double>(2 * m + 1));
+        for (int l = m + 2; l <= lmax; ++l)   // P^m_l = ((P^m_{l-1} * x) * (2l-1) - P^m_{l-2} * (l+m-1)) / (l-m)
+            plm[l * L1 + m] = __ddiv_rn(__dsub_rn(__dmul_rn(__dmul_rn(plm[(l - 1) * L1 + m], cost), static_cast<double>(2 * l - 1)),
+                                                  __dmul_rn(plm[(l - 2) * L1 + m], static_cast<double>(l + m - 1))),
+                                        static_cast<double>(l - m));
+    }
+    // cos(m phi), sin(m phi): c_m = (2 cosp) * c_{m-1} - c_{m-2}
+    double cm[kShMaxL + 1], sm[kShMaxL + 1];
+    cm[0] = 1.0;
+    sm[0] = 0.0;
+    if (lmax >= 1) {
+        cm[1] = cosp;
+        sm[1] = sinp;
+    }
+    const double two_c = __dmul_rn(2.0, cosp);
+    for (int m = 2; m <= lmax; ++m) {
+        cm[m] = __dsub_rn(__dmul_rn(two_c, cm[m - 1]), cm[m - 2]);
+        sm[m] = __dsub_rn(__dmul_rn(two_c, sm[m - 1]), sm[m - 2]);
+    }
+    // (P * coeff) * trig, into the reference's layout
+    int base = 0;
+    for (int l = lmax; l >= 0; --l) {
+        double *minus = out + base, *plus = out + base + l;
+        for (int m = 0; m <= l; ++m) plus[m] = __dmul_rn(__dmul_rn(plm[l * L1 + m], coeff[l * L1 + m]), cm[m]);
+        for (int k = 0; k < l; ++k) {   // val_minus[k] is m = -(k+1): the same P and coefficient as m = k+1, times sin
+            const int m = k + 1;
+            minus[k] = __dmul_rn(__dmul_rn(plm[l * L1 + m], coeff[l * L1 + m]), sm[m]);
+        }
+        base += 2 * l + 1;
+    }
+}
+
+__global__ void __launch_bounds__(kLsThreads) sh_density_kernel(const ShDensityParams p) {
+    __shared__ double sj[3][kLsTile];
+    __shared__ int stype[kLsTile];
+    const int i = blockIdx.x * kLsThreads + threadIdx.x;
+    const bool live = i < p.natoms;
+    const int nl = (p.lmax + 1) * (p.lmax + 1);
+    const double *pf = p.pos + static_cast<size_t>(p.frame) * 3 * p.npad;
+    const double *bx = p.box + static_cast<size_t>(p.frame) * 6;
+    BoxRegs b;
+    b.lhx = bx[0];
+    b.lhy = bx[1];
+    b.lhz = bx[2];
+    b.xy = bx[3];
+    b.xz = bx[4];
+    b.yz = bx[5];
+    b.nxy = b.nxz = b.nyz = 0.0;
+    double xi = 0, yi = 0, zi = 0;
+    int ti = 0;
+    if (live) {
+        const int s = p.atom_slot[i];
+        xi = pf[s];
+        yi = pf[p.npad + s];
+        zi = pf[2 * static_cast<size_t>(p.npad) + s];
+        ti = p.atom_type[i];
+    }
+    double plm[(kShMaxL + 1) * (kShMaxL + 1)], ylm[(kShMaxL + 1) * (kShMaxL + 1)];
+    bool wrap_bad = false;
+    for (int j0 = 0; j0 < p.natoms; j0 += kLsTile) {
+        const int n = min(kLsTile, p.natoms - j0);
+        __syncthreads();
+        for (int q = threadIdx.x; q < n; q += kLsThreads) {
+            const int s = p.atom_slot[j0 + q];
+            sj[0][q] = pf[s];
+            sj[1][q] = pf[p.npad + s];
+            sj[2][q] = pf[2 * static_cast<size_t>(p.npad) + s];
+            stype[q] = p.atom_type[j0 + q];
+        }
+        __syncthreads();
+        if (!live) continue;
+        for (int q = 0; q < n; ++q) {
+            const int j = j0 + q;
+            if (j == i) continue;
+            double dx = __dsub_rn(xi, sj[0][q]), dy = __dsub_rn(yi, sj[1][q]), dz = __dsub_rn(zi, sj[2][q]);
+            if (p.triclinic) {
+                if (!min_image_general<true>(dx, dy, dz, b)) wrap_bad = true;
+            } else {
+                if (!min_image_general<false>(dx, dy, dz, b)) wrap_bad = true;
+            }
+            const double d = __dsqrt_rn(d2_of(dx, dy, dz));
+            const int tj = stype[q];
+            const int pair = p.ntypes * ti + tj;
+            // int idx = (int) floorf((d - rmin) / dr): the double quotient is rounded to float first (sphericalbase.cpp:51)
+            const float qf = __double2float_rn(__ddiv_rn(__dsub_rn(d, p.rmin[pair]), p.dr[pair]));
+            const float fl = floorf(qf);
+            if (!(fl >= 0.0f) || !(fl < static_cast<float>(p.nbin))) continue;   // also NaN
+            const int idx = static_cast<int>(fl);
+            real_spherical_harmonics(p.lmax, dx, dy, dz, p.coeff, plm, ylm);
+            const size_t cell = (static_cast<size_t>(p.nbin) * (static_cast<size_t>(p.ntypes) * i + tj) + idx);
+            double *res = p.result + cell * nl;
+            for (int ll = 0; ll < nl; ++ll) res[ll] = __dadd_rn(res[ll], ylm[ll]);
+            if (p.counter) p.counter[cell] += 1;
+        }
+    }
+    if (wrap_bad) atomicExch(p.flags + 1, 1u);
+}
+
+cudaError_t launch_sh_density(const ShDensityParams &p, cudaStream_t stream) {
+    if (p.natoms <= 0) return cudaSuccess;
+    sh_density_kernel<<<(p.natoms + kLsThreads - 1) / kLsThreads, kLsThreads, 0, stream>>>(p);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
 // Mean square displacement (MSD<T>::calc_single_th, reference lib/src/msd.cpp:63-125): for lag t and type ty the
 // mean over origins and atoms of |x_i(o) - x_i(o+t)|^2 (optionally minus the displacement of the type's centre of
 // mass).  No minimum image: the reference works on the coordinates as stored.  HBM/L2-bound: 48 bytes read for

@@ -138,6 +138,34 @@ cudaError_t launch_neighbour_kernel(bool triclinic, bool fast, int grid, cudaStr
 cudaError_t launch_neighbour_finish(int grid, cudaStream_t stream, const NeighbourParams &p, unsigned int v_begin, unsigned int v_end);
 int neighbour_tile_atoms();
 
+// neighbour lists (Neighbours::update_neigh) and spherical-harmonic densities (SphericalBase::calc) of one frame
+constexpr int kLsMaxTypes = 8;   // atom types these two kernels handle
+constexpr int kShMaxL = 10;      // the reference instantiates l = 2 .. 10
+struct NeighListParams {
+    const double *pos;          // [frames][3][npad]
+    const double *box;          // [frames][6]
+    const int *atom_slot;       // [natoms] atom (caller's numbering) -> device slot
+    const int *atom_type;       // [natoms] dense type
+    unsigned long long *list;   // the reference's layout: per type t a block of natoms * (nneigh[t] + 1) words, count first
+    double *rpos;               // per type t a block of natoms * nneigh[t] * 4 doubles: r, x, y, z
+    unsigned int *flags;        // [0] a list overflowed ("Too many neighbours in shell!"), [1] minimum image did not converge
+    unsigned long long nneigh[kLsMaxTypes], list_offset[kLsMaxTypes], rpos_offset[kLsMaxTypes];
+    double cutoff2[kLsMaxTypes];
+    int natoms, npad, ntypes, frame, triclinic, sort;
+};
+cudaError_t launch_neigh_list(const NeighListParams &p, cudaStream_t stream);
+struct ShDensityParams {
+    const double *pos, *box;
+    const int *atom_slot, *atom_type;
+    const double *rmin, *dr;    // [ntypes*ntypes] per ordered type pair (type of i, type of j)
+    const double *coeff;        // [(lmax+1)^2] real spherical harmonics coefficients, [l][m]
+    double *result;             // [natoms][ntypes][nbin][(lmax+1)^2], zeroed by the caller
+    int *counter;               // [natoms][ntypes][nbin] or NULL
+    unsigned int *flags;
+    int natoms, npad, ntypes, frame, triclinic, lmax, nbin;
+};
+cudaError_t launch_sh_density(const ShDensityParams &p, cudaStream_t stream);
+
 // mean square displacement (MSD)
 struct MsdParams {
     const double *pos;        // [frames][3][npad]

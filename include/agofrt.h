@@ -284,6 +284,25 @@ AGOFRT_API int agofrt_traj_set_cm(agofrt_traj *traj, size_t first_frame, size_t 
 AGOFRT_API int agofrt_msd(agofrt_traj *traj, size_t primo, unsigned ntimesteps, unsigned leff, unsigned skip,
                           int cm_msd, int cm_self, double *out, agofrt_stats *stats);
 
+/* ---- the other pair loops over d2_minImage: neighbour lists and spherical-harmonic densities of one frame ---------- */
+/* Neighbours<T,double>::update_neigh(frame, sort) (lib/src/neighbour.cpp:8-76): for every atom and every type the list of
+ * the atoms of that type within the type's cutoff, in ascending atom index (sort: in ascending distance), with the
+ * minimum-image vector xi - xj of each.  nneigh[t] / cutoff2[t]: capacity and squared cutoff for type t (the reference's
+ * ListSpec).  Output in the reference's own layout: list_out = per type t a block of natoms * (nneigh[t] + 1) words, the
+ * count first; rpos_out = per type t a block of natoms * nneigh[t] * 4 doubles (r, x, y, z).  A list that overflows is
+ * AGOFRT_ERR_TOO_LARGE ("Too many neighbours in shell!", the reference's exception).  The literal minimum image; one
+ * thread walks the partners of its atom in the reference's order. */
+AGOFRT_API int agofrt_neighbours(agofrt_traj *traj, size_t frame, const uint64_t *nneigh, const double *cutoff2, int sort,
+                                 uint64_t *list_out, double *rpos_out);
+/* SphericalBase<lmax,double,T>::calc(frame, ...) without neighbour list (lib/src/sphericalbase.cpp:19-68): for every atom
+ * i, type and radial bin the sum over the atoms j of that type in that bin of the real spherical harmonics Y_lm of the
+ * direction xi - xj, l = 0 .. lmax <= 10 (SpecialFunctions::SphericalHarmonics, lib/include/specialfunctions.h:335-388:
+ * the same recursions, every operation rounded on its own, summed in ascending j).  rminmax [ntypes*ntypes][2]: radial
+ * range of the ordered type pair (type of i, type of j); result_out [natoms][ntypes][nbin][(lmax+1)^2] in the
+ * reference's layout (l = lmax .. 0, negative m's first), counter_out [natoms][ntypes][nbin] or NULL. */
+AGOFRT_API int agofrt_sh_density(agofrt_traj *traj, size_t frame, int lmax, unsigned nbin, const double *rminmax,
+                                 double *result_out, int *counter_out);
+
 /* ---- measurement --------------------------------------------------------------------------- */
 /* Sustained FP64 FMA issue rate of one device (DFMA chains, CUDA events): the roofline
  * denominator of SURVEY.md section 8(d).  Runs for about `seconds`. */

@@ -4,7 +4,7 @@
 // directory compiles this file together with the reference's own translation
 // units, taken where they lie under /root/reference:
 //     lib/src/gofrt.cpp  lib/src/basetrajectory.cpp  lib/src/trajectory.cpp
-//     lib/src/trajectory_numpy.cpp  lib/src/cronometro.C
+//     lib/src/trajectory_numpy.cpp  lib/src/cronometro.C  lib/src/neighbour.cpp  lib/src/sphericalbase.cpp
 // into oracle/_ref/analisi_ref*.so.  Nothing of the reference is copied into
 // this repository: this file only *includes* its headers and exposes them to
 // the tests with the same class names the reference's own module uses
@@ -28,6 +28,8 @@
 #include "trajectory_numpy.h"
 #include "gofrt.h"
 #include "blockaverage.h"
+#include "neighbour.h"
+#include "sphericalbase.h"
 
 namespace py = pybind11;
 
@@ -140,6 +142,61 @@ py::tuple block_average_gofrt(const std::string &path, unsigned nblocks, double 
     return py::make_tuple(mean, var, gofr.puntatoreCalcolo()->get_columns_description());
 }
 
+// Neighbours<Trajectory_numpy,double> (lib/include/neighbour.h, lib/src/neighbour.cpp): the lists of one frame as arrays.
+//   spec: one (max neighbours, cutoff^2, skin^2) per type, as the reference's ListSpec
+//   -> counts [natoms][ntypes], indices [natoms][ntypes][maxn] (-1 past the count), r [natoms][ntypes][maxn][4]
+//      (distance, x, y, z; 0 past the count), sann_n [natoms][ntypes] (only meaningful after a sorted update)
+py::tuple ref_neighbours(Trajectory_numpy &t, std::vector<std::tuple<size_t, double, double>> spec, size_t timestep, bool sort) {
+    Neighbours<Trajectory_numpy, double> nn(&t, spec);
+    nn.update_neigh(timestep, sort);
+    const long n = t.get_natoms(), nt = t.get_ntypes();
+    size_t maxn = 0;
+    for (auto &s : spec) maxn = std::max(maxn, std::get<0>(s));
+    py::array_t<long> counts({n, nt}), idx({n, nt, (long)maxn}), sann({n, nt});
+    py::array_t<double> r({n, nt, (long)maxn, 4L});
+    std::fill(idx.mutable_data(), idx.mutable_data() + idx.size(), -1L);
+    std::fill(r.mutable_data(), r.mutable_data() + r.size(), 0.0);
+    for (long i = 0; i < n; ++i)
+        for (long jt = 0; jt < nt; ++jt) {
+            auto it = nn.get_neigh(i, jt);
+            auto ir = nn.get_neigh_r(i, jt);
+            counts.mutable_at(i, jt) = (long)it.size();
+            sann.mutable_at(i, jt) = sort ? (long)nn.get_sann_n(i, jt) : -1L;
+            for (size_t k = 0; k < it.size(); ++k) {
+                idx.mutable_at(i, jt, (long)k) = (long)it.begin()[k];
+                for (int c = 0; c < 4; ++c) r.mutable_at(i, jt, (long)k, c) = ir.begin()[k][c];
+            }
+        }
+    return py::make_tuple(counts, idx, r, sann);
+}
+
+// SphericalBase<L,double,Trajectory_numpy>::calc without neighbour list (lib/src/sphericalbase.cpp:19-68):
+//   -> result [natoms][ntypes][nbin][(L+1)^2], counter [natoms][ntypes][nbin]
+template <int L>
+py::tuple ref_sh_density_l(Trajectory_numpy &t, size_t nbin, std::vector<std::pair<double, double>> rminmax, int timestep) {
+    SphericalBase<L, double, Trajectory_numpy> sb(&t, nbin, rminmax);
+    const long n = t.get_natoms(), nt = t.get_ntypes(), nl = (L + 1) * (L + 1);
+    py::array_t<double> result({n, nt, (long)nbin, nl});
+    py::array_t<int> counter({n, nt, (long)nbin});
+    std::vector<double> workspace(nl), cheby(2 * (L + 1));
+    sb.calc(timestep, result.mutable_data(), workspace.data(), cheby.data(), counter.mutable_data(), nullptr);
+    return py::make_tuple(result, counter);
+}
+py::tuple ref_sh_density(Trajectory_numpy &t, int lmax, size_t nbin, std::vector<std::pair<double, double>> rminmax, int timestep) {
+    switch (lmax) {
+        case 2: return ref_sh_density_l<2>(t, nbin, rminmax, timestep);
+        case 3: return ref_sh_density_l<3>(t, nbin, rminmax, timestep);
+        case 4: return ref_sh_density_l<4>(t, nbin, rminmax, timestep);
+        case 5: return ref_sh_density_l<5>(t, nbin, rminmax, timestep);
+        case 6: return ref_sh_density_l<6>(t, nbin, rminmax, timestep);
+        case 7: return ref_sh_density_l<7>(t, nbin, rminmax, timestep);
+        case 8: return ref_sh_density_l<8>(t, nbin, rminmax, timestep);
+        case 9: return ref_sh_density_l<9>(t, nbin, rminmax, timestep);
+        case 10: return ref_sh_density_l<10>(t, nbin, rminmax, timestep);
+        default: throw std::runtime_error("the reference instantiates SphericalBase for l = 2 .. 10");
+    }
+}
+
 }  // namespace
 
 PYBIND11_MODULE(analisi_ref, m) {
@@ -188,5 +245,7 @@ PYBIND11_MODULE(analisi_ref, m) {
     m.def("block_average_gofrt", &block_average_gofrt, py::arg("path"), py::arg("nblocks"),
           py::arg("rmin"), py::arg("rmax"), py::arg("nbin"), py::arg("tmax"), py::arg("nthreads"),
           py::arg("skip"), py::arg("every") = 1, py::arg("dump") = false, py::arg("wrap") = true);
+    m.def("neighbours", &ref_neighbours, py::arg("traj"), py::arg("spec"), py::arg("timestep"), py::arg("sort"));
+    m.def("sh_density", &ref_sh_density, py::arg("traj"), py::arg("lmax"), py::arg("nbin"), py::arg("rminmax"), py::arg("timestep"));
     m.def("info", []() -> std::string { return _info_msg; });
 }

@@ -72,3 +72,25 @@ def ctx():
     c = cabi.Context()
     yield c
     c.close()
+
+
+# Neighbours / SphericalBase fixtures from the compiled reference (tests/golden/make_golden.py: PAIR_LOOP_CASES)
+PAIR_LOOP_CASES = {
+    "tri2": (81, (4, 4, 3), 2, True, 1, [(40, 4.0, 4.0), (40, 6.25, 6.25)], 4, 3, [(0.5, 3.0), (0.4, 2.6), (0.4, 2.6), (0.0, 2.0)]),
+    "ortho3": (82, (5, 4, 3), 3, False, 2, [(30, 3.0, 3.0), (30, 3.0, 3.0), (30, 5.0, 5.0)], 6, 2, [(0.3, 2.4)] * 9),
+    "tri1_l10": (83, (3, 3, 3), 1, True, 0, [(60, 9.0, 9.0)], 10, 2, [(0.0, 3.2)]),
+}
+
+
+def pair_loop_case(name):
+    import hashlib
+    from analisi_b200 import synth
+    z = load_golden("pair_loops.npz")
+    pre = name + "/"
+    d = {k[len(pre):]: z[k] for k in z.files if k.startswith(pre)}
+    seed, cells, ntypes, tri, frame, spec, lmax, nbin, rminmax = PAIR_LOOP_CASES[name]
+    pos, box, types = synth.small_case(seed, cells, 1.1, ntypes, tri, 3, "parity")
+    sha = np.frombuffer(hashlib.sha256(np.ascontiguousarray(pos).tobytes()).digest(), dtype=np.uint8)
+    assert np.array_equal(sha, d["pos_in_sha256"]), "synth.small_case no longer reproduces the fixture's input: regenerate it"
+    d.update(pos=pos, box=box, types=types, ntypes=ntypes, tri=tri, frame=frame, spec=spec, lmax=lmax, nbin=nbin, rminmax=rminmax)
+    return d

@@ -200,6 +200,39 @@ def live_reference_tile_cases(m):
     np.savez_compressed(os.path.join(HERE, "live_reference_tile.npz"), **out)
 
 
+PAIR_LOOP_CASES = {
+    # name: (seed, cells, ntypes, triclinic, frame, neighbour spec [(max, cutoff^2, skin^2)], lmax, nbin, rminmax)
+    "tri2": (81, (4, 4, 3), 2, True, 1, [(40, 4.0, 4.0), (40, 6.25, 6.25)], 4, 3, [(0.5, 3.0), (0.4, 2.6), (0.4, 2.6), (0.0, 2.0)]),
+    "ortho3": (82, (5, 4, 3), 3, False, 2, [(30, 3.0, 3.0), (30, 3.0, 3.0), (30, 5.0, 5.0)], 6, 2, [(0.3, 2.4)] * 9),
+    "tri1_l10": (83, (3, 3, 3), 1, True, 0, [(60, 9.0, 9.0)], 10, 2, [(0.0, 3.2)]),
+}
+
+
+def pair_loop_fixtures(m):
+    """The other two pair loops over d2_minImage, from the compiled reference: Neighbours::update_neigh (unsorted and sorted
+    lists, SANN counts; lib/src/neighbour.cpp) and SphericalBase::calc (lib/src/sphericalbase.cpp).  Inputs are
+    synth.small_case(seed, ...) again (sha256 kept)."""
+    import hashlib
+    out = {}
+    for name, (seed, cells, ntypes, tri, frame, spec, lmax, nbin, rminmax) in PAIR_LOOP_CASES.items():
+        pos, box, types = synth.small_case(seed, cells, 1.1, ntypes, tri, 3, "parity")
+        fmt = m.BoxFormat.LammpsTriclinic if tri else m.BoxFormat.LammpsOrtho
+        tr = m.Trajectory(pos, np.zeros_like(pos), types, box, fmt, True, False)
+        out[name + "/pos_in_sha256"] = np.frombuffer(hashlib.sha256(np.ascontiguousarray(pos).tobytes()).digest(), dtype=np.uint8)
+        for sort in (False, True):
+            c, idx, r, sann = m.neighbours(tr, spec, frame, sort)
+            tag = "/sorted_" if sort else "/unsorted_"
+            out[name + tag + "counts"] = c
+            out[name + tag + "idx"] = idx
+            out[name + tag + "r"] = r
+            if sort:
+                out[name + "/sann_n"] = sann
+        res, cnt = m.sh_density(tr, lmax, nbin, rminmax, frame)
+        out[name + "/sh"] = res
+        out[name + "/sh_counter"] = cnt
+    np.savez_compressed(os.path.join(HERE, "pair_loops.npz"), **out)
+
+
 def cell_vectors_rotation(m):
     """Trajectory_numpy with BoxFormat.CellVectors and general (rotated) cells: the reference QR-rotates
     cell, positions and velocities into the LAMMPS frame (lib/include/triclinic.h:10-73 with Eigen's
@@ -287,6 +320,7 @@ def main():
     min_image_and_pbc(m)
     live_reference_cases(m)
     live_reference_tile_cases(m)
+    pair_loop_fixtures(m)
     cell_vectors_rotation(m)
     qr_many(m)
     cli_golden_text()

@@ -6,7 +6,7 @@ import pytest
 
 import oracle
 from analisi_b200 import cabi, synth
-from conftest import LIVE_CASES, TILE_CASES, live_case, load_golden, tile_case
+from conftest import LIVE_CASES, PAIR_LOOP_CASES, TILE_CASES, live_case, load_golden, pair_loop_case, tile_case
 
 pytestmark = pytest.mark.gpu
 
@@ -746,3 +746,46 @@ def test_c4_subset_against_the_reference_itself(ctx):
     assert np.array_equal(c[gold["lags"]], gold["counts"])
     assert hashlib.sha256(np.ascontiguousarray(c).astype("<u8").tobytes()).hexdigest() == meta["counts_sha256"]
     assert int(c.sum()) == meta["counts_sum"]
+
+
+# ---- the other pair loops over d2_minImage: neighbour lists and spherical-harmonic densities --------------------------
+@pytest.mark.parametrize("name", sorted(PAIR_LOOP_CASES))
+def test_neighbour_lists_vs_the_reference(ctx, name):
+    """agofrt_neighbours against Neighbours::update_neigh of the compiled reference: counts, partner indices in the
+    reference's order (ascending index, or ascending distance), distances and minimum-image vectors bit for bit."""
+    d = pair_loop_case(name)
+    bi = synth.lammps_rows_to_internal(d["box"])
+    pos = np.ascontiguousarray(d["pos"]).copy()
+    ctx.pbc_wrap(pos, bi)
+    tr = cabi.DeviceTrajectory(ctx, pos.shape[1], bi.shape[1], d["types"], d["ntypes"], pos.shape[0])
+    tr.upload(0, pos, bi)
+    spec = [(s[0], s[1]) for s in d["spec"]]
+    for sort, tag in ((False, "unsorted_"), (True, "sorted_")):
+        counts, idx, r = tr.neighbours(d["frame"], spec, sort=sort)
+        assert np.array_equal(counts, d[tag + "counts"])
+        assert np.array_equal(idx, d[tag + "idx"])
+        assert np.array_equal(r, d[tag + "r"])
+    assert counts.sum() > 0
+    # a list that overflows is the reference's exception
+    with pytest.raises(cabi.AgofrtError) as e:
+        tr.neighbours(d["frame"], [(2, s[1]) for s in d["spec"]])
+    assert e.value.code == cabi.ERR_TOO_LARGE and "Too many neighbours in shell" in str(e.value)
+    tr.close()
+
+
+@pytest.mark.parametrize("name", sorted(PAIR_LOOP_CASES))
+def test_spherical_harmonic_density_vs_the_reference(ctx, name):
+    """agofrt_sh_density against SphericalBase<l,double,Trajectory_numpy>::calc of the compiled reference (l = 4, 6, 10):
+    the per-atom, per-type, per-bin sums of real spherical harmonics and the neighbour counters, bit for bit."""
+    d = pair_loop_case(name)
+    bi = synth.lammps_rows_to_internal(d["box"])
+    pos = np.ascontiguousarray(d["pos"]).copy()
+    ctx.pbc_wrap(pos, bi)
+    tr = cabi.DeviceTrajectory(ctx, pos.shape[1], bi.shape[1], d["types"], d["ntypes"], pos.shape[0])
+    tr.upload(0, pos, bi)
+    res, cnt = tr.sh_density(d["frame"], d["lmax"], d["nbin"], d["rminmax"])
+    assert np.array_equal(cnt, d["sh_counter"]) and cnt.sum() > 0
+    assert res.shape == d["sh"].shape
+    bad = res != d["sh"]
+    assert not bad.any(), (int(bad.sum()), float(np.abs(res - d["sh"]).max()))
+    tr.close()
