@@ -21,6 +21,8 @@
 #include "analisi/gofrt.h"
 #include "analisi/istogrammaatomiraggio.h"
 #include "analisi/msd.h"
+#include "analisi/neighbour.h"
+#include "analisi/sphericalbase.h"
 #include "analisi/trajectory.h"
 #include "analisi/trajectory_numpy.h"
 
@@ -198,6 +200,58 @@ void define_neighbour_hist(py::module &m, const std::string &suffix) {
         });
 }
 
+// Neighbours / Neighbours_lammps (reference pyanalisi/src/pyanalisi.cpp:193-236): cutoff neighbour lists and SANN
+template <class TR>
+void define_neighbours(py::module &m, const std::string &suffix) {
+    using N = Neighbours<TR, double>;
+    auto rows = [](typename N::template NeighIterator<typename N::TType4> it) {
+        py::array_t<double> a({static_cast<ssize_t>(it.size()), static_cast<ssize_t>(4)});
+        if (it.size()) std::memcpy(a.mutable_data(), it.begin(), it.size() * 4 * sizeof(double));
+        return a;
+    };
+    auto idxs = [](typename N::template NeighIterator<size_t> it) {
+        py::array_t<size_t> a(static_cast<ssize_t>(it.size()));
+        if (it.size()) std::memcpy(a.mutable_data(), it.begin(), it.size() * sizeof(size_t));
+        return a;
+    };
+    py::class_<N>(m, ("Neighbours" + suffix).c_str(), py::module_local())
+        .def(py::init<TR *, typename N::ListSpec>(), py::keep_alive<1, 2>(),
+             "Trajectory instance, list of (max number of neighbours, cutoff**2, skin**2), one per atomic type")
+        .def("calculate_neigh", &N::update_neigh, py::call_guard<py::gil_scoped_release>())
+        .def("get_sann", [rows](N &n, size_t iatom, size_t jtype) { return rows(n.get_sann_r(iatom, jtype)); })
+        .def("get_sann_idx", [idxs](N &n, size_t iatom, size_t jtype) { return idxs(n.get_sann(iatom, jtype)); })
+        .def("get_neigh", [rows](N &n, size_t iatom, size_t jtype) { return rows(n.get_neigh_r(iatom, jtype)); })
+        .def("get_neigh_idx", [idxs](N &n, size_t iatom, size_t jtype) { return idxs(n.get_neigh(iatom, jtype)); });
+}
+
+// Addition: SphericalBase::calc of one frame (the reference reaches it through SphericalCorrelations / Steinhardt only)
+template <int L, class TR>
+py::tuple sh_density_l(TR &t, size_t nbin, std::vector<std::pair<double, double>> rminmax, int timestep) {
+    SphericalBase<L, double, TR> sb(&t, nbin, rminmax);
+    const ssize_t n = static_cast<ssize_t>(t.get_natoms()), nt = static_cast<ssize_t>(t.get_ntypes()), nl = (L + 1) * (L + 1);
+    py::array_t<double> result({n, nt, static_cast<ssize_t>(nbin), nl});
+    py::array_t<int> counter({n, nt, static_cast<ssize_t>(nbin)});
+    sb.calc(timestep, result.mutable_data(), nullptr, nullptr, counter.mutable_data(), nullptr);
+    return py::make_tuple(result, counter);
+}
+template <class TR>
+py::tuple sh_density(TR &t, int lmax, size_t nbin, std::vector<std::pair<double, double>> rminmax, int timestep) {
+    switch (lmax) {
+        case 0: return sh_density_l<0>(t, nbin, rminmax, timestep);
+        case 1: return sh_density_l<1>(t, nbin, rminmax, timestep);
+        case 2: return sh_density_l<2>(t, nbin, rminmax, timestep);
+        case 3: return sh_density_l<3>(t, nbin, rminmax, timestep);
+        case 4: return sh_density_l<4>(t, nbin, rminmax, timestep);
+        case 5: return sh_density_l<5>(t, nbin, rminmax, timestep);
+        case 6: return sh_density_l<6>(t, nbin, rminmax, timestep);
+        case 7: return sh_density_l<7>(t, nbin, rminmax, timestep);
+        case 8: return sh_density_l<8>(t, nbin, rminmax, timestep);
+        case 9: return sh_density_l<9>(t, nbin, rminmax, timestep);
+        case 10: return sh_density_l<10>(t, nbin, rminmax, timestep);
+        default: throw std::runtime_error("lmax must be in [0, 10]");
+    }
+}
+
 }  // namespace
 
 PYBIND11_MODULE(pyanalisi, m) {
@@ -262,6 +316,13 @@ PYBIND11_MODULE(pyanalisi, m) {
     define_msd<Trajectory_numpy>(m, "");
     define_neighbour_hist<Trajectory>(m, "_lammps");
     define_neighbour_hist<Trajectory_numpy>(m, "");
+    define_neighbours<Trajectory>(m, "_lammps");
+    define_neighbours<Trajectory_numpy>(m, "");
+    m.def("spherical_harmonic_density", &sh_density<Trajectory_numpy>, py::arg("traj"), py::arg("lmax"), py::arg("nbin"),
+          py::arg("rminmax"), py::arg("timestep"),
+          "SphericalBase::calc of one frame: (result [natoms][ntypes][nbin][(lmax+1)^2], counter [natoms][ntypes][nbin])");
+    m.def("spherical_harmonic_density_lammps", &sh_density<Trajectory>, py::arg("traj"), py::arg("lmax"), py::arg("nbin"),
+          py::arg("rminmax"), py::arg("timestep"));
     define_block_average<Trajectory>(m, "_lammps");
     define_block_average<Trajectory_numpy>(m, "");
 

@@ -12,7 +12,7 @@ import pytest
 import oracle
 from analisi_b200 import build as b
 from analisi_b200 import cabi, synth
-from conftest import GOLDEN, LIVE_CASES, ROOT, live_case, load_golden
+from conftest import GOLDEN, LIVE_CASES, PAIR_LOOP_CASES, ROOT, live_case, load_golden, pair_loop_case
 
 pytestmark = pytest.mark.gpu
 
@@ -547,3 +547,28 @@ def test_pyanalisi_msd(host):
     w = analysis.compute_msd(tr, start=2, stop=40, tmax=8, tskip_msd=5)
     ref2 = oracle.msd(pos, types, 30, 8, primo=2, skip=5, cm_msd=True, ntypes=2)
     assert w.shape == (8, 2, 2) and np.allclose(w, ref2, rtol=1e-12, atol=0) and np.array_equal(w[:, 1], ref2[:, 1])
+
+
+@pytest.mark.parametrize("name", sorted(PAIR_LOOP_CASES))
+def test_pyanalisi_neighbours_and_spherical_density(host, name):
+    """Neighbours (reference pyanalisi.cpp:193-236: calculate_neigh, get_neigh, get_sann, get_sann_idx) and
+    SphericalBase::calc through the host classes, against the fixtures of the compiled reference -- lists, SANN counts,
+    spherical-harmonic densities bit for bit."""
+    _, pa = host
+    d = pair_loop_case(name)
+    pos = np.ascontiguousarray(d["pos"])
+    fmt = pa.BoxFormat.LammpsTriclinic if d["tri"] else pa.BoxFormat.LammpsOrtho
+    tr = pa.Trajectory(pos, np.zeros_like(pos), d["types"].astype(np.int32), d["box"], fmt, True, False)
+    nn = pa.Neighbours(tr, [tuple(s) for s in d["spec"]])
+    nn.calculate_neigh(d["frame"], True)
+    for i in range(0, pos.shape[1], 5):
+        for jt in range(d["ntypes"]):
+            c = int(d["sorted_counts"][i, jt])
+            assert np.array_equal(nn.get_neigh(i, jt), d["sorted_r"][i, jt, :c])
+            assert np.array_equal(nn.get_neigh_idx(i, jt), d["sorted_idx"][i, jt, :c])
+            sn = int(d["sann_n"][i, jt])
+            assert nn.get_sann(i, jt).shape == (sn, 4) and np.array_equal(nn.get_sann_idx(i, jt), d["sorted_idx"][i, jt, :sn])
+    with pytest.raises(RuntimeError, match="Too many neighbours in shell"):
+        pa.Neighbours(tr, [(1, s[1], s[2]) for s in d["spec"]]).calculate_neigh(d["frame"], False)
+    res, cnt = pa.spherical_harmonic_density(tr, d["lmax"], d["nbin"], [tuple(r) for r in d["rminmax"]], d["frame"])
+    assert np.array_equal(cnt, d["sh_counter"]) and np.array_equal(res, d["sh"])
