@@ -81,6 +81,7 @@ struct NcclApi {
     ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t,
                               cudaStream_t) = nullptr;
     ncclResult_t (*Broadcast)(const void *, void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*CommSplit)(ncclComm_t, int, int, ncclComm_t *, void *) = nullptr;   // NCCL >= 2.18
     const char *(*GetErrorString)(ncclResult_t) = nullptr;
     bool ok = false;
@@ -111,6 +112,7 @@ static NcclApi &nccl_api() {
     LOAD(AllReduce, "ncclAllReduce")
     LOAD(GetErrorString, "ncclGetErrorString")
     LOAD(Broadcast, "ncclBroadcast")
+    LOAD(AllGather, "ncclAllGather")
 #undef LOAD
     api.CommSplit = reinterpret_cast<decltype(api.CommSplit)>(dlsym(api.handle, "ncclCommSplit"));   // optional
     api.ok = true;
@@ -1011,16 +1013,28 @@ static int upload_impl(agofrt_traj *t, size_t first_frame, size_t nframes, const
             // the shares change hands: rank r's frames and their bounds go to everybody, flags are combined
             NcclApi &api = nccl_api();
             NC(api.GroupStart());
-            for (int r = 0; r < world; ++r) {
-                uint64_t b0 = 0, e0 = 0;
-                agofrt_shard_range(nframes, r, world, &b0, &e0);
-                if (e0 <= b0) continue;
+            if (nframes % static_cast<size_t>(world) == 0) {
+                // equal shares: one in-place all-gather of the positions and one of the bounds
+                const size_t per = nframes / static_cast<size_t>(world);
                 for (int i = 0; i < nloc; ++i) {
-                    Dev &dv = ctx->devs[i];
                     TrajDev &d = t->dev[i];
-                    double *ppos = d.pos + b0 * 3 * static_cast<size_t>(t->npad);
-                    NC(api.Broadcast(ppos, ppos, (e0 - b0) * 3 * static_cast<size_t>(t->npad), ncclDouble, r, dv.comm_up, d.up));
-                    NC(api.Broadcast(d.bounds + b0 * 6, d.bounds + b0 * 6, (e0 - b0) * 6, ncclDouble, r, dv.comm_up, d.up));
+                    const size_t r = static_cast<size_t>(first_rank + i);
+                    NC(api.AllGather(d.pos + r * per * 3 * static_cast<size_t>(t->npad), d.pos, per * 3 * static_cast<size_t>(t->npad),
+                                     ncclDouble, ctx->devs[i].comm_up, d.up));
+                    NC(api.AllGather(d.bounds + r * per * 6, d.bounds, per * 6, ncclDouble, ctx->devs[i].comm_up, d.up));
+                }
+            } else {
+                for (int r = 0; r < world; ++r) {
+                    uint64_t b0 = 0, e0 = 0;
+                    agofrt_shard_range(nframes, r, world, &b0, &e0);
+                    if (e0 <= b0) continue;
+                    for (int i = 0; i < nloc; ++i) {
+                        Dev &dv = ctx->devs[i];
+                        TrajDev &d = t->dev[i];
+                        double *ppos = d.pos + b0 * 3 * static_cast<size_t>(t->npad);
+                        NC(api.Broadcast(ppos, ppos, (e0 - b0) * 3 * static_cast<size_t>(t->npad), ncclDouble, r, dv.comm_up, d.up));
+                        NC(api.Broadcast(d.bounds + b0 * 6, d.bounds + b0 * 6, (e0 - b0) * 6, ncclDouble, r, dv.comm_up, d.up));
+                    }
                 }
             }
             for (int i = 0; i < nloc; ++i)
@@ -1781,7 +1795,9 @@ static int block_impl(agofrt_plan *p, size_t primo, unsigned ntimesteps, unsigne
     int n_jchunks = 1;
     {
         const int max_chunks = std::max(1, (t->npad + 4 * kTileJ - 1) / (4 * kTileJ));
-        const uint64_t want = 16ull * total_ctas;
+        // enough units that the last one a CTA draws is a small part of its share: 64 per CTA (with 16, the 8-GPU run of
+        // the default bench step had 17 units of 17 ms per CTA: a tail of up to 6 %)
+        const uint64_t want = 64ull * total_ctas;
         const uint64_t base = std::max<uint64_t>(1, njobs * n_itiles);
         n_jchunks = static_cast<int>(std::min<uint64_t>(max_chunks, (want + base - 1) / base));
         n_jchunks = std::max(1, n_jchunks);
@@ -2181,42 +2197,52 @@ extern "C" int agofrt_blocks(agofrt_plan *p, size_t primo0, size_t stride, unsig
     ms_alloc = since0();
     agofrt_stats sum;
     memset(&sum, 0, sizeof(sum));
-    std::vector<char> first(nloc, 1);
-    for (unsigned b = 0; b < nblocks; ++b) {
-        const int g = static_cast<int>(b % static_cast<unsigned>(world));
-        if (g < first_rank || g >= first_rank + nloc) continue;
-        const int i = g - first_rank;
-        BlockTarget tg{i, p->dev[i].batch + static_cast<size_t>(b) * len, first[i] != 0};
-        first[i] = 0;
-        agofrt_stats st;
-        memset(&st, 0, sizeof(st));
-        rc = block_impl(p, primo0 + static_cast<size_t>(b) * stride, ntimesteps, leff, skip, every, options | AGOFRT_OPT_ON_DEVICE,
-                        nullptr, nullptr, &st, &tg);
-        if (rc == kNotBatchable)
-            return fail(AGOFRT_ERR_ARG, "block %u has no regular job list (single-pass minimum image not proven for its whole "
-                                        "frame range): run the blocks one by one with agofrt_block", b);
-        if (rc != AGOFRT_OK) return rc;
-        sum.pair_evals += st.pair_evals;
-        sum.jobs += st.jobs;
-        sum.jobs_fast += st.jobs_fast;
-        sum.launches += st.launches;
-        sum.kernel_modes |= st.kernel_modes;
+    // contiguous runs of blocks per device (agofrt_shard_range over the blocks): one exchange per device afterwards
+    for (int i = 0; i < nloc; ++i) {
+        uint64_t b0 = 0, b1 = 0;
+        agofrt_shard_range(nblocks, first_rank + i, world, &b0, &b1);
+        for (uint64_t b = b0; b < b1; ++b) {
+            BlockTarget tg{i, p->dev[i].batch + static_cast<size_t>(b) * len, b == b0};
+            agofrt_stats st;
+            memset(&st, 0, sizeof(st));
+            rc = block_impl(p, primo0 + static_cast<size_t>(b) * stride, ntimesteps, leff, skip, every, options | AGOFRT_OPT_ON_DEVICE,
+                            nullptr, nullptr, &st, &tg);
+            if (rc == kNotBatchable)
+                return fail(AGOFRT_ERR_ARG, "block %llu has no regular job list (single-pass minimum image not proven for its whole "
+                                            "frame range): run the blocks one by one with agofrt_block", static_cast<unsigned long long>(b));
+            if (rc != AGOFRT_OK) return rc;
+            sum.pair_evals += st.pair_evals;
+            sum.jobs += st.jobs;
+            sum.jobs_fast += st.jobs_fast;
+            sum.launches += st.launches;
+            sum.kernel_modes |= st.kernel_modes;
+        }
     }
     for (int i = 0; i < nloc; ++i) {
         CU(cudaSetDevice(ctx->devs[i].id));
         CU(cudaEventRecord(ctx->devs[i].ev_k1, ctx->devs[i].stream));
     }
     ms_enqueue = since0() - ms_alloc;
-    // every device receives every block
+    // every device receives every block: the run of device r travels in one piece
     if (world > 1) {
         NcclApi &api = nccl_api();
         NC(api.GroupStart());
-        for (unsigned b = 0; b < nblocks; ++b)
-            for (int i = 0; i < nloc; ++i) {
-                unsigned long long *q = p->dev[i].batch + static_cast<size_t>(b) * len;
-                NC(api.Broadcast(q, q, len, ncclUint64, static_cast<int>(b % static_cast<unsigned>(world)), ctx->devs[i].comm,
-                                 ctx->devs[i].stream));
+        if (nblocks % static_cast<unsigned>(world) == 0) {
+            const size_t per = static_cast<size_t>(nblocks / static_cast<unsigned>(world)) * len;
+            for (int i = 0; i < nloc; ++i)
+                NC(api.AllGather(p->dev[i].batch + static_cast<size_t>(first_rank + i) * per, p->dev[i].batch, per, ncclUint64,
+                                 ctx->devs[i].comm, ctx->devs[i].stream));
+        } else {
+            for (int r = 0; r < world; ++r) {
+                uint64_t b0 = 0, b1 = 0;
+                agofrt_shard_range(nblocks, r, world, &b0, &b1);
+                if (b1 <= b0) continue;
+                for (int i = 0; i < nloc; ++i) {
+                    unsigned long long *q = p->dev[i].batch + static_cast<size_t>(b0) * len;
+                    NC(api.Broadcast(q, q, static_cast<size_t>(b1 - b0) * len, ncclUint64, r, ctx->devs[i].comm, ctx->devs[i].stream));
+                }
             }
+        }
         NC(api.GroupEnd());
     }
     double kernel_ms = 0, total_ms = 0;

@@ -230,7 +230,7 @@ AGOFRT_API int agofrt_block(agofrt_plan *plan, size_t primo, unsigned ntimesteps
 
 /* Many small blocks at once (BlockAverageG on systems of a few dozen atoms, where one block is a millisecond of kernel
  * and sharding its work units over several GPUs buys nothing): block b = reset(ntimesteps); calculate(primo0 + b*stride),
- * WHOLE blocks dealt to the devices (block b to device b mod world -- the round-robin of blocks over MPI ranks of
+ * WHOLE blocks dealt to the devices (a contiguous run of blocks per device -- the reference deals blocks to MPI ranks,
  * lib/include/blockaverage.h:146-186), no host synchronisation between blocks, then every device receives every block
  * (NCCL broadcasts).  The window must hold the frames of all the blocks; every block must have a regular job list (the
  * single-pass minimum image proven for its frame range, or AGOFRT_OPT_FORCE_GENERAL), else AGOFRT_ERR_ARG: run them one by
