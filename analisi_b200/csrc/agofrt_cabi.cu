@@ -134,6 +134,7 @@ struct Dev {
     int id = 0;
     int sm_count = 0;
     size_t smem_optin = 0;
+    size_t smem_per_sm = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr, ev_k0 = nullptr, ev_k1 = nullptr;
     ncclComm_t comm = nullptr;
@@ -155,8 +156,43 @@ struct Dev {
         size_t bytes = 0;
     };
     Spare *spare = nullptr;   // [kSpares], guarded by hstage_mutex
+    // ... and the small ones of a plan (thresholds, histogram, counters): a cudaFree right after a long kernel was
+    // measured at up to 1.2 s (r2x), so objects that are created and destroyed per analysis recycle their buffers
+    std::vector<Spare> *pool = nullptr;   // guarded by hstage_mutex
 };
 constexpr int kSpares = 4;
+constexpr size_t kPoolEntries = 64, kPoolMaxBytes = 32u << 20;
+
+// device memory for the short-lived small buffers: recycled by size class (multiples of 256 bytes)
+static cudaError_t pool_malloc(Dev &dv, void **ptr, size_t bytes) {
+    const size_t want = (std::max<size_t>(bytes, 1) + 255) / 256 * 256;
+    {
+        std::lock_guard<std::mutex> lock(*dv.hstage_mutex);
+        for (size_t k = 0; k < dv.pool->size(); ++k)
+            if ((*dv.pool)[k].bytes == want) {
+                *ptr = (*dv.pool)[k].ptr;
+                dv.pool->erase(dv.pool->begin() + k);
+                return cudaSuccess;
+            }
+    }
+    return cudaMalloc(ptr, want);
+}
+template <class T>
+static cudaError_t pool_malloc(Dev &dv, T **ptr, size_t bytes) {
+    return pool_malloc(dv, reinterpret_cast<void **>(ptr), bytes);
+}
+static void pool_free(Dev &dv, void *ptr, size_t bytes) {
+    if (!ptr) return;
+    const size_t have = (std::max<size_t>(bytes, 1) + 255) / 256 * 256;
+    if (have <= kPoolMaxBytes) {
+        std::lock_guard<std::mutex> lock(*dv.hstage_mutex);
+        if (dv.pool->size() < kPoolEntries) {
+            dv.pool->push_back(Dev::Spare{ptr, have});
+            return;
+        }
+    }
+    cudaFree(ptr);
+}
 
 static void *spare_take(Dev &dv, size_t bytes) {
     std::lock_guard<std::mutex> lock(*dv.hstage_mutex);
@@ -203,7 +239,36 @@ struct agofrt_ctx {
     int world = 0;       // 0: not sharded beyond the local devices
     bool comm_ready = false;
     bool shard_only = false;
+    // page-locked read-back buffers of destroyed plans, recycled by size class like Dev::pool
+    std::vector<Dev::Spare> host_pool;
+    std::mutex host_pool_mutex;
 };
+
+static cudaError_t host_pool_alloc(agofrt_ctx *ctx, void **ptr, size_t bytes) {
+    const size_t want = (std::max<size_t>(bytes, 1) + 255) / 256 * 256;
+    {
+        std::lock_guard<std::mutex> lock(ctx->host_pool_mutex);
+        for (size_t k = 0; k < ctx->host_pool.size(); ++k)
+            if (ctx->host_pool[k].bytes == want) {
+                *ptr = ctx->host_pool[k].ptr;
+                ctx->host_pool.erase(ctx->host_pool.begin() + k);
+                return cudaSuccess;
+            }
+    }
+    return cudaHostAlloc(ptr, want, cudaHostAllocPortable);
+}
+static void host_pool_free(agofrt_ctx *ctx, void *ptr, size_t bytes) {
+    if (!ptr) return;
+    const size_t have = (std::max<size_t>(bytes, 1) + 255) / 256 * 256;
+    if (have <= kPoolMaxBytes) {
+        std::lock_guard<std::mutex> lock(ctx->host_pool_mutex);
+        if (ctx->host_pool.size() < kPoolEntries) {
+            ctx->host_pool.push_back(Dev::Spare{ptr, have});
+            return;
+        }
+    }
+    cudaFreeHost(ptr);
+}
 
 struct TrajDev {
     double *pos = nullptr;       // [max_frames][3][npad]
@@ -264,8 +329,6 @@ struct PlanDev {
     size_t ghist_len = 0;
     Job *jobs = nullptr;
     size_t jobs_cap = 0;
-    SmallUnit *units = nullptr;           // work units of the small-system kernel
-    size_t units_cap = 0;
     unsigned int *counter = nullptr;      // [1]
     unsigned long long *edges = nullptr;  // [1]
     unsigned long long *batch = nullptr;  // agofrt_blocks: [nblocks][len] counts of whole blocks
@@ -396,6 +459,7 @@ extern "C" int agofrt_ctx_create(agofrt_ctx **out, const int *devices, int ndev)
                         prop.minor);
         d.sm_count = prop.multiProcessorCount;
         d.smem_optin = prop.sharedMemPerBlockOptin;
+        d.smem_per_sm = prop.sharedMemPerMultiprocessor;
         CU(cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking));
         CU(cudaEventCreate(&d.ev_begin));
         CU(cudaEventCreate(&d.ev_end));
@@ -406,6 +470,7 @@ extern "C" int agofrt_ctx_create(agofrt_ctx **out, const int *devices, int ndev)
         CU(cudaEventCreateWithFlags(&d.hstage_free[1], cudaEventDisableTiming));
         d.hstage_mutex = new std::mutex();
         d.spare = new Dev::Spare[kSpares];
+        d.pool = new std::vector<Dev::Spare>();
         ctx->devs.push_back(d);
     }
     *out = ctx.release();
@@ -428,6 +493,9 @@ extern "C" int agofrt_ctx_destroy(agofrt_ctx *ctx) try {
         if (d.spare)
             for (int k = 0; k < kSpares; ++k) cudaFree(d.spare[k].ptr);
         delete[] d.spare;
+        if (d.pool)
+            for (const Dev::Spare &sp : *d.pool) cudaFree(sp.ptr);
+        delete d.pool;
         delete d.hstage_mutex;
         if (d.stream) cudaStreamDestroy(d.stream);
         if (d.ev_begin) cudaEventDestroy(d.ev_begin);
@@ -435,6 +503,7 @@ extern "C" int agofrt_ctx_destroy(agofrt_ctx *ctx) try {
         if (d.ev_k0) cudaEventDestroy(d.ev_k0);
         if (d.ev_k1) cudaEventDestroy(d.ev_k1);
     }
+    for (const Dev::Spare &sp : ctx->host_pool) cudaFreeHost(sp.ptr);
     delete ctx;
     return AGOFRT_OK;
 } catch (...) {
@@ -560,16 +629,18 @@ static void free_traj_dev(agofrt_traj *t) {
     for (size_t i = 0; i < t->dev.size(); ++i) {
         cudaSetDevice(t->ctx->devs[i].id);
         TrajDev &d = t->dev[i];
-        spare_give(t->ctx->devs[i], d.pos, d.pos_bytes);
-        cudaFree(d.box6);
-        cudaFree(d.bounds);
-        spare_give(t->ctx->devs[i], d.stage, d.stage_bytes);
-        cudaFree(d.box_stage);
-        cudaFree(d.perm);
-        cudaFree(d.type_pad);
-        cudaFree(d.type_start);
-        cudaFree(d.flags);
-        cudaFree(d.probe);
+        Dev &dv = t->ctx->devs[i];
+        const size_t npad1 = std::max(t->npad, 1);
+        spare_give(dv, d.pos, d.pos_bytes);
+        pool_free(dv, d.box6, t->max_frames * 6 * sizeof(double));
+        pool_free(dv, d.bounds, t->max_frames * 6 * sizeof(double));
+        spare_give(dv, d.stage, d.stage_bytes);
+        pool_free(dv, d.box_stage, t->max_frames * t->stride * sizeof(double));
+        pool_free(dv, d.perm, npad1 * sizeof(int));
+        pool_free(dv, d.type_pad, npad1 * sizeof(int));
+        pool_free(dv, d.type_start, (t->ntypes + 1) * sizeof(int));
+        pool_free(dv, d.flags, 8 * sizeof(unsigned int));
+        pool_free(dv, d.probe, 4 * sizeof(double));
         cudaFree(d.rot);
         cudaFree(d.nb_hist);
         cudaFree(d.nb_frames);
@@ -647,17 +718,17 @@ extern "C" int agofrt_traj_create(agofrt_traj **out, agofrt_ctx *ctx, size_t nat
                         max_frames * 3 * npad1 * sizeof(double), cudaGetErrorString(e));
         }
         d.pos_bytes = want_pos;
-        CU(cudaMalloc(&d.box6, max_frames * 6 * sizeof(double)));
-        CU(cudaMalloc(&d.bounds, max_frames * 6 * sizeof(double)));
+        CU(pool_malloc(ctx->devs[i], &d.box6, max_frames * 6 * sizeof(double)));
+        CU(pool_malloc(ctx->devs[i], &d.bounds, max_frames * 6 * sizeof(double)));
         d.stage = static_cast<double *>(spare_take(ctx->devs[i], want_stage));
         if (!d.stage) CU(cudaMalloc(&d.stage, want_stage));
         d.stage_bytes = want_stage;
-        CU(cudaMalloc(&d.box_stage, max_frames * box_stride * sizeof(double)));
-        CU(cudaMalloc(&d.perm, npad1 * sizeof(int)));
-        CU(cudaMalloc(&d.type_pad, npad1 * sizeof(int)));
-        CU(cudaMalloc(&d.type_start, (ntypes + 1) * sizeof(int)));
-        CU(cudaMalloc(&d.flags, 8 * sizeof(unsigned int)));
-        CU(cudaMalloc(&d.probe, 4 * sizeof(double)));
+        CU(pool_malloc(ctx->devs[i], &d.box_stage, max_frames * box_stride * sizeof(double)));
+        CU(pool_malloc(ctx->devs[i], &d.perm, npad1 * sizeof(int)));
+        CU(pool_malloc(ctx->devs[i], &d.type_pad, npad1 * sizeof(int)));
+        CU(pool_malloc(ctx->devs[i], &d.type_start, (ntypes + 1) * sizeof(int)));
+        CU(pool_malloc(ctx->devs[i], &d.flags, 8 * sizeof(unsigned int)));
+        CU(pool_malloc(ctx->devs[i], &d.probe, 4 * sizeof(double)));
         CU(cudaStreamCreateWithFlags(&d.up, cudaStreamNonBlocking));
         CU(cudaMemset(d.flags, 0, 8 * sizeof(unsigned int)));
         if (t->npad > 0) CU(cudaMemcpy(d.type_pad, t->type_pad.data(), t->npad * sizeof(int), cudaMemcpyHostToDevice));
@@ -671,8 +742,13 @@ extern "C" int agofrt_traj_create(agofrt_traj **out, agofrt_ctx *ctx, size_t nat
 
 extern "C" int agofrt_traj_destroy(agofrt_traj *t) try {
     if (!t) return AGOFRT_OK;
+    const bool debug = getenv("AGOFRT_DEBUG") != nullptr;
+    const auto t0 = std::chrono::steady_clock::now();
     free_traj_dev(t);
     delete t;
+    if (debug)
+        fprintf(stderr, "[agofrt] window released in %.1f ms\n",
+                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
     return AGOFRT_OK;
 } catch (...) {
     return on_exception();
@@ -1442,9 +1518,9 @@ static int validate_safe_zone(agofrt_plan *p) {
     double *dprobe = nullptr;
     int *dexp = nullptr;
     unsigned int *dbad = nullptr;
-    CU(cudaMalloc(&dprobe, probes.size() * sizeof(double)));
-    CU(cudaMalloc(&dexp, probes.size() * sizeof(int)));
-    CU(cudaMalloc(&dbad, sizeof(unsigned int)));
+    CU(pool_malloc(dv, &dprobe, probes.size() * sizeof(double)));
+    CU(pool_malloc(dv, &dexp, probes.size() * sizeof(int)));
+    CU(pool_malloc(dv, &dbad, sizeof(unsigned int)));
     unsigned int bad = 0;
     auto body = [&]() -> int {
         CU(cudaMemcpyAsync(dprobe, probes.data(), probes.size() * sizeof(double), cudaMemcpyHostToDevice, dv.stream));
@@ -1477,9 +1553,9 @@ static int validate_safe_zone(agofrt_plan *p) {
         if (bad2 != 0) p->safe2_ok = false;
         if (getenv("AGOFRT_DEBUG")) fprintf(stderr, "[agofrt] plan rmin %g dr %g nbin %u: two-floor validation, %u bad probes of %zu\n", p->rmin, p->dr, nbin, bad2, probes.size());
     }
-    cudaFree(dprobe);
-    cudaFree(dexp);
-    cudaFree(dbad);
+    pool_free(dv, dprobe, probes.size() * sizeof(double));
+    pool_free(dv, dexp, probes.size() * sizeof(int));
+    pool_free(dv, dbad, sizeof(unsigned int));
     return rc;
 }
 
@@ -1580,10 +1656,11 @@ extern "C" int agofrt_plan_create(agofrt_plan **out, agofrt_traj *traj, double r
     for (size_t i = 0; i < p->dev.size(); ++i) {
         CU(cudaSetDevice(traj->ctx->devs[i].id));
         PlanDev &d = p->dev[i];
-        CU(cudaMalloc(&d.thr, (nbin + 1) * sizeof(double)));
-        CU(cudaMalloc(&d.thr_full, (nbin + 1) * sizeof(double)));
-        CU(cudaMalloc(&d.counter, sizeof(unsigned int)));
-        CU(cudaMalloc(&d.edges, sizeof(unsigned long long)));
+        Dev &dv = traj->ctx->devs[i];
+        CU(pool_malloc(dv, &d.thr, (nbin + 1) * sizeof(double)));
+        CU(pool_malloc(dv, &d.thr_full, (nbin + 1) * sizeof(double)));
+        CU(pool_malloc(dv, &d.counter, sizeof(unsigned int)));
+        CU(pool_malloc(dv, &d.edges, sizeof(unsigned long long)));
         CU(cudaMemcpy(d.thr, p->thr.data(), (nbin + 1) * sizeof(double), cudaMemcpyHostToDevice));
         CU(cudaMemcpy(d.thr_full, p->thr_full.data(), (nbin + 1) * sizeof(double), cudaMemcpyHostToDevice));
     }
@@ -1591,10 +1668,8 @@ extern "C" int agofrt_plan_create(agofrt_plan **out, agofrt_traj *traj, double r
         const int rcv = validate_safe_zone(p.get());
         if (rcv != AGOFRT_OK) return rcv;
     }
-    CU(cudaHostAlloc(reinterpret_cast<void **>(&p->host_edges), sizeof(unsigned long long) * p->dev.size(),
-                     cudaHostAllocPortable));
-    CU(cudaHostAlloc(reinterpret_cast<void **>(&p->host_flags), sizeof(unsigned int) * p->dev.size(),
-                     cudaHostAllocPortable));
+    CU(host_pool_alloc(traj->ctx, reinterpret_cast<void **>(&p->host_edges), sizeof(unsigned long long) * p->dev.size()));
+    CU(host_pool_alloc(traj->ctx, reinterpret_cast<void **>(&p->host_flags), sizeof(unsigned int) * p->dev.size()));
     *out = p.release();
     return AGOFRT_OK;
 } catch (...) {
@@ -1614,22 +1689,38 @@ extern "C" int agofrt_plan_retarget(agofrt_plan *p, agofrt_traj *traj) try {
 
 extern "C" int agofrt_plan_destroy(agofrt_plan *p) try {
     if (!p) return AGOFRT_OK;
+    const bool debug = getenv("AGOFRT_DEBUG") != nullptr;
+    if (debug) {   // is anything still running on the devices?  (how long a device-wide wait takes right now)
+        const auto s0 = std::chrono::steady_clock::now();
+        for (size_t i = 0; i < p->dev.size(); ++i) {
+            cudaSetDevice(p->ctx->devs[i].id);
+            cudaDeviceSynchronize();
+        }
+        fprintf(stderr, "[agofrt] device-wide wait before the plan is released: %.1f ms\n",
+                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - s0).count());
+    }
+    const auto t0 = std::chrono::steady_clock::now();
     for (size_t i = 0; i < p->dev.size(); ++i) {
         cudaSetDevice(p->ctx->devs[i].id);
         PlanDev &d = p->dev[i];
-        cudaFree(d.thr);
-        cudaFree(d.thr_full);
-        cudaFree(d.ghist);
-        cudaFree(d.jobs);
-        cudaFree(d.units);
-        cudaFree(d.counter);
-        cudaFree(d.edges);
-        spare_give(p->ctx->devs[i], d.batch, d.batch_len * sizeof(unsigned long long));
+        Dev &dv = p->ctx->devs[i];
+        pool_free(dv, d.thr, (p->nbin + 1) * sizeof(double));
+        pool_free(dv, d.thr_full, (p->nbin + 1) * sizeof(double));
+        pool_free(dv, d.ghist, d.ghist_len * sizeof(unsigned long long));
+        pool_free(dv, d.jobs, d.jobs_cap * sizeof(Job));
+        pool_free(dv, d.counter, sizeof(unsigned int));
+        pool_free(dv, d.edges, sizeof(unsigned long long));
+        spare_give(dv, d.batch, d.batch_len * sizeof(unsigned long long));
     }
-    if (p->host_counts) cudaFreeHost(p->host_counts);
-    if (p->host_edges) cudaFreeHost(p->host_edges);
-    if (p->host_flags) cudaFreeHost(p->host_flags);
+    const auto t1 = std::chrono::steady_clock::now();
+    host_pool_free(p->ctx, p->host_counts, p->host_counts_len * sizeof(unsigned long long));
+    host_pool_free(p->ctx, p->host_edges, sizeof(unsigned long long) * p->dev.size());
+    host_pool_free(p->ctx, p->host_flags, sizeof(unsigned int) * p->dev.size());
     delete p;
+    if (debug)
+        fprintf(stderr, "[agofrt] plan released in %.1f ms (device buffers %.1f)\n",
+                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(),
+                std::chrono::duration<double, std::milli>(t1 - t0).count());
     return AGOFRT_OK;
 } catch (...) {
     return on_exception();
@@ -1809,54 +1900,60 @@ static int block_impl(agofrt_plan *p, size_t primo, unsigned ntimesteps, unsigne
     if (njobs * per_job >= 0xF0000000ull) return fail(AGOFRT_ERR_ARG, "too many work units in one block (%llu)",
                                                       static_cast<unsigned long long>(njobs * per_job));
 
-    // ---- small systems: runs of jobs of one lag, dealt to the warps of a CTA (pair_small_kernel) ----
-    // Default up to kSmallDefault slots (at most four warps per job: two jobs or more in flight per CTA), where it is
-    // 1.7x - 2.3x the tile kernel; with one job in flight per CTA (five to eight warps) the two tie
-    // (profiles/r1p_small_rate.jsonl), so that range is opt-in.
+    // ---- small systems: a contiguous range of jobs per CTA, batches of jobs per warp (pair_small_kernel) ----
+    // Default up to kSmallDefault slots; above (up to kSmallMax) opt-in.
     const bool small = t->npad > 0 && !(options & AGOFRT_OPT_NO_SMALL) &&
                        (t->npad <= kSmallDefault || ((options & AGOFRT_OPT_SMALL) && t->npad <= kSmallMax));
-    const int nsub = small ? (t->npad + 32 * kIPT - 1) / (32 * kIPT) : 1;   // warps per job
-    std::vector<SmallUnit> units_fast, units_gen;
-    uint64_t nu_fast = 0, nu_gen = 0, small_each = 0;
-    if (small && !nothing) {
-        // a unit should dwarf the merge of the CTA's histogram rows that ends it (rowlen words scanned,
-        // up to as many global atomics), keep every warp busy, and there should be several units per CTA
-        const uint64_t pairs_per_job = static_cast<uint64_t>(t->npad) * t->npad;
-        const uint64_t by_merge = (128ull * rowlen + pairs_per_job - 1) / pairs_per_job;
-        const uint64_t by_ctas = (njobs + 6ull * total_ctas - 1) / (6ull * total_ctas);
-        const uint64_t wave = static_cast<uint64_t>(kThreads / 32 / nsub);   // jobs a CTA works on at a time
-        uint64_t chunk = std::max<uint64_t>(std::max(by_merge, by_ctas), wave);
-        chunk = std::min<uint64_t>((chunk + wave - 1) / wave * wave, 65536);   // a unit's counts stay far below 2^32
-        if (implicit) {
-            // equal shares of the origins of one lag, whole rounds of the CTA's warp groups; unit u = (lag u / units_per_lag, share)
-            const uint64_t nch = (norig + chunk - 1) / chunk;
-            small_each = ((norig + nch - 1) / nch + wave - 1) / wave * wave;
-            const uint64_t upl = (norig + small_each - 1) / small_each;
-            (all_fast ? nu_fast : nu_gen) = upl * ((leff + every - 1) / every);
-        } else {
-            for (int pass = 0; pass < 2; ++pass) {
-                const std::vector<Job> &list = pass == 0 ? jobs_fast : jobs_gen;
-                std::vector<SmallUnit> &units = pass == 0 ? units_fast : units_gen;
-                size_t a = 0;
-                while (a < list.size()) {
-                    size_t b = a;
-                    while (b < list.size() && list[b].tout == list[a].tout) ++b;   // jobs are in lag-major order
-                    const uint64_t run = b - a, nch = (run + chunk - 1) / chunk;
-                    const uint64_t each = ((run + nch - 1) / nch + wave - 1) / wave * wave;   // equal shares, whole rounds
-                    for (size_t c0 = a; c0 < b; c0 += each)
-                        units.push_back(SmallUnit{static_cast<int>(c0), static_cast<int>(std::min<size_t>(each, b - c0)),
-                                                  list[a].tout});
-                    a = b;
-                }
-            }
-            nu_fast = units_fast.size();
-            nu_gen = units_gen.size();
-        }
-    }
-
+    // A warp of pair_small_kernel works on `small_jb` jobs at a time, their i slots packed over its lanes (64 per
+    // round): the batch size that wastes the fewest lanes of the last round, among those whose j frames fit the
+    // warp's slice of the stage area with two CTAs per SM, and that leave a batch or more to every warp.
+    int small_jb = 1, small_js = std::max(t->npad, 2), small_nb = 1;
     bool aggregate = p->nbin * static_cast<unsigned>(nt * (nt + 1) / 2) < 64;  // few counters: collisions are the rule
     if (options & AGOFRT_OPT_AGGREGATE) aggregate = true;
     if (options & AGOFRT_OPT_NO_AGGREGATE) aggregate = false;
+    if (small) {
+        // slots between the j frames of a batch: the threads of a warp read the frames of up to three consecutive jobs
+        // with 16-byte loads -- keep those on different banks (4-byte words: 2 * js mod 32 away from 0)
+        const int w = (2 * small_js) % 32;
+        if (w < 4 || w > 28) small_js += 2;
+        const size_t per_cta = (ctx->devs[0].smem_per_sm - 2048) / kMinBlocks;   // 1 KiB per CTA belongs to the system
+        const size_t per_job = static_cast<size_t>(kThreads / 32) * 3 * small_js * sizeof(double);
+        uint64_t total_warps = 0;
+        for (const Dev &d : ctx->devs) total_warps += static_cast<uint64_t>(kMinBlocks) * d.sm_count * (kThreads / 32);
+        const int by_jobs = static_cast<int>(std::min<uint64_t>(8, std::max<uint64_t>(1, njobs / std::max<uint64_t>(total_warps, 1))));
+        // the best batch (fewest empty lanes in its last round; ties: the larger) that fits beside `nb` histograms
+        auto best_batch = [&](int nb, int *jb_out) {
+            const size_t fixed = pair_small_kernel_smem_bytes(nt, static_cast<int>(p->nbin), static_cast<int>(p->nbin), p->glo,
+                                                              want_edges, 0, 0, nb);
+            const int fit = per_cta > fixed ? static_cast<int>((per_cta - fixed) / per_job) : 0;
+            const int jb_max = std::max(1, std::min(std::min(8, fit), by_jobs));
+            double best = -1;
+            for (int jb = 1; jb <= jb_max; ++jb) {
+                const int slots = jb * t->npad, rounds = (slots + 32 * kIPT - 1) / (32 * kIPT);
+                const double eff = static_cast<double>(slots) / (rounds * 32 * kIPT);
+                if (eff >= best - 1e-9) {
+                    best = std::max(best, eff);
+                    *jb_out = jb;
+                }
+            }
+            return fit >= 1 ? best : 0.0;
+        };
+        const double eff1 = best_batch(1, &small_jb);
+        // histograms a CTA keeps at a time: the lags its share of the jobs touches (one merge at the end instead of one
+        // per lag), as long as they fit without costing the batch its shape.  The warp-aggregated binning keys on the
+        // bin alone: one histogram.
+        const uint64_t jobs_per_cta = std::max<uint64_t>(1, njobs / std::max(1, total_ctas));
+        const int want_nb = aggregate ? 1 : static_cast<int>(std::min<uint64_t>(8, jobs_per_cta / std::max(1u, norig) + 2));
+        for (int nb = want_nb; nb >= 2; --nb) {
+            int jb = 1;
+            if (best_batch(nb, &jb) >= eff1 - 1e-9 && jb >= small_jb) {
+                small_nb = nb;
+                small_jb = jb;
+                break;
+            }
+        }
+    }
+
     const bool tri = t->stride == 9;
     // safe-zone binning needs the bin coordinate of every reachable distance to stay below 2^21
     bool use_safe = p->safe_ok && !(options & AGOFRT_OPT_NO_SAFE) && !t->has_nan;
@@ -1889,6 +1986,12 @@ static int block_impl(agofrt_plan *p, size_t primo, unsigned ntimesteps, unsigne
         if (options & AGOFRT_OPT_SPARSE) dense = false;
     }
     const size_t smem = pair_kernel_smem_bytes(nt, static_cast<int>(p->nbin), static_cast<int>(p->nbin), p->glo, want_edges);
+    const size_t smem_small = small ? pair_small_kernel_smem_bytes(nt, static_cast<int>(p->nbin), static_cast<int>(p->nbin), p->glo,
+                                                                   want_edges, small_jb, small_js, small_nb)
+                                    : 0;
+    if (smem_small > ctx->devs[0].smem_optin)
+        return fail(AGOFRT_ERR_ARG, "the small-system kernel needs %zu bytes of shared memory (limit %zu)", smem_small,
+                    ctx->devs[0].smem_optin);
     // dense windows: the two-floor form of the safe-zone binning (MODE_SAFE2) where the plan allows it
     const int nhi = static_cast<int>(p->nbin);
     // (opt-in: measured on C2 it is 6 % slower than the clamped form although it issues two instructions per pair
@@ -1897,11 +2000,10 @@ static int block_impl(agofrt_plan *p, size_t primo, unsigned ntimesteps, unsigne
 
     // ---- pinned read-back buffer ----
     if (!tg && len > p->host_counts_len) {
-        if (p->host_counts) cudaFreeHost(p->host_counts);
+        host_pool_free(ctx, p->host_counts, p->host_counts_len * sizeof(unsigned long long));
         p->host_counts = nullptr;
         p->host_counts_len = 0;
-        CU(cudaHostAlloc(reinterpret_cast<void **>(&p->host_counts), len * sizeof(unsigned long long),
-                         cudaHostAllocPortable));
+        CU(host_pool_alloc(ctx, reinterpret_cast<void **>(&p->host_counts), len * sizeof(unsigned long long)));
         p->host_counts_len = len;
     }
 
@@ -1916,36 +2018,22 @@ static int block_impl(agofrt_plan *p, size_t primo, unsigned ntimesteps, unsigne
         CU(cudaSetDevice(dv.id));
         unsigned long long *const ghist = tg ? tg->ghist : nullptr;
         if (!tg && len > pd.ghist_len) {
-            cudaFree(pd.ghist);
+            pool_free(dv, pd.ghist, pd.ghist_len * sizeof(unsigned long long));
             pd.ghist = nullptr;
             pd.ghist_len = 0;
-            CU(cudaMalloc(&pd.ghist, len * sizeof(unsigned long long)));
+            CU(pool_malloc(dv, &pd.ghist, len * sizeof(unsigned long long)));
             pd.ghist_len = len;
         }
         const size_t njall = jobs_fast.size() + jobs_gen.size();   // (0 with implicit jobs)
         if (njall > pd.jobs_cap) {
-            cudaFree(pd.jobs);
+            pool_free(dv, pd.jobs, pd.jobs_cap * sizeof(Job));
             pd.jobs = nullptr;
             pd.jobs_cap = 0;
-            CU(cudaMalloc(&pd.jobs, njall * sizeof(Job)));
+            CU(pool_malloc(dv, &pd.jobs, njall * sizeof(Job)));
             pd.jobs_cap = njall;
-        }
-        const size_t nuall = units_fast.size() + units_gen.size();
-        if (nuall > pd.units_cap) {
-            cudaFree(pd.units);
-            pd.units = nullptr;
-            pd.units_cap = 0;
-            CU(cudaMalloc(&pd.units, nuall * sizeof(SmallUnit)));
-            pd.units_cap = nuall;
         }
         if (!tg) CU(cudaEventRecord(dv.ev_begin, dv.stream));
         if (len > 0) CU(cudaMemsetAsync(tg ? ghist : pd.ghist, 0, len * sizeof(unsigned long long), dv.stream));
-        if (!units_fast.empty())
-            CU(cudaMemcpyAsync(pd.units, units_fast.data(), units_fast.size() * sizeof(SmallUnit), cudaMemcpyHostToDevice,
-                               dv.stream));
-        if (!units_gen.empty())
-            CU(cudaMemcpyAsync(pd.units + units_fast.size(), units_gen.data(), units_gen.size() * sizeof(SmallUnit),
-                               cudaMemcpyHostToDevice, dv.stream));
         CU(cudaMemsetAsync(pd.edges, 0, sizeof(unsigned long long), dv.stream));
         if (!tg || tg->first) CU(cudaMemsetAsync(td.flags + 1, 0, sizeof(unsigned int), dv.stream));
         if (!jobs_fast.empty())
@@ -1959,13 +2047,11 @@ static int block_impl(agofrt_plan *p, size_t primo, unsigned ntimesteps, unsigne
             for (int pass = 0; pass < 2; ++pass) {
                 const uint64_t nlist = pass == 0 ? n_fast : n_gen;
                 if (nlist == 0) continue;
-                const std::vector<SmallUnit> &ulist = pass == 0 ? units_fast : units_gen;
-                const uint64_t units = small ? (pass == 0 ? nu_fast : nu_gen) : nlist * per_job;
+                const uint64_t units = small ? nlist : nlist * per_job;   // the small-system kernel shares out jobs
                 uint64_t ub = 0, ue = 0;
                 agofrt_shard_range(units, g, world, &ub, &ue);
                 if (ue <= ub) continue;
                 PairParams pp;
-                pp.units = small ? pd.units + (pass == 0 ? 0 : units_fast.size()) : nullptr;
                 pp.pos = td.pos;
                 pp.box = td.box6;
                 pp.type_pad = td.type_pad;
@@ -1976,7 +2062,6 @@ static int block_impl(agofrt_plan *p, size_t primo, unsigned ntimesteps, unsigne
                 pp.imp_norig = static_cast<int>(norig);
                 pp.imp_skip = static_cast<int>(skip);
                 pp.imp_every = static_cast<int>(every);
-                pp.imp_each = static_cast<int>(small_each);
                 pp.ghist = tg ? ghist : pd.ghist;
                 pp.edges = pd.edges;
                 pp.counter = pd.counter;
@@ -1990,9 +2075,22 @@ static int block_impl(agofrt_plan *p, size_t primo, unsigned ntimesteps, unsigne
                 pp.npad = t->npad;
                 pp.ntypes = nt;
                 pp.nbin = static_cast<int>(p->nbin);
-                pp.n_itiles = small ? nsub : n_itiles;
-                pp.n_jchunks = n_jchunks;
+                pp.n_itiles = small ? small_jb : n_itiles;
+                pp.n_jchunks = small ? small_js : n_jchunks;
                 pp.jchunk = jchunk;
+                pp.small_nb = small_nb;
+                pp.small_w16 = 16;
+                if (small) {
+                    // the jobs of lag 0 lead the list (lag-major order)
+                    uint64_t lag0 = 0;
+                    if (implicit) {
+                        lag0 = norig;
+                    } else {
+                        const std::vector<Job> &list = pass == 0 ? jobs_fast : jobs_gen;
+                        while (lag0 < list.size() && list[lag0].tout == 0) ++lag0;
+                    }
+                    pp.jchunk = static_cast<int>(lag0);
+                }
                 pp.inv_dr = p->inv_dr;
                 pp.c0 = p->c0;
                 pp.hlo = p->hlo;
@@ -2015,6 +2113,9 @@ static int block_impl(agofrt_plan *p, size_t primo, unsigned ntimesteps, unsigne
                     mode = kModeAgg;
                 else if (pass == 0 && use_safe)
                     mode = use_safe2 ? kModeSafe2 : (dense ? kModeSafeDense : kModeSafe);
+                // lag 0 through the safe-zone binning: the self pairs are left out of the main pass, three instructions per
+                // pair (pair_small_kernel)
+                if (mode == kModeSafe || mode == kModeSafeDense) pp.small_w16 = 18;
                 const bool ubox = same_box && pass == 0 && !(options & AGOFRT_OPT_NO_UBOX) &&
                                   (mode == kModeThr || mode == kModeSafe || mode == kModeSafeDense || mode == kModeSafe2);
                 if (ubox) {
@@ -2026,21 +2127,16 @@ static int block_impl(agofrt_plan *p, size_t primo, unsigned ntimesteps, unsigne
                     for (int k = 0; k < 12; ++k) pp.ubox[k] = 0.0;
                 }
                 const int variant = (tri ? 1 : 0) | (pass == 0 ? 2 : 0) | (mode << 2) | (ubox ? 32 : 0) | (small ? 64 : 0);
-                const int grid = static_cast<int>(std::min<uint64_t>(ue - ub, static_cast<uint64_t>(kMinBlocks) * dv.sm_count));
+                // small systems: a CTA per batch round of its eight warps, at most
+                const uint64_t want_ctas = small ? (ue - ub + (kThreads / 32) * small_jb - 1) / ((kThreads / 32) * small_jb) : ue - ub;
+                const int grid = static_cast<int>(std::min<uint64_t>(want_ctas, static_cast<uint64_t>(kMinBlocks) * dv.sm_count));
                 CU(cudaMemsetAsync(pd.counter, 0, sizeof(unsigned int), dv.stream));
-                CU(launch_pair_kernel(variant, grid, smem, dv.stream, pp));
+                CU(launch_pair_kernel(variant, grid, small ? smem_small : smem, dv.stream, pp));
                 ++launches;
                 modes_used |= 1u << mode;
                 if (small) {
                     modes_used |= 1u << 8;
-                    uint64_t nj = 0;
-                    if (implicit) {
-                        const uint64_t upl = (norig + small_each - 1) / small_each;
-                        for (uint64_t u = ub; u < ue; ++u) nj += std::min<uint64_t>(small_each, norig - (u % upl) * small_each);
-                    } else {
-                        for (uint64_t u = ub; u < ue; ++u) nj += static_cast<uint64_t>(ulist[u].count);
-                    }
-                    my_pairs += nj * n2;
+                    my_pairs += (ue - ub) * n2;
                 } else {
                     // pair evaluations of this shard, counted on real atoms: units are equal-sized
                     my_pairs += static_cast<uint64_t>(static_cast<double>(ue - ub) / static_cast<double>(per_job) * n2 + 0.5);
@@ -2252,10 +2348,10 @@ extern "C" int agofrt_blocks(agofrt_plan *p, size_t primo0, size_t stride, unsig
         // what agofrt_block leaves behind: the last block in the plan's own histogram (agofrt_plan_last_counts, agofrt_blockavg_push)
         PlanDev &pd = p->dev[i];
         if (len > pd.ghist_len) {
-            cudaFree(pd.ghist);
+            pool_free(dv, pd.ghist, pd.ghist_len * sizeof(unsigned long long));
             pd.ghist = nullptr;
             pd.ghist_len = 0;
-            CU(cudaMalloc(&pd.ghist, len * sizeof(unsigned long long)));
+            CU(pool_malloc(dv, &pd.ghist, len * sizeof(unsigned long long)));
             pd.ghist_len = len;
         }
         CU(cudaMemcpyAsync(pd.ghist, pd.batch + static_cast<size_t>(nblocks - 1) * len, len * sizeof(unsigned long long),

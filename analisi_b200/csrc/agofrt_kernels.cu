@@ -417,11 +417,14 @@ __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a -
 // every histogram row: glo guard bins, nhi bins (the first nbin of them are merged; nhi = nbin today), one guard bin
 __host__ __device__ inline int row_stride(int nhi, int glo) { return glo + nhi + 1; }
 
-__host__ __device__ inline SmemLayout smem_layout(int ntypes, int nbin, int nhi, int glo, bool edges) {
+// stage_slots: doubles per coordinate row of the stage area -- kStages tiles of the tile kernel, or the warps' job
+// slices of pair_small_kernel (small_stage_slots); nhist: histograms kept at a time (pair_small_kernel: one per lag)
+__host__ __device__ inline SmemLayout smem_layout(int ntypes, int nbin, int nhi, int glo, bool edges,
+                                                   size_t stage_slots = static_cast<size_t>(kStages) * kTileJ, int nhist = 1) {
     SmemLayout L;
     size_t o = 0;
     L.stage = o;
-    o += static_cast<size_t>(kStages) * 3 * kTileJ * sizeof(double);
+    o += stage_slots * 3 * sizeof(double);
     L.thr2 = o;
     o += static_cast<size_t>(nbin + 3) * 2 * sizeof(double);
     L.thr_full = o;
@@ -429,7 +432,7 @@ __host__ __device__ inline SmemLayout smem_layout(int ntypes, int nbin, int nhi,
     L.bars = align_up(o, 8);
     o = L.bars + kStages * sizeof(uint64_t);
     L.hist = o;
-    o += static_cast<size_t>(ntypes) * (ntypes + 1) * row_stride(nhi, glo) * sizeof(unsigned int);
+    o += static_cast<size_t>(nhist) * ntypes * (ntypes + 1) * row_stride(nhi, glo) * sizeof(unsigned int);
     L.dump = o;
     o += 32 * sizeof(unsigned int);
     L.rowtab = o;
@@ -446,9 +449,18 @@ size_t pair_kernel_smem_bytes(int ntypes, int nbin, int nhi, int glo, bool edges
     return smem_layout(ntypes, nbin, nhi, glo, edges).total;
 }
 
+// pair_small_kernel: every warp of a CTA stages `jobs_per_batch` j frames of `job_stride` slots each
+__host__ __device__ inline size_t small_stage_slots(int jobs_per_batch, int job_stride) {
+    return static_cast<size_t>(kThreads / 32) * jobs_per_batch * job_stride;
+}
+size_t pair_small_kernel_smem_bytes(int ntypes, int nbin, int nhi, int glo, bool edges, int jobs_per_batch, int job_stride,
+                                    int nhist) {
+    return smem_layout(ntypes, nbin, nhi, glo, edges, small_stage_slots(jobs_per_batch, job_stride), nhist).total;
+}
+
 constexpr int kWarpsPerCta = kThreads / 32;
 
-// the (lag, origin) job / the small-system work unit with this index: read from the list, or derived (implicit jobs)
+// the (lag, origin) job with this index: read from the list, or derived (implicit jobs)
 __device__ __forceinline__ Job job_at(const PairParams &p, unsigned int k) {
     if (!p.imp) return p.jobs[k];
     const unsigned int lag = k / static_cast<unsigned int>(p.imp_norig), o = k - lag * static_cast<unsigned int>(p.imp_norig);
@@ -457,16 +469,6 @@ __device__ __forceinline__ Job job_at(const PairParams &p, unsigned int k) {
     j.tout = static_cast<int>(lag) * p.imp_every;
     j.fj = j.fi + j.tout;
     return j;
-}
-__device__ __forceinline__ SmallUnit unit_at(const PairParams &p, unsigned int u) {
-    if (!p.imp) return p.units[u];
-    const unsigned int upl = static_cast<unsigned int>((p.imp_norig + p.imp_each - 1) / p.imp_each);
-    const unsigned int lag = u / upl, share = u - lag * upl;
-    SmallUnit un;
-    un.begin = static_cast<int>(lag) * p.imp_norig + static_cast<int>(share) * p.imp_each;
-    un.count = min(p.imp_each, p.imp_norig - static_cast<int>(share) * p.imp_each);
-    un.lag = static_cast<int>(lag) * p.imp_every;
-    return un;
 }
 
 struct PairConst {
@@ -480,6 +482,7 @@ struct PairConst {
 // independent FP64 chains), then one cheap test for "some pair of the group may be in range", then
 // the binning of the group's pairs without per-pair branches.
 //   DIAG: the j atoms may include one of this thread's own i atoms (i == j goes to the "self" rows).
+//   ZSELF (pair_small_kernel, lag 0): i == j is skipped; the caller counts those pairs.
 // All kIPT x kJU squared distances of one group (straight-line, independent FP64 chains).
 //   jrow_bytes: bytes between the x, y and z rows of the staged j coordinates (a literal in pair_kernel)
 template <bool TRI, bool FAST>
@@ -715,7 +718,7 @@ __device__ __noinline__ void group_fix2(PairConst c, IAtoms ia, float inv_lo, fl
     }
 }
 
-template <bool TRI, bool FAST, int MODE, bool DIAG>
+template <bool TRI, bool FAST, int MODE, bool DIAG, bool ZSELF = false>
 __device__ __forceinline__ void process_group(const PairParams &p, const PairConst &c, const double (&xi)[kIPT],
                                               const double (&yi)[kIPT], const double (&zi)[kIPT],
                                               const int (&ii)[kIPT], const unsigned int (&row)[kIPT],
@@ -724,6 +727,16 @@ __device__ __forceinline__ void process_group(const PairParams &p, const PairCon
                                               unsigned long long &edges, bool &wrap_ok) {
     double d2[kIPT][kJU];
     group_distances<TRI, FAST>(c, xi, yi, zi, sx_addr, jrow_bytes, jrel, d2, wrap_ok);
+    if (ZSELF) {
+        // the pair of an atom with itself is left out here (NaN: out of range for every mode, never "near an edge")
+        // and counted by the caller
+#pragma unroll
+        for (int k = 0; k < kIPT; ++k) {
+#pragma unroll
+            for (int q = 0; q < kJU; ++q)
+                if (ii[k] == j + q) d2[k][q] = __longlong_as_double(0x7ff8000000000000ll);
+        }
+    }
     if (MODE == MODE_EDGES) {
 #pragma unroll
         for (int k = 0; k < kIPT; ++k) {
@@ -1082,25 +1095,60 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) pair_kernel(const PairPa
 //
 // pair_kernel gives a whole CTA (512 i slots) to one (lag, origin) job; with a few dozen atoms nine lanes in
 // ten hold no atom, and because consecutive tickets go to different CTAs nearly every job ends with a merge
-// of the CTA's histogram into the global row of its lag.  Here the work unit is a RUN OF JOBS OF ONE LAG
-// (SmallUnit, cut by the host) and the jobs of a unit are dealt to GROUPS OF W WARPS, W = ceil(npad / 64):
-// every warp of a group holds one sub-tile of 64 i slots of the group's job in registers, the group copies the
-// j frame into its own slice of the stage area (64*W slots per coordinate row, coalesced loads) and every warp
-// walks it with the same process_group as the large kernel -- same arithmetic, same binning modes, same
-// shared-memory histogram rows.  A CTA works on 8 / W jobs at a time; groups only meet their own warps (a named
-// barrier, or __syncwarp when W = 1) around the copy of a j frame, and the CTA meets once per unit, to merge
-// its rows into the global row of the unit's lag.
+// of the CTA's histogram into the global row of its lag.  Here
+//   * the jobs of the launch (lag-major) are cut into one contiguous range per CTA, of equal COST: all jobs cost the
+//     same except those of lag 0, where every atom meets itself at distance 0 -- which the safe-zone binning sees as
+//     "on a bin edge" (r = 0 is an edge of the extended grid whenever rmin / dr is an integer) and sends through its
+//     correction path (2.4x the time, measured on C1); a warp that holds such a job leaves the self pairs out of the
+//     main pass (ZSELF) and the remaining difference is a weight (small_w16 / 16).  No tickets, no tail;
+//   * a CTA keeps NB histograms in shared memory, one per lag, and walks its range NB lags at a time (C1: a CTA's
+//     483 jobs touch two lags of 756 jobs each -- one pass, one merge into the global rows at the end);
+//   * the jobs of a pass are split over the warps by cost, and a warp works on a BATCH of JB jobs at a time with
+//     the i slots of the batch PACKED over its lanes: slot s = (job s / npad, atom s % npad), 64 slots per round, two
+//     consecutive slots (always the same job: npad is even) per thread.  56 atoms x 8 jobs fill 7 rounds of 64
+//     lanes completely, where one job per warp leaves 8 of 64 slots empty;
+//   * the warp copies the JB j frames of the batch into its own slice of the stage area with 16-byte cp.async
+//     (one exposed round trip per batch), and every thread walks the j atoms of ITS job through process_group --
+//     same arithmetic, same binning modes as the tile kernel -- adding to the histogram of ITS job's lag; the j
+//     addresses of a warp differ only by the job (at most a few distinct addresses per LDS).
+// Warps never wait for each other inside a pass.
 // ---------------------------------------------------------------------------------------------
 constexpr int kWarps = kThreads / 32;
-constexpr int kSubTile = 32 * kIPT;   // i slots per warp
-static_assert(kWarps * kSubTile >= kSmallMax, "one job must fit the warps of a CTA");
-static_assert(kWarps * kSubTile * 3 <= kStages * 3 * kTileJ, "the group slices live in the stage area of pair_kernel");
+constexpr int kSubTile = 32 * kIPT;   // i slots per warp and round
+static_assert(kIPT == 2, "pair_small_kernel packs two consecutive slots per thread");
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+
+// cost of the jobs [0, k) of a lag-major list whose first n0 jobs are lag 0 (in sixteenths of a job), and its inverse
+// (the number of whole jobs that fit into cost x)
+struct SmallCost {
+    unsigned long long n0, w16;
+    __device__ __forceinline__ unsigned long long upto(unsigned long long k) const {
+        return k < n0 ? k * w16 : n0 * w16 + (k - n0) * 16ull;
+    }
+    __device__ __forceinline__ unsigned int jobs_in(unsigned long long x) const {
+        return static_cast<unsigned int>(x < n0 * w16 ? x / w16 : n0 + (x - n0 * w16) / 16ull);
+    }
+    // boundary `part` of `parts` equal-cost pieces of the jobs [a, b)
+    __device__ __forceinline__ unsigned int cut(unsigned int a, unsigned int b, unsigned int part, unsigned int parts) const {
+        if (part >= parts) return b;
+        const unsigned long long ca = upto(a), cb = upto(b);
+        return max(a, min(b, jobs_in(ca + (cb - ca) * part / parts)));
+    }
+};
 
 template <bool TRI, bool FAST, int MODE, bool UBOX>
 __global__ void __launch_bounds__(kThreads, kMinBlocks) pair_small_kernel(const PairParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
     constexpr bool EDGES = MODE == MODE_EDGES;
-    const SmemLayout L = smem_layout(p.ntypes, p.nbin, p.nhi, p.glo, EDGES);
+    const int JB = p.n_itiles, js = p.n_jchunks;   // jobs per batch, slots between the j frames of a batch
+    const int NB = p.small_nb;                      // histograms (lags) a CTA holds at a time
+    const SmemLayout L = smem_layout(p.ntypes, p.nbin, p.nhi, p.glo, EDGES, small_stage_slots(JB, js), NB);
     double *s_stage = reinterpret_cast<double *>(smem + L.stage);
     double2 *s_thr2 = reinterpret_cast<double2 *>(smem + L.thr2);
     double *s_thrf = reinterpret_cast<double *>(smem + L.thr_full);
@@ -1111,53 +1159,27 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) pair_small_kernel(const 
 
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
-    const int nt = p.ntypes, nbin = p.nbin;
+    const int nt = p.ntypes, nbin = p.nbin, npad = p.npad;
     const int P = nt * (nt + 1) / 2;
     const int hlen = 2 * P * nbin;
     const int rstride = row_stride(p.nhi, p.glo);
     const unsigned int self_off = static_cast<unsigned int>(P * rstride);
+    const int hwords = 2 * P * rstride;             // words of one histogram
 
     cta_tables<EDGES>(p, tid, P, rstride, s_hist, s_thr2, s_thrf, s_rowtab, s_tstart);
+    for (int k = hwords + tid; k < NB * hwords; k += kThreads) s_hist[k] = 0u;
     __syncthreads();
 
     PairConst c;
     c.thr2_addr = smem_u32(s_thr2);
     c.hist_addr = smem_u32(s_hist);
 
-    // groups of W warps: group `grp` takes jobs grp, grp + G, ... of a unit; warp `sub` of the group holds the
-    // i slots [sub*64, sub*64 + 64) of every job the group takes.  Warps beyond G*W (W = 3, 5, 6, 7) only take
-    // part in the CTA-wide steps.
-    const int W = p.n_itiles;                // warps per job
-    const int G = kWarps / W;                // jobs a CTA works on at a time
-    const int grp = warp / W, sub = warp - grp * W;
-    const bool working = grp < G;
-    const int srow = W * kSubTile;           // slots per coordinate row of a group slice
-    double *slice = s_stage + static_cast<size_t>(grp) * 3 * srow;
-    const uint32_t slice_addr = smem_u32(slice);
-    const uint32_t jrow_bytes = static_cast<uint32_t>(srow) * 8u;
-    const int gtid = sub * 32 + lane;        // thread within the group
-    const int gthreads = W * 32;
-    // named barriers 1..4, one per group (W >= 2 leaves at most 4 groups); literal ids, so that the CTA reserves
-    // five barriers and not all sixteen
-    auto group_sync = [&]() {
-        __syncwarp();
-        if (W > 1) {
-            switch (grp) {
-                case 0: asm volatile("bar.sync 1, %0;" ::"r"(gthreads) : "memory"); break;
-                case 1: asm volatile("bar.sync 2, %0;" ::"r"(gthreads) : "memory"); break;
-                case 2: asm volatile("bar.sync 3, %0;" ::"r"(gthreads) : "memory"); break;
-                default: asm volatile("bar.sync 4, %0;" ::"r"(gthreads) : "memory"); break;
-            }
-        }
-    };
+    // the warp's slice of the stage area: [3 coordinates][JB jobs][js slots]
+    const int crow = JB * js;
+    double *area = s_stage + static_cast<size_t>(warp) * 3 * crow;
+    const uint32_t area_addr = smem_u32(area);
+    const uint32_t jrow_bytes = static_cast<uint32_t>(crow) * 8u;
 
-    const int wi0 = sub * kSubTile;
-    int ii[kIPT], ti[kIPT];
-#pragma unroll
-    for (int k = 0; k < kIPT; ++k) {
-        ii[k] = wi0 + k * 32 + lane;
-        ti[k] = ii[k] < p.npad ? p.type_pad[ii[k]] : 0;
-    }
     if (UBOX) {
         c.box.lhx = p.ubox[0];
         c.box.lhy = p.ubox[1];
@@ -1177,19 +1199,71 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) pair_small_kernel(const 
     unsigned long long edges = 0;
     bool wrap_ok = true;
 
-    for (;;) {
-        if (tid == 0) s_sched[0] = p.unit_begin + atomicAdd(p.counter, 1u);
-        __syncthreads();   // also: every thread is past the merge of the previous unit
-        const unsigned int u = s_sched[0];
-        __syncthreads();
-        if (u >= p.unit_end) break;
-        const SmallUnit un = unit_at(p, u);
+    // this CTA's share of the jobs [unit_begin, unit_end) of the launch
+    SmallCost cost;
+    cost.n0 = static_cast<unsigned long long>(p.jchunk);
+    cost.w16 = static_cast<unsigned long long>(p.small_w16);
+    const unsigned int cta_a = cost.cut(p.unit_begin, p.unit_end, blockIdx.x, gridDim.x);
+    const unsigned int cta_b = cost.cut(p.unit_begin, p.unit_end, blockIdx.x + 1, gridDim.x);
+    // a pass ends before its 32-bit shared-memory counters could wrap (every pair adds at most one)
+    const unsigned int pass_cap = 0x7fffffffu / static_cast<unsigned int>(npad * npad);
+    const unsigned int norig = static_cast<unsigned int>(p.imp_norig), every = static_cast<unsigned int>(p.imp_every);
 
-        if (working) {
-            for (int jb = grp; jb < un.count; jb += G) {
-                const Job job = job_at(p, static_cast<unsigned int>(un.begin + jb));
+    for (unsigned int s0 = cta_a; s0 < cta_b;) {
+        // ---- the pass [s0, s1): jobs of the lags l0 .. l0 + NB - 1 (lag = index * every) ----
+        unsigned int s1, l0;
+        if (p.imp) {
+            l0 = s0 / norig;
+            s1 = min(cta_b, (l0 + static_cast<unsigned int>(NB)) * norig);
+        } else {
+            l0 = static_cast<unsigned int>(p.jobs[s0].tout) / every;
+            if (tid == 0) s_sched[1] = cta_b;
+            __syncthreads();
+            for (unsigned int k = s0 + 1u + tid; k < cta_b; k += kThreads)
+                if (static_cast<unsigned int>(p.jobs[k].tout) / every >= l0 + static_cast<unsigned int>(NB)) {
+                    atomicMin(&s_sched[1], k);
+                    break;
+                }
+            __syncthreads();
+            s1 = s_sched[1];
+        }
+        s1 = min(s1, s0 + pass_cap);
+        const unsigned int wa = cost.cut(s0, s1, warp, kWarps), wb = cost.cut(s0, s1, warp + 1, kWarps);
+
+        for (unsigned int b0 = wa; b0 < wb; b0 += JB) {
+            const int nj = min(JB, static_cast<int>(wb - b0));
+            // lane l holds job l of the batch (lanes past the batch repeat its last job; never used)
+            const Job mine = job_at(p, b0 + static_cast<unsigned int>(min(lane, nj - 1)));
+            const int mybuf = static_cast<int>(static_cast<unsigned int>(mine.tout) / every - l0);   // its histogram
+            __syncwarp();   // every lane is done with the previous batch's j frames
+            for (int jl = 0; jl < nj; ++jl) {
+                const int fj = __shfl_sync(0xffffffffu, mine.fj, jl);
+                const double *src = p.pos + static_cast<size_t>(fj) * 3 * npad;
+                const uint32_t dst = area_addr + static_cast<uint32_t>(jl * js) * 8u;
+                for (int q = 2 * lane; q < npad; q += 64) {
+                    cp_async16(dst + static_cast<uint32_t>(q) * 8u, src + q);
+                    cp_async16(dst + jrow_bytes + static_cast<uint32_t>(q) * 8u, src + npad + q);
+                    cp_async16(dst + 2u * jrow_bytes + static_cast<uint32_t>(q) * 8u, src + 2 * npad + q);
+                }
+            }
+            // the packed slot of this thread in round 0: (job jl, atoms atom, atom + 1)
+            int jl = 0, atom = 2 * lane;
+            while (atom >= npad) {
+                atom -= npad;
+                ++jl;
+            }
+            cp_async_wait_all();
+            __syncwarp();
+
+            const int total = nj * npad;
+            for (int base = 0; base < total; base += kSubTile) {
+                const bool valid = jl < nj;
+                const int jv = valid ? jl : 0, av = valid ? atom : 0;
+                const int fi = __shfl_sync(0xffffffffu, mine.fi, jv);
+                unsigned int *hist = s_hist + __shfl_sync(0xffffffffu, mybuf, jv) * hwords;
+                c.hist_addr = smem_u32(hist);
                 if (!UBOX) {
-                    const double *bx = p.box + static_cast<size_t>(job.fi) * 6;
+                    const double *bx = p.box + static_cast<size_t>(fi) * 6;
                     c.box.lhx = __ldg(bx + 0);
                     c.box.lhy = __ldg(bx + 1);
                     c.box.lhz = __ldg(bx + 2);
@@ -1199,34 +1273,39 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) pair_small_kernel(const 
                     c.box.nxy = -c.box.xy;
                     c.box.nxz = -c.box.xz;
                     c.box.nyz = -c.box.yz;
-            c.box.nxy = -c.box.xy;
-            c.box.nxz = -c.box.xz;
-            c.box.nyz = -c.box.yz;
                     c.nLx = __dmul_rn(c.box.lhx, -2.0);
                     c.nLy = __dmul_rn(c.box.lhy, -2.0);
                     c.nLz = __dmul_rn(c.box.lhz, -2.0);
                 }
                 double xi[kIPT], yi[kIPT], zi[kIPT];
-                const double *pi = p.pos + static_cast<size_t>(job.fi) * 3 * p.npad;
-#pragma unroll
-                for (int k = 0; k < kIPT; ++k) {
-                    if (ii[k] < p.npad) {
-                        xi[k] = pi[ii[k]];
-                        yi[k] = pi[p.npad + ii[k]];
-                        zi[k] = pi[2 * p.npad + ii[k]];
-                    } else {
-                        xi[k] = yi[k] = zi[k] = __longlong_as_double(0x7ff8000000000000ll);
-                    }
+                int ii[kIPT], ti[kIPT];
+                {
+                    const double *pi = p.pos + static_cast<size_t>(fi) * 3 * npad + av;
+                    const double2 vx = *reinterpret_cast<const double2 *>(pi);
+                    const double2 vy = *reinterpret_cast<const double2 *>(pi + npad);
+                    const double2 vz = *reinterpret_cast<const double2 *>(pi + 2 * npad);
+                    const int2 vt = *reinterpret_cast<const int2 *>(p.type_pad + av);
+                    const double ghost = __longlong_as_double(0x7ff8000000000000ll);
+                    xi[0] = valid ? vx.x : ghost;
+                    xi[1] = valid ? vx.y : ghost;
+                    yi[0] = valid ? vy.x : ghost;
+                    yi[1] = valid ? vy.y : ghost;
+                    zi[0] = valid ? vz.x : ghost;
+                    zi[1] = valid ? vz.y : ghost;
+                    ti[0] = vt.x;
+                    ti[1] = vt.y;
+                    ii[0] = av;
+                    ii[1] = av + 1;
                 }
-                const double *pj = p.pos + static_cast<size_t>(job.fj) * 3 * p.npad;
-                group_sync();   // every warp of the group is done with the previous job's copy
-                for (int q = gtid; q < p.npad; q += gthreads) {
-                    slice[q] = pj[q];
-                    slice[srow + q] = pj[p.npad + q];
-                    slice[2 * srow + q] = pj[2 * p.npad + q];
-                }
-                group_sync();
+                const uint32_t jaddr = area_addr + static_cast<uint32_t>(jv * js) * 8u;
 
+                // Lag 0 (fi == fj): every atom meets itself at distance 0, which the safe-zone binning sees as "on a bin
+                // edge" (r = 0 is an edge of the extended grid whenever rmin / dr is an integer) and sends through its
+                // correction path -- 2.4x the time of any other job (measured, r2w).  A warp that holds such a job leaves the
+                // self pairs out of the main pass instead (three instructions per pair, on 1 job in 189 of C1).
+                constexpr bool kSafe = MODE == MODE_SAFE || MODE == MODE_SAFE_DENSE;
+                const int tout = __shfl_sync(0xffffffffu, mine.tout, jv);   // (every lane takes part: no short-circuit)
+                const bool zself = kSafe && __any_sync(0xffffffffu, valid && tout == 0);
                 for (int ty = 0; ty < nt; ++ty) {
                     const int lo = s_tstart[ty], hi = s_tstart[ty + 1];
                     if (lo >= hi) continue;
@@ -1236,39 +1315,60 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) pair_small_kernel(const 
                     // every pair, the atom with itself included, goes to the "different atoms" row here: with a few
                     // dozen atoms EVERY group holds some of the warp's own atoms, and a per-pair i == j row select
                     // would cost three instructions on each of the N^2 pairs; the N self pairs are moved below
+                    if (!zself) {
 #pragma unroll 1
-                    for (int j = lo; j < hi; j += kJU)
-                        process_group<TRI, FAST, MODE, false>(p, c, xi, yi, zi, ii, row, slice_addr, jrow_bytes, j, j,
-                                                              s_thr2, s_thrf, s_hist, self_off, edges, wrap_ok);
+                        for (int j = lo; j < hi; j += kJU)
+                            process_group<TRI, FAST, MODE, false>(p, c, xi, yi, zi, ii, row, jaddr, jrow_bytes, j, j, s_thr2,
+                                                                  s_thrf, hist, self_off, edges, wrap_ok);
+                    } else {
+#pragma unroll 1
+                        for (int j = lo; j < hi; j += kJU)
+                            process_group<TRI, FAST, MODE, false, true>(p, c, xi, yi, zi, ii, row, jaddr, jrow_bytes, j, j,
+                                                                        s_thr2, s_thrf, hist, self_off, edges, wrap_ok);
+                    }
                 }
                 // the self pairs (i, frame fi) - (i, frame fj): from the "different atoms" row of the atom's type to its
-                // "same atom" row, at the exact bin of the threshold table (where the pass above -- fast path plus
-                // correction, or a bracket search -- has counted them)
+                // "same atom" row (or only into the latter, when the main pass has left them out), at the exact bin of
+                // the threshold table (where the pass above -- fast path plus correction, or a bracket search -- has
+                // counted them)
+                if (valid) {
+                    const double *sj = area + static_cast<size_t>(jv) * js + av;
 #pragma unroll
-                for (int k = 0; k < kIPT; ++k) {
-                    if (ii[k] >= p.npad) continue;
-                    double dx = __dsub_rn(xi[k], slice[ii[k]]);
-                    double dy = __dsub_rn(yi[k], slice[srow + ii[k]]);
-                    double dz = __dsub_rn(zi[k], slice[2 * srow + ii[k]]);
-                    if (FAST)
-                        min_image_single<TRI>(dx, dy, dz, c.box, c.nLx, c.nLy, c.nLz);
-                    else
-                        wrap_ok &= min_image_general<TRI>(dx, dy, dz, c.box);
-                    const double d2 = d2_of(dx, dy, dz);
-                    if ((d2 >= s_thr2[1].x) && (d2 < s_thr2[nbin].y)) {   // false for the NaN of a ghost slot
-                        int g = static_cast<int>(bin_guess1(d2, p.inv_dr, p.c0, static_cast<unsigned int>(nbin) + 2u)) - 1;
-                        g = min(max(g, 0), nbin - 1);
-                        while (d2 < s_thr2[g + 1].x) --g;
-                        while (d2 >= s_thr2[g + 1].y) ++g;
-                        unsigned int *w = s_hist + s_rowtab[ti[k] * nt + ti[k]] + g;
-                        atomicAdd(w, 0xffffffffu);
-                        atomicAdd(w + self_off, 1u);
+                    for (int k = 0; k < kIPT; ++k) {
+                        double dx = __dsub_rn(xi[k], sj[k]);
+                        double dy = __dsub_rn(yi[k], sj[crow + k]);
+                        double dz = __dsub_rn(zi[k], sj[2 * crow + k]);
+                        if (FAST)
+                            min_image_single<TRI>(dx, dy, dz, c.box, c.nLx, c.nLy, c.nLz);
+                        else
+                            wrap_ok &= min_image_general<TRI>(dx, dy, dz, c.box);
+                        const double d2 = d2_of(dx, dy, dz);
+                        if ((d2 >= s_thr2[1].x) && (d2 < s_thr2[nbin].y)) {   // false for the NaN of a ghost slot
+                            int g = static_cast<int>(bin_guess1(d2, p.inv_dr, p.c0, static_cast<unsigned int>(nbin) + 2u)) - 1;
+                            g = min(max(g, 0), nbin - 1);
+                            while (d2 < s_thr2[g + 1].x) --g;
+                            while (d2 >= s_thr2[g + 1].y) ++g;
+                            unsigned int *w = hist + s_rowtab[ti[k] * nt + ti[k]] + g;
+                            if (!zself) atomicAdd(w, 0xffffffffu);
+                            atomicAdd(w + self_off, 1u);
+                        }
                     }
+                }
+                // the thread's slot of the next round
+                atom += kSubTile;
+                while (atom >= npad) {
+                    atom -= npad;
+                    ++jl;
                 }
             }
         }
+        // ---- the histograms of the pass into the global rows of their lags ----
         __syncthreads();
-        cta_flush(p, tid, un.lag, hlen, rstride, s_hist);
+        const unsigned int l_last = p.imp ? (s1 - 1u) / norig : static_cast<unsigned int>(p.jobs[s1 - 1u].tout) / every;
+        for (unsigned int l = l0; l <= l_last; ++l)
+            cta_flush(p, tid, static_cast<int>(l * every), hlen, rstride, s_hist + (l - l0) * hwords);
+        __syncthreads();
+        s0 = s1;
     }
     if (EDGES) {
         for (int o = 16; o > 0; o >>= 1) edges += __shfl_xor_sync(0xffffffffu, edges, o);

@@ -45,20 +45,12 @@ struct Job {
     int tout;  // output lag row
 };
 
-// pair_small_kernel: a run of jobs of ONE lag, dealt to the warp groups of a CTA
-struct SmallUnit {
-    int begin;   // first job of the run (index into PairParams::jobs)
-    int count;   // jobs in the run
-    int lag;     // their common output lag row
-};
-
 struct PairParams {
     const double *pos;        // [frames][3][npad]  (x row, y row, z row per frame; ghosts are NaN)
     const double *box;        // [frames][6]: lx/2, ly/2, lz/2, xy, xz, yz
     const int *type_pad;      // [npad] dense type of every slot (ghosts: the type of their group)
     const int *type_start;    // [ntypes+1] first slot of every type group
     const Job *jobs;
-    const SmallUnit *units;   // pair_small_kernel only: the work units (pair_kernel derives them from jobs)
     unsigned long long *ghist;  // [leff][2P][nbin]
     unsigned long long *edges;  // [1] (EDGES variant)
     unsigned int *counter;      // work-unit ticket
@@ -67,10 +59,13 @@ struct PairParams {
     const double *thr_full;     // [nbin+1] plain thresholds (EDGES variant)
     double rmin2, rmax2;
     double ubox[12];            // UBOX variants: lx/2, ly/2, lz/2, xy, xz, yz, -lx, -ly, -lz, -xy, -xz, -yz of the one box of the window
-    unsigned unit_begin, unit_end;
+    unsigned unit_begin, unit_end;    // pair_kernel: work units (job, i tile, j chunk) of this launch; pair_small_kernel: its JOBS
     int npad, ntypes, nbin;
-    int n_itiles, n_jchunks, jchunk;  // jchunk is a multiple of kTileJ; pair_small_kernel: n_itiles = warps per job
-                                      // (i sub-tiles of 32*kIPT slots, 1..8), the other two unused
+    int n_itiles, n_jchunks, jchunk;  // jchunk is a multiple of kTileJ; pair_small_kernel: n_itiles = jobs a warp works on
+                                      // at a time, n_jchunks = slots between their j frames in the warp's stage slice,
+                                      // jchunk = how many jobs at the head of the job list are lag 0
+    int small_nb, small_w16;          // pair_small_kernel: histograms (lags) a CTA holds at a time; cost of a lag-0 job in
+                                      // sixteenths of another job's
     float inv_dr, c0;                 // bin guess = floor(sqrtf(d2) * inv_dr + c0)
     float c0h, lim, qmax;             // MODE_SAFE: c0 - 0.5, 0.5 - eps, nbin + 0.25 (clamp of the bin coordinate)
     int glo;                          // guard bins below bin 0 in every shared-memory histogram row
@@ -78,13 +73,14 @@ struct PairParams {
     int skew;                         // MODE_SAFE2: half of the warps start every tile with a dummy binning run (phase_skew)
     float inv_lo, inv_hi, bias0, smax;  // MODE_SAFE2: inv_dr * (1 -+ 2^-20), 1.5*2^23 + c0 (c0 an integer), clamp of sqrt(d2)
     unsigned hlo, hspan, hhi;         // candidate tests on the high word of d2 (hhi = hlo + hspan)
-    // implicit jobs (imp != 0; jobs / units are then not read): job k = lag (k / imp_norig) * imp_every, origin frame
-    // imp_f0 + (k % imp_norig) * imp_skip; pair_small_kernel: unit u = share (u % units_per_lag) of imp_each origins
-    // of lag u / units_per_lag
-    int imp, imp_f0, imp_norig, imp_skip, imp_every, imp_each;
+    // implicit jobs (imp != 0; jobs is then not read): job k = lag (k / imp_norig) * imp_every, origin frame
+    // imp_f0 + (k % imp_norig) * imp_skip
+    int imp, imp_f0, imp_norig, imp_skip, imp_every;
 };
 
 size_t pair_kernel_smem_bytes(int ntypes, int nbin, int nhi, int glo, bool edges);
+size_t pair_small_kernel_smem_bytes(int ntypes, int nbin, int nhi, int glo, bool edges, int jobs_per_batch, int job_stride,
+                                    int nhist);
 
 // variant = TRI | FAST<<1 | MODE<<2 | UBOX<<5 | SMALL<<6, MODE: 0 thresholds, 1 thresholds + warp aggregation, 2 edges, 3 safe-zone,
 // 4 safe-zone without the group filter (dense in-range workloads: nearly every group holds an in-range pair)

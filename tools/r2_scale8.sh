@@ -14,7 +14,7 @@ for g in 1 2 4 $n; do
   fi
   python -c "
 import json;d=json.loads([l for l in open('$out/${tag}_bench_n$g.json') if l.startswith('{')][-1])
-print('N=$g value %.4g e2e %.4g ms %.1f e2e_ms %.1f sha %s eq_ref %s frac %.3f'%(d['value'], d['e2e']['value'], d['ms_per_step'], d['e2e']['ms_per_step'], d['counts_sha256'][:12], d['counts_check']['equal_to_reference'], d['roofline']['frac']))"
+print('N=$g value %.4g e2e %.4g ms %.1f e2e_ms %.1f pageable_ms %.1f sha %s eq_ref %s frac %.3f'%(d['value'], d['e2e']['value'], d['ms_per_step'], d['e2e']['ms_per_step'], d['e2e']['from_pageable_arrays']['ms_per_step'], d['counts_sha256'][:12], d['counts_check']['equal_to_reference'], d['roofline']['frac']))"
   grep "e2e steps" $out/${tag}_bench_n$g.log | head -2
 done
 for g in 1 $n; do

@@ -1,0 +1,17 @@
+#!/bin/bash
+# packed small-system kernel: parity first, then C1 (device + e2e), a full capture of the kernel, then the whole GPU suite
+tag=${1:-r2w}; out=gpurun_out; mkdir -p $out
+timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -x -q > $out/${tag}_pytest_parity.log 2>&1
+echo "parity rc=$?"; tail -5 $out/${tag}_pytest_parity.log
+timeout 600 python bench.py --workload C1 --steps 5 --warmup 3 > $out/${tag}_C1.json 2> $out/${tag}_C1.log
+echo "C1 rc=$?"; python -c "
+import json;d=json.load(open('$out/${tag}_C1.json'))
+print('C1: device ms %.2f e2e ms %.2f frac %.3f value %.4g'%(d['ms_per_step'], d['e2e']['ms_per_step'], d['roofline']['frac'], d['value']))"
+grep "\[bench\] pass" $out/${tag}_C1.log | tail -3
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:pair_small -s 3 -c 1 \
+    -f -o $out/${tag}_small_c1 python bench.py --workload C1 --steps 1 --warmup 1 --no-cpu-baseline --no-traffic --no-e2e > $out/${tag}_ncu_c1.log 2>&1
+echo "ncu c1 rc=$?"
+AGOFRT_DEBUG=1 timeout 900 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-traffic > $out/${tag}_bench_default.json 2> $out/${tag}_bench_default.log
+echo "bench rc=$?"; grep "e2e step\|released\|upload of" $out/${tag}_bench_default.log | tail -40
+timeout 1500 python -m pytest tests -m gpu -x -q --deselect tests/test_gpu_parity.py > $out/${tag}_pytest_rest.log 2>&1
+echo "rest rc=$?"; tail -5 $out/${tag}_pytest_rest.log
