@@ -1,27 +1,33 @@
 #!/usr/bin/env python
 """bench.py -- g(r,t) pair-distance evaluations per second on B200 (BASELINE.json's metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload C2] [--impl native|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload C4] [--impl native|reference]
 
-A "step" is one Gofrt block: ``reset(ntimesteps); calculate(primo)`` of the named workload, i.e.
-ceil(leff/every) * ceil(ntimesteps/skip) (lag, origin) jobs of N^2 pair evaluations each, through
-the C ABI of libagofrt.so (no PyTorch in the data path; torch is only used for the multi-process
-rendezvous, the barrier and the NCCL-id broadcast).
+Default step: the north-star workload C4 (100 000 atoms, triclinic cell), a regular subset of its (lag, origin) jobs
+(synth.BENCH_SUBSET: every 8th lag, every 96th origin -- 2.08e12 pair evaluations, 2.3 s on one B200).  Its counts are
+compared with the counts of the UNMODIFIED reference on the same input (tests/golden/c4_subset_counts.json, sha256).
+A "step" is one Gofrt block: ``reset(ntimesteps); calculate(primo)``, i.e. ceil(leff/every) * ceil(ntimesteps/skip)
+(lag, origin) jobs of N^2 pair evaluations each.
 
-``value``   pair evaluations / s with the trajectory window already resident in HBM, timed with
-            CUDA events on the library's own stream (agofrt_stats.total_ms), max over ranks.
-``e2e``     the same through the host-buffer call sequence a user makes: upload of the window from
-            pinned host memory (H2D), the block, and the read-back of the counts (D2H), wall clock
-            around the calls with a device synchronise inside them.
-``roofline`` FP64-pipe bound: 16 (orthorhombic) / 19 (triclinic) FP64
-            operations per pair evaluation against the DFMA issue rate measured in this same run.
-``cpu_baseline`` the reference's own CPU implementation (oracle/_ref, compiled from the unmodified
-            sources) -- or the oracle port when that is absent -- on a bounded sample of the same
-            workload on this box's host cores.
+``value``   pair evaluations / s with the trajectory window already resident in HBM, through the C ABI of
+            libagofrt.so, timed with CUDA events on the library's own stream (agofrt_stats.total_ms), max over ranks.
+``e2e``     the same through the reference-facing python module of this repository (python/pyanalisi*.so), every step:
+            ``Trajectory(pos, vel, types, box, fmt, wrap=True)`` (box conversion, type compaction, upload from page-locked
+            numpy arrays -- with N ranks every rank uploads 1/N of the frames and the shares are exchanged GPU to GPU --,
+            wrap on the GPUs), ``Gofrt(...)``, ``reset``, ``calculate``, ``np.array(g)``; wall clock between barriers.
+            ``e2e.from_pageable_arrays`` is one more step from ordinary (pageable) numpy arrays.
+``roofline`` FP64-pipe bound: 16 (orthorhombic) / 19 (triclinic) FP64 operations per pair
+            evaluation against the DFMA issue rate measured in this same run; also the fraction counted on the FP64
+            instructions the kernel really issues (14 / 17), and the DRAM traffic of one launch, measured by re-running
+            the step once under ncu at the end of the run (nothing of that child is timed).
+``cpu_baseline`` the reference's own CPU implementation (oracle/_ref, compiled from the unmodified sources) -- or the
+            oracle port when that is absent -- on a bounded sample of the same workload on this box's host cores.
+``counts_sha256`` / ``counts_check`` the checksum of the step's integer counts (identical for every N), the reference's
+            checksum, and the lag-0 self-pair property.
 
-N > 1: one process per GPU (torchrun); every rank holds the whole window, the work units of the
-block are sharded over the ranks, one NCCL all-reduce of the integer histograms per step
-("strong" scaling: the total work per step is fixed).
+N > 1: one process per GPU (torchrun); every rank holds the whole window, the work units of the block are sharded over
+the ranks, one NCCL all-reduce of the integer histograms per step ("strong" scaling: the total work per step is fixed).
+No PyTorch in the data path: torch is only used for the multi-process rendezvous, the barrier and the NCCL-id broadcast.
 """
 import argparse
 import dataclasses
