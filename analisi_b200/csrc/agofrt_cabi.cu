@@ -1920,7 +1920,8 @@ static int block_impl(agofrt_plan *p, size_t primo, unsigned ntimesteps, unsigne
         const size_t per_job = static_cast<size_t>(kThreads / 32) * 3 * small_js * sizeof(double);
         uint64_t total_warps = 0;
         for (const Dev &d : ctx->devs) total_warps += static_cast<uint64_t>(kMinBlocks) * d.sm_count * (kThreads / 32);
-        const int by_jobs = static_cast<int>(std::min<uint64_t>(8, std::max<uint64_t>(1, njobs / std::max<uint64_t>(total_warps, 1))));
+        int by_jobs = static_cast<int>(std::min<uint64_t>(8, std::max<uint64_t>(1, njobs / std::max<uint64_t>(total_warps, 1))));
+        if (const char *e = getenv("AGOFRT_SMALL_BATCH")) by_jobs = std::max(1, std::min(8, atoi(e)));   // (tests: large batches on few jobs)
         // the best batch (fewest empty lanes in its last round; ties: the larger) that fits beside `nb` histograms
         auto best_batch = [&](int nb, int *jb_out) {
             const size_t fixed = pair_small_kernel_smem_bytes(nt, static_cast<int>(p->nbin), static_cast<int>(p->nbin), p->glo,
@@ -1943,7 +1944,9 @@ static int block_impl(agofrt_plan *p, size_t primo, unsigned ntimesteps, unsigne
         // per lag), as long as they fit without costing the batch its shape.  The warp-aggregated binning keys on the
         // bin alone: one histogram.
         const uint64_t jobs_per_cta = std::max<uint64_t>(1, njobs / std::max(1, total_ctas));
-        const int want_nb = aggregate ? 1 : static_cast<int>(std::min<uint64_t>(8, jobs_per_cta / std::max(1u, norig) + 2));
+        int want_nb = static_cast<int>(std::min<uint64_t>(8, jobs_per_cta / std::max(1u, norig) + 2));
+        if (const char *e = getenv("AGOFRT_SMALL_HISTS")) want_nb = std::max(1, std::min(8, atoi(e)));
+        if (aggregate) want_nb = 1;
         for (int nb = want_nb; nb >= 2; --nb) {
             int jb = 1;
             if (best_batch(nb, &jb) >= eff1 - 1e-9 && jb >= small_jb) {

@@ -580,6 +580,50 @@ def test_small_system_many_units_per_lag(ctx):
     assert int(c.sum()) == int(co.sum())
 
 
+@pytest.mark.parametrize("natoms,ntypes,triclinic", [(5, 1, False), (20, 2, True), (37, 3, False), (56, 2, False),
+                                                     (72, 2, True), (100, 3, False), (130, 1, True), (200, 2, True)])
+@pytest.mark.parametrize("batch,hists", [(8, 1), (8, 3), (3, 2), (2, 8)])
+def test_small_system_packed_batches(ctx, monkeypatch, natoms, ntypes, triclinic, batch, hists):
+    """The shapes a launch with many jobs takes, forced on a few jobs: `batch` jobs per warp with their i slots packed
+    over its lanes (two consecutive slots per thread, up to three jobs within one round), `hists` lag histograms per
+    CTA (batches that straddle lags), lag 0 with rmin = 0 (the self pairs are left out of the main pass and counted
+    alone), implicit and explicit job lists, every binning mode, both minimum-image paths."""
+    monkeypatch.setenv("AGOFRT_SMALL_BATCH", str(batch))
+    monkeypatch.setenv("AGOFRT_SMALL_HISTS", str(hists))
+    nframes = 40
+    pos, bi, types = _small_system(900 + natoms, natoms, ntypes, triclinic, nframes)
+    ctx.pbc_wrap(pos, bi)
+    for args, kw in (((0.0, 2.9, 64, 11, 25), {}),                                   # 11 lags x 25 origins, self pairs in bin 0
+                     ((0.5, 3.0, 40, 9, 27), dict(primo=2, skip=2, every=3))):      # ragged loops, rmin / dr an integer
+        co = oracle.counts(pos, bi, types, *args, ntypes=ntypes, **kw)
+        for opt in (0, cabi.OPT_EXPLICIT_JOBS, cabi.OPT_FORCE_GENERAL, cabi.OPT_AGGREGATE, cabi.OPT_NO_SAFE,
+                    cabi.OPT_DENSE, cabi.OPT_SPARSE | cabi.OPT_NO_UBOX):
+            c, st = gpu_counts(ctx, pos, bi, types, ntypes, *args, options=opt | cabi.OPT_SMALL, **kw)
+            assert np.array_equal(c, co), (args, opt)
+            assert ran_small(st)
+        c5, st5, e5 = gpu_counts(ctx, pos, bi, types, ntypes, *args, edges=True, options=cabi.OPT_SMALL, **kw)
+        _, eo = oracle.counts(pos, bi, types, *args, ntypes=ntypes, return_edges=True, **kw)
+        assert np.array_equal(c5, co) and e5 == eo and ran_small(st5)
+
+
+@pytest.mark.parametrize("batch,hists", [(8, 2), (4, 4)])
+def test_small_system_packed_batches_npt_unwrapped(ctx, monkeypatch, batch, hists):
+    """Explicit job lists of both kinds (single-pass and general minimum image) in one block, box changing every
+    frame, through packed batches."""
+    monkeypatch.setenv("AGOFRT_SMALL_BATCH", str(batch))
+    monkeypatch.setenv("AGOFRT_SMALL_HISTS", str(hists))
+    natoms = 88
+    pos, bi, types = _small_system(1234, natoms, 2, True, 30, npt=True)
+    shift = np.random.default_rng(5).integers(-2, 3, size=(1, natoms, 3))
+    shift[:, ::3] = 0
+    pos = pos + shift * bi[:, None, 3:6] * 2
+    args = (0.0, 3.1, 50, 8, 20)
+    co = oracle.counts(pos, bi, types, *args, ntypes=2)
+    c, st = gpu_counts(ctx, pos, bi, types, 2, *args)
+    assert np.array_equal(c, co) and ran_small(st)
+    assert 0 < st["jobs_fast"] < st["jobs"] or st["jobs_fast"] in (0, st["jobs"])
+
+
 # ---- block averages on the device (MediaVar) ------------------------------------------------------------------------
 def test_block_average_on_device(ctx):
     """agofrt_blockavg_*: mean and variance of the mean over blocks, bit-identical to the oracle's MediaVar
