@@ -1803,6 +1803,9 @@ struct BlockTarget {
     int dev;                    // local device
     unsigned long long *ghist;  // [len] on that device
     bool first;                 // first block of the batch on this device: reset the error flag
+    // the part [part_a, part_b) / part_den of the block's work units that this device takes (agofrt_blocks shares out
+    // blocks AND parts of blocks when the blocks do not divide among the devices); part_den == 0: all of it
+    uint32_t part_a = 0, part_b = 0, part_den = 0;
 };
 constexpr int kNotBatchable = 1;   // block_impl with a target: the block has no regular job list (caller falls back)
 
@@ -2053,6 +2056,10 @@ static int block_impl(agofrt_plan *p, size_t primo, unsigned ntimesteps, unsigne
                 const uint64_t units = small ? nlist : nlist * per_job;   // the small-system kernel shares out jobs
                 uint64_t ub = 0, ue = 0;
                 agofrt_shard_range(units, g, world, &ub, &ue);
+                if (tg && tg->part_den) {
+                    ub = static_cast<uint64_t>(static_cast<unsigned __int128>(units) * tg->part_a / tg->part_den);
+                    ue = static_cast<uint64_t>(static_cast<unsigned __int128>(units) * tg->part_b / tg->part_den);
+                }
                 if (ue <= ub) continue;
                 PairParams pp;
                 pp.pos = td.pos;
@@ -2296,12 +2303,28 @@ extern "C" int agofrt_blocks(agofrt_plan *p, size_t primo0, size_t stride, unsig
     ms_alloc = since0();
     agofrt_stats sum;
     memset(&sum, 0, sizeof(sum));
-    // contiguous runs of blocks per device (agofrt_shard_range over the blocks): one exchange per device afterwards
+    // Contiguous runs of blocks per device.  When the blocks divide among the devices, whole blocks (every device then
+    // sends its run to the others in one piece); otherwise device r takes the work units [r, r+1) * nblocks / world of
+    // the batch -- whole blocks and PARTS of blocks (20 blocks on 8 GPUs: 2.5 each) -- into zeroed slots, and the
+    // integer counts of all devices are summed (one all-reduce over the batch).
+    const bool whole = world <= 1 || nblocks % static_cast<unsigned>(world) == 0;
     for (int i = 0; i < nloc; ++i) {
-        uint64_t b0 = 0, b1 = 0;
-        agofrt_shard_range(nblocks, first_rank + i, world, &b0, &b1);
-        for (uint64_t b = b0; b < b1; ++b) {
+        const uint64_t r = static_cast<uint64_t>(first_rank + i), W = static_cast<uint64_t>(world);
+        // in units of 1/W block: this device owns [r * nblocks, (r + 1) * nblocks)
+        const uint64_t own_a = r * nblocks, own_b = (r + 1) * nblocks;
+        const uint64_t b0 = own_a / W, b1 = (own_b + W - 1) / W;
+        if (!whole) {
+            CU(cudaSetDevice(ctx->devs[i].id));
+            CU(cudaMemsetAsync(p->dev[i].batch, 0, static_cast<size_t>(nblocks) * len * sizeof(unsigned long long), ctx->devs[i].stream));
+        }
+        for (uint64_t b = b0; b < b1 && b < nblocks; ++b) {
             BlockTarget tg{i, p->dev[i].batch + static_cast<size_t>(b) * len, b == b0};
+            if (!whole) {
+                tg.part_a = static_cast<uint32_t>(std::max(own_a, b * W) - b * W);
+                tg.part_b = static_cast<uint32_t>(std::min(own_b, (b + 1) * W) - b * W);
+                tg.part_den = static_cast<uint32_t>(W);
+                if (tg.part_b <= tg.part_a) continue;
+            }
             agofrt_stats st;
             memset(&st, 0, sizeof(st));
             rc = block_impl(p, primo0 + static_cast<size_t>(b) * stride, ntimesteps, leff, skip, every, options | AGOFRT_OPT_ON_DEVICE,
@@ -2311,8 +2334,8 @@ extern "C" int agofrt_blocks(agofrt_plan *p, size_t primo0, size_t stride, unsig
                                             "frame range): run the blocks one by one with agofrt_block", static_cast<unsigned long long>(b));
             if (rc != AGOFRT_OK) return rc;
             sum.pair_evals += st.pair_evals;
-            sum.jobs += st.jobs;
-            sum.jobs_fast += st.jobs_fast;
+            sum.jobs += (whole || tg.part_a == 0) ? st.jobs : 0;   // a block shared by two devices counts once
+            sum.jobs_fast += (whole || tg.part_a == 0) ? st.jobs_fast : 0;
             sum.launches += st.launches;
             sum.kernel_modes |= st.kernel_modes;
         }
@@ -2322,25 +2345,19 @@ extern "C" int agofrt_blocks(agofrt_plan *p, size_t primo0, size_t stride, unsig
         CU(cudaEventRecord(ctx->devs[i].ev_k1, ctx->devs[i].stream));
     }
     ms_enqueue = since0() - ms_alloc;
-    // every device receives every block: the run of device r travels in one piece
+    // every device receives every block: the run of device r travels in one piece, or the partial counts are summed
     if (world > 1) {
         NcclApi &api = nccl_api();
         NC(api.GroupStart());
-        if (nblocks % static_cast<unsigned>(world) == 0) {
+        if (whole) {
             const size_t per = static_cast<size_t>(nblocks / static_cast<unsigned>(world)) * len;
             for (int i = 0; i < nloc; ++i)
                 NC(api.AllGather(p->dev[i].batch + static_cast<size_t>(first_rank + i) * per, p->dev[i].batch, per, ncclUint64,
                                  ctx->devs[i].comm, ctx->devs[i].stream));
         } else {
-            for (int r = 0; r < world; ++r) {
-                uint64_t b0 = 0, b1 = 0;
-                agofrt_shard_range(nblocks, r, world, &b0, &b1);
-                if (b1 <= b0) continue;
-                for (int i = 0; i < nloc; ++i) {
-                    unsigned long long *q = p->dev[i].batch + static_cast<size_t>(b0) * len;
-                    NC(api.Broadcast(q, q, static_cast<size_t>(b1 - b0) * len, ncclUint64, r, ctx->devs[i].comm, ctx->devs[i].stream));
-                }
-            }
+            for (int i = 0; i < nloc; ++i)
+                NC(api.AllReduce(p->dev[i].batch, p->dev[i].batch, static_cast<size_t>(nblocks) * len, ncclUint64, ncclSum,
+                                 ctx->devs[i].comm, ctx->devs[i].stream));
         }
         NC(api.GroupEnd());
     }
