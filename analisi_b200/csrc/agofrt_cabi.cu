@@ -25,6 +25,7 @@
 #include <numeric>
 #include <string>
 #include <thread>
+#include <unordered_map>
 #include <unordered_set>
 #include <vector>
 
@@ -388,16 +389,39 @@ extern "C" int agofrt_device_count(int *count) try {
 // that computes still fails with AGOFRT_ERR_CUDA.
 static std::mutex g_pageable_mutex;
 static std::unordered_set<void *> g_pageable;
+// Page-locking costs milliseconds per call (cudaHostAlloc of the two 29 MB window buffers of the C1 run: 6-31 ms,
+// r2ab): buffers of 1 MiB .. 256 MiB that are given back are kept (at most 8, 512 MiB in all) and handed to the next
+// request of the same size -- a process that builds a trajectory object per analysis pays for them once.
+static std::unordered_map<void *, size_t> g_pinned;                  // live page-locked buffers and their sizes
+static std::vector<std::pair<void *, size_t>> g_pinned_pool;
+static size_t g_pinned_pool_bytes = 0;
+constexpr size_t kPinnedPoolMin = 1u << 20, kPinnedPoolMax = 256u << 20, kPinnedPoolTotal = 512u << 20, kPinnedPoolEntries = 8;
 
 extern "C" int agofrt_host_alloc(void **ptr, size_t bytes) try {
     if (!ptr) return fail(AGOFRT_ERR_ARG, "ptr is NULL");
     *ptr = nullptr;
-    const cudaError_t e = cudaHostAlloc(ptr, bytes ? bytes : 1, cudaHostAllocPortable);
-    if (e == cudaSuccess) return AGOFRT_OK;
+    const size_t want = (std::max<size_t>(bytes, 1) + 4095) / 4096 * 4096;
+    {
+        std::lock_guard<std::mutex> lock(g_pageable_mutex);
+        for (size_t k = 0; k < g_pinned_pool.size(); ++k)
+            if (g_pinned_pool[k].second == want) {
+                *ptr = g_pinned_pool[k].first;
+                g_pinned_pool_bytes -= want;
+                g_pinned_pool.erase(g_pinned_pool.begin() + k);
+                g_pinned[*ptr] = want;
+                return AGOFRT_OK;
+            }
+    }
+    const cudaError_t e = cudaHostAlloc(ptr, want, cudaHostAllocPortable);
+    if (e == cudaSuccess) {
+        std::lock_guard<std::mutex> lock(g_pageable_mutex);
+        g_pinned[*ptr] = want;
+        return AGOFRT_OK;
+    }
     cudaGetLastError();
     if (e == cudaErrorInsufficientDriver || e == cudaErrorNoDevice) {
         void *p = nullptr;
-        if (posix_memalign(&p, 4096, bytes ? bytes : 1) != 0) return fail(AGOFRT_ERR_INTERNAL, "out of host memory (%zu bytes)", bytes);
+        if (posix_memalign(&p, 4096, want) != 0) return fail(AGOFRT_ERR_INTERNAL, "out of host memory (%zu bytes)", bytes);
         std::lock_guard<std::mutex> lock(g_pageable_mutex);
         g_pageable.insert(p);
         *ptr = p;
@@ -416,6 +440,17 @@ extern "C" int agofrt_host_free(void *ptr) try {
             g_pageable.erase(it);
             free(ptr);
             return AGOFRT_OK;
+        }
+        auto pin = g_pinned.find(ptr);
+        if (pin != g_pinned.end()) {
+            const size_t have = pin->second;
+            g_pinned.erase(pin);
+            if (have >= kPinnedPoolMin && have <= kPinnedPoolMax && g_pinned_pool.size() < kPinnedPoolEntries &&
+                g_pinned_pool_bytes + have <= kPinnedPoolTotal) {
+                g_pinned_pool.emplace_back(ptr, have);
+                g_pinned_pool_bytes += have;
+                return AGOFRT_OK;
+            }
         }
     }
     CU(cudaFreeHost(ptr));

@@ -72,7 +72,8 @@ AGOFRT_API const char *agofrt_last_error(void);
 AGOFRT_API int agofrt_device_count(int *count);
 
 /* Pinned host memory for window buffers (the reference uses fftw_malloc only as an aligned
- * allocator, lib/src/trajectory.cpp:362-371). */
+ * allocator, lib/src/trajectory.cpp:362-371).  Buffers of 1 MiB .. 256 MiB given back with agofrt_host_free are kept
+ * page-locked (at most 8, 512 MiB in all) and handed to the next request of the same size. */
 AGOFRT_API int agofrt_host_alloc(void **ptr, size_t bytes);
 AGOFRT_API int agofrt_host_free(void *ptr);
 
