@@ -1,6 +1,8 @@
 // agofrt_kernels.cu -- hand-written sm_100a kernels of libagofrt.so.  See agofrt_kernels.cuh.
 #include "agofrt_kernels.cuh"
 
+#include <cstdlib>
+
 #include <cmath>
 
 namespace agofrt {
@@ -2186,6 +2188,101 @@ __global__ void __launch_bounds__(kMsdThreads) msd_partial_kernel(const MsdParam
     }
 }
 
+// The same sums when every frame is an origin (skip == 1) and no centre of mass is subtracted: the later frames of
+// consecutive origins overlap in all but one frame, so a thread keeps the kMsdLags later frames of its atom in a
+// REGISTER RING and reads two frames per origin (the origin itself and the one later frame that enters the ring)
+// instead of kMsdLags + 1 -- 6 loads for 144 FP64 operations: the kernel is bound by the FP64 pipe, not by L1.  The
+// origin loop is unrolled by the ring length, so every ring index is a literal; the loads of origin o + 4 are issued
+// before the arithmetic of origin o.  Every running sum sees the origins in the same order as in msd_partial_kernel:
+// the same partials, bit for bit.
+__global__ void __launch_bounds__(kMsdThreads) msd_ring_kernel(const MsdParams p) {
+    __shared__ double red[kMsdThreads];
+    constexpr int R = kMsdLags;
+    const int t0 = blockIdx.x * R, tid = threadIdx.x;
+    const int nl = min(R, p.leff - t0);
+    const int fmax = p.f0 + p.ntimesteps - 1 + p.leff - 1;   // the last frame any lag of the block touches
+    for (int tile = blockIdx.y; tile < p.ntiles; tile += gridDim.y) {
+        const int slot = p.tile_start[tile] + tid;
+        const bool live = tid < p.tile_count[tile];
+        double acc[R];
+#pragma unroll
+        for (int l = 0; l < R; ++l) acc[l] = 0.0;
+        if (live) {
+            const size_t row = static_cast<size_t>(p.npad);
+            const double *base = p.pos + slot;
+            // frames past fmax are only ever asked for by the lags >= nl of the last chunk, whose sums are dropped
+            auto frame = [&](int f) { return base + static_cast<size_t>(min(f, fmax)) * 3 * row; };
+            double rx[R], ry[R], rz[R];
+#pragma unroll
+            for (int l = 0; l < R - 1; ++l) {
+                const double *q = frame(p.f0 + t0 + l);
+                rx[l] = q[0];
+                ry[l] = q[row];
+                rz[l] = q[2 * row];
+            }
+            // in flight: the origin frame and the entering later frame of the next D origins (an L2 round trip is
+            // longer than the arithmetic of one origin: 144 FP64 instructions)
+            constexpr int D = 4;
+            static_assert(R % D == 0, "the stage of an origin must be a literal");
+            double pxa[D], pya[D], pza[D], pxn[D], pyn[D], pzn[D];
+#pragma unroll
+            for (int d = 0; d < D; ++d) {
+                const double *qa = frame(p.f0 + d), *qn = frame(p.f0 + d + t0 + R - 1);
+                pxa[d] = qa[0];
+                pya[d] = qa[row];
+                pza[d] = qa[2 * row];
+                pxn[d] = qn[0];
+                pyn[d] = qn[row];
+                pzn[d] = qn[2 * row];
+            }
+            for (int im0 = 0; im0 < p.ntimesteps; im0 += R) {
+#pragma unroll
+                for (int u = 0; u < R; ++u) {
+                    const int im = im0 + u;
+                    if (im < p.ntimesteps) {
+                        rx[(u + R - 1) % R] = pxn[u % D];
+                        ry[(u + R - 1) % R] = pyn[u % D];
+                        rz[(u + R - 1) % R] = pzn[u % D];
+                        const double x0 = pxa[u % D], y0 = pya[u % D], z0 = pza[u % D];
+                        // the loads of origin im + D (clamped: past the last origin they are not used).  (An additional
+                        // prefetch.global.L2 of the frames 32 origins ahead made it slower: 15.8 against 13.1 ms, r2o.)
+                        const double *qa1 = frame(p.f0 + im + D), *qn1 = frame(p.f0 + im + D + t0 + R - 1);
+                        pxa[u % D] = qa1[0];
+                        pya[u % D] = qa1[row];
+                        pza[u % D] = qa1[2 * row];
+                        pxn[u % D] = qn1[0];
+                        pyn[u % D] = qn1[row];
+                        pzn[u % D] = qn1[2 * row];
+#pragma unroll
+                        for (int l = 0; l < R; ++l) {
+                            const int sl = (u + l) % R;
+                            const double dx = __dsub_rn(x0, rx[sl]);
+                            const double dy = __dsub_rn(y0, ry[sl]);
+                            const double dz = __dsub_rn(z0, rz[sl]);
+                            acc[l] = __dadd_rn(acc[l], __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)));
+                        }
+                    }
+                }
+            }
+        }
+#pragma unroll 1
+        for (int l = 0; l < nl; ++l) {
+            double v = 0.0;
+#pragma unroll
+            for (int q = 0; q < R; ++q)
+                if (q == l) v = acc[q];   // (static indexing keeps acc in registers)
+            red[tid] = v;
+            __syncthreads();
+            for (int s = kMsdThreads / 2; s > 0; s >>= 1) {
+                if (tid < s) red[tid] = __dadd_rn(red[tid], red[tid + s]);
+                __syncthreads();
+            }
+            if (tid == 0) p.partial[static_cast<size_t>(t0 + l) * p.ntiles + tile] = red[0];
+            __syncthreads();
+        }
+    }
+}
+
 __global__ void msd_finish_kernel(const MsdParams p) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= p.leff * p.ntypes) return;
@@ -2216,7 +2313,11 @@ cudaError_t launch_msd(const MsdParams &p, cudaStream_t stream) {
     if (p.leff <= 0 || p.ntypes <= 0) return cudaSuccess;
     if (p.ntiles > 0) {
         dim3 grid((p.leff + kMsdLags - 1) / kMsdLags, p.ntiles < 65535 ? p.ntiles : 65535);
-        msd_partial_kernel<<<grid, kMsdThreads, 0, stream>>>(p);
+        static const bool ring_ok = !(getenv("AGOFRT_MSD_RING") && atoi(getenv("AGOFRT_MSD_RING")) == 0);
+        if (p.skip == 1 && !p.cm_self && ring_ok)
+            msd_ring_kernel<<<grid, kMsdThreads, 0, stream>>>(p);
+        else
+            msd_partial_kernel<<<grid, kMsdThreads, 0, stream>>>(p);
     }
     const int n = p.leff * p.ntypes;
     msd_finish_kernel<<<(n + 127) / 128, 128, 0, stream>>>(p);

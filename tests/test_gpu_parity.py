@@ -486,6 +486,28 @@ def test_msd_vs_oracle(ctx, cm_msd, cm_self, lmax, skip):
     tr.close()
 
 
+@pytest.mark.parametrize("cm_msd,nts,lmax,primo", [(False, 37, 21, 2), (True, 16, 16, 0), (False, 5, 33, 1), (True, 40, 0, 0)])
+def test_msd_register_ring_vs_oracle(ctx, cm_msd, nts, lmax, primo):
+    """MSD with every frame an origin (skip = 1, no centre of mass subtracted): the kernel that keeps the later frames
+    of an atom in a register ring.  Origin counts that are not multiples of the ring, a ragged last chunk of lags,
+    fewer origins than the ring is long."""
+    pos, box, types = synth.small_case(96, (7, 6, 5), 1.1, 2, True, 82)   # 210 atoms, 82 frames
+    pos = np.ascontiguousarray(pos)
+    bi = synth.lammps_rows_to_internal(box)
+    tr = cabi.DeviceTrajectory(ctx, pos.shape[1], 9, types, 2, pos.shape[0])
+    tr.upload(0, pos, bi)
+    cm = oracle.cm_positions(pos, types, 2)
+    tr.set_cm(0, cm)
+    v, st = tr.msd(primo, nts, lmax, 1, cm_msd, False)
+    ref = oracle.msd(pos, types, nts, lmax, primo=primo, skip=1, cm_msd=cm_msd, cm_self=False, ntypes=2, cm=cm)
+    assert v.shape == ref.shape
+    scale = np.maximum(np.abs(ref[:, 0]), 1e-300)
+    assert (np.abs(v[:, 0] - ref[:, 0]) <= 1e-12 * scale).all()
+    if cm_msd:
+        assert np.array_equal(v[:, 1], ref[:, 1])
+    tr.close()
+
+
 # ---- the small-system kernel (up to 512 device slots: one (lag, origin) job per group of ceil(slots/64) warps) -------
 def _small_system(seed, natoms, ntypes, triclinic, nframes, npt=False):
     """`natoms` atoms cut out of a jittered lattice (the box shrunk to match), random types of unequal share."""

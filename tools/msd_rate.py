@@ -16,6 +16,7 @@ try:
 except Exception:
     peak = None
 ctx = cabi.Context([0])
+fp64 = ctx.fp64_peak(0.5)   # DFMA/s measured here: 9 FP64 operations per displacement is the other bound
 # (label, workload, frames in the window, averaged steps, lags); "C4 full" is the north-star window: 2.3 GB, far larger than L2
 CASES = (("C2", "C2", 400, 300, 100), ("C4", "C4", 60, 40, 20), ("C4full", "C4", 957, 757, 200))
 only = sys.argv[1:]
@@ -35,8 +36,10 @@ for label, name, nframes, nts, lmax in CASES:
     print(json.dumps({"case": label, "natoms": w.natoms, "frames": nframes, "window_bytes": nframes * w.natoms * 24, "lags": lmax,
                       "origins": nts, "displacements": st["pair_evals_total"], "kernel_ms": st["kernel_ms"],
                       "algorithmic_gbs": gbs, "hbm_peak_gbs": peak}), file=sys.stderr)
-    print("%s: %d atoms, window %d frames (%.0f MB), %d lags x %d origins: %.3e displacements in %.2f ms = %.0f GB/s algorithmic%s; msd(lag %d) = %.4f"
+    print("%s: %d atoms, window %d frames (%.0f MB), %d lags x %d origins: %.3e displacements in %.2f ms = %.0f GB/s algorithmic%s, "
+          "%.1f %% of the FP64 rate (9 operations per displacement, %.3g DFMA/s); msd(lag %d) = %.17g"
           % (label, w.natoms, nframes, nframes * w.natoms * 24 / 1e6, lmax, nts, st["pair_evals_total"], st["kernel_ms"], gbs,
-             " = %.0f %% of the measured HBM peak %.0f GB/s" % (100 * gbs / peak, peak) if peak else "", lmax - 1, v[-1, 0, 0]))
+             " = %.0f %% of the measured HBM peak %.0f GB/s" % (100 * gbs / peak, peak) if peak else "",
+             100 * st["pair_evals_total"] * 9 / (st["kernel_ms"] * 1e-3) / fp64, fp64, lmax - 1, v[-1, 0, 0]))
     tr.close()
 ctx.close()
