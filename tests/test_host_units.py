@@ -64,3 +64,34 @@ def test_block_average_geometry_and_welford(units):
     assert np.allclose(mean, blocks.mean(axis=0), rtol=1e-14)
     assert np.allclose(var, blocks.var(axis=0, ddof=1) / 5, rtol=1e-12)
     assert units["ntypes"] == 2 and units["type_ids"] == [0, 0, 1]
+
+
+# ---- analisi_b200/analysis.py: the python-side helpers that need no extension -----------------------------------------
+def test_analysis_lag_split():
+    """Analysis.max_l of the reference (pyanalisi/analysis.py:77-89): half of the window by default, the rest are origins;
+    a window too short for one origin keeps one."""
+    from analisi_b200 import analysis as an
+    assert an.lag_split(0, 100) == (50, 50)
+    assert an.lag_split(10, 110, 30) == (30, 70)
+    assert an.lag_split(0, 10, 10) == (9, 1)
+    assert an.lag_split(0, 10, 25) == (9, 1)
+    assert an.lag_split(5, 6) == (0, 1)
+    assert an.max_l is an.lag_split
+    with pytest.raises(RuntimeError):
+        an.lag_split(7, 7)
+
+
+def test_analysis_shell_normalise_and_hist2gofr():
+    """g(r) = histogram / volume of the spherical shell of every bin (the only normalisation the reference applies on the
+    python side, pyanalisi/analysis.py:91-99)."""
+    import math
+    from analisi_b200 import analysis as an
+    rmin, dr, nbin = 0.5, 0.25, 6
+    h = np.arange(2 * 3 * nbin, dtype=np.float64).reshape(2, 3, nbin) + 1.0
+    g = an.shell_normalise(h, rmin, dr)
+    for k in range(nbin):
+        vol = 4.0 * math.pi / 3.0 * ((rmin + (k + 1) * dr) ** 3 - (rmin + k * dr) ** 3)
+        assert np.allclose(g[..., k], h[..., k] / vol, rtol=1e-14, atol=0)
+    assert np.array_equal(an.hist2gofr(nbin, dr, rmin, h), g)
+    with pytest.raises(ValueError):
+        an.hist2gofr(nbin + 1, dr, rmin, h)
