@@ -195,11 +195,11 @@ enum {
     AGOFRT_OPT_DENSE = 32,         /* force the kernel without the group filter (dense in-range workloads)      */
     AGOFRT_OPT_SPARSE = 64,        /* force the group-filtered kernel meant for sparse in-range workloads      */
     AGOFRT_OPT_NO_UBOX = 128,      /* never pass a constant box as kernel parameter (uniform operands)         */
-    AGOFRT_OPT_NO_SMALL = 256,     /* never take the small-system kernel (one job per group of warps) */
+    AGOFRT_OPT_NO_SMALL = 256,     /* never take the small-system kernel (job ranges per CTA, batches of jobs per warp) */
     AGOFRT_OPT_ON_DEVICE = 512,    /* leave the counts on the device for agofrt_blockavg_push: counts_out may be NULL
                                       and is not written */
-    AGOFRT_OPT_SMALL = 1024,       /* take the small-system kernel for up to 512 device slots (default: up to 256, one
-                                      to four warps per job, where it beats the tile kernel; measured equal above) */
+    AGOFRT_OPT_SMALL = 1024,       /* take the small-system kernel for up to 512 device slots (default: up to 256, where
+                                      it beats the tile kernel) */
     AGOFRT_OPT_SAFE2 = 2048,       /* dense windows: the two-floor form of the safe-zone binning (two round-down FFMAs give the
                                       histogram word and the near-an-edge flag); exact like the others, measured slower */
     AGOFRT_OPT_SKEW = 4096,        /* with AGOFRT_OPT_SAFE2: offset half of the warps by one binning run (A/B measurements) */
@@ -232,8 +232,10 @@ AGOFRT_API int agofrt_block(agofrt_plan *plan, size_t primo, unsigned ntimesteps
 /* Many small blocks at once (BlockAverageG on systems of a few dozen atoms, where one block is a millisecond of kernel
  * and sharding its work units over several GPUs buys nothing): block b = reset(ntimesteps); calculate(primo0 + b*stride),
  * WHOLE blocks dealt to the devices (a contiguous run of blocks per device -- the reference deals blocks to MPI ranks,
- * lib/include/blockaverage.h:146-186), no host synchronisation between blocks, then every device receives every block
- * (NCCL broadcasts).  The window must hold the frames of all the blocks; every block must have a regular job list (the
+ * lib/include/blockaverage.h:146-186; when the blocks do not divide among the devices a device also takes PART of the
+ * work units of a block), one host thread per local device issuing its blocks, no host synchronisation between blocks,
+ * then every device receives every block (one NCCL all-gather, or an all-reduce of the zero-filled batch when blocks
+ * were split).  The window must hold the frames of all the blocks; every block must have a regular job list (the
  * single-pass minimum image proven for its frame range, or AGOFRT_OPT_FORCE_GENERAL), else AGOFRT_ERR_ARG: run them one by
  * one.  The counts stay on the devices: agofrt_plan_block_counts reads one block back, agofrt_blockavg_push_blocks folds
  * them all, in block order, into a device-resident mean / variance; the last block is also what agofrt_plan_last_counts

@@ -25,8 +25,8 @@ def gpu_counts(ctx, pos, box_internal, ids, ntypes, rmin, rmax, nbin, tmax, nts,
     return out
 
 
-# systems of up to 256 device slots take the small-system kernel (one job per group of warps) unless told
-# otherwise (up to 512 with OPT_SMALL): the small fixtures run through both kernels
+# systems of up to 256 device slots take the small-system kernel unless told otherwise (up to 512 with OPT_SMALL):
+# the small fixtures run through both kernels
 BOTH_KERNELS = pytest.mark.parametrize("no_small", [0, cabi.OPT_NO_SMALL], ids=["small-kernel", "tile-kernel"])
 
 
@@ -508,7 +508,7 @@ def test_msd_register_ring_vs_oracle(ctx, cm_msd, nts, lmax, primo):
     tr.close()
 
 
-# ---- the small-system kernel (up to 512 device slots: one (lag, origin) job per group of ceil(slots/64) warps) -------
+# ---- the small-system kernel (up to 512 device slots) -------------------------------------------------------------
 def _small_system(seed, natoms, ntypes, triclinic, nframes, npt=False):
     """`natoms` atoms cut out of a jittered lattice (the box shrunk to match), random types of unequal share."""
     rng = np.random.default_rng([seed, natoms, ntypes])
@@ -523,14 +523,13 @@ def _small_system(seed, natoms, ntypes, triclinic, nframes, npt=False):
 
 
 @pytest.mark.parametrize("natoms,ntypes,triclinic", [
-    (5, 1, False), (33, 2, True), (56, 2, False), (64, 1, True),          # one warp per job
+    (5, 1, False), (33, 2, True), (56, 2, False), (64, 1, True),          # one round of 64 slots per job
     (65, 3, False), (97, 2, True), (128, 1, False), (110, 3, True),       # two
     (150, 2, False), (256, 1, True), (300, 2, True), (380, 3, False),     # three, four, five, six
     (440, 1, False), (490, 2, True), (512, 1, False)])                    # seven, eight
 def test_small_system_kernel(ctx, natoms, ntypes, triclinic):
-    """One job per group of W = ceil(slots / 64) warps, runs of one lag per CTA: same counts as the oracle and as
-    the tile kernel, for every W, ghost slots in every type group, several units per lag and ragged lag / origin
-    loops."""
+    """The small-system kernel (contiguous job ranges per CTA, jobs split over the warps) on 5 .. 512 atoms: same counts
+    as the oracle and as the tile kernel, ghost slots in every type group, ragged lag / origin loops."""
     nframes = 40
     pos, bi, types = _small_system(400 + natoms, natoms, ntypes, triclinic, nframes)
     ctx.pbc_wrap(pos, bi)
