@@ -362,7 +362,7 @@ def measure_traffic(args, name):
     if args.full:
         cmd.append("--full")
     try:
-        r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=900)
+        r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=300)
         if r.returncode != 0:
             return None, "ncu run failed (rc %d): %s" % (r.returncode, (r.stderr or r.stdout)[-200:].replace("\n", " "))
         import csv
