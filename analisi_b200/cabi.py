@@ -25,7 +25,7 @@ UP_WRAP, UP_WRITEBACK, UP_SHARED = 1, 2, 4
 SYMBOLS = [
     "agofrt_version", "agofrt_last_error", "agofrt_device_count", "agofrt_host_alloc", "agofrt_host_free",
     "agofrt_ctx_create", "agofrt_ctx_destroy", "agofrt_ctx_ndev", "agofrt_comm_unique_id", "agofrt_comm_join",
-    "agofrt_ctx_set_shard", "agofrt_shard_range", "agofrt_traj_create", "agofrt_traj_destroy", "agofrt_traj_upload", "agofrt_traj_upload_wrap", "agofrt_plan_retarget",
+    "agofrt_ctx_set_shard", "agofrt_shard_range", "agofrt_block_share", "agofrt_traj_create", "agofrt_traj_destroy", "agofrt_traj_upload", "agofrt_traj_upload_wrap", "agofrt_plan_retarget",
     "agofrt_traj_download_frame", "agofrt_pbc_wrap", "agofrt_traj_d2_all", "agofrt_traj_d2_pair", "agofrt_plan_create",
     "agofrt_plan_destroy", "agofrt_plan_thresholds", "agofrt_block", "agofrt_neighbour_hist", "agofrt_traj_set_cm", "agofrt_msd", "agofrt_fp64_peak",
     "agofrt_blockavg_create", "agofrt_blockavg_destroy", "agofrt_blockavg_begin", "agofrt_blockavg_push", "agofrt_blockavg_end",
@@ -87,6 +87,7 @@ def lib():
     L.agofrt_comm_join.argtypes = [vp, C.c_char_p, C.c_int, C.c_int]
     L.agofrt_ctx_set_shard.argtypes = [vp, C.c_int, C.c_int]
     L.agofrt_shard_range.argtypes = [C.c_uint64, C.c_int, C.c_int, u64p, u64p]
+    L.agofrt_block_share.argtypes = [C.c_uint, C.c_int, C.c_int, C.c_uint, C.POINTER(C.c_uint), C.POINTER(C.c_uint)]
     L.agofrt_traj_create.argtypes = [C.POINTER(vp), vp, C.c_size_t, C.c_int, ip, C.c_int, C.c_size_t]
     L.agofrt_traj_destroy.argtypes = [vp]
     L.agofrt_traj_upload.argtypes = [vp, C.c_size_t, C.c_size_t, vp, vp]
@@ -146,6 +147,13 @@ def shard_range(units, rank, world):
     b, e = C.c_uint64(0), C.c_uint64(0)
     _check(lib().agofrt_shard_range(int(units), int(rank), int(world), C.byref(b), C.byref(e)))
     return int(b.value), int(e.value)
+
+
+def block_share(nblocks, rank, world, block):
+    """(part_a, part_b): rank `rank` of `world` takes the work units [part_a, part_b) / world of `block` (agofrt_blocks)."""
+    a, b = C.c_uint(0), C.c_uint(0)
+    _check(lib().agofrt_block_share(int(nblocks), int(rank), int(world), int(block), C.byref(a), C.byref(b)))
+    return int(a.value), int(b.value)
 
 
 def _dp(a):

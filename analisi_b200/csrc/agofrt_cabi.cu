@@ -647,6 +647,20 @@ extern "C" int agofrt_shard_range(uint64_t units, int rank, int world, uint64_t 
     return on_exception();
 }
 
+extern "C" int agofrt_block_share(unsigned nblocks, int rank, int world, unsigned block, unsigned *part_a, unsigned *part_b) try {
+    if (!part_a || !part_b) return fail(AGOFRT_ERR_ARG, "NULL argument");
+    if (world <= 0 || rank < 0 || rank >= world || block >= nblocks) return fail(AGOFRT_ERR_ARG, "bad rank / world / block");
+    // in units of 1/world block: the rank owns [rank * nblocks, (rank + 1) * nblocks), the block is [block * world, (block + 1) * world)
+    const uint64_t W = static_cast<uint64_t>(world), own_a = static_cast<uint64_t>(rank) * nblocks,
+                   own_b = (static_cast<uint64_t>(rank) + 1) * nblocks, blk_a = static_cast<uint64_t>(block) * W, blk_b = blk_a + W;
+    const uint64_t a = std::max(own_a, blk_a), b = std::min(own_b, blk_b);
+    *part_a = b > a ? static_cast<unsigned>(a - blk_a) : 0u;
+    *part_b = b > a ? static_cast<unsigned>(b - blk_a) : 0u;
+    return AGOFRT_OK;
+} catch (...) {
+    return on_exception();
+}
+
 // a multi-device context without a joined communicator is its own communicator
 static int ensure_local_comm(agofrt_ctx *ctx) {
     if (ctx->comm_ready || ctx->shard_only || ctx->devs.size() <= 1) return AGOFRT_OK;
@@ -2351,21 +2365,22 @@ extern "C" int agofrt_blocks(agofrt_plan *p, size_t primo0, size_t stride, unsig
     auto enqueue_device = [&](int i) -> int {
         agofrt_stats &sm = sums[i];
         memset(&sm, 0, sizeof(sm));
-        const uint64_t r = static_cast<uint64_t>(first_rank + i), W = static_cast<uint64_t>(world);
-        // in units of 1/W block: this device owns [r * nblocks, (r + 1) * nblocks)
-        const uint64_t own_a = r * nblocks, own_b = (r + 1) * nblocks;
-        const uint64_t b0 = own_a / W, b1 = (own_b + W - 1) / W;
         if (!whole) {
             CU(cudaSetDevice(ctx->devs[i].id));
             CU(cudaMemsetAsync(p->dev[i].batch, 0, static_cast<size_t>(nblocks) * len * sizeof(unsigned long long), ctx->devs[i].stream));
         }
-        for (uint64_t b = b0; b < b1 && b < nblocks; ++b) {
-            BlockTarget tg{i, p->dev[i].batch + static_cast<size_t>(b) * len, b == b0};
+        bool first = true;
+        for (unsigned b = 0; b < nblocks; ++b) {
+            unsigned part_a = 0, part_b = 0;
+            const int rcs_share = agofrt_block_share(nblocks, first_rank + i, world, b, &part_a, &part_b);
+            if (rcs_share != AGOFRT_OK) return rcs_share;
+            if (part_b <= part_a) continue;
+            BlockTarget tg{i, p->dev[i].batch + static_cast<size_t>(b) * len, first};
+            first = false;
             if (!whole) {
-                tg.part_a = static_cast<uint32_t>(std::max(own_a, b * W) - b * W);
-                tg.part_b = static_cast<uint32_t>(std::min(own_b, (b + 1) * W) - b * W);
-                tg.part_den = static_cast<uint32_t>(W);
-                if (tg.part_b <= tg.part_a) continue;
+                tg.part_a = part_a;
+                tg.part_b = part_b;
+                tg.part_den = static_cast<uint32_t>(world);
             }
             agofrt_stats st;
             memset(&st, 0, sizeof(st));

@@ -98,6 +98,11 @@ AGOFRT_API int agofrt_ctx_set_shard(agofrt_ctx *ctx, int first_rank, int world);
 /* The contiguous share [begin,end) of `units` equal work units that device `rank` of `world`
  * computes (pure host arithmetic; agofrt_block uses exactly this). */
 AGOFRT_API int agofrt_shard_range(uint64_t units, int rank, int world, uint64_t *begin, uint64_t *end);
+/* The geometry of agofrt_blocks: what rank `rank` of `world` takes of block `block` of `nblocks`, as the part
+ * [*part_a, *part_b) / world of the block's work units (0, 0: nothing; 0, world: the whole block).  Rank r owns the
+ * stretch [r, r + 1) * nblocks / world of the batch: whole blocks when nblocks is a multiple of world (the reference's
+ * dealing of blocks to MPI ranks, lib/include/blockaverage.h:146-186), whole blocks and parts of blocks otherwise. */
+AGOFRT_API int agofrt_block_share(unsigned nblocks, int rank, int world, unsigned block, unsigned *part_a, unsigned *part_b);
 
 /* ---- trajectory window --------------------------------------------------------------------- */
 /* type_id[natoms] are dense ids in [0,ntypes) (BaseTrajectory::get_type).  box_stride is 6

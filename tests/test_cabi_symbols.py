@@ -42,6 +42,37 @@ def test_shard_range_partitions():
         cabi.shard_range(10, 2, 2)
 
 
+def test_block_share_deals_every_block_exactly_once():
+    """The geometry of agofrt_blocks (no compute): over the ranks, the parts of every block tile [0, world) once and in rank
+    order; every rank gets nblocks / world blocks' worth; whole blocks when the blocks divide among the ranks (the
+    reference's dealing of blocks to MPI ranks, lib/include/blockaverage.h:146-186), contiguous runs always."""
+    for nblocks in (1, 2, 3, 7, 8, 20, 33):
+        for world in (1, 2, 3, 4, 8):
+            per_rank = [0] * world
+            for b in range(nblocks):
+                edge = 0
+                for r in range(world):
+                    a, e = cabi.block_share(nblocks, r, world, b)
+                    if e > a:
+                        assert a == edge, (nblocks, world, b, r)
+                        edge = e
+                        per_rank[r] += e - a
+                    else:
+                        assert (a, e) == (0, 0)
+                assert edge == world, (nblocks, world, b)
+            assert per_rank == [nblocks] * world      # in units of 1/world block
+            for r in range(world):
+                mine = [b for b in range(nblocks) if cabi.block_share(nblocks, r, world, b)[1] > 0]
+                assert mine == list(range(mine[0], mine[-1] + 1)) if mine else True
+                if nblocks % world == 0:
+                    assert all(cabi.block_share(nblocks, r, world, b) == (0, world) for b in mine)
+                    assert mine == list(range(r * nblocks // world, (r + 1) * nblocks // world))
+    assert cabi.block_share(20, 0, 8, 2) == (0, 4) and cabi.block_share(20, 1, 8, 2) == (4, 8)   # 2.5 blocks each
+    for bad in ((4, 2, 2, 0), (4, -1, 2, 0), (4, 0, 0, 0), (4, 0, 2, 4)):
+        with pytest.raises(cabi.AgofrtError):
+            cabi.block_share(*bad)
+
+
 def test_no_gpu_is_a_loud_error():
     if cabi.device_count() > 0:
         pytest.skip("a GPU is present")
