@@ -813,6 +813,34 @@ def test_c4_subset_against_the_reference_itself(ctx):
     assert int(c.sum()) == meta["counts_sum"]
 
 
+@pytest.mark.parametrize("name", ["C2", "C3"])
+@pytest.mark.parametrize("options", [0, cabi.OPT_FORCE_GENERAL, cabi.OPT_NO_SAFE], ids=["default", "general", "thresholds"])
+def test_full_n_against_the_reference_itself(ctx, name, options):
+    """BASELINE.json configs[1] (C2: 4096 atoms, cubic, dense) and configs[2] (C3: 12 288 atoms, 3 types, triclinic) at
+    their full atom counts, on the atoms / cell / bins bench.py uses for them, a few (lag, origin) jobs: the tile kernel
+    against the counts of the UNMODIFIED reference (tests/golden/make_full_n_golden.py), wrap on the device."""
+    import hashlib
+    import json
+    import os
+    from conftest import GOLDEN
+    meta = json.load(open(os.path.join(GOLDEN, "full_n_counts.json")))[name]
+    gold = np.load(os.path.join(GOLDEN, "full_n_counts.npz"))[name + "/counts"]
+    w = synth.WORKLOADS[name]
+    pos, box, types = synth.generate(w, nframes=meta["frames"])
+    assert hashlib.sha256(np.ascontiguousarray(pos).tobytes()).hexdigest() == meta["pos_in_sha256"]
+    bi = synth.lammps_rows_to_internal(box)
+    tr = cabi.DeviceTrajectory(ctx, w.natoms, bi.shape[1], types, w.ntypes, meta["frames"])
+    tr.upload_ex(0, pos, bi, wrap=True)
+    plan = cabi.Plan(tr, w.rmin, w.rmax, w.nbin)
+    leff = cabi.gofrt_leff(meta["ntimesteps"], meta["tmax"])
+    c, st = plan.block(meta["primo"], meta["ntimesteps"], leff, meta["skip"], meta["every"], options=options)
+    plan.close()
+    tr.close()
+    assert not ran_small(st)
+    assert np.array_equal(c, gold)
+    assert int(c.sum()) == meta["counts_sum"]
+
+
 # ---- the other pair loops over d2_minImage: neighbour lists and spherical-harmonic densities --------------------------
 @pytest.mark.parametrize("name", sorted(PAIR_LOOP_CASES))
 def test_neighbour_lists_vs_the_reference(ctx, name):

@@ -246,3 +246,28 @@ def test_c4_subset_golden_is_self_consistent():
     assert int(full.sum()) == meta["counts_sum"]
     assert int(full[0, 1, 0]) == 100000 * 8 and int(full[0, 1, 1:].sum()) == 0
     assert list(z["lags"]) == list(range(0, 201, 8))
+
+
+@pytest.mark.parametrize("name", ["C2", "C3"])
+def test_full_n_golden_oracle_equals_the_reference(name):
+    """tests/golden/full_n_counts.*: BASELINE.json configs[1] and configs[2] at their FULL atom counts (4096 cubic, 12 288
+    triclinic with 3 types) on a few (lag, origin) jobs, counts of the unmodified reference
+    (tests/golden/make_full_n_golden.py).  The oracle reproduces them; the GPU test of the same name compares the tile
+    kernel with them."""
+    import hashlib
+    import json
+    from analisi_b200 import synth
+    from conftest import GOLDEN
+    meta = json.load(open(os.path.join(GOLDEN, "full_n_counts.json")))[name]
+    gold = np.load(os.path.join(GOLDEN, "full_n_counts.npz"))[name + "/counts"]
+    w = synth.WORKLOADS[name]
+    assert meta["workload"] == w.name
+    pos, box, types = synth.generate(w, nframes=meta["frames"])
+    assert hashlib.sha256(np.ascontiguousarray(pos).tobytes()).hexdigest() == meta["pos_in_sha256"], \
+        "synth.generate no longer reproduces the fixture's input: regenerate it"
+    bi = synth.lammps_rows_to_internal(box)
+    pos = oracle.pbc_wrap(pos, bi)
+    c = oracle.counts(pos, bi, types, w.rmin, w.rmax, w.nbin, meta["tmax"], meta["ntimesteps"], primo=meta["primo"],
+                      skip=meta["skip"], every=meta["every"], ntypes=w.ntypes)
+    assert np.array_equal(c, gold)
+    assert hashlib.sha256(np.ascontiguousarray(gold).astype("<u8").tobytes()).hexdigest() == meta["counts_sha256"]
